@@ -1,0 +1,142 @@
+"""ctypes binding of libpomdp_b200.so (the C ABI declared in include/pomdp_b200.h).
+
+The product has exactly one backend: the CUDA library built in-tree by
+``gym_pomdp_b200.build`` (``python -m gym_pomdp_b200.build``).  If it is missing, loading
+fails loudly -- there is no CPU fallback and nothing here imports oracle/.
+
+``_inject_for_tests`` exists for the CPU-only test-suite: it swaps in
+tests/hostsim/libpomdp_hostsim.so (the same per-env functors compiled with g++, same
+symbols, host pointers) so the Python host logic can be exercised without a GPU.  It is
+never called from product code.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpomdp_b200.so")
+
+FLAG_DONE = 1
+FLAG_BAD_ACTION = 2
+FLAG_STEPPED_DONE = 4
+FLAG_BAD_STATE = 8
+FLAG_ERRORS = FLAG_BAD_ACTION | FLAG_STEPPED_DONE | FLAG_BAD_STATE
+
+KIND_ROCK, KIND_TAG, KIND_BATTLESHIP, KIND_TIGER, KIND_NETWORK = range(5)
+
+COORD_GET_INDEX, COORD_GET_COORD, COORD_IS_INSIDE, COORD_ADD_MOVE, COORD_L1, \
+    COORD_TAG_GET_INDEX, COORD_TAG_GET_COORD, COORD_TAG_IS_INSIDE = range(8)
+
+
+class RockParams(ctypes.Structure):
+    _fields_ = [("board_size", c_int32), ("num_rocks", c_int32), ("stochastic", c_int32),
+                ("reserved", c_int32), ("p_move", c_double)]
+
+
+class TagParams(ctypes.Structure):
+    _fields_ = [("num_opponents", c_int32), ("reserved", c_int32), ("move_prob", c_double)]
+
+
+class BattleshipParams(ctypes.Structure):
+    _fields_ = [("x_size", c_int32), ("y_size", c_int32), ("max_len", c_int32), ("reserved", c_int32)]
+
+
+class TigerParams(ctypes.Structure):
+    _fields_ = [("listen_prob", c_double)]
+
+
+class NetworkParams(ctypes.Structure):
+    _fields_ = [("n_machines", c_int32), ("problem_type", c_int32), ("p", c_double), ("q", c_double),
+                ("p_ob", c_double)]
+
+
+_P = c_void_p  # device (or, under hostsim, host) array pointers travel as raw addresses
+_STEP_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
+_RESET_TAIL = [_P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
+
+_PROTOTYPES = {
+    "pomdp_abi_version": (c_int32, []),
+    "pomdp_last_error": (c_char_p, []),
+    "pomdp_rock_state_words": (c_int32, [POINTER(RockParams)]),
+    "pomdp_rock_table_bytes": (c_int64, []),
+    "pomdp_rock_build_table": (c_int32, [POINTER(RockParams), c_void_p]),
+    "pomdp_rock_step": (c_int32, [POINTER(RockParams), _P] + _STEP_TAIL),
+    "pomdp_rock_reset": (c_int32, [POINTER(RockParams), _P] + _RESET_TAIL),
+    "pomdp_tag_step": (c_int32, [POINTER(TagParams)] + _STEP_TAIL),
+    "pomdp_tag_reset": (c_int32, [POINTER(TagParams)] + _RESET_TAIL),
+    "pomdp_battleship_step": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_battleship_reset": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64, c_uint64,
+                                         c_uint32, c_void_p]),
+    "pomdp_battleship_reset_rejection": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64,
+                                                   c_uint64, c_uint32, c_void_p]),
+    "pomdp_tiger_step": (c_int32, [POINTER(TigerParams)] + _STEP_TAIL),
+    "pomdp_tiger_reset": (c_int32, [POINTER(TigerParams)] + _RESET_TAIL),
+    "pomdp_network_step": (c_int32, [POINTER(NetworkParams)] + _STEP_TAIL),
+    "pomdp_network_reset": (c_int32, [POINTER(NetworkParams), _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
+    "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+_is_hostsim = False
+
+
+def _bind(path):
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError = a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def lib():
+    """The loaded CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m gym_pomdp_b200.build` "
+                "(nvcc, sm_100a).  gym_pomdp_b200 has no CPU fallback.")
+        _lib = _bind(LIB_PATH)
+        got = _lib.pomdp_abi_version()
+        if got != 1:
+            raise RuntimeError(f"libpomdp_b200.so ABI version {got}, expected 1")
+    return _lib
+
+
+def is_hostsim():
+    return _is_hostsim
+
+
+def _inject_for_tests(path):
+    """TESTS ONLY: bind the g++-compiled host simulation of the kernels instead."""
+    global _lib, _is_hostsim
+    if path is None:
+        _lib, _is_hostsim = None, False
+        return
+    cand = _bind(path)
+    assert hasattr(cand, "pomdp_is_hostsim"), "refusing to inject a library that is not the hostsim"
+    _lib, _is_hostsim = cand, True
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pomdp_last_error()
+        raise RuntimeError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Raw address of a torch tensor's first element (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(device):
+    """cudaStream_t of torch's current stream on `device` (0 for host tensors under hostsim)."""
+    import torch
+    if device.type != "cuda":
+        return None
+    return torch.cuda.current_stream(device).cuda_stream

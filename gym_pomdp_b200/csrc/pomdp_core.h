@@ -1,0 +1,539 @@
+// pomdp_core.h -- per-env-instance transition functions over PACKED int32 state words.
+//
+// Everything here is a register-level `__host__ __device__` inline function: the CUDA
+// kernels in pomdp_kernels.cu wrap them with the memory movement (vectorised global
+// loads/stores, TMA staging of the static maps), and tests/hostsim/ compiles the very same
+// functions with g++ so that the kernel LOGIC can be checked against oracle/ in a
+// container without a GPU.  The host build is a test vehicle only -- the shipped library
+// has no CPU path.
+//
+// Semantics follow d3sm0/gym_pomdp (paths below are under gym_pomdp/envs/ of the
+// reference); layouts and the draw-slot contract are documented in include/pomdp_b200.h
+// and DESIGN.md.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define POMDP_HD __host__ __device__ __forceinline__
+#define POMDP_UNROLL _Pragma("unroll")
+#else
+#define POMDP_HD inline
+#define POMDP_UNROLL
+#endif
+
+namespace pomdp {
+
+typedef unsigned __int128 u128;
+
+enum : int32_t { FLAG_DONE = 1, FLAG_BAD_ACTION = 2, FLAG_STEPPED_DONE = 4, FLAG_BAD_STATE = 8 };
+enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1 };
+
+// ------------------------------------------------------------------ Philox4x32-10 ----
+struct U4 { uint32_t x, y, z, w; };
+
+POMDP_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+POMDP_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+    POMDP_UNROLL
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        U4 nx;
+        nx.x = hi1 ^ c.y ^ k0;
+        nx.y = lo1;
+        nx.z = hi0 ^ c.w ^ k1;
+        nx.w = lo0;
+        c = nx;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Draw-slot contract (include/pomdp_b200.h): block b holds slots 4b..4b+3 of (env, step).
+POMDP_HD U4 draw_block(uint64_t seed, uint64_t env, uint32_t step, uint32_t domain, uint32_t block) {
+    U4 c;
+    c.x = (uint32_t)env;
+    c.y = (uint32_t)(env >> 32);
+    c.z = step;
+    c.w = (domain << 24) | block;
+    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+POMDP_HD uint32_t word_of(const U4& r, int j) { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; }
+// np.random.randint(n) / choice index under the coupling rule: floor(u * n), u = r / 2^32.
+POMDP_HD uint32_t rand_below(uint32_t r, uint32_t n) { return mulhi32(r, n); }
+// np.random.binomial(1, p) with T = ceil(p * 2^32)  (0 <= T <= 2^32, hence 64-bit).
+POMDP_HD bool bern(uint32_t r, uint64_t T) { return (uint64_t)r < T; }
+
+// ------------------------------------------------------------------ geometry --------
+// Moves, coord.py:101-106: 0 N(0,+1) 1 E(+1,0) 2 S(0,-1) 3 W(-1,0) 4 NULL(0,0).
+POMDP_HD int move_dx(int m) { return (m == 1) - (m == 3); }
+POMDP_HD int move_dy(int m) { return (m == 0) - (m == 2); }
+// Grid, coord.py:58-66
+POMDP_HD int grid_get_index(int x_size, int x, int y) { return x_size * y + x; }
+POMDP_HD bool grid_is_inside(int x_size, int y_size, int x, int y) {
+    return x >= 0 && y >= 0 && x < x_size && y < y_size;
+}
+POMDP_HD int iabs(int v) { return v < 0 ? -v : v; }
+// Grid.euclidean_distance is np.linalg.norm(., 1): the L1 norm (coord.py:79-81).
+POMDP_HD int l1_distance(int x0, int y0, int x1, int y1) { return iabs(x0 - x1) + iabs(y0 - y1); }
+
+// TagGrid, tag.py:46-66.  29 cells: two rows of 10, then a 3x3 block at x in 5..7, y in 2..4.
+POMDP_HD bool tag_is_inside(int x, int y) {
+    return y >= 2 ? (x >= 5 && x < 8 && y < 5) : (x >= 0 && x < 10 && y >= 0);
+}
+POMDP_HD void tag_get_coord(uint32_t idx, int& x, int& y) {
+    if (idx < 20) {
+        y = idx >= 10;
+        x = (int)idx - 10 * y;
+    } else {
+        const uint32_t j = idx - 20;
+        const int q = (int)((j * 11u) >> 5);  // j / 3 for j < 9
+        x = (int)j - 3 * q + 5;
+        y = q + 2;
+    }
+}
+POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y - 2) * 3 + x - 5; }
+
+// ====================================================================== RockSample ===
+// Static maps of one Rock configuration; 400 bytes, staged into shared memory per block.
+struct RockTable {
+    int8_t grid[256];      // [x | y << 4] -> rock id written by rock.py:110-111, -1 = none
+    uint8_t rock_pos[16];  // rock i -> x | y << 4   (rock.py:106)
+    uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2 (rock.py:383-387)
+};
+static_assert(sizeof(RockTable) == 400 && sizeof(RockTable) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+
+struct RockDev {  // passed by value to the kernels
+    int32_t n, k;
+    int32_t stochastic;
+    int32_t penal;        // rock.py:117 (-100) / rock.py:432 (0)
+    uint32_t start;       // x | y << 4 of config init_pos
+    uint32_t pad;
+    uint64_t move_T;      // ceil(p_move * 2^32)
+};
+
+template <typename S> struct RockBits;
+template <> struct RockBits<uint32_t> { static constexpr uint32_t DONE = 0x80000000u; };
+template <> struct RockBits<uint64_t> { static constexpr uint64_t DONE = 0x8000000000000000ull; };
+
+// rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step).
+template <typename S>
+POMDP_HD void rock_step(const RockDev& p, const RockTable* __restrict__ t, S s, int32_t a,
+                        uint64_t seed, uint64_t env, uint32_t step,
+                        S& s2, int32_t& ob, float& rw, int32_t& fl) {
+    s2 = s; ob = 0; rw = 0.f; fl = 0;
+    if (s & RockBits<S>::DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }   // rock.py:126
+    if ((uint32_t)a >= (uint32_t)(5 + p.k)) { fl = FLAG_BAD_ACTION; return; }     // rock.py:125
+    const int x = (int)(s & 15), y = (int)((s >> 4) & 15);
+    U4 r = {0, 0, 0, 0};
+    if (p.stochastic || a > 4) r = draw_block(seed, env, step, DOMAIN_STEP, 0);
+    if (p.stochastic && !bern(r.x, p.move_T)) return;                             // rock.py:443
+    int reward = 0;
+    bool done = false;
+    if (a < 4) {                                                                  // rock.py:134-158
+        const int nx = x + move_dx(a), ny = y + move_dy(a);
+        if ((unsigned)nx < (unsigned)p.n && (unsigned)ny < (unsigned)p.n) {
+            s2 = (s & ~(S)0xFF) | (S)(nx | (ny << 4));
+        } else if (a == 1) {                                                      // east exit, 139-141
+            reward = 10;
+            done = true;
+        } else {
+            reward = p.penal;
+        }
+    } else if (a == 4) {                                                          // rock.py:160-169
+        int rock = t->grid[(uint32_t)s & 0xFF];
+        if (rock >= p.k) { fl |= FLAG_BAD_STATE; rock = -1; }   // reference: IndexError at rock.py:162
+        const int sh = 8 + 2 * (rock < 0 ? 0 : rock);
+        const uint32_t code = rock >= 0 ? (uint32_t)(s >> sh) & 3u : 0u;
+        if (code != 0) {
+            reward = code == 1 ? 10 : -10;
+            s2 = s & ~((S)3 << sh);
+        } else {
+            reward = p.penal;
+        }
+    } else {                                                                      // rock.py:171-175, 401-407
+        const int rock = a - 5;
+        const uint32_t rp = t->rock_pos[rock];
+        const int d = l1_distance(x, y, (int)(rp & 15), (int)(rp >> 4));
+        const bool truthful = r.y <= t->thr_m1[d];
+        const bool good = ((uint32_t)(s >> (8 + 2 * rock)) & 3u) == 1u;
+        ob = (good == truthful) ? 2 : 1;
+    }
+    if (!p.stochastic) done = done || (reward == p.penal);                        // rock.py:193 vs 503
+    if (done) { s2 |= RockBits<S>::DONE; fl |= FLAG_DONE; }
+    rw = (float)reward;
+}
+
+// rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)); slot i = rock i.
+template <typename S>
+POMDP_HD S rock_reset(const RockDev& p, uint64_t seed, uint64_t env, uint32_t step) {
+    S s = (S)p.start;
+    for (int b = 0; 4 * b < p.k; ++b) {
+        const U4 r = draw_block(seed, env, step, DOMAIN_RESET, (uint32_t)b);
+        POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * b + j;
+            const uint32_t w = word_of(r, j);
+            const uint32_t code = w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u);
+            if (i < p.k) s |= (S)code << (8 + 2 * i);
+        }
+    }
+    return s;
+}
+
+// ============================================================================= Tag ===
+struct TagDev {
+    int32_t n_opp;
+    int32_t pad;
+    uint64_t move_T;  // ceil(move_prob * 2^32)
+};
+constexpr uint32_t TAG_DONE = 0x80000000u;
+constexpr int TAG_CELLS = 29;
+
+POMDP_HD int tag_num_opp(uint32_t s) { return ((int32_t)(s << 1)) >> 26; }  // bits 25-30, sign-extended
+POMDP_HD uint32_t tag_set_num_opp(uint32_t s, int v) { return (s & ~(63u << 25)) | (((uint32_t)v & 63u) << 25); }
+
+// tag.py:260-280: the multiset of Moves the opponent draws from, as 2-bit codes packed
+// little-end first; returns its length (2 or 4 for distinct cells).
+POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
+    int cnt = 0;
+    list = 0;
+#define POMDP_TAG_APPEND(cond, m) do { if (cond) { list |= (uint32_t)(m) << (2 * cnt); ++cnt; } } while (0)
+    POMDP_TAG_APPEND(ox >= ax, 1);
+    POMDP_TAG_APPEND(oy >= ay, 0);
+    POMDP_TAG_APPEND(ox <= ax, 3);
+    POMDP_TAG_APPEND(oy <= ay, 2);
+    POMDP_TAG_APPEND(ox == ax && oy > ay, 0);
+    POMDP_TAG_APPEND(oy == ay && ox > ax, 1);
+    POMDP_TAG_APPEND(ox == ax && oy < ay, 2);
+    POMDP_TAG_APPEND(oy == ay && ox < ax, 3);
+#undef POMDP_TAG_APPEND
+    return cnt;
+}
+
+// tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).
+POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
+                       uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    s2 = s; ob = 0; rw = 0.f; fl = 0;
+    if (s & TAG_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }             // tag.py:110
+    if ((uint32_t)a >= 5u) { fl = FLAG_BAD_ACTION; return; }                      // tag.py:109
+    uint32_t agent = s & 31u;
+    bool bad = agent >= (uint32_t)TAG_CELLS;
+    for (int j = 0; j < p.n_opp; ++j) bad = bad || ((s >> (5 + 5 * j)) & 31u) >= (uint32_t)TAG_CELLS;
+    if (bad) { fl = FLAG_BAD_STATE; return; }                                     // tag.py:116-117
+    int ax, ay;
+    tag_get_coord(agent, ax, ay);
+    int nopp = tag_num_opp(s);
+    float reward;
+    if (a == 4) {                                                                 // tag.py:119-131
+        bool tagged = false;
+        reward = 0.f;
+        U4 r0 = draw_block(seed, env, step, DOMAIN_STEP, 0);
+        U4 r1 = r0;
+        if (p.n_opp > 2) r1 = draw_block(seed, env, step, DOMAIN_STEP, 1);
+        for (int j = 0; j < p.n_opp; ++j) {
+            const int sh = 5 + 5 * j;
+            const uint32_t o = (s2 >> sh) & 31u;
+            if (o == agent) {
+                reward = 10.f;
+                tagged = true;
+                --nopp;
+            } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
+                const U4& r = j < 2 ? r0 : r1;
+                const uint32_t w_move = word_of(r, (2 * j) & 3), w_pick = word_of(r, (2 * j + 1) & 3);
+                int ox, oy;
+                tag_get_coord(o, ox, oy);
+                uint32_t list;
+                const int cnt = tag_admissible(ax, ay, ox, oy, list);
+                if (bern(w_move, p.move_T)) {                                     // tag.py:204
+                    const int m = (int)((list >> (2 * rand_below(w_pick, (uint32_t)cnt))) & 3u);  // tag.py:205
+                    const int nx = ox + move_dx(m), ny = oy + move_dy(m);
+                    if (tag_is_inside(nx, ny))                                    // tag.py:206-207
+                        s2 = (s2 & ~(31u << sh)) | ((uint32_t)tag_get_index(nx, ny) << sh);
+                }
+            }
+        }
+        if (!tagged) reward = -10.f;
+    } else {                                                                      // tag.py:133-137
+        reward = -1.f;
+        const int nx = ax + move_dx(a), ny = ay + move_dy(a);
+        if (tag_is_inside(nx, ny)) {
+            agent = (uint32_t)tag_get_index(nx, ny);
+            s2 = (s2 & ~31u) | agent;
+        }
+    }
+    ob = (int32_t)agent;                                                          // tag.py:219-226
+    if (a < 4)
+        for (int j = 0; j < p.n_opp; ++j)
+            if (((s2 >> (5 + 5 * j)) & 31u) == agent) ob = TAG_CELLS;
+    s2 = tag_set_num_opp(s2, nopp);
+    if (nopp == 0) { s2 |= TAG_DONE; fl |= FLAG_DONE; }                           // tag.py:142
+    rw = reward;
+}
+
+// tag.py:97-102, 181-193: slot 0 = agent cell, slot 1+j = opponent j; ob = _sample_ob(state, 0).
+POMDP_HD void tag_reset(const TagDev& p, uint64_t seed, uint64_t env, uint32_t step, uint32_t& s, int32_t& ob) {
+    const U4 r0 = draw_block(seed, env, step, DOMAIN_RESET, 0);
+    U4 r1 = r0;
+    if (p.n_opp > 3) r1 = draw_block(seed, env, step, DOMAIN_RESET, 1);
+    const uint32_t agent = rand_below(r0.x, TAG_CELLS);
+    s = agent;
+    ob = (int32_t)agent;
+    for (int j = 0; j < p.n_opp; ++j) {
+        const uint32_t w = (1 + j) < 4 ? word_of(r0, 1 + j) : word_of(r1, (1 + j) & 3);
+        const uint32_t o = rand_below(w, TAG_CELLS);
+        s |= o << (5 + 5 * j);
+        if (o == agent) ob = TAG_CELLS;
+    }
+    s = tag_set_num_opp(s, p.n_opp);
+}
+
+// =========================================================================== Tiger ===
+struct TigerDev {
+    uint64_t listen_G;  // floor(listen_prob * 2^32):  (u > p)  <=>  (r > G)
+};
+constexpr uint32_t TIGER_DONE = 0x80000000u;
+
+// tiger.py:72-88 (+ _compute_rw 164-172, _is_terminal 155-162, _sample_state 117-119, _sample_ob 140-149)
+POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
+                         uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    s2 = s; ob = 0; rw = 0.f; fl = 0;
+    if (s & TIGER_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }
+    if ((uint32_t)a >= 3u) { fl = FLAG_BAD_ACTION; return; }
+    if (s > 1u) { fl = FLAG_BAD_STATE; return; }
+    uint32_t st = s & 1u;
+    const bool terminal = a != 2 && (uint32_t)a == st;
+    rw = a == 2 ? -1.f : (terminal ? -20.f : 10.f);
+    if (terminal) {                       // tiger.py:81-83: the observation returned is the state itself
+        ob = (int32_t)st;
+        s2 = s | TIGER_DONE;
+        fl = FLAG_DONE;
+        return;
+    }
+    const U4 r = draw_block(seed, env, step, DOMAIN_STEP, 0);
+    if (a < 2) st = rand_below(r.x, 2);   // state_space.sample(), tiger.py:118-119
+    const bool flip = (uint64_t)r.y > p.listen_G;   // p > correct_prob, tiger.py:143-148
+    ob = 2;
+    if (a == 2) ob = (int32_t)(flip ? 1u - st : st);
+    s2 = st;
+}
+
+// tiger.py:60-66
+POMDP_HD void tiger_reset(uint64_t seed, uint64_t env, uint32_t step, uint32_t& s, int32_t& ob) {
+    const U4 r = draw_block(seed, env, step, DOMAIN_RESET, 0);
+    s = rand_below(r.x, 2);
+    ob = 2;
+}
+
+// ========================================================================= Network ===
+constexpr int NETWORK_MAX = 30;
+struct NetworkDev {
+    int32_t n;
+    uint32_t deg3;                   // machines with more than 2 neighbours (reward 2, network.py:89-92)
+    uint64_t p_T, q_T, ob_T;         // ceil(prob * 2^32)
+    uint32_t nb[NETWORK_MAX + 2];    // neighbour bit masks (network.py:144-168)
+};
+constexpr uint32_t NETWORK_DONE = 0x80000000u;
+
+POMDP_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+// network.py:71-114.  Reward is carried as an exact integer number of tenths.
+POMDP_HD void network_step(const NetworkDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
+                           uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    s2 = s; ob = 0; rw = 0.f; fl = 0;
+    const uint32_t all = (1u << p.n) - 1u;
+    if (s & NETWORK_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }
+    if ((uint32_t)a >= (uint32_t)(2 * p.n + 1)) { fl = FLAG_BAD_ACTION; return; }
+    if (s & ~all) { fl = FLAG_BAD_STATE; return; }
+    const uint32_t down = ~s & all;
+    int tenths = 10 * popc32(s) + 10 * popc32(s & p.deg3);                        // network.py:87-92
+    uint32_t nw = s;
+    uint32_t w_act = 0;
+    for (int b = 0; 4 * b <= p.n; ++b) {                                          // network.py:94-99
+        const U4 r = draw_block(seed, env, step, DOMAIN_STEP, (uint32_t)b);
+        POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int m = 4 * b + j;
+            const uint32_t w = word_of(r, j);
+            if (m < p.n) {
+                const uint64_t T = (p.nb[m] & down) ? p.q_T : p.p_T;
+                if (((s >> m) & 1u) && bern(w, T)) nw &= ~(1u << m);
+            } else if (m == p.n) {
+                w_act = w;
+            }
+        }
+    }
+    ob = 2;
+    if (a < 2 * p.n) {                                                            // network.py:101-112
+        const int machine = a >> 1;
+        const int hit = bern(w_act, p.ob_T) ? 1 : 0;
+        if (a & 1) {
+            tenths -= 25;
+            nw |= 1u << machine;
+            ob = hit;
+        } else {
+            tenths -= 1;
+            const int bit = (int)((nw >> machine) & 1u);
+            ob = hit ? bit : 1 - bit;
+        }
+    }
+    s2 = nw;
+#if defined(__CUDA_ARCH__)
+    rw = __fdiv_rn((float)tenths, 10.0f);
+#else
+    rw = (float)tenths / 10.0f;
+#endif
+}
+
+// ====================================================================== BattleShip ===
+constexpr int SHIP_WORDS = 8;
+constexpr int SHIP_MAX_CELLS = 120;
+struct ShipDev {
+    int32_t X, Y, max_len, n_tiles;
+    uint64_t col0_lo, col0_hi;   // cells with x == 0
+    uint64_t colL_lo, colL_hi;   // cells with x == X-1
+};
+struct ShipState {
+    u128 occ, vis;     // bit c = cell c = X*y + x
+    int remaining;
+    bool done;
+};
+
+POMDP_HD ShipState ship_unpack(const uint32_t w[SHIP_WORDS]) {
+    ShipState st;
+    st.occ = (u128)w[0] | ((u128)w[1] << 32) | ((u128)w[2] << 64) | ((u128)(w[3] & 0x00FFFFFFu) << 96);
+    st.vis = (u128)w[4] | ((u128)w[5] << 32) | ((u128)w[6] << 64) | ((u128)w[7] << 96);
+    st.remaining = (int)((w[3] >> 24) & 0x7Fu);
+    st.done = (w[3] >> 31) != 0;
+    return st;
+}
+POMDP_HD void ship_pack(const ShipState& st, uint32_t w[SHIP_WORDS]) {
+    w[0] = (uint32_t)st.occ; w[1] = (uint32_t)(st.occ >> 32); w[2] = (uint32_t)(st.occ >> 64);
+    w[3] = ((uint32_t)(st.occ >> 96) & 0x00FFFFFFu) | ((uint32_t)(st.remaining & 0x7F) << 24) | (st.done ? 0x80000000u : 0u);
+    w[4] = (uint32_t)st.vis; w[5] = (uint32_t)(st.vis >> 32); w[6] = (uint32_t)(st.vis >> 64); w[7] = (uint32_t)(st.vis >> 96);
+}
+
+// battleship.py:91-122 on the 8 packed words (the `diagonal` writes at 111-113 are dead state).
+POMDP_HD void battleship_step(const ShipDev& p, const uint32_t w[SHIP_WORDS], int32_t a,
+                              uint32_t w2[SHIP_WORDS], int32_t& ob, float& rw, int32_t& fl) {
+    POMDP_UNROLL
+    for (int i = 0; i < SHIP_WORDS; ++i) w2[i] = w[i];
+    ob = 0; rw = 0.f; fl = 0;
+    if (w[3] >> 31) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }               // battleship.py:93
+    if ((uint32_t)a >= (uint32_t)p.n_tiles) { fl = FLAG_BAD_ACTION; return; }     // battleship.py:94
+    const int wi = a >> 5;
+    const uint32_t bit = 1u << (a & 31);
+    const uint32_t ow = wi == 0 ? w[0] : wi == 1 ? w[1] : wi == 2 ? w[2] : w[3];
+    const uint32_t vw = wi == 0 ? w[4] : wi == 1 ? w[5] : wi == 2 ? w[6] : w[7];
+    int remaining = (int)((w[3] >> 24) & 0x7Fu);
+    int reward = 0;
+    if (vw & bit) {
+        reward = -10;
+    } else {
+        reward = -1;
+        if (ow & bit) { ob = 1; --remaining; }
+        POMDP_UNROLL
+        for (int i = 0; i < 4; ++i) if (wi == i) w2[4 + i] |= bit;
+    }
+    bool done = false;
+    if (remaining == 0) { reward += p.n_tiles; done = true; }                     // battleship.py:118-120
+    w2[3] = (w2[3] & 0x00FFFFFFu) | ((uint32_t)(remaining & 0x7F) << 24) | (done ? 0x80000000u : 0u);
+    if (done) fl = FLAG_DONE;
+    rw = (float)reward;
+}
+
+// Cells a new ship may not touch (battleship.py:195-211): occupied cells and every cell q
+// with an occupied cell at q + {N,E,S,W,NE,SE,SW}.  q + NW is never looked at (range(8)
+// over the Compass enum stops before NorthWest).
+POMDP_HD u128 ship_blocked(const ShipDev& p, u128 occ) {
+    const u128 col0 = (u128)p.col0_lo | ((u128)p.col0_hi << 64);
+    const u128 colL = (u128)p.colL_lo | ((u128)p.colL_hi << 64);
+    const int X = p.X;
+    u128 b = occ;
+    b |= occ >> X;                    // q + N occupied
+    b |= occ << X;                    // q + S occupied
+    b |= (occ >> 1) & ~colL;          // q + E occupied (q not in the last column)
+    b |= (occ << 1) & ~col0;          // q + W
+    b |= (occ >> (X + 1)) & ~colL;    // q + NE
+    b |= (occ << (X - 1)) & ~colL;    // q + SE
+    b |= (occ << (X + 1)) & ~col0;    // q + SW
+    return b;
+}
+
+// Would the reference's collision() accept this (pos, dir, length)?  Walks length + 1
+// cells and needs the cell after each inside the board (battleship.py:199-201).
+POMDP_HD bool ship_candidate_ok(const ShipDev& p, u128 blocked, int pos, int dir, int length) {
+    const int x = pos % p.X, y = pos / p.X;
+    const int dx = move_dx(dir), dy = move_dy(dir);   // Compass 0..3 == Moves 0..3
+    if (!grid_is_inside(p.X, p.Y, x + (length + 1) * dx, y + (length + 1) * dy)) return false;
+    const int stride = dy * p.X + dx;
+    bool ok = true;
+    for (int i = 0; i <= length; ++i) ok = ok && !((uint32_t)(blocked >> (pos + i * stride)) & 1u);
+    return ok;
+}
+
+// battleship.py:182-193
+POMDP_HD void ship_mark(const ShipDev& p, ShipState& st, int pos, int dir, int length) {
+    const int stride = move_dy(dir) * p.X + move_dx(dir);
+    for (int i = 0; i < length; ++i) {
+        const u128 bit = (u128)1 << (pos + i * stride);
+        st.occ |= bit;
+        if (!(st.vis & bit)) ++st.remaining;
+    }
+}
+
+// battleship.py:167-180 as written: rejection sampling; attempt a -> slots 2a (pos), 2a+1 (dir).
+POMDP_HD bool battleship_reset_rejection(const ShipDev& p, uint64_t seed, uint64_t env, uint32_t step,
+                                         ShipState& st, int max_attempts) {
+    st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+    int a = 0;
+    U4 r = {0, 0, 0, 0};
+    for (int length = p.max_len; length >= 2; --length) {
+        const u128 blocked = ship_blocked(p, st.occ);
+        for (;;) {
+            if (a >= max_attempts) return false;
+            if ((a & 1) == 0) r = draw_block(seed, env, step, DOMAIN_RESET, (uint32_t)(a >> 1));
+            const uint32_t w_pos = (a & 1) ? r.z : r.x, w_dir = (a & 1) ? r.w : r.y;
+            ++a;
+            const int pos = (int)rand_below(w_pos, (uint32_t)p.n_tiles), dir = (int)rand_below(w_dir, 4);
+            if (ship_candidate_ok(p, blocked, pos, dir, length)) { ship_mark(p, st, pos, dir, length); break; }
+        }
+    }
+    return true;
+}
+
+// ================================================================ belief histogram ===
+// Calls add(bin) for every count this env contributes (bins: include/pomdp_b200.h).
+template <class F>
+POMDP_HD void belief_bins(int kind, int p0, int p1, const uint32_t* s, F add) {
+    if (kind == 0) {               // Rock: p0 = k, p1 = words
+        const uint64_t v = p1 == 2 ? ((uint64_t)s[0] | ((uint64_t)s[1] << 32)) : (uint64_t)s[0];
+        for (int i = 0; i < p0; ++i) if (((v >> (8 + 2 * i)) & 3u) == 1u) add(i);
+        add(p0 + (int)(v & 0xFF));
+    } else if (kind == 1) {        // Tag
+        add((int)(s[0] & 31u));
+        add(TAG_CELLS + (int)((s[0] >> 5) & 31u));
+    } else if (kind == 2) {        // BattleShip: p0 = n_tiles
+        for (int c = 0; c < p0; ++c) if ((s[c >> 5] >> (c & 31)) & 1u) add(c);
+    } else if (kind == 3) {        // Tiger
+        add((int)(s[0] & 1u));
+    } else {                       // Network: p0 = n
+        for (int m = 0; m < p0; ++m) if ((s[0] >> m) & 1u) add(m);
+    }
+}
+
+}  // namespace pomdp

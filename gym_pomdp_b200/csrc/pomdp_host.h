@@ -1,0 +1,185 @@
+// pomdp_host.h -- host-only glue shared by pomdp_kernels.cu (the product) and
+// tests/hostsim/ (test vehicle): argument validation, conversion of the public parameter
+// structs (include/pomdp_b200.h) into the by-value kernel parameter PODs, and construction
+// of the static per-config maps.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pomdp_b200.h"
+#include "pomdp_core.h"
+
+namespace pomdp {
+namespace host {
+
+inline char* err_buf() {
+    static thread_local char buf[256] = "";
+    return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// binomial(1, p) == [r < T],  T = ceil(p * 2^32)   (p * 2^32 is exact in a double)
+inline uint64_t bern_T(double p) {
+    if (!(p > 0.0)) return 0;
+    if (p >= 1.0) return 1ull << 32;
+    return (uint64_t)ceil(p * 4294967296.0);
+}
+// (u > p) == [r > G],  G = floor(p * 2^32)
+inline uint64_t gt_G(double p) {
+    if (!(p > 0.0)) return 0;
+    if (p >= 1.0) return 1ull << 32;
+    return (uint64_t)floor(p * 4294967296.0);
+}
+
+// ---- RockSample benchmark layouts (the constants of rock.py:43-64) -----------------
+struct RockLayout {
+    int board, k_a, k_b;   // rock.py:101: num_rocks must be one of the two 'size' members
+    int sx, sy, n_listed;
+    int8_t pos[16][2];
+};
+inline const RockLayout* rock_layout(int board) {
+    static const RockLayout L[] = {
+        {2, 2, 1, 0, 0, 1, {{1, 0}}},
+        {4, 4, 3, 0, 0, 3, {{1, 0}, {3, 1}, {2, 3}}},
+        {7, 7, 8, 0, 3, 8, {{2, 0}, {0, 1}, {3, 1}, {6, 3}, {2, 4}, {3, 4}, {5, 5}, {1, 6}}},
+        {11, 11, 11, 0, 5, 11,
+         {{0, 3}, {0, 7}, {1, 8}, {2, 4}, {3, 3}, {3, 8}, {4, 3}, {5, 8}, {6, 1}, {9, 3}, {9, 9}}},
+        {15, 15, 15, 0, 5, 16,
+         {{0, 7}, {0, 3}, {1, 2}, {1, 2}, {2, 6}, {3, 7}, {3, 2}, {4, 7}, {5, 2}, {6, 9}, {9, 7}, {9, 1},
+          {11, 8}, {13, 10}, {14, 9}, {12, 2}}},
+    };
+    for (const RockLayout& l : L)
+        if (l.board == board) return &l;
+    return nullptr;
+}
+
+inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 : 2; }
+
+// Fills the kernel params and (if tbl != nullptr) the static maps.  Returns 0 or POMDP_E_BADARG.
+inline int make_rock(const PomdpRockParams* q, RockDev* d, RockTable* tbl) {
+    if (!q) return fail(POMDP_E_BADARG, "rock: params is NULL");
+    const RockLayout* L = rock_layout(q->board_size);
+    if (!L) return fail(POMDP_E_BADARG, "rock: board_size %d is not a key of rock.config (2,4,7,11,15)", q->board_size);
+    if (q->num_rocks != L->k_a && q->num_rocks != L->k_b)
+        return fail(POMDP_E_BADARG, "rock: num_rocks %d not in config[%d]['size'] (%d,%d)", q->num_rocks,
+                    q->board_size, L->k_a, L->k_b);
+    if (q->num_rocks > L->n_listed)
+        return fail(POMDP_E_BADARG, "rock: config[%d] lists only %d rocks (the reference fails in _get_init_state)",
+                    q->board_size, L->n_listed);
+    if (d) {
+        memset(d, 0, sizeof(*d));
+        d->n = q->board_size;
+        d->k = q->num_rocks;
+        d->stochastic = q->stochastic ? 1 : 0;
+        d->penal = q->stochastic ? 0 : -100;
+        d->start = (uint32_t)(L->sx | (L->sy << 4));
+        d->move_T = bern_T(q->p_move);
+    }
+    if (tbl) {
+        memset(tbl, 0, sizeof(*tbl));
+        memset(tbl->grid, -1, sizeof(tbl->grid));
+        memset(tbl->rock_pos, 0xFF, sizeof(tbl->rock_pos));
+        for (int i = 0; i < L->n_listed; ++i) {   // every listed rock is written; later ids overwrite (rock.py:110-111)
+            const int cell = L->pos[i][0] | (L->pos[i][1] << 4);
+            tbl->grid[cell] = (int8_t)i;
+            tbl->rock_pos[i] = (uint8_t)cell;
+        }
+        for (int dd = 0; dd < 32; ++dd) {
+            const double eff = (1 + pow(2, -(double)dd / 20)) * .5;      // rock.py:383-387
+            tbl->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
+        }
+    }
+    return 0;
+}
+
+inline int make_tag(const PomdpTagParams* q, TagDev* d) {
+    if (!q) return fail(POMDP_E_BADARG, "tag: params is NULL");
+    if (q->num_opponents < 1 || q->num_opponents > 4)
+        return fail(POMDP_E_BADARG, "tag: num_opponents %d outside 1..4", q->num_opponents);
+    memset(d, 0, sizeof(*d));
+    d->n_opp = q->num_opponents;
+    d->move_T = bern_T(q->move_prob);
+    return 0;
+}
+
+inline int make_tiger(const PomdpTigerParams* q, TigerDev* d) {
+    if (!q) return fail(POMDP_E_BADARG, "tiger: params is NULL");
+    d->listen_G = gt_G(q->listen_prob);
+    return 0;
+}
+
+inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
+    if (!q) return fail(POMDP_E_BADARG, "network: params is NULL");
+    const int n = q->n_machines;
+    if (n < 1 || n > NETWORK_MAX) return fail(POMDP_E_BADARG, "network: n_machines %d outside 1..%d", n, NETWORK_MAX);
+    memset(d, 0, sizeof(*d));
+    d->n = n;
+    d->p_T = bern_T(q->p);
+    d->q_T = bern_T(q->q);
+    d->ob_T = bern_T(q->p_ob);
+    int deg[NETWORK_MAX] = {0};
+    auto link = [&](int i, int j) { d->nb[i] |= 1u << j; ++deg[i]; };
+    if (q->problem_type == 3) {                     // network.py:153-168
+        if (n < 4 || n % 3 != 1) return fail(POMDP_E_BADARG, "network: 3-legs needs n >= 4 and n %% 3 == 1 (network.py:155)");
+        link(0, 1); link(0, 2); link(0, 3);
+        for (int i = 1; i < n; ++i) {
+            if (i < n - 3) link(i, i + 3);
+            if (i <= 4) link(i, 0); else link(i, i - 3);
+        }
+    } else {                                        // network.py:144-151
+        for (int i = 0; i < n; ++i) { link(i, (i + 1) % n); link(i, (i + n - 1) % n); }
+    }
+    for (int i = 0; i < n; ++i)
+        if (deg[i] > 2) d->deg3 |= 1u << i;         // len(neighbours) counts duplicates too (network.py:89)
+    return 0;
+}
+
+inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
+    if (!q) return fail(POMDP_E_BADARG, "battleship: params is NULL");
+    if (q->x_size < 1 || q->y_size < 1 || q->x_size * q->y_size > SHIP_MAX_CELLS)
+        return fail(POMDP_E_BADARG, "battleship: board %dx%d outside 1..%d cells", q->x_size, q->y_size, SHIP_MAX_CELLS);
+    if (q->max_len < 2) return fail(POMDP_E_BADARG, "battleship: max_len %d < 2", q->max_len);
+    int total = 0;
+    for (int l = 2; l <= q->max_len; ++l) total += l;
+    if (total > 127) return fail(POMDP_E_BADARG, "battleship: total ship length %d does not fit 7 bits", total);
+    memset(d, 0, sizeof(*d));
+    d->X = q->x_size; d->Y = q->y_size; d->max_len = q->max_len; d->n_tiles = q->x_size * q->y_size;
+    u128 c0 = 0, cL = 0;
+    for (int y = 0; y < d->Y; ++y) { c0 |= (u128)1 << (y * d->X); cL |= (u128)1 << (y * d->X + d->X - 1); }
+    d->col0_lo = (uint64_t)c0; d->col0_hi = (uint64_t)(c0 >> 64);
+    d->colL_lo = (uint64_t)cL; d->colL_hi = (uint64_t)(cL >> 64);
+    return 0;
+}
+
+inline int hist_bins(int kind, int p0, int p1) {
+    switch (kind) {
+        case POMDP_KIND_ROCK: return p0 + 256;
+        case POMDP_KIND_TAG: return 2 * TAG_CELLS;
+        case POMDP_KIND_BATTLESHIP: return p0;
+        case POMDP_KIND_TIGER: return 2;
+        case POMDP_KIND_NETWORK: return p0;
+    }
+    (void)p1;
+    return -1;
+}
+
+inline int check_io(const void* state, const void* action, const void* next, const void* obs, const void* rw,
+                    const void* fl, int64_t n) {
+    if (n < 0) return fail(POMDP_E_BADARG, "n = %lld is negative", (long long)n);
+    if (n == 0) return 0;
+    if (!state || !action || !next || !obs || !rw || !fl) return fail(POMDP_E_BADARG, "a required array pointer is NULL");
+    const uintptr_t any = (uintptr_t)state | (uintptr_t)action | (uintptr_t)next | (uintptr_t)obs | (uintptr_t)rw | (uintptr_t)fl;
+    if (any & 3) return fail(POMDP_E_ALIGN, "array pointers must be 4-byte aligned");
+    return 0;
+}
+
+}  // namespace host
+}  // namespace pomdp

@@ -1,0 +1,727 @@
+// pomdp_kernels.cu -- sm_100a kernels + the C ABI of include/pomdp_b200.h.
+//
+// Data movement design:
+//  * W=1/W=2 envs (Rock, Tag, Tiger, Network): SoA int32 streams.  One thread owns FOUR
+//    consecutive env instances: 16-byte vector loads of state/action, 16-byte vector
+//    stores of next_state/obs/reward/flags, fully coalesced (a warp moves 512 B per
+//    instruction).  Persistent grid-stride loop, grid = min(work, SMs x resident CTAs).
+//  * Rock's static maps (rock-id grid, rock coordinates, sensor thresholds; 400 B) are
+//    copied global -> shared once per CTA with ONE TMA bulk copy (cp.async.bulk +
+//    mbarrier complete_tx); the first global loads are issued before the wait so the
+//    table fetch hides under them.  Lookups are per-thread divergent, which is what
+//    shared memory (not the constant bank) is for.
+//  * BattleShip (W=8, 32 B per board): board tiles are moved global -> shared and
+//    shared -> global with TMA bulk copies (8 KB per 256-env tile), compute reads/writes
+//    the tile in shared memory; reset is one WARP per env (ballot scan over the 4*n_tiles
+//    placement candidates).
+//  * Philox4x32-10 in registers; no RNG state in memory.
+//
+// There is no CPU path in this file: every entry point launches a kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pomdp_core.h"
+#include "pomdp_host.h"
+
+using namespace pomdp;
+
+#define POMDP_THREADS 256
+
+// ----------------------------------------------------------------------------- PTX ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Streaming (evict-first) vector accesses: every byte is touched once per launch.
+__device__ __forceinline__ int4 ld_stream4(const int32_t* p) { return __ldcs(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ void st_stream4(int32_t* p, int4 v) { __stcs(reinterpret_cast<int4*>(p), v); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+// ------------------------------------------------------------------- env policies ---
+// Each policy adapts one env's functor from pomdp_core.h to the generic streaming kernels.
+struct RockEnv1 {
+    typedef RockDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = true;
+    __device__ static __forceinline__ void step(const Params& p, const RockTable* t, State s, int32_t a, uint64_t seed,
+                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
+                                                int32_t& fl) {
+        rock_step<uint32_t>(p, t, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
+                                                 State& s, int32_t& ob) {
+        s = rock_reset<uint32_t>(p, seed, env, step_ctr);
+        ob = 0;
+    }
+};
+struct RockEnv2 {
+    typedef RockDev Params;
+    typedef uint64_t State;
+    static constexpr bool kTable = true;
+    __device__ static __forceinline__ void step(const Params& p, const RockTable* t, State s, int32_t a, uint64_t seed,
+                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
+                                                int32_t& fl) {
+        rock_step<uint64_t>(p, t, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
+                                                 State& s, int32_t& ob) {
+        s = rock_reset<uint64_t>(p, seed, env, step_ctr);
+        ob = 0;
+    }
+};
+struct TagEnvP {
+    typedef TagDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
+                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
+                                                int32_t& fl) {
+        tag_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
+                                                 State& s, int32_t& ob) {
+        tag_reset(p, seed, env, step_ctr, s, ob);
+    }
+};
+struct TigerEnvP {
+    typedef TigerDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
+                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
+                                                int32_t& fl) {
+        tiger_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset(const Params&, uint64_t seed, uint64_t env, uint32_t step_ctr,
+                                                 State& s, int32_t& ob) {
+        tiger_reset(seed, env, step_ctr, s, ob);
+    }
+};
+struct NetworkEnvP {
+    typedef NetworkDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
+                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
+                                                int32_t& fl) {
+        network_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset(const Params& p, uint64_t, uint64_t, uint32_t, State& s, int32_t& ob) {
+        s = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
+        ob = 0;
+    }
+};
+
+// Load / store four consecutive packed states (32- or 64-bit) with 16-byte accesses.
+__device__ __forceinline__ void load_states4(const int32_t* base, int64_t i, uint32_t s[4]) {
+    const int4 v = ld_stream4(base + i);
+    s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; s[2] = (uint32_t)v.z; s[3] = (uint32_t)v.w;
+}
+__device__ __forceinline__ void load_states4(const int32_t* base, int64_t i, uint64_t s[4]) {
+    const int4 v0 = ld_stream4(base + 2 * i), v1 = ld_stream4(base + 2 * i + 4);
+    s[0] = (uint32_t)v0.x | ((uint64_t)(uint32_t)v0.y << 32); s[1] = (uint32_t)v0.z | ((uint64_t)(uint32_t)v0.w << 32);
+    s[2] = (uint32_t)v1.x | ((uint64_t)(uint32_t)v1.y << 32); s[3] = (uint32_t)v1.z | ((uint64_t)(uint32_t)v1.w << 32);
+}
+__device__ __forceinline__ void store_states4(int32_t* base, int64_t i, const uint32_t s[4]) {
+    st_stream4(base + i, make_int4((int)s[0], (int)s[1], (int)s[2], (int)s[3]));
+}
+__device__ __forceinline__ void store_states4(int32_t* base, int64_t i, const uint64_t s[4]) {
+    st_stream4(base + 2 * i, make_int4((int)(uint32_t)s[0], (int)(s[0] >> 32), (int)(uint32_t)s[1], (int)(s[1] >> 32)));
+    st_stream4(base + 2 * i + 4, make_int4((int)(uint32_t)s[2], (int)(s[2] >> 32), (int)(uint32_t)s[3], (int)(s[3] >> 32)));
+}
+__device__ __forceinline__ uint32_t load_state1(const int32_t* base, int64_t i, uint32_t) { return (uint32_t)base[i]; }
+__device__ __forceinline__ uint64_t load_state1(const int32_t* base, int64_t i, uint64_t) {
+    return (uint32_t)base[2 * i] | ((uint64_t)(uint32_t)base[2 * i + 1] << 32);
+}
+__device__ __forceinline__ void store_state1(int32_t* base, int64_t i, uint32_t s) { base[i] = (int32_t)s; }
+__device__ __forceinline__ void store_state1(int32_t* base, int64_t i, uint64_t s) {
+    base[2 * i] = (int32_t)(uint32_t)s;
+    base[2 * i + 1] = (int32_t)(s >> 32);
+}
+
+// ----------------------------------------------------------------- step (streams) ---
+// kVec: all six arrays are 16-byte aligned -> 4 envs per thread with vector accesses;
+// otherwise a scalar thread-per-env path (only reached for oddly offset views).
+template <class Env, bool kVec>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const RockTable* __restrict__ g_table,
+                  const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
+                  int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n,
+                  uint64_t goff, uint64_t seed, uint32_t step_ctr) {
+    typedef typename Env::State S;
+    __shared__ alignas(16) RockTable tbl;
+    __shared__ alignas(8) uint64_t bar;
+    const RockTable* t = nullptr;
+    if (Env::kTable) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&bar, (uint32_t)sizeof(RockTable));
+            tma_bulk_g2s(&tbl, g_table, (uint32_t)sizeof(RockTable), &bar);
+        }
+        __syncthreads();   // barrier object initialised before anyone polls it
+        t = &tbl;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    bool table_ready = !Env::kTable;
+    if (kVec) {
+        const int64_t n_groups = n >> 2;
+        for (int64_t g = tid; g < n_groups; g += nthreads) {
+            const int64_t i = g << 2;
+            S s[4], s2[4];
+            load_states4(state, i, s);
+            const int4 av = ld_stream4(action + i);
+            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }   // loads above are already in flight
+            const int32_t a[4] = {av.x, av.y, av.z, av.w};
+            int32_t ob[4], fl[4];
+            float rw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                Env::step(p, t, s[j], a[j], seed, goff + (uint64_t)(i + j), step_ctr, s2[j], ob[j], rw[j], fl[j]);
+            store_states4(next_state, i, s2);
+            st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
+            st_stream4(reward + i, make_float4(rw[0], rw[1], rw[2], rw[3]));
+            st_stream4(flags + i, make_int4(fl[0], fl[1], fl[2], fl[3]));
+        }
+        // tail (n % 4 envs): the first few threads of the grid
+        const int64_t i = (n_groups << 2) + tid;
+        if (i < n) {
+            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
+            S s2; int32_t ob, fl; float rw;
+            Env::step(p, t, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+            store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthreads) {
+            const S s = load_state1(state, i, S());
+            const int32_t a = action[i];
+            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
+            S s2; int32_t ob, fl; float rw;
+            Env::step(p, t, s, a, seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+            store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
+        }
+    }
+    // a CTA must not exit while its bulk copy may still be in flight
+    if (!table_ready) mbar_wait(&bar, 0);
+}
+
+// ---------------------------------------------------------------- reset (streams) ---
+template <class Env>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __restrict__ state,
+                   int32_t* __restrict__ obs, const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
+                   uint64_t seed, uint32_t step_ctr) {
+    typedef typename Env::State S;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        if (mask && !mask[i]) continue;
+        S s; int32_t ob;
+        Env::reset(p, seed, goff + (uint64_t)i, step_ctr, s, ob);
+        store_state1(state, i, s);
+        if (obs) obs[i] = ob;
+    }
+}
+
+// --------------------------------------------------------------- BattleShip step ----
+// One thread per board; the CTA's tile of boards (POMDP_THREADS x 32 B) travels through
+// shared memory with TMA bulk copies in both directions.
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_step_kernel(const __grid_constant__ ShipDev p, const int32_t* state,
+                             const int32_t* __restrict__ action, int32_t* next_state, int32_t* __restrict__ obs,
+                             float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n) {
+    __shared__ alignas(128) uint32_t tile[POMDP_THREADS * SHIP_WORDS];
+    __shared__ alignas(8) uint64_t bar;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const int64_t n_tiles = (n + POMDP_THREADS - 1) / POMDP_THREADS;
+    uint32_t parity = 0;
+    for (int64_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+        const int64_t base = tix * POMDP_THREADS;
+        const int cnt = (int)min((int64_t)POMDP_THREADS, n - base);
+        const uint32_t bytes = (uint32_t)cnt * SHIP_WORDS * 4u;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, bytes);
+            tma_bulk_g2s(tile, state + base * SHIP_WORDS, bytes, &bar);
+        }
+        const int64_t i = base + threadIdx.x;
+        int32_t a = 0;
+        if (threadIdx.x < cnt) a = __ldcs(action + i);
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        if (threadIdx.x < cnt) {
+            uint32_t w[SHIP_WORDS], w2[SHIP_WORDS];
+            uint4* mine = reinterpret_cast<uint4*>(tile + threadIdx.x * SHIP_WORDS);
+            const uint4 lo = mine[0], hi = mine[1];
+            w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+            int32_t ob, fl; float rw;
+            battleship_step(p, w, a, w2, ob, rw, fl);
+            mine[0] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+            mine[1] = make_uint4(w2[4], w2[5], w2[6], w2[7]);
+            __stcs(obs + i, ob); __stcs(reward + i, rw); __stcs(flags + i, fl);
+        }
+        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the bulk-copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_bulk_s2g(next_state + base * SHIP_WORDS, tile, bytes);
+            tma_commit();
+            tma_wait_read0();         // tile may be overwritten once the engine has read it
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tma_wait_all0();
+}
+
+// Fallback for state pointers that are not 16-byte aligned (bulk copies need that).
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_step_plain_kernel(const __grid_constant__ ShipDev p, const int32_t* state,
+                                   const int32_t* __restrict__ action, int32_t* next_state, int32_t* __restrict__ obs,
+                                   float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t w[SHIP_WORDS], w2[SHIP_WORDS];
+#pragma unroll
+        for (int k = 0; k < SHIP_WORDS; ++k) w[k] = (uint32_t)state[i * SHIP_WORDS + k];
+        int32_t ob, fl; float rw;
+        battleship_step(p, w, action[i], w2, ob, rw, fl);
+#pragma unroll
+        for (int k = 0; k < SHIP_WORDS; ++k) next_state[i * SHIP_WORDS + k] = (int32_t)w2[k];
+        obs[i] = ob; reward[i] = rw; flags[i] = fl;
+    }
+}
+
+// --------------------------------------------------------------- BattleShip reset ---
+// One warp per env (BASELINE.json: "warp-per-env ship scan").  For each ship the 32 lanes
+// test the 4*n_tiles (pos, dir) candidates c = 4*pos + dir, lane l taking c = l + 32 j;
+// ballots give, per j, the accepted set in increasing c; the k-th accepted candidate is
+// taken with k = floor(u * count), u from draw slot = ship index.
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
+                                   int32_t* __restrict__ obs, int32_t* __restrict__ flags,
+                                   const uint8_t* __restrict__ mask, int64_t n, uint64_t goff, uint64_t seed,
+                                   uint32_t step_ctr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n_cand = 4 * p.n_tiles;
+    const int n_iter = (n_cand + 31) >> 5;    // <= 15
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        if (mask && !mask[i]) continue;       // warp-uniform
+        ShipState st;
+        st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+        const U4 r = draw_block(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, 0);
+        U4 r_hi = r;
+        bool ok_all = true;
+        int ship = 0;
+        for (int length = p.max_len; length >= 2; --length, ++ship) {
+            if (ship == 4) r_hi = draw_block(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, 1);
+            const u128 blocked = ship_blocked(p, st.occ);
+            uint32_t mine = 0;                // bit j: candidate lane + 32 j is accepted
+            int total = 0;
+            for (int j = 0; j < n_iter; ++j) {
+                const int c = lane + 32 * j;
+                const bool ok = c < n_cand && ship_candidate_ok(p, blocked, c >> 2, c & 3, length);
+                mine |= (uint32_t)ok << j;
+                total += __popc(__ballot_sync(0xffffffffu, ok));
+            }
+            if (total == 0) { ok_all = false; break; }   // the reference would loop forever
+            const uint32_t w = ship < 4 ? word_of(r, ship) : word_of(r_hi, ship & 3);
+            int k = (int)rand_below(w, (uint32_t)total);
+            int chosen = -1;
+            for (int j = 0; j < n_iter; ++j) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+                const int cnt = __popc(m);
+                if (chosen < 0) {
+                    if (k < cnt) chosen = 32 * j + (int)__fns(m, 0, k + 1);
+                    else k -= cnt;
+                }
+            }
+            ship_mark(p, st, chosen >> 2, chosen & 3, length);
+        }
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        if (lane < SHIP_WORDS) {
+            uint32_t v = w8[0];
+#pragma unroll
+            for (int k = 1; k < SHIP_WORDS; ++k) if (lane == k) v = w8[k];
+            state[i * SHIP_WORDS + lane] = (int32_t)v;
+        }
+        if (lane == 8 && obs) obs[i] = 0;                                  // battleship.py:137
+        if (lane == 9 && flags) flags[i] = ok_all ? 0 : FLAG_BAD_STATE;
+    }
+}
+
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_reset_rejection_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
+                                        int32_t* __restrict__ obs, int32_t* __restrict__ flags,
+                                        const uint8_t* __restrict__ mask, int64_t n, uint64_t goff, uint64_t seed,
+                                        uint32_t step_ctr) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        if (mask && !mask[i]) continue;
+        ShipState st;
+        const bool ok = battleship_reset_rejection(p, seed, goff + (uint64_t)i, step_ctr, st, 4096);
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        uint4* dst = reinterpret_cast<uint4*>(state + i * SHIP_WORDS);
+        if ((reinterpret_cast<uintptr_t>(state) & 15) == 0) {
+            dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+        }
+        if (obs) obs[i] = 0;
+        if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
+    }
+}
+
+// ------------------------------------------------------------------- coord helpers ---
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                   int32_t* __restrict__ out, int64_t n) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        switch (op) {
+            case POMDP_COORD_GET_INDEX: out[i] = grid_get_index(xs, a[2 * i], a[2 * i + 1]); break;
+            case POMDP_COORD_GET_COORD: out[2 * i] = a[i] % xs; out[2 * i + 1] = a[i] / xs; break;
+            case POMDP_COORD_IS_INSIDE: out[i] = grid_is_inside(xs, ys, a[2 * i], a[2 * i + 1]); break;
+            case POMDP_COORD_ADD_MOVE: {
+                const int m = b[i];
+                out[2 * i] = a[2 * i] + move_dx(m);
+                out[2 * i + 1] = a[2 * i + 1] + move_dy(m);
+                break;
+            }
+            case POMDP_COORD_L1: out[i] = l1_distance(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]); break;
+            case POMDP_COORD_TAG_GET_INDEX: {
+                const int x = a[2 * i], y = a[2 * i + 1];
+                out[i] = tag_is_inside(x, y) ? tag_get_index(x, y) : -1;
+                break;
+            }
+            case POMDP_COORD_TAG_GET_COORD: {
+                int x = -1, y = -1;
+                if ((uint32_t)a[i] < (uint32_t)TAG_CELLS) tag_get_coord((uint32_t)a[i], x, y);
+                out[2 * i] = x; out[2 * i + 1] = y;
+                break;
+            }
+            case POMDP_COORD_TAG_IS_INSIDE: out[i] = tag_is_inside(a[2 * i], a[2 * i + 1]); break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- belief histogram ---
+// Shared-memory histogram per CTA (<= 512 bins), one 64-bit global atomic per non-empty
+// bin per CTA at the end.
+#define POMDP_HIST_MAX_BINS 512
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
+                         unsigned long long* __restrict__ hist, int bins) {
+    __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t s[SHIP_WORDS];
+        for (int k = 0; k < words && k < SHIP_WORDS; ++k) s[k] = (uint32_t)state[i * words + k];
+        belief_bins(kind, p0, p1, s, [&](int bin) { atomicAdd(&sh[bin], 1u); });
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+}
+
+// ============================================================================ host ===
+namespace {
+
+inline int device_sms() {
+    static thread_local int cached_dev = -1, cached_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached_dev = dev; cached_sms = sms;
+    }
+    return cached_sms;
+}
+
+// Persistent grid: enough CTAs to fill every SM with the kernel's resident-CTA count
+// (occupancy queried once per kernel and cached by kernel address).
+template <class K>
+inline int grid_for(K kernel, int64_t n_threads_needed) {
+    struct Entry { const void* fn; int per_sm; };
+    static thread_local Entry cache[32];
+    static thread_local int n_cached = 0;
+    int per_sm = 0;
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].fn == (const void*)kernel) per_sm = cache[i].per_sm;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, POMDP_THREADS, 0) != cudaSuccess || per_sm <= 0)
+            per_sm = 4;
+        if (n_cached < 32) cache[n_cached++] = Entry{(const void*)kernel, per_sm};
+    }
+    int64_t need = (n_threads_needed + POMDP_THREADS - 1) / POMDP_THREADS;
+    const int64_t cap = (int64_t)device_sms() * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+inline int finish(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return host::fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+inline bool aligned16(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+    return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f) & 15) == 0;
+}
+
+template <class Env>
+int launch_step(const typename Env::Params& p, const void* d_table, const int32_t* state, const int32_t* action,
+                int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
+                uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
+    int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    cudaStream_t st = (cudaStream_t)stream;
+    const RockTable* tb = (const RockTable*)d_table;
+    if (aligned16(state, action, next_state, obs, reward, flags)) {
+        auto k = pomdp_step_kernel<Env, true>;
+        const int grid = grid_for(k, (n + 3) >> 2);
+        k<<<grid, POMDP_THREADS, 0, st>>>(p, tb, state, action, next_state, obs, reward, flags, n, (uint64_t)goff, seed,
+                                         step_ctr);
+    } else {
+        auto k = pomdp_step_kernel<Env, false>;
+        const int grid = grid_for(k, n);
+        k<<<grid, POMDP_THREADS, 0, st>>>(p, tb, state, action, next_state, obs, reward, flags, n, (uint64_t)goff, seed,
+                                         step_ctr);
+    }
+    return finish(what);
+}
+
+template <class Env>
+int launch_reset(const typename Env::Params& p, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
+                 int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
+    if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "%s: bad n or NULL state", what);
+    if (n == 0) return 0;
+    auto k = pomdp_reset_kernel<Env>;
+    const int grid = grid_for(k, n);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+    return finish(what);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pomdp_abi_version(void) { return POMDP_ABI_VERSION; }
+const char* pomdp_last_error(void) { return host::err_buf(); }
+
+// ---- Rock
+int pomdp_rock_state_words(const PomdpRockParams* q) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    return rc ? rc : host::rock_words(q);
+}
+int64_t pomdp_rock_table_bytes(void) { return (int64_t)sizeof(RockTable); }
+int pomdp_rock_build_table(const PomdpRockParams* q, void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "rock: host_table is NULL");
+    RockDev d;
+    return host::make_rock(q, &d, (RockTable*)host_table);
+}
+int pomdp_rock_step(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                    int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
+                    uint64_t seed, uint32_t step_ctr, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if (host::rock_words(q) == 1)
+        return launch_step<RockEnv1>(d, d_table, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                     stream, "pomdp_rock_step");
+    return launch_step<RockEnv2>(d, d_table, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                 stream, "pomdp_rock_step");
+}
+int pomdp_rock_reset(const PomdpRockParams* q, const void* d_table, int32_t* state, int32_t* obs, const uint8_t* mask,
+                     int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    (void)d_table;
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if (host::rock_words(q) == 1)
+        return launch_reset<RockEnv1>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
+    return launch_reset<RockEnv2>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
+}
+
+// ---- Tag
+int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                   int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                   uint32_t step_ctr, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return launch_step<TagEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                stream, "pomdp_tag_step");
+}
+int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
+                    uint64_t seed, uint32_t step_ctr, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return launch_reset<TagEnvP>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_tag_reset");
+}
+
+// ---- Tiger
+int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                     int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                     uint32_t step_ctr, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_step<TigerEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                  stream, "pomdp_tiger_step");
+}
+int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
+                      int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_reset<TigerEnvP>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_tiger_reset");
+}
+
+// ---- Network
+int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                       int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                       uint32_t step_ctr, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_step<NetworkEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                    stream, "pomdp_network_step");
+}
+int pomdp_network_reset(const PomdpNetworkParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
+                        void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_reset<NetworkEnvP>(d, state, obs, mask, n, 0, 0, 0, stream, "pomdp_network_reset");
+}
+
+// ---- BattleShip
+int pomdp_battleship_step(const PomdpBattleshipParams* q, const int32_t* state, const int32_t* action,
+                          int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next_state, obs, reward, flags, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((((uintptr_t)state | (uintptr_t)next_state) & 15) == 0) {
+        auto k = pomdp_battleship_step_kernel;
+        const int grid = grid_for(k, n);
+        k<<<grid, POMDP_THREADS, 0, st>>>(d, state, action, next_state, obs, reward, flags, n);
+    } else {
+        auto k = pomdp_battleship_step_plain_kernel;
+        const int grid = grid_for(k, n);
+        k<<<grid, POMDP_THREADS, 0, st>>>(d, state, action, next_state, obs, reward, flags, n);
+    }
+    return finish("pomdp_battleship_step");
+}
+int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                           const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                           void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if (q->max_len - 1 > 8) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
+    if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset: bad n or NULL state");
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_reset_scan_kernel;
+    const int grid = grid_for(k, n * 32);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, seed, step_ctr);
+    return finish("pomdp_battleship_reset");
+}
+int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                                     const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                                     void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset_rejection: bad n or NULL state");
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_reset_rejection_kernel;
+    const int grid = grid_for(k, n);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, seed, step_ctr);
+    return finish("pomdp_battleship_reset_rejection");
+}
+
+// ---- helpers
+int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n,
+                   void* stream) {
+    if (op < 0 || op > POMDP_COORD_TAG_IS_INSIDE) return host::fail(POMDP_E_BADARG, "coord: unknown op %d", op);
+    if (n < 0 || (n > 0 && (!a || !out))) return host::fail(POMDP_E_BADARG, "coord: bad n or NULL pointer");
+    if ((op == POMDP_COORD_ADD_MOVE || op == POMDP_COORD_L1) && n > 0 && !b)
+        return host::fail(POMDP_E_BADARG, "coord: op %d needs b", op);
+    if ((op == POMDP_COORD_GET_COORD || op == POMDP_COORD_GET_INDEX) && xs <= 0)
+        return host::fail(POMDP_E_BADARG, "coord: x_size must be positive");
+    if (n == 0) return 0;
+    auto k = pomdp_coord_kernel;
+    const int grid = grid_for(k, n);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(op, xs, ys, a, b, out, n);
+    return finish("pomdp_coord_op");
+}
+
+int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1) { return host::hist_bins(kind, p0, p1); }
+int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                      long long* hist, void* stream) {
+    const int bins = host::hist_bins(kind, p0, p1);
+    if (bins <= 0 || bins > POMDP_HIST_MAX_BINS) return host::fail(POMDP_E_BADARG, "belief_hist: bad kind/bins");
+    if (words < 1 || words > SHIP_WORDS) return host::fail(POMDP_E_BADARG, "belief_hist: words %d outside 1..8", words);
+    if (n < 0 || (n > 0 && (!state || !hist))) return host::fail(POMDP_E_BADARG, "belief_hist: bad n or NULL pointer");
+    if (n == 0) return 0;
+    auto k = pomdp_belief_hist_kernel;
+    const int grid = grid_for(k, n);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(kind, p0, p1, state, words, n, (unsigned long long*)hist, bins);
+    return finish("pomdp_belief_hist");
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""Common host-side machinery of the batched POMDP environments.
+
+The reference's envs are single-instance Python objects with the old-gym protocol
+(``reset() -> ob``; ``step(a) -> (ob, reward, done, {"state": s})``) plus the underscore
+hooks planners use (``_set_state``, ``_get_init_state``, ``_generate_legal``,
+``_compute_prob`` ...).  Here one object holds ``batch_size`` independent
+instances as packed int32 words in a torch tensor on a B200 and every call is one CUDA
+kernel reached through the ctypes C ABI (gym_pomdp_b200/_lib.py).
+
+Two calling modes:
+
+* ``batch_size=None`` (default, what ``gym.make(id)`` callers get): one instance, Python
+  scalars in and out, ``info["state"]`` / ``_set_state`` in the reference's own formats,
+  and the reference's ``assert``/``IndexError`` behaviour on bad calls -- a drop-in.
+* ``batch_size=B``: tensors in and out (``obs`` int32[B], ``reward`` float32[B], ``done``
+  bool[B]); ``info["state"]`` is the packed state tensor int32[B, words] and
+  ``info["flags"]`` carries the per-instance error bits that replace the asserts.
+
+``simulate(state, action)`` is the functional generative model G(s, a) -> (s', o, r, flags)
+on caller-owned particle tensors: what a POMCP / particle-filter caller does with
+``_set_state(s); step(a)`` in a Python loop, as one launch.
+"""
+import torch
+
+from .. import _lib
+
+
+def _as_device(device):
+    return torch.device(device) if not isinstance(device, torch.device) else device
+
+
+class BatchedPomdpEnv(object):
+    metadata = {"render.modes": ["ansi"]}
+    kind = -1            # POMDP_KIND_* for the belief histogram
+    state_words = 1      # int32 words per instance
+
+    def __init__(self, batch_size=None, device="cuda", seed=0, global_offset=0):
+        self._scalar = batch_size is None
+        self.batch_size = 1 if self._scalar else int(batch_size)
+        if self.batch_size < 0:
+            raise ValueError("batch_size must be >= 0")
+        self.device = _as_device(device)
+        _lib.lib()  # fail loudly if the CUDA library has not been built
+        if self.device.type != "cuda" and not _lib.is_hostsim():
+            raise RuntimeError("gym_pomdp_b200 runs on CUDA devices only (no CPU path); got device=%r" % (device,))
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._step_ctr = 0
+        self.global_offset = int(global_offset)   # index of instance 0 in the global batch (multi-GPU shards)
+        self.state = None
+        self.flags = None
+        self.done = False if self._scalar else None
+        self.last_action = None
+
+    # ------------------------------------------------------------------ plumbing ----
+    def _stream(self):
+        return _lib.stream_handle(self.device)
+
+    def _next_ctr(self):
+        self._step_ctr = (self._step_ctr + 1) & 0xFFFFFFFF
+        return self._step_ctr
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _guard(self):
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else _NullCtx()
+
+    # subclasses: raw C calls on tensors --------------------------------------------
+    def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
+        raise NotImplementedError
+
+    def _c_reset(self, state, obs, mask, n, ctr):
+        raise NotImplementedError
+
+    # subclasses: scalar-mode conversions -------------------------------------------
+    def _state_to_ref(self, words):
+        raise NotImplementedError
+
+    def _state_from_ref(self, ref_state):
+        raise NotImplementedError
+
+    def _reward_to_py(self, reward, action):
+        return float(reward)
+
+    def _raise_for_flags(self, flags):
+        if flags & _lib.FLAG_BAD_STATE:
+            raise AssertionError("state outside the environment's domain")
+
+    # -------------------------------------------------------- functional interface ---
+    def simulate(self, state, action, out=None, step_ctr=None):
+        """G(s, a): one transition for every particle.
+
+        state int32[n, words] (or [n] when words == 1), action int32[n].  Returns
+        (next_state, obs, reward, flags); ``out`` may supply those four tensors
+        (``out[0]`` may be ``state`` itself for an in-place step).
+        """
+        n = action.shape[0]
+        if out is None:
+            out = (torch.empty_like(state), self._empty((n,), torch.int32), self._empty((n,), torch.float32),
+                   self._empty((n,), torch.int32))
+        next_state, obs, reward, flags = out
+        ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
+        with self._guard():
+            self._c_step(state, action, next_state, obs, reward, flags, n, ctr)
+        return next_state, obs, reward, flags
+
+    def init_states(self, n=None, out=None, mask=None, step_ctr=None):
+        """Batched ``_get_init_state``: fresh initial states (and the reset observation)."""
+        n = self.batch_size if n is None else int(n)
+        if out is None:
+            shape = (n, self.state_words) if self.state_words > 1 else (n,)
+            out = (self._empty(shape, torch.int32), self._empty((n,), torch.int32))
+        state, obs = out
+        ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
+        with self._guard():
+            self._c_reset(state, obs, mask, n, ctr)
+        return state, obs
+
+    # ------------------------------------------------------------------ gym surface ---
+    def seed(self, seed=None):
+        """The reference seeds numpy's global RNG (e.g. rock.py:120-121); here the seed keys
+        the stateless Philox stream and restarts the step counter."""
+        self._seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self._step_ctr = 0
+        return [seed]
+
+    def reset(self, mask=None):
+        if self.state is None or mask is None:
+            self.state, obs = self.init_states(self.batch_size)
+            self.flags = torch.zeros(self.batch_size, dtype=torch.int32, device=self.device)
+        else:
+            m = mask.to(device=self.device, dtype=torch.uint8)
+            obs = torch.zeros(self.batch_size, dtype=torch.int32, device=self.device)
+            self.init_states(self.batch_size, out=(self.state, obs), mask=m)
+            self.flags = torch.where(m.bool(), torch.zeros_like(self.flags), self.flags)
+        self._on_reset()
+        if self._scalar:
+            self.done = False
+            return int(obs[0].item())
+        return obs
+
+    def _on_reset(self):
+        pass
+
+    def step(self, action):
+        if self._scalar:
+            return self._step_scalar(action)
+        if self.state is None:
+            raise AssertionError("step() before reset()")
+        action = torch.as_tensor(action, device=self.device).to(torch.int32).contiguous()
+        if action.shape != (self.batch_size,):
+            raise ValueError("action must have shape (%d,), got %s" % (self.batch_size, tuple(action.shape)))
+        next_state, obs, reward, flags = self.simulate(self.state, action)
+        self.state, self.flags = next_state, flags
+        done = (flags & _lib.FLAG_DONE) != 0
+        return obs, reward, done, {"state": next_state, "flags": flags}
+
+    def _step_scalar(self, action):
+        # the reference's two asserts (rock.py:125-126 and siblings)
+        assert self.action_space.contains(action)
+        assert self.done is False
+        if self.state is None:
+            raise AttributeError("%s has no state: call reset() first" % type(self).__name__)
+        a = torch.tensor([int(action)], dtype=torch.int32, device=self.device)
+        next_state, obs, reward, flags = self.simulate(self.state, a)
+        fl = int(flags[0].item())
+        self._raise_for_flags(fl)
+        self.state, self.flags = next_state, flags
+        self.last_action = int(action)
+        self.done = bool(fl & _lib.FLAG_DONE)
+        ob = int(obs[0].item())
+        self._after_scalar_step(int(action), ob)
+        return ob, self._reward_to_py(float(reward[0].item()), int(action)), self.done, {"state": self._info_state()}
+
+    def _after_scalar_step(self, action, ob):
+        pass
+
+    def _info_state(self):
+        return self._state_to_ref(self.state[0])
+
+    def _set_state(self, state):
+        """Batched: packed int32 tensor (copied).  Scalar: the reference's own state format."""
+        if self._scalar:
+            self.done = False
+            self.state = self._state_from_ref(state)
+        else:
+            state = torch.as_tensor(state, device=self.device).to(torch.int32)
+            expect = (self.batch_size, self.state_words) if self.state_words > 1 else (self.batch_size,)
+            if tuple(state.shape) != expect:
+                raise ValueError("state must have shape %s, got %s" % (expect, tuple(state.shape)))
+            self.state = state.clone().contiguous()
+        self.flags = torch.zeros(self.batch_size, dtype=torch.int32, device=self.device)
+
+    def _get_init_state(self):
+        state, _ = self.init_states(self.batch_size)
+        if self._scalar:
+            return self._state_to_ref(state[0])
+        return state
+
+    def render(self, mode="ansi", close=False):
+        if close:
+            return
+        if self._scalar and self.state is not None:
+            print(type(self).__name__, self._info_state())
+
+    def close(self):
+        return
+
+    # ------------------------------------------------------------- belief histogram ---
+    def _hist_args(self):
+        raise NotImplementedError
+
+    def belief_histogram(self, state=None, all_reduce=False):
+        """int64 counts over the particle set (bins: include/pomdp_b200.h); with
+        ``all_reduce`` the counts are summed over all ranks of the default process group
+        (NCCL on GPUs) -- the only collective on the path."""
+        state = self.state if state is None else state
+        p0, p1 = self._hist_args()
+        L = _lib.lib()
+        bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
+        hist = torch.zeros(bins, dtype=torch.int64, device=self.device)
+        n = state.shape[0]
+        with self._guard():
+            _lib.check(L.pomdp_belief_hist(self.kind, p0, p1, _lib.ptr(state), self.state_words, n, _lib.ptr(hist),
+                                           self._stream()), "pomdp_belief_hist")
+        if all_reduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        return hist
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,157 @@
+"""BattleShip on the GPU: host side of ``pomdp_battleship_step`` / ``pomdp_battleship_reset``.
+
+Stands in for gym_pomdp/envs/battleship.py ``BattleShipEnv`` (64-211).  Packed state: 8
+int32 words per board -- words 0-3 occupied bits (cell c = x_size*y + x, i.e. the action
+index), word 3 bits 24-30 ``total_remaining`` and bit 31 done, words 4-7 visited bits.
+Unlike the reference (battleship.py:11 "TODO fix state", 124-126) the board travels WITH
+the state, so ``_set_state`` restores a consistent game.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..geometry import Grid
+from ..spaces import Discrete
+from .base import BatchedPomdpEnv
+
+
+class ShipState(object):
+    """battleship.py:40-43, plus the board the reference keeps in ``env.grid``."""
+
+    def __init__(self):
+        self.ships = []
+        self.total_remaining = 0
+        self.occupied = None   # bool [x_size, y_size]
+        self.visited = None
+
+
+class BattleShipEnv(BatchedPomdpEnv):
+    kind = _lib.KIND_BATTLESHIP
+    state_words = 8
+
+    def __init__(self, board_size=(5, 5), max_len=3, batch_size=None, device="cuda", seed=0, global_offset=0,
+                 reset_mode="scan"):
+        super().__init__(batch_size, device, seed, global_offset)
+        self.grid = Grid(*board_size)
+        self._params = _lib.BattleshipParams(board_size[0], board_size[1], max_len, 0)
+        self.action_space = Discrete(self.grid.n_tiles)
+        self.observation_space = Discrete(2)
+        self.num_obs = 2
+        self._reward_range = self.action_space.n / 4.
+        self._discount = 1.
+        self.total_remaining = max_len - 1      # battleship.py:74 (an env attribute the reference only asserts on)
+        self.max_len = max_len + 1              # battleship.py:75
+        if reset_mode not in ("scan", "rejection"):
+            raise ValueError("reset_mode must be 'scan' (warp per env) or 'rejection' (the reference's loop)")
+        self.reset_mode = reset_mode
+        self.reset_flags = None
+        self.t = 0
+        self.tot_rw = 0
+
+    def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
+        _lib.check(_lib.lib().pomdp_battleship_step(
+            ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state), _lib.ptr(obs),
+            _lib.ptr(reward), _lib.ptr(flags), n, self._stream()), "pomdp_battleship_step")
+
+    def _c_reset(self, state, obs, mask, n, ctr):
+        L = _lib.lib()
+        fn = L.pomdp_battleship_reset if self.reset_mode == "scan" else L.pomdp_battleship_reset_rejection
+        self.reset_flags = torch.zeros(n, dtype=torch.int32, device=self.device)
+        _lib.check(fn(ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(obs), _lib.ptr(self.reset_flags),
+                      _lib.ptr(mask), n, self.global_offset, self._seed, ctr, self._stream()), "pomdp_battleship_reset")
+
+    def _hist_args(self):
+        return self.grid.n_tiles, 0
+
+    # ---------------------------------------------------------------------- codec ---
+    def pack(self, occupied, visited, total_remaining=None, done=None):
+        """occupied / visited bool [n, x_size, y_size] -> packed int32 [n, 8]."""
+        occ = torch.as_tensor(occupied, device=self.device).bool()
+        vis = torch.as_tensor(visited, device=self.device).bool()
+        n = occ.shape[0]
+        # cell c = x_size * y + x  ->  flatten in (y, x) order
+        occ_c = occ.permute(0, 2, 1).reshape(n, -1).to(torch.int64)
+        vis_c = vis.permute(0, 2, 1).reshape(n, -1).to(torch.int64)
+        words = torch.zeros((n, 8), dtype=torch.int64, device=self.device)
+        for c in range(self.grid.n_tiles):
+            words[:, c >> 5] |= occ_c[:, c] << (c & 31)
+            words[:, 4 + (c >> 5)] |= vis_c[:, c] << (c & 31)
+        rem = (occ_c * (1 - vis_c)).sum(dim=1) if total_remaining is None else \
+            torch.as_tensor(total_remaining, device=self.device).to(torch.int64)
+        words[:, 3] |= (rem & 0x7F) << 24
+        if done is not None:
+            words[:, 3] |= torch.as_tensor(done, device=self.device).to(torch.int64) << 31
+        return ((words + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)
+
+    def unpack(self, words):
+        """packed -> (occupied[n, X, Y], visited[n, X, Y], total_remaining[n], done[n])"""
+        w = words.to(torch.int64) & 0xFFFFFFFF
+        n = w.shape[0]
+        c = torch.arange(self.grid.n_tiles, device=words.device)
+        occ_c = (w[:, (c >> 5)] >> (c & 31)) & 1
+        vis_c = (w[:, 4 + (c >> 5)] >> (c & 31)) & 1
+        X, Y = self.grid.x_size, self.grid.y_size
+        occ = occ_c.reshape(n, Y, X).permute(0, 2, 1).bool()
+        vis = vis_c.reshape(n, Y, X).permute(0, 2, 1).bool()
+        return occ, vis, ((w[:, 3] >> 24) & 0x7F).to(torch.int32), ((w[:, 3] >> 31) & 1).bool()
+
+    # ---------------------------------------------------------------- scalar mode ---
+    def _on_reset(self):
+        self.tot_rw = 0
+        self.t = 0
+        self.last_action = -1
+
+    def _state_to_ref(self, words):
+        occ, vis, rem, _ = self.unpack(words.reshape(1, 8))
+        st = ShipState()
+        st.total_remaining = int(rem[0])
+        st.occupied = occ[0].cpu().numpy()
+        st.visited = vis[0].cpu().numpy()
+        return st
+
+    def _state_from_ref(self, state):
+        return self.pack(np.asarray(state.occupied)[None], np.asarray(state.visited)[None],
+                         total_remaining=[state.total_remaining])
+
+    def _reward_to_py(self, reward, action):
+        return int(reward)
+
+    def _after_scalar_step(self, action, ob):
+        self.t += 1
+
+    def _step_scalar(self, action):
+        out = super()._step_scalar(action)
+        self.tot_rw += out[1]
+        return out
+
+    def _generate_legal(self, state=None):
+        """battleship.py:157-165: the unvisited cells."""
+        words = self.state if state is None else state
+        _, vis, _, _ = self.unpack(words.reshape(-1, 8))
+        n = vis.shape[0]
+        unvisited = ~vis.permute(0, 2, 1).reshape(n, -1)       # action index = x_size * y + x
+        if self._scalar and state is None:
+            return [int(a) for a in torch.nonzero(unvisited[0])[:, 0]]
+        return unvisited
+
+    def _generate_preferred(self, history):
+        return self._generate_legal()
+
+    def _compute_prob(self, action, next_state, ob):
+        """battleship.py:80-89"""
+        if self._scalar:
+            x, y = self.grid.get_coord(action)
+            if ob == 0 and next_state.visited[x][y]:
+                return 1
+            if ob == 1 and next_state.occupied[x][y]:
+                return 1
+            return int(ob == 0)
+        occ, vis, _, _ = self.unpack(next_state)
+        n = occ.shape[0]
+        action = torch.as_tensor(action, device=next_state.device).long()
+        ob = torch.as_tensor(ob, device=next_state.device).long()
+        occ_a = torch.gather(occ.permute(0, 2, 1).reshape(n, -1), 1, action[:, None])[:, 0]
+        vis_a = torch.gather(vis.permute(0, 2, 1).reshape(n, -1), 1, action[:, None])[:, 0]
+        return (((ob == 0) & vis_a) | ((ob == 1) & occ_a) | (ob == 0)).double()

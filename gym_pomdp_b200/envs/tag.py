@@ -1,0 +1,153 @@
+"""Tag on the GPU: host side of ``pomdp_tag_step`` / ``pomdp_tag_reset``.
+
+Stands in for gym_pomdp/envs/tag.py ``TagEnv`` (84-280).  Packed state: bits 0-4 agent
+cell, 5 bits per opponent cell from bit 5, bits 25-30 ``num_opp`` (signed), bit 31 done.
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from ..geometry import TagGrid
+from ..spaces import Discrete
+from .base import BatchedPomdpEnv
+
+TAG = 4  # tag.py:28-33
+
+
+class TagState(object):
+    """tag.py:284-291"""
+
+    def __init__(self, coord):
+        self.agent_pos = coord
+        self.opponent_pos = []
+        self.num_opp = 0
+
+    def __str__(self):
+        return str(len(self.opponent_pos))
+
+
+class TagEnv(BatchedPomdpEnv):
+    kind = _lib.KIND_TAG
+
+    def __init__(self, num_opponents=1, move_prob=.8, obs_cells=29, board_size=(10, 5), batch_size=None,
+                 device="cuda", seed=0, global_offset=0):
+        super().__init__(batch_size, device, seed, global_offset)
+        if obs_cells != 29 or tuple(board_size) != (10, 5):
+            # TagGrid hard-codes the 29-cell board whatever these say (tag.py:46-66)
+            raise ValueError("the Tag board is the reference's fixed 29-cell one")
+        self.num_opponents = num_opponents
+        self.move_prob = move_prob
+        self._params = _lib.TagParams(num_opponents, 0, float(move_prob))
+        self._reward_range = 10 * num_opponents
+        self._discount = .95
+        self.action_space = Discrete(5)
+        self.grid = TagGrid(board_size, obs_cells=obs_cells)
+        self.observation_space = Discrete(self.grid.n_tiles + 1)
+        self.time = 0
+        if not 1 <= num_opponents <= 4:
+            raise ValueError("num_opponents must be in 1..4")
+
+    def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
+        _lib.check(_lib.lib().pomdp_tag_step(
+            ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state), _lib.ptr(obs),
+            _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, self._stream()), "pomdp_tag_step")
+
+    def _c_reset(self, state, obs, mask, n, ctr):
+        _lib.check(_lib.lib().pomdp_tag_reset(
+            ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(obs), _lib.ptr(mask), n, self.global_offset,
+            self._seed, ctr, self._stream()), "pomdp_tag_reset")
+
+    def _hist_args(self):
+        return 0, 0
+
+    # ---------------------------------------------------------------------- codec ---
+    def pack(self, agent, opp, num_opp=None, done=None):
+        """agent int[n] cell ids, opp int[n, num_opponents] -> packed int32[n]."""
+        agent = torch.as_tensor(agent, device=self.device).to(torch.int64)
+        opp = torch.as_tensor(opp, device=self.device).to(torch.int64).reshape(agent.shape[0], -1)
+        v = agent.clone()
+        for j in range(self.num_opponents):
+            v |= opp[:, j] << (5 + 5 * j)
+        nop = torch.full_like(agent, self.num_opponents) if num_opp is None else \
+            torch.as_tensor(num_opp, device=self.device).to(torch.int64)
+        v |= (nop & 63) << 25
+        if done is not None:
+            v |= torch.as_tensor(done, device=self.device).to(torch.int64) << 31
+        return ((v + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)
+
+    def unpack(self, words):
+        """packed -> (agent[n], opp[n, num_opponents], num_opp[n], done[n])"""
+        v = words.to(torch.int64) & 0xFFFFFFFF
+        agent = v & 31
+        opp = torch.stack([(v >> (5 + 5 * j)) & 31 for j in range(self.num_opponents)], dim=1)
+        nop = (v >> 25) & 63
+        nop = torch.where(nop >= 32, nop - 64, nop)
+        return agent.to(torch.int32), opp.to(torch.int32), nop.to(torch.int32), ((v >> 31) & 1).bool()
+
+    def encode_array(self, words):
+        """int32 ``[agent_idx, opp_idx...]`` rows, the reference's ``_encode_state`` (tag.py:158-165)."""
+        agent, opp, _, _ = self.unpack(words)
+        return torch.cat([agent[:, None], opp], dim=1)
+
+    def decode_array(self, arr):
+        """inverse of ``encode_array`` (tag.py:167-179: every opponent with idx > -1 counts)."""
+        arr = torch.as_tensor(arr, device=self.device).to(torch.int64).reshape(-1, 1 + self.num_opponents)
+        return self.pack(arr[:, 0], arr[:, 1:], num_opp=(arr[:, 1:] > -1).sum(dim=1))
+
+    # ---------------------------------------------------------------- scalar mode ---
+    def _on_reset(self):
+        self.time = 0
+        self.last_action = 4
+
+    def _state_to_ref(self, words):
+        agent, opp, nop, _ = self.unpack(words.reshape(1))
+        st = TagState(self.grid.get_tag_coord(int(agent[0])))
+        st.opponent_pos = [self.grid.get_tag_coord(int(o)) for o in opp[0]]
+        st.num_opp = int(nop[0])
+        return st
+
+    def _state_from_ref(self, state):
+        agent = [self.grid.get_index(state.agent_pos)]
+        opp = [[self.grid.get_index(o) for o in state.opponent_pos]]
+        return self.pack(agent, opp, num_opp=[state.num_opp])
+
+    def _after_scalar_step(self, action, ob):
+        self.time += 1
+
+    def _generate_legal(self, state=None):
+        """tag.py:228-229"""
+        if self._scalar and state is None:
+            return list(range(self.action_space.n))
+        n = (self.state if state is None else state).shape[0]
+        return torch.ones((n, 5), dtype=torch.bool, device=self.device)
+
+    def _generate_preferred(self, history):
+        """tag.py:231-243 (scalar mode)"""
+        if not self._scalar:
+            raise NotImplementedError("history-dependent heuristics are host-side, single-instance only")
+        if history.size == 0:
+            return self._generate_legal()
+        st = self._info_state()
+        if history[-1].ob == self.grid.n_tiles and self.grid.is_corner(st.agent_pos):
+            return [TAG]
+        from ..geometry import Moves
+        actions = [d for d in range(4) if history[-1].action != self.grid.opposite(d)
+                   and self.grid.is_inside(st.agent_pos + Moves.get_coord(d))]
+        assert len(actions) > 0
+        return actions
+
+    def _compute_prob(self, action, next_state, ob):
+        """tag.py:209-217"""
+        if self._scalar:
+            p_ob = int(ob == self.grid.get_index(next_state.agent_pos))
+            if ob == self.grid.n_tiles:
+                for opp_pos in next_state.opponent_pos:
+                    if opp_pos == next_state.agent_pos:
+                        return 1.
+            return p_ob
+        agent, opp, _, _ = self.unpack(next_state)
+        ob = torch.as_tensor(ob, device=next_state.device).to(torch.int32)
+        same = (opp == agent[:, None]).any(dim=1)
+        return torch.where((ob == self.grid.n_tiles) & same, torch.ones_like(ob, dtype=torch.float64),
+                           (ob == agent).double())

@@ -1,0 +1,239 @@
+/*
+ * pomdp_b200.h -- C ABI of libpomdp_b200.so: batched step()/reset() generative models of
+ * d3sm0/gym_pomdp's RockSample, Tag, BattleShip, Tiger and Network environments as
+ * hand-written CUDA kernels for sm_100a (NVIDIA B200).
+ *
+ * The reference has no FFI / plugin layer at all (100 % Python).  Its
+ * boundary is the old-gym Env protocol
+ *      reset() -> ob ;  step(a) -> (ob, reward, done, {"state": s})
+ * implemented per env in gym_pomdp/envs/{rock,tag,battleship,tiger,network}.py.  Each
+ * entry point below replaces ONE of those Python methods for a whole batch of independent
+ * env instances ("particles"); the citation on each function is the reference method it
+ * stands in for.  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add.
+ *
+ * Conventions (all entry points)
+ * ------------------------------
+ *  - Plain pointers and sizes only; every array pointer is DEVICE memory owned by the
+ *    caller (torch tensors on the Python side).  The library never allocates, frees or
+ *    keeps a pointer past the call's stream ordering.  `params` structs are HOST memory,
+ *    read during the call only.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous on it.  The caller selects the device (cudaSetDevice / torch device
+ *    guard) -- pointers, stream and current device must agree.
+ *  - Return value: 0 on success, otherwise a cudaError_t value or one of the POMDP_E_*
+ *    codes below; pomdp_last_error() gives a thread-local message.  No C++ exceptions
+ *    cross the ABI.
+ *  - State is `words` int32 per env, row-major [n, words] (layout per env below).
+ *    `next_state` may alias `state` (in-place step).  obs / flags are int32[n], reward is
+ *    float[n].
+ *  - flags[i]: bit 0 POMDP_FLAG_DONE (the reference's `done`), and the batched stand-ins
+ *    for the reference's hot-path asserts (rock.py:125-126, tag.py:109-110,
+ *    battleship.py:93-95, tiger.py:74-75, network.py:73-74), which cannot raise per
+ *    element: POMDP_FLAG_BAD_ACTION (action not in action_space), POMDP_FLAG_STEPPED_DONE
+ *    (state already terminal), POMDP_FLAG_BAD_STATE (state outside the env's domain, e.g.
+ *    Rock(15,15)'s dangling grid id at (12,2), where the reference raises IndexError).
+ *    An env with an error flag is left unchanged with obs 0 and reward 0 (BAD_STATE on a
+ *    Rock sample is treated as "no rock here").
+ *  - Randomness: stateless Philox4x32-10.  The word for draw slot j of env i is
+ *        philox(key = seed, ctr = (lo32(g), hi32(g), step_ctr, (domain<<24) | (j>>2)))[j&3]
+ *    with g = global_offset + i, domain 0 for step and 1 for reset.  Results therefore do
+ *    not depend on how a batch is sharded across GPUs.  Slot tables and the word->decision
+ *    rules (u = r / 2^32;  binomial(1,p) = [u < p];  randint(n) = floor(u*n)) are listed
+ *    per env in DESIGN.md and mirror the reference's np.random call sites.
+ *  - No CPU fallback: every compute entry point launches CUDA kernels and fails with a
+ *    CUDA error when no device is present.
+ */
+#ifndef POMDP_B200_H
+#define POMDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POMDP_ABI_VERSION 1
+
+#define POMDP_FLAG_DONE          1
+#define POMDP_FLAG_BAD_ACTION    2
+#define POMDP_FLAG_STEPPED_DONE  4
+#define POMDP_FLAG_BAD_STATE     8
+
+#define POMDP_E_BADARG   (-1)   /* null pointer, negative n, unsupported configuration */
+#define POMDP_E_ALIGN    (-2)   /* a pointer is not 4-byte aligned */
+
+int pomdp_abi_version(void);
+const char* pomdp_last_error(void);
+
+/* ------------------------------------------------------------------ RockSample ---- */
+/* rock.py:99-118 (RockEnv.__init__), rock.py:429-432 (StochasticRockEnv.__init__).     */
+typedef struct PomdpRockParams {
+    int32_t board_size;   /* key of rock.config: 2, 4, 7, 11 or 15                      */
+    int32_t num_rocks;    /* must be a member of config[board_size]['size'] (rock.py:101)*/
+    int32_t stochastic;   /* 0 = RockEnv, 1 = StochasticRockEnv                         */
+    int32_t reserved;
+    double  p_move;       /* StochasticRockEnv p_move (rock.py:429); ignored otherwise   */
+} PomdpRockParams;
+
+/* State layout: 1 word if num_rocks <= 11 else 2 (little-endian 64-bit).
+ *   bits 0-3 agent x, bits 4-7 agent y, bits 8+2i..9+2i rock i status as a 2-bit two's
+ *   complement code (0b11 = -1 bad, 0b00 = 0 collected, 0b01 = +1 good), top bit = done. */
+int     pomdp_rock_state_words(const PomdpRockParams* params);
+/* Static per-config maps (rock-id grid, rock coordinates, sensor thresholds) that the
+ * kernels stage into shared memory with one TMA bulk copy per block.  The caller uploads
+ * the filled buffer to the device (16-byte aligned) and passes it as `d_table`.          */
+int64_t pomdp_rock_table_bytes(void);
+int     pomdp_rock_build_table(const PomdpRockParams* params, void* host_table);
+/* RockEnv.step rock.py:123-194 / StochasticRockEnv.step rock.py:434-504.
+ * Draw slots: 0 = p_move gate (stochastic only), 1 = sensor Bernoulli (rock.py:404).     */
+int pomdp_rock_step(const PomdpRockParams* params, const void* d_table,
+                    const int32_t* state, const int32_t* action,
+                    int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                    int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                    void* stream);
+/* RockEnv.reset rock.py:236-241 (+ _get_init_state 266-271, Rock.__init__ 78-80).
+ * Draw slot i = rock i.  `mask` (device, uint8[n]) may be NULL = reset all; otherwise only
+ * envs with mask[i] != 0 are reset (the others keep state and get obs untouched).        */
+int pomdp_rock_reset(const PomdpRockParams* params, const void* d_table,
+                     int32_t* state, int32_t* obs, const uint8_t* mask,
+                     int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                     void* stream);
+
+/* ------------------------------------------------------------------------- Tag ---- */
+/* tag.py:87-95 (TagEnv.__init__).  The board is the fixed 29-cell one (tag.py:46-66).  */
+typedef struct PomdpTagParams {
+    int32_t num_opponents;  /* 1..4 */
+    int32_t reserved;
+    double  move_prob;      /* tag.py:87 */
+} PomdpTagParams;
+/* State: 1 word.  bits 0-4 agent cell, bits 5+5j..9+5j opponent j's cell (0..28),
+ * bits 25-30 num_opp (6-bit two's complement; the reference lets it go negative with
+ * several opponents), bit 31 done.                                                       */
+/* TagEnv.step tag.py:108-143 (+ move_opponent 201-207, _admissable_actions 260-280,
+ * _sample_ob 219-226).  Draw slots per opponent j: 2j = move Bernoulli, 2j+1 = choice.   */
+int pomdp_tag_step(const PomdpTagParams* params,
+                   const int32_t* state, const int32_t* action,
+                   int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                   int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                   void* stream);
+/* TagEnv.reset tag.py:97-102 (+ _get_init_state 181-193).  Slot 0 agent, 1+j opponent j. */
+int pomdp_tag_reset(const PomdpTagParams* params,
+                    int32_t* state, int32_t* obs, const uint8_t* mask,
+                    int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                    void* stream);
+
+/* ------------------------------------------------------------------ BattleShip ---- */
+/* battleship.py:67-75 (BattleShipEnv.__init__).                                        */
+typedef struct PomdpBattleshipParams {
+    int32_t x_size, y_size;   /* board_size; x_size * y_size <= 120 */
+    int32_t max_len;          /* ships of length max_len .. 2 (battleship.py:74-75,171) */
+    int32_t reserved;
+} PomdpBattleshipParams;
+/* State: 8 words per env.  Cell c = x_size*y + x (the action index, coord.py:64-66).
+ *   words 0-3: occupied bit c (bits 0..119); word 3 bits 24-30 total_remaining, bit 31 done
+ *   words 4-7: visited bit c.                                                            */
+/* BattleShipEnv.step battleship.py:91-122.  No draws.                                   */
+int pomdp_battleship_step(const PomdpBattleshipParams* params,
+                          const int32_t* state, const int32_t* action,
+                          int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                          int64_t n, void* stream);
+/* BattleShipEnv.reset battleship.py:131-137 (+ _get_init_state 167-180, collision 195-211,
+ * mark_ship 182-193).  One WARP per env: the warp enumerates all 4*n_tiles (pos, dir)
+ * candidates with the reference's collision rule, and ship s takes the k-th accepted one,
+ * k = floor(u * count) from draw slot s -- the same distribution as the reference's
+ * rejection loop, in fixed time.  POMDP_FLAG_BAD_STATE is raised in flags (may be NULL)
+ * when no placement exists (the reference would spin forever).                           */
+int pomdp_battleship_reset(const PomdpBattleshipParams* params,
+                           int32_t* state, int32_t* obs, int32_t* flags, const uint8_t* mask,
+                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                           void* stream);
+/* Same method, thread per env, literally the reference's rejection loop: attempt a uses
+ * slot 2a = randint(n_tiles), 2a+1 = randint(4).  Exists so that reset can be checked
+ * element-wise against the reference under a coupled draw stream.                        */
+int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* params,
+                           int32_t* state, int32_t* obs, int32_t* flags, const uint8_t* mask,
+                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                           void* stream);
+
+/* ----------------------------------------------------------------------- Tiger ---- */
+typedef struct PomdpTigerParams {
+    double listen_prob;  /* tiger.py:141: _sample_ob's default .85 (self.correct_prob is unused there) */
+} PomdpTigerParams;
+/* State: 1 word, bit 0 = tiger door, bit 31 done.
+ * TigerEnv.step tiger.py:72-88.  Slot 0 = state resample (actions 0/1), slot 1 = uniform. */
+int pomdp_tiger_step(const PomdpTigerParams* params,
+                     const int32_t* state, const int32_t* action,
+                     int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                     int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                     void* stream);
+/* TigerEnv.reset tiger.py:60-66.  Slot 0 = state.  obs = 2 (NULL).                       */
+int pomdp_tiger_reset(const PomdpTigerParams* params,
+                      int32_t* state, int32_t* obs, const uint8_t* mask,
+                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                      void* stream);
+
+/* --------------------------------------------------------------------- Network ---- */
+/* network.py:27-38.                                                                    */
+typedef struct PomdpNetworkParams {
+    int32_t n_machines;     /* <= 30; 3-legs needs n >= 4 and n % 3 == 1 (network.py:155)*/
+    int32_t problem_type;   /* 3 = make_3legs_neighbours, else make_ring_neighbours      */
+    double  p, q, p_ob;     /* .1, .33, .95 (network.py:28-29, 57-59)                    */
+} PomdpNetworkParams;
+/* State: 1 word, bit m = machine m is up; bit 31 done (never set: network.py never ends).
+ * NetworkEnv.step network.py:71-114.  Slot m = machine m's failure draw, slot n = the
+ * action's observation draw.  reward is float32 of (tenths / 10).                         */
+int pomdp_network_step(const PomdpNetworkParams* params,
+                       const int32_t* state, const int32_t* action,
+                       int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                       void* stream);
+/* NetworkEnv.reset network.py:61-69: all machines up, obs = 0 (OFF).                     */
+int pomdp_network_reset(const PomdpNetworkParams* params,
+                        int32_t* state, int32_t* obs, const uint8_t* mask,
+                        int64_t n, void* stream);
+
+/* ------------------------------------------------------------ Grid / Coord helpers --- */
+/* coord.py:7-114 and tag.py:36-66 as batched device functions (bit-exact integer work).
+ * Coordinates travel as int32 pairs (x, y), i.e. arrays shaped [n, 2].
+ *   POMDP_COORD_GET_INDEX : a = coords[n,2]            -> out[n]   = x_size*y + x  (coord.py:58-59)
+ *   POMDP_COORD_GET_COORD : a = idx[n]                 -> out[n,2] = (idx % x_size, idx / x_size) (coord.py:64-66)
+ *   POMDP_COORD_IS_INSIDE : a = coords[n,2]            -> out[n]   = Grid.is_inside (coord.py:61-62, 18-19)
+ *   POMDP_COORD_ADD_MOVE  : a = coords[n,2], b = m[n]  -> out[n,2] = Coord + Moves.get_coord(m) (coord.py:10-13, 101-110)
+ *   POMDP_COORD_L1        : a, b = coords[n,2]         -> out[n]   = |dx| + |dy| (Grid.euclidean_distance is the
+ *                                                                     1-norm, coord.py:79-81)
+ *   POMDP_COORD_TAG_GET_INDEX / TAG_GET_COORD / TAG_IS_INSIDE : TagGrid versions (tag.py:46-66);
+ *                           TAG_GET_INDEX returns -1 where the reference's asserts would fire.
+ * `b` may be NULL for the one-operand ops.                                                 */
+#define POMDP_COORD_GET_INDEX      0
+#define POMDP_COORD_GET_COORD      1
+#define POMDP_COORD_IS_INSIDE      2
+#define POMDP_COORD_ADD_MOVE       3
+#define POMDP_COORD_L1             4
+#define POMDP_COORD_TAG_GET_INDEX  5
+#define POMDP_COORD_TAG_GET_COORD  6
+#define POMDP_COORD_TAG_IS_INSIDE  7
+int pomdp_coord_op(int32_t op, int32_t x_size, int32_t y_size,
+                   const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void* stream);
+
+/* ----------------------------------------------------------- belief histogram ------ */
+/* Per-shard counts over a batch of packed states, accumulated into int64 hist[bins]
+ * (the caller zeroes it and all-reduces it across GPUs with NCCL).  No reference
+ * counterpart; bins per env are listed in DESIGN.md:
+ *   kind 0 Rock      : [0,k) rocks still good (status +1), then 256 agent cells (x | y<<4)
+ *   kind 1 Tag       : 29 agent cells then 29 opponent-0 cells
+ *   kind 2 BattleShip: x_size*y_size occupied counts
+ *   kind 3 Tiger     : 2 ;  kind 4 Network: n_machines up counts                          */
+#define POMDP_KIND_ROCK 0
+#define POMDP_KIND_TAG 1
+#define POMDP_KIND_BATTLESHIP 2
+#define POMDP_KIND_TIGER 3
+#define POMDP_KIND_NETWORK 4
+int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1);
+int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
+                      int64_t n, long long* hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POMDP_B200_H */

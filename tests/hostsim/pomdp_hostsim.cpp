@@ -1,0 +1,265 @@
+// pomdp_hostsim.cpp -- TEST VEHICLE, NOT A PRODUCT PATH.
+//
+// Compiles the per-env functors of gym_pomdp_b200/csrc/pomdp_core.h (the exact code the
+// CUDA kernels inline) with g++ and exports the C ABI of include/pomdp_b200.h over HOST
+// pointers, so that the packed-state logic can be checked against oracle/ in a container
+// that has no GPU (SURVEY.md §4 tier 5).  Only tests/ loads the resulting
+// tests/hostsim/libpomdp_hostsim.so; gym_pomdp_b200/ never does and has no CPU fallback.
+// What this cannot cover -- and what the `-m gpu` tests are for -- is everything in
+// pomdp_kernels.cu: the vector/TMA data movement, the warp-ballot placement scan, the
+// shared-memory histogram, launch geometry.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../gym_pomdp_b200/csrc/pomdp_core.h"
+#include "../../gym_pomdp_b200/csrc/pomdp_host.h"
+
+using namespace pomdp;
+
+namespace {
+template <typename S> S load_state(const int32_t* base, int64_t i);
+template <> uint32_t load_state<uint32_t>(const int32_t* base, int64_t i) { return (uint32_t)base[i]; }
+template <> uint64_t load_state<uint64_t>(const int32_t* base, int64_t i) {
+    return (uint32_t)base[2 * i] | ((uint64_t)(uint32_t)base[2 * i + 1] << 32);
+}
+void store_state(int32_t* base, int64_t i, uint32_t s) { base[i] = (int32_t)s; }
+void store_state(int32_t* base, int64_t i, uint64_t s) { base[2 * i] = (int32_t)(uint32_t)s; base[2 * i + 1] = (int32_t)(s >> 32); }
+
+template <typename S>
+int rock_step_host(const RockDev& d, const RockTable* t, const int32_t* state, const int32_t* action, int32_t* next,
+                   int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step) {
+    for (int64_t i = 0; i < n; ++i) {
+        S s2;
+        rock_step<S>(d, t, load_state<S>(state, i), action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        store_state(next, i, s2);
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int pomdp_abi_version(void) { return POMDP_ABI_VERSION; }
+const char* pomdp_last_error(void) { return host::err_buf(); }
+int pomdp_is_hostsim(void) { return 1; }   // lets tests assert which library they are talking to
+
+int pomdp_rock_state_words(const PomdpRockParams* q) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    return rc ? rc : host::rock_words(q);
+}
+int64_t pomdp_rock_table_bytes(void) { return (int64_t)sizeof(RockTable); }
+int pomdp_rock_build_table(const PomdpRockParams* q, void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "rock: host_table is NULL");
+    RockDev d;
+    return host::make_rock(q, &d, (RockTable*)host_table);
+}
+int pomdp_rock_step(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action,
+                    int32_t* next, int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed,
+                    uint32_t step, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    if (!table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    const RockTable* t = (const RockTable*)table;
+    return host::rock_words(q) == 1 ? rock_step_host<uint32_t>(d, t, state, action, next, obs, rw, fl, n, goff, seed, step)
+                                    : rock_step_host<uint64_t>(d, t, state, action, next, obs, rw, fl, n, goff, seed, step);
+}
+int pomdp_rock_reset(const PomdpRockParams* q, const void*, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
+                     int64_t goff, uint64_t seed, uint32_t step, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        if (host::rock_words(q) == 1) store_state(state, i, rock_reset<uint32_t>(d, seed, (uint64_t)(goff + i), step));
+        else store_state(state, i, rock_reset<uint64_t>(d, seed, (uint64_t)(goff + i), step));
+        if (obs) obs[i] = 0;
+    }
+    return 0;
+}
+
+int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
+                   float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t s2;
+        tag_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        next[i] = (int32_t)s2;
+    }
+    return 0;
+}
+int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
+                    uint64_t seed, uint32_t step, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        uint32_t s; int32_t ob;
+        tag_reset(d, seed, (uint64_t)(goff + i), step, s, ob);
+        state[i] = (int32_t)s;
+        if (obs) obs[i] = ob;
+    }
+    return 0;
+}
+
+int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
+                     float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t s2;
+        tiger_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        next[i] = (int32_t)s2;
+    }
+    return 0;
+}
+int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
+                      int64_t goff, uint64_t seed, uint32_t step, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        uint32_t s; int32_t ob;
+        tiger_reset(seed, (uint64_t)(goff + i), step, s, ob);
+        state[i] = (int32_t)s;
+        if (obs) obs[i] = ob;
+    }
+    return 0;
+}
+
+int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next,
+                       int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                       void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t s2;
+        network_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        next[i] = (int32_t)s2;
+    }
+    return 0;
+}
+int pomdp_network_reset(const PomdpNetworkParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        state[i] = (int32_t)((1u << d.n) - 1u);
+        if (obs) obs[i] = 0;
+    }
+    return 0;
+}
+
+int pomdp_battleship_step(const PomdpBattleshipParams* q, const int32_t* state, const int32_t* action, int32_t* next,
+                          int32_t* obs, float* rw, int32_t* fl, int64_t n, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t w[SHIP_WORDS], w2[SHIP_WORDS];
+        for (int k = 0; k < SHIP_WORDS; ++k) w[k] = (uint32_t)state[i * SHIP_WORDS + k];
+        battleship_step(d, w, action[i], w2, obs[i], rw[i], fl[i]);
+        for (int k = 0; k < SHIP_WORDS; ++k) next[i * SHIP_WORDS + k] = (int32_t)w2[k];
+    }
+    return 0;
+}
+// Serial stand-in for the warp scan: same candidate order, same k-th-accepted rule.
+int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                           const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        ShipState st;
+        st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+        bool ok_all = true;
+        int ship = 0;
+        for (int length = d.max_len; length >= 2 && ok_all; --length, ++ship) {
+            const U4 r = draw_block(seed, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)(ship >> 2));
+            const u128 blocked = ship_blocked(d, st.occ);
+            int total = 0;
+            for (int c = 0; c < 4 * d.n_tiles; ++c) total += ship_candidate_ok(d, blocked, c >> 2, c & 3, length);
+            if (total == 0) { ok_all = false; break; }
+            int k = (int)rand_below(word_of(r, ship & 3), (uint32_t)total);
+            for (int c = 0; c < 4 * d.n_tiles; ++c)
+                if (ship_candidate_ok(d, blocked, c >> 2, c & 3, length) && k-- == 0) { ship_mark(d, st, c >> 2, c & 3, length); break; }
+        }
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+        if (obs) obs[i] = 0;
+        if (flags) flags[i] = ok_all ? 0 : FLAG_BAD_STATE;
+    }
+    return 0;
+}
+int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                                     const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        ShipState st;
+        const bool ok = battleship_reset_rejection(d, seed, (uint64_t)(goff + i), step, st, 4096);
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+        if (obs) obs[i] = 0;
+        if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
+    }
+    return 0;
+}
+
+int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
+    for (int64_t i = 0; i < n; ++i) {
+        switch (op) {
+            case POMDP_COORD_GET_INDEX: out[i] = grid_get_index(xs, a[2 * i], a[2 * i + 1]); break;
+            case POMDP_COORD_GET_COORD: out[2 * i] = a[i] % xs; out[2 * i + 1] = a[i] / xs; break;
+            case POMDP_COORD_IS_INSIDE: out[i] = grid_is_inside(xs, ys, a[2 * i], a[2 * i + 1]); break;
+            case POMDP_COORD_ADD_MOVE: out[2 * i] = a[2 * i] + move_dx(b[i]); out[2 * i + 1] = a[2 * i + 1] + move_dy(b[i]); break;
+            case POMDP_COORD_L1: out[i] = l1_distance(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]); break;
+            case POMDP_COORD_TAG_GET_INDEX: out[i] = tag_is_inside(a[2 * i], a[2 * i + 1]) ? tag_get_index(a[2 * i], a[2 * i + 1]) : -1; break;
+            case POMDP_COORD_TAG_GET_COORD: {
+                int x = -1, y = -1;
+                if ((uint32_t)a[i] < (uint32_t)TAG_CELLS) tag_get_coord((uint32_t)a[i], x, y);
+                out[2 * i] = x; out[2 * i + 1] = y;
+                break;
+            }
+            case POMDP_COORD_TAG_IS_INSIDE: out[i] = tag_is_inside(a[2 * i], a[2 * i + 1]); break;
+            default: return host::fail(POMDP_E_BADARG, "coord: unknown op %d", op);
+        }
+    }
+    return 0;
+}
+
+int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1) { return host::hist_bins(kind, p0, p1); }
+int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                      long long* hist, void*) {
+    if (host::hist_bins(kind, p0, p1) <= 0) return host::fail(POMDP_E_BADARG, "belief_hist: bad kind");
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t s[SHIP_WORDS] = {0};
+        for (int k = 0; k < words && k < SHIP_WORDS; ++k) s[k] = (uint32_t)state[i * words + k];
+        belief_bins(kind, p0, p1, s, [&](int bin) { ++hist[bin]; });
+    }
+    return 0;
+}
+
+}  // extern "C"
