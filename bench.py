@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the RockSample(11,11) step() hot path, batch 2^22 per B200.
+
+    python bench.py [--gpus N --steps K --warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                   # CPU arm (oracle port, all host cores)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1: one rank per GPU
+
+A "step" is ONE pass of the hot path over one batch: one ``pomdp_rock_step`` launch that
+reads (state, action) for 2^22 env instances and writes (next_state, obs, reward, flags).
+Env instances are independent, so N GPUs = N index shards of a global batch of N * 2^22
+(weak scaling, no data-path collective; Philox is keyed by the GLOBAL env index).
+
+Prints one JSON line (rank 0).  Keys beyond the base contract: ``roofline``,
+``cpu_baseline``, ``e2e``, ``clocks``, ``gpu_launches``.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec RockSample(11,11) batch=2^22 per B200"
+UNIT = "env-steps/s"
+BYTES_PER_STEP = 24          # read state 4 + action 4, write next_state 4 + obs 4 + reward 4 + flags 4
+L2_BYTES = 126 * 2 ** 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--board", type=int, default=11)
+    ap.add_argument("--rocks", type=int, default=11)
+    ap.add_argument("--batch", type=int, default=1 << 22, help="env instances per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly through ctypes instead of a CUDA graph")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------- clocks ---
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except (ValueError, IndexError):
+            return local
+    return local
+
+
+# --------------------------------------------------------------------- reference arm ---
+def run_reference(args):
+    """The reference's algorithm on host cores: the oracle's Python port of rock.py:123-194,
+    every core stepping its own bounded sample per step (see oracle/cpu_baseline.py)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as C
+    procs = os.cpu_count() or 1
+    # bounded: the whole K+W run ~ 60 s at ~7e5 steps/s/core
+    count = max(2000, min(400000, int(60.0 * 7e5 / max(1, args.steps + args.warmup))))
+    arm = C.RockCpuArm(args.board, args.rocks, count, procs)
+    for _ in range(args.warmup):
+        arm.step()
+    total, t = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = arm.step()
+        total += n
+        t += dt
+    arm.close()
+    v = total / t
+    sample = "%d steps x %d procs x %d RockSample(%d,%d) (state, action) pairs per step, oracle.pomdp_oracle.rock_step" % (
+        args.steps, procs, count, args.board, args.rocks)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "RockSample(%d,%d) step(): synthetic (state, action) -> (next_state, obs, reward, flags)"
+                        % (args.board, args.rocks),
+            "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus,
+            "parallelism": "index-shard x%d (no collective)" % n_gpus,
+            "state_words": 1 if args.rocks <= 11 else 2,
+            "inputs": "x,y~U{0..n-1}, status~U{-1,0,1}, action~U{0..4+k}, seed 0x5EED"}
+
+
+# ------------------------------------------------------------------------- B200 arm ---
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import gym_pomdp_b200 as gp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- gym_pomdp_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    B, n, k = args.batch, args.board, args.rocks
+    K, W = args.steps, args.warmup
+
+    env = gp.make("Rock-v0", board_size=n, num_rocks=k, batch_size=B, device=dev, seed=0x5EED, global_offset=rank * B)
+    words = env.state_words
+    bytes_per_step = 8 * words + 16
+    set_bytes = B * bytes_per_step
+    # rotate through enough independent buffer sets that a launch never finds its inputs in L2
+    n_sets = max(2, -(-4 * L2_BYTES // set_bytes))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED + rank)
+    sets = []
+    for _ in range(n_sets):
+        x = torch.randint(0, n, (B,), generator=gen, device=dev)
+        y = torch.randint(0, n, (B,), generator=gen, device=dev)
+        status = torch.randint(-1, 2, (B, k), generator=gen, device=dev)
+        action = torch.randint(0, 5 + k, (B,), generator=gen, device=dev, dtype=torch.int32)
+        state = env.pack(x, y, status)
+        del x, y, status
+        out = (torch.empty_like(state), torch.empty(B, dtype=torch.int32, device=dev),
+               torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.int32, device=dev))
+        sets.append((state, action, out))
+
+    def launch(i):
+        s, a, o = sets[i % n_sets]
+        env.simulate(s, a, out=o, step_ctr=i + 1)
+
+    # warm-up (also loads the module, sizes the grid)
+    for i in range(max(W, 3) if args.no_graph else 3):
+        launch(i)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(dev)
+    graph_w = graph_t = None
+    if not args.no_graph:
+        # One CUDA graph holding exactly K step launches (and one with W for the warm-up):
+        # removes the Python/ctypes launch path from a ~20 us kernel's critical path.
+        with torch.cuda.stream(stream):
+            graph_w = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_w, stream=stream):
+                for i in range(max(W, 3)):
+                    launch(i)
+            graph_t = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_t, stream=stream):
+                for i in range(K):
+                    launch(i)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            if graph_t is not None:
+                graph_t.replay()
+            else:
+                for i in range(K):
+                    launch(i)
+            e1.record(stream)
+        return e0, e1
+
+    with torch.cuda.stream(stream):
+        if graph_w is not None:
+            graph_w.replay()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    e0, e1 = timed_region()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks_note = "sampled during the timed region"
+    if len(sampler.samples) < 5:
+        # the region is shorter than a few NVML polls: repeat the identical work (untimed) while sampling
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            timed_region()
+            torch.cuda.synchronize()
+        clocks_note = "timed region %.1f ms is shorter than 5 NVML polls; sampled over untimed repeats of it" % ms
+    sampler.stop()
+    clocks = sampler.summary()
+    clocks["note"] = clocks_note
+
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_gpus * B * K / (ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API ---------------
+    E = max(1, args.e2e_steps)
+    pin = dict(device="cpu", pin_memory=True)
+    s0, a0, _ = sets[0]
+    h_state, h_action = s0.cpu().pin_memory(), a0.cpu().pin_memory()
+    h_out = (torch.empty(s0.shape, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin),
+             torch.empty(B, dtype=torch.float32, **pin), torch.empty(B, dtype=torch.int32, **pin))
+    for i in range(3):
+        env.simulate_host(h_state, h_action, h_out, step_ctr=i + 1)
+    barrier()
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for i in range(E):
+        env.simulate_host(h_state, h_action, h_out, step_ctr=i + 1)
+    ee1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ee0.elapsed_time(ee1)
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n_gpus * B * E / (e2e_ms * 1e-3)
+    # sanity: the host result of the last e2e step equals the device path on the same inputs
+    chk = env.simulate(s0, a0, step_ctr=E)
+    assert torch.equal(chk[1].cpu(), h_out[1]) and torch.equal(chk[0].cpu(), h_out[0]), "e2e result != device result"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:  # noqa: BLE001
+        peak = 6650.0
+    per_launch_ms = ms / K
+    achieved = B * bytes_per_step / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
+                "algorithmic_bytes_per_launch": B * bytes_per_step, "avg_launch_us": per_launch_ms * 1e3,
+                "peak_source": peak_src,
+                "read_only_frac": (B * (4 * words + 4) / (per_launch_ms * 1e-3) / 1e9) / peak}
+
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cpu_baseline as C
+        procs = os.cpu_count() or 1
+        per_proc = max(20000, int(args.cpu_seconds * 7e5))
+        cpu = C.time_rock(n, k, per_proc, procs)
+        cpu = {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+
+    cfg = workload_config(args, n_gpus)
+    cfg["l2"] = "%d rotating buffer sets of %.0f MB (%.0f MB total) > 126 MB L2; no flush needed" % (
+        n_sets, set_bytes / 1e6, n_sets * set_bytes / 1e6)
+    cfg["launch"] = "eager ctypes launches" if args.no_graph else "one CUDA graph of K pomdp_rock_step launches"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": cfg,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (4 * words + 4),
+                "d2h_bytes_per_step": B * (4 * words + 12), "steps": E, "ms_per_step": e2e_ms / E,
+                "wall_ms_per_step": e2e_wall / E,
+                "path": "env.simulate_host: pinned host (state, action) -> 3-stream chunked H2D/kernel/D2H -> pinned host results"},
+        "clocks": clocks, "gpu_launches": K,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "rock_step_ncu_summary.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

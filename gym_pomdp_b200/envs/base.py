@@ -118,6 +118,49 @@ class BatchedPomdpEnv(object):
             self._c_reset(state, obs, mask, n, ctr)
         return state, obs
 
+    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20):
+        """G(s, a) on HOST buffers (pinned CPU tensors): what a numpy-holding caller of the
+        reference does.  The batch is cut into chunks that are copied in, stepped and copied
+        out on three rotating CUDA streams, so the H2D copy, the kernel and the D2H copy of
+        neighbouring chunks overlap (PCIe is full duplex).  ``out`` = (next_state, obs,
+        reward, flags) pinned CPU tensors.  Returns after all results have landed."""
+        n = action.shape[0]
+        ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
+        ws = self._host_ws(min(chunk, max(n, 1)))
+        base_off = self.global_offset
+        with self._guard():
+            cur = torch.cuda.current_stream(self.device)
+            for st in ws["streams"]:
+                st.wait_stream(cur)
+            for ci, lo in enumerate(range(0, n, ws["chunk"])):
+                hi = min(n, lo + ws["chunk"])
+                m = hi - lo
+                slot = ws["slots"][ci % len(ws["slots"])]
+                with torch.cuda.stream(ws["streams"][ci % len(ws["streams"])]):
+                    d = [b[:m] for b in slot]
+                    d[0].copy_(state[lo:hi], non_blocking=True)
+                    d[1].copy_(action[lo:hi], non_blocking=True)
+                    self.global_offset = base_off + lo
+                    self._c_step(d[0], d[1], d[2], d[3], d[4], d[5], m, ctr)
+                    for k in range(4):
+                        out[k][lo:hi].copy_(d[2 + k], non_blocking=True)
+            self.global_offset = base_off
+            for st in ws["streams"]:
+                cur.wait_stream(st)
+            cur.synchronize()
+        return out
+
+    def _host_ws(self, chunk):
+        ws = getattr(self, "_hws", None)
+        if ws is None or ws["chunk"] < chunk:
+            sshape = (chunk, self.state_words) if self.state_words > 1 else (chunk,)
+            slots = [(self._empty(sshape, torch.int32), self._empty((chunk,), torch.int32),
+                      self._empty(sshape, torch.int32), self._empty((chunk,), torch.int32),
+                      self._empty((chunk,), torch.float32), self._empty((chunk,), torch.int32)) for _ in range(3)]
+            ws = self._hws = {"chunk": chunk, "slots": slots,
+                              "streams": [torch.cuda.Stream(self.device) for _ in range(3)]}
+        return ws
+
     # ------------------------------------------------------------------ gym surface ---
     def seed(self, seed=None):
         """The reference seeds numpy's global RNG (e.g. rock.py:120-121); here the seed keys

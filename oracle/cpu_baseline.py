@@ -1,0 +1,113 @@
+"""CPU baseline leg of bench.py: the oracle's pure-Python RockSample step() loop timed on
+host cores.
+
+TEST/BENCH INFRASTRUCTURE ONLY -- imported by bench.py's ``cpu_baseline`` leg and by
+``bench.py --impl reference``; never by gym_pomdp_b200/.
+
+What is timed: for every (state, action) of a bounded sample of the benchmark's synthetic
+workload, one call of ``oracle.pomdp_oracle.rock_step`` -- the scalar Python restatement of
+rock.py:123-194, the same kind of code the reference runs (a Python ``step()`` per env
+instance) minus its object/dict churn, so it is if anything FASTER than the reference's
+own loop (reference 4.5e4 steps/s/core on Rock(11,11)).  Draw words come
+from a pre-generated numpy array (cheaper than the reference's np.random.binomial call).
+The unmodified reference itself cannot run on the GPU box (/root/reference is absent
+there), hence ``kind = "port"``.
+"""
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+from . import pomdp_oracle as O
+
+
+def rock_workload(n, k, count, seed=0x5EED):
+    """The synthetic distribution of SURVEY.md §8d in the reference's own units."""
+    rs = np.random.RandomState(seed & 0x7FFFFFFF)
+    x = rs.randint(0, n, count)
+    y = rs.randint(0, n, count)
+    status = rs.randint(-1, 2, (count, k))
+    action = rs.randint(0, 5 + k, count)
+    words = rs.randint(0, 2 ** 32, (count, 2), dtype=np.uint64)
+    return x, y, status, action, words
+
+
+def _rock_loop(args):
+    n, k, count, seed = args
+    cfg = O.RockCfg(n, k)
+    x, y, status, action, words = rock_workload(n, k, count, seed)
+    xs, ys, acts = x.tolist(), y.tolist(), action.tolist()
+    sts, ws = status.tolist(), words.tolist()
+    step = O.rock_step
+    acc = 0
+    t0 = time.perf_counter()
+    for i in range(count):
+        w = ws[i]
+        out = step(cfg, xs[i], ys[i], sts[i], acts[i], w.__getitem__)
+        acc += out[4]
+    dt = time.perf_counter() - t0
+    return count, dt, acc
+
+
+def time_rock(n, k, steps_per_proc, procs=None, seed=0x5EED):
+    """Runs ``procs`` worker processes (default: every host core), each stepping its own
+    ``steps_per_proc`` sampled envs once.  Returns dict(value=steps/s aggregate, ...)."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(n, k, steps_per_proc, seed + 7919 * p) for p in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_rock_loop(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_rock_loop, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)      # workers run concurrently: aggregate = total / slowest loop
+    return {"value": total / slowest, "unit": "env-steps/s", "cores": procs, "kind": "port",
+            "sample": "%d procs x %d RockSample(%d,%d) (state, action) pairs through oracle.pomdp_oracle.rock_step"
+                      % (procs, steps_per_proc, n, k),
+            "loop_seconds": slowest, "wall_seconds": wall, "steps": total}
+
+
+# ---- persistent arm for ``bench.py --impl reference --steps K --warmup W`` -------------
+_W = {}
+
+
+def _arm_init(n, k, count, seed_base):
+    ident = mp.current_process()._identity
+    rank = ident[0] if ident else 0
+    cfg = O.RockCfg(n, k)
+    x, y, status, action, words = rock_workload(n, k, count, seed_base + 7919 * rank)
+    _W.update(cfg=cfg, xs=x.tolist(), ys=y.tolist(), acts=action.tolist(), sts=status.tolist(), ws=words.tolist(),
+              count=count)
+
+
+def _arm_step(_):
+    cfg, xs, ys, acts, sts, ws, count = (_W[k] for k in ("cfg", "xs", "ys", "acts", "sts", "ws", "count"))
+    step = O.rock_step
+    acc = 0
+    t0 = time.perf_counter()
+    for i in range(count):
+        acc += step(cfg, xs[i], ys[i], sts[i], acts[i], ws[i].__getitem__)[4]
+    return time.perf_counter() - t0, acc
+
+
+class RockCpuArm(object):
+    """Every host core steps its own fixed sample of ``count`` (state, action) pairs per step()."""
+
+    def __init__(self, n, k, count, procs=None, seed=0x5EED):
+        self.procs = procs or os.cpu_count() or 1
+        self.count = count
+        self.n, self.k = n, k
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_arm_init, initargs=(n, k, count, seed))
+
+    def step(self):
+        """One pass: returns (env-steps done, wall seconds of the pass)."""
+        t0 = time.perf_counter()
+        self.pool.map(_arm_step, range(self.procs), chunksize=1)
+        return self.procs * self.count, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
