@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
 
     def summary(self):

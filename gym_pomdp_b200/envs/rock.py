@@ -227,7 +227,11 @@ class RockEnv(BatchedPomdpEnv):
         rock = (action - SAMPLE - 1).clamp(0, self.num_rocks - 1)
         pos = torch.tensor([[p.x, p.y] for p in self._rock_pos], device=next_state.device)
         d = (x.long() - pos[rock, 0]).abs() + (y.long() - pos[rock, 1]).abs()
-        eff = (1 + torch.pow(torch.tensor(2., dtype=torch.float64, device=next_state.device), -d.double() / 20)) * .5
+        # rock.py:383-387 evaluated in Python doubles per distance (bit-equal to the reference; torch.pow on
+        # the device may differ in the last ulp), then gathered
+        eff_tab = torch.tensor([self._efficiency((0, 0), (dd, 0)) for dd in range(2 * self.grid.x_size)],
+                               dtype=torch.float64, device=next_state.device)
+        eff = eff_tab[d]
         st = torch.gather(status.long(), 1, rock[:, None])[:, 0]
         match = ((ob == GOOD) & (st == 1)) | ((ob == BAD) & (st == -1))
         p_check = torch.where(match, eff, 1 - eff)
