@@ -239,8 +239,10 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
+    torch.cuda.profiler.start()     # ncu --profile-from-start off: list only the timed region's launches
     e0, e1 = timed_region()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks_note = "sampled during the timed region"

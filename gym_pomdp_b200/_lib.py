@@ -16,6 +16,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uin
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
+ABI_VERSION = 2
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -58,7 +59,7 @@ _PROTOTYPES = {
     "pomdp_abi_version": (c_int32, []),
     "pomdp_last_error": (c_char_p, []),
     "pomdp_rock_state_words": (c_int32, [POINTER(RockParams)]),
-    "pomdp_rock_table_bytes": (c_int64, []),
+    "pomdp_rock_table_bytes": (c_int64, [POINTER(RockParams)]),
     "pomdp_rock_build_table": (c_int32, [POINTER(RockParams), c_void_p]),
     "pomdp_rock_step": (c_int32, [POINTER(RockParams), _P] + _STEP_TAIL),
     "pomdp_rock_reset": (c_int32, [POINTER(RockParams), _P] + _RESET_TAIL),
@@ -103,8 +104,8 @@ def lib():
                 "(nvcc, sm_100a).  gym_pomdp_b200 has no CPU fallback.")
         _lib = _bind(LIB_PATH)
         got = _lib.pomdp_abi_version()
-        if got != 1:
-            raise RuntimeError(f"libpomdp_b200.so ABI version {got}, expected 1")
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libpomdp_b200.so ABI version {got}, expected {ABI_VERSION}")
     return _lib
 
 

@@ -56,17 +56,37 @@ POMDP_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
     return c;
 }
 
-// Draw-slot contract (include/pomdp_b200.h): block b holds slots 4b..4b+3 of (env, step).
-POMDP_HD U4 draw_block(uint64_t seed, uint64_t env, uint32_t step, uint32_t domain, uint32_t block) {
+// Draw-slot contract v2 (include/pomdp_b200.h): ONE Philox block holds the SAME slot of FOUR
+// consecutive env instances -- word(env, slot) = philox(key = seed,
+// ctr = (lo32(env >> 2), hi32(env >> 2), step, (domain << 24) | slot))[env & 3] -- so a thread
+// that owns an aligned group of four envs pays one Philox call per slot, not one per env.
+POMDP_HD U4 draw_quad(uint64_t seed, uint64_t group, uint32_t step, uint32_t domain, uint32_t slot) {
     U4 c;
-    c.x = (uint32_t)env;
-    c.y = (uint32_t)(env >> 32);
+    c.x = (uint32_t)group;
+    c.y = (uint32_t)(group >> 32);
     c.z = step;
-    c.w = (domain << 24) | block;
+    c.w = (domain << 24) | slot;
     return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
 POMDP_HD uint32_t word_of(const U4& r, int j) { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; }
+
+POMDP_HD uint32_t draw_word(uint64_t seed, uint64_t env, uint32_t step, uint32_t domain, uint32_t slot) {
+    return word_of(draw_quad(seed, env >> 2, step, domain, slot), (int)(env & 3));
+}
+
+// Draw providers handed to the per-env functors: draw(slot) -> uint32 word.
+struct LazyDraw {          // scalar paths: one Philox call per requested slot
+    uint64_t seed, env;
+    uint32_t step, domain;
+    POMDP_HD uint32_t operator()(int slot) const { return draw_word(seed, env, step, domain, (uint32_t)slot); }
+};
+template <int N>
+struct WordDraw {          // vector path: words precomputed from the group's quads
+    uint32_t w[N];
+    POMDP_HD uint32_t operator()(int slot) const { return w[slot]; }
+};
+
 // np.random.randint(n) / choice index under the coupling rule: floor(u * n), u = r / 2^32.
 POMDP_HD uint32_t rand_below(uint32_t r, uint32_t n) { return mulhi32(r, n); }
 // np.random.binomial(1, p) with T = ceil(p * 2^32)  (0 <= T <= 2^32, hence 64-bit).
@@ -103,90 +123,117 @@ POMDP_HD void tag_get_coord(uint32_t idx, int& x, int& y) {
 POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y - 2) * 3 + x - 5; }
 
 // ====================================================================== RockSample ===
-// Static maps of one Rock configuration; 400 bytes, staged into shared memory per block.
-struct RockTable {
+// Static maps of one Rock configuration, built on the host (pomdp_host.h: make_rock) and
+// staged into shared memory by ONE TMA bulk copy per CTA:
+//   RockTableHdr (400 B)  -- the reference's own maps (grid, rock coordinates, sensor thresholds)
+//   uint32 lut[256 << na_shift]  -- the transition table the step functor reads: ONE shared-
+//       memory load per env, indexed by (agent cell = x | y << 4, action):
+//         a in 0..3 (move)   bits 0-7 next cell, bits 8-15 reward (int8), bit 16 done
+//         a == 4   (sample)  bits 0-5 bit offset of the status of the rock under the agent
+//                            (ROCK_NONE_SH<S> when there is none), bit 8 = dangling grid id
+//         a >= 5   (check)   ceil(eff(d) * 2^32) - 1 for d = L1(agent, rock a-5)  (rock.py:383-387)
+struct RockTableHdr {
     int8_t grid[256];      // [x | y << 4] -> rock id written by rock.py:110-111, -1 = none
     uint8_t rock_pos[16];  // rock i -> x | y << 4   (rock.py:106)
-    uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2 (rock.py:383-387)
+    uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2
 };
-static_assert(sizeof(RockTable) == 400 && sizeof(RockTable) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+static_assert(sizeof(RockTableHdr) == 400 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
 
 struct RockDev {  // passed by value to the kernels
     int32_t n, k;
     int32_t stochastic;
     int32_t penal;        // rock.py:117 (-100) / rock.py:432 (0)
     uint32_t start;       // x | y << 4 of config init_pos
-    uint32_t pad;
+    uint32_t n_actions;   // 5 + k (rock.py:113)
+    uint32_t na_shift;    // log2 of the LUT row length: 4 (<= 16 actions) or 5
+    uint32_t table_bytes; // sizeof(RockTableHdr) + 4 * (256 << na_shift)
     uint64_t move_T;      // ceil(p_move * 2^32)
 };
 
 template <typename S> struct RockBits;
-template <> struct RockBits<uint32_t> { static constexpr uint32_t DONE = 0x80000000u; };
-template <> struct RockBits<uint64_t> { static constexpr uint64_t DONE = 0x8000000000000000ull; };
+template <> struct RockBits<uint32_t> { static constexpr uint32_t DONE = 0x80000000u; static constexpr uint32_t NONE_SH = 30; };
+template <> struct RockBits<uint64_t> { static constexpr uint64_t DONE = 0x8000000000000000ull; static constexpr uint32_t NONE_SH = 62; };
 
-// rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step).
+// shifts whose count wraps at the word size (one SHF on the GPU; the LUT's sample offset is
+// garbage for the other action classes and must not be undefined behaviour)
+POMDP_HD uint32_t shr_wrap(uint32_t v, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(v, 0u, sh);
+#else
+    return v >> (sh & 31u);
+#endif
+}
+POMDP_HD uint64_t shr_wrap(uint64_t v, uint32_t sh) { return v >> (sh & 63u); }
+POMDP_HD uint32_t shl_wrap(uint32_t v, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(0u, v, sh);
+#else
+    return v << (sh & 31u);
+#endif
+}
+POMDP_HD uint64_t shl_wrap(uint64_t v, uint32_t sh) { return v << (sh & 63u); }
+
+// rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step), branch-free:
+// every env runs the same instruction stream whatever its action class, so the four envs
+// of a thread and the 32 threads of a warp never diverge.
+//   w_gate   = draw slot 0 (p_move gate, StochasticRock only, rock.py:443)
+//   w_sensor = draw slot 1 (np.random.binomial(1, eff), rock.py:404)
 template <typename S>
-POMDP_HD void rock_step(const RockDev& p, const RockTable* __restrict__ t, S s, int32_t a,
-                        uint64_t seed, uint64_t env, uint32_t step,
-                        S& s2, int32_t& ob, float& rw, int32_t& fl) {
-    s2 = s; ob = 0; rw = 0.f; fl = 0;
-    if (s & RockBits<S>::DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }   // rock.py:126
-    if ((uint32_t)a >= (uint32_t)(5 + p.k)) { fl = FLAG_BAD_ACTION; return; }     // rock.py:125
-    const int x = (int)(s & 15), y = (int)((s >> 4) & 15);
-    U4 r = {0, 0, 0, 0};
-    if (p.stochastic || a > 4) r = draw_block(seed, env, step, DOMAIN_STEP, 0);
-    if (p.stochastic && !bern(r.x, p.move_T)) return;                             // rock.py:443
-    int reward = 0;
-    bool done = false;
-    if (a < 4) {                                                                  // rock.py:134-158
-        const int nx = x + move_dx(a), ny = y + move_dy(a);
-        if ((unsigned)nx < (unsigned)p.n && (unsigned)ny < (unsigned)p.n) {
-            s2 = (s & ~(S)0xFF) | (S)(nx | (ny << 4));
-        } else if (a == 1) {                                                      // east exit, 139-141
-            reward = 10;
-            done = true;
-        } else {
-            reward = p.penal;
-        }
-    } else if (a == 4) {                                                          // rock.py:160-169
-        int rock = t->grid[(uint32_t)s & 0xFF];
-        if (rock >= p.k) { fl |= FLAG_BAD_STATE; rock = -1; }   // reference: IndexError at rock.py:162
-        const int sh = 8 + 2 * (rock < 0 ? 0 : rock);
-        const uint32_t code = rock >= 0 ? (uint32_t)(s >> sh) & 3u : 0u;
-        if (code != 0) {
-            reward = code == 1 ? 10 : -10;
-            s2 = s & ~((S)3 << sh);
-        } else {
-            reward = p.penal;
-        }
-    } else {                                                                      // rock.py:171-175, 401-407
-        const int rock = a - 5;
-        const uint32_t rp = t->rock_pos[rock];
-        const int d = l1_distance(x, y, (int)(rp & 15), (int)(rp >> 4));
-        const bool truthful = r.y <= t->thr_m1[d];
-        const bool good = ((uint32_t)(s >> (8 + 2 * rock)) & 3u) == 1u;
-        ob = (good == truthful) ? 2 : 1;
+POMDP_HD void rock_step(const RockDev& p, const uint32_t* __restrict__ lut, S s, int32_t a, uint32_t w_gate,
+                        uint32_t w_sensor, S& s2, int32_t& ob, float& rw, int32_t& fl) {
+    const bool stepped_done = (s & RockBits<S>::DONE) != 0;                       // rock.py:126
+    const bool bad_action = (uint32_t)a >= p.n_actions;                           // rock.py:125
+    const uint32_t ai = (uint32_t)a < p.n_actions ? (uint32_t)a : p.n_actions - 1u;
+    const uint32_t v = lut[(((uint32_t)s & 0xFFu) << p.na_shift) + ai];
+    const bool is_move = ai < 4u, is_sample = ai == 4u, is_check = ai > 4u;
+    const uint32_t sh = is_check ? 2u * ai - 2u : (v & 63u);                      // 8 + 2 * (a - 5)
+    const uint32_t code = (uint32_t)shr_wrap(s, sh) & 3u;                         // 1 good, 3 bad, 0 collected / none
+    // check (rock.py:171-175, 401-407): truthful reading w.p. eff, else flipped
+    const bool truthful = w_sensor <= v;
+    const int32_t ob_check = ((code == 1u) == truthful) ? 2 : 1;
+    // sample (rock.py:160-169)
+    const bool has_rock = code != 0u;
+    const S cleared = s & ~shl_wrap((S)3, sh);
+    const int32_t rw_sample = code == 1u ? 10 : (has_rock ? -10 : p.penal);
+    // move (rock.py:134-158): the LUT row holds the next cell, the reward and the exit/wall `done`
+    const S moved = (s & ~(S)0xFF) | (S)(v & 0xFFu);
+    const int32_t rw_move = (int32_t)(int8_t)(v >> 8);
+    const bool done_move = ((v >> 16) & 1u) != 0;
+
+    S ns = is_move ? moved : ((is_sample && has_rock) ? cleared : s);
+    int32_t reward = is_move ? rw_move : (is_sample ? rw_sample : 0);
+    bool done = is_move ? done_move : (is_sample && !has_rock && !p.stochastic);  // rock.py:193 vs 503
+    int32_t o = is_check ? ob_check : 0;
+    int32_t f = (is_sample && (v & 0x100u)) ? (int32_t)FLAG_BAD_STATE : 0;        // reference: IndexError, rock.py:162
+    if (p.stochastic && !bern(w_gate, p.move_T)) { ns = s; reward = 0; done = false; o = 0; f = 0; }  // rock.py:443
+    if (done) { ns |= RockBits<S>::DONE; f |= FLAG_DONE; }
+    if (stepped_done || bad_action) {
+        ns = s; reward = 0; o = 0;
+        f = stepped_done ? (FLAG_DONE | FLAG_STEPPED_DONE) : FLAG_BAD_ACTION;
     }
-    if (!p.stochastic) done = done || (reward == p.penal);                        // rock.py:193 vs 503
-    if (done) { s2 |= RockBits<S>::DONE; fl |= FLAG_DONE; }
-    rw = (float)reward;
+    s2 = ns; ob = o; rw = (float)reward; fl = f;
 }
 
-// rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)); slot i = rock i.
-template <typename S>
-POMDP_HD S rock_reset(const RockDev& p, uint64_t seed, uint64_t env, uint32_t step) {
+// rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)); draw slot i = rock i.
+POMDP_HD uint32_t rock_status_code(uint32_t w) { return w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u); }
+
+template <typename S, class D>
+POMDP_HD S rock_reset(const RockDev& p, const D& draw) {
     S s = (S)p.start;
-    for (int b = 0; 4 * b < p.k; ++b) {
-        const U4 r = draw_block(seed, env, step, DOMAIN_RESET, (uint32_t)b);
-        POMDP_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            const int i = 4 * b + j;
-            const uint32_t w = word_of(r, j);
-            const uint32_t code = w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u);
-            if (i < p.k) s |= (S)code << (8 + 2 * i);
-        }
-    }
+    for (int i = 0; i < p.k; ++i) s |= (S)rock_status_code(draw(i)) << (8 + 2 * i);
     return s;
+}
+// Four envs of one aligned group: one Philox call per rock.
+template <typename S>
+POMDP_HD void rock_reset4(const RockDev& p, uint64_t seed, uint64_t group, uint32_t step, S out[4]) {
+    out[0] = out[1] = out[2] = out[3] = (S)p.start;
+    for (int i = 0; i < p.k; ++i) {
+        const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)i);
+        out[0] |= (S)rock_status_code(q.x) << (8 + 2 * i);
+        out[1] |= (S)rock_status_code(q.y) << (8 + 2 * i);
+        out[2] |= (S)rock_status_code(q.z) << (8 + 2 * i);
+        out[3] |= (S)rock_status_code(q.w) << (8 + 2 * i);
+    }
 }
 
 // ============================================================================= Tag ===
@@ -197,6 +244,7 @@ struct TagDev {
 };
 constexpr uint32_t TAG_DONE = 0x80000000u;
 constexpr int TAG_CELLS = 29;
+constexpr int TAG_MAX_OPP = 4;
 
 POMDP_HD int tag_num_opp(uint32_t s) { return ((int32_t)(s << 1)) >> 26; }  // bits 25-30, sign-extended
 POMDP_HD uint32_t tag_set_num_opp(uint32_t s, int v) { return (s & ~(63u << 25)) | (((uint32_t)v & 63u) << 25); }
@@ -220,7 +268,9 @@ POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
 }
 
 // tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).
-POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
+// Draw slots per opponent j: 2j = np.random.binomial(1, move_prob) (tag.py:204), 2j+1 = np.random.choice (tag.py:205).
+template <class D>
+POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, const D& draw,
                        uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     s2 = s; ob = 0; rw = 0.f; fl = 0;
     if (s & TAG_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }             // tag.py:110
@@ -236,10 +286,9 @@ POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, uint64_t seed, ui
     if (a == 4) {                                                                 // tag.py:119-131
         bool tagged = false;
         reward = 0.f;
-        U4 r0 = draw_block(seed, env, step, DOMAIN_STEP, 0);
-        U4 r1 = r0;
-        if (p.n_opp > 2) r1 = draw_block(seed, env, step, DOMAIN_STEP, 1);
-        for (int j = 0; j < p.n_opp; ++j) {
+        POMDP_UNROLL
+        for (int j = 0; j < TAG_MAX_OPP; ++j) {
+            if (j >= p.n_opp) break;
             const int sh = 5 + 5 * j;
             const uint32_t o = (s2 >> sh) & 31u;
             if (o == agent) {
@@ -247,8 +296,7 @@ POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, uint64_t seed, ui
                 tagged = true;
                 --nopp;
             } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
-                const U4& r = j < 2 ? r0 : r1;
-                const uint32_t w_move = word_of(r, (2 * j) & 3), w_pick = word_of(r, (2 * j + 1) & 3);
+                const uint32_t w_move = draw(2 * j), w_pick = draw(2 * j + 1);
                 int ox, oy;
                 tag_get_coord(o, ox, oy);
                 uint32_t list;
@@ -280,16 +328,15 @@ POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, uint64_t seed, ui
 }
 
 // tag.py:97-102, 181-193: slot 0 = agent cell, slot 1+j = opponent j; ob = _sample_ob(state, 0).
-POMDP_HD void tag_reset(const TagDev& p, uint64_t seed, uint64_t env, uint32_t step, uint32_t& s, int32_t& ob) {
-    const U4 r0 = draw_block(seed, env, step, DOMAIN_RESET, 0);
-    U4 r1 = r0;
-    if (p.n_opp > 3) r1 = draw_block(seed, env, step, DOMAIN_RESET, 1);
-    const uint32_t agent = rand_below(r0.x, TAG_CELLS);
+template <class D>
+POMDP_HD void tag_reset(const TagDev& p, const D& draw, uint32_t& s, int32_t& ob) {
+    const uint32_t agent = rand_below(draw(0), TAG_CELLS);
     s = agent;
     ob = (int32_t)agent;
-    for (int j = 0; j < p.n_opp; ++j) {
-        const uint32_t w = (1 + j) < 4 ? word_of(r0, 1 + j) : word_of(r1, (1 + j) & 3);
-        const uint32_t o = rand_below(w, TAG_CELLS);
+    POMDP_UNROLL
+    for (int j = 0; j < TAG_MAX_OPP; ++j) {
+        if (j >= p.n_opp) break;
+        const uint32_t o = rand_below(draw(1 + j), TAG_CELLS);
         s |= o << (5 + 5 * j);
         if (o == agent) ob = TAG_CELLS;
     }
@@ -303,7 +350,9 @@ struct TigerDev {
 constexpr uint32_t TIGER_DONE = 0x80000000u;
 
 // tiger.py:72-88 (+ _compute_rw 164-172, _is_terminal 155-162, _sample_state 117-119, _sample_ob 140-149)
-POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
+// Draw slot 0 = state_space.sample() (tiger.py:118-119), slot 1 = np.random.uniform() (tiger.py:143).
+template <class D>
+POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, const D& draw,
                          uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     s2 = s; ob = 0; rw = 0.f; fl = 0;
     if (s & TIGER_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }
@@ -318,18 +367,17 @@ POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, uint64_t seed
         fl = FLAG_DONE;
         return;
     }
-    const U4 r = draw_block(seed, env, step, DOMAIN_STEP, 0);
-    if (a < 2) st = rand_below(r.x, 2);   // state_space.sample(), tiger.py:118-119
-    const bool flip = (uint64_t)r.y > p.listen_G;   // p > correct_prob, tiger.py:143-148
+    if (a < 2) st = rand_below(draw(0), 2);   // state_space.sample(), tiger.py:118-119
+    const bool flip = (uint64_t)draw(1) > p.listen_G;   // p > correct_prob, tiger.py:143-148
     ob = 2;
     if (a == 2) ob = (int32_t)(flip ? 1u - st : st);
     s2 = st;
 }
 
 // tiger.py:60-66
-POMDP_HD void tiger_reset(uint64_t seed, uint64_t env, uint32_t step, uint32_t& s, int32_t& ob) {
-    const U4 r = draw_block(seed, env, step, DOMAIN_RESET, 0);
-    s = rand_below(r.x, 2);
+template <class D>
+POMDP_HD void tiger_reset(const D& draw, uint32_t& s, int32_t& ob) {
+    s = rand_below(draw(0), 2);
     ob = 2;
 }
 
@@ -351,52 +399,63 @@ POMDP_HD int popc32(uint32_t v) {
 #endif
 }
 
-// network.py:71-114.  Reward is carried as an exact integer number of tenths.
-POMDP_HD void network_step(const NetworkDev& p, uint32_t s, int32_t a, uint64_t seed, uint64_t env, uint32_t step,
-                           uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
-    s2 = s; ob = 0; rw = 0.f; fl = 0;
+// network.py:71-114 for L consecutive envs of ONE draw group (L = 4: a thread's aligned
+// group, lane0 = 0; L = 1: a single env, lane0 = env & 3).  Slot m = machine m's failure
+// draw, slot n = the action's observation draw: one Philox call per slot serves all L envs.
+// Reward is carried as an exact integer number of tenths.
+template <int L>
+POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], uint64_t seed,
+                             uint64_t group, int lane0, uint32_t step,
+                             uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
     const uint32_t all = (1u << p.n) - 1u;
-    if (s & NETWORK_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }
-    if ((uint32_t)a >= (uint32_t)(2 * p.n + 1)) { fl = FLAG_BAD_ACTION; return; }
-    if (s & ~all) { fl = FLAG_BAD_STATE; return; }
-    const uint32_t down = ~s & all;
-    int tenths = 10 * popc32(s) + 10 * popc32(s & p.deg3);                        // network.py:87-92
-    uint32_t nw = s;
-    uint32_t w_act = 0;
-    for (int b = 0; 4 * b <= p.n; ++b) {                                          // network.py:94-99
-        const U4 r = draw_block(seed, env, step, DOMAIN_STEP, (uint32_t)b);
+    uint32_t nw[L], down[L];
+    int tenths[L];
+    bool live[L];
+    POMDP_UNROLL
+    for (int j = 0; j < L; ++j) {
+        fl[j] = 0;
+        if (s[j] & NETWORK_DONE) fl[j] = FLAG_DONE | FLAG_STEPPED_DONE;
+        else if ((uint32_t)a[j] >= (uint32_t)(2 * p.n + 1)) fl[j] = FLAG_BAD_ACTION;
+        else if (s[j] & ~all) fl[j] = FLAG_BAD_STATE;
+        live[j] = fl[j] == 0;
+        nw[j] = s[j];
+        down[j] = ~s[j] & all;
+        tenths[j] = 10 * popc32(s[j]) + 10 * popc32(s[j] & p.deg3);               // network.py:87-92
+    }
+    for (int m = 0; m < p.n; ++m) {                                               // network.py:94-99
+        const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
         POMDP_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            const int m = 4 * b + j;
-            const uint32_t w = word_of(r, j);
-            if (m < p.n) {
-                const uint64_t T = (p.nb[m] & down) ? p.q_T : p.p_T;
-                if (((s >> m) & 1u) && bern(w, T)) nw &= ~(1u << m);
-            } else if (m == p.n) {
-                w_act = w;
+        for (int j = 0; j < L; ++j) {
+            const uint64_t T = (p.nb[m] & down[j]) ? p.q_T : p.p_T;
+            if (((s[j] >> m) & 1u) && bern(word_of(q, lane0 + j), T)) nw[j] &= ~(1u << m);
+        }
+    }
+    const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
+    POMDP_UNROLL
+    for (int j = 0; j < L; ++j) {
+        int o = 2;
+        if (a[j] < 2 * p.n) {                                                     // network.py:101-112
+            const int machine = (a[j] >> 1) & 31;
+            const int hit = bern(word_of(qa, lane0 + j), p.ob_T) ? 1 : 0;
+            if (a[j] & 1) {
+                tenths[j] -= 25;
+                nw[j] |= 1u << machine;
+                o = hit;
+            } else {
+                tenths[j] -= 1;
+                const int bit = (int)((nw[j] >> machine) & 1u);
+                o = hit ? bit : 1 - bit;
             }
         }
-    }
-    ob = 2;
-    if (a < 2 * p.n) {                                                            // network.py:101-112
-        const int machine = a >> 1;
-        const int hit = bern(w_act, p.ob_T) ? 1 : 0;
-        if (a & 1) {
-            tenths -= 25;
-            nw |= 1u << machine;
-            ob = hit;
-        } else {
-            tenths -= 1;
-            const int bit = (int)((nw >> machine) & 1u);
-            ob = hit ? bit : 1 - bit;
-        }
-    }
-    s2 = nw;
 #if defined(__CUDA_ARCH__)
-    rw = __fdiv_rn((float)tenths, 10.0f);
+        const float r = __fdiv_rn((float)tenths[j], 10.0f);
 #else
-    rw = (float)tenths / 10.0f;
+        const float r = (float)tenths[j] / 10.0f;
 #endif
+        s2[j] = live[j] ? nw[j] : s[j];
+        ob[j] = live[j] ? o : 0;
+        rw[j] = live[j] ? r : 0.f;
+    }
 }
 
 // ====================================================================== BattleShip ===
@@ -501,13 +560,12 @@ POMDP_HD bool battleship_reset_rejection(const ShipDev& p, uint64_t seed, uint64
                                          ShipState& st, int max_attempts) {
     st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
     int a = 0;
-    U4 r = {0, 0, 0, 0};
     for (int length = p.max_len; length >= 2; --length) {
         const u128 blocked = ship_blocked(p, st.occ);
         for (;;) {
             if (a >= max_attempts) return false;
-            if ((a & 1) == 0) r = draw_block(seed, env, step, DOMAIN_RESET, (uint32_t)(a >> 1));
-            const uint32_t w_pos = (a & 1) ? r.z : r.x, w_dir = (a & 1) ? r.w : r.y;
+            const uint32_t w_pos = draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)(2 * a));
+            const uint32_t w_dir = draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)(2 * a + 1));
             ++a;
             const int pos = (int)rand_below(w_pos, (uint32_t)p.n_tiles), dir = (int)rand_below(w_dir, 4);
             if (ship_candidate_ok(p, blocked, pos, dir, length)) { ship_mark(p, st, pos, dir, length); break; }

@@ -63,8 +63,14 @@ inline const RockLayout* rock_layout(int board) {
 
 inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 : 2; }
 
-// Fills the kernel params and (if tbl != nullptr) the static maps.  Returns 0 or POMDP_E_BADARG.
-inline int make_rock(const PomdpRockParams* q, RockDev* d, RockTable* tbl) {
+inline int rock_na_shift(const PomdpRockParams* q) { return 5 + q->num_rocks <= 16 ? 4 : 5; }
+inline int64_t rock_table_bytes(const PomdpRockParams* q) {
+    return (int64_t)sizeof(RockTableHdr) + 4 * ((int64_t)256 << rock_na_shift(q));
+}
+
+// Fills the kernel params and (if tbl != nullptr) the static maps: the 400-byte header
+// followed by the transition LUT (layout: pomdp_core.h).  Returns 0 or POMDP_E_BADARG.
+inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
     if (!q) return fail(POMDP_E_BADARG, "rock: params is NULL");
     const RockLayout* L = rock_layout(q->board_size);
     if (!L) return fail(POMDP_E_BADARG, "rock: board_size %d is not a key of rock.config (2,4,7,11,15)", q->board_size);
@@ -74,27 +80,60 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, RockTable* tbl) {
     if (q->num_rocks > L->n_listed)
         return fail(POMDP_E_BADARG, "rock: config[%d] lists only %d rocks (the reference fails in _get_init_state)",
                     q->board_size, L->n_listed);
+    const int n = q->board_size, k = q->num_rocks;
+    const int penal = q->stochastic ? 0 : -100;
+    const int na_shift = rock_na_shift(q);
     if (d) {
         memset(d, 0, sizeof(*d));
-        d->n = q->board_size;
-        d->k = q->num_rocks;
+        d->n = n;
+        d->k = k;
         d->stochastic = q->stochastic ? 1 : 0;
-        d->penal = q->stochastic ? 0 : -100;
+        d->penal = penal;
         d->start = (uint32_t)(L->sx | (L->sy << 4));
+        d->n_actions = (uint32_t)(5 + k);
+        d->na_shift = (uint32_t)na_shift;
+        d->table_bytes = (uint32_t)rock_table_bytes(q);
         d->move_T = bern_T(q->p_move);
     }
     if (tbl) {
-        memset(tbl, 0, sizeof(*tbl));
-        memset(tbl->grid, -1, sizeof(tbl->grid));
-        memset(tbl->rock_pos, 0xFF, sizeof(tbl->rock_pos));
+        RockTableHdr* h = (RockTableHdr*)tbl;
+        uint32_t* lut = (uint32_t*)((char*)tbl + sizeof(RockTableHdr));
+        memset(tbl, 0, (size_t)rock_table_bytes(q));
+        memset(h->grid, -1, sizeof(h->grid));
+        memset(h->rock_pos, 0xFF, sizeof(h->rock_pos));
         for (int i = 0; i < L->n_listed; ++i) {   // every listed rock is written; later ids overwrite (rock.py:110-111)
             const int cell = L->pos[i][0] | (L->pos[i][1] << 4);
-            tbl->grid[cell] = (int8_t)i;
-            tbl->rock_pos[i] = (uint8_t)cell;
+            h->grid[cell] = (int8_t)i;
+            h->rock_pos[i] = (uint8_t)cell;
         }
         for (int dd = 0; dd < 32; ++dd) {
             const double eff = (1 + pow(2, -(double)dd / 20)) * .5;      // rock.py:383-387
-            tbl->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
+            h->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
+        }
+        const uint32_t none_sh = k <= 11 ? RockBits<uint32_t>::NONE_SH : RockBits<uint64_t>::NONE_SH;
+        for (int cell = 0; cell < 256; ++cell) {
+            const int x = cell & 15, y = cell >> 4;
+            uint32_t* row = lut + ((size_t)cell << na_shift);
+            for (int a = 0; a < 4; ++a) {                                // rock.py:134-158
+                const int nx = x + move_dx(a), ny = y + move_dy(a);
+                uint32_t next = (uint32_t)cell;
+                int reward = 0, done = 0;
+                if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n) next = (uint32_t)(nx | (ny << 4));
+                else if (a == 1) { reward = 10; done = 1; }             // east exit, rock.py:139-141
+                else { reward = penal; done = !q->stochastic; }         // rock.py:193 (commented out at 503)
+                row[a] = next | ((uint32_t)(uint8_t)(int8_t)reward << 8) | ((uint32_t)done << 16);
+            }
+            {                                                            // rock.py:160-169
+                const int rock = h->grid[cell];
+                uint32_t e = none_sh;
+                if (rock >= k) e |= 0x100u;                              // reference: IndexError at rock.py:162
+                else if (rock >= 0) e = (uint32_t)(8 + 2 * rock);
+                row[4] = e;
+            }
+            for (int r = 0; r < k; ++r) {                                // rock.py:171-175, 383-387, 401-407
+                const int rp = h->rock_pos[r];
+                row[5 + r] = h->thr_m1[l1_distance(x, y, rp & 15, rp >> 4)];
+            }
         }
     }
     return 0;

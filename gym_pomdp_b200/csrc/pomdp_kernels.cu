@@ -26,6 +26,13 @@
 using namespace pomdp;
 
 #define POMDP_THREADS 256
+// step kernels: CTA size and the min-resident-CTAs register hint (tuned on B200)
+#ifndef POMDP_STEP_THREADS
+#define POMDP_STEP_THREADS 512
+#endif
+#ifndef POMDP_STEP_MINB
+#define POMDP_STEP_MINB 2
+#endif
 
 // ----------------------------------------------------------------------------- PTX ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,97 +84,171 @@ __device__ __forceinline__ void st_stream4(int32_t* p, int4 v) { __stcs(reinterp
 __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
 // ------------------------------------------------------------------- env policies ---
-// Each policy adapts one env's functor from pomdp_core.h to the generic streaming kernels.
-struct RockEnv1 {
+// Each policy adapts one env's functors from pomdp_core.h to the generic streaming kernels:
+//   step4 / reset4 : the FOUR envs of one aligned draw group (one thread, one Philox call per slot)
+//   step1 / reset1 : a single env (tails, unaligned views, masked resets)
+template <typename S>
+struct RockEnvT {
     typedef RockDev Params;
-    typedef uint32_t State;
+    typedef S State;
     static constexpr bool kTable = true;
-    __device__ static __forceinline__ void step(const Params& p, const RockTable* t, State s, int32_t a, uint64_t seed,
-                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
-                                                int32_t& fl) {
-        rock_step<uint32_t>(p, t, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    __device__ static __forceinline__ void step4(const Params& p, const uint32_t* lut, const S s[4], const int32_t a[4],
+                                                 uint64_t seed, uint64_t group, uint32_t ctr, S s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        const U4 qs = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
+        U4 qg = {0, 0, 0, 0};
+        if (p.stochastic) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
+        rock_step<S>(p, lut, s[0], a[0], qg.x, qs.x, s2[0], ob[0], rw[0], fl[0]);
+        rock_step<S>(p, lut, s[1], a[1], qg.y, qs.y, s2[1], ob[1], rw[1], fl[1]);
+        rock_step<S>(p, lut, s[2], a[2], qg.z, qs.z, s2[2], ob[2], rw[2], fl[2]);
+        rock_step<S>(p, lut, s[3], a[3], qg.w, qs.w, s2[3], ob[3], rw[3], fl[3]);
     }
-    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
-                                                 State& s, int32_t& ob) {
-        s = rock_reset<uint32_t>(p, seed, env, step_ctr);
+    __device__ static __forceinline__ void step1(const Params& p, const uint32_t* lut, S s, int32_t a, uint64_t seed,
+                                                 uint64_t env, uint32_t ctr, S& s2, int32_t& ob, float& rw, int32_t& fl) {
+        const uint32_t ws = draw_word(seed, env, ctr, DOMAIN_STEP, 1);
+        const uint32_t wg = p.stochastic ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
+        rock_step<S>(p, lut, s, a, wg, ws, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset4(const Params& p, uint64_t seed, uint64_t group, uint32_t ctr, S s[4],
+                                                  int32_t ob[4]) {
+        rock_reset4<S>(p, seed, group, ctr, s);
+        ob[0] = ob[1] = ob[2] = ob[3] = 0;
+    }
+    __device__ static __forceinline__ void reset1(const Params& p, uint64_t seed, uint64_t env, uint32_t ctr, S& s,
+                                                  int32_t& ob) {
+        s = rock_reset<S>(p, LazyDraw{seed, env, ctr, DOMAIN_RESET});
         ob = 0;
     }
 };
-struct RockEnv2 {
-    typedef RockDev Params;
-    typedef uint64_t State;
-    static constexpr bool kTable = true;
-    __device__ static __forceinline__ void step(const Params& p, const RockTable* t, State s, int32_t a, uint64_t seed,
-                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
-                                                int32_t& fl) {
-        rock_step<uint64_t>(p, t, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+typedef RockEnvT<uint32_t> RockEnv1;
+typedef RockEnvT<uint64_t> RockEnv2;
+
+// Precomputes the NS draw words of each of the four envs of a group (NS Philox calls).
+template <int NS>
+__device__ __forceinline__ void quad_words(uint64_t seed, uint64_t group, uint32_t ctr, uint32_t domain, int n_used,
+                                           WordDraw<NS> d[4]) {
+#pragma unroll
+    for (int slot = 0; slot < NS; ++slot) {
+        U4 q = {0, 0, 0, 0};
+        if (slot < n_used) q = draw_quad(seed, group, ctr, domain, (uint32_t)slot);   // uniform branch
+        d[0].w[slot] = q.x; d[1].w[slot] = q.y; d[2].w[slot] = q.z; d[3].w[slot] = q.w;
     }
-    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
-                                                 State& s, int32_t& ob) {
-        s = rock_reset<uint64_t>(p, seed, env, step_ctr);
-        ob = 0;
-    }
-};
-struct TagEnvP {
+}
+
+// NOPP = 1: the stock Tag-v0 (two draw slots); NOPP = 4: any num_opponents in 1..4.
+template <int NOPP>
+struct TagEnvT {
     typedef TagDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
-                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
-                                                int32_t& fl) {
-        tag_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
+                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        WordDraw<2 * NOPP> d[4];
+        quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tag_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }
-    __device__ static __forceinline__ void reset(const Params& p, uint64_t seed, uint64_t env, uint32_t step_ctr,
-                                                 State& s, int32_t& ob) {
-        tag_reset(p, seed, env, step_ctr, s, ob);
+    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        tag_step(p, s, a, LazyDraw{seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset4(const Params& p, uint64_t seed, uint64_t group, uint32_t ctr,
+                                                  State s[4], int32_t ob[4]) {
+        WordDraw<1 + NOPP> d[4];
+        quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
+    }
+    __device__ static __forceinline__ void reset1(const Params& p, uint64_t seed, uint64_t env, uint32_t ctr, State& s,
+                                                  int32_t& ob) {
+        tag_reset(p, LazyDraw{seed, env, ctr, DOMAIN_RESET}, s, ob);
     }
 };
+
 struct TigerEnvP {
     typedef TigerDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
-                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
-                                                int32_t& fl) {
-        tiger_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
+                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        WordDraw<2> d[4];
+        quad_words<2>(seed, group, ctr, DOMAIN_STEP, 2, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tiger_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }
-    __device__ static __forceinline__ void reset(const Params&, uint64_t seed, uint64_t env, uint32_t step_ctr,
-                                                 State& s, int32_t& ob) {
-        tiger_reset(seed, env, step_ctr, s, ob);
+    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        tiger_step(p, s, a, LazyDraw{seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+    }
+    __device__ static __forceinline__ void reset4(const Params&, uint64_t seed, uint64_t group, uint32_t ctr, State s[4],
+                                                  int32_t ob[4]) {
+        WordDraw<1> d[4];
+        quad_words<1>(seed, group, ctr, DOMAIN_RESET, 1, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tiger_reset(d[j], s[j], ob[j]);
+    }
+    __device__ static __forceinline__ void reset1(const Params&, uint64_t seed, uint64_t env, uint32_t ctr, State& s,
+                                                  int32_t& ob) {
+        tiger_reset(LazyDraw{seed, env, ctr, DOMAIN_RESET}, s, ob);
     }
 };
+
 struct NetworkEnvP {
     typedef NetworkDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step(const Params& p, const RockTable*, State s, int32_t a, uint64_t seed,
-                                                uint64_t env, uint32_t step_ctr, State& s2, int32_t& ob, float& rw,
-                                                int32_t& fl) {
-        network_step(p, s, a, seed, env, step_ctr, s2, ob, rw, fl);
+    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
+                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        network_step_n<4>(p, s, a, seed, group, 0, ctr, s2, ob, rw, fl);
     }
-    __device__ static __forceinline__ void reset(const Params& p, uint64_t, uint64_t, uint32_t, State& s, int32_t& ob) {
-        s = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
+    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        network_step_n<1>(p, &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
+    }
+    __device__ static __forceinline__ void reset4(const Params& p, uint64_t, uint64_t, uint32_t, State s[4],
+                                                  int32_t ob[4]) {
+        s[0] = s[1] = s[2] = s[3] = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
+        ob[0] = ob[1] = ob[2] = ob[3] = 0;
+    }
+    __device__ static __forceinline__ void reset1(const Params& p, uint64_t, uint64_t, uint32_t, State& s, int32_t& ob) {
+        s = (1u << p.n) - 1u;
         ob = 0;
     }
 };
 
-// Load / store four consecutive packed states (32- or 64-bit) with 16-byte accesses.
-__device__ __forceinline__ void load_states4(const int32_t* base, int64_t i, uint32_t s[4]) {
-    const int4 v = ld_stream4(base + i);
-    s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; s[2] = (uint32_t)v.z; s[3] = (uint32_t)v.w;
-}
-__device__ __forceinline__ void load_states4(const int32_t* base, int64_t i, uint64_t s[4]) {
-    const int4 v0 = ld_stream4(base + 2 * i), v1 = ld_stream4(base + 2 * i + 4);
-    s[0] = (uint32_t)v0.x | ((uint64_t)(uint32_t)v0.y << 32); s[1] = (uint32_t)v0.z | ((uint64_t)(uint32_t)v0.w << 32);
-    s[2] = (uint32_t)v1.x | ((uint64_t)(uint32_t)v1.y << 32); s[3] = (uint32_t)v1.z | ((uint64_t)(uint32_t)v1.w << 32);
-}
-__device__ __forceinline__ void store_states4(int32_t* base, int64_t i, const uint32_t s[4]) {
-    st_stream4(base + i, make_int4((int)s[0], (int)s[1], (int)s[2], (int)s[3]));
-}
-__device__ __forceinline__ void store_states4(int32_t* base, int64_t i, const uint64_t s[4]) {
-    st_stream4(base + 2 * i, make_int4((int)(uint32_t)s[0], (int)(s[0] >> 32), (int)(uint32_t)s[1], (int)(s[1] >> 32)));
-    st_stream4(base + 2 * i + 4, make_int4((int)(uint32_t)s[2], (int)(s[2] >> 32), (int)(uint32_t)s[3], (int)(s[3] >> 32)));
-}
+// Four consecutive packed states (32- or 64-bit each) as 16-byte vectors.
+template <typename S> struct StateVec;
+template <> struct StateVec<uint32_t> {
+    int4 v;
+    __device__ __forceinline__ void load(const int32_t* base, int64_t i) { v = ld_stream4(base + i); }
+    __device__ __forceinline__ void unpack(uint32_t s[4]) const {
+        s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; s[2] = (uint32_t)v.z; s[3] = (uint32_t)v.w;
+    }
+    __device__ static __forceinline__ void store(int32_t* base, int64_t i, const uint32_t s[4]) {
+        st_stream4(base + i, make_int4((int)s[0], (int)s[1], (int)s[2], (int)s[3]));
+    }
+};
+template <> struct StateVec<uint64_t> {
+    int4 v0, v1;
+    __device__ __forceinline__ void load(const int32_t* base, int64_t i) {
+        v0 = ld_stream4(base + 2 * i);
+        v1 = ld_stream4(base + 2 * i + 4);
+    }
+    __device__ __forceinline__ void unpack(uint64_t s[4]) const {
+        s[0] = (uint32_t)v0.x | ((uint64_t)(uint32_t)v0.y << 32); s[1] = (uint32_t)v0.z | ((uint64_t)(uint32_t)v0.w << 32);
+        s[2] = (uint32_t)v1.x | ((uint64_t)(uint32_t)v1.y << 32); s[3] = (uint32_t)v1.z | ((uint64_t)(uint32_t)v1.w << 32);
+    }
+    __device__ static __forceinline__ void store(int32_t* base, int64_t i, const uint64_t s[4]) {
+        st_stream4(base + 2 * i, make_int4((int)(uint32_t)s[0], (int)(s[0] >> 32), (int)(uint32_t)s[1], (int)(s[1] >> 32)));
+        st_stream4(base + 2 * i + 4, make_int4((int)(uint32_t)s[2], (int)(s[2] >> 32), (int)(uint32_t)s[3], (int)(s[3] >> 32)));
+    }
+};
 __device__ __forceinline__ uint32_t load_state1(const int32_t* base, int64_t i, uint32_t) { return (uint32_t)base[i]; }
 __device__ __forceinline__ uint64_t load_state1(const int32_t* base, int64_t i, uint64_t) {
     return (uint32_t)base[2 * i] | ((uint64_t)(uint32_t)base[2 * i + 1] << 32);
@@ -179,56 +260,73 @@ __device__ __forceinline__ void store_state1(int32_t* base, int64_t i, uint64_t 
 }
 
 // ----------------------------------------------------------------- step (streams) ---
-// kVec: all six arrays are 16-byte aligned -> 4 envs per thread with vector accesses;
-// otherwise a scalar thread-per-env path (only reached for oddly offset views).
+// kVec: all six arrays are 16-byte aligned and global_offset is a multiple of 4 -> every
+// thread owns aligned groups of FOUR envs (16-byte vector loads/stores, one Philox call per
+// draw slot per group).  The loop is software-pipelined: the loads of a thread's next group
+// are issued before the current group is computed, so two groups' worth of bytes per
+// thread are in flight.  Otherwise: scalar thread-per-env path (oddly offset views).
 template <class Env, bool kVec>
-__global__ void __launch_bounds__(POMDP_THREADS)
-pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const RockTable* __restrict__ g_table,
+__global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
+pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
                   const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
                   int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n,
-                  uint64_t goff, uint64_t seed, uint32_t step_ctr) {
+                  uint64_t goff, uint64_t seed, uint32_t step_ctr, uint32_t table_bytes) {
     typedef typename Env::State S;
-    __shared__ alignas(16) RockTable tbl;
+    extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
-    const RockTable* t = nullptr;
+    const uint32_t* lut = nullptr;
     if (Env::kTable) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
-            mbar_expect_tx(&bar, (uint32_t)sizeof(RockTable));
-            tma_bulk_g2s(&tbl, g_table, (uint32_t)sizeof(RockTable), &bar);
+            mbar_expect_tx(&bar, table_bytes);
+            tma_bulk_g2s(smem_table, g_table, table_bytes, &bar);
         }
         __syncthreads();   // barrier object initialised before anyone polls it
-        t = &tbl;
+        lut = reinterpret_cast<const uint32_t*>(smem_table + sizeof(RockTableHdr));
     }
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     bool table_ready = !Env::kTable;
     if (kVec) {
         const int64_t n_groups = n >> 2;
-        for (int64_t g = tid; g < n_groups; g += nthreads) {
+        const uint64_t group0 = goff >> 2;
+        int64_t g = tid;
+        StateVec<S> cur_s;
+        int4 cur_a = make_int4(0, 0, 0, 0);
+        if (g < n_groups) {
+            cur_s.load(state, g << 2);
+            cur_a = ld_stream4(action + (g << 2));
+        }
+        if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }   // the loads above are already in flight
+        while (g < n_groups) {
+            const int64_t gn = g + nthreads;
+            StateVec<S> nxt_s = cur_s;
+            int4 nxt_a = cur_a;
+            if (gn < n_groups) {
+                nxt_s.load(state, gn << 2);
+                nxt_a = ld_stream4(action + (gn << 2));
+            }
             const int64_t i = g << 2;
             S s[4], s2[4];
-            load_states4(state, i, s);
-            const int4 av = ld_stream4(action + i);
-            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }   // loads above are already in flight
-            const int32_t a[4] = {av.x, av.y, av.z, av.w};
+            cur_s.unpack(s);
+            const int32_t a[4] = {cur_a.x, cur_a.y, cur_a.z, cur_a.w};
             int32_t ob[4], fl[4];
             float rw[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                Env::step(p, t, s[j], a[j], seed, goff + (uint64_t)(i + j), step_ctr, s2[j], ob[j], rw[j], fl[j]);
-            store_states4(next_state, i, s2);
+            Env::step4(p, lut, s, a, seed, group0 + (uint64_t)g, step_ctr, s2, ob, rw, fl);
+            StateVec<S>::store(next_state, i, s2);
             st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
             st_stream4(reward + i, make_float4(rw[0], rw[1], rw[2], rw[3]));
             st_stream4(flags + i, make_int4(fl[0], fl[1], fl[2], fl[3]));
+            cur_s = nxt_s;
+            cur_a = nxt_a;
+            g = gn;
         }
         // tail (n % 4 envs): the first few threads of the grid
         const int64_t i = (n_groups << 2) + tid;
         if (i < n) {
-            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
             S s2; int32_t ob, fl; float rw;
-            Env::step(p, t, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+            Env::step1(p, lut, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
             store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
         }
     } else {
@@ -237,7 +335,7 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const RockTabl
             const int32_t a = action[i];
             if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
             S s2; int32_t ob, fl; float rw;
-            Env::step(p, t, s, a, seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+            Env::step1(p, lut, s, a, seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
             store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
         }
     }
@@ -246,17 +344,47 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const RockTabl
 }
 
 // ---------------------------------------------------------------- reset (streams) ---
-template <class Env>
+// kVec (state 16-byte aligned, global_offset % 4 == 0): four envs per thread, one Philox call
+// per draw slot per group, vector stores when the whole group is reset.
+template <class Env, bool kVec>
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __restrict__ state,
                    int32_t* __restrict__ obs, const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
                    uint64_t seed, uint32_t step_ctr) {
     typedef typename Env::State S;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+    int64_t scalar_from = 0;
+    if (kVec) {
+        const int64_t n_groups = n >> 2;
+        const bool obs_vec = obs && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
+        for (int64_t g = tid; g < n_groups; g += nthreads) {
+            const int64_t i = g << 2;
+            bool m[4] = {true, true, true, true};
+            if (mask) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = mask[i + j] != 0;
+            }
+            if (!(m[0] || m[1] || m[2] || m[3])) continue;
+            S s[4];
+            int32_t ob[4];
+            Env::reset4(p, seed, (goff >> 2) + (uint64_t)g, step_ctr, s, ob);
+            if (m[0] && m[1] && m[2] && m[3]) {
+                StateVec<S>::store(state, i, s);
+                if (obs_vec) st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
+                else if (obs) { obs[i] = ob[0]; obs[i + 1] = ob[1]; obs[i + 2] = ob[2]; obs[i + 3] = ob[3]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m[j]) { store_state1(state, i + j, s[j]); if (obs) obs[i + j] = ob[j]; }
+            }
+        }
+        scalar_from = n_groups << 2;
+    }
+    for (int64_t i = scalar_from + tid; i < n; i += nthreads) {
         if (mask && !mask[i]) continue;
         S s; int32_t ob;
-        Env::reset(p, seed, goff + (uint64_t)i, step_ctr, s, ob);
+        Env::reset1(p, seed, goff + (uint64_t)i, step_ctr, s, ob);
         store_state1(state, i, s);
         if (obs) obs[i] = ob;
     }
@@ -347,12 +475,9 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
         if (mask && !mask[i]) continue;       // warp-uniform
         ShipState st;
         st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
-        const U4 r = draw_block(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, 0);
-        U4 r_hi = r;
         bool ok_all = true;
         int ship = 0;
         for (int length = p.max_len; length >= 2; --length, ++ship) {
-            if (ship == 4) r_hi = draw_block(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, 1);
             const u128 blocked = ship_blocked(p, st.occ);
             uint32_t mine = 0;                // bit j: candidate lane + 32 j is accepted
             int total = 0;
@@ -363,7 +488,7 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
                 total += __popc(__ballot_sync(0xffffffffu, ok));
             }
             if (total == 0) { ok_all = false; break; }   // the reference would loop forever
-            const uint32_t w = ship < 4 ? word_of(r, ship) : word_of(r_hi, ship & 3);
+            const uint32_t w = draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, (uint32_t)ship);   // warp-uniform
             int k = (int)rand_below(w, (uint32_t)total);
             int chosen = -1;
             for (int j = 0; j < n_iter; ++j) {
@@ -484,21 +609,22 @@ inline int device_sms() {
 }
 
 // Persistent grid: enough CTAs to fill every SM with the kernel's resident-CTA count
-// (occupancy queried once per kernel and cached by kernel address).
+// (occupancy queried once per (kernel, CTA size, dynamic smem) and cached).
 template <class K>
-inline int grid_for(K kernel, int64_t n_threads_needed) {
-    struct Entry { const void* fn; int per_sm; };
-    static thread_local Entry cache[32];
+inline int grid_for(K kernel, int64_t n_threads_needed, int threads = POMDP_THREADS, size_t smem = 0) {
+    struct Entry { const void* fn; int threads; size_t smem; int per_sm; };
+    static thread_local Entry cache[48];
     static thread_local int n_cached = 0;
     int per_sm = 0;
     for (int i = 0; i < n_cached; ++i)
-        if (cache[i].fn == (const void*)kernel) per_sm = cache[i].per_sm;
+        if (cache[i].fn == (const void*)kernel && cache[i].threads == threads && cache[i].smem == smem)
+            per_sm = cache[i].per_sm;
     if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, POMDP_THREADS, 0) != cudaSuccess || per_sm <= 0)
-            per_sm = 4;
-        if (n_cached < 32) cache[n_cached++] = Entry{(const void*)kernel, per_sm};
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm <= 0)
+            per_sm = 2;
+        if (n_cached < 48) cache[n_cached++] = Entry{(const void*)kernel, threads, smem, per_sm};
     }
-    int64_t need = (n_threads_needed + POMDP_THREADS - 1) / POMDP_THREADS;
+    int64_t need = (n_threads_needed + threads - 1) / threads;
     const int64_t cap = (int64_t)device_sms() * per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
@@ -515,26 +641,27 @@ inline bool aligned16(const void* a, const void* b, const void* c, const void* d
 }
 
 template <class Env>
-int launch_step(const typename Env::Params& p, const void* d_table, const int32_t* state, const int32_t* action,
-                int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
-                uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
+int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, const int32_t* state,
+                const int32_t* action, int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
+                int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
     int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
     if (rc) return rc;
     if (n == 0) return 0;
+    if (goff < 0) return host::fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
     if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
         return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
     cudaStream_t st = (cudaStream_t)stream;
-    const RockTable* tb = (const RockTable*)d_table;
-    if (aligned16(state, action, next_state, obs, reward, flags)) {
+    const size_t smem = Env::kTable ? table_bytes : 0;
+    if (aligned16(state, action, next_state, obs, reward, flags) && (goff & 3) == 0) {
         auto k = pomdp_step_kernel<Env, true>;
-        const int grid = grid_for(k, (n + 3) >> 2);
-        k<<<grid, POMDP_THREADS, 0, st>>>(p, tb, state, action, next_state, obs, reward, flags, n, (uint64_t)goff, seed,
-                                         step_ctr);
+        const int grid = grid_for(k, (n + 3) >> 2, POMDP_STEP_THREADS, smem);
+        k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
+                                                  (uint64_t)goff, seed, step_ctr, table_bytes);
     } else {
         auto k = pomdp_step_kernel<Env, false>;
-        const int grid = grid_for(k, n);
-        k<<<grid, POMDP_THREADS, 0, st>>>(p, tb, state, action, next_state, obs, reward, flags, n, (uint64_t)goff, seed,
-                                         step_ctr);
+        const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
+        k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
+                                                  (uint64_t)goff, seed, step_ctr, table_bytes);
     }
     return finish(what);
 }
@@ -544,9 +671,16 @@ int launch_reset(const typename Env::Params& p, int32_t* state, int32_t* obs, co
                  int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
     if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "%s: bad n or NULL state", what);
     if (n == 0) return 0;
-    auto k = pomdp_reset_kernel<Env>;
-    const int grid = grid_for(k, n);
-    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+    if (goff < 0) return host::fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
+    if ((((uintptr_t)state) & 15) == 0 && (goff & 3) == 0) {
+        auto k = pomdp_reset_kernel<Env, true>;
+        const int grid = grid_for(k, (n + 3) >> 2);
+        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+    } else {
+        auto k = pomdp_reset_kernel<Env, false>;
+        const int grid = grid_for(k, n);
+        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+    }
     return finish(what);
 }
 
@@ -562,11 +696,14 @@ int pomdp_rock_state_words(const PomdpRockParams* q) {
     int rc = host::make_rock(q, nullptr, nullptr);
     return rc ? rc : host::rock_words(q);
 }
-int64_t pomdp_rock_table_bytes(void) { return (int64_t)sizeof(RockTable); }
+int64_t pomdp_rock_table_bytes(const PomdpRockParams* q) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    return rc ? (int64_t)rc : host::rock_table_bytes(q);
+}
 int pomdp_rock_build_table(const PomdpRockParams* q, void* host_table) {
     if (!host_table) return host::fail(POMDP_E_BADARG, "rock: host_table is NULL");
     RockDev d;
-    return host::make_rock(q, &d, (RockTable*)host_table);
+    return host::make_rock(q, &d, host_table);
 }
 int pomdp_rock_step(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* action,
                     int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
@@ -575,10 +712,10 @@ int pomdp_rock_step(const PomdpRockParams* q, const void* d_table, const int32_t
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
     if (host::rock_words(q) == 1)
-        return launch_step<RockEnv1>(d, d_table, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
-                                     stream, "pomdp_rock_step");
-    return launch_step<RockEnv2>(d, d_table, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
-                                 stream, "pomdp_rock_step");
+        return launch_step<RockEnv1>(d, d_table, d.table_bytes, state, action, next_state, obs, reward, flags, n, goff,
+                                     seed, step_ctr, stream, "pomdp_rock_step");
+    return launch_step<RockEnv2>(d, d_table, d.table_bytes, state, action, next_state, obs, reward, flags, n, goff, seed,
+                                 step_ctr, stream, "pomdp_rock_step");
 }
 int pomdp_rock_reset(const PomdpRockParams* q, const void* d_table, int32_t* state, int32_t* obs, const uint8_t* mask,
                      int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
@@ -598,15 +735,20 @@ int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t*
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    return launch_step<TagEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
-                                stream, "pomdp_tag_step");
+    if (d.n_opp == 1)
+        return launch_step<TagEnvT<1>>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed,
+                                       step_ctr, stream, "pomdp_tag_step");
+    return launch_step<TagEnvT<4>>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                   stream, "pomdp_tag_step");
 }
 int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
                     uint64_t seed, uint32_t step_ctr, void* stream) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    return launch_reset<TagEnvP>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_tag_reset");
+    if (d.n_opp == 1)
+        return launch_reset<TagEnvT<1>>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_tag_reset");
+    return launch_reset<TagEnvT<4>>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_tag_reset");
 }
 
 // ---- Tiger
@@ -616,7 +758,7 @@ int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int3
     TigerDev d;
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
-    return launch_step<TigerEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<TigerEnvP>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                   stream, "pomdp_tiger_step");
 }
 int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
@@ -634,7 +776,7 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
-    return launch_step<NetworkEnvP>(d, nullptr, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<NetworkEnvP>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                     stream, "pomdp_network_step");
 }
 int pomdp_network_reset(const PomdpNetworkParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,

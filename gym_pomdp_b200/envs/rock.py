@@ -34,11 +34,11 @@ class RockEnv(BatchedPomdpEnv):
         # rock.py:101 -- the reference asserts on an unknown configuration
         assert words > 0, L.pomdp_last_error().decode()
         self.state_words = words
-        nbytes = L.pomdp_rock_table_bytes()
+        nbytes = L.pomdp_rock_table_bytes(ctypes.byref(self._params))
         host = np.zeros(nbytes, dtype=np.uint8)
         _lib.check(L.pomdp_rock_build_table(ctypes.byref(self._params), host.ctypes.data), "pomdp_rock_build_table")
         self._table_host = host
-        self._table = torch.from_numpy(host.copy()).to(self.device)   # 400 B, staged to smem by TMA per CTA
+        self._table = torch.from_numpy(host.copy()).to(self.device)   # header + LUT, staged to smem by TMA per CTA
         self._grid_map = host[:256].view(np.int8)                     # [x | y << 4] -> rock id
         self._rock_pos = [Coord(int(b) & 15, int(b) >> 4) for b in host[256:256 + num_rocks]]
         thr_m1 = host[272:400].view(np.uint32)

@@ -36,11 +36,15 @@
  *    An env with an error flag is left unchanged with obs 0 and reward 0 (BAD_STATE on a
  *    Rock sample is treated as "no rock here").
  *  - Randomness: stateless Philox4x32-10.  The word for draw slot j of env i is
- *        philox(key = seed, ctr = (lo32(g), hi32(g), step_ctr, (domain<<24) | (j>>2)))[j&3]
- *    with g = global_offset + i, domain 0 for step and 1 for reset.  Results therefore do
- *    not depend on how a batch is sharded across GPUs.  Slot tables and the word->decision
- *    rules (u = r / 2^32;  binomial(1,p) = [u < p];  randint(n) = floor(u*n)) are listed
- *    per env in DESIGN.md and mirror the reference's np.random call sites.
+ *        philox(key = seed, ctr = (lo32(g>>2), hi32(g>>2), step_ctr, (domain<<24) | j))[g & 3]
+ *    with g = global_offset + i, domain 0 for step and 1 for reset: one Philox block holds
+ *    the same slot of four consecutive envs, so a thread that owns an aligned group of
+ *    four pays one Philox call per slot.  Results do not depend on how a batch is sharded
+ *    across GPUs (shards whose global_offset is a multiple of 4 take the vector path; any
+ *    other offset is still correct, on the scalar path).  Slot tables and the
+ *    word->decision rules (u = r / 2^32;  binomial(1,p) = [u < p];  randint(n) =
+ *    floor(u*n)) are listed per env in DESIGN.md and mirror the reference's np.random
+ *    call sites.
  *  - No CPU fallback: every compute entry point launches CUDA kernels and fails with a
  *    CUDA error when no device is present.
  */
@@ -53,7 +57,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 1
+#define POMDP_ABI_VERSION 2
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -80,10 +84,13 @@ typedef struct PomdpRockParams {
  *   bits 0-3 agent x, bits 4-7 agent y, bits 8+2i..9+2i rock i status as a 2-bit two's
  *   complement code (0b11 = -1 bad, 0b00 = 0 collected, 0b01 = +1 good), top bit = done. */
 int     pomdp_rock_state_words(const PomdpRockParams* params);
-/* Static per-config maps (rock-id grid, rock coordinates, sensor thresholds) that the
- * kernels stage into shared memory with one TMA bulk copy per block.  The caller uploads
- * the filled buffer to the device (16-byte aligned) and passes it as `d_table`.          */
-int64_t pomdp_rock_table_bytes(void);
+/* Static per-config maps that the step kernel stages into shared memory with one TMA bulk
+ * copy per CTA: a 400-byte header (rock-id grid, rock coordinates, sensor thresholds: the
+ * reference's own tables) followed by the transition LUT indexed by (agent cell, action)
+ * (16.4 KB for <= 11 rocks, 32.8 KB otherwise; layout in gym_pomdp_b200/csrc/pomdp_core.h).
+ * The caller uploads the filled buffer to the device (16-byte aligned) and passes it as
+ * `d_table`.                                                                              */
+int64_t pomdp_rock_table_bytes(const PomdpRockParams* params);
 int     pomdp_rock_build_table(const PomdpRockParams* params, void* host_table);
 /* RockEnv.step rock.py:123-194 / StochasticRockEnv.step rock.py:434-504.
  * Draw slots: 0 = p_move gate (stochastic only), 1 = sensor Bernoulli (rock.py:404).     */

@@ -15,11 +15,13 @@ Draw-slot contract shared by the kernels, the C oracle and this file::
 
     word(seed, env, step, domain, slot) =
         philox4x32_10(key=(seed & 0xffffffff, seed >> 32),
-                      ctr=(env & 0xffffffff, env >> 32, step, (domain << 24) | (slot >> 2))
-                     )[slot & 3]
+                      ctr=(g & 0xffffffff, g >> 32, step, (domain << 24) | slot)
+                     )[env & 3]          with g = env >> 2
 
-``env`` is the GLOBAL env index (shard-invariant), ``step`` the caller's step counter,
-``domain`` 0 for step(), 1 for reset().
+i.e. one Philox block holds the SAME slot of FOUR consecutive envs (a GPU thread owns an
+aligned group of four envs and pays one Philox call per slot).  ``env`` is the GLOBAL env
+index (shard-invariant), ``step`` the caller's step counter, ``domain`` 0 for step(), 1
+for reset().
 """
 import numpy as np
 
@@ -54,26 +56,25 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
             c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def draw_block(seed, env, step, domain, block):
-    """One 4-word Philox block per env; env may be an array of global indices."""
-    env = np.asarray(env, dtype=np.uint64)
+def draw_quad(seed, group, step, domain, slot):
+    """One 4-word Philox block per draw group (= 4 consecutive envs); group may be an array."""
+    group = np.asarray(group, dtype=np.uint64)
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    return philox4x32_10(env & MASK, env >> np.uint64(32),
+    return philox4x32_10(group & MASK, group >> np.uint64(32),
                          np.uint64(int(step) & 0xFFFFFFFF),
-                         np.uint64(((int(domain) & 0xFF) << 24) | (int(block) & 0xFFFFFF)),
+                         np.uint64(((int(domain) & 0xFF) << 24) | (int(slot) & 0xFFFFFF)),
                          seed & 0xFFFFFFFF, seed >> 32)
 
 
 def draw_slots(seed, env, step, domain, n_slots):
-    """uint32 array [len(env), n_slots] of draw words, slot-major per the contract."""
+    """uint32 array [len(env), n_slots] of draw words per the contract above."""
     env = np.atleast_1d(np.asarray(env, dtype=np.uint64))
     out = np.empty((env.shape[0], n_slots), dtype=np.uint32)
-    for b in range((n_slots + 3) // 4):
-        words = draw_block(seed, env, step, domain, b)
-        for j in range(4):
-            s = 4 * b + j
-            if s < n_slots:
-                out[:, s] = words[j]
+    lane = (env & np.uint64(3)).astype(np.int64)
+    rows = np.arange(env.shape[0])
+    for s in range(n_slots):
+        words = np.stack(draw_quad(seed, env >> np.uint64(2), step, domain, s), axis=1)
+        out[:, s] = words[rows, lane]
     return out
 
 

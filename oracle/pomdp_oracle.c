@@ -52,15 +52,17 @@ void oracle_philox_kat(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     philox4x32_10(out, key[0], key[1]);
 }
 
-/* word(seed, env, step, domain, slot) per include/pomdp_b200.h; out is [n, n_slots]. */
+/* word(seed, env, step, domain, slot) per include/pomdp_b200.h: one Philox block holds the
+ * same slot of four consecutive envs (counter = env >> 2, word = env & 3).  out is [n, n_slots]. */
 void oracle_fill_draws(uint64_t seed, uint64_t global_offset, int64_t n, uint32_t step, uint32_t domain,
                        int n_slots, uint32_t* out) {
     for (int64_t i = 0; i < n; ++i) {
-        uint64_t env = global_offset + (uint64_t)i;
-        for (int b = 0; 4 * b < n_slots; ++b) {
-            uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), step, (domain << 24) | (uint32_t)b};
+        const uint64_t env = global_offset + (uint64_t)i;
+        const uint64_t group = env >> 2;
+        for (int slot = 0; slot < n_slots; ++slot) {
+            uint32_t c[4] = {(uint32_t)group, (uint32_t)(group >> 32), step, (domain << 24) | (uint32_t)slot};
             philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-            for (int j = 0; j < 4 && 4 * b + j < n_slots; ++j) out[i * n_slots + 4 * b + j] = c[j];
+            out[i * n_slots + slot] = c[env & 3];
         }
     }
 }

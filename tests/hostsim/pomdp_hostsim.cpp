@@ -26,11 +26,15 @@ void store_state(int32_t* base, int64_t i, uint32_t s) { base[i] = (int32_t)s; }
 void store_state(int32_t* base, int64_t i, uint64_t s) { base[2 * i] = (int32_t)(uint32_t)s; base[2 * i + 1] = (int32_t)(s >> 32); }
 
 template <typename S>
-int rock_step_host(const RockDev& d, const RockTable* t, const int32_t* state, const int32_t* action, int32_t* next,
+int rock_step_host(const RockDev& d, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
                    int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step) {
+    const uint32_t* lut = (const uint32_t*)((const char*)table + sizeof(RockTableHdr));
     for (int64_t i = 0; i < n; ++i) {
         S s2;
-        rock_step<S>(d, t, load_state<S>(state, i), action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        const uint64_t env = (uint64_t)(goff + i);
+        const uint32_t wg = d.stochastic ? draw_word(seed, env, step, DOMAIN_STEP, 0) : 0u;
+        const uint32_t ws = draw_word(seed, env, step, DOMAIN_STEP, 1);
+        rock_step<S>(d, lut, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
         store_state(next, i, s2);
     }
     return 0;
@@ -47,11 +51,14 @@ int pomdp_rock_state_words(const PomdpRockParams* q) {
     int rc = host::make_rock(q, nullptr, nullptr);
     return rc ? rc : host::rock_words(q);
 }
-int64_t pomdp_rock_table_bytes(void) { return (int64_t)sizeof(RockTable); }
+int64_t pomdp_rock_table_bytes(const PomdpRockParams* q) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    return rc ? (int64_t)rc : host::rock_table_bytes(q);
+}
 int pomdp_rock_build_table(const PomdpRockParams* q, void* host_table) {
     if (!host_table) return host::fail(POMDP_E_BADARG, "rock: host_table is NULL");
     RockDev d;
-    return host::make_rock(q, &d, (RockTable*)host_table);
+    return host::make_rock(q, &d, host_table);
 }
 int pomdp_rock_step(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action,
                     int32_t* next, int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed,
@@ -62,7 +69,7 @@ int pomdp_rock_step(const PomdpRockParams* q, const void* table, const int32_t* 
     rc = host::check_io(state, action, next, obs, rw, fl, n);
     if (rc) return rc;
     if (!table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
-    const RockTable* t = (const RockTable*)table;
+    const void* t = table;
     return host::rock_words(q) == 1 ? rock_step_host<uint32_t>(d, t, state, action, next, obs, rw, fl, n, goff, seed, step)
                                     : rock_step_host<uint64_t>(d, t, state, action, next, obs, rw, fl, n, goff, seed, step);
 }
@@ -73,8 +80,9 @@ int pomdp_rock_reset(const PomdpRockParams* q, const void*, int32_t* state, int3
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
-        if (host::rock_words(q) == 1) store_state(state, i, rock_reset<uint32_t>(d, seed, (uint64_t)(goff + i), step));
-        else store_state(state, i, rock_reset<uint64_t>(d, seed, (uint64_t)(goff + i), step));
+        const LazyDraw draw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET};
+        if (host::rock_words(q) == 1) store_state(state, i, rock_reset<uint32_t>(d, draw));
+        else store_state(state, i, rock_reset<uint64_t>(d, draw));
         if (obs) obs[i] = 0;
     }
     return 0;
@@ -89,7 +97,7 @@ int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t*
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s2;
-        tag_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        tag_step(d, (uint32_t)state[i], action[i], LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -102,7 +110,7 @@ int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         uint32_t s; int32_t ob;
-        tag_reset(d, seed, (uint64_t)(goff + i), step, s, ob);
+        tag_reset(d, LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
         state[i] = (int32_t)s;
         if (obs) obs[i] = ob;
     }
@@ -118,7 +126,7 @@ int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int3
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s2;
-        tiger_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        tiger_step(d, (uint32_t)state[i], action[i], LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -131,7 +139,7 @@ int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, c
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         uint32_t s; int32_t ob;
-        tiger_reset(seed, (uint64_t)(goff + i), step, s, ob);
+        tiger_reset(LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
         state[i] = (int32_t)s;
         if (obs) obs[i] = ob;
     }
@@ -147,8 +155,18 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
     rc = host::check_io(state, action, next, obs, rw, fl, n);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
-        uint32_t s2;
-        network_step(d, (uint32_t)state[i], action[i], seed, (uint64_t)(goff + i), step, s2, obs[i], rw[i], fl[i]);
+        // alternate the two flavours the kernels use: aligned groups of four, and single envs
+        const uint64_t env = (uint64_t)(goff + i);
+        if ((env & 3) == 0 && i + 4 <= n && ((i >> 2) & 1) == 0) {
+            uint32_t s4[4], s2[4];
+            for (int j = 0; j < 4; ++j) s4[j] = (uint32_t)state[i + j];
+            network_step_n<4>(d, s4, action + i, seed, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
+            for (int j = 0; j < 4; ++j) next[i + j] = (int32_t)s2[j];
+            i += 3;
+            continue;
+        }
+        uint32_t s1 = (uint32_t)state[i], s2;
+        network_step_n<1>(d, &s1, action + i, seed, env >> 2, (int)(env & 3), step, &s2, obs + i, rw + i, fl + i);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -193,12 +211,11 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
         bool ok_all = true;
         int ship = 0;
         for (int length = d.max_len; length >= 2 && ok_all; --length, ++ship) {
-            const U4 r = draw_block(seed, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)(ship >> 2));
             const u128 blocked = ship_blocked(d, st.occ);
             int total = 0;
             for (int c = 0; c < 4 * d.n_tiles; ++c) total += ship_candidate_ok(d, blocked, c >> 2, c & 3, length);
             if (total == 0) { ok_all = false; break; }
-            int k = (int)rand_below(word_of(r, ship & 3), (uint32_t)total);
+            int k = (int)rand_below(draw_word(seed, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total);
             for (int c = 0; c < 4 * d.n_tiles; ++c)
                 if (ship_candidate_ok(d, blocked, c >> 2, c & 3, length) && k-- == 0) { ship_mark(d, st, c >> 2, c & 3, length); break; }
         }
