@@ -39,19 +39,29 @@ POMDP_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-POMDP_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+// The ten round keys (k + i * Weyl constant) are computed once per call on the host and reach
+// the kernels as a __grid_constant__ parameter, so on the device they are constant-bank
+// operands of the round's LOP3: a Philox round is 2 IMAD.WIDE + 2 LOP3 and nothing else.
+struct PhiloxKey { uint32_t k0[10], k1[10]; };
+
+POMDP_HD PhiloxKey philox_key(uint64_t seed) {
+    PhiloxKey k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) { k.k0[i] = a; k.k1[i] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return k;
+}
+
+POMDP_HD U4 philox4x32_10(U4 c, const PhiloxKey& key) {
     POMDP_UNROLL
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         U4 nx;
-        nx.x = hi1 ^ c.y ^ k0;
+        nx.x = hi1 ^ c.y ^ key.k0[i];
         nx.y = lo1;
-        nx.z = hi0 ^ c.w ^ k1;
+        nx.z = hi0 ^ c.w ^ key.k1[i];
         nx.w = lo0;
         c = nx;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return c;
 }
@@ -60,26 +70,27 @@ POMDP_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 // consecutive env instances -- word(env, slot) = philox(key = seed,
 // ctr = (lo32(env >> 2), hi32(env >> 2), step, (domain << 24) | slot))[env & 3] -- so a thread
 // that owns an aligned group of four envs pays one Philox call per slot, not one per env.
-POMDP_HD U4 draw_quad(uint64_t seed, uint64_t group, uint32_t step, uint32_t domain, uint32_t slot) {
+POMDP_HD U4 draw_quad(const PhiloxKey& seed, uint64_t group, uint32_t step, uint32_t domain, uint32_t slot) {
     U4 c;
     c.x = (uint32_t)group;
     c.y = (uint32_t)(group >> 32);
     c.z = step;
     c.w = (domain << 24) | slot;
-    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32_10(c, seed);
 }
 
 POMDP_HD uint32_t word_of(const U4& r, int j) { return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w; }
 
-POMDP_HD uint32_t draw_word(uint64_t seed, uint64_t env, uint32_t step, uint32_t domain, uint32_t slot) {
+POMDP_HD uint32_t draw_word(const PhiloxKey& seed, uint64_t env, uint32_t step, uint32_t domain, uint32_t slot) {
     return word_of(draw_quad(seed, env >> 2, step, domain, slot), (int)(env & 3));
 }
 
 // Draw providers handed to the per-env functors: draw(slot) -> uint32 word.
 struct LazyDraw {          // scalar paths: one Philox call per requested slot
-    uint64_t seed, env;
+    const PhiloxKey* key;
+    uint64_t env;
     uint32_t step, domain;
-    POMDP_HD uint32_t operator()(int slot) const { return draw_word(seed, env, step, domain, (uint32_t)slot); }
+    POMDP_HD uint32_t operator()(int slot) const { return draw_word(*key, env, step, domain, (uint32_t)slot); }
 };
 template <int N>
 struct WordDraw {          // vector path: words precomputed from the group's quads
@@ -124,20 +135,34 @@ POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y -
 
 // ====================================================================== RockSample ===
 // Static maps of one Rock configuration, built on the host (pomdp_host.h: make_rock) and
-// staged into shared memory by ONE TMA bulk copy per CTA:
-//   RockTableHdr (400 B)  -- the reference's own maps (grid, rock coordinates, sensor thresholds)
-//   uint32 lut[256 << na_shift]  -- the transition table the step functor reads: ONE shared-
-//       memory load per env, indexed by (agent cell = x | y << 4, action):
-//         a in 0..3 (move)   bits 0-7 next cell, bits 8-15 reward (int8), bit 16 done
-//         a == 4   (sample)  bits 0-5 bit offset of the status of the rock under the agent
-//                            (ROCK_NONE_SH<S> when there is none), bit 8 = dangling grid id
-//         a >= 5   (check)   ceil(eff(d) * 2^32) - 1 for d = L1(agent, rock a-5)  (rock.py:383-387)
+// staged into shared memory by ONE TMA bulk copy per CTA.  Byte layout:
+//   RockTableHdr (400 B)        the reference's own maps (grid, rock coordinates, sensor thresholds)
+//   RockEntry rtab[64]          results: 8 rows x 8 entries, entry = row + 2 * status code + truthful
+//   RockEntry special[8]        3 used: NOOP (failed p_move gate), STEPPED_DONE, BAD_ACTION
+//   RockEntry lut[rows << NA]   transitions, indexed by (agent cell = x | y << 4, action); only
+//                               the rows of reachable cells (16 * (n-1) + n of 256) are stored/copied
+// The step functor is two dependent 8-byte shared-memory loads and ~20 integer instructions,
+// identical for every action class -- no divergence, no int->float conversion.
+//   lut entry:  x = ceil(eff(d) * 2^32) - 1 for a check of rock a-5 at L1 distance d (rock.py:383-387),
+//                   0xFFFFFFFF otherwise
+//               y = byte 0: (bit offset of the status this action looks at) - 1   [none: RockBits::NONE_SH1]
+//                   byte 1: cell ^ next cell (moves), byte 2: 6 if the status is cleared (sample), byte 3: rtab row
+//   rtab entry: x = reward as float bits, y = flags | obs << 8 | done << 31
 struct RockTableHdr {
     int8_t grid[256];      // [x | y << 4] -> rock id written by rock.py:110-111, -1 = none
     uint8_t rock_pos[16];  // rock i -> x | y << 4   (rock.py:106)
     uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2
 };
 static_assert(sizeof(RockTableHdr) == 400 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+struct alignas(8) RockEntry { uint32_t x, y; };
+
+enum : uint32_t {   // rtab rows (multiples of 8) and special lut entries
+    ROCK_ROW_ZERO = 0, ROCK_ROW_EXIT = 8, ROCK_ROW_WALL = 16, ROCK_ROW_SAMPLE = 24, ROCK_ROW_DANGLING = 32,
+    ROCK_ROW_CHECK = 40, ROCK_ROW_STEPPED_DONE = 48, ROCK_ROW_BAD_ACTION = 56, ROCK_RTAB_ENTRIES = 64,
+    ROCK_IDX_NOOP = 0, ROCK_IDX_STEPPED_DONE = 1, ROCK_IDX_BAD_ACTION = 2, ROCK_SPECIALS = 8,
+};
+constexpr uint32_t ROCK_RTAB_OFFSET = sizeof(RockTableHdr);
+constexpr uint32_t ROCK_LUT_OFFSET = ROCK_RTAB_OFFSET + ROCK_RTAB_ENTRIES * sizeof(RockEntry);   // specials, then rows
 
 struct RockDev {  // passed by value to the kernels
     int32_t n, k;
@@ -145,17 +170,26 @@ struct RockDev {  // passed by value to the kernels
     int32_t penal;        // rock.py:117 (-100) / rock.py:432 (0)
     uint32_t start;       // x | y << 4 of config init_pos
     uint32_t n_actions;   // 5 + k (rock.py:113)
-    uint32_t na_shift;    // log2 of the LUT row length: 4 (<= 16 actions) or 5
-    uint32_t table_bytes; // sizeof(RockTableHdr) + 4 * (256 << na_shift)
-    uint64_t move_T;      // ceil(p_move * 2^32)
+    uint32_t table_bytes; // bytes the TMA copy moves (header + rtab + specials + stored rows)
+    uint32_t smem_bytes;  // shared-memory allocation: room for all 256 rows, so that a corrupt
+                          // cell index reads garbage instead of faulting
+    uint32_t gate_on;     // p_move > 0
+    uint32_t gate_thr_m1; // ceil(p_move * 2^32) - 1
 };
 
 template <typename S> struct RockBits;
-template <> struct RockBits<uint32_t> { static constexpr uint32_t DONE = 0x80000000u; static constexpr uint32_t NONE_SH = 30; };
-template <> struct RockBits<uint64_t> { static constexpr uint64_t DONE = 0x8000000000000000ull; static constexpr uint32_t NONE_SH = 62; };
+template <> struct RockBits<uint32_t> {
+    static constexpr uint32_t DONE = 0x80000000u;
+    static constexpr uint32_t NONE_SH1 = 29;   // bits 30-31: unused / done (0 in a steppable state)
+    static constexpr uint32_t NA_SHIFT = 4;    // <= 11 rocks -> <= 16 actions
+};
+template <> struct RockBits<uint64_t> {
+    static constexpr uint64_t DONE = 0x8000000000000000ull;
+    static constexpr uint32_t NONE_SH1 = 61;
+    static constexpr uint32_t NA_SHIFT = 5;    // 12..15 rocks -> <= 20 actions
+};
 
-// shifts whose count wraps at the word size (one SHF on the GPU; the LUT's sample offset is
-// garbage for the other action classes and must not be undefined behaviour)
+// shifts whose count wraps at the word size (one SHF on the GPU)
 POMDP_HD uint32_t shr_wrap(uint32_t v, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(v, 0u, sh);
@@ -172,46 +206,38 @@ POMDP_HD uint32_t shl_wrap(uint32_t v, uint32_t sh) {
 #endif
 }
 POMDP_HD uint64_t shl_wrap(uint64_t v, uint32_t sh) { return v << (sh & 63u); }
+POMDP_HD float bits_to_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f;
+    __builtin_memcpy(&f, &b, 4);
+    return f;
+#endif
+}
 
-// rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step), branch-free:
-// every env runs the same instruction stream whatever its action class, so the four envs
-// of a thread and the 32 threads of a warp never diverge.
+// rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step).
+//   lut      -> special[0] (the rows follow at lut + ROCK_SPECIALS), rtab -> rtab[0]
 //   w_gate   = draw slot 0 (p_move gate, StochasticRock only, rock.py:443)
 //   w_sensor = draw slot 1 (np.random.binomial(1, eff), rock.py:404)
-template <typename S>
-POMDP_HD void rock_step(const RockDev& p, const uint32_t* __restrict__ lut, S s, int32_t a, uint32_t w_gate,
-                        uint32_t w_sensor, S& s2, int32_t& ob, float& rw, int32_t& fl) {
-    const bool stepped_done = (s & RockBits<S>::DONE) != 0;                       // rock.py:126
-    const bool bad_action = (uint32_t)a >= p.n_actions;                           // rock.py:125
-    const uint32_t ai = (uint32_t)a < p.n_actions ? (uint32_t)a : p.n_actions - 1u;
-    const uint32_t v = lut[(((uint32_t)s & 0xFFu) << p.na_shift) + ai];
-    const bool is_move = ai < 4u, is_sample = ai == 4u, is_check = ai > 4u;
-    const uint32_t sh = is_check ? 2u * ai - 2u : (v & 63u);                      // 8 + 2 * (a - 5)
-    const uint32_t code = (uint32_t)shr_wrap(s, sh) & 3u;                         // 1 good, 3 bad, 0 collected / none
-    // check (rock.py:171-175, 401-407): truthful reading w.p. eff, else flipped
-    const bool truthful = w_sensor <= v;
-    const int32_t ob_check = ((code == 1u) == truthful) ? 2 : 1;
-    // sample (rock.py:160-169)
-    const bool has_rock = code != 0u;
-    const S cleared = s & ~shl_wrap((S)3, sh);
-    const int32_t rw_sample = code == 1u ? 10 : (has_rock ? -10 : p.penal);
-    // move (rock.py:134-158): the LUT row holds the next cell, the reward and the exit/wall `done`
-    const S moved = (s & ~(S)0xFF) | (S)(v & 0xFFu);
-    const int32_t rw_move = (int32_t)(int8_t)(v >> 8);
-    const bool done_move = ((v >> 16) & 1u) != 0;
-
-    S ns = is_move ? moved : ((is_sample && has_rock) ? cleared : s);
-    int32_t reward = is_move ? rw_move : (is_sample ? rw_sample : 0);
-    bool done = is_move ? done_move : (is_sample && !has_rock && !p.stochastic);  // rock.py:193 vs 503
-    int32_t o = is_check ? ob_check : 0;
-    int32_t f = (is_sample && (v & 0x100u)) ? (int32_t)FLAG_BAD_STATE : 0;        // reference: IndexError, rock.py:162
-    if (p.stochastic && !bern(w_gate, p.move_T)) { ns = s; reward = 0; done = false; o = 0; f = 0; }  // rock.py:443
-    if (done) { ns |= RockBits<S>::DONE; f |= FLAG_DONE; }
-    if (stepped_done || bad_action) {
-        ns = s; reward = 0; o = 0;
-        f = stepped_done ? (FLAG_DONE | FLAG_STEPPED_DONE) : FLAG_BAD_ACTION;
-    }
-    s2 = ns; ob = o; rw = (float)reward; fl = f;
+template <typename S, bool STOCH>
+POMDP_HD void rock_step(const RockDev& p, const RockEntry* __restrict__ lut, const RockEntry* __restrict__ rtab, S s,
+                        int32_t a, uint32_t w_gate, uint32_t w_sensor, S& s2, int32_t& ob, float& rw, int32_t& fl) {
+    uint32_t idx = ROCK_SPECIALS + ((((uint32_t)s & 0xFFu) << RockBits<S>::NA_SHIFT) + (uint32_t)a);
+    if (STOCH) idx = (p.gate_on && w_gate <= p.gate_thr_m1) ? idx : (uint32_t)ROCK_IDX_NOOP;   // rock.py:443
+    idx = (uint32_t)a >= p.n_actions ? (uint32_t)ROCK_IDX_BAD_ACTION : idx;                    // rock.py:125
+    idx = (s & RockBits<S>::DONE) ? (uint32_t)ROCK_IDX_STEPPED_DONE : idx;                     // rock.py:126
+    const RockEntry e = lut[idx];
+    const uint32_t code2 = (uint32_t)shr_wrap(s, e.y) & 6u;          // 2 * status code: 2 good, 6 bad, 0 collected / none
+    const S clear = shl_wrap((S)((e.y >> 16) & 0xFFu), e.y);         // sample: the rock's two status bits (rock.py:168)
+    S ns = (s ^ (S)((e.y >> 8) & 0xFFu)) & ~clear;                   // move: cell ^= delta (rock.py:134-158)
+    const uint32_t truthful = w_sensor <= e.x ? 1u : 0u;             // rock.py:404
+    const RockEntry r = rtab[(e.y >> 24) + code2 + truthful];
+    ns |= (S)(r.y & 0x80000000u) << (8 * sizeof(S) - 32);            // done
+    s2 = ns;
+    rw = bits_to_float(r.x);
+    ob = (int32_t)((r.y >> 8) & 0xFFu);
+    fl = (int32_t)(r.y & 0xFFu);
 }
 
 // rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)); draw slot i = rock i.
@@ -225,7 +251,7 @@ POMDP_HD S rock_reset(const RockDev& p, const D& draw) {
 }
 // Four envs of one aligned group: one Philox call per rock.
 template <typename S>
-POMDP_HD void rock_reset4(const RockDev& p, uint64_t seed, uint64_t group, uint32_t step, S out[4]) {
+POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t group, uint32_t step, S out[4]) {
     out[0] = out[1] = out[2] = out[3] = (S)p.start;
     for (int i = 0; i < p.k; ++i) {
         const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)i);
@@ -404,7 +430,7 @@ POMDP_HD int popc32(uint32_t v) {
 // draw, slot n = the action's observation draw: one Philox call per slot serves all L envs.
 // Reward is carried as an exact integer number of tenths.
 template <int L>
-POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], uint64_t seed,
+POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], const PhiloxKey& seed,
                              uint64_t group, int lane0, uint32_t step,
                              uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
     const uint32_t all = (1u << p.n) - 1u;
@@ -556,7 +582,7 @@ POMDP_HD void ship_mark(const ShipDev& p, ShipState& st, int pos, int dir, int l
 }
 
 // battleship.py:167-180 as written: rejection sampling; attempt a -> slots 2a (pos), 2a+1 (dir).
-POMDP_HD bool battleship_reset_rejection(const ShipDev& p, uint64_t seed, uint64_t env, uint32_t step,
+POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step,
                                          ShipState& st, int max_attempts) {
     st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
     int a = 0;

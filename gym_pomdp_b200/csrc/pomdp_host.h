@@ -63,13 +63,25 @@ inline const RockLayout* rock_layout(int board) {
 
 inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 : 2; }
 
-inline int rock_na_shift(const PomdpRockParams* q) { return 5 + q->num_rocks <= 16 ? 4 : 5; }
-inline int64_t rock_table_bytes(const PomdpRockParams* q) {
-    return (int64_t)sizeof(RockTableHdr) + 4 * ((int64_t)256 << rock_na_shift(q));
+inline int rock_na_shift(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 4 : 5; }
+inline int rock_rows(const PomdpRockParams* q) { return 16 * (q->board_size - 1) + q->board_size; }  // cells x | y << 4 with x, y < n
+inline int64_t rock_table_bytes(const PomdpRockParams* q) {   // what pomdp_rock_build_table fills and the TMA copy moves
+    const int64_t b = (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + ((int64_t)rock_rows(q) << rock_na_shift(q)));
+    return (b + 15) & ~(int64_t)15;
+}
+inline int64_t rock_smem_bytes(const PomdpRockParams* q) {
+    return (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + ((int64_t)256 << rock_na_shift(q)));
+}
+inline uint32_t float_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+inline RockEntry rock_result(int reward, int flags, int obs, bool done) {
+    RockEntry r;
+    r.x = float_bits((float)reward);
+    r.y = (uint32_t)(flags | (done ? FLAG_DONE : 0)) | ((uint32_t)obs << 8) | (done ? 0x80000000u : 0u);
+    return r;
 }
 
-// Fills the kernel params and (if tbl != nullptr) the static maps: the 400-byte header
-// followed by the transition LUT (layout: pomdp_core.h).  Returns 0 or POMDP_E_BADARG.
+// Fills the kernel params and (if tbl != nullptr) the static maps (layout: pomdp_core.h).
+// Returns 0 or POMDP_E_BADARG.
 inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
     if (!q) return fail(POMDP_E_BADARG, "rock: params is NULL");
     const RockLayout* L = rock_layout(q->board_size);
@@ -81,23 +93,27 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         return fail(POMDP_E_BADARG, "rock: config[%d] lists only %d rocks (the reference fails in _get_init_state)",
                     q->board_size, L->n_listed);
     const int n = q->board_size, k = q->num_rocks;
-    const int penal = q->stochastic ? 0 : -100;
+    const bool stoch = q->stochastic != 0;
+    const int penal = stoch ? 0 : -100;
     const int na_shift = rock_na_shift(q);
     if (d) {
         memset(d, 0, sizeof(*d));
         d->n = n;
         d->k = k;
-        d->stochastic = q->stochastic ? 1 : 0;
+        d->stochastic = stoch ? 1 : 0;
         d->penal = penal;
         d->start = (uint32_t)(L->sx | (L->sy << 4));
         d->n_actions = (uint32_t)(5 + k);
-        d->na_shift = (uint32_t)na_shift;
         d->table_bytes = (uint32_t)rock_table_bytes(q);
-        d->move_T = bern_T(q->p_move);
+        d->smem_bytes = (uint32_t)rock_smem_bytes(q);
+        const uint64_t T = bern_T(q->p_move);
+        d->gate_on = T != 0;
+        d->gate_thr_m1 = T ? (uint32_t)(T - 1) : 0u;
     }
     if (tbl) {
         RockTableHdr* h = (RockTableHdr*)tbl;
-        uint32_t* lut = (uint32_t*)((char*)tbl + sizeof(RockTableHdr));
+        RockEntry* rtab = (RockEntry*)((char*)tbl + ROCK_RTAB_OFFSET);
+        RockEntry* lut = (RockEntry*)((char*)tbl + ROCK_LUT_OFFSET);
         memset(tbl, 0, (size_t)rock_table_bytes(q));
         memset(h->grid, -1, sizeof(h->grid));
         memset(h->rock_pos, 0xFF, sizeof(h->rock_pos));
@@ -110,29 +126,52 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
             const double eff = (1 + pow(2, -(double)dd / 20)) * .5;      // rock.py:383-387
             h->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
         }
-        const uint32_t none_sh = k <= 11 ? RockBits<uint32_t>::NONE_SH : RockBits<uint64_t>::NONE_SH;
-        for (int cell = 0; cell < 256; ++cell) {
+        // ---- result rows: entry = row + 2 * code + truthful; code 0 collected/none, 1 good, 3 bad (2 never packed)
+        const bool wall_done = !stoch;                                   // rock.py:193; commented out at rock.py:503
+        for (int c = 0; c < 4; ++c)
+            for (int t = 0; t < 2; ++t) {
+                const int j = 2 * c + t;
+                rtab[ROCK_ROW_ZERO + j] = rock_result(0, 0, 0, false);
+                rtab[ROCK_ROW_EXIT + j] = rock_result(10, 0, 0, true);                           // rock.py:139-141
+                rtab[ROCK_ROW_WALL + j] = rock_result(penal, 0, 0, wall_done);
+                const int rs = c == 0 ? penal : (c == 1 ? 10 : -10);                             // rock.py:160-169
+                rtab[ROCK_ROW_SAMPLE + j] = rock_result(rs, 0, 0, c == 0 && wall_done);
+                rtab[ROCK_ROW_DANGLING + j] = rock_result(penal, FLAG_BAD_STATE, 0, wall_done);  // IndexError at rock.py:162
+                rtab[ROCK_ROW_CHECK + j] = rock_result(0, 0, ((c == 1) == (t == 1)) ? 2 : 1, false);  // rock.py:401-407
+                rtab[ROCK_ROW_STEPPED_DONE + j] = rock_result(0, FLAG_DONE | FLAG_STEPPED_DONE, 0, false);
+                rtab[ROCK_ROW_BAD_ACTION + j] = rock_result(0, FLAG_BAD_ACTION, 0, false);
+            }
+        const uint32_t none1 = k <= 11 ? RockBits<uint32_t>::NONE_SH1 : RockBits<uint64_t>::NONE_SH1;
+        auto entry = [&](uint32_t thr, uint32_t sh1, uint32_t delta, uint32_t clear, uint32_t row) {
+            RockEntry e;
+            e.x = thr;
+            e.y = sh1 | (delta << 8) | (clear << 16) | (row << 24);
+            return e;
+        };
+        lut[ROCK_IDX_NOOP] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_ZERO);
+        lut[ROCK_IDX_STEPPED_DONE] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_STEPPED_DONE);
+        lut[ROCK_IDX_BAD_ACTION] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_BAD_ACTION);
+        const int rows = rock_rows(q);
+        for (int cell = 0; cell < rows; ++cell) {
             const int x = cell & 15, y = cell >> 4;
-            uint32_t* row = lut + ((size_t)cell << na_shift);
+            RockEntry* row = lut + ROCK_SPECIALS + ((size_t)cell << na_shift);
+            for (int a = 0; a < (1 << na_shift); ++a) row[a] = lut[ROCK_IDX_BAD_ACTION];
             for (int a = 0; a < 4; ++a) {                                // rock.py:134-158
                 const int nx = x + move_dx(a), ny = y + move_dy(a);
-                uint32_t next = (uint32_t)cell;
-                int reward = 0, done = 0;
-                if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n) next = (uint32_t)(nx | (ny << 4));
-                else if (a == 1) { reward = 10; done = 1; }             // east exit, rock.py:139-141
-                else { reward = penal; done = !q->stochastic; }         // rock.py:193 (commented out at 503)
-                row[a] = next | ((uint32_t)(uint8_t)(int8_t)reward << 8) | ((uint32_t)done << 16);
+                if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n)
+                    row[a] = entry(0xFFFFFFFFu, none1, (uint32_t)(cell ^ (nx | (ny << 4))), 0, ROCK_ROW_ZERO);
+                else
+                    row[a] = entry(0xFFFFFFFFu, none1, 0, 0, a == 1 ? ROCK_ROW_EXIT : ROCK_ROW_WALL);
             }
             {                                                            // rock.py:160-169
                 const int rock = h->grid[cell];
-                uint32_t e = none_sh;
-                if (rock >= k) e |= 0x100u;                              // reference: IndexError at rock.py:162
-                else if (rock >= 0) e = (uint32_t)(8 + 2 * rock);
-                row[4] = e;
+                if (rock >= k) row[4] = entry(0xFFFFFFFFu, none1, 0, 6, ROCK_ROW_DANGLING);
+                else if (rock >= 0) row[4] = entry(0xFFFFFFFFu, (uint32_t)(7 + 2 * rock), 0, 6, ROCK_ROW_SAMPLE);
+                else row[4] = entry(0xFFFFFFFFu, none1, 0, 6, ROCK_ROW_SAMPLE);
             }
             for (int r = 0; r < k; ++r) {                                // rock.py:171-175, 383-387, 401-407
                 const int rp = h->rock_pos[r];
-                row[5 + r] = h->thr_m1[l1_distance(x, y, rp & 15, rp >> 4)];
+                row[5 + r] = entry(h->thr_m1[l1_distance(x, y, rp & 15, rp >> 4)], (uint32_t)(7 + 2 * r), 0, 0, ROCK_ROW_CHECK);
             }
         }
     }

@@ -87,45 +87,48 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterp
 // Each policy adapts one env's functors from pomdp_core.h to the generic streaming kernels:
 //   step4 / reset4 : the FOUR envs of one aligned draw group (one thread, one Philox call per slot)
 //   step1 / reset1 : a single env (tails, unaligned views, masked resets)
-template <typename S>
+template <typename S, bool STOCH>
 struct RockEnvT {
     typedef RockDev Params;
     typedef S State;
     static constexpr bool kTable = true;
-    __device__ static __forceinline__ void step4(const Params& p, const uint32_t* lut, const S s[4], const int32_t a[4],
-                                                 uint64_t seed, uint64_t group, uint32_t ctr, S s2[4], int32_t ob[4],
-                                                 float rw[4], int32_t fl[4]) {
+    __device__ static __forceinline__ void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
+                                                 int32_t ob[4], float rw[4], int32_t fl[4]) {
+        const RockEntry* rtab = reinterpret_cast<const RockEntry*>(tbl + ROCK_RTAB_OFFSET);
+        const RockEntry* lut = reinterpret_cast<const RockEntry*>(tbl + ROCK_LUT_OFFSET);
         const U4 qs = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
         U4 qg = {0, 0, 0, 0};
-        if (p.stochastic) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
-        rock_step<S>(p, lut, s[0], a[0], qg.x, qs.x, s2[0], ob[0], rw[0], fl[0]);
-        rock_step<S>(p, lut, s[1], a[1], qg.y, qs.y, s2[1], ob[1], rw[1], fl[1]);
-        rock_step<S>(p, lut, s[2], a[2], qg.z, qs.z, s2[2], ob[2], rw[2], fl[2]);
-        rock_step<S>(p, lut, s[3], a[3], qg.w, qs.w, s2[3], ob[3], rw[3], fl[3]);
+        if (STOCH) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
+        rock_step<S, STOCH>(p, lut, rtab, s[0], a[0], qg.x, qs.x, s2[0], ob[0], rw[0], fl[0]);
+        rock_step<S, STOCH>(p, lut, rtab, s[1], a[1], qg.y, qs.y, s2[1], ob[1], rw[1], fl[1]);
+        rock_step<S, STOCH>(p, lut, rtab, s[2], a[2], qg.z, qs.z, s2[2], ob[2], rw[2], fl[2]);
+        rock_step<S, STOCH>(p, lut, rtab, s[3], a[3], qg.w, qs.w, s2[3], ob[3], rw[3], fl[3]);
     }
-    __device__ static __forceinline__ void step1(const Params& p, const uint32_t* lut, S s, int32_t a, uint64_t seed,
-                                                 uint64_t env, uint32_t ctr, S& s2, int32_t& ob, float& rw, int32_t& fl) {
+    __device__ static __forceinline__ void step1(const Params& p, const unsigned char* tbl, S s, int32_t a,
+                                                 const PhiloxKey& seed, uint64_t env, uint32_t ctr, S& s2, int32_t& ob,
+                                                 float& rw, int32_t& fl) {
+        const RockEntry* rtab = reinterpret_cast<const RockEntry*>(tbl + ROCK_RTAB_OFFSET);
+        const RockEntry* lut = reinterpret_cast<const RockEntry*>(tbl + ROCK_LUT_OFFSET);
         const uint32_t ws = draw_word(seed, env, ctr, DOMAIN_STEP, 1);
-        const uint32_t wg = p.stochastic ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
-        rock_step<S>(p, lut, s, a, wg, ws, s2, ob, rw, fl);
+        const uint32_t wg = STOCH ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
+        rock_step<S, STOCH>(p, lut, rtab, s, a, wg, ws, s2, ob, rw, fl);
     }
-    __device__ static __forceinline__ void reset4(const Params& p, uint64_t seed, uint64_t group, uint32_t ctr, S s[4],
-                                                  int32_t ob[4]) {
+    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
+                                                  S s[4], int32_t ob[4]) {
         rock_reset4<S>(p, seed, group, ctr, s);
         ob[0] = ob[1] = ob[2] = ob[3] = 0;
     }
-    __device__ static __forceinline__ void reset1(const Params& p, uint64_t seed, uint64_t env, uint32_t ctr, S& s,
-                                                  int32_t& ob) {
-        s = rock_reset<S>(p, LazyDraw{seed, env, ctr, DOMAIN_RESET});
+    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr,
+                                                  S& s, int32_t& ob) {
+        s = rock_reset<S>(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET});
         ob = 0;
     }
 };
-typedef RockEnvT<uint32_t> RockEnv1;
-typedef RockEnvT<uint64_t> RockEnv2;
 
 // Precomputes the NS draw words of each of the four envs of a group (NS Philox calls).
 template <int NS>
-__device__ __forceinline__ void quad_words(uint64_t seed, uint64_t group, uint32_t ctr, uint32_t domain, int n_used,
+__device__ __forceinline__ void quad_words(const PhiloxKey& seed, uint64_t group, uint32_t ctr, uint32_t domain, int n_used,
                                            WordDraw<NS> d[4]) {
 #pragma unroll
     for (int slot = 0; slot < NS; ++slot) {
@@ -141,29 +144,29 @@ struct TagEnvT {
     typedef TagDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
-                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
         WordDraw<2 * NOPP> d[4];
         quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tag_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }
-    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
-        tag_step(p, s, a, LazyDraw{seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+        tag_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
     }
-    __device__ static __forceinline__ void reset4(const Params& p, uint64_t seed, uint64_t group, uint32_t ctr,
+    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
                                                   State s[4], int32_t ob[4]) {
         WordDraw<1 + NOPP> d[4];
         quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
     }
-    __device__ static __forceinline__ void reset1(const Params& p, uint64_t seed, uint64_t env, uint32_t ctr, State& s,
+    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
                                                   int32_t& ob) {
-        tag_reset(p, LazyDraw{seed, env, ctr, DOMAIN_RESET}, s, ob);
+        tag_reset(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
     }
 };
 
@@ -171,29 +174,29 @@ struct TigerEnvP {
     typedef TigerDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
-                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
         WordDraw<2> d[4];
         quad_words<2>(seed, group, ctr, DOMAIN_STEP, 2, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tiger_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }
-    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
-        tiger_step(p, s, a, LazyDraw{seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+        tiger_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
     }
-    __device__ static __forceinline__ void reset4(const Params&, uint64_t seed, uint64_t group, uint32_t ctr, State s[4],
+    __device__ static __forceinline__ void reset4(const Params&, const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s[4],
                                                   int32_t ob[4]) {
         WordDraw<1> d[4];
         quad_words<1>(seed, group, ctr, DOMAIN_RESET, 1, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tiger_reset(d[j], s[j], ob[j]);
     }
-    __device__ static __forceinline__ void reset1(const Params&, uint64_t seed, uint64_t env, uint32_t ctr, State& s,
+    __device__ static __forceinline__ void reset1(const Params&, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
                                                   int32_t& ob) {
-        tiger_reset(LazyDraw{seed, env, ctr, DOMAIN_RESET}, s, ob);
+        tiger_reset(LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
     }
 };
 
@@ -201,22 +204,22 @@ struct NetworkEnvP {
     typedef NetworkDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const uint32_t*, const State s[4], const int32_t a[4],
-                                                 uint64_t seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
         network_step_n<4>(p, s, a, seed, group, 0, ctr, s2, ob, rw, fl);
     }
-    __device__ static __forceinline__ void step1(const Params& p, const uint32_t*, State s, int32_t a, uint64_t seed,
+    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
         network_step_n<1>(p, &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
     }
-    __device__ static __forceinline__ void reset4(const Params& p, uint64_t, uint64_t, uint32_t, State s[4],
+    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State s[4],
                                                   int32_t ob[4]) {
         s[0] = s[1] = s[2] = s[3] = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
         ob[0] = ob[1] = ob[2] = ob[3] = 0;
     }
-    __device__ static __forceinline__ void reset1(const Params& p, uint64_t, uint64_t, uint32_t, State& s, int32_t& ob) {
+    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State& s, int32_t& ob) {
         s = (1u << p.n) - 1u;
         ob = 0;
     }
@@ -270,11 +273,11 @@ __global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
 pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
                   const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
                   int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n,
-                  uint64_t goff, uint64_t seed, uint32_t step_ctr, uint32_t table_bytes) {
+                  uint64_t goff, const __grid_constant__ PhiloxKey seed, uint32_t step_ctr, uint32_t table_bytes) {
     typedef typename Env::State S;
     extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
-    const uint32_t* lut = nullptr;
+    const unsigned char* lut = smem_table;
     if (Env::kTable) {
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
@@ -283,7 +286,6 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
             tma_bulk_g2s(smem_table, g_table, table_bytes, &bar);
         }
         __syncthreads();   // barrier object initialised before anyone polls it
-        lut = reinterpret_cast<const uint32_t*>(smem_table + sizeof(RockTableHdr));
     }
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -350,7 +352,7 @@ template <class Env, bool kVec>
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __restrict__ state,
                    int32_t* __restrict__ obs, const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
-                   uint64_t seed, uint32_t step_ctr) {
+                   const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
     typedef typename Env::State S;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -465,8 +467,8 @@ pomdp_battleship_step_plain_kernel(const __grid_constant__ ShipDev p, const int3
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
                                    int32_t* __restrict__ obs, int32_t* __restrict__ flags,
-                                   const uint8_t* __restrict__ mask, int64_t n, uint64_t goff, uint64_t seed,
-                                   uint32_t step_ctr) {
+                                   const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
+                                   const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int n_cand = 4 * p.n_tiles;
@@ -517,8 +519,8 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_battleship_reset_rejection_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
                                         int32_t* __restrict__ obs, int32_t* __restrict__ flags,
-                                        const uint8_t* __restrict__ mask, int64_t n, uint64_t goff, uint64_t seed,
-                                        uint32_t step_ctr) {
+                                        const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
+                                        const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
         if (mask && !mask[i]) continue;
@@ -640,8 +642,16 @@ inline bool aligned16(const void* a, const void* b, const void* c, const void* d
     return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f) & 15) == 0;
 }
 
+template <class K>
+inline int allow_smem(K kernel, size_t smem) {   // dynamic shared memory above 48 KB is opt-in per kernel
+    if (smem <= 48 * 1024) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e == cudaSuccess ? 0 : host::fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+}
+
 template <class Env>
-int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, const int32_t* state,
+int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                const int32_t* state,
                 const int32_t* action, int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
                 int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
     int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
@@ -651,17 +661,20 @@ int launch_step(const typename Env::Params& p, const void* d_table, uint32_t tab
     if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
         return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = Env::kTable ? table_bytes : 0;
+    const size_t smem = Env::kTable ? smem_bytes : 0;
+    const PhiloxKey key = philox_key(seed);
     if (aligned16(state, action, next_state, obs, reward, flags) && (goff & 3) == 0) {
         auto k = pomdp_step_kernel<Env, true>;
+        if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, (n + 3) >> 2, POMDP_STEP_THREADS, smem);
         k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
-                                                  (uint64_t)goff, seed, step_ctr, table_bytes);
+                                                  (uint64_t)goff, key, step_ctr, table_bytes);
     } else {
         auto k = pomdp_step_kernel<Env, false>;
+        if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
         k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
-                                                  (uint64_t)goff, seed, step_ctr, table_bytes);
+                                                  (uint64_t)goff, key, step_ctr, table_bytes);
     }
     return finish(what);
 }
@@ -675,11 +688,11 @@ int launch_reset(const typename Env::Params& p, int32_t* state, int32_t* obs, co
     if ((((uintptr_t)state) & 15) == 0 && (goff & 3) == 0) {
         auto k = pomdp_reset_kernel<Env, true>;
         const int grid = grid_for(k, (n + 3) >> 2);
-        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     } else {
         auto k = pomdp_reset_kernel<Env, false>;
         const int grid = grid_for(k, n);
-        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, seed, step_ctr);
+        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     }
     return finish(what);
 }
@@ -711,11 +724,16 @@ int pomdp_rock_step(const PomdpRockParams* q, const void* d_table, const int32_t
     RockDev d;
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
-    if (host::rock_words(q) == 1)
-        return launch_step<RockEnv1>(d, d_table, d.table_bytes, state, action, next_state, obs, reward, flags, n, goff,
-                                     seed, step_ctr, stream, "pomdp_rock_step");
-    return launch_step<RockEnv2>(d, d_table, d.table_bytes, state, action, next_state, obs, reward, flags, n, goff, seed,
-                                 step_ctr, stream, "pomdp_rock_step");
+#define POMDP_ROCK_STEP(S, STOCH)                                                                                     \
+    return launch_step<RockEnvT<S, STOCH>>(d, d_table, d.table_bytes, d.smem_bytes, state, action, next_state, obs,   \
+                                           reward, flags, n, goff, seed, step_ctr, stream, "pomdp_rock_step")
+    if (host::rock_words(q) == 1) {
+        if (d.stochastic) POMDP_ROCK_STEP(uint32_t, true);
+        POMDP_ROCK_STEP(uint32_t, false);
+    }
+    if (d.stochastic) POMDP_ROCK_STEP(uint64_t, true);
+    POMDP_ROCK_STEP(uint64_t, false);
+#undef POMDP_ROCK_STEP
 }
 int pomdp_rock_reset(const PomdpRockParams* q, const void* d_table, int32_t* state, int32_t* obs, const uint8_t* mask,
                      int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
@@ -724,8 +742,8 @@ int pomdp_rock_reset(const PomdpRockParams* q, const void* d_table, int32_t* sta
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
     if (host::rock_words(q) == 1)
-        return launch_reset<RockEnv1>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
-    return launch_reset<RockEnv2>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
+        return launch_reset<RockEnvT<uint32_t, false>>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
+    return launch_reset<RockEnvT<uint64_t, false>>(d, state, obs, mask, n, goff, seed, step_ctr, stream, "pomdp_rock_reset");
 }
 
 // ---- Tag
@@ -736,9 +754,9 @@ int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t*
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
     if (d.n_opp == 1)
-        return launch_step<TagEnvT<1>>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed,
+        return launch_step<TagEnvT<1>>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed,
                                        step_ctr, stream, "pomdp_tag_step");
-    return launch_step<TagEnvT<4>>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<TagEnvT<4>>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                    stream, "pomdp_tag_step");
 }
 int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
@@ -758,7 +776,7 @@ int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int3
     TigerDev d;
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
-    return launch_step<TigerEnvP>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<TigerEnvP>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                   stream, "pomdp_tiger_step");
 }
 int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
@@ -776,7 +794,7 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
-    return launch_step<NetworkEnvP>(d, nullptr, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<NetworkEnvP>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                     stream, "pomdp_network_step");
 }
 int pomdp_network_reset(const PomdpNetworkParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
@@ -819,7 +837,7 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
     if (n == 0) return 0;
     auto k = pomdp_battleship_reset_scan_kernel;
     const int grid = grid_for(k, n * 32);
-    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, seed, step_ctr);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     return finish("pomdp_battleship_reset");
 }
 int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
@@ -832,7 +850,7 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
     if (n == 0) return 0;
     auto k = pomdp_battleship_reset_rejection_kernel;
     const int grid = grid_for(k, n);
-    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, seed, step_ctr);
+    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     return finish("pomdp_battleship_reset_rejection");
 }
 

@@ -28,13 +28,16 @@ void store_state(int32_t* base, int64_t i, uint64_t s) { base[2 * i] = (int32_t)
 template <typename S>
 int rock_step_host(const RockDev& d, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
                    int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step) {
-    const uint32_t* lut = (const uint32_t*)((const char*)table + sizeof(RockTableHdr));
+    const RockEntry* rtab = (const RockEntry*)((const char*)table + ROCK_RTAB_OFFSET);
+    const RockEntry* lut = (const RockEntry*)((const char*)table + ROCK_LUT_OFFSET);
+    const PhiloxKey key = philox_key(seed);
     for (int64_t i = 0; i < n; ++i) {
         S s2;
         const uint64_t env = (uint64_t)(goff + i);
-        const uint32_t wg = d.stochastic ? draw_word(seed, env, step, DOMAIN_STEP, 0) : 0u;
-        const uint32_t ws = draw_word(seed, env, step, DOMAIN_STEP, 1);
-        rock_step<S>(d, lut, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
+        const uint32_t wg = d.stochastic ? draw_word(key, env, step, DOMAIN_STEP, 0) : 0u;
+        const uint32_t ws = draw_word(key, env, step, DOMAIN_STEP, 1);
+        if (d.stochastic) rock_step<S, true>(d, lut, rtab, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
+        else rock_step<S, false>(d, lut, rtab, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
         store_state(next, i, s2);
     }
     return 0;
@@ -64,6 +67,7 @@ int pomdp_rock_step(const PomdpRockParams* q, const void* table, const int32_t* 
                     int32_t* next, int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed,
                     uint32_t step, void*) {
     RockDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
     rc = host::check_io(state, action, next, obs, rw, fl, n);
@@ -76,11 +80,12 @@ int pomdp_rock_step(const PomdpRockParams* q, const void* table, const int32_t* 
 int pomdp_rock_reset(const PomdpRockParams* q, const void*, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
                      int64_t goff, uint64_t seed, uint32_t step, void*) {
     RockDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
-        const LazyDraw draw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET};
+        const LazyDraw draw{&key, (uint64_t)(goff + i), step, DOMAIN_RESET};
         if (host::rock_words(q) == 1) store_state(state, i, rock_reset<uint32_t>(d, draw));
         else store_state(state, i, rock_reset<uint64_t>(d, draw));
         if (obs) obs[i] = 0;
@@ -91,13 +96,14 @@ int pomdp_rock_reset(const PomdpRockParams* q, const void*, int32_t* state, int3
 int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
                    float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     TagDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
     rc = host::check_io(state, action, next, obs, rw, fl, n);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s2;
-        tag_step(d, (uint32_t)state[i], action[i], LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
+        tag_step(d, (uint32_t)state[i], action[i], LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -105,12 +111,13 @@ int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t*
 int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
                     uint64_t seed, uint32_t step, void*) {
     TagDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         uint32_t s; int32_t ob;
-        tag_reset(d, LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
+        tag_reset(d, LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
         state[i] = (int32_t)s;
         if (obs) obs[i] = ob;
     }
@@ -120,13 +127,14 @@ int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const
 int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
                      float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     TigerDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
     rc = host::check_io(state, action, next, obs, rw, fl, n);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s2;
-        tiger_step(d, (uint32_t)state[i], action[i], LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
+        tiger_step(d, (uint32_t)state[i], action[i], LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -134,12 +142,13 @@ int pomdp_tiger_step(const PomdpTigerParams* q, const int32_t* state, const int3
 int pomdp_tiger_reset(const PomdpTigerParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n,
                       int64_t goff, uint64_t seed, uint32_t step, void*) {
     TigerDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         uint32_t s; int32_t ob;
-        tiger_reset(LazyDraw{seed, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
+        tiger_reset(LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_RESET}, s, ob);
         state[i] = (int32_t)s;
         if (obs) obs[i] = ob;
     }
@@ -150,6 +159,7 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
                        int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
                        void*) {
     NetworkDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_network(q, &d);
     if (rc) return rc;
     rc = host::check_io(state, action, next, obs, rw, fl, n);
@@ -160,13 +170,13 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
         if ((env & 3) == 0 && i + 4 <= n && ((i >> 2) & 1) == 0) {
             uint32_t s4[4], s2[4];
             for (int j = 0; j < 4; ++j) s4[j] = (uint32_t)state[i + j];
-            network_step_n<4>(d, s4, action + i, seed, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
+            network_step_n<4>(d, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
             for (int j = 0; j < 4; ++j) next[i + j] = (int32_t)s2[j];
             i += 3;
             continue;
         }
         uint32_t s1 = (uint32_t)state[i], s2;
-        network_step_n<1>(d, &s1, action + i, seed, env >> 2, (int)(env & 3), step, &s2, obs + i, rw + i, fl + i);
+        network_step_n<1>(d, &s1, action + i, key, env >> 2, (int)(env & 3), step, &s2, obs + i, rw + i, fl + i);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -202,6 +212,7 @@ int pomdp_battleship_step(const PomdpBattleshipParams* q, const int32_t* state, 
 int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     ShipDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_ship(q, &d);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
@@ -215,7 +226,7 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
             int total = 0;
             for (int c = 0; c < 4 * d.n_tiles; ++c) total += ship_candidate_ok(d, blocked, c >> 2, c & 3, length);
             if (total == 0) { ok_all = false; break; }
-            int k = (int)rand_below(draw_word(seed, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total);
+            int k = (int)rand_below(draw_word(key, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total);
             for (int c = 0; c < 4 * d.n_tiles; ++c)
                 if (ship_candidate_ok(d, blocked, c >> 2, c & 3, length) && k-- == 0) { ship_mark(d, st, c >> 2, c & 3, length); break; }
         }
@@ -230,12 +241,13 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
 int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
                                      const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     ShipDev d;
+    const PhiloxKey key = philox_key(seed);
     int rc = host::make_ship(q, &d);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         ShipState st;
-        const bool ok = battleship_reset_rejection(d, seed, (uint64_t)(goff + i), step, st, 4096);
+        const bool ok = battleship_reset_rejection(d, key, (uint64_t)(goff + i), step, st, 4096);
         uint32_t w8[SHIP_WORDS];
         ship_pack(st, w8);
         for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
