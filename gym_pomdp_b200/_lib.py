@@ -14,7 +14,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpomdp_b200.so")
+# POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
+LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
 ABI_VERSION = 2
 FLAG_DONE = 1

@@ -63,20 +63,20 @@ inline const RockLayout* rock_layout(int board) {
 
 inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 : 2; }
 
-inline int rock_na_shift(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 4 : 5; }
 inline int rock_rows(const PomdpRockParams* q) { return 16 * (q->board_size - 1) + q->board_size; }  // cells x | y << 4 with x, y < n
 inline int64_t rock_table_bytes(const PomdpRockParams* q) {   // what pomdp_rock_build_table fills and the TMA copy moves
-    const int64_t b = (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + ((int64_t)rock_rows(q) << rock_na_shift(q)));
-    return (b + 15) & ~(int64_t)15;
+    return (int64_t)ROCK_LUT_OFFSET + 16 * ((int64_t)ROCK_SPECIALS + (int64_t)rock_rows(q) * (5 + q->num_rocks));
 }
 inline int64_t rock_smem_bytes(const PomdpRockParams* q) {
-    return (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + ((int64_t)256 << rock_na_shift(q)));
+    return (int64_t)ROCK_LUT_OFFSET + 16 * ((int64_t)ROCK_SPECIALS + (int64_t)256 * (5 + q->num_rocks));
 }
 inline uint32_t float_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
 inline RockEntry rock_result(int reward, int flags, int obs, bool done) {
     RockEntry r;
     r.x = float_bits((float)reward);
-    r.y = (uint32_t)(flags | (done ? FLAG_DONE : 0)) | ((uint32_t)obs << 8) | (done ? 0x80000000u : 0u);
+    r.y = (uint32_t)obs;
+    r.z = (uint32_t)(flags | (done ? FLAG_DONE : 0));
+    r.w = done ? 0x80000000u : 0u;
     return r;
 }
 
@@ -92,10 +92,10 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
     if (q->num_rocks > L->n_listed)
         return fail(POMDP_E_BADARG, "rock: config[%d] lists only %d rocks (the reference fails in _get_init_state)",
                     q->board_size, L->n_listed);
-    const int n = q->board_size, k = q->num_rocks;
+    const int n = q->board_size, k = q->num_rocks, n_act = 5 + k;
     const bool stoch = q->stochastic != 0;
+    const bool wide = k > 11;                    // 64-bit packed states
     const int penal = stoch ? 0 : -100;
-    const int na_shift = rock_na_shift(q);
     if (d) {
         memset(d, 0, sizeof(*d));
         d->n = n;
@@ -103,7 +103,7 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         d->stochastic = stoch ? 1 : 0;
         d->penal = penal;
         d->start = (uint32_t)(L->sx | (L->sy << 4));
-        d->n_actions = (uint32_t)(5 + k);
+        d->n_actions = (uint32_t)n_act;
         d->table_bytes = (uint32_t)rock_table_bytes(q);
         d->smem_bytes = (uint32_t)rock_smem_bytes(q);
         const uint64_t T = bern_T(q->p_move);
@@ -141,37 +141,41 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
                 rtab[ROCK_ROW_STEPPED_DONE + j] = rock_result(0, FLAG_DONE | FLAG_STEPPED_DONE, 0, false);
                 rtab[ROCK_ROW_BAD_ACTION + j] = rock_result(0, FLAG_BAD_ACTION, 0, false);
             }
-        const uint32_t none1 = k <= 11 ? RockBits<uint32_t>::NONE_SH1 : RockBits<uint64_t>::NONE_SH1;
-        auto entry = [&](uint32_t thr, uint32_t sh1, uint32_t delta, uint32_t clear, uint32_t row) {
+        const uint32_t none_sh = wide ? RockBits<uint64_t>::NONE_SH : RockBits<uint32_t>::NONE_SH;
+        // status_bit: bit offset of the rock status the action reads (or -1); clear: wipe those two bits; delta: cell xor
+        auto entry = [&](uint32_t thr, int status_bit, bool clear, uint32_t delta, uint32_t row) {
             RockEntry e;
+            const uint32_t sh = status_bit < 0 ? none_sh : (uint32_t)(status_bit - 5);
+            const uint64_t cmask = clear ? ((uint64_t)3 << (status_bit < 0 ? (int)none_sh + 5 : status_bit)) : 0;
             e.x = thr;
-            e.y = sh1 | (delta << 8) | (clear << 16) | (row << 24);
+            e.y = sh | ((row * (uint32_t)sizeof(RockEntry)) << 8) | (wide ? delta << 24 : 0u);
+            e.z = (uint32_t)cmask;
+            e.w = wide ? (uint32_t)(cmask >> 32) : delta;
             return e;
         };
-        lut[ROCK_IDX_NOOP] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_ZERO);
-        lut[ROCK_IDX_STEPPED_DONE] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_STEPPED_DONE);
-        lut[ROCK_IDX_BAD_ACTION] = entry(0xFFFFFFFFu, none1, 0, 0, ROCK_ROW_BAD_ACTION);
+        lut[ROCK_IDX_NOOP] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_ZERO);
+        lut[ROCK_IDX_STEPPED_DONE] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_STEPPED_DONE);
+        lut[ROCK_IDX_BAD_ACTION] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_BAD_ACTION);
         const int rows = rock_rows(q);
         for (int cell = 0; cell < rows; ++cell) {
             const int x = cell & 15, y = cell >> 4;
-            RockEntry* row = lut + ROCK_SPECIALS + ((size_t)cell << na_shift);
-            for (int a = 0; a < (1 << na_shift); ++a) row[a] = lut[ROCK_IDX_BAD_ACTION];
+            RockEntry* row = lut + ROCK_SPECIALS + (size_t)cell * n_act;
             for (int a = 0; a < 4; ++a) {                                // rock.py:134-158
                 const int nx = x + move_dx(a), ny = y + move_dy(a);
                 if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n)
-                    row[a] = entry(0xFFFFFFFFu, none1, (uint32_t)(cell ^ (nx | (ny << 4))), 0, ROCK_ROW_ZERO);
+                    row[a] = entry(0xFFFFFFFFu, -1, false, (uint32_t)(cell ^ (nx | (ny << 4))), ROCK_ROW_ZERO);
                 else
-                    row[a] = entry(0xFFFFFFFFu, none1, 0, 0, a == 1 ? ROCK_ROW_EXIT : ROCK_ROW_WALL);
+                    row[a] = entry(0xFFFFFFFFu, -1, false, 0, a == 1 ? ROCK_ROW_EXIT : ROCK_ROW_WALL);
             }
             {                                                            // rock.py:160-169
                 const int rock = h->grid[cell];
-                if (rock >= k) row[4] = entry(0xFFFFFFFFu, none1, 0, 6, ROCK_ROW_DANGLING);
-                else if (rock >= 0) row[4] = entry(0xFFFFFFFFu, (uint32_t)(7 + 2 * rock), 0, 6, ROCK_ROW_SAMPLE);
-                else row[4] = entry(0xFFFFFFFFu, none1, 0, 6, ROCK_ROW_SAMPLE);
+                if (rock >= k) row[4] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_DANGLING);
+                else if (rock >= 0) row[4] = entry(0xFFFFFFFFu, 8 + 2 * rock, true, 0, ROCK_ROW_SAMPLE);
+                else row[4] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_SAMPLE);
             }
             for (int r = 0; r < k; ++r) {                                // rock.py:171-175, 383-387, 401-407
                 const int rp = h->rock_pos[r];
-                row[5 + r] = entry(h->thr_m1[l1_distance(x, y, rp & 15, rp >> 4)], (uint32_t)(7 + 2 * r), 0, 0, ROCK_ROW_CHECK);
+                row[5 + r] = entry(h->thr_m1[l1_distance(x, y, rp & 15, rp >> 4)], 8 + 2 * r, false, 0, ROCK_ROW_CHECK);
             }
         }
     }
