@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off; "
+                         "measured to slow graph replay by ~8%, so never on for a reported number)")
+    ap.add_argument("--clock-period", type=float, default=0.01, help="NVML polling period (s) during the timed region")
     return ap.parse_args()
 
 
@@ -60,6 +64,8 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
         self.ok = False
         try:
+            if period <= 0:
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -236,24 +242,31 @@ def run_b200(args):
     with torch.cuda.stream(stream):
         if graph_w is not None:
             graph_w.replay()
+            # the first launch of a graph exec uploads its 2000 nodes to the device (~1.5 us per node,
+            # measured): do that outside the timed region, as cudaGraphUpload would
+            graph_t.replay()
     barrier()
-    sampler = ClockSampler(physical_gpu_index(local))
-    sampler.start()
-    torch.cuda.profiler.start()     # ncu --profile-from-start off: list only the timed region's launches
+    sampler = ClockSampler(physical_gpu_index(local), period=args.clock_period)
+    if args.clock_period > 0:
+        sampler.start()
+    if args.profiler_range:
+        torch.cuda.profiler.start()     # ncu --profile-from-start off: list only the timed region's launches
     e0, e1 = timed_region()
     torch.cuda.synchronize()
-    torch.cuda.profiler.stop()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks_note = "sampled during the timed region"
-    if len(sampler.samples) < 5:
+    if args.clock_period > 0 and len(sampler.samples) < 5:
         # the region is shorter than a few NVML polls: repeat the identical work (untimed) while sampling
         t_end = time.time() + 0.6
         while time.time() < t_end:
             timed_region()
             torch.cuda.synchronize()
         clocks_note = "timed region %.1f ms is shorter than 5 NVML polls; sampled over untimed repeats of it" % ms
-    sampler.stop()
+    if args.clock_period > 0:
+        sampler.stop()
     clocks = sampler.summary()
     clocks["note"] = clocks_note
 
@@ -322,7 +335,8 @@ def run_b200(args):
     cfg = workload_config(args, n_gpus)
     cfg["l2"] = "%d rotating buffer sets of %.0f MB (%.0f MB total) > 126 MB L2; no flush needed" % (
         n_sets, set_bytes / 1e6, n_sets * set_bytes / 1e6)
-    cfg["launch"] = "eager ctypes launches" if args.no_graph else "one CUDA graph of K pomdp_rock_step launches"
+    cfg["launch"] = "eager ctypes launches" if args.no_graph else \
+        "one CUDA graph of K pomdp_rock_step launches (replayed once untimed first: graph upload)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -135,24 +135,25 @@ POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y -
 
 // ====================================================================== RockSample ===
 // Static maps of one Rock configuration, built on the host (pomdp_host.h: make_rock) and
-// staged into shared memory by ONE TMA bulk copy per CTA.  Byte layout (16-byte entries):
+// staged into shared memory by ONE TMA bulk copy per CTA.  Byte layout:
 //   RockTableHdr (400 B)         the reference's own maps (grid, rock coordinates, sensor thresholds)
-//   RockEntry rtab[64]           results: 8 rows x 8 entries; entry = row + 2 * status code + truthful
-//   RockEntry special[4]         NOOP (failed p_move gate), STEPPED_DONE, BAD_ACTION
-//   RockEntry lut[rows * n_act]  transitions, indexed by (agent cell = x | y << 4, action); only the
+//   RockRes rtab[64]  (16 B)     results: 8 rows x 8 entries; entry = row + 2 * status code + truthful
+//   RockLut special[4] (8 B)     NOOP (failed p_move gate), STEPPED_DONE, BAD_ACTION
+//   RockLut lut[rows * n_act]    transitions, indexed by (agent cell = x | y << 4, action); only the
 //                                rows of reachable cells (16 * (n-1) + n of 256) are stored and copied
-// The step functor is two dependent 16-byte shared-memory loads whose words are used as they
-// come (no field extraction, no int->float conversion) and ~15 integer instructions that are
+// The step functor is two dependent shared-memory loads and ~20 integer instructions that are
 // the same for every action class, so neither the four envs of a thread nor the 32 threads
-// of a warp diverge.
+// of a warp diverge, and there is no int->float conversion.  Shared-memory bandwidth is the
+// scarce resource next to the ALU pipe (measured): the lut access is random
+// over ~22 KB (bank conflicts), so its entries are kept at 8 bytes; the rtab access hits
+// <= 64 distinct addresses (mostly broadcasts), so its entries can afford 16 bytes whose
+// words are stored as they come.
 //   lut entry   x = ceil(eff(d) * 2^32) - 1 for a check of rock a-5 at L1 distance d (rock.py:383-387,
 //                   401-407); 0xFFFFFFFF for the other actions
-//               y = bits 0-7: (bit offset of the status this action looks at) - 5, so that
-//                   (state >> y) & 0x60 = 32 * status code          [no status: RockBits::NONE_SH]
-//                   bits 8-23: byte offset of the rtab row;  bits 24-31 (64-bit states): cell ^ next cell
-//               z,w = 32-bit states: CLEAR mask, XOR mask: next = (state & ~z) ^ w  (sample clears the
-//                   rock's two status bits, rock.py:168; a move xors the cell byte, rock.py:134-158)
-//                     64-bit states: the 64-bit CLEAR mask (the XOR byte travels in y)
+//               y = byte 0: (bit offset of the status this action looks at) - 1, so that
+//                           (state >> y) & 6 = 2 * status code          [no status: RockBits::NONE_SH1]
+//                   byte 1: rtab row;  byte 2: cell ^ next cell (moves, rock.py:134-158);
+//                   byte 3: 6 if the status is cleared (sample, rock.py:168) else 0
 //   rtab entry  x = reward (float bits), y = obs, z = flags, w = 0x80000000 if done
 struct RockTableHdr {
     int8_t grid[256];      // [x | y << 4] -> rock id written by rock.py:110-111, -1 = none
@@ -160,7 +161,8 @@ struct RockTableHdr {
     uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2
 };
 static_assert(sizeof(RockTableHdr) == 400 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
-struct alignas(16) RockEntry { uint32_t x, y, z, w; };
+struct alignas(8) RockLut { uint32_t x, y; };
+struct alignas(16) RockRes { uint32_t x, y, z, w; };
 
 enum : uint32_t {   // rtab rows (entry index of the row's first entry) and special lut entries
     ROCK_ROW_ZERO = 0, ROCK_ROW_EXIT = 8, ROCK_ROW_WALL = 16, ROCK_ROW_SAMPLE = 24, ROCK_ROW_DANGLING = 32,
@@ -168,7 +170,7 @@ enum : uint32_t {   // rtab rows (entry index of the row's first entry) and spec
     ROCK_IDX_NOOP = 0, ROCK_IDX_STEPPED_DONE = 1, ROCK_IDX_BAD_ACTION = 2, ROCK_SPECIALS = 4,
 };
 constexpr uint32_t ROCK_RTAB_OFFSET = sizeof(RockTableHdr);
-constexpr uint32_t ROCK_LUT_OFFSET = ROCK_RTAB_OFFSET + ROCK_RTAB_ENTRIES * sizeof(RockEntry);   // specials, then rows
+constexpr uint32_t ROCK_LUT_OFFSET = ROCK_RTAB_OFFSET + ROCK_RTAB_ENTRIES * sizeof(RockRes);   // specials, then rows
 
 struct RockDev {  // passed by value to the kernels
     int32_t n, k;
@@ -186,14 +188,14 @@ struct RockDev {  // passed by value to the kernels
 template <typename S> struct RockBits;
 template <> struct RockBits<uint32_t> {
     static constexpr uint32_t DONE = 0x80000000u;
-    static constexpr uint32_t NONE_SH = 25;   // status bits 30-31: unused / done (0 in a steppable state)
+    static constexpr uint32_t NONE_SH1 = 29;   // status bits 30-31: unused / done (0 in a steppable state)
 };
 template <> struct RockBits<uint64_t> {
     static constexpr uint64_t DONE = 0x8000000000000000ull;
-    static constexpr uint32_t NONE_SH = 57;
+    static constexpr uint32_t NONE_SH1 = 61;
 };
 
-// shift whose count wraps at the word size (one SHF on the GPU; upper bits of the count are ignored)
+// shifts whose count wraps at the word size (one SHF on the GPU; upper bits of the count are ignored)
 POMDP_HD uint32_t shr_wrap(uint32_t v, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(v, 0u, sh);
@@ -202,6 +204,21 @@ POMDP_HD uint32_t shr_wrap(uint32_t v, uint32_t sh) {
 #endif
 }
 POMDP_HD uint32_t shr_wrap(uint64_t v, uint32_t sh) { return (uint32_t)(v >> (sh & 63u)); }
+POMDP_HD uint32_t shl_wrap(uint32_t v, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(0u, v, sh);
+#else
+    return v << (sh & 31u);
+#endif
+}
+POMDP_HD uint64_t shl_wrap(uint64_t v, uint32_t sh) { return v << (sh & 63u); }
+POMDP_HD uint32_t byte_of(uint32_t v, int b) {   // one PRMT
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0u, 0x4440u | (uint32_t)b);
+#else
+    return (v >> (8 * b)) & 0xFFu;
+#endif
+}
 POMDP_HD float bits_to_float(uint32_t b) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(b);
@@ -211,30 +228,26 @@ POMDP_HD float bits_to_float(uint32_t b) {
     return f;
 #endif
 }
-POMDP_HD uint32_t rock_apply(uint32_t s, const RockEntry& e) { return (s & ~e.z) ^ e.w; }
-POMDP_HD uint64_t rock_apply(uint64_t s, const RockEntry& e) {
-    return (s & ~((uint64_t)e.z | ((uint64_t)e.w << 32))) ^ (uint64_t)(e.y >> 24);
-}
-POMDP_HD uint32_t rock_or_done(uint32_t s, uint32_t done_mask) { return s | done_mask; }
-POMDP_HD uint64_t rock_or_done(uint64_t s, uint32_t done_mask) { return s | ((uint64_t)done_mask << 32); }
 
 // rock.py:123-194 (RockEnv.step) and rock.py:434-504 (StochasticRockEnv.step).
 //   lut      -> special[0] (the rows follow at lut + ROCK_SPECIALS), rtab -> rtab[0]
 //   w_gate   = draw slot 0 (p_move gate, StochasticRock only, rock.py:443)
 //   w_sensor = draw slot 1 (np.random.binomial(1, eff), rock.py:404)
 template <typename S, bool STOCH>
-POMDP_HD void rock_step(const RockDev& p, const RockEntry* __restrict__ lut, const RockEntry* __restrict__ rtab, S s,
+POMDP_HD void rock_step(const RockDev& p, const RockLut* __restrict__ lut, const RockRes* __restrict__ rtab, S s,
                         int32_t a, uint32_t w_gate, uint32_t w_sensor, S& s2, int32_t& ob, float& rw, int32_t& fl) {
     uint32_t idx = ROCK_SPECIALS + ((uint32_t)s & 0xFFu) * p.n_actions + (uint32_t)a;
     if (STOCH) idx = (p.gate_on && w_gate <= p.gate_thr_m1) ? idx : (uint32_t)ROCK_IDX_NOOP;   // rock.py:443
     idx = (uint32_t)a >= p.n_actions ? (uint32_t)ROCK_IDX_BAD_ACTION : idx;                    // rock.py:125
     idx = (s & RockBits<S>::DONE) ? (uint32_t)ROCK_IDX_STEPPED_DONE : idx;                     // rock.py:126
-    const RockEntry e = lut[idx];
-    const uint32_t code_off = shr_wrap(s, e.y) & 0x60u;              // 32 * status code: 1 good, 3 bad, 0 collected / none
-    const uint32_t row_off = sizeof(S) == 4 ? (e.y >> 8) : ((e.y >> 8) & 0xFFFFu);
-    const uint32_t off = row_off + code_off + (w_sensor <= e.x ? 16u : 0u);        // + truthful (rock.py:404)
-    const RockEntry r = *reinterpret_cast<const RockEntry*>(reinterpret_cast<const char*>(rtab) + off);
-    s2 = rock_or_done(rock_apply(s, e), r.w);
+    const RockLut e = lut[idx];
+    const uint32_t code2 = shr_wrap(s, e.y) & 6u;                    // 2 * status code: 1 good, 3 bad, 0 collected / none
+    const uint32_t truthful = w_sensor <= e.x ? 1u : 0u;             // rock.py:404
+    const RockRes r = rtab[byte_of(e.y, 1) + code2 + truthful];
+    const S clear = shl_wrap((S)byte_of(e.y, 3), e.y);               // sample: the rock's two status bits
+    S ns = (s ^ (S)byte_of(e.y, 2)) & ~clear;                        // move: cell ^= delta
+    ns |= (S)r.w << (8 * sizeof(S) - 32);                            // done
+    s2 = ns;
     rw = bits_to_float(r.x);
     ob = (int32_t)r.y;
     fl = (int32_t)r.z;

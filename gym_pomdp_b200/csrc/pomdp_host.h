@@ -65,14 +65,15 @@ inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 
 
 inline int rock_rows(const PomdpRockParams* q) { return 16 * (q->board_size - 1) + q->board_size; }  // cells x | y << 4 with x, y < n
 inline int64_t rock_table_bytes(const PomdpRockParams* q) {   // what pomdp_rock_build_table fills and the TMA copy moves
-    return (int64_t)ROCK_LUT_OFFSET + 16 * ((int64_t)ROCK_SPECIALS + (int64_t)rock_rows(q) * (5 + q->num_rocks));
+    const int64_t b = (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + (int64_t)rock_rows(q) * (5 + q->num_rocks));
+    return (b + 15) & ~(int64_t)15;
 }
 inline int64_t rock_smem_bytes(const PomdpRockParams* q) {
-    return (int64_t)ROCK_LUT_OFFSET + 16 * ((int64_t)ROCK_SPECIALS + (int64_t)256 * (5 + q->num_rocks));
+    return (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + (int64_t)256 * (5 + q->num_rocks));
 }
 inline uint32_t float_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
-inline RockEntry rock_result(int reward, int flags, int obs, bool done) {
-    RockEntry r;
+inline RockRes rock_result(int reward, int flags, int obs, bool done) {
+    RockRes r;
     r.x = float_bits((float)reward);
     r.y = (uint32_t)obs;
     r.z = (uint32_t)(flags | (done ? FLAG_DONE : 0));
@@ -112,8 +113,8 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
     }
     if (tbl) {
         RockTableHdr* h = (RockTableHdr*)tbl;
-        RockEntry* rtab = (RockEntry*)((char*)tbl + ROCK_RTAB_OFFSET);
-        RockEntry* lut = (RockEntry*)((char*)tbl + ROCK_LUT_OFFSET);
+        RockRes* rtab = (RockRes*)((char*)tbl + ROCK_RTAB_OFFSET);
+        RockLut* lut = (RockLut*)((char*)tbl + ROCK_LUT_OFFSET);
         memset(tbl, 0, (size_t)rock_table_bytes(q));
         memset(h->grid, -1, sizeof(h->grid));
         memset(h->rock_pos, 0xFF, sizeof(h->rock_pos));
@@ -141,16 +142,12 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
                 rtab[ROCK_ROW_STEPPED_DONE + j] = rock_result(0, FLAG_DONE | FLAG_STEPPED_DONE, 0, false);
                 rtab[ROCK_ROW_BAD_ACTION + j] = rock_result(0, FLAG_BAD_ACTION, 0, false);
             }
-        const uint32_t none_sh = wide ? RockBits<uint64_t>::NONE_SH : RockBits<uint32_t>::NONE_SH;
+        const int none_bit = wide ? (int)RockBits<uint64_t>::NONE_SH1 + 1 : (int)RockBits<uint32_t>::NONE_SH1 + 1;
         // status_bit: bit offset of the rock status the action reads (or -1); clear: wipe those two bits; delta: cell xor
         auto entry = [&](uint32_t thr, int status_bit, bool clear, uint32_t delta, uint32_t row) {
-            RockEntry e;
-            const uint32_t sh = status_bit < 0 ? none_sh : (uint32_t)(status_bit - 5);
-            const uint64_t cmask = clear ? ((uint64_t)3 << (status_bit < 0 ? (int)none_sh + 5 : status_bit)) : 0;
+            RockLut e;
             e.x = thr;
-            e.y = sh | ((row * (uint32_t)sizeof(RockEntry)) << 8) | (wide ? delta << 24 : 0u);
-            e.z = (uint32_t)cmask;
-            e.w = wide ? (uint32_t)(cmask >> 32) : delta;
+            e.y = (uint32_t)((status_bit < 0 ? none_bit : status_bit) - 1) | (row << 8) | (delta << 16) | ((clear ? 6u : 0u) << 24);
             return e;
         };
         lut[ROCK_IDX_NOOP] = entry(0xFFFFFFFFu, -1, false, 0, ROCK_ROW_ZERO);
@@ -159,7 +156,7 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         const int rows = rock_rows(q);
         for (int cell = 0; cell < rows; ++cell) {
             const int x = cell & 15, y = cell >> 4;
-            RockEntry* row = lut + ROCK_SPECIALS + (size_t)cell * n_act;
+            RockLut* row = lut + ROCK_SPECIALS + (size_t)cell * n_act;
             for (int a = 0; a < 4; ++a) {                                // rock.py:134-158
                 const int nx = x + move_dx(a), ny = y + move_dy(a);
                 if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n)

@@ -19,6 +19,7 @@
 // There is no CPU path in this file: every entry point launches a kernel.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pomdp_core.h"
 #include "pomdp_host.h"
@@ -74,6 +75,15 @@ __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_sme
                  "r"(bytes)
                  : "memory");
 }
+// Programmatic dependent launch (PDL): a step kernel is launched with the programmatic-stream-
+// serialization attribute, so its CTAs may be scheduled -- and run their prologue: barrier init,
+// TMA copy of the static table -- while the previous kernel in the stream is still draining.
+// pdl_wait() blocks until that kernel has completed and its writes are visible; nothing that
+// another kernel may have produced is touched before it.  pdl_launch_dependents() lets the NEXT
+// kernel's CTAs start filling SM slots as soon as this kernel's CTAs retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -95,8 +105,8 @@ struct RockEnvT {
     __device__ static __forceinline__ void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
                                                  int32_t ob[4], float rw[4], int32_t fl[4]) {
-        const RockEntry* rtab = reinterpret_cast<const RockEntry*>(tbl + ROCK_RTAB_OFFSET);
-        const RockEntry* lut = reinterpret_cast<const RockEntry*>(tbl + ROCK_LUT_OFFSET);
+        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
+        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
         const U4 qs = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
         U4 qg = {0, 0, 0, 0};
         if (STOCH) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
@@ -108,8 +118,8 @@ struct RockEnvT {
     __device__ static __forceinline__ void step1(const Params& p, const unsigned char* tbl, S s, int32_t a,
                                                  const PhiloxKey& seed, uint64_t env, uint32_t ctr, S& s2, int32_t& ob,
                                                  float& rw, int32_t& fl) {
-        const RockEntry* rtab = reinterpret_cast<const RockEntry*>(tbl + ROCK_RTAB_OFFSET);
-        const RockEntry* lut = reinterpret_cast<const RockEntry*>(tbl + ROCK_LUT_OFFSET);
+        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
+        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
         const uint32_t ws = draw_word(seed, env, ctr, DOMAIN_STEP, 1);
         const uint32_t wg = STOCH ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
         rock_step<S, STOCH>(p, lut, rtab, s, a, wg, ws, s2, ob, rw, fl);
@@ -287,6 +297,8 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
         }
         __syncthreads();   // barrier object initialised before anyone polls it
     }
+    pdl_wait();                // everything above overlapped the previous kernel's tail; state/action may be its outputs
+    pdl_launch_dependents();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     bool table_ready = !Env::kTable;
@@ -649,6 +661,28 @@ inline int allow_smem(K kernel, size_t smem) {   // dynamic shared memory above 
     return e == cudaSuccess ? 0 : host::fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
 }
 
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("POMDP_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait above); also valid
+// under stream capture, where it becomes a programmatic dependency edge of the CUDA graph.
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <class Env>
 int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
                 const int32_t* state,
@@ -667,14 +701,14 @@ int launch_step(const typename Env::Params& p, const void* d_table, uint32_t tab
         auto k = pomdp_step_kernel<Env, true>;
         if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, (n + 3) >> 2, POMDP_STEP_THREADS, smem);
-        k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
-                                                  (uint64_t)goff, key, step_ctr, table_bytes);
+        launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
+                   (uint64_t)goff, key, step_ctr, table_bytes);
     } else {
         auto k = pomdp_step_kernel<Env, false>;
         if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
-        k<<<grid, POMDP_STEP_THREADS, smem, st>>>(p, d_table, state, action, next_state, obs, reward, flags, n,
-                                                  (uint64_t)goff, key, step_ctr, table_bytes);
+        launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
+                   (uint64_t)goff, key, step_ctr, table_bytes);
     }
     return finish(what);
 }

@@ -28,8 +28,8 @@ void store_state(int32_t* base, int64_t i, uint64_t s) { base[2 * i] = (int32_t)
 template <typename S>
 int rock_step_host(const RockDev& d, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
                    int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step) {
-    const RockEntry* rtab = (const RockEntry*)((const char*)table + ROCK_RTAB_OFFSET);
-    const RockEntry* lut = (const RockEntry*)((const char*)table + ROCK_LUT_OFFSET);
+    const RockRes* rtab = (const RockRes*)((const char*)table + ROCK_RTAB_OFFSET);
+    const RockLut* lut = (const RockLut*)((const char*)table + ROCK_LUT_OFFSET);
     const PhiloxKey key = philox_key(seed);
     for (int64_t i = 0; i < n; ++i) {
         S s2;
