@@ -250,6 +250,24 @@ inline int hist_bins(int kind, int p0, int p1) {
     return -1;
 }
 
+// shared argument checks of pomdp_coord_op / pomdp_belief_hist (host side, before any launch)
+inline int check_coord_op(int op, int xs, const void* a, const void* b, const void* out, int64_t n) {
+    if (op < 0 || op > POMDP_COORD_TAG_IS_INSIDE) return fail(POMDP_E_BADARG, "coord: unknown op %d", op);
+    if (n < 0 || (n > 0 && (!a || !out))) return fail(POMDP_E_BADARG, "coord: bad n or NULL pointer");
+    if ((op == POMDP_COORD_ADD_MOVE || op == POMDP_COORD_L1) && n > 0 && !b)
+        return fail(POMDP_E_BADARG, "coord: op %d needs b", op);
+    if ((op == POMDP_COORD_GET_COORD || op == POMDP_COORD_GET_INDEX) && xs <= 0)
+        return fail(POMDP_E_BADARG, "coord: x_size must be positive");
+    return 0;
+}
+inline int check_hist(int kind, int p0, int p1, const void* state, int words, int64_t n, const void* hist, int max_bins) {
+    const int bins = hist_bins(kind, p0, p1);
+    if (bins <= 0 || bins > max_bins) return fail(POMDP_E_BADARG, "belief_hist: bad kind/bins");
+    if (words < 1 || words > SHIP_WORDS) return fail(POMDP_E_BADARG, "belief_hist: words %d outside 1..8", words);
+    if (n < 0 || (n > 0 && (!state || !hist))) return fail(POMDP_E_BADARG, "belief_hist: bad n or NULL pointer");
+    return 0;
+}
+
 inline int check_io(const void* state, const void* action, const void* next, const void* obs, const void* rw,
                     const void* fl, int64_t n) {
     if (n < 0) return fail(POMDP_E_BADARG, "n = %lld is negative", (long long)n);

@@ -891,12 +891,8 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
 // ---- helpers
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n,
                    void* stream) {
-    if (op < 0 || op > POMDP_COORD_TAG_IS_INSIDE) return host::fail(POMDP_E_BADARG, "coord: unknown op %d", op);
-    if (n < 0 || (n > 0 && (!a || !out))) return host::fail(POMDP_E_BADARG, "coord: bad n or NULL pointer");
-    if ((op == POMDP_COORD_ADD_MOVE || op == POMDP_COORD_L1) && n > 0 && !b)
-        return host::fail(POMDP_E_BADARG, "coord: op %d needs b", op);
-    if ((op == POMDP_COORD_GET_COORD || op == POMDP_COORD_GET_INDEX) && xs <= 0)
-        return host::fail(POMDP_E_BADARG, "coord: x_size must be positive");
+    const int rc = host::check_coord_op(op, xs, a, b, out, n);
+    if (rc) return rc;
     if (n == 0) return 0;
     auto k = pomdp_coord_kernel;
     const int grid = grid_for(k, n);
@@ -907,10 +903,9 @@ int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const i
 int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1) { return host::hist_bins(kind, p0, p1); }
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
                       long long* hist, void* stream) {
+    const int rc = host::check_hist(kind, p0, p1, state, words, n, hist, POMDP_HIST_MAX_BINS);
+    if (rc) return rc;
     const int bins = host::hist_bins(kind, p0, p1);
-    if (bins <= 0 || bins > POMDP_HIST_MAX_BINS) return host::fail(POMDP_E_BADARG, "belief_hist: bad kind/bins");
-    if (words < 1 || words > SHIP_WORDS) return host::fail(POMDP_E_BADARG, "belief_hist: words %d outside 1..8", words);
-    if (n < 0 || (n > 0 && (!state || !hist))) return host::fail(POMDP_E_BADARG, "belief_hist: bad n or NULL pointer");
     if (n == 0) return 0;
     auto k = pomdp_belief_hist_kernel;
     const int grid = grid_for(k, n);

@@ -65,7 +65,7 @@ class TagEnv(BatchedPomdpEnv):
     def pack(self, agent, opp, num_opp=None, done=None):
         """agent int[n] cell ids, opp int[n, num_opponents] -> packed int32[n]."""
         agent = torch.as_tensor(agent, device=self.device).to(torch.int64)
-        opp = torch.as_tensor(opp, device=self.device).to(torch.int64).reshape(agent.shape[0], -1)
+        opp = torch.as_tensor(opp, device=self.device).to(torch.int64).reshape(agent.shape[0], self.num_opponents)
         v = agent.clone()
         for j in range(self.num_opponents):
             v |= opp[:, j] << (5 + 5 * j)

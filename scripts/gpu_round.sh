@@ -13,8 +13,8 @@ echo "== bench eager"; timeout 600 python bench.py --no-graph --no-cpu --steps 5
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>> $OUT/bench.err | tee $OUT/bench_reference.json
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --no-graph --no-cpu --steps 20 --warmup 3 --e2e-steps 1 > $OUT/ncu_launch_bench.log 2>&1
+    python bench.py --no-graph --no-cpu --profiler-range --steps 20 --warmup 3 --e2e-steps 1 > $OUT/ncu_launch_bench.log 2>&1
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:pomdp_step_kernel -s 5 -c 3 -f -o $OUT/rock_step \
-    python bench.py --no-graph --no-cpu --steps 20 --warmup 3 --e2e-steps 1 > $OUT/ncu_full_bench.log 2>&1
+    python bench.py --no-graph --no-cpu --profiler-range --steps 20 --warmup 3 --e2e-steps 1 > $OUT/ncu_full_bench.log 2>&1
 ls -la $OUT

@@ -258,6 +258,8 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
 }
 
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
+    const int rc = host::check_coord_op(op, xs, a, b, out, n);
+    if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         switch (op) {
             case POMDP_COORD_GET_INDEX: out[i] = grid_get_index(xs, a[2 * i], a[2 * i + 1]); break;
@@ -282,7 +284,8 @@ int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const i
 int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1) { return host::hist_bins(kind, p0, p1); }
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
                       long long* hist, void*) {
-    if (host::hist_bins(kind, p0, p1) <= 0) return host::fail(POMDP_E_BADARG, "belief_hist: bad kind");
+    const int rc = host::check_hist(kind, p0, p1, state, words, n, hist, 512);
+    if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s[SHIP_WORDS] = {0};
         for (int k = 0; k < words && k < SHIP_WORDS; ++k) s[k] = (uint32_t)state[i * words + k];

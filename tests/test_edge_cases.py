@@ -1,0 +1,282 @@
+"""Shapes and corner cases of the batched entry points: empty and ragged batches, views that
+are not 16-byte aligned, shard offsets that are not multiples of four, in-place steps,
+masked resets and the per-element error flags that stand in for the reference's asserts
+(rock.py:125-126, tag.py:109-110, battleship.py:93-95, tiger.py:74-75, network.py:73-74).
+
+Runs on the host simulation here and, marked ``gpu``, on the CUDA library -- where the
+same cases drive the vector path, the scalar path, the tail and the grid-stride loop of
+pomdp_step_kernel / pomdp_reset_kernel against each other.
+"""
+import numpy as np
+import pytest
+import torch
+
+import gym_pomdp_b200 as gp
+from gym_pomdp_b200 import _lib
+
+from backends import backend  # noqa: F401
+
+
+def make_all(dev, B, seed=77, **kw):
+    return {
+        "rock": gp.make("Rock-v0", board_size=11, num_rocks=11, batch_size=B, device=dev, seed=seed, **kw),
+        "rock15": gp.make("Rock-v0", board_size=15, num_rocks=15, batch_size=B, device=dev, seed=seed, **kw),
+        "srock": gp.make("StochasticRock-v0", board_size=7, num_rocks=8, batch_size=B, device=dev, seed=seed, **kw),
+        "tag": gp.make("Tag-v0", batch_size=B, device=dev, seed=seed, **kw),
+        "tag3": gp.make("Tag-v0", num_opponents=3, batch_size=B, device=dev, seed=seed, **kw),
+        "tiger": gp.make("Tiger-v0", batch_size=B, device=dev, seed=seed, **kw),
+        "network": gp.make("Network-v0", batch_size=B, device=dev, seed=seed, **kw),
+        "ship": gp.make("Battleship-v0", board_size=(10, 10), batch_size=B, device=dev, seed=seed, **kw),
+    }
+
+
+def random_inputs(env, name, n, rs, dev):
+    """Synthetic (state, action) of SURVEY.md §8d for every env."""
+    if name.startswith("rock") or name == "srock":
+        b, k = env.grid.x_size, env.num_rocks
+        state = env.pack(rs.randint(0, b, n), rs.randint(0, b, n), rs.randint(-1, 2, (n, k)))
+        action = rs.randint(0, 5 + k, n)
+    elif name.startswith("tag"):
+        k = env.num_opponents
+        state = env.pack(rs.randint(0, 29, n), rs.randint(0, 29, (n, k)))
+        action = rs.randint(0, 5, n)
+    elif name == "tiger":
+        state, action = env.pack(rs.randint(0, 2, n)), rs.randint(0, 3, n)
+    elif name == "network":
+        state = torch.as_tensor(rs.randint(0, 1024, n), device=dev).int()
+        action = rs.randint(0, 21, n)
+    else:
+        state, _ = env.init_states(n, step_ctr=99)
+        action = rs.randint(0, 100, n)
+    return state, torch.as_tensor(action, device=dev).int()
+
+
+NAMES = ["rock", "rock15", "srock", "tag", "tag3", "tiger", "network", "ship"]
+
+
+def eq(a, b):
+    return all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_empty_batch(backend, name):
+    env = make_all(backend, 0)[name]
+    rs = np.random.RandomState(0)
+    state, action = random_inputs(env, name, 0, rs, backend)
+    out = env.simulate(state, action, step_ctr=1)
+    assert [o.shape[0] for o in out] == [0, 0, 0, 0]
+    st, ob = env.init_states(0)
+    assert st.shape[0] == 0 and ob.shape[0] == 0
+    assert int(env.belief_histogram(st).sum()) == 0
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_ragged_sizes_offsets_and_alignment_agree(backend, name):
+    """One big aligned launch is the reference; every sub-range of it -- any length, any
+    start (so global_offset % 4 != 0 and pointers off the 16-byte grid), i.e. the scalar
+    kernel path and the 1..3-env tail -- must reproduce the same rows: the draw word of an
+    env depends on its GLOBAL index only."""
+    N = 1003
+    env = make_all(backend, N)[name]
+    rs = np.random.RandomState(5)
+    state, action = random_inputs(env, name, N, rs, backend)
+    full = env.simulate(state, action, step_ctr=9)
+    for lo, hi in [(0, 1), (0, 3), (0, 4), (0, 5), (1, 2), (1, 9), (2, 1003), (3, 260), (4, 1001), (7, 7), (128, 640),
+                   (998, 1003)]:
+        env.global_offset = lo
+        part = env.simulate(state[lo:hi], action[lo:hi], step_ctr=9)
+        env.global_offset = 0
+        assert eq(part, [f[lo:hi] for f in full]), (name, lo, hi)
+    # reset: same property
+    fs, fo = env.init_states(N, step_ctr=4)
+    for lo, hi in [(0, 2), (1, 6), (5, 1003), (8, 1000)]:
+        env.global_offset = lo
+        ps = torch.empty_like(fs[lo:hi])
+        po = torch.empty_like(fo[lo:hi])
+        buf_s, buf_o = torch.empty_like(fs), torch.empty_like(fo)      # views into bigger buffers: odd alignment
+        env.init_states(hi - lo, out=(buf_s[lo:hi], buf_o[lo:hi]), step_ctr=4)
+        env.global_offset = 0
+        assert torch.equal(buf_s[lo:hi], fs[lo:hi]) and torch.equal(buf_o[lo:hi], fo[lo:hi]), (name, lo, hi)
+        del ps, po
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_in_place_step(backend, name):
+    N = 517
+    env = make_all(backend, N)[name]
+    rs = np.random.RandomState(6)
+    state, action = random_inputs(env, name, N, rs, backend)
+    ref = env.simulate(state, action, step_ctr=3)
+    work = state.clone()
+    out = (work, torch.empty(N, dtype=torch.int32, device=backend), torch.empty(N, dtype=torch.float32, device=backend),
+           torch.empty(N, dtype=torch.int32, device=backend))
+    env.simulate(work, action, out=out, step_ctr=3)       # next_state aliases state
+    assert eq(out, ref)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_shard_invariance(backend, name):
+    """Index-split shards (what N GPUs do) reproduce the single-device batch exactly."""
+    N = 4096
+    env = make_all(backend, N)[name]
+    rs = np.random.RandomState(8)
+    state, action = random_inputs(env, name, N, rs, backend)
+    full = env.simulate(state, action, step_ctr=21)
+    full_reset = env.init_states(N, step_ctr=22)
+    for shards in (2, 8):
+        per = N // shards
+        parts, resets = [], []
+        for r in range(shards):
+            e = make_all(backend, per, global_offset=r * per)[name]
+            parts.append(e.simulate(state[r * per:(r + 1) * per], action[r * per:(r + 1) * per], step_ctr=21))
+            resets.append(e.init_states(per, step_ctr=22))
+        cat = [torch.cat([p[i] for p in parts]) for i in range(4)]
+        assert eq(cat, full), (name, shards)
+        assert eq([torch.cat([p[i] for p in resets]) for i in range(2)], full_reset), (name, shards)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_determinism_and_counter_separation(backend, name):
+    N = 2048
+    env = make_all(backend, N)[name]
+    rs = np.random.RandomState(9)
+    state, action = random_inputs(env, name, N, rs, backend)
+    a = env.simulate(state, action, step_ctr=5)
+    b = env.simulate(state, action, step_ctr=5)
+    assert eq(a, b)
+    if name not in ("ship",):                              # BattleShip's step draws nothing
+        c = env.simulate(state, action, step_ctr=6)
+        env2 = make_all(backend, N, seed=78)[name]
+        d = env2.simulate(state, action, step_ctr=5)
+        assert not eq(a, c) and not eq(a, d)
+    r1, r2 = env.init_states(N, step_ctr=5), env.init_states(N, step_ctr=6)
+    if name != "network":                                  # network.py:61-69: deterministic reset
+        assert not torch.equal(r1[0], r2[0])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_masked_reset(backend, name):
+    N = 777
+    env = make_all(backend, N)[name]
+    env.reset()
+    rs = np.random.RandomState(10)
+    state, action = random_inputs(env, name, N, rs, backend)
+    env._set_state(state)
+    before = env.state.clone()
+    mask = torch.as_tensor(rs.randint(0, 2, N), device=backend).bool()
+    mask[:8] = torch.tensor([1, 0, 0, 0, 1, 1, 1, 1], device=backend).bool()    # a partial and a full group of four
+    ctr = env._step_ctr + 1
+    obs = env.reset(mask=mask)
+    fresh, fresh_ob = env.init_states(N, step_ctr=ctr)
+    m = mask.view(-1, *([1] * (before.dim() - 1)))
+    assert torch.equal(env.state, torch.where(m, fresh, before))
+    assert torch.equal(obs[mask], fresh_ob[mask])
+
+
+def test_error_flags(backend):
+    envs = make_all(backend, 8)
+    dev = backend
+    F = _lib
+    # bad action / stepping a finished env / state outside the domain: flagged, state unchanged, obs = reward = 0
+    for name in NAMES:
+        env = envs[name]
+        rs = np.random.RandomState(11)
+        state, action = random_inputs(env, name, 8, rs, dev)
+        bad = action.clone()
+        bad[0], bad[3] = env.action_space.n, -1
+        ns, ob, rw, fl = env.simulate(state, bad, step_ctr=2)
+        for i in (0, 3):
+            assert int(fl[i]) == F.FLAG_BAD_ACTION, (name, int(fl[i]))
+            assert torch.equal(ns[i], state[i]) and int(ob[i]) == 0 and float(rw[i]) == 0.0
+        good = env.simulate(state, action, step_ctr=2)
+        for i in (1, 2, 4, 5, 6, 7):
+            assert all(torch.equal(x[i], y[i]) for x, y in zip((ns, ob, rw, fl), good)), name
+    # Rock: walk off the east edge -> done; stepping again -> STEPPED_DONE
+    env = envs["rock"]
+    s = env.pack([10] * 8, [3] * 8, np.ones((8, 11), int))
+    ns, ob, rw, fl = env.simulate(s, torch.ones(8, dtype=torch.int32, device=dev), step_ctr=1)
+    assert (rw == 10).all() and (fl == F.FLAG_DONE).all() and env.unpack(ns)[3].all()
+    ns2, ob2, rw2, fl2 = env.simulate(ns, torch.zeros(8, dtype=torch.int32, device=dev), step_ctr=2)
+    assert (fl2 == (F.FLAG_DONE | F.FLAG_STEPPED_DONE)).all() and torch.equal(ns2, ns) and (rw2 == 0).all()
+    # Rock(15,15): the dangling grid id at (12, 2) (rock.py:60 lists 16 rocks, IndexError at rock.py:162)
+    env = envs["rock15"]
+    s = env.pack([12] * 8, [2] * 8, np.ones((8, 15), int))
+    ns, ob, rw, fl = env.simulate(s, torch.full((8,), 4, dtype=torch.int32, device=dev), step_ctr=1)
+    assert ((fl & F.FLAG_BAD_STATE) != 0).all() and (rw == -100).all()
+    # Tag: agent cell 31 is not on the 29-cell board
+    env = envs["tag"]
+    s = env.pack([31] * 8, np.zeros((8, 1), int))
+    ns, ob, rw, fl = env.simulate(s, torch.zeros(8, dtype=torch.int32, device=dev), step_ctr=1)
+    assert (fl == F.FLAG_BAD_STATE).all() and torch.equal(ns, s)
+    # Tiger: terminal step returns obs = state and a finished env
+    env = envs["tiger"]
+    s = env.pack([0, 1] * 4)
+    a = torch.tensor([0, 1] * 4, dtype=torch.int32, device=dev)
+    ns, ob, rw, fl = env.simulate(s, a, step_ctr=1)
+    assert (rw == -20).all() and (fl == F.FLAG_DONE).all() and ob.tolist() == [0, 1] * 4       # tiger.py:81-83
+    _, _, _, fl2 = env.simulate(ns, a, step_ctr=2)
+    assert (fl2 == (F.FLAG_DONE | F.FLAG_STEPPED_DONE)).all()
+    # Network: bits above n_machines are not a state
+    env = envs["network"]
+    s = torch.full((8,), 1 << 12, dtype=torch.int32, device=dev)
+    ns, ob, rw, fl = env.simulate(s, torch.zeros(8, dtype=torch.int32, device=dev), step_ctr=1)
+    assert (fl == F.FLAG_BAD_STATE).all() and torch.equal(ns, s)
+
+
+def test_battleship_sink_everything(backend):
+    """Shoot every cell of every board: reward -1 per fresh shot, +n_tiles on the last hit, done
+    exactly when total_remaining hits 0, -10 on repeats, STEPPED_DONE afterwards."""
+    B = 64
+    env = gp.make("Battleship-v0", board_size=(10, 10), batch_size=B, device=backend, seed=3)
+    env.reset()
+    occ, _, _, _ = env.unpack(env.state)
+    occ = occ.cpu().numpy().reshape(B, 10, 10)
+    hits = np.zeros(B, int)
+    finished = np.zeros(B, bool)
+    for a in range(100):
+        act = torch.full((B,), a, dtype=torch.int32, device=backend)
+        ob, rw, done, info = env.step(act)
+        ob, rw, done, fl = ob.cpu().numpy(), rw.cpu().numpy(), done.cpu().numpy(), info["flags"].cpu().numpy()
+        live = ~finished
+        hit = occ[:, a % 10, a // 10]
+        hits[live] += hit[live]
+        last = live & (hits == 5) & hit
+        assert np.array_equal(ob[live], hit[live].astype(np.int32))
+        assert np.array_equal(rw[live], np.where(last[live], 99.0, -1.0).astype(np.float32))
+        assert np.array_equal(done[live], last[live])
+        assert ((fl[finished] & _lib.FLAG_STEPPED_DONE) != 0).all()
+        finished |= last
+    assert finished.all()
+    # repeat shot on an unfinished board costs -10 and reports a miss
+    env.reset()
+    a0 = torch.zeros(B, dtype=torch.int32, device=backend)
+    env.step(a0)
+    ob, rw, done, _ = env.step(a0)
+    assert (rw == -10).all() and (ob == 0).all() and not done.any()
+
+
+def test_belief_histogram_matches_bincount(backend):
+    N = 5000
+    envs = make_all(backend, N)
+    rs = np.random.RandomState(12)
+    for name in NAMES:
+        env = envs[name]
+        state, _ = random_inputs(env, name, N, rs, backend)
+        h = env.belief_histogram(state).cpu().numpy()
+        if name.startswith("rock") or name == "srock":
+            x, y, st, _ = (v.cpu().numpy() for v in env.unpack(state))
+            k = env.num_rocks
+            exp = np.concatenate([(st == 1).sum(0), np.bincount(x | (y << 4), minlength=256)])
+            assert np.array_equal(h, exp), name
+        elif name.startswith("tag"):
+            ag, op, _, _ = (v.cpu().numpy() for v in env.unpack(state))
+            exp = np.concatenate([np.bincount(ag, minlength=29), np.bincount(op[:, 0], minlength=29)])
+            assert np.array_equal(h, exp), name
+        elif name == "tiger":
+            assert np.array_equal(h, np.bincount(env.unpack(state)[0].cpu().numpy(), minlength=2))
+        elif name == "network":
+            s = state.cpu().numpy()
+            assert np.array_equal(h, [((s >> m) & 1).sum() for m in range(10)])
+        else:
+            occ = env.unpack(state)[0].cpu().numpy().reshape(N, 10, 10)
+            assert np.array_equal(h.reshape(10, 10), occ.sum(0).T)      # bin c = 10*y + x
