@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -56,6 +56,9 @@ _P = c_void_p  # device (or, under hostsim, host) array pointers travel as raw a
 _STEP_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 _RESET_TAIL = [_P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 
+_POLICY_TAIL = [_P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
+_ROLLOUT_TAIL = [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_int32, c_double, c_void_p]
+
 _PROTOTYPES = {
     "pomdp_abi_version": (c_int32, []),
     "pomdp_last_error": (c_char_p, []),
@@ -75,6 +78,16 @@ _PROTOTYPES = {
     "pomdp_tiger_reset": (c_int32, [POINTER(TigerParams)] + _RESET_TAIL),
     "pomdp_network_step": (c_int32, [POINTER(NetworkParams)] + _STEP_TAIL),
     "pomdp_network_reset": (c_int32, [POINTER(NetworkParams), _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_policy": (c_int32, [POINTER(RockParams), _P] + _POLICY_TAIL),
+    "pomdp_rock_rollout": (c_int32, [POINTER(RockParams), _P] + _ROLLOUT_TAIL),
+    "pomdp_tag_policy": (c_int32, [POINTER(TagParams)] + _POLICY_TAIL),
+    "pomdp_tag_rollout": (c_int32, [POINTER(TagParams)] + _ROLLOUT_TAIL),
+    "pomdp_battleship_policy": (c_int32, [POINTER(BattleshipParams)] + _POLICY_TAIL),
+    "pomdp_battleship_rollout": (c_int32, [POINTER(BattleshipParams)] + _ROLLOUT_TAIL),
+    "pomdp_tiger_policy": (c_int32, [POINTER(TigerParams)] + _POLICY_TAIL),
+    "pomdp_tiger_rollout": (c_int32, [POINTER(TigerParams)] + _ROLLOUT_TAIL),
+    "pomdp_network_policy": (c_int32, [POINTER(NetworkParams)] + _POLICY_TAIL),
+    "pomdp_network_rollout": (c_int32, [POINTER(NetworkParams)] + _ROLLOUT_TAIL),
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = [os.path.join(CSRC, "pomdp_kernels.cu")]
-HEADERS = [os.path.join(CSRC, "pomdp_core.h"), os.path.join(CSRC, "pomdp_host.h"),
+HEADERS = [os.path.join(CSRC, "pomdp_core.h"), os.path.join(CSRC, "pomdp_envs.h"), os.path.join(CSRC, "pomdp_host.h"),
            os.path.join(os.path.dirname(HERE), "include", "pomdp_b200.h")]
 OUT = os.path.join(CSRC, "libpomdp_b200.so")
 

@@ -26,7 +26,7 @@ namespace pomdp {
 typedef unsigned __int128 u128;
 
 enum : int32_t { FLAG_DONE = 1, FLAG_BAD_ACTION = 2, FLAG_STEPPED_DONE = 4, FLAG_BAD_STATE = 8 };
-enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1 };
+enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1, DOMAIN_POLICY = 2 };
 
 // ------------------------------------------------------------------ Philox4x32-10 ----
 struct U4 { uint32_t x, y, z, w; };
@@ -103,6 +103,14 @@ POMDP_HD uint32_t rand_below(uint32_t r, uint32_t n) { return mulhi32(r, n); }
 // np.random.binomial(1, p) with T = ceil(p * 2^32)  (0 <= T <= 2^32, hence 64-bit).
 POMDP_HD bool bern(uint32_t r, uint64_t T) { return (uint64_t)r < T; }
 
+POMDP_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
 // ------------------------------------------------------------------ geometry --------
 // Moves, coord.py:101-106: 0 N(0,+1) 1 E(+1,0) 2 S(0,-1) 3 W(-1,0) 4 NULL(0,0).
 POMDP_HD int move_dx(int m) { return (m == 1) - (m == 3); }
@@ -136,7 +144,7 @@ POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y -
 // ====================================================================== RockSample ===
 // Static maps of one Rock configuration, built on the host (pomdp_host.h: make_rock) and
 // staged into shared memory by ONE TMA bulk copy per CTA.  Byte layout:
-//   RockTableHdr (400 B)         the reference's own maps (grid, rock coordinates, sensor thresholds)
+//   RockTableHdr (432 B)         the reference's own maps (grid, rock coordinates, sensor thresholds, legal-list order)
 //   RockRes rtab[64]  (16 B)     results: 8 rows x 8 entries; entry = row + 2 * status code + truthful
 //   RockLut special[4] (8 B)     NOOP (failed p_move gate), STEPPED_DONE, BAD_ACTION
 //   RockLut lut[rows * n_act]    transitions, indexed by (agent cell = x | y << 4, action); only the
@@ -159,8 +167,10 @@ struct RockTableHdr {
     int8_t grid[256];      // [x | y << 4] -> rock id written by rock.py:110-111, -1 = none
     uint8_t rock_pos[16];  // rock i -> x | y << 4   (rock.py:106)
     uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2
+    uint8_t legal_act[32]; // position in _generate_legal's candidate order (rock.py:273-291: E, N, S, W, SAMPLE, then
+                           // one check per rock i in rock order) -> the action id that entry holds
 };
-static_assert(sizeof(RockTableHdr) == 400 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+static_assert(sizeof(RockTableHdr) == 432 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
 struct alignas(8) RockLut { uint32_t x, y; };
 struct alignas(16) RockRes { uint32_t x, y, z, w; };
 
@@ -273,6 +283,47 @@ POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t grou
         out[2] |= (S)rock_status_code(q.z) << (8 + 2 * i);
         out[3] |= (S)rock_status_code(q.w) << (8 + 2 * i);
     }
+}
+
+// ---- uniform-legal policy: np.random.choice(env._generate_legal()) --------------------
+POMDP_HD int nth_set_bit(uint32_t m, uint32_t j) {   // index of the (j+1)-th set bit of m (j < popc(m))
+#if defined(__CUDA_ARCH__)
+    return (int)__fns(m, 0u, (int)j + 1);
+#else
+    for (uint32_t i = 0; i < j; ++i) m &= m - 1;
+    return __builtin_ctz(m);
+#endif
+}
+// bits 0, 2, 4, ... of v gathered into the low half
+POMDP_HD uint32_t compress_even(uint32_t v) {
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    v = (v | (v >> 8)) & 0x0000FFFFu;
+    return v;
+}
+POMDP_HD uint32_t rock_alive_bits(uint32_t s) { return compress_even(s >> 8); }           // bit i: rock i status != 0
+POMDP_HD uint32_t rock_alive_bits(uint64_t s) {
+    return compress_even((uint32_t)(s >> 8)) | (compress_even((uint32_t)(s >> 40)) << 16);
+}
+// rock.py:273-291 as a bit mask in the reference's LIST order (bit 0 E, 1 N, 2 S, 3 W, 4 SAMPLE, 5+i check of
+// rock i); hdr->legal_act maps a list position to its action id.  The dangling cell of Rock(15,15)/(7,7), where the
+// reference's own _generate_legal raises IndexError, offers no SAMPLE.
+template <typename S>
+POMDP_HD uint32_t rock_legal_list(const RockDev& p, const RockLut* __restrict__ lut, S s) {
+    const uint32_t x = (uint32_t)s & 15u, y = ((uint32_t)s >> 4) & 15u;
+    uint32_t m = 1u | ((y + 1u < (uint32_t)p.n) ? 2u : 0u) | (y > 0u ? 4u : 0u) | (x > 0u ? 8u : 0u);
+    const RockLut e = lut[ROCK_SPECIALS + ((uint32_t)s & 0xFFu) * p.n_actions + 4u];
+    m |= (shr_wrap(s, e.y) & 6u) ? 16u : 0u;                           // a rock under the agent that is not collected
+    m |= (rock_alive_bits(s) & ((1u << p.k) - 1u)) << 5;
+    return m;
+}
+template <typename S>
+POMDP_HD int32_t rock_policy(const RockDev& p, const RockTableHdr* __restrict__ hdr, const RockLut* __restrict__ lut, S s,
+                             uint32_t w) {
+    const uint32_t m = rock_legal_list<S>(p, lut, s);
+    return (int32_t)hdr->legal_act[nth_set_bit(m, rand_below(w, (uint32_t)popc32(m)))];
 }
 
 // ============================================================================= Tag ===
@@ -430,13 +481,6 @@ struct NetworkDev {
 };
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
 
-POMDP_HD int popc32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __popc(v);
-#else
-    return __builtin_popcount(v);
-#endif
-}
 
 // network.py:71-114 for L consecutive envs of ONE draw group (L = 4: a thread's aligned
 // group, lane0 = 0; L = 1: a single env, lane0 = env & 3).  Slot m = machine m's failure
@@ -612,6 +656,66 @@ POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed
     }
     return true;
 }
+
+// battleship.py:157-165: _generate_legal = the unvisited cells in increasing action order; the policy draws one
+// uniformly (np.random.choice).  An exhausted board (unreachable while total_remaining > 0) yields action 0.
+POMDP_HD int32_t battleship_policy(const ShipDev& p, const uint32_t w[SHIP_WORDS], uint32_t word) {
+    uint32_t open_[4];
+    int cnt = 0;
+    POMDP_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const int lim = p.n_tiles - 32 * i;
+        const uint32_t valid = lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+        open_[i] = ~w[4 + i] & valid;
+        cnt += popc32(open_[i]);
+    }
+    if (cnt == 0) return 0;
+    int k = (int)rand_below(word, (uint32_t)cnt);
+    int32_t a = 0;
+    bool found = false;
+    POMDP_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const int c = popc32(open_[i]);
+        if (!found) {
+            if (k < c) { a = 32 * i + nth_set_bit(open_[i], (uint32_t)k); found = true; }
+            else k -= c;
+        }
+    }
+    return a;
+}
+
+// ========================================================================= rollouts ===
+// what a POMCP simulation does with these envs (the loops at rock.py:563-572 and
+// tag.py:310-316): until done or T steps,  a = np.random.choice(env._generate_legal());  ob, rw, done = env.step(a);
+// r += rw * discount;  discount *= env._discount.   Step t of a rollout that starts at counter c uses counter c + t
+// for BOTH its policy draw (domain POLICY, slot 0) and the step's own draws (domain STEP), so a fused rollout is, draw
+// for draw, T launches of `policy` + `step` with step_ctr = c, c+1, ...  The return is accumulated in IEEE doubles
+// with separately rounded multiply and add, exactly as CPython does.
+POMDP_HD double dmul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+POMDP_HD double dadd_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+struct RolloutAcc {
+    double ret, disc;
+    int32_t steps, flags;
+    POMDP_HD void init(bool done) { ret = 0.0; disc = 1.0; steps = 0; flags = done ? (int32_t)FLAG_DONE : 0; }
+    POMDP_HD void add(double reward, double gamma, int32_t fl) {
+        ret = dadd_rn(ret, dmul_rn(reward, disc));
+        disc = dmul_rn(disc, gamma);
+        ++steps;
+        flags |= fl;
+    }
+};
 
 // ================================================================ belief histogram ===
 // Calls add(bin) for every count this env contributes (bins: include/pomdp_b200.h).

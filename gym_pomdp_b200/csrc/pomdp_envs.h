@@ -1,0 +1,198 @@
+// pomdp_envs.h -- per-env adapters between the transition functors of pomdp_core.h and the generic streaming
+// kernels of pomdp_kernels.cu (step / reset / policy / rollout).  `__host__ __device__` like pomdp_core.h, so
+// tests/hostsim/ drives exactly the same adapters on the CPU.
+#pragma once
+#include "pomdp_core.h"
+
+namespace pomdp {
+
+// ------------------------------------------------------------------- env policies ---
+// Each policy adapts one env's functors from pomdp_core.h to the generic streaming kernels:
+//   step4 / reset4 : the FOUR envs of one aligned draw group (one thread, one Philox call per slot)
+//   step1 / reset1 : a single env (tails, unaligned views, masked resets)
+//   policy         : np.random.choice(env._generate_legal()) from one draw word (uniform over the reference's list)
+//   is_done        : the packed state's terminal bit
+template <typename S, bool STOCH>
+struct RockEnvT {
+    typedef RockDev Params;
+    typedef S State;
+    static constexpr bool kTable = true;
+    static POMDP_HD int32_t policy(const Params& p, const unsigned char* tbl, S s, uint32_t w) {   // rock.py:273-291
+        return rock_policy<S>(p, reinterpret_cast<const RockTableHdr*>(tbl),
+                              reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET), s, w);
+    }
+    static POMDP_HD bool is_done(S s) { return (s & RockBits<S>::DONE) != 0; }
+    static POMDP_HD double reward64(float rw) { return (double)rw; }          // integral rewards (rock.py:141-169)
+    static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
+                                                 int32_t ob[4], float rw[4], int32_t fl[4]) {
+        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
+        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
+        const U4 qs = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
+        U4 qg = {0, 0, 0, 0};
+        if (STOCH) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
+        rock_step<S, STOCH>(p, lut, rtab, s[0], a[0], qg.x, qs.x, s2[0], ob[0], rw[0], fl[0]);
+        rock_step<S, STOCH>(p, lut, rtab, s[1], a[1], qg.y, qs.y, s2[1], ob[1], rw[1], fl[1]);
+        rock_step<S, STOCH>(p, lut, rtab, s[2], a[2], qg.z, qs.z, s2[2], ob[2], rw[2], fl[2]);
+        rock_step<S, STOCH>(p, lut, rtab, s[3], a[3], qg.w, qs.w, s2[3], ob[3], rw[3], fl[3]);
+    }
+    static POMDP_HD void step1(const Params& p, const unsigned char* tbl, S s, int32_t a,
+                                                 const PhiloxKey& seed, uint64_t env, uint32_t ctr, S& s2, int32_t& ob,
+                                                 float& rw, int32_t& fl) {
+        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
+        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
+        const uint32_t ws = draw_word(seed, env, ctr, DOMAIN_STEP, 1);
+        const uint32_t wg = STOCH ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
+        rock_step<S, STOCH>(p, lut, rtab, s, a, wg, ws, s2, ob, rw, fl);
+    }
+    static POMDP_HD void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
+                                                  S s[4], int32_t ob[4]) {
+        rock_reset4<S>(p, seed, group, ctr, s);
+        ob[0] = ob[1] = ob[2] = ob[3] = 0;
+    }
+    static POMDP_HD void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr,
+                                                  S& s, int32_t& ob) {
+        s = rock_reset<S>(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET});
+        ob = 0;
+    }
+};
+
+// Precomputes the NS draw words of each of the four envs of a group (NS Philox calls).
+template <int NS>
+POMDP_HD void quad_words(const PhiloxKey& seed, uint64_t group, uint32_t ctr, uint32_t domain, int n_used,
+                                           WordDraw<NS> d[4]) {
+    POMDP_UNROLL
+    for (int slot = 0; slot < NS; ++slot) {
+        U4 q = {0, 0, 0, 0};
+        if (slot < n_used) q = draw_quad(seed, group, ctr, domain, (uint32_t)slot);   // uniform branch
+        d[0].w[slot] = q.x; d[1].w[slot] = q.y; d[2].w[slot] = q.z; d[3].w[slot] = q.w;
+    }
+}
+
+// NOPP = 1: the stock Tag-v0 (two draw slots); NOPP = 4: any num_opponents in 1..4.
+template <int NOPP>
+struct TagEnvT {
+    typedef TagDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tag.py:228-229
+        return (int32_t)rand_below(w, 5u);
+    }
+    static POMDP_HD bool is_done(State s) { return (s & TAG_DONE) != 0; }
+    static POMDP_HD double reward64(float rw) { return (double)rw; }
+    static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        WordDraw<2 * NOPP> d[4];
+        quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
+    POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) tag_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
+    }
+    static POMDP_HD void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        tag_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+    }
+    static POMDP_HD void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
+                                                  State s[4], int32_t ob[4]) {
+        WordDraw<1 + NOPP> d[4];
+        quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
+    POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
+    }
+    static POMDP_HD void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
+                                                  int32_t& ob) {
+        tag_reset(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
+    }
+};
+
+struct TigerEnvP {
+    typedef TigerDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tiger.py:111-112
+        return (int32_t)rand_below(w, 3u);
+    }
+    static POMDP_HD bool is_done(State s) { return (s & TIGER_DONE) != 0; }
+    static POMDP_HD double reward64(float rw) { return (double)rw; }
+    static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        WordDraw<2> d[4];
+        quad_words<2>(seed, group, ctr, DOMAIN_STEP, 2, d);
+    POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) tiger_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
+    }
+    static POMDP_HD void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        tiger_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+    }
+    static POMDP_HD void reset4(const Params&, const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s[4],
+                                                  int32_t ob[4]) {
+        WordDraw<1> d[4];
+        quad_words<1>(seed, group, ctr, DOMAIN_RESET, 1, d);
+    POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) tiger_reset(d[j], s[j], ob[j]);
+    }
+    static POMDP_HD void reset1(const Params&, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
+                                                  int32_t& ob) {
+        tiger_reset(LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
+    }
+};
+
+struct NetworkEnvP {
+    typedef NetworkDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    static POMDP_HD int32_t policy(const Params& p, const unsigned char*, State, uint32_t w) {     // network.py:129-130
+        return (int32_t)rand_below(w, (uint32_t)(2 * p.n + 1));
+    }
+    static POMDP_HD bool is_done(State s) { return (s & NETWORK_DONE) != 0; }
+    // the reference's reward is the Python double s - 0.1 / s - 2.5 / s == tenths / 10.0 (network.py:87-108); the
+    // float32 the step kernel emits determines the integer number of tenths uniquely
+    static POMDP_HD double reward64(float rw) {
+        const double t = (double)rw * 10.0;
+        return (double)(long long)(t < 0 ? t - 0.5 : t + 0.5) / 10.0;
+    }
+    static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
+                                                 float rw[4], int32_t fl[4]) {
+        network_step_n<4>(p, s, a, seed, group, 0, ctr, s2, ob, rw, fl);
+    }
+    static POMDP_HD void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
+                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
+                                                 int32_t& fl) {
+        network_step_n<1>(p, &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
+    }
+    static POMDP_HD void reset4(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State s[4],
+                                                  int32_t ob[4]) {
+        s[0] = s[1] = s[2] = s[3] = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
+        ob[0] = ob[1] = ob[2] = ob[3] = 0;
+    }
+    static POMDP_HD void reset1(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State& s, int32_t& ob) {
+        s = (1u << p.n) - 1u;
+        ob = 0;
+    }
+};
+
+
+// One env through a whole rollout (scalar kernel path; tests/hostsim runs the same function).
+template <class Env>
+POMDP_HD void rollout1(const typename Env::Params& p, const unsigned char* tbl, typename Env::State& s,
+                       const PhiloxKey& seed, uint64_t env, uint32_t ctr0, int32_t max_steps, double gamma,
+                       RolloutAcc& acc) {
+    acc.init(Env::is_done(s));
+    for (int32_t t = 0; t < max_steps && !Env::is_done(s); ++t) {
+        const uint32_t ctr = ctr0 + (uint32_t)t;
+        const int32_t a = Env::policy(p, tbl, s, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
+        typename Env::State s2;
+        int32_t ob, fl;
+        float rw;
+        Env::step1(p, tbl, s, a, seed, env, ctr, s2, ob, rw, fl);
+        s = s2;
+        acc.add(Env::reward64(rw), gamma, fl);
+    }
+}
+
+}  // namespace pomdp

@@ -123,6 +123,12 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
             h->grid[cell] = (int8_t)i;
             h->rock_pos[i] = (uint8_t)cell;
         }
+        for (int b = 0; b < 32; ++b) {            // rock.py:273-291: [E, N, S, W, SAMPLE, grid[rock.pos] + 5 ...]
+            static const uint8_t head[5] = {1, 0, 2, 3, 4};
+            if (b < 5) h->legal_act[b] = head[b];
+            else if (b - 5 < k) h->legal_act[b] = (uint8_t)(5 + h->grid[h->rock_pos[b - 5]]);
+            else h->legal_act[b] = 0xFF;
+        }
         for (int dd = 0; dd < 32; ++dd) {
             const double eff = (1 + pow(2, -(double)dd / 20)) * .5;      // rock.py:383-387
             h->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
@@ -265,6 +271,26 @@ inline int check_hist(int kind, int p0, int p1, const void* state, int words, in
     if (bins <= 0 || bins > max_bins) return fail(POMDP_E_BADARG, "belief_hist: bad kind/bins");
     if (words < 1 || words > SHIP_WORDS) return fail(POMDP_E_BADARG, "belief_hist: words %d outside 1..8", words);
     if (n < 0 || (n > 0 && (!state || !hist))) return fail(POMDP_E_BADARG, "belief_hist: bad n or NULL pointer");
+    return 0;
+}
+
+inline int check_policy(const void* state, const void* action, int64_t n, int64_t goff, const char* what) {
+    if (n < 0) return fail(POMDP_E_BADARG, "%s: n = %lld is negative", what, (long long)n);
+    if (goff < 0) return fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
+    if (n == 0) return 0;
+    if (!state || !action) return fail(POMDP_E_BADARG, "%s: a required array pointer is NULL", what);
+    if (((uintptr_t)state | (uintptr_t)action) & 3) return fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
+    return 0;
+}
+inline int check_rollout(const void* state, const void* final_state, const void* ret, const void* steps, const void* flags,
+                         int64_t n, int64_t goff, int32_t max_steps, const char* what) {
+    if (n < 0) return fail(POMDP_E_BADARG, "%s: n = %lld is negative", what, (long long)n);
+    if (goff < 0) return fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
+    if (max_steps < 0) return fail(POMDP_E_BADARG, "%s: max_steps is negative", what);
+    if (n == 0) return 0;
+    if (!state || !ret || !steps || !flags) return fail(POMDP_E_BADARG, "%s: a required array pointer is NULL", what);
+    if ((((uintptr_t)state | (uintptr_t)final_state | (uintptr_t)steps | (uintptr_t)flags) & 3) || ((uintptr_t)ret & 7))
+        return fail(POMDP_E_ALIGN, "%s: int32 arrays must be 4-byte and the float64 return array 8-byte aligned", what);
     return 0;
 }
 

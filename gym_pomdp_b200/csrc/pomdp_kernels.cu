@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "pomdp_core.h"
+#include "pomdp_envs.h"
 #include "pomdp_host.h"
 
 using namespace pomdp;
@@ -92,148 +93,6 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ int4 ld_stream4(const int32_t* p) { return __ldcs(reinterpret_cast<const int4*>(p)); }
 __device__ __forceinline__ void st_stream4(int32_t* p, int4 v) { __stcs(reinterpret_cast<int4*>(p), v); }
 __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
-
-// ------------------------------------------------------------------- env policies ---
-// Each policy adapts one env's functors from pomdp_core.h to the generic streaming kernels:
-//   step4 / reset4 : the FOUR envs of one aligned draw group (one thread, one Philox call per slot)
-//   step1 / reset1 : a single env (tails, unaligned views, masked resets)
-template <typename S, bool STOCH>
-struct RockEnvT {
-    typedef RockDev Params;
-    typedef S State;
-    static constexpr bool kTable = true;
-    __device__ static __forceinline__ void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
-                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
-                                                 int32_t ob[4], float rw[4], int32_t fl[4]) {
-        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
-        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
-        const U4 qs = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
-        U4 qg = {0, 0, 0, 0};
-        if (STOCH) qg = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
-        rock_step<S, STOCH>(p, lut, rtab, s[0], a[0], qg.x, qs.x, s2[0], ob[0], rw[0], fl[0]);
-        rock_step<S, STOCH>(p, lut, rtab, s[1], a[1], qg.y, qs.y, s2[1], ob[1], rw[1], fl[1]);
-        rock_step<S, STOCH>(p, lut, rtab, s[2], a[2], qg.z, qs.z, s2[2], ob[2], rw[2], fl[2]);
-        rock_step<S, STOCH>(p, lut, rtab, s[3], a[3], qg.w, qs.w, s2[3], ob[3], rw[3], fl[3]);
-    }
-    __device__ static __forceinline__ void step1(const Params& p, const unsigned char* tbl, S s, int32_t a,
-                                                 const PhiloxKey& seed, uint64_t env, uint32_t ctr, S& s2, int32_t& ob,
-                                                 float& rw, int32_t& fl) {
-        const RockRes* rtab = reinterpret_cast<const RockRes*>(tbl + ROCK_RTAB_OFFSET);
-        const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
-        const uint32_t ws = draw_word(seed, env, ctr, DOMAIN_STEP, 1);
-        const uint32_t wg = STOCH ? draw_word(seed, env, ctr, DOMAIN_STEP, 0) : 0u;
-        rock_step<S, STOCH>(p, lut, rtab, s, a, wg, ws, s2, ob, rw, fl);
-    }
-    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
-                                                  S s[4], int32_t ob[4]) {
-        rock_reset4<S>(p, seed, group, ctr, s);
-        ob[0] = ob[1] = ob[2] = ob[3] = 0;
-    }
-    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr,
-                                                  S& s, int32_t& ob) {
-        s = rock_reset<S>(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET});
-        ob = 0;
-    }
-};
-
-// Precomputes the NS draw words of each of the four envs of a group (NS Philox calls).
-template <int NS>
-__device__ __forceinline__ void quad_words(const PhiloxKey& seed, uint64_t group, uint32_t ctr, uint32_t domain, int n_used,
-                                           WordDraw<NS> d[4]) {
-#pragma unroll
-    for (int slot = 0; slot < NS; ++slot) {
-        U4 q = {0, 0, 0, 0};
-        if (slot < n_used) q = draw_quad(seed, group, ctr, domain, (uint32_t)slot);   // uniform branch
-        d[0].w[slot] = q.x; d[1].w[slot] = q.y; d[2].w[slot] = q.z; d[3].w[slot] = q.w;
-    }
-}
-
-// NOPP = 1: the stock Tag-v0 (two draw slots); NOPP = 4: any num_opponents in 1..4.
-template <int NOPP>
-struct TagEnvT {
-    typedef TagDev Params;
-    typedef uint32_t State;
-    static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
-                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
-                                                 float rw[4], int32_t fl[4]) {
-        WordDraw<2 * NOPP> d[4];
-        quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tag_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
-    }
-    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
-                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
-                                                 int32_t& fl) {
-        tag_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
-    }
-    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
-                                                  State s[4], int32_t ob[4]) {
-        WordDraw<1 + NOPP> d[4];
-        quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
-    }
-    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
-                                                  int32_t& ob) {
-        tag_reset(p, LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
-    }
-};
-
-struct TigerEnvP {
-    typedef TigerDev Params;
-    typedef uint32_t State;
-    static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
-                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
-                                                 float rw[4], int32_t fl[4]) {
-        WordDraw<2> d[4];
-        quad_words<2>(seed, group, ctr, DOMAIN_STEP, 2, d);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tiger_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
-    }
-    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
-                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
-                                                 int32_t& fl) {
-        tiger_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
-    }
-    __device__ static __forceinline__ void reset4(const Params&, const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s[4],
-                                                  int32_t ob[4]) {
-        WordDraw<1> d[4];
-        quad_words<1>(seed, group, ctr, DOMAIN_RESET, 1, d);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tiger_reset(d[j], s[j], ob[j]);
-    }
-    __device__ static __forceinline__ void reset1(const Params&, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,
-                                                  int32_t& ob) {
-        tiger_reset(LazyDraw{&seed, env, ctr, DOMAIN_RESET}, s, ob);
-    }
-};
-
-struct NetworkEnvP {
-    typedef NetworkDev Params;
-    typedef uint32_t State;
-    static constexpr bool kTable = false;
-    __device__ static __forceinline__ void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
-                                                 const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
-                                                 float rw[4], int32_t fl[4]) {
-        network_step_n<4>(p, s, a, seed, group, 0, ctr, s2, ob, rw, fl);
-    }
-    __device__ static __forceinline__ void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
-                                                 uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
-                                                 int32_t& fl) {
-        network_step_n<1>(p, &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
-    }
-    __device__ static __forceinline__ void reset4(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State s[4],
-                                                  int32_t ob[4]) {
-        s[0] = s[1] = s[2] = s[3] = (1u << p.n) - 1u;   // network.py:61-69: all up, obs = OFF (0)
-        ob[0] = ob[1] = ob[2] = ob[3] = 0;
-    }
-    __device__ static __forceinline__ void reset1(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State& s, int32_t& ob) {
-        s = (1u << p.n) - 1u;
-        ob = 0;
-    }
-};
 
 // Four consecutive packed states (32- or 64-bit each) as 16-byte vectors.
 template <typename S> struct StateVec;
@@ -401,6 +260,183 @@ pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __re
         Env::reset1(p, seed, goff + (uint64_t)i, step_ctr, s, ob);
         store_state1(state, i, s);
         if (obs) obs[i] = ob;
+    }
+}
+
+// ------------------------------------------------------- policy / rollout (streams) ---
+// Stages the static table (Rock) into shared memory with one TMA bulk copy and waits for it.
+template <class Env>
+__device__ __forceinline__ void stage_table_sync(unsigned char* smem_table, const void* g_table, uint32_t table_bytes,
+                                                 uint64_t* bar) {
+    if (Env::kTable) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bar, table_bytes);
+            tma_bulk_g2s(smem_table, g_table, table_bytes, bar);
+        }
+        __syncthreads();
+        mbar_wait(bar, 0);
+    }
+}
+
+// action[i] = np.random.choice(env._generate_legal()) for every env: draw (domain POLICY, slot 0) of step_ctr.
+template <class Env, bool kVec>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_policy_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
+                    const int32_t* __restrict__ state, int32_t* __restrict__ action, int64_t n, uint64_t goff,
+                    const __grid_constant__ PhiloxKey seed, uint32_t step_ctr, uint32_t table_bytes) {
+    typedef typename Env::State S;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    const unsigned char* tbl = smem_table;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int64_t scalar_from = 0;
+    if (kVec) {
+        const int64_t n_groups = n >> 2;
+        for (int64_t g = tid; g < n_groups; g += nthreads) {
+            StateVec<S> v;
+            v.load(state, g << 2);
+            S s[4];
+            v.unpack(s);
+            const U4 q = draw_quad(seed, (goff >> 2) + (uint64_t)g, step_ctr, DOMAIN_POLICY, 0);
+            st_stream4(action + (g << 2), make_int4(Env::policy(p, tbl, s[0], q.x), Env::policy(p, tbl, s[1], q.y),
+                                                    Env::policy(p, tbl, s[2], q.z), Env::policy(p, tbl, s[3], q.w)));
+        }
+        scalar_from = n_groups << 2;
+    }
+    for (int64_t i = scalar_from + tid; i < n; i += nthreads)
+        action[i] = Env::policy(p, tbl, load_state1(state, i, S()), draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_POLICY, 0));
+}
+
+// Fused T-step rollout under the uniform-legal policy: the packed states stay in registers for the whole
+// rollout; per env the kernel reads 4W bytes and writes 4W + 16 (final state, float64 return, steps, flags).
+// One thread owns an aligned group of four envs, so every Philox call (one policy word + the step's own
+// slots per time step) serves four envs; all four share the discount gamma^t.
+template <class Env, bool kVec>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
+                     const int32_t* state, int32_t* final_state, double* __restrict__ ret, int32_t* __restrict__ steps,
+                     int32_t* __restrict__ flags, int64_t n, uint64_t goff, const __grid_constant__ PhiloxKey seed,
+                     uint32_t ctr0, int32_t max_steps, double gamma, uint32_t table_bytes) {
+    typedef typename Env::State S;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    const unsigned char* tbl = smem_table;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int64_t scalar_from = 0;
+    if (kVec) {
+        const int64_t n_groups = n >> 2;
+        for (int64_t g = tid; g < n_groups; g += nthreads) {
+            const int64_t i = g << 2;
+            const uint64_t group = (goff >> 2) + (uint64_t)g;
+            StateVec<S> v;
+            v.load(state, i);
+            S s[4];
+            v.unpack(s);
+            double r[4] = {0.0, 0.0, 0.0, 0.0}, disc = 1.0;
+            int32_t nst[4] = {0, 0, 0, 0}, facc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) facc[j] = Env::is_done(s[j]) ? (int32_t)FLAG_DONE : 0;
+            for (int32_t t = 0; t < max_steps; ++t) {
+                bool act[4], any = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { act[j] = !Env::is_done(s[j]); any = any || act[j]; }
+                if (!any) break;
+                const uint32_t ctr = ctr0 + (uint32_t)t;
+                const U4 q = draw_quad(seed, group, ctr, DOMAIN_POLICY, 0);
+                const int32_t a[4] = {Env::policy(p, tbl, s[0], q.x), Env::policy(p, tbl, s[1], q.y),
+                                      Env::policy(p, tbl, s[2], q.z), Env::policy(p, tbl, s[3], q.w)};
+                S s2[4];
+                int32_t ob[4], fl[4];
+                float rw[4];
+                Env::step4(p, tbl, s, a, seed, group, ctr, s2, ob, rw, fl);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (act[j]) {
+                        s[j] = s2[j];
+                        r[j] = dadd_rn(r[j], dmul_rn(Env::reward64(rw[j]), disc));
+                        ++nst[j];
+                        facc[j] |= fl[j];
+                    }
+                disc = dmul_rn(disc, gamma);
+            }
+            if (final_state) StateVec<S>::store(final_state, i, s);
+            __stcs(reinterpret_cast<double2*>(ret + i), make_double2(r[0], r[1]));
+            __stcs(reinterpret_cast<double2*>(ret + i) + 1, make_double2(r[2], r[3]));
+            st_stream4(steps + i, make_int4(nst[0], nst[1], nst[2], nst[3]));
+            st_stream4(flags + i, make_int4(facc[0], facc[1], facc[2], facc[3]));
+        }
+        scalar_from = n_groups << 2;
+    }
+    for (int64_t i = scalar_from + tid; i < n; i += nthreads) {
+        S s = load_state1(state, i, S());
+        RolloutAcc acc;
+        rollout1<Env>(p, tbl, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, acc);
+        if (final_state) store_state1(final_state, i, s);
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
+    }
+}
+
+// BattleShip: one thread per board (8 words in registers); the step draws nothing, the policy one word per step.
+__device__ __forceinline__ void ship_load(const int32_t* state, int64_t i, bool vec, uint32_t w[SHIP_WORDS]) {
+    if (vec) {
+        const uint4 lo = __ldcs(reinterpret_cast<const uint4*>(state + i * SHIP_WORDS));
+        const uint4 hi = __ldcs(reinterpret_cast<const uint4*>(state + i * SHIP_WORDS) + 1);
+        w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SHIP_WORDS; ++k) w[k] = (uint32_t)state[i * SHIP_WORDS + k];
+    }
+}
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_policy_kernel(const __grid_constant__ ShipDev p, const int32_t* __restrict__ state,
+                               int32_t* __restrict__ action, int64_t n, uint64_t goff,
+                               const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
+    const bool vec = (reinterpret_cast<uintptr_t>(state) & 15) == 0;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t w[SHIP_WORDS];
+        ship_load(state, i, vec, w);
+        action[i] = battleship_policy(p, w, draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_POLICY, 0));
+    }
+}
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_rollout_kernel(const __grid_constant__ ShipDev p, const int32_t* state, int32_t* final_state,
+                                double* __restrict__ ret, int32_t* __restrict__ steps, int32_t* __restrict__ flags,
+                                int64_t n, uint64_t goff, const __grid_constant__ PhiloxKey seed, uint32_t ctr0,
+                                int32_t max_steps, double gamma) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(final_state)) & 15) == 0;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t w[SHIP_WORDS], w2[SHIP_WORDS];
+        ship_load(state, i, vec, w);
+        RolloutAcc acc;
+        acc.init((w[3] >> 31) != 0);
+        for (int32_t t = 0; t < max_steps && !(w[3] >> 31); ++t) {
+            const int32_t a = battleship_policy(p, w, draw_word(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, DOMAIN_POLICY, 0));
+            int32_t ob, fl;
+            float rw;
+            battleship_step(p, w, a, w2, ob, rw, fl);
+#pragma unroll
+            for (int k = 0; k < SHIP_WORDS; ++k) w[k] = w2[k];
+            acc.add((double)rw, gamma, fl);
+        }
+        if (final_state) {
+            if (vec) {
+                uint4* dst = reinterpret_cast<uint4*>(final_state + i * SHIP_WORDS);
+                __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+                __stcs(dst + 1, make_uint4(w[4], w[5], w[6], w[7]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < SHIP_WORDS; ++k) final_state[i * SHIP_WORDS + k] = (int32_t)w[k];
+            }
+        }
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
 }
 
@@ -731,6 +767,60 @@ int launch_reset(const typename Env::Params& p, int32_t* state, int32_t* obs, co
     return finish(what);
 }
 
+template <class Env>
+int launch_policy(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                  const int32_t* state, int32_t* action, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                  void* stream, const char* what) {
+    int rc = host::check_policy(state, action, n, goff, what);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = Env::kTable ? smem_bytes : 0;
+    const PhiloxKey key = philox_key(seed);
+    if ((((uintptr_t)state | (uintptr_t)action) & 15) == 0 && (goff & 3) == 0) {
+        auto k = pomdp_policy_kernel<Env, true>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, (n + 3) >> 2, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            p, d_table, state, action, n, (uint64_t)goff, key, step_ctr, table_bytes);
+    } else {
+        auto k = pomdp_policy_kernel<Env, false>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            p, d_table, state, action, n, (uint64_t)goff, key, step_ctr, table_bytes);
+    }
+    return finish(what);
+}
+
+template <class Env>
+int launch_rollout(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                   const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags, int64_t n,
+                   int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps, double discount, void* stream,
+                   const char* what) {
+    int rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = Env::kTable ? smem_bytes : 0;
+    const PhiloxKey key = philox_key(seed);
+    const uintptr_t any = (uintptr_t)state | (uintptr_t)final_state | (uintptr_t)ret | (uintptr_t)steps | (uintptr_t)flags;
+    if ((any & 15) == 0 && (goff & 3) == 0) {
+        auto k = pomdp_rollout_kernel<Env, true>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, (n + 3) >> 2, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            p, d_table, state, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps, discount,
+            table_bytes);
+    } else {
+        auto k = pomdp_rollout_kernel<Env, false>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            p, d_table, state, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps, discount,
+            table_bytes);
+    }
+    return finish(what);
+}
+
 }  // namespace
 
 extern "C" {
@@ -886,6 +976,113 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
     const int grid = grid_for(k, n);
     k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     return finish("pomdp_battleship_reset_rejection");
+}
+
+// ---- uniform-legal policy and fused rollouts
+#define POMDP_ROCK_DISPATCH(FN, ...)                                                          \
+    do {                                                                                      \
+        if (host::rock_words(q) == 1) {                                                       \
+            if (d.stochastic) return FN<RockEnvT<uint32_t, true>>(__VA_ARGS__);               \
+            return FN<RockEnvT<uint32_t, false>>(__VA_ARGS__);                                \
+        }                                                                                     \
+        if (d.stochastic) return FN<RockEnvT<uint64_t, true>>(__VA_ARGS__);                   \
+        return FN<RockEnvT<uint64_t, false>>(__VA_ARGS__);                                    \
+    } while (0)
+
+int pomdp_rock_policy(const PomdpRockParams* q, const void* d_table, const int32_t* state, int32_t* action, int64_t n,
+                      int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    POMDP_ROCK_DISPATCH(launch_policy, d, d_table, d.table_bytes, d.smem_bytes, state, action, n, goff, seed, step_ctr,
+                        stream, "pomdp_rock_policy");
+}
+int pomdp_rock_rollout(const PomdpRockParams* q, const void* d_table, const int32_t* state, int32_t* final_state,
+                       double* ret, int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                       uint32_t step_ctr, int32_t max_steps, double discount, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    POMDP_ROCK_DISPATCH(launch_rollout, d, d_table, d.table_bytes, d.smem_bytes, state, final_state, ret, steps, flags, n,
+                        goff, seed, step_ctr, max_steps, discount, stream, "pomdp_rock_rollout");
+}
+#undef POMDP_ROCK_DISPATCH
+
+int pomdp_tag_policy(const PomdpTagParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                     uint64_t seed, uint32_t step_ctr, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return launch_policy<TagEnvT<1>>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
+}
+int pomdp_tag_rollout(const PomdpTagParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
+                      int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps,
+                      double discount, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if (d.n_opp == 1)
+        return launch_rollout<TagEnvT<1>>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+                                          max_steps, discount, stream, "pomdp_tag_rollout");
+    return launch_rollout<TagEnvT<4>>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+                                      max_steps, discount, stream, "pomdp_tag_rollout");
+}
+int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                       uint64_t seed, uint32_t step_ctr, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_policy<TigerEnvP>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_tiger_policy");
+}
+int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, int32_t* final_state, double* ret,
+                        int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                        int32_t max_steps, double discount, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_rollout<TigerEnvP>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+                                     max_steps, discount, stream, "pomdp_tiger_rollout");
+}
+int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                         uint64_t seed, uint32_t step_ctr, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_policy<NetworkEnvP>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_network_policy");
+}
+int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, int32_t* final_state, double* ret,
+                          int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                          int32_t max_steps, double discount, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_rollout<NetworkEnvP>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+                                       max_steps, discount, stream, "pomdp_network_rollout");
+}
+int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state, int32_t* action, int64_t n,
+                            int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, action, n, goff, "pomdp_battleship_policy"))) return rc;
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_policy_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, action, n, (uint64_t)goff, philox_key(seed), step_ctr);
+    return finish("pomdp_battleship_policy");
+}
+int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, int32_t* final_state, double* ret,
+                             int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                             int32_t max_steps, double discount, void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, "pomdp_battleship_rollout")))
+        return rc;
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_rollout_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, final_state, ret, steps, flags, n, (uint64_t)goff,
+                                                                philox_key(seed), step_ctr, max_steps, discount);
+    return finish("pomdp_battleship_rollout");
 }
 
 // ---- helpers

@@ -20,6 +20,8 @@ Two calling modes:
 on caller-owned particle tensors: what a POMCP / particle-filter caller does with
 ``_set_state(s); step(a)`` in a Python loop, as one launch.
 """
+import ctypes
+
 import torch
 
 from .. import _lib
@@ -74,6 +76,23 @@ class BatchedPomdpEnv(object):
     def _c_reset(self, state, obs, mask, n, ctr):
         raise NotImplementedError
 
+    _abi = None          # "rock", "tag", ...: prefix of the env's C entry points
+
+    def _c_head(self):
+        """Leading arguments of the env's C entry points: (params,) or (params, d_table)."""
+        return (ctypes.byref(self._params),)
+
+    def _c_policy(self, state, action, n, ctr):
+        fn = getattr(_lib.lib(), "pomdp_%s_policy" % self._abi)
+        _lib.check(fn(*self._c_head(), _lib.ptr(state), _lib.ptr(action), n, self.global_offset, self._seed, ctr,
+                      self._stream()), "pomdp_%s_policy" % self._abi)
+
+    def _c_rollout(self, state, final_state, ret, steps, flags, n, ctr, max_steps, discount):
+        fn = getattr(_lib.lib(), "pomdp_%s_rollout" % self._abi)
+        _lib.check(fn(*self._c_head(), _lib.ptr(state), _lib.ptr(final_state), _lib.ptr(ret), _lib.ptr(steps),
+                      _lib.ptr(flags), n, self.global_offset, self._seed, ctr, int(max_steps), float(discount),
+                      self._stream()), "pomdp_%s_rollout" % self._abi)
+
     # subclasses: scalar-mode conversions -------------------------------------------
     def _state_to_ref(self, words):
         raise NotImplementedError
@@ -117,6 +136,43 @@ class BatchedPomdpEnv(object):
         with self._guard():
             self._c_reset(state, obs, mask, n, ctr)
         return state, obs
+
+    def sample_legal_actions(self, state=None, out=None, step_ctr=None):
+        """Batched ``np.random.choice(env._generate_legal())``: one uniformly drawn legal action per
+        particle (the reference's list order decides which), as int32[n].  Uses the POLICY draw of
+        ``step_ctr``; the default is the counter the NEXT ``simulate``/``step`` call will use, so
+        ``a = sample_legal_actions(s); simulate(s, a)`` is one rollout step."""
+        state = self.state if state is None else state
+        n = state.shape[0]
+        action = self._empty((n,), torch.int32) if out is None else out
+        ctr = ((self._step_ctr + 1) & 0xFFFFFFFF) if step_ctr is None else int(step_ctr)
+        with self._guard():
+            self._c_policy(state, action, n, ctr)
+        return action
+
+    def rollout(self, state=None, max_steps=100, discount=None, out=None, step_ctr=None):
+        """Monte-Carlo rollouts under the uniform-legal policy, fused into ONE kernel (states stay
+        in registers): until done or ``max_steps``,
+        ``a = choice(_generate_legal()); ob, rw, done = step(a); ret += rw * disc; disc *= discount``.
+
+        Returns (final_state, ret float64[n], steps int32[n], flags int32[n]).  ``discount`` defaults
+        to the env's ``_discount``.  Draw for draw identical to ``max_steps`` rounds of
+        ``sample_legal_actions`` + ``simulate`` with counters step_ctr, step_ctr + 1, ..."""
+        state = self.state if state is None else state
+        n = state.shape[0]
+        if out is None:
+            out = (torch.empty_like(state), self._empty((n,), torch.float64), self._empty((n,), torch.int32),
+                   self._empty((n,), torch.int32))
+        final_state, ret, steps, flags = out
+        if step_ctr is None:
+            ctr = (self._step_ctr + 1) & 0xFFFFFFFF
+            self._step_ctr = (self._step_ctr + int(max_steps)) & 0xFFFFFFFF
+        else:
+            ctr = int(step_ctr)
+        with self._guard():
+            self._c_rollout(state, final_state, ret, steps, flags, n, ctr, max_steps,
+                            self._discount if discount is None else discount)
+        return final_state, ret, steps, flags
 
     def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20):
         """G(s, a) on HOST buffers (pinned CPU tensors): what a numpy-holding caller of the

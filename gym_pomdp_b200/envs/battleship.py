@@ -29,6 +29,7 @@ class ShipState(object):
 
 class BattleShipEnv(BatchedPomdpEnv):
     kind = _lib.KIND_BATTLESHIP
+    _abi = "battleship"
     state_words = 8
 
     def __init__(self, board_size=(5, 5), max_len=3, batch_size=None, device="cuda", seed=0, global_offset=0,

@@ -21,6 +21,7 @@ SAMPLE = 4                         # rock.py:18-23
 
 class RockEnv(BatchedPomdpEnv):
     kind = _lib.KIND_ROCK
+    _abi = "rock"
     _stochastic = False
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, batch_size=None, device="cuda", seed=0,
@@ -53,6 +54,9 @@ class RockEnv(BatchedPomdpEnv):
         self._side = None   # scalar mode: per-rock belief side-stats (rock.py:82-86)
 
     # -------------------------------------------------------------------- C calls ---
+    def _c_head(self):
+        return (ctypes.byref(self._params), _lib.ptr(self._table))
+
     def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
         _lib.check(_lib.lib().pomdp_rock_step(
             ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state),

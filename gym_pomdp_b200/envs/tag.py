@@ -29,6 +29,7 @@ class TagState(object):
 
 class TagEnv(BatchedPomdpEnv):
     kind = _lib.KIND_TAG
+    _abi = "tag"
 
     def __init__(self, num_opponents=1, move_prob=.8, obs_cells=29, board_size=(10, 5), batch_size=None,
                  device="cuda", seed=0, global_offset=0):

@@ -16,6 +16,7 @@ LEFT, RIGHT, LISTEN = 0, 1, 2   # tiger.py:21-24; observations: 0 left, 1 right,
 
 class TigerEnv(BatchedPomdpEnv):
     kind = _lib.KIND_TIGER
+    _abi = "tiger"
 
     def __init__(self, seed=0, correct_prob=.85, batch_size=None, device="cuda", global_offset=0):
         super().__init__(batch_size, device, seed, global_offset)

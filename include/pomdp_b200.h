@@ -37,7 +37,7 @@
  *    Rock sample is treated as "no rock here").
  *  - Randomness: stateless Philox4x32-10.  The word for draw slot j of env i is
  *        philox(key = seed, ctr = (lo32(g>>2), hi32(g>>2), step_ctr, (domain<<24) | j))[g & 3]
- *    with g = global_offset + i, domain 0 for step and 1 for reset: one Philox block holds
+ *    with g = global_offset + i, domain 0 for step, 1 for reset and 2 for the policy draw: one Philox block holds
  *    the same slot of four consecutive envs, so a thread that owns an aligned group of
  *    four pays one Philox call per slot.  Results do not depend on how a batch is sharded
  *    across GPUs (shards whose global_offset is a multiple of 4 take the vector path; any
@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 2
+#define POMDP_ABI_VERSION 3
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -85,8 +85,8 @@ typedef struct PomdpRockParams {
  *   complement code (0b11 = -1 bad, 0b00 = 0 collected, 0b01 = +1 good), top bit = done. */
 int     pomdp_rock_state_words(const PomdpRockParams* params);
 /* Static per-config maps that the step kernel stages into shared memory with one TMA bulk
- * copy per CTA: a 400-byte header (rock-id grid, rock coordinates, sensor thresholds: the
- * reference's own tables) followed by the transition LUT indexed by (agent cell, action)
+ * copy per CTA: a 432-byte header (rock-id grid, rock coordinates, sensor thresholds, order of
+ * the legal-action list: the reference's own tables) followed by the transition LUT indexed by (agent cell, action)
  * (16.4 KB for <= 11 rocks, 32.8 KB otherwise; layout in gym_pomdp_b200/csrc/pomdp_core.h).
  * The caller uploads the filled buffer to the device (16-byte aligned) and passes it as
  * `d_table`.                                                                              */
@@ -199,6 +199,61 @@ int pomdp_network_step(const PomdpNetworkParams* params,
 int pomdp_network_reset(const PomdpNetworkParams* params,
                         int32_t* state, int32_t* obs, const uint8_t* mask,
                         int64_t n, void* stream);
+
+/* ------------------------------------------- uniform-legal policy and fused rollouts --- */
+/* What a POMCP / Monte-Carlo caller does with these envs between two tree nodes (the loops at
+ * rock.py:563-572 and tag.py:310-316):
+ *
+ *     while not done and t < max_steps:
+ *         a = np.random.choice(env._generate_legal())         # pomdp_E_policy
+ *         ob, rw, done, _ = env.step(a)                       # pomdp_E_step
+ *         r += rw * discount;  discount *= gamma;  t += 1
+ *
+ * pomdp_E_policy  : action[i] = legal_i[floor(u * len(legal_i))], legal_i = the reference's
+ *                   _generate_legal list IN ITS ORDER (rock.py:273-291; tag.py:228-229;
+ *                   battleship.py:157-165; tiger.py:111-112; network.py:129-130), u from draw
+ *                   (domain 2 = POLICY, slot 0) of `step_ctr`.
+ * pomdp_E_rollout : the whole loop in ONE kernel, states in registers.  Step t uses counter
+ *                   step_ctr + t for its policy draw and for the step's own draws, so it equals,
+ *                   draw for draw, max_steps launches of pomdp_E_policy + pomdp_E_step with
+ *                   step_ctr, step_ctr+1, ...  Outputs per env: final_state (may be NULL, may alias
+ *                   state), ret = sum_t rw_t * discount^t as float64 accumulated exactly like the
+ *                   Python loop (separately rounded multiply and add; Network's reward is the exact
+ *                   double tenths/10.0), steps taken, flags = OR of the steps' flags (bit 0 = the
+ *                   rollout ended in a terminal state).  An env that is already terminal takes 0 steps.
+ * Rock(15,15)/(7,7): the dangling cell, where the reference's own _generate_legal raises
+ * IndexError, offers no SAMPLE action.                                                         */
+int pomdp_rock_policy(const PomdpRockParams* params, const void* d_table,
+                      const int32_t* state, int32_t* action,
+                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_rock_rollout(const PomdpRockParams* params, const void* d_table,
+                       const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                       int32_t max_steps, double discount, void* stream);
+int pomdp_tag_policy(const PomdpTagParams* params, const int32_t* state, int32_t* action,
+                     int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_tag_rollout(const PomdpTagParams* params,
+                      const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                      int32_t max_steps, double discount, void* stream);
+int pomdp_battleship_policy(const PomdpBattleshipParams* params, const int32_t* state, int32_t* action,
+                            int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_battleship_rollout(const PomdpBattleshipParams* params,
+                             const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                             int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                             int32_t max_steps, double discount, void* stream);
+int pomdp_tiger_policy(const PomdpTigerParams* params, const int32_t* state, int32_t* action,
+                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_tiger_rollout(const PomdpTigerParams* params,
+                        const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                        int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                        int32_t max_steps, double discount, void* stream);
+int pomdp_network_policy(const PomdpNetworkParams* params, const int32_t* state, int32_t* action,
+                         int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_network_rollout(const PomdpNetworkParams* params,
+                          const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                          int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                          int32_t max_steps, double discount, void* stream);
 
 /* ------------------------------------------------------------ Grid / Coord helpers --- */
 /* coord.py:7-114 and tag.py:36-66 as batched device functions (bit-exact integer work).

@@ -175,3 +175,67 @@ def network_step(n, problem_type, machines, action, draws, p=0.1, q=0.33, p_ob=0
                                    _p(machines), _p(_c(action, np.int32)), _p(_c(draws, np.uint32)), _p(obs), _p(reward))
     assert rc == 0
     return machines, obs, reward
+
+
+# ---- legal actions + uniform-legal rollouts ------------------------
+def rock_legal(n, k, x, y, status):
+    legal = np.empty(40, np.int32)
+    cnt = lib().oracle_rock_legal(c_int(n), c_int(k), c_int(int(x)), c_int(int(y)), _p(_c(status, np.int8)), _p(legal))
+    assert cnt >= 0
+    return legal[:cnt].tolist()
+
+
+def rock_rollout(n, k, stochastic, p_move, x, y, status, seed, goff, ctr0, max_steps, gamma):
+    """Returns (x, y, status, ret, steps, done, err) after the rollouts; inputs are not modified."""
+    N = len(x)
+    x, y = _c(x, np.int32).copy(), _c(y, np.int32).copy()
+    status = _c(status, np.int8).copy().reshape(N, k)
+    ret, steps = np.empty(N, np.float64), np.empty(N, np.int32)
+    done, err = np.empty(N, np.uint8), np.empty(N, np.uint8)
+    rc = lib().oracle_rock_rollout(c_int(n), c_int(k), c_int(int(stochastic)), c_double(p_move), c_int64(N), _p(x), _p(y),
+                                   _p(status), c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps),
+                                   c_double(gamma), _p(ret), _p(steps), _p(done), _p(err))
+    assert rc == 0
+    return x, y, status, ret, steps, done.astype(bool), err
+
+
+def tag_rollout(n_opp, move_prob, agent, opp, num_opp, seed, goff, ctr0, max_steps, gamma):
+    N = len(agent)
+    agent = _c(agent, np.int32).copy()
+    opp = _c(opp, np.int32).copy().reshape(N, n_opp)
+    num_opp = _c(num_opp, np.int32).copy()
+    ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
+    lib().oracle_tag_rollout(c_int(n_opp), c_double(move_prob), c_int64(N), _p(agent), _p(opp), _p(num_opp), c_uint64(seed),
+                             c_uint64(goff), c_uint32(ctr0), c_int(max_steps), c_double(gamma), _p(ret), _p(steps), _p(done))
+    return agent, opp, num_opp, ret, steps, done.astype(bool)
+
+
+def tiger_rollout(listen_prob, state, seed, goff, ctr0, max_steps, gamma):
+    N = len(state)
+    state = _c(state, np.int32).copy()
+    ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
+    lib().oracle_tiger_rollout(c_double(listen_prob), c_int64(N), _p(state), c_uint64(seed), c_uint64(goff), c_uint32(ctr0),
+                               c_int(max_steps), c_double(gamma), _p(ret), _p(steps), _p(done))
+    return state, ret, steps, done.astype(bool)
+
+
+def network_rollout(n, problem_type, machines, seed, goff, ctr0, max_steps, gamma, p=0.1, q=0.33, p_ob=0.95):
+    N = len(machines)
+    machines = _c(machines, np.int8).copy().reshape(N, n)
+    ret, steps = np.empty(N, np.float64), np.empty(N, np.int32)
+    rc = lib().oracle_network_rollout(c_int(n), c_int(problem_type), c_double(p), c_double(q), c_double(p_ob), c_int64(N),
+                                      _p(machines), c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps),
+                                      c_double(gamma), _p(ret), _p(steps))
+    assert rc == 0
+    return machines, ret, steps
+
+
+def battleship_rollout(xs, ys, occ, vis, remaining, seed, goff, ctr0, max_steps, gamma):
+    N = len(remaining)
+    vis = _c(vis, np.uint8).copy().reshape(N, xs, ys)
+    remaining = _c(remaining, np.int32).copy()
+    ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
+    lib().oracle_battleship_rollout(c_int(xs), c_int(ys), c_int64(N), _p(_c(occ, np.uint8)), _p(vis), _p(remaining),
+                                    c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps), c_double(gamma),
+                                    _p(ret), _p(steps), _p(done))
+    return vis.astype(bool), remaining, ret, steps, done.astype(bool)

@@ -1,0 +1,207 @@
+"""Record ROLLOUTS of the unmodified reference under its own ``_generate_legal`` + ``step``
+(the loops at rock.py:563-572 and tag.py:310-316) into tests/golden/rollouts.npz.
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (the GPU box has no /root/reference).
+Run:  python oracle/gen_rollouts.py         (deterministic, about 10 s)
+
+Episode e of an env is instance e of a batch: seed 0x5EED, reset at counter 1, then rollout
+step t at counter 2 + t.  The reference's draws are scripted from the Philox words of that
+(instance, counter):  np.random.choice(legal) <- (domain POLICY, slot 0); the step's own
+draws <- (domain STEP, its slots) in the order the reference consumes them.  Recorded per
+episode: the state after reset, the actions taken, the discounted return exactly as the
+Python loop accumulates it (``r += rw * discount; discount *= env._discount``), the number
+of steps, the final state and ``done``.  Nothing here knows the packed device layout.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import philox, ref_shim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SEED = 0x5EED
+RESET_CTR, FIRST_CTR = 1, 2
+
+
+def W(e, ctr, domain, n_slots):
+    return philox.draw_slots(SEED, np.array([e]), ctr, domain, n_slots)[0]
+
+
+def run(env, d, e, T, n_step_slots, feed_step, snapshot, gamma=None):
+    """One episode of the reference's loop.  feed_step(words, action) scripts the step's draws."""
+    gamma = env._discount if gamma is None else gamma
+    r, disc, t, acts, done = 0.0, 1.0, 0, [], False
+    while t < T and not done:
+        ctr = FIRST_CTR + t
+        legal = env._generate_legal()
+        d.clear()
+        d.feed([W(e, ctr, philox.DOMAIN_POLICY, 1)[0]])
+        a = int(np.random.choice(legal))                       # scripted: legal[floor(u * len)]
+        d.clear()
+        feed_step(W(e, ctr, philox.DOMAIN_STEP, n_step_slots), a)
+        ob, rw, done, info = env.step(a)
+        d.clear()
+        r += rw * disc
+        disc *= gamma
+        acts.append(a)
+        t += 1
+    return r, t, acts, bool(done), snapshot()
+
+
+def pad(rows, T):
+    out = -np.ones((len(rows), T), np.int32)
+    for i, row in enumerate(rows):
+        out[i, :len(row)] = row
+    return out
+
+
+def gen_rock(E, out, tag, n, k, stochastic, M, T):
+    d = ref_shim.draws()
+    env = E.StochasticRockEnv(n, k) if stochastic else E.RockEnv(n, k)
+    res = {key: [] for key in ("x0", "y0", "st0", "ret", "steps", "acts", "done", "x1", "y1", "st1")}
+
+    def snap():
+        return env.state.agent_pos.x, env.state.agent_pos.y, [r.status for r in env.state.rocks]
+    for e in range(M):
+        d.clear(); d.feed(W(e, RESET_CTR, philox.DOMAIN_RESET, k))
+        env.reset()
+        d.clear()
+        x0, y0, st0 = snap()
+
+        def feed_step(w, a):
+            d.feed([w[0], w[1]] if stochastic else [w[1]])      # rock.py:443 gate first, then the sensor (404)
+        r, t, acts, done, (x1, y1, st1) = run(env, d, e, T, 2, feed_step, snap)
+        for key, v in zip(res, (x0, y0, st0, r, t, acts, done, x1, y1, st1)):
+            res[key].append(v)
+    for key in res:
+        out[f"{tag}_{key}"] = pad(res[key], T) if key == "acts" else np.array(res[key])
+    out[f"{tag}_cfg"] = np.array([n, k, int(stochastic), T])
+    out[f"{tag}_discount"] = env._discount
+    print(tag, "mean steps", np.mean(res["steps"]), "done", int(np.sum(res["done"])), "mean ret", np.mean(res["ret"]))
+
+
+def gen_tag(E, out, tag, n_opp, M, T):
+    d = ref_shim.draws()
+    env = E.TagEnv(num_opponents=n_opp)
+    g = env.grid
+    res = {key: [] for key in ("agent0", "opp0", "ret", "steps", "acts", "done", "agent1", "opp1", "nopp1")}
+    orig_move = env.move_opponent
+    cur = {}
+
+    def move_opponent(opp):                                      # slots 2j, 2j+1 belong to opponent j (tag.py:201-207)
+        d.clear(); d.feed([cur["w"][2 * opp], cur["w"][2 * opp + 1]])
+        orig_move(opp)
+        d.clear()
+    env.move_opponent = move_opponent
+
+    def snap():
+        return g.get_index(env.state.agent_pos), [g.get_index(o) for o in env.state.opponent_pos], env.state.num_opp
+    for e in range(M):
+        d.clear(); d.feed(W(e, RESET_CTR, philox.DOMAIN_RESET, 1 + n_opp))
+        env.reset()
+        d.clear()
+        a0, o0, _ = snap()
+
+        def feed_step(w, a):
+            cur["w"] = w
+        r, t, acts, done, (a1, o1, n1) = run(env, d, e, T, 2 * n_opp, feed_step, snap, gamma=env._discount)
+        for key, v in zip(res, (a0, o0, r, t, acts, done, a1, o1, n1)):
+            res[key].append(v)
+    env.move_opponent = orig_move
+    for key in res:
+        out[f"{tag}_{key}"] = pad(res[key], T) if key == "acts" else np.array(res[key])
+    out[f"{tag}_cfg"] = np.array([n_opp, T])
+    out[f"{tag}_discount"] = env._discount
+    print(tag, "mean steps", np.mean(res["steps"]), "done", int(np.sum(res["done"])), "mean ret", np.mean(res["ret"]))
+
+
+def gen_tiger(E, out, M, T):
+    d = ref_shim.draws()
+    env = E.TigerEnv()
+    res = {key: [] for key in ("s0", "ret", "steps", "acts", "done", "s1")}
+    for e in range(M):
+        d.clear(); d.feed_gym(W(e, RESET_CTR, philox.DOMAIN_RESET, 1))
+        env.reset()
+        s0 = env.state
+
+        def feed_step(w, a):
+            d.feed_gym([w[0]]); d.feed([w[1]])                  # tiger.py:118-119 (gym's RNG), 143
+        r, t, acts, done, s1 = run(env, d, e, T, 2, feed_step, lambda: env.state)
+        for key, v in zip(res, (s0, r, t, acts, done, s1)):
+            res[key].append(v)
+    for key in res:
+        out[f"tiger_{key}"] = pad(res[key], T) if key == "acts" else np.array(res[key])
+    out["tiger_cfg"] = np.array([T])
+    out["tiger_discount"] = env._discount
+    print("tiger mean steps", np.mean(res["steps"]), "mean ret", np.mean(res["ret"]))
+
+
+def gen_network(E, out, M, T):
+    d = ref_shim.draws()
+    n = 10
+    env = E.NetworkEnv(n_machines=n, problem_type=3)
+    res = {key: [] for key in ("ret", "steps", "acts", "s1")}
+    for e in range(M):
+        env.reset()
+
+        def feed_step(w, a):                                    # one draw per UP machine in index order, then the action's
+            d.feed([w[m] for m in range(n) if env.state[m]] + ([w[n]] if a < 2 * n else []))
+        r, t, acts, done, s1 = run(env, d, e, T, n + 1, feed_step, lambda: int(sum(int(v) << m for m, v in enumerate(env.state))))
+        assert not done
+        for key, v in zip(res, (r, t, acts, s1)):
+            res[key].append(v)
+    for key in res:
+        out[f"network_{key}"] = pad(res[key], T) if key == "acts" else np.array(res[key])
+    out["network_cfg"] = np.array([n, 3, T])
+    out["network_discount"] = env._discount
+    print("network mean ret", np.mean(res["ret"]))
+
+
+def gen_battleship(E, out, tag, xs, ys, M, T):
+    d = ref_shim.draws()
+    env = E.BattleShipEnv(board_size=(xs, ys))
+    res = {key: [] for key in ("occ", "ret", "steps", "acts", "done", "vis1", "rem1")}
+
+    def board(attr):
+        return np.array([[getattr(env.grid.board[x, y], attr) for y in range(ys)] for x in range(xs)])
+    for e in range(M):
+        d.clear(); d.feed(W(e, RESET_CTR, philox.DOMAIN_RESET, 600))    # rejection loop: attempt a -> slots 2a, 2a+1
+        env.reset()
+        d.clear()
+        occ = board("occupied")
+        r, t, acts, done, (vis1, rem1) = run(env, d, e, T, 1, lambda w, a: None,
+                                             lambda: (board("visited"), env.state.total_remaining))
+        for key, v in zip(res, (occ, r, t, acts, done, vis1, rem1)):
+            res[key].append(v)
+    for key in res:
+        out[f"{tag}_{key}"] = pad(res[key], T) if key == "acts" else np.array(res[key])
+    out[f"{tag}_cfg"] = np.array([xs, ys, 3, T])
+    out[f"{tag}_discount"] = env._discount
+    print(tag, "mean steps", np.mean(res["steps"]), "done", int(np.sum(res["done"])), "mean ret", np.mean(res["ret"]))
+
+
+def main():
+    E = ref_shim.load_reference()
+    out = {"seed": SEED, "reset_ctr": RESET_CTR, "first_ctr": FIRST_CTR}
+    with ref_shim.scripted_numpy():
+        gen_rock(E, out, "rock_7_8", 7, 8, False, 96, 60)
+        gen_rock(E, out, "rock_11_11", 11, 11, False, 96, 80)
+        gen_rock(E, out, "rock_15_15", 15, 15, False, 64, 60)
+        gen_rock(E, out, "srock_7_8", 7, 8, True, 64, 60)
+        gen_tag(E, out, "tag_1opp", 1, 96, 90)
+        gen_tag(E, out, "tag_2opp", 2, 48, 90)
+        gen_tiger(E, out, 128, 30)
+        gen_network(E, out, 48, 40)
+        gen_battleship(E, out, "ship_5x5", 5, 5, 48, 30)
+        gen_battleship(E, out, "ship_10x10", 10, 10, 48, 110)
+    np.savez_compressed(os.path.join(GOLDEN, "rollouts.npz"), **out)
+    print("wrote rollouts.npz")
+
+
+if __name__ == "__main__":
+    main()

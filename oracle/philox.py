@@ -33,6 +33,7 @@ MASK = np.uint64(0xFFFFFFFF)
 
 DOMAIN_STEP = 0
 DOMAIN_RESET = 1
+DOMAIN_POLICY = 2
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

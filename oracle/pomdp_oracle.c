@@ -470,3 +470,154 @@ int oracle_network_step(int n, int problem_type, double p, double q, double p_ob
     }
     return 0;
 }
+
+/* ------------------------------------- legal actions + uniform-legal rollouts ------ */
+/* SURVEY.md §8f rank 1.  The loops at rock.py:563-572 and tag.py:310-316:
+ *     a = np.random.choice(env._generate_legal()); ob, rw, done, _ = env.step(a);
+ *     r += rw * discount; discount *= env._discount
+ * Rollout step t of env e uses the Philox words of step counter ctr0 + t: domain 2 (POLICY)
+ * slot 0 for `choice` (index = floor(u * len)), domain 0 (STEP) for the step's own slots. */
+static uint32_t draw_word1(uint64_t seed, uint64_t env, uint32_t step, uint32_t domain, int slot) {
+    const uint64_t group = env >> 2;
+    uint32_t c[4] = {(uint32_t)group, (uint32_t)(group >> 32), step, (domain << 24) | (uint32_t)slot};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return c[env & 3];
+}
+
+/* rock.py:273-291, list order preserved.  The dangling cell (grid id >= k), where the
+ * reference's _generate_legal itself raises IndexError, offers no SAMPLE. */
+int oracle_rock_legal(int n, int k, int x, int y, const int8_t* status, int32_t* legal) {
+    int8_t* grid = (int8_t*)malloc((size_t)n * n);
+    int32_t rock_pos[32], start[2];
+    int cnt = 0;
+    if (oracle_rock_grid(n, k, grid, rock_pos, start) < 0) { free(grid); return -1; }
+    legal[cnt++] = 1;
+    if (y + 1 < n) legal[cnt++] = 0;
+    if (y - 1 >= 0) legal[cnt++] = 2;
+    if (x - 1 >= 0) legal[cnt++] = 3;
+    {
+        const int rock = grid[x * n + y];
+        if (rock >= 0 && rock < k && status[rock] != 0) legal[cnt++] = 4;
+    }
+    for (int r = 0; r < k; ++r)
+        if (status[r] != 0) legal[cnt++] = grid[rock_pos[2 * r] * n + rock_pos[2 * r + 1]] + 1 + 4;
+    free(grid);
+    return cnt;
+}
+
+int oracle_rock_rollout(int n, int k, int stochastic, double p_move, int64_t N, int32_t* x, int32_t* y, int8_t* status,
+                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                        int32_t* steps, uint8_t* done, uint8_t* err) {
+    for (int64_t i = 0; i < N; ++i) {
+        double r = 0., disc = 1.;
+        int t = 0;
+        uint8_t fin = 0, e_acc = 0;
+        while (t < max_steps && !fin) {
+            int32_t legal[40], a, ob;
+            uint32_t dr[2];
+            double rw;
+            uint8_t e1;
+            const int cnt = oracle_rock_legal(n, k, x[i], y[i], status + i * k, legal);
+            if (cnt < 0) return -1;
+            a = legal[below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), cnt)];
+            dr[0] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 0);
+            dr[1] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 1);
+            if (oracle_rock_step(n, k, stochastic, p_move, 1, x + i, y + i, status + i * k, &a, dr, &ob, &rw, &fin, &e1))
+                return -1;
+            r += rw * disc;
+            disc *= gamma;
+            e_acc |= e1;
+            ++t;
+        }
+        ret[i] = r; steps[i] = t; done[i] = fin; err[i] = e_acc;
+    }
+    return 0;
+}
+
+void oracle_tag_rollout(int n_opp, double move_prob, int64_t N, int32_t* agent, int32_t* opp, int32_t* num_opp,
+                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                        int32_t* steps, uint8_t* done) {
+    for (int64_t i = 0; i < N; ++i) {
+        double r = 0., disc = 1.;
+        int t = 0;
+        uint8_t fin = 0;
+        while (t < max_steps && !fin) {
+            uint32_t dr[8];
+            int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 5), ob;   /* tag.py:228-229 */
+            double rw;
+            for (int s = 0; s < 2 * n_opp; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
+            oracle_tag_step(n_opp, move_prob, 1, agent + i, opp + i * n_opp, num_opp + i, &a, dr, &ob, &rw, &fin);
+            r += rw * disc;
+            disc *= gamma;
+            ++t;
+        }
+        ret[i] = r; steps[i] = t; done[i] = fin;
+    }
+}
+
+void oracle_tiger_rollout(double listen_prob, int64_t N, int32_t* state, uint64_t seed, uint64_t goff, uint32_t ctr0,
+                          int max_steps, double gamma, double* ret, int32_t* steps, uint8_t* done) {
+    for (int64_t i = 0; i < N; ++i) {
+        double r = 0., disc = 1.;
+        int t = 0;
+        uint8_t fin = 0;
+        while (t < max_steps && !fin) {
+            uint32_t dr[2];
+            int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 3), ob;   /* tiger.py:111-112 */
+            double rw;
+            dr[0] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 0);
+            dr[1] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 1);
+            oracle_tiger_step(listen_prob, 1, state + i, &a, dr, &ob, &rw, &fin);
+            r += rw * disc;
+            disc *= gamma;
+            ++t;
+        }
+        ret[i] = r; steps[i] = t; done[i] = fin;
+    }
+}
+
+int oracle_network_rollout(int n, int problem_type, double p, double q, double p_ob, int64_t N, int8_t* machines,
+                           uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                           int32_t* steps) {
+    for (int64_t i = 0; i < N; ++i) {
+        double r = 0., disc = 1.;
+        for (int t = 0; t < max_steps; ++t) {                                                            /* never done */
+            uint32_t dr[65];
+            int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 2 * n + 1), ob;   /* network.py:129-130 */
+            double rw;
+            for (int s = 0; s <= n; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
+            if (oracle_network_step(n, problem_type, p, q, p_ob, 1, machines + i * n, &a, dr, &ob, &rw)) return -1;
+            r += rw * disc;
+            disc *= gamma;
+        }
+        ret[i] = r; steps[i] = max_steps;
+    }
+    return 0;
+}
+
+/* battleship.py:157-165: legal = unvisited cells in increasing action order */
+void oracle_battleship_rollout(int xs, int ys, int64_t N, const uint8_t* occ, uint8_t* vis, int32_t* remaining,
+                               uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                               int32_t* steps, uint8_t* done) {
+    const int n_tiles = xs * ys;
+    for (int64_t i = 0; i < N; ++i) {
+        double r = 0., disc = 1.;
+        int t = 0;
+        uint8_t fin = 0;
+        while (t < max_steps && !fin) {
+            int32_t legal[128], a, ob;
+            int cnt = 0;
+            double rw;
+            for (int act = 0; act < n_tiles; ++act) {
+                const int x = act % xs, y = act / xs;
+                if (!vis[i * n_tiles + x * ys + y]) legal[cnt++] = act;
+            }
+            a = cnt ? legal[below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), cnt)] : 0;
+            oracle_battleship_step(xs, ys, 1, occ + i * n_tiles, vis + i * n_tiles, remaining + i, &a, &ob, &rw, &fin);
+            r += rw * disc;
+            disc *= gamma;
+            ++t;
+        }
+        ret[i] = r; steps[i] = t; done[i] = fin;
+    }
+}

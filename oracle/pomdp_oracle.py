@@ -591,3 +591,57 @@ def network_compute_prob(action, next_state, ob, p_ob=0.95):
     if action < 2 * n:
         return p_ob if next_state[action // 2] == ob else 1 - p_ob
     return 1. if ob == 2 else 0
+
+
+# ---------------------------------------------------------------------------------------
+# Legal actions and uniform-legal rollouts
+# ---------------------------------------------------------------------------------------
+def tag_generate_legal():
+    """tag.py:228-229"""
+    return list(range(5))
+
+
+def tiger_generate_legal():
+    """tiger.py:111-112"""
+    return list(range(3))
+
+
+def network_generate_legal(n_machines):
+    """network.py:129-130"""
+    return list(range(2 * n_machines + 1))
+
+
+def battleship_generate_legal(board):
+    """battleship.py:157-165: the unvisited cells, in increasing action order"""
+    legal = []
+    for action in range(board.x_size * board.y_size):
+        x, y = grid_get_coord(board.x_size, action)
+        if not board.visited[x][y]:
+            legal.append(action)
+    return legal
+
+
+def rollout(legal, step, is_done, max_steps, gamma, draws):
+    """The loop at rock.py:563-572 / tag.py:310-316 for ONE env instance::
+
+        while not done and t < max_steps:
+            a = np.random.choice(env._generate_legal())
+            ob, rw, done, _ = env.step(a)
+            r += rw * discount;  discount *= env._discount
+
+    ``legal()`` -> list, ``step(a, draw)`` -> (reward, done) (mutating the caller's state),
+    ``is_done()`` -> bool; ``draws(t)`` -> (policy_word, draw) for rollout step t, i.e. the
+    words of step counter c + t: domain POLICY slot 0 for ``choice`` (index = floor(u * len)),
+    domain STEP for the step's own slots.  Returns (ret, steps, actions taken).
+    """
+    ret, disc, t, actions = 0.0, 1.0, 0, []
+    while t < max_steps and not is_done():
+        w, draw = draws(t)
+        lst = legal()
+        a = lst[rand_below(w, len(lst))]
+        rw, _ = step(a, draw)
+        ret += rw * disc
+        disc *= gamma
+        actions.append(a)
+        t += 1
+    return ret, t, actions

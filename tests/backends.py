@@ -18,11 +18,11 @@ GOLDEN_SEED = 0x5EED
 
 def build_hostsim():
     src = os.path.join(HOSTSIM_DIR, "pomdp_hostsim.cpp")
-    deps = [src, os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_core.h"),
+    deps = [src, os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_core.h"), os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_envs.h"),
             os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_host.h"), os.path.join(ROOT, "include", "pomdp_b200.h")]
     if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(d) <= os.path.getmtime(HOSTSIM_SO) for d in deps):
         return HOSTSIM_SO
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", HOSTSIM_SO, src],
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", HOSTSIM_SO, src],
                    check=True)
     return HOSTSIM_SO
 

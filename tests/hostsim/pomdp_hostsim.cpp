@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "../../gym_pomdp_b200/csrc/pomdp_core.h"
+#include "../../gym_pomdp_b200/csrc/pomdp_envs.h"
 #include "../../gym_pomdp_b200/csrc/pomdp_host.h"
 
 using namespace pomdp;
@@ -39,6 +40,39 @@ int rock_step_host(const RockDev& d, const void* table, const int32_t* state, co
         if (d.stochastic) rock_step<S, true>(d, lut, rtab, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
         else rock_step<S, false>(d, lut, rtab, load_state<S>(state, i), action[i], wg, ws, s2, obs[i], rw[i], fl[i]);
         store_state(next, i, s2);
+    }
+    return 0;
+}
+}  // namespace
+
+// ---- uniform-legal policy and fused rollouts: the SAME adapters (pomdp_envs.h) the kernels instantiate
+namespace {
+template <typename S> S load_any(const int32_t* base, int64_t i) { return load_state<S>(base, i); }
+
+template <class Env>
+int policy_host(const typename Env::Params& d, const void* table, const int32_t* state, int32_t* action, int64_t n,
+                int64_t goff, uint64_t seed, uint32_t step, const char* what) {
+    int rc = host::check_policy(state, action, n, goff, what);
+    if (rc) return rc;
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i)
+        action[i] = Env::policy(d, (const unsigned char*)table, load_any<typename Env::State>(state, i),
+                                draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0));
+    return 0;
+}
+template <class Env>
+int rollout_host(const typename Env::Params& d, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+                 int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
+                 double gamma, const char* what) {
+    int rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what);
+    if (rc) return rc;
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        typename Env::State s = load_any<typename Env::State>(state, i);
+        RolloutAcc acc;
+        rollout1<Env>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma, acc);
+        if (final_state) store_state(final_state, i, s);
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
     return 0;
 }
@@ -253,6 +287,121 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
         for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
         if (obs) obs[i] = 0;
         if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
+    }
+    return 0;
+}
+
+#define HOSTSIM_ROCK_DISPATCH(FN, ...)                                                        \
+    do {                                                                                      \
+        if (!table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");                 \
+        if (host::rock_words(q) == 1) {                                                       \
+            if (d.stochastic) return FN<RockEnvT<uint32_t, true>>(__VA_ARGS__);               \
+            return FN<RockEnvT<uint32_t, false>>(__VA_ARGS__);                                \
+        }                                                                                     \
+        if (d.stochastic) return FN<RockEnvT<uint64_t, true>>(__VA_ARGS__);                   \
+        return FN<RockEnvT<uint64_t, false>>(__VA_ARGS__);                                    \
+    } while (0)
+
+int pomdp_rock_policy(const PomdpRockParams* q, const void* table, const int32_t* state, int32_t* action, int64_t n,
+                      int64_t goff, uint64_t seed, uint32_t step, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    HOSTSIM_ROCK_DISPATCH(policy_host, d, table, state, action, n, goff, seed, step, "pomdp_rock_policy");
+}
+int pomdp_rock_rollout(const PomdpRockParams* q, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+                       int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                       int32_t max_steps, double gamma, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    HOSTSIM_ROCK_DISPATCH(rollout_host, d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+                          "pomdp_rock_rollout");
+}
+int pomdp_tag_policy(const PomdpTagParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff, uint64_t seed,
+                     uint32_t step, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return policy_host<TagEnvT<1>>(d, nullptr, state, action, n, goff, seed, step, "pomdp_tag_policy");
+}
+int pomdp_tag_rollout(const PomdpTagParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
+                      int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps, double gamma,
+                      void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return rollout_host<TagEnvT<4>>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+                                    "pomdp_tag_rollout");
+}
+int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                       uint64_t seed, uint32_t step, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return policy_host<TigerEnvP>(d, nullptr, state, action, n, goff, seed, step, "pomdp_tiger_policy");
+}
+int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
+                        int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
+                        double gamma, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return rollout_host<TigerEnvP>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+                                   "pomdp_tiger_rollout");
+}
+int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                         uint64_t seed, uint32_t step, void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return policy_host<NetworkEnvP>(d, nullptr, state, action, n, goff, seed, step, "pomdp_network_policy");
+}
+int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, int32_t* final_state, double* ret,
+                          int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                          int32_t max_steps, double gamma, void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return rollout_host<NetworkEnvP>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+                                     "pomdp_network_rollout");
+}
+int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                            uint64_t seed, uint32_t step, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, action, n, goff, "pomdp_battleship_policy"))) return rc;
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i)
+        action[i] = battleship_policy(d, (const uint32_t*)state + i * SHIP_WORDS,
+                                      draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0));
+    return 0;
+}
+int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, int32_t* final_state, double* ret,
+                             int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                             int32_t max_steps, double gamma, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, "pomdp_battleship_rollout")))
+        return rc;
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t w[SHIP_WORDS], w2[SHIP_WORDS];
+        memcpy(w, state + i * SHIP_WORDS, sizeof(w));
+        RolloutAcc acc;
+        acc.init((w[3] >> 31) != 0);
+        for (int32_t t = 0; t < max_steps && !(w[3] >> 31); ++t) {
+            const int32_t a = battleship_policy(d, w, draw_word(key, (uint64_t)(goff + i), step + (uint32_t)t, DOMAIN_POLICY, 0));
+            int32_t ob, fl;
+            float rw;
+            battleship_step(d, w, a, w2, ob, rw, fl);
+            memcpy(w, w2, sizeof(w));
+            acc.add((double)rw, gamma, fl);
+        }
+        if (final_state) memcpy(final_state + i * SHIP_WORDS, w, sizeof(w));
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
     return 0;
 }
