@@ -67,11 +67,15 @@ _PROTOTYPES = {
     "pomdp_rock_build_table": (c_int32, [POINTER(RockParams), c_void_p]),
     "pomdp_rock_step": (c_int32, [POINTER(RockParams), _P] + _STEP_TAIL),
     "pomdp_rock_reset": (c_int32, [POINTER(RockParams), _P] + _RESET_TAIL),
-    "pomdp_tag_step": (c_int32, [POINTER(TagParams)] + _STEP_TAIL),
+    "pomdp_tag_table_bytes": (c_int64, []),
+    "pomdp_tag_build_table": (c_int32, [c_void_p]),
+    "pomdp_tag_step": (c_int32, [POINTER(TagParams), _P] + _STEP_TAIL),
     "pomdp_tag_reset": (c_int32, [POINTER(TagParams)] + _RESET_TAIL),
     "pomdp_battleship_step": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_battleship_reset": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64, c_uint64,
                                          c_uint32, c_void_p]),
+    "pomdp_battleship_reset_warpscan": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64, c_uint64,
+                                                  c_uint32, c_void_p]),
     "pomdp_battleship_reset_rejection": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64,
                                                    c_uint64, c_uint32, c_void_p]),
     "pomdp_tiger_step": (c_int32, [POINTER(TigerParams)] + _STEP_TAIL),
@@ -80,8 +84,8 @@ _PROTOTYPES = {
     "pomdp_network_reset": (c_int32, [POINTER(NetworkParams), _P, _P, _P, c_int64, c_void_p]),
     "pomdp_rock_policy": (c_int32, [POINTER(RockParams), _P] + _POLICY_TAIL),
     "pomdp_rock_rollout": (c_int32, [POINTER(RockParams), _P] + _ROLLOUT_TAIL),
-    "pomdp_tag_policy": (c_int32, [POINTER(TagParams)] + _POLICY_TAIL),
-    "pomdp_tag_rollout": (c_int32, [POINTER(TagParams)] + _ROLLOUT_TAIL),
+    "pomdp_tag_policy": (c_int32, [POINTER(TagParams), _P] + _POLICY_TAIL),
+    "pomdp_tag_rollout": (c_int32, [POINTER(TagParams), _P] + _ROLLOUT_TAIL),
     "pomdp_battleship_policy": (c_int32, [POINTER(BattleshipParams)] + _POLICY_TAIL),
     "pomdp_battleship_rollout": (c_int32, [POINTER(BattleshipParams)] + _ROLLOUT_TAIL),
     "pomdp_tiger_policy": (c_int32, [POINTER(TigerParams)] + _POLICY_TAIL),

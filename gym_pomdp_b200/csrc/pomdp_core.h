@@ -357,10 +357,89 @@ POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
     return cnt;
 }
 
+// Static maps of the fixed 29-cell board, derived from the functions above on the host (pomdp_host.h:
+// make_tag_table) and staged into shared memory by ONE TMA bulk copy per CTA, like Rock's.
+//   pair[agent * 32 + opp]  bits 5c..5c+4 (c = 0..3): the opponent's cell if element c of the reference's move
+//                           multiset (tag.py:260-280) is drawn -- the move's target, or `opp` itself when the target
+//                           is off the board (tag.py:206-207);  bits 20-22: the multiset's length
+//   mv[agent]               bits 5a..5a+4 (a = 0..3): the agent's cell after move a (tag.py:133-137)
+// 32 x 32 pair entries so that a corrupt 5-bit cell id reads a zero entry instead of faulting.
+struct TagTables {
+    uint32_t pair[32 * 32];
+    uint32_t mv[32];
+};
+static_assert(sizeof(TagTables) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+POMDP_HD uint32_t tag_pair_entry(int agent, int opp) {
+    int ax, ay, ox, oy;
+    tag_get_coord((uint32_t)agent, ax, ay);
+    tag_get_coord((uint32_t)opp, ox, oy);
+    uint32_t list;
+    const int cnt = tag_admissible(ax, ay, ox, oy, list);
+    uint32_t e = (uint32_t)cnt << 20;
+    for (int c = 0; c < 4; ++c) {
+        int cell = opp;
+        if (c < cnt) {
+            const int m = (int)((list >> (2 * c)) & 3u);
+            const int nx = ox + move_dx(m), ny = oy + move_dy(m);
+            if (tag_is_inside(nx, ny)) cell = tag_get_index(nx, ny);
+        }
+        e |= (uint32_t)cell << (5 * c);
+    }
+    return e;
+}
+POMDP_HD uint32_t tag_mv_entry(int agent) {
+    int ax, ay;
+    tag_get_coord((uint32_t)agent, ax, ay);
+    uint32_t e = 0;
+    for (int a = 0; a < 4; ++a) {
+        const int nx = ax + move_dx(a), ny = ay + move_dy(a);
+        e |= (uint32_t)(tag_is_inside(nx, ny) ? tag_get_index(nx, ny) : agent) << (5 * a);
+    }
+    return e;
+}
+POMDP_HD void tag_build_tables(TagTables* T) {
+    for (int i = 0; i < 32 * 32; ++i) {
+        const int agent = i >> 5, opp = i & 31;
+        T->pair[i] = (agent < TAG_CELLS && opp < TAG_CELLS) ? tag_pair_entry(agent, opp) : 0u;
+    }
+    for (int i = 0; i < 32; ++i) T->mv[i] = i < TAG_CELLS ? tag_mv_entry(i) : 0u;
+}
+
+// The stock Tag-v0 (one opponent) without a branch: both the move and the TAG outcome are formed from two table
+// words and the result is selected.  Same semantics as tag_step below (which handles 1..4 opponents).
+//   w_move = draw slot 0 (np.random.binomial(1, move_prob), tag.py:204), w_pick = slot 1 (np.random.choice, tag.py:205)
+POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w_move,
+                            uint32_t w_pick, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    const uint32_t agent = s & 31u, opp = (s >> 5) & 31u;
+    const int nopp = tag_num_opp(s);
+    const uint32_t e = T->pair[agent * 32u + opp];
+    const uint32_t mvw = T->mv[agent];
+    const bool is_tag = a == 4;
+    const bool hit = opp == agent;                                                        // tag.py:122-126
+    const bool moves = is_tag && !hit && nopp > 0 && bern(w_move, p.move_T);              // tag.py:128, 204
+    const uint32_t opp_t = (e >> (5u * rand_below(w_pick, e >> 20))) & 31u;               // tag.py:205-207
+    const uint32_t agent2 = is_tag ? agent : ((mvw >> (5u * ((uint32_t)a & 3u))) & 31u);  // tag.py:133-137
+    const uint32_t opp2 = moves ? opp_t : opp;
+    const int nopp2 = nopp - ((is_tag && hit) ? 1 : 0);
+    const bool done = nopp2 == 0;                                                         // tag.py:142
+    uint32_t ns = tag_set_num_opp((s & ~1023u) | agent2 | (opp2 << 5), nopp2) | (done ? TAG_DONE : 0u);
+    float reward = is_tag ? (hit ? 10.f : -10.f) : -1.f;
+    int32_t o = (!is_tag && agent2 == opp2) ? TAG_CELLS : (int32_t)agent2;                // tag.py:219-226
+    int32_t f = done ? (int32_t)FLAG_DONE : 0;
+    // the reference's asserts (tag.py:109-110, 116-117): flagged, state untouched, obs = reward = 0
+    const int32_t err = (s & TAG_DONE) ? (int32_t)(FLAG_DONE | FLAG_STEPPED_DONE)
+                        : ((uint32_t)a >= 5u) ? (int32_t)FLAG_BAD_ACTION
+                        : (agent >= (uint32_t)TAG_CELLS || opp >= (uint32_t)TAG_CELLS) ? (int32_t)FLAG_BAD_STATE : 0;
+    s2 = err ? s : ns;
+    ob = err ? 0 : o;
+    rw = err ? 0.f : reward;
+    fl = err ? err : f;
+}
+
 // tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).
 // Draw slots per opponent j: 2j = np.random.binomial(1, move_prob) (tag.py:204), 2j+1 = np.random.choice (tag.py:205).
 template <class D>
-POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, const D& draw,
+POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, const D& draw,
                        uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     s2 = s; ob = 0; rw = 0.f; fl = 0;
     if (s & TAG_DONE) { fl = FLAG_DONE | FLAG_STEPPED_DONE; return; }             // tag.py:110
@@ -369,8 +448,6 @@ POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, const D& draw,
     bool bad = agent >= (uint32_t)TAG_CELLS;
     for (int j = 0; j < p.n_opp; ++j) bad = bad || ((s >> (5 + 5 * j)) & 31u) >= (uint32_t)TAG_CELLS;
     if (bad) { fl = FLAG_BAD_STATE; return; }                                     // tag.py:116-117
-    int ax, ay;
-    tag_get_coord(agent, ax, ay);
     int nopp = tag_num_opp(s);
     float reward;
     if (a == 4) {                                                                 // tag.py:119-131
@@ -386,27 +463,18 @@ POMDP_HD void tag_step(const TagDev& p, uint32_t s, int32_t a, const D& draw,
                 tagged = true;
                 --nopp;
             } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
-                const uint32_t w_move = draw(2 * j), w_pick = draw(2 * j + 1);
-                int ox, oy;
-                tag_get_coord(o, ox, oy);
-                uint32_t list;
-                const int cnt = tag_admissible(ax, ay, ox, oy, list);
-                if (bern(w_move, p.move_T)) {                                     // tag.py:204
-                    const int m = (int)((list >> (2 * rand_below(w_pick, (uint32_t)cnt))) & 3u);  // tag.py:205
-                    const int nx = ox + move_dx(m), ny = oy + move_dy(m);
-                    if (tag_is_inside(nx, ny))                                    // tag.py:206-207
-                        s2 = (s2 & ~(31u << sh)) | ((uint32_t)tag_get_index(nx, ny) << sh);
+                const uint32_t e = T->pair[agent * 32u + o];
+                if (bern(draw(2 * j), p.move_T)) {                                // tag.py:204
+                    const uint32_t pick = rand_below(draw(2 * j + 1), e >> 20);   // tag.py:205
+                    s2 = (s2 & ~(31u << sh)) | (((e >> (5u * pick)) & 31u) << sh);  // tag.py:206-207
                 }
             }
         }
         if (!tagged) reward = -10.f;
     } else {                                                                      // tag.py:133-137
         reward = -1.f;
-        const int nx = ax + move_dx(a), ny = ay + move_dy(a);
-        if (tag_is_inside(nx, ny)) {
-            agent = (uint32_t)tag_get_index(nx, ny);
-            s2 = (s2 & ~31u) | agent;
-        }
+        agent = (T->mv[agent] >> (5 * a)) & 31u;
+        s2 = (s2 & ~31u) | agent;
     }
     ob = (int32_t)agent;                                                          // tag.py:219-226
     if (a < 4)
@@ -544,10 +612,14 @@ POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int
 // ====================================================================== BattleShip ===
 constexpr int SHIP_WORDS = 8;
 constexpr int SHIP_MAX_CELLS = 120;
+constexpr int SHIP_MAX_SHIPS = 8;
 struct ShipDev {
     int32_t X, Y, max_len, n_tiles;
     uint64_t col0_lo, col0_hi;   // cells with x == 0
     uint64_t colL_lo, colL_hi;   // cells with x == X-1
+    // [dir][ship index] start cells from which the reference's look-ahead stays on the board: the cell
+    // length + 1 steps ahead must be inside (battleship.py:199-201), ship index 0 = the longest ship
+    uint64_t inside_lo[4][SHIP_MAX_SHIPS], inside_hi[4][SHIP_MAX_SHIPS];
 };
 struct ShipState {
     u128 occ, vis;     // bit c = cell c = X*y + x
@@ -628,6 +700,62 @@ POMDP_HD bool ship_candidate_ok(const ShipDev& p, u128 blocked, int pos, int dir
     return ok;
 }
 
+// ---- bitboard placement: every (pos, dir) candidate of one ship at once ------------------------------------------
+// valid[d] bit pos  <=>  collision() is False for Ship(pos, direction d, length)  (battleship.py:195-211): the
+// look-ahead cell is on the board and none of the length + 1 cells pos + i*dir is blocked.
+POMDP_HD void ship_valid_starts(const ShipDev& p, u128 blocked, int ship_index, int length, u128 valid[4]) {
+    const u128 board = ((u128)1 << p.n_tiles) - 1;
+    const u128 open_ = ~blocked & board;
+    POMDP_UNROLL
+    for (int d = 0; d < 4; ++d) {
+        const int st = move_dy(d) * p.X + move_dx(d);          // +X, +1, -X, -1
+        u128 v = (u128)p.inside_lo[d][ship_index] | ((u128)p.inside_hi[d][ship_index] << 64);
+        for (int i = 0; i <= length; ++i) v &= st > 0 ? (open_ >> (i * st)) : (open_ << (i * -st));
+        valid[d] = v;
+    }
+}
+POMDP_HD uint32_t u128_word(u128 v, int w) { return (uint32_t)(v >> (32 * w)); }
+POMDP_HD int ship_count(const u128 valid[4]) {
+    int total = 0;
+    POMDP_UNROLL
+    for (int d = 0; d < 4; ++d)
+        for (int w = 0; w < 4; ++w) total += popc32(u128_word(valid[d], w));
+    return total;
+}
+// the k-th accepted candidate in increasing c = 4 * pos + dir (k < ship_count): word, then a 5-step binary search on
+// the bit position with masked popcounts, then the direction
+POMDP_HD int ship_pick(const u128 valid[4], int k) {
+    uint32_t m[4] = {0, 0, 0, 0};
+    int base = 0;
+    bool found = false;
+    POMDP_UNROLL
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t a0 = u128_word(valid[0], w), a1 = u128_word(valid[1], w), a2 = u128_word(valid[2], w),
+                       a3 = u128_word(valid[3], w);
+        const int c = popc32(a0) + popc32(a1) + popc32(a2) + popc32(a3);
+        if (!found) {
+            if (k < c) { m[0] = a0; m[1] = a1; m[2] = a2; m[3] = a3; base = 32 * w; found = true; }
+            else k -= c;
+        }
+    }
+    int lo = 0;
+    POMDP_UNROLL
+    for (int half = 16; half >= 1; half >>= 1) {
+        const uint32_t mask = ((1u << half) - 1u) << lo;
+        const int c = popc32(m[0] & mask) + popc32(m[1] & mask) + popc32(m[2] & mask) + popc32(m[3] & mask);
+        if (k >= c) { k -= c; lo += half; }
+    }
+    int dir = 0;
+    bool got = false;
+    POMDP_UNROLL
+    for (int d = 0; d < 4; ++d)
+        if (!got && ((m[d] >> lo) & 1u)) {
+            if (k == 0) { dir = d; got = true; }
+            else --k;
+        }
+    return 4 * (base + lo) + dir;
+}
+
 // battleship.py:182-193
 POMDP_HD void ship_mark(const ShipDev& p, ShipState& st, int pos, int dir, int length) {
     const int stride = move_dy(dir) * p.X + move_dx(dir);
@@ -653,6 +781,23 @@ POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed
             const int pos = (int)rand_below(w_pos, (uint32_t)p.n_tiles), dir = (int)rand_below(w_dir, 4);
             if (ship_candidate_ok(p, blocked, pos, dir, length)) { ship_mark(p, st, pos, dir, length); break; }
         }
+    }
+    return true;
+}
+
+// battleship.py:167-180 in fixed time: ship s takes the k-th of its accepted (pos, dir) candidates, k = floor(u * count),
+// u = draw slot s -- the distribution of the reference's rejection loop (uniform over the accepted set).  Returns
+// false when some ship has no placement (the reference would loop forever).
+POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step, ShipState& st) {
+    st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+    int ship = 0;
+    for (int length = p.max_len; length >= 2; --length, ++ship) {
+        u128 valid[4];
+        ship_valid_starts(p, ship_blocked(p, st.occ), ship, length, valid);
+        const int total = ship_count(valid);
+        if (total == 0) return false;
+        const int c = ship_pick(valid, (int)rand_below(draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total));
+        ship_mark(p, st, c >> 2, c & 3, length);
     }
     return true;
 }

@@ -16,7 +16,7 @@ template <typename S, bool STOCH>
 struct RockEnvT {
     typedef RockDev Params;
     typedef S State;
-    static constexpr bool kTable = true;
+    static constexpr bool kTable = true;             // table built on the host, staged per CTA by one TMA bulk copy
     static POMDP_HD int32_t policy(const Params& p, const unsigned char* tbl, S s, uint32_t w) {   // rock.py:273-291
         return rock_policy<S>(p, reinterpret_cast<const RockTableHdr*>(tbl),
                               reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET), s, w);
@@ -74,30 +74,39 @@ template <int NOPP>
 struct TagEnvT {
     typedef TagDev Params;
     typedef uint32_t State;
-    static constexpr bool kTable = false;
+    static constexpr bool kTable = true;             // TagTables: built on the host, staged per CTA by one TMA bulk copy
     static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tag.py:228-229
         return (int32_t)rand_below(w, 5u);
     }
     static POMDP_HD bool is_done(State s) { return (s & TAG_DONE) != 0; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }
-    static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+    static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
+        const TagTables* T = reinterpret_cast<const TagTables*>(tbl);
+        if (NOPP == 1) {
+            const U4 qm = draw_quad(seed, group, ctr, DOMAIN_STEP, 0), qp = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
+            tag_step_1opp(p, T, s[0], a[0], qm.x, qp.x, s2[0], ob[0], rw[0], fl[0]);
+            tag_step_1opp(p, T, s[1], a[1], qm.y, qp.y, s2[1], ob[1], rw[1], fl[1]);
+            tag_step_1opp(p, T, s[2], a[2], qm.z, qp.z, s2[2], ob[2], rw[2], fl[2]);
+            tag_step_1opp(p, T, s[3], a[3], qm.w, qp.w, s2[3], ob[3], rw[3], fl[3]);
+            return;
+        }
         WordDraw<2 * NOPP> d[4];
         quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
-    POMDP_UNROLL
-        for (int j = 0; j < 4; ++j) tag_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
+        POMDP_UNROLL
+        for (int j = 0; j < 4; ++j) tag_step(p, T, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }
-    static POMDP_HD void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
+    static POMDP_HD void step1(const Params& p, const unsigned char* tbl, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
-        tag_step(p, s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
+        tag_step(p, reinterpret_cast<const TagTables*>(tbl), s, a, LazyDraw{&seed, env, ctr, DOMAIN_STEP}, s2, ob, rw, fl);
     }
     static POMDP_HD void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
                                                   State s[4], int32_t ob[4]) {
         WordDraw<1 + NOPP> d[4];
         quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
-    POMDP_UNROLL
+        POMDP_UNROLL
         for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
     }
     static POMDP_HD void reset1(const Params& p, const PhiloxKey& seed, uint64_t env, uint32_t ctr, State& s,

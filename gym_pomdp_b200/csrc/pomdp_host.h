@@ -241,6 +241,18 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
     for (int y = 0; y < d->Y; ++y) { c0 |= (u128)1 << (y * d->X); cL |= (u128)1 << (y * d->X + d->X - 1); }
     d->col0_lo = (uint64_t)c0; d->col0_hi = (uint64_t)(c0 >> 64);
     d->colL_lo = (uint64_t)cL; d->colL_hi = (uint64_t)(cL >> 64);
+    if (q->max_len - 1 <= SHIP_MAX_SHIPS) {
+        int ship = 0;
+        for (int length = q->max_len; length >= 2; --length, ++ship)
+            for (int dir = 0; dir < 4; ++dir) {
+                u128 m = 0;
+                for (int y = 0; y < d->Y; ++y)
+                    for (int x = 0; x < d->X; ++x)
+                        if (grid_is_inside(d->X, d->Y, x + (length + 1) * move_dx(dir), y + (length + 1) * move_dy(dir)))
+                            m |= (u128)1 << (y * d->X + x);
+                d->inside_lo[dir][ship] = (uint64_t)m; d->inside_hi[dir][ship] = (uint64_t)(m >> 64);
+            }
+    }
     return 0;
 }
 

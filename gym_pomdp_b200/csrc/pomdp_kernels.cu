@@ -156,6 +156,7 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
         }
         __syncthreads();   // barrier object initialised before anyone polls it
     }
+
     pdl_wait();                // everything above overlapped the previous kernel's tail; state/action may be its outputs
     pdl_launch_dependents();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -564,6 +565,34 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
     }
 }
 
+// One THREAD per env: the 4 * n_tiles candidates of a ship are four 128-bit masks built with ~length shifts each
+// (pomdp_core.h: ship_valid_starts), so a placement costs ~1e3 instructions instead of the warp scan's ~5e4.
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_reset_bitboard_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
+                                       int32_t* __restrict__ obs, int32_t* __restrict__ flags,
+                                       const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
+                                       const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
+    const bool vec = (reinterpret_cast<uintptr_t>(state) & 15) == 0;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        if (mask && !mask[i]) continue;
+        ShipState st;
+        const bool ok = battleship_reset_bitboard(p, seed, goff + (uint64_t)i, step_ctr, st);
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        if (vec) {
+            uint4* dst = reinterpret_cast<uint4*>(state + i * SHIP_WORDS);
+            __stcs(dst, make_uint4(w8[0], w8[1], w8[2], w8[3]));
+            __stcs(dst + 1, make_uint4(w8[4], w8[5], w8[6], w8[7]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+        }
+        if (obs) obs[i] = 0;                                               // battleship.py:137
+        if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
+    }
+}
+
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_battleship_reset_rejection_kernel(const __grid_constant__ ShipDev p, int32_t* __restrict__ state,
                                         int32_t* __restrict__ obs, int32_t* __restrict__ flags,
@@ -871,16 +900,23 @@ int pomdp_rock_reset(const PomdpRockParams* q, const void* d_table, int32_t* sta
 }
 
 // ---- Tag
-int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
-                   int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
-                   uint32_t step_ctr, void* stream) {
+int64_t pomdp_tag_table_bytes(void) { return (int64_t)sizeof(TagTables); }
+int pomdp_tag_build_table(void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "tag: host_table is NULL");
+    tag_build_tables((TagTables*)host_table);
+    return 0;
+}
+int pomdp_tag_step(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                   int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
+                   uint64_t seed, uint32_t step_ctr, void* stream) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
+    const uint32_t tb = (uint32_t)sizeof(TagTables);
     if (d.n_opp == 1)
-        return launch_step<TagEnvT<1>>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed,
+        return launch_step<TagEnvT<1>>(d, d_table, tb, tb, state, action, next_state, obs, reward, flags, n, goff, seed,
                                        step_ctr, stream, "pomdp_tag_step");
-    return launch_step<TagEnvT<4>>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<TagEnvT<4>>(d, d_table, tb, tb, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                    stream, "pomdp_tag_step");
 }
 int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
@@ -956,13 +992,26 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
     ShipDev d;
     int rc = host::make_ship(q, &d);
     if (rc) return rc;
-    if (q->max_len - 1 > 8) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
     if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset: bad n or NULL state");
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_reset_bitboard_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
+    return finish("pomdp_battleship_reset");
+}
+int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                                    const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                                    void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
+    if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset_warpscan: bad n or NULL state");
     if (n == 0) return 0;
     auto k = pomdp_battleship_reset_scan_kernel;
     const int grid = grid_for(k, n * 32);
     k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
-    return finish("pomdp_battleship_reset");
+    return finish("pomdp_battleship_reset_warpscan");
 }
 int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
                                      const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
@@ -1008,23 +1057,25 @@ int pomdp_rock_rollout(const PomdpRockParams* q, const void* d_table, const int3
 }
 #undef POMDP_ROCK_DISPATCH
 
-int pomdp_tag_policy(const PomdpTagParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
-                     uint64_t seed, uint32_t step_ctr, void* stream) {
+int pomdp_tag_policy(const PomdpTagParams* q, const void* d_table, const int32_t* state, int32_t* action, int64_t n,
+                     int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    return launch_policy<TagEnvT<1>>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
+    const uint32_t tb = (uint32_t)sizeof(TagTables);
+    return launch_policy<TagEnvT<1>>(d, d_table, tb, tb, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
 }
-int pomdp_tag_rollout(const PomdpTagParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
-                      int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps,
-                      double discount, void* stream) {
+int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_t* state, int32_t* final_state, double* ret,
+                      int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                      int32_t max_steps, double discount, void* stream) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
+    const uint32_t tb = (uint32_t)sizeof(TagTables);
     if (d.n_opp == 1)
-        return launch_rollout<TagEnvT<1>>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+        return launch_rollout<TagEnvT<1>>(d, d_table, tb, tb, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                           max_steps, discount, stream, "pomdp_tag_rollout");
-    return launch_rollout<TagEnvT<4>>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+    return launch_rollout<TagEnvT<4>>(d, d_table, tb, tb, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                       max_steps, discount, stream, "pomdp_tag_rollout");
 }
 int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,

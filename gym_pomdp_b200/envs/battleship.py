@@ -44,8 +44,9 @@ class BattleShipEnv(BatchedPomdpEnv):
         self._discount = 1.
         self.total_remaining = max_len - 1      # battleship.py:74 (an env attribute the reference only asserts on)
         self.max_len = max_len + 1              # battleship.py:75
-        if reset_mode not in ("scan", "rejection"):
-            raise ValueError("reset_mode must be 'scan' (warp per env) or 'rejection' (the reference's loop)")
+        if reset_mode not in ("scan", "warpscan", "rejection"):
+            raise ValueError("reset_mode must be 'scan' (bitboard, thread per env), 'warpscan' (warp per env; same boards) "
+                             "or 'rejection' (the reference's loop)")
         self.reset_mode = reset_mode
         self.reset_flags = None
         self.t = 0
@@ -58,7 +59,8 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _c_reset(self, state, obs, mask, n, ctr):
         L = _lib.lib()
-        fn = L.pomdp_battleship_reset if self.reset_mode == "scan" else L.pomdp_battleship_reset_rejection
+        fn = {"scan": L.pomdp_battleship_reset, "warpscan": L.pomdp_battleship_reset_warpscan,
+              "rejection": L.pomdp_battleship_reset_rejection}[self.reset_mode]
         self.reset_flags = torch.zeros(n, dtype=torch.int32, device=self.device)
         _lib.check(fn(ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(obs), _lib.ptr(self.reset_flags),
                       _lib.ptr(mask), n, self.global_offset, self._seed, ctr, self._stream()), "pomdp_battleship_reset")

@@ -5,6 +5,7 @@ cell, 5 bits per opponent cell from bit 5, bits 25-30 ``num_opp`` (signed), bit 
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -48,10 +49,17 @@ class TagEnv(BatchedPomdpEnv):
         self.time = 0
         if not 1 <= num_opponents <= 4:
             raise ValueError("num_opponents must be in 1..4")
+        L = _lib.lib()
+        host = np.zeros(L.pomdp_tag_table_bytes(), dtype=np.uint8)
+        _lib.check(L.pomdp_tag_build_table(host.ctypes.data), "pomdp_tag_build_table")
+        self._table = torch.from_numpy(host).to(self.device)     # board maps, staged to shared memory by TMA per CTA
+
+    def _c_head(self):
+        return (ctypes.byref(self._params), _lib.ptr(self._table))
 
     def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
         _lib.check(_lib.lib().pomdp_tag_step(
-            ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state), _lib.ptr(obs),
+            ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state), _lib.ptr(obs),
             _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, self._stream()), "pomdp_tag_step")
 
     def _c_reset(self, state, obs, mask, n, ctr):

@@ -117,9 +117,16 @@ typedef struct PomdpTagParams {
 /* State: 1 word.  bits 0-4 agent cell, bits 5+5j..9+5j opponent j's cell (0..28),
  * bits 25-30 num_opp (6-bit two's complement; the reference lets it go negative with
  * several opponents), bit 31 done.                                                       */
+/* Static maps of the 29-cell board (4224 bytes: for every (agent, opponent) pair the cells the
+ * opponent can reach through the move multiset of tag.py:260-280, and the agent's cell after each
+ * move; layout in gym_pomdp_b200/csrc/pomdp_core.h: TagTables).  Filled on the host, uploaded by
+ * the caller (16-byte aligned) and passed as `d_table`; the kernels stage it into shared memory
+ * with one TMA bulk copy per CTA.                                                             */
+int64_t pomdp_tag_table_bytes(void);
+int     pomdp_tag_build_table(void* host_table);
 /* TagEnv.step tag.py:108-143 (+ move_opponent 201-207, _admissable_actions 260-280,
  * _sample_ob 219-226).  Draw slots per opponent j: 2j = move Bernoulli, 2j+1 = choice.   */
-int pomdp_tag_step(const PomdpTagParams* params,
+int pomdp_tag_step(const PomdpTagParams* params, const void* d_table,
                    const int32_t* state, const int32_t* action,
                    int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
                    int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
@@ -146,12 +153,19 @@ int pomdp_battleship_step(const PomdpBattleshipParams* params,
                           int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
                           int64_t n, void* stream);
 /* BattleShipEnv.reset battleship.py:131-137 (+ _get_init_state 167-180, collision 195-211,
- * mark_ship 182-193).  One WARP per env: the warp enumerates all 4*n_tiles (pos, dir)
- * candidates with the reference's collision rule, and ship s takes the k-th accepted one,
- * k = floor(u * count) from draw slot s -- the same distribution as the reference's
- * rejection loop, in fixed time.  POMDP_FLAG_BAD_STATE is raised in flags (may be NULL)
- * when no placement exists (the reference would spin forever).                           */
+ * mark_ship 182-193) in fixed time: all 4*n_tiles (pos, dir) candidates of a ship are tested with
+ * the reference's collision rule and ship s takes the k-th accepted one in increasing
+ * c = 4*pos + dir, k = floor(u * count) from draw slot s -- the same distribution as the
+ * reference's rejection loop (uniform over the accepted set).  POMDP_FLAG_BAD_STATE is raised in
+ * flags (may be NULL) when no placement exists (the reference would spin forever).
+ *   pomdp_battleship_reset          one THREAD per env, candidates as four 128-bit masks (bitboard)
+ *   pomdp_battleship_reset_warpscan one WARP per env, lanes test candidates, ballots count them
+ * Both produce identical boards.                                                              */
 int pomdp_battleship_reset(const PomdpBattleshipParams* params,
+                           int32_t* state, int32_t* obs, int32_t* flags, const uint8_t* mask,
+                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                           void* stream);
+int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* params,
                            int32_t* state, int32_t* obs, int32_t* flags, const uint8_t* mask,
                            int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                            void* stream);
@@ -230,9 +244,9 @@ int pomdp_rock_rollout(const PomdpRockParams* params, const void* d_table,
                        const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                        int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                        int32_t max_steps, double discount, void* stream);
-int pomdp_tag_policy(const PomdpTagParams* params, const int32_t* state, int32_t* action,
+int pomdp_tag_policy(const PomdpTagParams* params, const void* d_table, const int32_t* state, int32_t* action,
                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
-int pomdp_tag_rollout(const PomdpTagParams* params,
+int pomdp_tag_rollout(const PomdpTagParams* params, const void* d_table,
                       const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                       int32_t max_steps, double discount, void* stream);

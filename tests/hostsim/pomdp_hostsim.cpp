@@ -55,8 +55,9 @@ int policy_host(const typename Env::Params& d, const void* table, const int32_t*
     int rc = host::check_policy(state, action, n, goff, what);
     if (rc) return rc;
     const PhiloxKey key = philox_key(seed);
+    const unsigned char* tbl = (const unsigned char*)table;
     for (int64_t i = 0; i < n; ++i)
-        action[i] = Env::policy(d, (const unsigned char*)table, load_any<typename Env::State>(state, i),
+        action[i] = Env::policy(d, tbl, load_any<typename Env::State>(state, i),
                                 draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0));
     return 0;
 }
@@ -67,10 +68,11 @@ int rollout_host(const typename Env::Params& d, const void* table, const int32_t
     int rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what);
     if (rc) return rc;
     const PhiloxKey key = philox_key(seed);
+    const unsigned char* tbl = (const unsigned char*)table;
     for (int64_t i = 0; i < n; ++i) {
         typename Env::State s = load_any<typename Env::State>(state, i);
         RolloutAcc acc;
-        rollout1<Env>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma, acc);
+        rollout1<Env>(d, tbl, s, key, (uint64_t)(goff + i), step, max_steps, gamma, acc);
         if (final_state) store_state(final_state, i, s);
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
@@ -127,17 +129,28 @@ int pomdp_rock_reset(const PomdpRockParams* q, const void*, int32_t* state, int3
     return 0;
 }
 
-int pomdp_tag_step(const PomdpTagParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
-                   float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+int64_t pomdp_tag_table_bytes(void) { return (int64_t)sizeof(TagTables); }
+int pomdp_tag_build_table(void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "tag: host_table is NULL");
+    tag_build_tables((TagTables*)host_table);
+    return 0;
+}
+int pomdp_tag_step(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
+                   int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     TagDev d;
     const PhiloxKey key = philox_key(seed);
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
     rc = host::check_io(state, action, next, obs, rw, fl, n);
     if (rc) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
+    const TagTables* T = (const TagTables*)table;
     for (int64_t i = 0; i < n; ++i) {
         uint32_t s2;
-        tag_step(d, (uint32_t)state[i], action[i], LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_STEP}, s2, obs[i], rw[i], fl[i]);
+        const LazyDraw draw{&key, (uint64_t)(goff + i), step, DOMAIN_STEP};
+        // the stock one-opponent env alternates between the kernels' two functors (general / branch-free)
+        if (d.n_opp == 1 && (i & 1)) tag_step_1opp(d, T, (uint32_t)state[i], action[i], draw(0), draw(1), s2, obs[i], rw[i], fl[i]);
+        else tag_step(d, T, (uint32_t)state[i], action[i], draw, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }
     return 0;
@@ -249,6 +262,25 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
     const PhiloxKey key = philox_key(seed);
     int rc = host::make_ship(q, &d);
     if (rc) return rc;
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
+    for (int64_t i = 0; i < n; ++i) {
+        if (mask && !mask[i]) continue;
+        ShipState st;
+        const bool ok = battleship_reset_bitboard(d, key, (uint64_t)(goff + i), step, st);
+        uint32_t w8[SHIP_WORDS];
+        ship_pack(st, w8);
+        for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+        if (obs) obs[i] = 0;
+        if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
+    }
+    return 0;
+}
+int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+                           const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    ShipDev d;
+    const PhiloxKey key = philox_key(seed);
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         ShipState st;
@@ -318,20 +350,24 @@ int pomdp_rock_rollout(const PomdpRockParams* q, const void* table, const int32_
     HOSTSIM_ROCK_DISPATCH(rollout_host, d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                           "pomdp_rock_rollout");
 }
-int pomdp_tag_policy(const PomdpTagParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff, uint64_t seed,
-                     uint32_t step, void*) {
+int pomdp_tag_policy(const PomdpTagParams* q, const void* table, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
+                     uint64_t seed, uint32_t step, void*) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    return policy_host<TagEnvT<1>>(d, nullptr, state, action, n, goff, seed, step, "pomdp_tag_policy");
+    return policy_host<TagEnvT<1>>(d, table, state, action, n, goff, seed, step, "pomdp_tag_policy");
 }
-int pomdp_tag_rollout(const PomdpTagParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
-                      int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps, double gamma,
-                      void*) {
+int pomdp_tag_rollout(const PomdpTagParams* q, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+                      int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
+                      double gamma, void*) {
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    return rollout_host<TagEnvT<4>>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
+    if (d.n_opp == 1)
+        return rollout_host<TagEnvT<1>>(d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+                                        "pomdp_tag_rollout");
+    return rollout_host<TagEnvT<4>>(d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                                     "pomdp_tag_rollout");
 }
 int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,

@@ -280,3 +280,23 @@ def test_belief_histogram_matches_bincount(backend):
         else:
             occ = env.unpack(state)[0].cpu().numpy().reshape(N, 10, 10)
             assert np.array_equal(h.reshape(10, 10), occ.sum(0).T)      # bin c = 10*y + x
+
+
+@pytest.mark.parametrize("size,max_len", [((10, 10), 3), ((5, 5), 3), ((10, 10), 5), ((12, 10), 4), ((4, 7), 3), ((3, 3), 3)])
+def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
+    """The two fixed-time placement kernels (thread-per-env bitboards, warp-per-env ballot scan) enumerate the same
+    accepted (pos, dir) set in the same order, so they must produce identical boards -- including 'no placement
+    exists' (3x3 with ships 3 and 2), which both flag instead of spinning like the reference."""
+    B = 3000
+    a = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=9, reset_mode="scan")
+    b = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=9, reset_mode="warpscan")
+    sa, _ = a.init_states(B, step_ctr=4)
+    sb, _ = b.init_states(B, step_ctr=4)
+    assert torch.equal(sa, sb) and torch.equal(a.reset_flags, b.reset_flags)
+    if size == (3, 3):
+        assert (a.reset_flags == _lib.FLAG_BAD_STATE).all()
+    else:
+        assert not a.reset_flags.any()
+        occ, vis, rem, done = a.unpack(sa)
+        n_cells = sum(range(2, max_len + 1))
+        assert (occ.reshape(B, -1).sum(1) == n_cells).all() and (rem == n_cells).all()

@@ -207,7 +207,7 @@ def test_fused_rollout_equals_policy_plus_step_launches(backend, name, kw, goff)
     s0, _ = env.init_states(N, step_ctr=1)
     final, ret, steps, flags = env.rollout(s0, max_steps=T, step_ctr=10)
     s = s0
-    r = torch.zeros(N, dtype=torch.float64, device=backend)
+    r = torch.zeros(N, dtype=torch.float64)     # accumulated on the CPU: torch's CUDA `x / 10` multiplies by a reciprocal
     st = torch.zeros(N, dtype=torch.int32, device=backend)
     fl = torch.zeros(N, dtype=torch.int32, device=backend)
     disc = 1.0
@@ -215,12 +215,15 @@ def test_fused_rollout_equals_policy_plus_step_launches(backend, name, kw, goff)
         a = env.sample_legal_actions(s, step_ctr=10 + t)
         ns, ob, rw, f = env.simulate(s, a, step_ctr=10 + t)
         act = (f & _lib.FLAG_STEPPED_DONE) == 0
-        rw64 = torch.round(rw.double() * 10) / 10 if name == "Network-v0" else rw.double()
-        r = torch.where(act, r + rw64 * disc, r)
+        rw64 = torch.round(rw.double().cpu() * 10) / 10 if name == "Network-v0" else rw.double().cpu()
+        r = torch.where(act.cpu(), r + rw64 * disc, r)
         st += act.int()
         fl |= torch.where(act, f, torch.zeros_like(f))
         s, disc = ns, disc * env._discount
-    assert torch.equal(final, s) and torch.equal(ret, r) and torch.equal(steps, st) and torch.equal(flags, fl)
+    assert torch.equal(final, s), (final != s.reshape(final.shape)).nonzero()[:8].tolist()
+    assert torch.equal(steps, st) and torch.equal(flags, fl)
+    bad = (ret.cpu() != r).nonzero()[:4, 0].tolist()
+    assert not bad, [(i, float(ret[i]).hex(), float(r[i]).hex()) for i in bad]
     # an env that is already terminal takes no step
     f2, r2, s2, fl2 = env.rollout(final, max_steps=5, step_ctr=100)
     fin = (flags & 1) != 0
