@@ -92,6 +92,16 @@ _PROTOTYPES = {
     "pomdp_tiger_rollout": (c_int32, [POINTER(TigerParams)] + _ROLLOUT_TAIL),
     "pomdp_network_policy": (c_int32, [POINTER(NetworkParams)] + _POLICY_TAIL),
     "pomdp_network_rollout": (c_int32, [POINTER(NetworkParams)] + _ROLLOUT_TAIL),
+    "pomdp_rock_obs_prob": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_legal_mask": (c_int32, [POINTER(RockParams), _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_tag_obs_prob": (c_int32, [POINTER(TagParams), _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_tag_legal_mask": (c_int32, [POINTER(TagParams), _P, _P, c_int64, c_void_p]),
+    "pomdp_battleship_obs_prob": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_battleship_legal_mask": (c_int32, [POINTER(BattleshipParams), _P, _P, c_int64, c_void_p]),
+    "pomdp_tiger_obs_prob": (c_int32, [POINTER(TigerParams), _P, _P, _P, _P, c_int64, c_double, c_void_p]),
+    "pomdp_tiger_legal_mask": (c_int32, [POINTER(TigerParams), _P, _P, c_int64, c_void_p]),
+    "pomdp_network_obs_prob": (c_int32, [POINTER(NetworkParams), _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_network_legal_mask": (c_int32, [POINTER(NetworkParams), _P, _P, c_int64, c_void_p]),
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),

@@ -144,7 +144,7 @@ POMDP_HD int tag_get_index(int x, int y) { return y < 2 ? y * 10 + x : 20 + (y -
 // ====================================================================== RockSample ===
 // Static maps of one Rock configuration, built on the host (pomdp_host.h: make_rock) and
 // staged into shared memory by ONE TMA bulk copy per CTA.  Byte layout:
-//   RockTableHdr (432 B)         the reference's own maps (grid, rock coordinates, sensor thresholds, legal-list order)
+//   RockTableHdr (688 B)         the reference's own maps (grid, rock coordinates, sensor thresholds, legal-list order)
 //   RockRes rtab[64]  (16 B)     results: 8 rows x 8 entries; entry = row + 2 * status code + truthful
 //   RockLut special[4] (8 B)     NOOP (failed p_move gate), STEPPED_DONE, BAD_ACTION
 //   RockLut lut[rows * n_act]    transitions, indexed by (agent cell = x | y << 4, action); only the
@@ -169,8 +169,9 @@ struct RockTableHdr {
     uint32_t thr_m1[32];   // d -> ceil(eff(d) * 2^32) - 1, eff = (1 + 2^(-d/20)) / 2
     uint8_t legal_act[32]; // position in _generate_legal's candidate order (rock.py:273-291: E, N, S, W, SAMPLE, then
                            // one check per rock i in rock order) -> the action id that entry holds
+    double eff[32];        // d -> eff(d) as the Python double of rock.py:383-387 (for _compute_prob, rock.py:250-264)
 };
-static_assert(sizeof(RockTableHdr) == 432 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+static_assert(sizeof(RockTableHdr) == 688 && sizeof(RockTableHdr) % 16 == 0, "TMA bulk copy needs 16 B multiples");
 struct alignas(8) RockLut { uint32_t x, y; };
 struct alignas(16) RockRes { uint32_t x, y, z, w; };
 
@@ -312,6 +313,7 @@ POMDP_HD uint32_t rock_alive_bits(uint64_t s) {
 // reference's own _generate_legal raises IndexError, offers no SAMPLE.
 template <typename S>
 POMDP_HD uint32_t rock_legal_list(const RockDev& p, const RockLut* __restrict__ lut, S s) {
+    s &= ~RockBits<S>::DONE;                                           // the list is a function of (agent, rocks) only
     const uint32_t x = (uint32_t)s & 15u, y = ((uint32_t)s >> 4) & 15u;
     uint32_t m = 1u | ((y + 1u < (uint32_t)p.n) ? 2u : 0u) | (y > 0u ? 4u : 0u) | (x > 0u ? 8u : 0u);
     const RockLut e = lut[ROCK_SPECIALS + ((uint32_t)s & 0xFFu) * p.n_actions + 4u];
@@ -504,6 +506,7 @@ POMDP_HD void tag_reset(const TagDev& p, const D& draw, uint32_t& s, int32_t& ob
 // =========================================================================== Tiger ===
 struct TigerDev {
     uint64_t listen_G;  // floor(listen_prob * 2^32):  (u > p)  <=>  (r > G)
+    double listen_prob;
 };
 constexpr uint32_t TIGER_DONE = 0x80000000u;
 
@@ -545,6 +548,7 @@ struct NetworkDev {
     int32_t n;
     uint32_t deg3;                   // machines with more than 2 neighbours (reward 2, network.py:89-92)
     uint64_t p_T, q_T, ob_T;         // ceil(prob * 2^32)
+    double p_ob;
     uint32_t nb[NETWORK_MAX + 2];    // neighbour bit masks (network.py:144-168)
 };
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
@@ -827,6 +831,66 @@ POMDP_HD int32_t battleship_policy(const ShipDev& p, const uint32_t w[SHIP_WORDS
         }
     }
     return a;
+}
+
+// ============================================ observation likelihoods and legal-action masks ===
+// the reference's _compute_prob(action, next_state, ob) -- the particle-reweighting step
+// that follows step() in a particle filter -- as float64, the values the reference's Python floats hold (1 - p is
+// formed with one rounded subtraction, as `1 - eff` is in Python); and _generate_legal as a bit mask over ACTION ids.
+POMDP_HD double dsub_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+// rock.py:250-264
+template <typename S>
+POMDP_HD double rock_obs_prob(const RockDev& p, const RockTableHdr* __restrict__ hdr, S s, int32_t a, int32_t ob) {
+    if (a <= 4) return ob == 0 ? 1.0 : 0.0;
+    const uint32_t r = (uint32_t)(a - 5) < (uint32_t)p.k ? (uint32_t)(a - 5) : 0u;
+    const uint32_t rp = hdr->rock_pos[r];
+    const double eff = hdr->eff[l1_distance((int)((uint32_t)s & 15u), (int)(((uint32_t)s >> 4) & 15u), (int)(rp & 15u), (int)(rp >> 4)) & 31];
+    const uint32_t code = (uint32_t)(s >> (8 + 2 * r)) & 3u;           // 1 good, 3 bad, 0 collected
+    if ((ob == 2 && code == 1u) || (ob == 1 && code == 3u)) return eff;
+    return dsub_rn(1.0, eff);
+}
+// action-indexed legal mask (rock.py:273-291; Rock(15,15)'s two rocks at (1,2) both map to action 8)
+template <typename S>
+POMDP_HD uint32_t rock_legal_mask(const RockDev& p, const RockTableHdr* __restrict__ hdr, const RockLut* __restrict__ lut, S s) {
+    const uint32_t lst = rock_legal_list<S>(p, lut, s);
+    uint32_t m = ((lst & 1u) << 1) | ((lst >> 1) & 1u) | (lst & 0x1Cu);     // E<->N swap: list [E,N,S,W,SAMPLE] -> actions 1,0,2,3,4
+    for (int i = 0; i < p.k; ++i)
+        if ((lst >> (5 + i)) & 1u) m |= 1u << hdr->legal_act[5 + i];
+    return m;
+}
+// tag.py:209-217
+POMDP_HD double tag_obs_prob(const TagDev& p, uint32_t s, int32_t ob) {
+    const uint32_t agent = s & 31u;
+    if (ob == TAG_CELLS)
+        for (int j = 0; j < p.n_opp; ++j)
+            if (((s >> (5 + 5 * j)) & 31u) == agent) return 1.0;
+    return ob == (int32_t)agent ? 1.0 : 0.0;
+}
+// tiger.py:125-138
+POMDP_HD double tiger_obs_prob(double correct_prob, uint32_t s, int32_t a, int32_t ob) {
+    if (a == 2 && ob != 2) return (int32_t)(s & 1u) == ob ? correct_prob : dsub_rn(1.0, correct_prob);
+    if (a != 2 && ob == 2) return 1.0;
+    return 0.0;
+}
+// network.py:43-55
+POMDP_HD double network_obs_prob(const NetworkDev& p, double p_ob, uint32_t s, int32_t a, int32_t ob) {
+    if ((uint32_t)a < (uint32_t)(2 * p.n)) return (int32_t)((s >> (a >> 1)) & 1u) == ob ? p_ob : dsub_rn(1.0, p_ob);
+    return ob == 2 ? 1.0 : 0.0;
+}
+// battleship.py:80-89
+POMDP_HD double battleship_obs_prob(const ShipDev& p, const uint32_t w[SHIP_WORDS], int32_t a, int32_t ob) {
+    const uint32_t c = (uint32_t)a < (uint32_t)p.n_tiles ? (uint32_t)a : 0u;
+    const uint32_t occ = (c >> 5) == 0 ? w[0] : (c >> 5) == 1 ? w[1] : (c >> 5) == 2 ? w[2] : w[3];
+    const uint32_t vis = (c >> 5) == 0 ? w[4] : (c >> 5) == 1 ? w[5] : (c >> 5) == 2 ? w[6] : w[7];
+    if (ob == 0 && ((vis >> (c & 31)) & 1u)) return 1.0;
+    if (ob == 1 && ((occ >> (c & 31)) & 1u)) return 1.0;
+    return ob == 0 ? 1.0 : 0.0;
 }
 
 // ========================================================================= rollouts ===

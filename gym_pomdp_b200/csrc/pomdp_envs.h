@@ -22,6 +22,13 @@ struct RockEnvT {
                               reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET), s, w);
     }
     static POMDP_HD bool is_done(S s) { return (s & RockBits<S>::DONE) != 0; }
+    static POMDP_HD double obs_prob(const Params& p, const unsigned char* tbl, S s, int32_t a, int32_t ob, double) {
+        return rock_obs_prob<S>(p, reinterpret_cast<const RockTableHdr*>(tbl), s, a, ob);
+    }
+    static POMDP_HD void legal_mask(const Params& p, const unsigned char* tbl, S s, uint32_t* m) {
+        m[0] = rock_legal_mask<S>(p, reinterpret_cast<const RockTableHdr*>(tbl), reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET), s);
+    }
+    static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }          // integral rewards (rock.py:141-169)
     static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
@@ -79,6 +86,11 @@ struct TagEnvT {
         return (int32_t)rand_below(w, 5u);
     }
     static POMDP_HD bool is_done(State s) { return (s & TAG_DONE) != 0; }
+    static POMDP_HD double obs_prob(const Params& p, const unsigned char*, State s, int32_t, int32_t ob, double) {
+        return tag_obs_prob(p, s, ob);
+    }
+    static POMDP_HD void legal_mask(const Params&, const unsigned char*, State, uint32_t* m) { m[0] = 31u; }   // tag.py:228-229
+    static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }
     static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
@@ -115,6 +127,18 @@ struct TagEnvT {
     }
 };
 
+// Tag's table-free queries (observation likelihood, legal mask)
+struct TagNoTable {
+    typedef TagDev Params;
+    typedef uint32_t State;
+    static constexpr bool kTable = false;
+    static POMDP_HD double obs_prob(const Params& p, const unsigned char*, State s, int32_t, int32_t ob, double) {
+        return tag_obs_prob(p, s, ob);
+    }
+    static POMDP_HD void legal_mask(const Params&, const unsigned char*, State, uint32_t* m) { m[0] = 31u; }   // tag.py:228-229
+    static POMDP_HD int mask_words(const Params&) { return 1; }
+};
+
 struct TigerEnvP {
     typedef TigerDev Params;
     typedef uint32_t State;
@@ -123,6 +147,11 @@ struct TigerEnvP {
         return (int32_t)rand_below(w, 3u);
     }
     static POMDP_HD bool is_done(State s) { return (s & TIGER_DONE) != 0; }
+    static POMDP_HD double obs_prob(const Params&, const unsigned char*, State s, int32_t a, int32_t ob, double correct_prob) {
+        return tiger_obs_prob(correct_prob, s, a, ob);
+    }
+    static POMDP_HD void legal_mask(const Params&, const unsigned char*, State, uint32_t* m) { m[0] = 7u; }    // tiger.py:111-112
+    static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }
     static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
@@ -158,6 +187,15 @@ struct NetworkEnvP {
         return (int32_t)rand_below(w, (uint32_t)(2 * p.n + 1));
     }
     static POMDP_HD bool is_done(State s) { return (s & NETWORK_DONE) != 0; }
+    static POMDP_HD double obs_prob(const Params& p, const unsigned char*, State s, int32_t a, int32_t ob, double) {
+        return network_obs_prob(p, p.p_ob, s, a, ob);
+    }
+    static POMDP_HD void legal_mask(const Params& p, const unsigned char*, State, uint32_t* m) {              // network.py:129-130
+        const int na = 2 * p.n + 1;
+        m[0] = na >= 32 ? 0xFFFFFFFFu : ((1u << na) - 1u);
+        if (na > 32) m[1] = (1u << (na - 32)) - 1u;
+    }
+    static POMDP_HD int mask_words(const Params& p) { return (2 * p.n + 1 + 31) / 32; }
     // the reference's reward is the Python double s - 0.1 / s - 2.5 / s == tenths / 10.0 (network.py:87-108); the
     // float32 the step kernel emits determines the integer number of tenths uniquely
     static POMDP_HD double reward64(float rw) {

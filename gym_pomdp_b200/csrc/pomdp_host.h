@@ -132,6 +132,7 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         for (int dd = 0; dd < 32; ++dd) {
             const double eff = (1 + pow(2, -(double)dd / 20)) * .5;      // rock.py:383-387
             h->thr_m1[dd] = (uint32_t)(bern_T(eff) - 1);
+            h->eff[dd] = eff;
         }
         // ---- result rows: entry = row + 2 * code + truthful; code 0 collected/none, 1 good, 3 bad (2 never packed)
         const bool wall_done = !stoch;                                   // rock.py:193; commented out at rock.py:503
@@ -198,6 +199,7 @@ inline int make_tag(const PomdpTagParams* q, TagDev* d) {
 inline int make_tiger(const PomdpTigerParams* q, TigerDev* d) {
     if (!q) return fail(POMDP_E_BADARG, "tiger: params is NULL");
     d->listen_G = gt_G(q->listen_prob);
+    d->listen_prob = q->listen_prob;
     return 0;
 }
 
@@ -210,6 +212,7 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     d->p_T = bern_T(q->p);
     d->q_T = bern_T(q->q);
     d->ob_T = bern_T(q->p_ob);
+    d->p_ob = q->p_ob;
     int deg[NETWORK_MAX] = {0};
     auto link = [&](int i, int j) { d->nb[i] |= 1u << j; ++deg[i]; };
     if (q->problem_type == 3) {                     // network.py:153-168
@@ -292,6 +295,14 @@ inline int check_policy(const void* state, const void* action, int64_t n, int64_
     if (n == 0) return 0;
     if (!state || !action) return fail(POMDP_E_BADARG, "%s: a required array pointer is NULL", what);
     if (((uintptr_t)state | (uintptr_t)action) & 3) return fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
+    return 0;
+}
+inline int check_obs_prob(const void* state, const void* action, const void* obs, const void* prob, int64_t n, const char* what) {
+    if (n < 0) return fail(POMDP_E_BADARG, "%s: n = %lld is negative", what, (long long)n);
+    if (n == 0) return 0;
+    if (!state || !action || !obs || !prob) return fail(POMDP_E_BADARG, "%s: a required array pointer is NULL", what);
+    if ((((uintptr_t)state | (uintptr_t)action | (uintptr_t)obs) & 3) || ((uintptr_t)prob & 7))
+        return fail(POMDP_E_ALIGN, "%s: int32 arrays must be 4-byte and the float64 array 8-byte aligned", what);
     return 0;
 }
 inline int check_rollout(const void* state, const void* final_state, const void* ret, const void* steps, const void* flags,

@@ -394,6 +394,65 @@ __device__ __forceinline__ void ship_load(const int32_t* state, int64_t i, bool 
         for (int k = 0; k < SHIP_WORDS; ++k) w[k] = (uint32_t)state[i * SHIP_WORDS + k];
     }
 }
+// prob[i] = env._compute_prob(action[i], next_state[i], obs[i]) (float64);  mask[i, :] = env._generate_legal() as bits
+template <class Env>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_obs_prob_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
+                      const int32_t* __restrict__ state, const int32_t* __restrict__ action, const int32_t* __restrict__ obs,
+                      double* __restrict__ prob, int64_t n, double extra, uint32_t table_bytes) {
+    typedef typename Env::State S;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads)
+        prob[i] = Env::obs_prob(p, smem_table, load_state1(state, i, S()), __ldcs(action + i), __ldcs(obs + i), extra);
+}
+template <class Env>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_legal_mask_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
+                        const int32_t* __restrict__ state, uint32_t* __restrict__ mask, int64_t n, uint32_t table_bytes) {
+    typedef typename Env::State S;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    const int words = Env::mask_words(p);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t m[2] = {0u, 0u};
+        Env::legal_mask(p, smem_table, load_state1(state, i, S()), m);
+        mask[i * words] = m[0];
+        if (words > 1) mask[i * words + 1] = m[1];
+    }
+}
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_obs_prob_kernel(const __grid_constant__ ShipDev p, const int32_t* __restrict__ state,
+                                 const int32_t* __restrict__ action, const int32_t* __restrict__ obs,
+                                 double* __restrict__ prob, int64_t n) {
+    const bool vec = (reinterpret_cast<uintptr_t>(state) & 15) == 0;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t w[SHIP_WORDS];
+        ship_load(state, i, vec, w);
+        prob[i] = battleship_obs_prob(p, w, action[i], obs[i]);
+    }
+}
+// battleship.py:157-165: bit c of the ceil(n_tiles / 32)-word mask = cell c not visited
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_legal_mask_kernel(const __grid_constant__ ShipDev p, const int32_t* __restrict__ state,
+                                   uint32_t* __restrict__ mask, int64_t n) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int words = (p.n_tiles + 31) >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lim = p.n_tiles - 32 * k;
+            const uint32_t valid = lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+            if (k < words) mask[i * words + k] = ~(uint32_t)state[i * SHIP_WORDS + 4 + k] & valid;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_battleship_policy_kernel(const __grid_constant__ ShipDev p, const int32_t* __restrict__ state,
                                int32_t* __restrict__ action, int64_t n, uint64_t goff,
@@ -850,6 +909,37 @@ int launch_rollout(const typename Env::Params& p, const void* d_table, uint32_t 
     return finish(what);
 }
 
+template <class Env>
+int launch_obs_prob(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                    const int32_t* state, const int32_t* action, const int32_t* obs, double* prob, int64_t n, double extra,
+                    void* stream, const char* what) {
+    int rc = host::check_obs_prob(state, action, obs, prob, n, what);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = Env::kTable ? smem_bytes : 0;
+    auto k = pomdp_obs_prob_kernel<Env>;
+    if ((rc = allow_smem(k, smem))) return rc;
+    k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(p, d_table, state, action, obs, prob, n,
+                                                                                           extra, table_bytes);
+    return finish(what);
+}
+template <class Env>
+int launch_legal_mask(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                      const int32_t* state, uint32_t* mask, int64_t n, void* stream, const char* what) {
+    int rc = host::check_policy(state, mask, n, 0, what);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = Env::kTable ? smem_bytes : 0;
+    auto k = pomdp_legal_mask_kernel<Env>;
+    if ((rc = allow_smem(k, smem))) return rc;
+    k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(p, d_table, state, mask, n, table_bytes);
+    return finish(what);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1134,6 +1224,89 @@ int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* stat
     k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, final_state, ret, steps, flags, n, (uint64_t)goff,
                                                                 philox_key(seed), step_ctr, max_steps, discount);
     return finish("pomdp_battleship_rollout");
+}
+
+// ---- observation likelihoods (_compute_prob) and legal-action masks (_generate_legal): SURVEY.md §8f ranks 2-3
+#define POMDP_ROCK_DISPATCH2(FN, ...)                                                                          \
+    do {                                                                                                       \
+        if (host::rock_words(q) == 1) return FN<RockEnvT<uint32_t, false>>(__VA_ARGS__);                       \
+        return FN<RockEnvT<uint64_t, false>>(__VA_ARGS__);                                                     \
+    } while (0)
+int pomdp_rock_obs_prob(const PomdpRockParams* q, const void* d_table, const int32_t* next_state, const int32_t* action,
+                        const int32_t* obs, double* prob, int64_t n, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    POMDP_ROCK_DISPATCH2(launch_obs_prob, d, d_table, d.table_bytes, d.smem_bytes, next_state, action, obs, prob, n, 0.0, stream,
+                         "pomdp_rock_obs_prob");
+}
+int pomdp_rock_legal_mask(const PomdpRockParams* q, const void* d_table, const int32_t* state, uint32_t* mask, int64_t n,
+                          void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    POMDP_ROCK_DISPATCH2(launch_legal_mask, d, d_table, d.table_bytes, d.smem_bytes, state, mask, n, stream, "pomdp_rock_legal_mask");
+}
+#undef POMDP_ROCK_DISPATCH2
+int pomdp_tag_obs_prob(const PomdpTagParams* q, const int32_t* next_state, const int32_t* action, const int32_t* obs,
+                       double* prob, int64_t n, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return launch_obs_prob<TagNoTable>(d, nullptr, 0, 0, next_state, action, obs, prob, n, 0.0, stream, "pomdp_tag_obs_prob");
+}
+int pomdp_tag_legal_mask(const PomdpTagParams* q, const int32_t* state, uint32_t* mask, int64_t n, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return launch_legal_mask<TagNoTable>(d, nullptr, 0, 0, state, mask, n, stream, "pomdp_tag_legal_mask");
+}
+int pomdp_tiger_obs_prob(const PomdpTigerParams* q, const int32_t* next_state, const int32_t* action, const int32_t* obs,
+                         double* prob, int64_t n, double correct_prob, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_obs_prob<TigerEnvP>(d, nullptr, 0, 0, next_state, action, obs, prob, n, correct_prob, stream, "pomdp_tiger_obs_prob");
+}
+int pomdp_tiger_legal_mask(const PomdpTigerParams* q, const int32_t* state, uint32_t* mask, int64_t n, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_legal_mask<TigerEnvP>(d, nullptr, 0, 0, state, mask, n, stream, "pomdp_tiger_legal_mask");
+}
+int pomdp_network_obs_prob(const PomdpNetworkParams* q, const int32_t* next_state, const int32_t* action, const int32_t* obs,
+                           double* prob, int64_t n, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_obs_prob<NetworkEnvP>(d, nullptr, 0, 0, next_state, action, obs, prob, n, 0.0, stream, "pomdp_network_obs_prob");
+}
+int pomdp_network_legal_mask(const PomdpNetworkParams* q, const int32_t* state, uint32_t* mask, int64_t n, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_legal_mask<NetworkEnvP>(d, nullptr, 0, 0, state, mask, n, stream, "pomdp_network_legal_mask");
+}
+int pomdp_battleship_obs_prob(const PomdpBattleshipParams* q, const int32_t* next_state, const int32_t* action,
+                              const int32_t* obs, double* prob, int64_t n, void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_obs_prob(next_state, action, obs, prob, n, "pomdp_battleship_obs_prob"))) return rc;
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_obs_prob_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, next_state, action, obs, prob, n);
+    return finish("pomdp_battleship_obs_prob");
+}
+int pomdp_battleship_legal_mask(const PomdpBattleshipParams* q, const int32_t* state, uint32_t* mask, int64_t n, void* stream) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, mask, n, 0, "pomdp_battleship_legal_mask"))) return rc;
+    if (n == 0) return 0;
+    auto k = pomdp_battleship_legal_mask_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, mask, n);
+    return finish("pomdp_battleship_legal_mask");
 }
 
 // ---- helpers

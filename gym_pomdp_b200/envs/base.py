@@ -93,6 +93,46 @@ class BatchedPomdpEnv(object):
                       _lib.ptr(flags), n, self.global_offset, self._seed, ctr, int(max_steps), float(discount),
                       self._stream()), "pomdp_%s_rollout" % self._abi)
 
+    def _c_obs_prob(self, next_state, action, obs, prob, n, *extra):
+        fn = getattr(_lib.lib(), "pomdp_%s_obs_prob" % self._abi)
+        _lib.check(fn(*self._c_query_head(), _lib.ptr(next_state), _lib.ptr(action), _lib.ptr(obs), _lib.ptr(prob), n, *extra,
+                      self._stream()), "pomdp_%s_obs_prob" % self._abi)
+
+    def _c_query_head(self):
+        """Leading arguments of the table-free query entry points (obs_prob / legal_mask)."""
+        return (ctypes.byref(self._params),)
+
+    def observation_prob(self, action, next_state, ob, *extra):
+        """Batched ``_compute_prob(action, next_state, ob)``: float64[n], one kernel (particle reweighting;
+        SURVEY.md §8f rank 2).  ``next_state`` is the packed post-step state."""
+        n = next_state.shape[0]
+        dev = next_state.device
+        action = torch.as_tensor(action, device=dev).to(torch.int32).expand(n).contiguous()
+        ob = torch.as_tensor(ob, device=dev).to(torch.int32).expand(n).contiguous()
+        prob = torch.empty(n, dtype=torch.float64, device=dev)
+        with self._guard():
+            self._c_obs_prob(next_state.contiguous(), action, ob, prob, n, *extra)
+        return prob
+
+    def legal_mask_words(self, state=None):
+        """``_generate_legal()`` for every particle as bit masks over action ids: int32[n, ceil(n_actions / 32)]
+        (SURVEY.md §8f rank 3), one kernel."""
+        state = self.state if state is None else state
+        n = state.shape[0]
+        words = (self.action_space.n + 31) // 32
+        mask = torch.empty((n, words), dtype=torch.int32, device=state.device)
+        fn = getattr(_lib.lib(), "pomdp_%s_legal_mask" % self._abi)
+        with self._guard():
+            _lib.check(fn(*self._c_query_head(), _lib.ptr(state.contiguous()), _lib.ptr(mask), n, self._stream()),
+                       "pomdp_%s_legal_mask" % self._abi)
+        return mask
+
+    def legal_mask(self, state=None):
+        """bool[n, n_actions] view of ``legal_mask_words``"""
+        w = self.legal_mask_words(state).to(torch.int64) & 0xFFFFFFFF
+        a = torch.arange(self.action_space.n, device=w.device)
+        return ((w[:, a // 32] >> (a % 32)) & 1).bool()
+
     # subclasses: scalar-mode conversions -------------------------------------------
     def _state_to_ref(self, words):
         raise NotImplementedError

@@ -131,10 +131,7 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _generate_legal(self, state=None):
         """battleship.py:157-165: the unvisited cells."""
-        words = self.state if state is None else state
-        _, vis, _, _ = self.unpack(words.reshape(-1, 8))
-        n = vis.shape[0]
-        unvisited = ~vis.permute(0, 2, 1).reshape(n, -1)       # action index = x_size * y + x
+        unvisited = self.legal_mask(None if state is None else state.reshape(-1, 8))   # action index = x_size * y + x
         if self._scalar and state is None:
             return [int(a) for a in torch.nonzero(unvisited[0])[:, 0]]
         return unvisited
@@ -151,10 +148,4 @@ class BattleShipEnv(BatchedPomdpEnv):
             if ob == 1 and next_state.occupied[x][y]:
                 return 1
             return int(ob == 0)
-        occ, vis, _, _ = self.unpack(next_state)
-        n = occ.shape[0]
-        action = torch.as_tensor(action, device=next_state.device).long()
-        ob = torch.as_tensor(ob, device=next_state.device).long()
-        occ_a = torch.gather(occ.permute(0, 2, 1).reshape(n, -1), 1, action[:, None])[:, 0]
-        vis_a = torch.gather(vis.permute(0, 2, 1).reshape(n, -1), 1, action[:, None])[:, 0]
-        return (((ob == 0) & vis_a) | ((ob == 1) & occ_a) | (ob == 0)).double()
+        return self.observation_prob(action, next_state, ob)

@@ -95,8 +95,7 @@ class NetworkEnv(BatchedPomdpEnv):
     def _generate_legal(self, state=None):
         if self._scalar and state is None:
             return list(range(self.action_space.n))
-        n = (self.state if state is None else state).shape[0]
-        return torch.ones((n, self.action_space.n), dtype=torch.bool, device=self.device)
+        return self.legal_mask(state)
 
     def _generate_preferred(self, history):
         return self._generate_legal()
@@ -110,16 +109,8 @@ class NetworkEnv(BatchedPomdpEnv):
             if action < self._n_machines * 2:
                 return self._p_ob if next_state[action // 2] == ob else 1 - self._p_ob
             return 1. if ob == NULL else 0
-        bits = self.unpack(next_state).long()
-        action = torch.as_tensor(action, device=next_state.device).long()
-        ob = torch.as_tensor(ob, device=next_state.device).long()
-        machine = (action // 2).clamp(0, self._n_machines - 1)
-        up = torch.gather(bits, 1, machine[:, None])[:, 0]
-        f64 = dict(dtype=torch.float64, device=next_state.device)
-        p = torch.where(up == ob, torch.tensor(self._p_ob, **f64), torch.tensor(1 - self._p_ob, **f64))
-        return torch.where(action < 2 * self._n_machines, p, (ob == NULL).double())
+        return self.observation_prob(action, next_state, ob)
 
-    # topology builders (network.py:144-168), kept as static methods like the reference
     @staticmethod
     def make_ring_neighbours(n_machines):
         return [[(i + 1) % n_machines, (i + n_machines - 1) % n_machines] for i in range(n_machines)]

@@ -57,6 +57,8 @@ class RockEnv(BatchedPomdpEnv):
     def _c_head(self):
         return (ctypes.byref(self._params), _lib.ptr(self._table))
 
+    _c_query_head = _c_head
+
     def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
         _lib.check(_lib.lib().pomdp_rock_step(
             ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state),
@@ -191,24 +193,7 @@ class RockEnv(BatchedPomdpEnv):
                     p = self._rock_pos[i]
                     legal.append(int(self._grid_map[p.x | (p.y << 4)]) + 1 + SAMPLE)
             return legal
-        words = self.state if state is None else state
-        x, y, status, _ = self.unpack(words)
-        n = self.grid.x_size
-        mask = torch.zeros((x.shape[0], self.action_space.n), dtype=torch.bool, device=words.device)
-        mask[:, 1] = True
-        mask[:, 0] = y + 1 < n
-        mask[:, 2] = y - 1 >= 0
-        mask[:, 3] = x - 1 >= 0
-        gm = torch.from_numpy(self._grid_map.astype(np.int64)).to(words.device)
-        rock = gm[(x | (y << 4)).long()]
-        has = (rock >= 0) & (rock < self.num_rocks)
-        st_under = torch.gather(status, 1, rock.clamp(0, self.num_rocks - 1)[:, None])[:, 0]
-        mask[:, SAMPLE] = has & (st_under != 0)
-        for i in range(self.num_rocks):
-            p = self._rock_pos[i]
-            a = int(self._grid_map[p.x | (p.y << 4)]) + 1 + SAMPLE
-            mask[:, a] |= status[:, i] != 0
-        return mask
+        return self.legal_mask(state)
 
     def _generate_preferred(self, history):
         if not self._use_heuristic:
@@ -225,21 +210,7 @@ class RockEnv(BatchedPomdpEnv):
             if (ob == GOOD and rock["status"] == 1) or (ob == BAD and rock["status"] == -1):
                 return eff
             return 1 - eff
-        x, y, status, _ = self.unpack(next_state)
-        action = torch.as_tensor(action, device=next_state.device).long()
-        ob = torch.as_tensor(ob, device=next_state.device).long()
-        rock = (action - SAMPLE - 1).clamp(0, self.num_rocks - 1)
-        pos = torch.tensor([[p.x, p.y] for p in self._rock_pos], device=next_state.device)
-        d = (x.long() - pos[rock, 0]).abs() + (y.long() - pos[rock, 1]).abs()
-        # rock.py:383-387 evaluated in Python doubles per distance (bit-equal to the reference; torch.pow on
-        # the device may differ in the last ulp), then gathered
-        eff_tab = torch.tensor([self._efficiency((0, 0), (dd, 0)) for dd in range(2 * self.grid.x_size)],
-                               dtype=torch.float64, device=next_state.device)
-        eff = eff_tab[d]
-        st = torch.gather(status.long(), 1, rock[:, None])[:, 0]
-        match = ((ob == GOOD) & (st == 1)) | ((ob == BAD) & (st == -1))
-        p_check = torch.where(match, eff, 1 - eff)
-        return torch.where(action <= SAMPLE, (ob == NULL).double(), p_check)
+        return self.observation_prob(action, next_state, ob)
 
 
 class StochasticRockEnv(RockEnv):

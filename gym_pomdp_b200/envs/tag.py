@@ -128,8 +128,7 @@ class TagEnv(BatchedPomdpEnv):
         """tag.py:228-229"""
         if self._scalar and state is None:
             return list(range(self.action_space.n))
-        n = (self.state if state is None else state).shape[0]
-        return torch.ones((n, 5), dtype=torch.bool, device=self.device)
+        return self.legal_mask(state)
 
     def _generate_preferred(self, history):
         """tag.py:231-243 (scalar mode)"""
@@ -155,8 +154,4 @@ class TagEnv(BatchedPomdpEnv):
                     if opp_pos == next_state.agent_pos:
                         return 1.
             return p_ob
-        agent, opp, _, _ = self.unpack(next_state)
-        ob = torch.as_tensor(ob, device=next_state.device).to(torch.int32)
-        same = (opp == agent[:, None]).any(dim=1)
-        return torch.where((ob == self.grid.n_tiles) & same, torch.ones_like(ob, dtype=torch.float64),
-                           (ob == agent).double())
+        return self.observation_prob(action, next_state, ob)

@@ -77,8 +77,7 @@ class TigerEnv(BatchedPomdpEnv):
     def _generate_legal(self, state=None):
         if self._scalar and state is None:
             return list(range(self.action_space.n))
-        n = (self.state if state is None else state).shape[0]
-        return torch.ones((n, 3), dtype=torch.bool, device=self.device)
+        return self.legal_mask(state)
 
     def _generate_preferred(self, history):
         return self._generate_legal()
@@ -92,11 +91,4 @@ class TigerEnv(BatchedPomdpEnv):
             elif action != LISTEN and ob == 2:
                 p_ob = 1.
             return p_ob
-        tiger, _ = self.unpack(next_state)
-        action = torch.as_tensor(action, device=next_state.device)
-        ob = torch.as_tensor(ob, device=next_state.device)
-        f64 = dict(dtype=torch.float64, device=next_state.device)
-        listen = torch.where(tiger == ob, torch.tensor(correct_prob, **f64), torch.tensor(1 - correct_prob, **f64))
-        zero = torch.zeros_like(listen)
-        return torch.where((action == LISTEN) & (ob != 2), listen,
-                           torch.where((action != LISTEN) & (ob == 2), zero + 1., zero))
+        return self.observation_prob(action, next_state, ob, float(correct_prob))

@@ -85,8 +85,8 @@ typedef struct PomdpRockParams {
  *   complement code (0b11 = -1 bad, 0b00 = 0 collected, 0b01 = +1 good), top bit = done. */
 int     pomdp_rock_state_words(const PomdpRockParams* params);
 /* Static per-config maps that the step kernel stages into shared memory with one TMA bulk
- * copy per CTA: a 432-byte header (rock-id grid, rock coordinates, sensor thresholds, order of
- * the legal-action list: the reference's own tables) followed by the transition LUT indexed by (agent cell, action)
+ * copy per CTA: a 688-byte header (rock-id grid, rock coordinates, sensor thresholds and efficiencies,
+ * order of the legal-action list: the reference's own tables) followed by the transition LUT indexed by (agent cell, action)
  * (16.4 KB for <= 11 rocks, 32.8 KB otherwise; layout in gym_pomdp_b200/csrc/pomdp_core.h).
  * The caller uploads the filled buffer to the device (16-byte aligned) and passes it as
  * `d_table`.                                                                              */
@@ -268,6 +268,38 @@ int pomdp_network_rollout(const PomdpNetworkParams* params,
                           const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                           int32_t max_steps, double discount, void* stream);
+
+/* --------------------------------- observation likelihoods and legal-action masks --- */
+/* what a particle filter / POMCP node does right after step().
+ * pomdp_E_obs_prob  : prob[i] = env._compute_prob(action[i], next_state[i], obs[i]) as float64, the
+ *                     value the reference's Python float holds (rock.py:250-264; tag.py:209-217;
+ *                     battleship.py:80-89; tiger.py:125-138 with its `correct_prob` argument;
+ *                     network.py:43-55).  `next_state` is the packed post-step state.
+ * pomdp_E_legal_mask: env._generate_legal() as a bit mask over action ids, ceil(n_actions/32) uint32
+ *                     words per env, row-major (rock.py:273-291; tag.py:228-229; battleship.py:157-165
+ *                     = ceil(n_tiles/32) words, bit c = cell c unvisited; tiger.py:111-112; network.py:129-130).      */
+int pomdp_rock_obs_prob(const PomdpRockParams* params, const void* d_table,
+                        const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
+                        int64_t n, void* stream);
+int pomdp_rock_legal_mask(const PomdpRockParams* params, const void* d_table,
+                          const int32_t* state, uint32_t* mask, int64_t n, void* stream);
+int pomdp_tag_obs_prob(const PomdpTagParams* params,
+                       const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
+                       int64_t n, void* stream);
+int pomdp_tag_legal_mask(const PomdpTagParams* params, const int32_t* state, uint32_t* mask, int64_t n, void* stream);
+int pomdp_battleship_obs_prob(const PomdpBattleshipParams* params,
+                              const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
+                              int64_t n, void* stream);
+int pomdp_battleship_legal_mask(const PomdpBattleshipParams* params, const int32_t* state, uint32_t* mask,
+                                int64_t n, void* stream);
+int pomdp_tiger_obs_prob(const PomdpTigerParams* params,
+                         const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
+                         int64_t n, double correct_prob, void* stream);
+int pomdp_tiger_legal_mask(const PomdpTigerParams* params, const int32_t* state, uint32_t* mask, int64_t n, void* stream);
+int pomdp_network_obs_prob(const PomdpNetworkParams* params,
+                           const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
+                           int64_t n, void* stream);
+int pomdp_network_legal_mask(const PomdpNetworkParams* params, const int32_t* state, uint32_t* mask, int64_t n, void* stream);
 
 /* ------------------------------------------------------------ Grid / Coord helpers --- */
 /* coord.py:7-114 and tag.py:36-66 as batched device functions (bit-exact integer work).

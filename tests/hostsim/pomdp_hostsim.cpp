@@ -80,6 +80,31 @@ int rollout_host(const typename Env::Params& d, const void* table, const int32_t
 }
 }  // namespace
 
+namespace {
+template <class Env>
+int obs_prob_host(const typename Env::Params& d, const void* table, const int32_t* state, const int32_t* action, const int32_t* obs,
+                  double* prob, int64_t n, double extra, const char* what) {
+    int rc = host::check_obs_prob(state, action, obs, prob, n, what);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        prob[i] = Env::obs_prob(d, (const unsigned char*)table, load_any<typename Env::State>(state, i), action[i], obs[i], extra);
+    return 0;
+}
+template <class Env>
+int legal_mask_host(const typename Env::Params& d, const void* table, const int32_t* state, uint32_t* mask, int64_t n,
+                    const char* what) {
+    int rc = host::check_policy(state, mask, n, 0, what);
+    if (rc) return rc;
+    const int words = Env::mask_words(d);
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t m[2] = {0u, 0u};
+        Env::legal_mask(d, (const unsigned char*)table, load_any<typename Env::State>(state, i), m);
+        for (int k = 0; k < words; ++k) mask[i * words + k] = m[k];
+    }
+    return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int pomdp_abi_version(void) { return POMDP_ABI_VERSION; }
@@ -439,6 +464,86 @@ int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* stat
         if (final_state) memcpy(final_state + i * SHIP_WORDS, w, sizeof(w));
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
+    return 0;
+}
+
+int pomdp_rock_obs_prob(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action, const int32_t* obs,
+                        double* prob, int64_t n, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    if (host::rock_words(q) == 1) return obs_prob_host<RockEnvT<uint32_t, false>>(d, table, state, action, obs, prob, n, 0.0, "pomdp_rock_obs_prob");
+    return obs_prob_host<RockEnvT<uint64_t, false>>(d, table, state, action, obs, prob, n, 0.0, "pomdp_rock_obs_prob");
+}
+int pomdp_rock_legal_mask(const PomdpRockParams* q, const void* table, const int32_t* state, uint32_t* mask, int64_t n, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    if (host::rock_words(q) == 1) return legal_mask_host<RockEnvT<uint32_t, false>>(d, table, state, mask, n, "pomdp_rock_legal_mask");
+    return legal_mask_host<RockEnvT<uint64_t, false>>(d, table, state, mask, n, "pomdp_rock_legal_mask");
+}
+int pomdp_tag_obs_prob(const PomdpTagParams* q, const int32_t* state, const int32_t* action, const int32_t* obs, double* prob,
+                       int64_t n, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return obs_prob_host<TagNoTable>(d, nullptr, state, action, obs, prob, n, 0.0, "pomdp_tag_obs_prob");
+}
+int pomdp_tag_legal_mask(const PomdpTagParams* q, const int32_t* state, uint32_t* mask, int64_t n, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    return legal_mask_host<TagNoTable>(d, nullptr, state, mask, n, "pomdp_tag_legal_mask");
+}
+int pomdp_tiger_obs_prob(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, const int32_t* obs, double* prob,
+                         int64_t n, double correct_prob, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return obs_prob_host<TigerEnvP>(d, nullptr, state, action, obs, prob, n, correct_prob, "pomdp_tiger_obs_prob");
+}
+int pomdp_tiger_legal_mask(const PomdpTigerParams* q, const int32_t* state, uint32_t* mask, int64_t n, void*) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return legal_mask_host<TigerEnvP>(d, nullptr, state, mask, n, "pomdp_tiger_legal_mask");
+}
+int pomdp_network_obs_prob(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, const int32_t* obs,
+                           double* prob, int64_t n, void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return obs_prob_host<NetworkEnvP>(d, nullptr, state, action, obs, prob, n, 0.0, "pomdp_network_obs_prob");
+}
+int pomdp_network_legal_mask(const PomdpNetworkParams* q, const int32_t* state, uint32_t* mask, int64_t n, void*) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return legal_mask_host<NetworkEnvP>(d, nullptr, state, mask, n, "pomdp_network_legal_mask");
+}
+int pomdp_battleship_obs_prob(const PomdpBattleshipParams* q, const int32_t* state, const int32_t* action, const int32_t* obs,
+                              double* prob, int64_t n, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_obs_prob(state, action, obs, prob, n, "pomdp_battleship_obs_prob"))) return rc;
+    for (int64_t i = 0; i < n; ++i) prob[i] = battleship_obs_prob(d, (const uint32_t*)state + i * SHIP_WORDS, action[i], obs[i]);
+    return 0;
+}
+int pomdp_battleship_legal_mask(const PomdpBattleshipParams* q, const int32_t* state, uint32_t* mask, int64_t n, void*) {
+    ShipDev d;
+    int rc = host::make_ship(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, mask, n, 0, "pomdp_battleship_legal_mask"))) return rc;
+    const int words = (d.n_tiles + 31) >> 5;
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < words; ++k) {
+            const int lim = d.n_tiles - 32 * k;
+            const uint32_t valid = lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+            mask[i * words + k] = ~(uint32_t)state[i * SHIP_WORDS + 4 + k] & valid;
+        }
     return 0;
 }
 
