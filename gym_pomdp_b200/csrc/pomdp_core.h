@@ -264,25 +264,39 @@ POMDP_HD void rock_step(const RockDev& p, const RockLut* __restrict__ lut, const
     fl = (int32_t)r.z;
 }
 
-// rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)); draw slot i = rock i.
+// rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)), one uniform per rock.  Only the comparison with
+// one half matters, so EIGHT rocks share one draw word: rock i's uniform is u = r_i / 2^32 with
+// r_i = rotl32(word of slot i >> 3, 4 * (i & 7)).  The deciding (top) bits of the eight r_i are eight different bits
+// of the slot's word, hence independent fair coins; reset needs ceil(k / 8) Philox calls per four envs, not k.
+POMDP_HD uint32_t rotl32(uint32_t v, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(v, v, sh);
+#else
+    sh &= 31u;
+    return sh ? (v << sh) | (v >> (32u - sh)) : v;
+#endif
+}
+POMDP_HD uint32_t rock_reset_word(uint32_t slot_word, int rock) { return rotl32(slot_word, 4u * ((uint32_t)rock & 7u)); }
 POMDP_HD uint32_t rock_status_code(uint32_t w) { return w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u); }
 
 template <typename S, class D>
 POMDP_HD S rock_reset(const RockDev& p, const D& draw) {
     S s = (S)p.start;
-    for (int i = 0; i < p.k; ++i) s |= (S)rock_status_code(draw(i)) << (8 + 2 * i);
+    for (int i = 0; i < p.k; ++i) s |= (S)rock_status_code(rock_reset_word(draw(i >> 3), i)) << (8 + 2 * i);
     return s;
 }
-// Four envs of one aligned group: one Philox call per rock.
+// Four envs of one aligned group: one Philox call per eight rocks.
 template <typename S>
 POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t group, uint32_t step, S out[4]) {
     out[0] = out[1] = out[2] = out[3] = (S)p.start;
-    for (int i = 0; i < p.k; ++i) {
-        const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)i);
-        out[0] |= (S)rock_status_code(q.x) << (8 + 2 * i);
-        out[1] |= (S)rock_status_code(q.y) << (8 + 2 * i);
-        out[2] |= (S)rock_status_code(q.z) << (8 + 2 * i);
-        out[3] |= (S)rock_status_code(q.w) << (8 + 2 * i);
+    for (int j = 0; 8 * j < p.k; ++j) {
+        const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)j);
+        for (int i = 8 * j; i < 8 * j + 8 && i < p.k; ++i) {
+            out[0] |= (S)rock_status_code(rock_reset_word(q.x, i)) << (8 + 2 * i);
+            out[1] |= (S)rock_status_code(rock_reset_word(q.y, i)) << (8 + 2 * i);
+            out[2] |= (S)rock_status_code(rock_reset_word(q.z, i)) << (8 + 2 * i);
+            out[3] |= (S)rock_status_code(rock_reset_word(q.w, i)) << (8 + 2 * i);
+        }
     }
 }
 

@@ -711,21 +711,65 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 }
 
 // ---------------------------------------------------------------- belief histogram ---
-// Shared-memory histogram per CTA (<= 512 bins), one 64-bit global atomic per non-empty
-// bin per CTA at the end.
+// Warp-aggregated counting into a shared-memory histogram per CTA (<= 512 bins), then one 64-bit global atomic per
+// non-empty bin per CTA.  Two kinds of bins (pomdp_core.h: belief_bins is the definition the tests check against):
+//  * bit bins (Rock "rock i still good", BattleShip occupied cells, Network "machine m up"): one __ballot_sync per
+//    bit per warp iteration; lane (b & 31) keeps the running popcount of bit b in a register -- no atomics at all
+//    until the warp is done;
+//  * categorical bins (Rock agent cell, Tag agent/opponent cell, Tiger door): __match_any_sync groups the lanes that
+//    hit the same bin and the group's leader adds its size once, so a concentrated belief (every particle in the
+//    same cell) costs one shared-memory atomic per warp instead of a 32-way serialised one.
 #define POMDP_HIST_MAX_BINS 512
+__device__ __forceinline__ void hist_add_grouped(uint32_t* sh, bool valid, int bin) {
+    const unsigned m = __match_any_sync(0xffffffffu, valid ? bin : -1);
+    if (valid && (int)(threadIdx.x & 31) == __ffs((int)m) - 1) atomicAdd(&sh[bin], (uint32_t)__popc(m));
+}
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins) {
     __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
     for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n_bits = kind == POMDP_KIND_ROCK ? p0 : (kind == POMDP_KIND_BATTLESHIP || kind == POMDP_KIND_NETWORK) ? p0 : 0;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};                      // lane l: running count of bit bins l, l+32, l+64, l+96
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
-        uint32_t s[SHIP_WORDS];
-        for (int k = 0; k < words && k < SHIP_WORDS; ++k) s[k] = (uint32_t)state[i * words + k];
-        belief_bins(kind, p0, p1, s, [&](int bin) { atomicAdd(&sh[bin], 1u); });
+    const int64_t n_round = (n + 31) & ~(int64_t)31;         // whole warps iterate together (ballots)
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(state) & 7) == 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += nthreads) {
+        const bool valid = i < n;
+        uint32_t s[SHIP_WORDS] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (valid) {
+            if (words == 1) s[0] = (uint32_t)__ldcs(state + i);
+            else if (words == 2 && aligned8) { const int2 v = __ldcs(reinterpret_cast<const int2*>(state) + i); s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; }
+            else for (int k = 0; k < 4 && k < words; ++k) s[k] = (uint32_t)state[i * words + k];     // occupied words only
+        }
+        if (kind == POMDP_KIND_ROCK) {
+            const uint64_t v = (uint64_t)s[0] | ((uint64_t)s[1] << 32);
+            for (int b = 0; b < n_bits; ++b) {
+                const unsigned bal = __ballot_sync(0xffffffffu, ((v >> (8 + 2 * b)) & 3u) == 1u);
+                if (lane == b) acc[0] += (uint32_t)__popc(bal);
+            }
+            hist_add_grouped(sh, valid, p0 + (int)(v & 0xFF));
+        } else if (kind == POMDP_KIND_TAG) {
+            hist_add_grouped(sh, valid, (int)(s[0] & 31u));
+            hist_add_grouped(sh, valid, TAG_CELLS + (int)((s[0] >> 5) & 31u));
+        } else if (kind == POMDP_KIND_TIGER) {
+            hist_add_grouped(sh, valid, (int)(s[0] & 1u));
+        } else {                                             // BattleShip / Network: bit b of the first words
+            for (int b = 0; b < n_bits; ++b) {
+                const uint32_t w = (b >> 5) == 0 ? s[0] : (b >> 5) == 1 ? s[1] : (b >> 5) == 2 ? s[2] : s[3];
+                const unsigned bal = __ballot_sync(0xffffffffu, (w >> (b & 31)) & 1u);
+                if (lane == (b & 31)) {
+                    const uint32_t c = (uint32_t)__popc(bal);
+                    if ((b >> 5) == 0) acc[0] += c; else if ((b >> 5) == 1) acc[1] += c; else if ((b >> 5) == 2) acc[2] += c; else acc[3] += c;
+                }
+            }
+        }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], acc[j]);
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);

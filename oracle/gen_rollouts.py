@@ -22,6 +22,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import philox, ref_shim  # noqa: E402
+from oracle.pomdp_oracle import rock_reset_word  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SEED = 0x5EED
@@ -68,7 +69,8 @@ def gen_rock(E, out, tag, n, k, stochastic, M, T):
     def snap():
         return env.state.agent_pos.x, env.state.agent_pos.y, [r.status for r in env.state.rocks]
     for e in range(M):
-        d.clear(); d.feed(W(e, RESET_CTR, philox.DOMAIN_RESET, k))
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (k + 7) // 8)
+        d.clear(); d.feed([rock_reset_word(int(rw[r >> 3]), r) for r in range(k)])   # rock r's uniform(0,1), rock.py:78-80
         env.reset()
         d.clear()
         x0, y0, st0 = snap()
