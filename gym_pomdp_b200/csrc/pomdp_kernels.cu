@@ -711,18 +711,45 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 }
 
 // ---------------------------------------------------------------- belief histogram ---
-// Warp-aggregated counting into a shared-memory histogram per CTA (<= 512 bins), then one 64-bit global atomic per
-// non-empty bin per CTA.  Two kinds of bins (pomdp_core.h: belief_bins is the definition the tests check against):
-//  * bit bins (Rock "rock i still good", BattleShip occupied cells, Network "machine m up"): one __ballot_sync per
-//    bit per warp iteration; lane (b & 31) keeps the running popcount of bit b in a register -- no atomics at all
-//    until the warp is done;
-//  * categorical bins (Rock agent cell, Tag agent/opponent cell, Tiger door): __match_any_sync groups the lanes that
-//    hit the same bin and the group's leader adds its size once, so a concentrated belief (every particle in the
-//    same cell) costs one shared-memory atomic per warp instead of a 32-way serialised one.
+// Shared-memory histogram per CTA (<= 512 bins), then one 64-bit global atomic per non-empty bin per CTA
+// (pomdp_core.h: belief_bins is the definition the tests check against).  Two kinds of bins:
+//  * bit bins (Rock "rock i still good", Tiger door, BattleShip occupied cells, Network "machine m up"), which
+//    every particle hits with probability ~1/2 -- as shared-memory atomics these are 32-way same-address conflicts.
+//    Instead: one __ballot_sync per bit per warp iteration, and lane (b & 31) keeps the running popcount of bit b in a
+//    register; no atomic until the warp is done;
+//  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (spread over many
+//    addresses).
+// W = 1 states are read four envs per thread (16-byte loads) to keep enough bytes in flight.
 #define POMDP_HIST_MAX_BINS 512
-__device__ __forceinline__ void hist_add_grouped(uint32_t* sh, bool valid, int bin) {
-    const unsigned m = __match_any_sync(0xffffffffu, valid ? bin : -1);
-    if (valid && (int)(threadIdx.x & 31) == __ffs((int)m) - 1) atomicAdd(&sh[bin], (uint32_t)__popc(m));
+struct HistAcc {
+    uint32_t acc[4];   // lane l: running count of bit bins l, l+32, l+64, l+96
+    __device__ __forceinline__ void add(int b, unsigned ballot, int lane) {
+        if (lane == (b & 31)) {
+            const uint32_t c = (uint32_t)__popc(ballot);
+            if ((b >> 5) == 0) acc[0] += c; else if ((b >> 5) == 1) acc[1] += c; else if ((b >> 5) == 2) acc[2] += c; else acc[3] += c;
+        }
+    }
+};
+__device__ __forceinline__ void hist_one(int kind, int p0, int n_bits, bool valid, const uint32_t s[4], uint32_t* sh,
+                                         HistAcc& h, int lane) {
+    if (kind == POMDP_KIND_ROCK) {
+        const uint64_t v = (uint64_t)s[0] | ((uint64_t)s[1] << 32);
+        for (int b = 0; b < n_bits; ++b) h.add(b, __ballot_sync(0xffffffffu, ((v >> (8 + 2 * b)) & 3u) == 1u), lane);
+        if (valid) atomicAdd(&sh[p0 + (int)(v & 0xFF)], 1u);
+    } else if (kind == POMDP_KIND_TAG) {
+        if (valid) {
+            atomicAdd(&sh[s[0] & 31u], 1u);
+            atomicAdd(&sh[TAG_CELLS + ((s[0] >> 5) & 31u)], 1u);
+        }
+    } else if (kind == POMDP_KIND_TIGER) {
+        h.add(0, __ballot_sync(0xffffffffu, valid && !(s[0] & 1u)), lane);
+        h.add(1, __ballot_sync(0xffffffffu, valid && (s[0] & 1u)), lane);
+    } else {                                                 // BattleShip / Network: bit b of the first words
+        for (int b = 0; b < n_bits; ++b) {
+            const uint32_t w = (b >> 5) == 0 ? s[0] : (b >> 5) == 1 ? s[1] : (b >> 5) == 2 ? s[2] : s[3];
+            h.add(b, __ballot_sync(0xffffffffu, (w >> (b & 31)) & 1u), lane);
+        }
+    }
 }
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
@@ -731,48 +758,48 @@ pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ s
     for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int n_bits = kind == POMDP_KIND_ROCK ? p0 : (kind == POMDP_KIND_BATTLESHIP || kind == POMDP_KIND_NETWORK) ? p0 : 0;
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};                      // lane l: running count of bit bins l, l+32, l+64, l+96
+    const int n_bits = kind == POMDP_KIND_TAG ? 0 : kind == POMDP_KIND_TIGER ? 2 : p0;
+    HistAcc h = {{0u, 0u, 0u, 0u}};
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = (n + 31) & ~(int64_t)31;         // whole warps iterate together (ballots)
+    int64_t scalar_from = 0;
+    if (words == 1 && (reinterpret_cast<uintptr_t>(state) & 15) == 0) {
+        const int64_t n_groups = n >> 2;
+        const int64_t g_round = (n_groups + 31) & ~(int64_t)31;          // whole warps iterate together (ballots)
+        for (int64_t g = tid; g < g_round; g += nthreads) {
+            const bool valid = g < n_groups;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (valid) v = ld_stream4(state + (g << 2));
+            const uint32_t e[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t s[4] = {e[j], 0u, 0u, 0u};
+                hist_one(kind, p0, n_bits, valid, s, sh, h, lane);
+            }
+        }
+        scalar_from = n_groups << 2;
+    }
+    const int64_t rem = n - scalar_from;
+    const int64_t r_round = (rem + 31) & ~(int64_t)31;
     const bool aligned8 = (reinterpret_cast<uintptr_t>(state) & 7) == 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += nthreads) {
-        const bool valid = i < n;
-        uint32_t s[SHIP_WORDS] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (int64_t r = tid; r < r_round; r += nthreads) {
+        const int64_t i = scalar_from + r;
+        const bool valid = r < rem;
+        uint32_t s[4] = {0u, 0u, 0u, 0u};
         if (valid) {
             if (words == 1) s[0] = (uint32_t)__ldcs(state + i);
             else if (words == 2 && aligned8) { const int2 v = __ldcs(reinterpret_cast<const int2*>(state) + i); s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; }
-            else for (int k = 0; k < 4 && k < words; ++k) s[k] = (uint32_t)state[i * words + k];     // occupied words only
+            else for (int k = 0; k < 4 && k < words; ++k) s[k] = (uint32_t)state[i * words + k];     // BattleShip: occupied words only
         }
-        if (kind == POMDP_KIND_ROCK) {
-            const uint64_t v = (uint64_t)s[0] | ((uint64_t)s[1] << 32);
-            for (int b = 0; b < n_bits; ++b) {
-                const unsigned bal = __ballot_sync(0xffffffffu, ((v >> (8 + 2 * b)) & 3u) == 1u);
-                if (lane == b) acc[0] += (uint32_t)__popc(bal);
-            }
-            hist_add_grouped(sh, valid, p0 + (int)(v & 0xFF));
-        } else if (kind == POMDP_KIND_TAG) {
-            hist_add_grouped(sh, valid, (int)(s[0] & 31u));
-            hist_add_grouped(sh, valid, TAG_CELLS + (int)((s[0] >> 5) & 31u));
-        } else if (kind == POMDP_KIND_TIGER) {
-            hist_add_grouped(sh, valid, (int)(s[0] & 1u));
-        } else {                                             // BattleShip / Network: bit b of the first words
-            for (int b = 0; b < n_bits; ++b) {
-                const uint32_t w = (b >> 5) == 0 ? s[0] : (b >> 5) == 1 ? s[1] : (b >> 5) == 2 ? s[2] : s[3];
-                const unsigned bal = __ballot_sync(0xffffffffu, (w >> (b & 31)) & 1u);
-                if (lane == (b & 31)) {
-                    const uint32_t c = (uint32_t)__popc(bal);
-                    if ((b >> 5) == 0) acc[0] += c; else if ((b >> 5) == 1) acc[1] += c; else if ((b >> 5) == 2) acc[2] += c; else acc[3] += c;
-                }
-            }
-        }
+        hist_one(kind, p0, n_bits, valid, s, sh, h, lane);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        if (acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], acc[j]);
+        if (h.acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], h.acc[j]);
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+    (void)p1;
 }
 
 // ============================================================================ host ===
