@@ -279,10 +279,44 @@ POMDP_HD uint32_t rotl32(uint32_t v, uint32_t sh) {
 POMDP_HD uint32_t rock_reset_word(uint32_t slot_word, int rock) { return rotl32(slot_word, 4u * ((uint32_t)rock & 7u)); }
 POMDP_HD uint32_t rock_status_code(uint32_t w) { return w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u); }
 
+POMDP_HD uint32_t brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+// The eight 2-bit status codes of one reset word at once (rock j of the word in bits 2j..2j+1): rock j's r = rotl32(w, 4j)
+// compares with 2^31 through its top bit = bit 31 - 4j of w: set -> good (01), clear -> bad (11); the tie r == 2^31
+// (collected, 00) needs w to be exactly that single bit.  Equals rock_status_code(rock_reset_word(w, j)) for every w.
+POMDP_HD uint32_t rock_reset_codes8(uint32_t w) {
+    uint32_t x = brev32(w) & 0x11111111u;                  // bit 4j  = deciding bit of rock j
+    x = (x | (x >> 2)) & 0x05050505u;                       // nibble-spaced -> 2-spaced, byte by byte
+    x = (x | (x >> 4)) & 0x00550055u;
+    x = (x | (x >> 8)) & 0x00005555u;                       // bit 2j = deciding bit of rock j
+    uint32_t codes = 0x5555u | ((~x & 0x5555u) << 1);
+    if ((w & (w - 1u)) == 0u && (w & 0x88888888u)) {        // a single bit at a deciding position: that rock ties
+#if defined(__CUDA_ARCH__)
+        const int pos = 31 - __clz((int)w);
+#else
+        const int pos = 31 - __builtin_clz(w);
+#endif
+        codes &= ~(3u << (2 * ((31 - pos) >> 2)));
+    }
+    return codes;
+}
+
 template <typename S, class D>
 POMDP_HD S rock_reset(const RockDev& p, const D& draw) {
     S s = (S)p.start;
-    for (int i = 0; i < p.k; ++i) s |= (S)rock_status_code(rock_reset_word(draw(i >> 3), i)) << (8 + 2 * i);
+    for (int j = 0; 8 * j < p.k; ++j) {
+        const int cnt = p.k - 8 * j < 8 ? p.k - 8 * j : 8;
+        s |= (S)(rock_reset_codes8(draw(j)) & ((1u << (2 * cnt)) - 1u)) << (8 + 16 * j);
+    }
     return s;
 }
 // Four envs of one aligned group: one Philox call per eight rocks.
@@ -291,12 +325,12 @@ POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t grou
     out[0] = out[1] = out[2] = out[3] = (S)p.start;
     for (int j = 0; 8 * j < p.k; ++j) {
         const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)j);
-        for (int i = 8 * j; i < 8 * j + 8 && i < p.k; ++i) {
-            out[0] |= (S)rock_status_code(rock_reset_word(q.x, i)) << (8 + 2 * i);
-            out[1] |= (S)rock_status_code(rock_reset_word(q.y, i)) << (8 + 2 * i);
-            out[2] |= (S)rock_status_code(rock_reset_word(q.z, i)) << (8 + 2 * i);
-            out[3] |= (S)rock_status_code(rock_reset_word(q.w, i)) << (8 + 2 * i);
-        }
+        const int cnt = p.k - 8 * j < 8 ? p.k - 8 * j : 8;
+        const uint32_t m = (1u << (2 * cnt)) - 1u;
+        out[0] |= (S)(rock_reset_codes8(q.x) & m) << (8 + 16 * j);
+        out[1] |= (S)(rock_reset_codes8(q.y) & m) << (8 + 16 * j);
+        out[2] |= (S)(rock_reset_codes8(q.z) & m) << (8 + 16 * j);
+        out[3] |= (S)(rock_reset_codes8(q.w) & m) << (8 + 16 * j);
     }
 }
 

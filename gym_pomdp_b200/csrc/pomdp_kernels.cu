@@ -751,7 +751,7 @@ __device__ __forceinline__ void hist_one(int kind, int p0, int n_bits, bool vali
         }
     }
 }
-__global__ void __launch_bounds__(POMDP_THREADS)
+__global__ void __launch_bounds__(1024)
 pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins) {
     __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
@@ -1400,8 +1400,11 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     const int bins = host::hist_bins(kind, p0, p1);
     if (n == 0) return 0;
     auto k = pomdp_belief_hist_kernel;
-    const int grid = grid_for(k, n);
-    k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(kind, p0, p1, state, words, n, (unsigned long long*)hist, bins);
+    // one 1024-thread CTA per SM: every CTA ends with one global atomic per non-empty bin, all CTAs on the same few
+    // hundred addresses, so the CTA count (not the batch) sets that cost
+    const int64_t want = (n + 4095) / 4096;
+    const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());
+    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(kind, p0, p1, state, words, n, (unsigned long long*)hist, bins);
     return finish("pomdp_belief_hist");
 }
 
