@@ -277,32 +277,46 @@ def run_b200(args):
     value = n_gpus * B * K / (ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------
+    # env.simulate_host(packed=True): pinned host (state, action) -> chunked H2D / kernel / D2H on three streams ->
+    # pinned host (next_state, result) with result = obs | flags << 8 | reward << 16 (include/pomdp_b200.h).  The
+    # unpacked variant (four result arrays, 16 B/env back) is timed too and reported as e2e.unpacked.
     E = max(1, args.e2e_steps)
     pin = dict(device="cpu", pin_memory=True)
     s0, a0, _ = sets[0]
     h_state, h_action = s0.cpu().pin_memory(), a0.cpu().pin_memory()
     h_out = (torch.empty(s0.shape, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin),
              torch.empty(B, dtype=torch.float32, **pin), torch.empty(B, dtype=torch.int32, **pin))
-    for i in range(3):
-        env.simulate_host(h_state, h_action, h_out, step_ctr=i + 1)
-    barrier()
-    t0 = time.perf_counter()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ee0.record()
-    for i in range(E):
-        env.simulate_host(h_state, h_action, h_out, step_ctr=i + 1)
-    ee1.record()
-    torch.cuda.synchronize()
-    e2e_ms = ee0.elapsed_time(ee1)
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    h_packed = (torch.empty(s0.shape, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin))
+
+    def time_e2e(packed):
+        out = h_packed if packed else h_out
+        for i in range(3):
+            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed)
+        barrier()
+        t0 = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
+        for i in range(E):
+            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed)
+        ee1.record()
+        torch.cuda.synchronize()
+        ms_ = ee0.elapsed_time(ee1)
+        wall = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms_], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_, wall
+
+    e2e_un_ms, _ = time_e2e(False)
+    e2e_ms, e2e_wall = time_e2e(True)
     e2e_value = n_gpus * B * E / (e2e_ms * 1e-3)
-    # sanity: the host result of the last e2e step equals the device path on the same inputs
+    # sanity: the host results of the last e2e steps equal the device path on the same inputs
     chk = env.simulate(s0, a0, step_ctr=E)
     assert torch.equal(chk[1].cpu(), h_out[1]) and torch.equal(chk[0].cpu(), h_out[0]), "e2e result != device result"
+    p_ob, p_rw, p_fl = env.unpack_result(h_packed[1])
+    assert torch.equal(h_packed[0], h_out[0]) and torch.equal(p_ob, h_out[1]) and torch.equal(p_rw, h_out[2]) \
+        and torch.equal(p_fl, h_out[3]), "packed e2e result != unpacked e2e result"
 
     if rank != 0:
         if world > 1:
@@ -343,9 +357,13 @@ def run_b200(args):
         "dtype": "int32", "data": "synthetic", "config": cfg,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (4 * words + 4),
-                "d2h_bytes_per_step": B * (4 * words + 12), "steps": E, "ms_per_step": e2e_ms / E,
+                "d2h_bytes_per_step": B * (4 * words + 4), "steps": E, "ms_per_step": e2e_ms / E,
                 "wall_ms_per_step": e2e_wall / E,
-                "path": "env.simulate_host: pinned host (state, action) -> 3-stream chunked H2D/kernel/D2H -> pinned host results"},
+                "path": "env.simulate_host(packed=True): pinned host (state, action) -> 3-stream chunked H2D/kernel/D2H -> "
+                        "pinned host (next_state, result = obs | flags << 8 | reward << 16)",
+                "unpacked": {"value": n_gpus * B * E / (e2e_un_ms * 1e-3), "ms_per_step": e2e_un_ms / E,
+                             "d2h_bytes_per_step": B * (4 * words + 12),
+                             "path": "env.simulate_host: four result arrays (next_state, obs, reward, flags) back"}},
         "clocks": clocks, "gpu_launches": K,
     }
     print(json.dumps(line))

@@ -59,6 +59,8 @@ _RESET_TAIL = [_P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 _POLICY_TAIL = [_P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 _ROLLOUT_TAIL = [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_int32, c_double, c_void_p]
 
+_STEPP_TAIL = [_P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
+
 _PROTOTYPES = {
     "pomdp_abi_version": (c_int32, []),
     "pomdp_last_error": (c_char_p, []),
@@ -82,6 +84,10 @@ _PROTOTYPES = {
     "pomdp_tiger_reset": (c_int32, [POINTER(TigerParams)] + _RESET_TAIL),
     "pomdp_network_step": (c_int32, [POINTER(NetworkParams)] + _STEP_TAIL),
     "pomdp_network_reset": (c_int32, [POINTER(NetworkParams), _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_step_packed": (c_int32, [POINTER(RockParams), _P] + _STEPP_TAIL),
+    "pomdp_tag_step_packed": (c_int32, [POINTER(TagParams), _P] + _STEPP_TAIL),
+    "pomdp_tiger_step_packed": (c_int32, [POINTER(TigerParams)] + _STEPP_TAIL),
+    "pomdp_network_step_packed": (c_int32, [POINTER(NetworkParams)] + _STEPP_TAIL),
     "pomdp_rock_policy": (c_int32, [POINTER(RockParams), _P] + _POLICY_TAIL),
     "pomdp_rock_rollout": (c_int32, [POINTER(RockParams), _P] + _ROLLOUT_TAIL),
     "pomdp_tag_policy": (c_int32, [POINTER(TagParams), _P] + _POLICY_TAIL),

@@ -941,6 +941,19 @@ POMDP_HD double battleship_obs_prob(const ShipDev& p, const uint32_t w[SHIP_WORD
     return ob == 0 ? 1.0 : 0.0;
 }
 
+// ========================================================================== packed results ===
+// Compact result word of the *_step_packed entry points (halves the bytes a host caller has to fetch):
+//   bits 0-7 obs, bits 8-15 flags, bits 16-31 the reward as a signed 16-bit count of reward UNITS -- 1 for
+//   Rock / Tag / BattleShip / Tiger (their rewards are integers), 0.1 for Network (rewards are tenths).
+POMDP_HD int32_t pack_result(int32_t ob, int32_t units, int32_t fl) {
+    return (int32_t)(((uint32_t)ob & 0xFFu) | (((uint32_t)fl & 0xFFu) << 8) | ((uint32_t)units << 16));
+}
+POMDP_HD int32_t reward_units_int(float rw) { return (int32_t)rw; }
+POMDP_HD int32_t reward_units_tenths(float rw) {
+    const float t = rw * 10.0f;
+    return (int32_t)(t < 0.f ? t - 0.5f : t + 0.5f);
+}
+
 // ========================================================================= rollouts ===
 // what a POMCP simulation does with these envs (the loops at rock.py:563-572 and
 // tag.py:310-316): until done or T steps,  a = np.random.choice(env._generate_legal());  ob, rw, done = env.step(a);

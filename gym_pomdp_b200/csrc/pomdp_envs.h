@@ -30,6 +30,7 @@ struct RockEnvT {
     }
     static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }          // integral rewards (rock.py:141-169)
+    static POMDP_HD int32_t reward_units(float rw) { return reward_units_int(rw); }
     static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const S s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, S s2[4],
                                                  int32_t ob[4], float rw[4], int32_t fl[4]) {
@@ -92,6 +93,7 @@ struct TagEnvT {
     static POMDP_HD void legal_mask(const Params&, const unsigned char*, State, uint32_t* m) { m[0] = 31u; }   // tag.py:228-229
     static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }
+    static POMDP_HD int32_t reward_units(float rw) { return reward_units_int(rw); }
     static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
@@ -153,6 +155,7 @@ struct TigerEnvP {
     static POMDP_HD void legal_mask(const Params&, const unsigned char*, State, uint32_t* m) { m[0] = 7u; }    // tiger.py:111-112
     static POMDP_HD int mask_words(const Params&) { return 1; }
     static POMDP_HD double reward64(float rw) { return (double)rw; }
+    static POMDP_HD int32_t reward_units(float rw) { return reward_units_int(rw); }
     static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
@@ -198,6 +201,7 @@ struct NetworkEnvP {
     static POMDP_HD int mask_words(const Params& p) { return (2 * p.n + 1 + 31) / 32; }
     // the reference's reward is the Python double s - 0.1 / s - 2.5 / s == tenths / 10.0 (network.py:87-108); the
     // float32 the step kernel emits determines the integer number of tenths uniquely
+    static POMDP_HD int32_t reward_units(float rw) { return reward_units_tenths(rw); }
     static POMDP_HD double reward64(float rw) {
         const double t = (double)rw * 10.0;
         return (double)(long long)(t < 0 ? t - 0.5 : t + 0.5) / 10.0;

@@ -137,7 +137,9 @@ __device__ __forceinline__ void store_state1(int32_t* base, int64_t i, uint64_t 
 // draw slot per group).  The loop is software-pipelined: the loads of a thread's next group
 // are issued before the current group is computed, so two groups' worth of bytes per
 // thread are in flight.  Otherwise: scalar thread-per-env path (oddly offset views).
-template <class Env, bool kVec>
+// kPacked: obs / reward / flags leave as ONE int32 stream (pack_result, pomdp_core.h) written to `obs`; `reward` and
+// `flags` are unused.  16 instead of 24 bytes per env-step on the device, 8 instead of 16 for a host caller to fetch.
+template <class Env, bool kVec, bool kPacked = false>
 __global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
 pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
                   const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
@@ -189,9 +191,16 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
             float rw[4];
             Env::step4(p, lut, s, a, seed, group0 + (uint64_t)g, step_ctr, s2, ob, rw, fl);
             StateVec<S>::store(next_state, i, s2);
-            st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
-            st_stream4(reward + i, make_float4(rw[0], rw[1], rw[2], rw[3]));
-            st_stream4(flags + i, make_int4(fl[0], fl[1], fl[2], fl[3]));
+            if (kPacked) {
+                st_stream4(obs + i, make_int4(pack_result(ob[0], Env::reward_units(rw[0]), fl[0]),
+                                              pack_result(ob[1], Env::reward_units(rw[1]), fl[1]),
+                                              pack_result(ob[2], Env::reward_units(rw[2]), fl[2]),
+                                              pack_result(ob[3], Env::reward_units(rw[3]), fl[3])));
+            } else {
+                st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
+                st_stream4(reward + i, make_float4(rw[0], rw[1], rw[2], rw[3]));
+                st_stream4(flags + i, make_int4(fl[0], fl[1], fl[2], fl[3]));
+            }
             cur_s = nxt_s;
             cur_a = nxt_a;
             g = gn;
@@ -201,7 +210,9 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
         if (i < n) {
             S s2; int32_t ob, fl; float rw;
             Env::step1(p, lut, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
-            store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
+            store_state1(next_state, i, s2);
+            if (kPacked) obs[i] = pack_result(ob, Env::reward_units(rw), fl);
+            else { obs[i] = ob; reward[i] = rw; flags[i] = fl; }
         }
     } else {
         for (int64_t i = tid; i < n; i += nthreads) {
@@ -210,7 +221,9 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
             if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
             S s2; int32_t ob, fl; float rw;
             Env::step1(p, lut, s, a, seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
-            store_state1(next_state, i, s2); obs[i] = ob; reward[i] = rw; flags[i] = fl;
+            store_state1(next_state, i, s2);
+            if (kPacked) obs[i] = pack_result(ob, Env::reward_units(rw), fl);
+            else { obs[i] = ob; reward[i] = rw; flags[i] = fl; }
         }
     }
     // a CTA must not exit while its bulk copy may still be in flight
@@ -878,11 +891,12 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t s
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-template <class Env>
+template <class Env, bool kPacked = false>
 int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
                 const int32_t* state,
                 const int32_t* action, int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
                 int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
+    if (kPacked) { reward = reinterpret_cast<float*>(obs); flags = obs; }   // one result stream; keeps the checks below uniform
     int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
     if (rc) return rc;
     if (n == 0) return 0;
@@ -893,13 +907,13 @@ int launch_step(const typename Env::Params& p, const void* d_table, uint32_t tab
     const size_t smem = Env::kTable ? smem_bytes : 0;
     const PhiloxKey key = philox_key(seed);
     if (aligned16(state, action, next_state, obs, reward, flags) && (goff & 3) == 0) {
-        auto k = pomdp_step_kernel<Env, true>;
+        auto k = pomdp_step_kernel<Env, true, kPacked>;
         if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, (n + 3) >> 2, POMDP_STEP_THREADS, smem);
         launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
                    (uint64_t)goff, key, step_ctr, table_bytes);
     } else {
-        auto k = pomdp_step_kernel<Env, false>;
+        auto k = pomdp_step_kernel<Env, false, kPacked>;
         if ((rc = allow_smem(k, smem))) return rc;
         const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
         launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
@@ -1186,6 +1200,55 @@ int pomdp_battleship_reset_rejection(const PomdpBattleshipParams* q, int32_t* st
     const int grid = grid_for(k, n);
     k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     return finish("pomdp_battleship_reset_rejection");
+}
+
+// ---- step with the compact result stream (obs | flags << 8 | reward_units << 16)
+int pomdp_rock_step_packed(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                           int32_t* next_state, int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                           void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+#define POMDP_ROCK_STEPP(S, STOCH)                                                                                    \
+    return launch_step<RockEnvT<S, STOCH>, true>(d, d_table, d.table_bytes, d.smem_bytes, state, action, next_state,  \
+                                                 result, nullptr, nullptr, n, goff, seed, step_ctr, stream,          \
+                                                 "pomdp_rock_step_packed")
+    if (host::rock_words(q) == 1) {
+        if (d.stochastic) POMDP_ROCK_STEPP(uint32_t, true);
+        POMDP_ROCK_STEPP(uint32_t, false);
+    }
+    if (d.stochastic) POMDP_ROCK_STEPP(uint64_t, true);
+    POMDP_ROCK_STEPP(uint64_t, false);
+#undef POMDP_ROCK_STEPP
+}
+int pomdp_tag_step_packed(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                          int32_t* next_state, int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                          void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    const uint32_t tb = (uint32_t)sizeof(TagTables);
+    if (d.n_opp == 1)
+        return launch_step<TagEnvT<1>, true>(d, d_table, tb, tb, state, action, next_state, result, nullptr, nullptr, n, goff,
+                                             seed, step_ctr, stream, "pomdp_tag_step_packed");
+    return launch_step<TagEnvT<4>, true>(d, d_table, tb, tb, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
+                                         step_ctr, stream, "pomdp_tag_step_packed");
+}
+int pomdp_tiger_step_packed(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                            int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_step<TigerEnvP, true>(d, nullptr, 0, 0, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
+                                        step_ctr, stream, "pomdp_tiger_step_packed");
+}
+int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                              int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    return launch_step<NetworkEnvP, true>(d, nullptr, 0, 0, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
+                                          step_ctr, stream, "pomdp_network_step_packed");
 }
 
 // ---- uniform-legal policy and fused rollouts

@@ -18,6 +18,7 @@ OFF, ON, NULL = 0, 1, 2   # network.py:12-15
 class NetworkEnv(BatchedPomdpEnv):
     kind = _lib.KIND_NETWORK
     _abi = "network"
+    _reward_unit = 10          # packed results carry the reward in tenths (network.py:104, 108)
 
     def __init__(self, n_machines=10, problem_type=3, depth=60, batch_size=None, device="cuda", seed=0,
                  global_offset=0):

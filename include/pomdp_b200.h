@@ -215,6 +215,29 @@ int pomdp_network_reset(const PomdpNetworkParams* params,
                         int32_t* state, int32_t* obs, const uint8_t* mask,
                         int64_t n, void* stream);
 
+/* ----------------------------------------------------- step with a compact result --- */
+/* Same transition as pomdp_E_step (same draws, same next_state), but obs / reward / flags leave as
+ * ONE int32 stream:   result[i] = obs | flags << 8 | reward_units << 16
+ * with reward_units a signed 16-bit count of reward units: 1 for Rock, Tag and Tiger (integer
+ * rewards), 0.1 for Network (rewards are tenths: s - 0.1, s - 2.5).  16 instead of 24 bytes per
+ * env-step of device traffic, and 8 instead of 16 bytes per env for a host caller to fetch over
+ * PCIe.  (BattleShip's 32-byte boards dominate its traffic; it has no packed variant.)          */
+#define POMDP_RESULT_OBS(r)    ((int32_t)((uint32_t)(r) & 0xFFu))
+#define POMDP_RESULT_FLAGS(r)  ((int32_t)(((uint32_t)(r) >> 8) & 0xFFu))
+#define POMDP_RESULT_UNITS(r)  ((int32_t)(r) >> 16)
+int pomdp_rock_step_packed(const PomdpRockParams* params, const void* d_table,
+                           const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* result,
+                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_tag_step_packed(const PomdpTagParams* params, const void* d_table,
+                          const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* result,
+                          int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_tiger_step_packed(const PomdpTigerParams* params,
+                            const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* result,
+                            int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_network_step_packed(const PomdpNetworkParams* params,
+                              const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* result,
+                              int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+
 /* ------------------------------------------- uniform-legal policy and fused rollouts --- */
 /* What a POMCP / Monte-Carlo caller does with these envs between two tree nodes (the loops at
  * rock.py:563-572 and tag.py:310-316):

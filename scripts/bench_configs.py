@@ -136,6 +136,21 @@ def main():
                      "launches": K, "buffer_sets": n_sets})
         print(json.dumps(rows[-1]), flush=True)
 
+        if name != "battleship":
+            psets = [(torch.empty_like(sets[0][0]), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
+
+            def step_packed(i):
+                s, a, _ = sets[i % n_sets]
+                env.simulate(s, a, out=psets[i % n_sets], step_ctr=i + 1, packed=True)
+            ms = time_graph(step_packed, K, dev)
+            pb = 8 * W + 8
+            gbs = B * pb / (ms * 1e-3) / 1e9
+            rows.append({"config": label, "kernel": "step_packed", "batch": B, "state_words": W, "bytes_per_unit": pb,
+                         "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+                         "note": "obs|flags|reward in one int32 stream: 8W+8 bytes per env-step"})
+            print(json.dumps(rows[-1]), flush=True)
+            del psets
+
         # reset: bytes written = state words + obs (+ flags for BattleShip)
         reset_bytes = 4 * W + 4 + (4 if name == "battleship" else 0)
         rsets = [(torch.empty_like(sets[0][0]), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]

@@ -105,6 +105,22 @@ int legal_mask_host(const typename Env::Params& d, const void* table, const int3
 }
 }  // namespace
 
+namespace {
+// *_step_packed on the host: the unpacked entry point, then pack_result per env (what the kernels' epilogue does)
+template <class Env, class F>
+int step_packed_host(F step, const int32_t* state, const int32_t* action, int32_t* next, int32_t* result, int64_t n) {
+    if (n <= 0) return step(state, action, next, result, (float*)result, result, n);
+    int32_t* ob = new int32_t[n];
+    int32_t* fl = new int32_t[n];
+    float* rw = new float[n];
+    const int rc = step(state, action, next, ob, rw, fl, n);
+    if (!rc)
+        for (int64_t i = 0; i < n; ++i) result[i] = pack_result(ob[i], Env::reward_units(rw[i]), fl[i]);
+    delete[] ob; delete[] fl; delete[] rw;
+    return rc;
+}
+}  // namespace
+
 extern "C" {
 
 int pomdp_abi_version(void) { return POMDP_ABI_VERSION; }
@@ -545,6 +561,39 @@ int pomdp_battleship_legal_mask(const PomdpBattleshipParams* q, const int32_t* s
             mask[i * words + k] = ~(uint32_t)state[i * SHIP_WORDS + 4 + k] & valid;
         }
     return 0;
+}
+
+int pomdp_rock_step_packed(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
+                           int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    if (n > 0 && !result) return host::fail(POMDP_E_BADARG, "a required array pointer is NULL");
+    return step_packed_host<RockEnvT<uint32_t, false>>(
+        [&](const int32_t* s, const int32_t* a, int32_t* nx, int32_t* ob, float* rw, int32_t* fl, int64_t m) {
+            return pomdp_rock_step(q, table, s, a, nx, ob, rw, fl, m, goff, seed, step, nullptr);
+        }, state, action, next, result, n);
+}
+int pomdp_tag_step_packed(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
+                          int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    if (n > 0 && !result) return host::fail(POMDP_E_BADARG, "a required array pointer is NULL");
+    return step_packed_host<TagEnvT<1>>(
+        [&](const int32_t* s, const int32_t* a, int32_t* nx, int32_t* ob, float* rw, int32_t* fl, int64_t m) {
+            return pomdp_tag_step(q, table, s, a, nx, ob, rw, fl, m, goff, seed, step, nullptr);
+        }, state, action, next, result, n);
+}
+int pomdp_tiger_step_packed(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* result,
+                            int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    if (n > 0 && !result) return host::fail(POMDP_E_BADARG, "a required array pointer is NULL");
+    return step_packed_host<TigerEnvP>(
+        [&](const int32_t* s, const int32_t* a, int32_t* nx, int32_t* ob, float* rw, int32_t* fl, int64_t m) {
+            return pomdp_tiger_step(q, s, a, nx, ob, rw, fl, m, goff, seed, step, nullptr);
+        }, state, action, next, result, n);
+}
+int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next,
+                              int32_t* result, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    if (n > 0 && !result) return host::fail(POMDP_E_BADARG, "a required array pointer is NULL");
+    return step_packed_host<NetworkEnvP>(
+        [&](const int32_t* s, const int32_t* a, int32_t* nx, int32_t* ob, float* rw, int32_t* fl, int64_t m) {
+            return pomdp_network_step(q, s, a, nx, ob, rw, fl, m, goff, seed, step, nullptr);
+        }, state, action, next, result, n);
 }
 
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {

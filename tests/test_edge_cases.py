@@ -300,3 +300,45 @@ def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
         occ, vis, rem, done = a.unpack(sa)
         n_cells = sum(range(2, max_len + 1))
         assert (occ.reshape(B, -1).sum(1) == n_cells).all() and (rem == n_cells).all()
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if n != "ship"])
+def test_packed_step_equals_unpacked(backend, name):
+    """*_step_packed: same transition, obs | flags << 8 | reward_units << 16 in one stream -- on the vector path, the
+    scalar path (odd offset) and with error flags present."""
+    N = 1003
+    env = make_all(backend, N)[name]
+    rs = np.random.RandomState(13)
+    state, action = random_inputs(env, name, N, rs, backend)
+    action[5] = env.action_space.n                               # BAD_ACTION survives the packing
+    ref = env.simulate(state, action, step_ctr=8)
+    ns, res = env.simulate(state, action, step_ctr=8, packed=True)
+    ob, rw, fl = env.unpack_result(res)
+    assert torch.equal(ns, ref[0]) and torch.equal(ob, ref[1]) and torch.equal(rw, ref[2]) and torch.equal(fl, ref[3])
+    env.global_offset = 3
+    ref = env.simulate(state[3:], action[3:], step_ctr=8)
+    ns, res = env.simulate(state[3:], action[3:], step_ctr=8, packed=True)
+    env.global_offset = 0
+    ob, rw, fl = env.unpack_result(res)
+    assert torch.equal(ns, ref[0]) and torch.equal(ob, ref[1]) and torch.equal(rw, ref[2]) and torch.equal(fl, ref[3])
+    # in place
+    work = state.clone()
+    env.simulate(work, action, out=(work, torch.empty(N, dtype=torch.int32, device=backend)), step_ctr=8, packed=True)
+    assert torch.equal(work, env.simulate(state, action, step_ctr=8)[0])
+
+
+def test_packed_reward_range(backend):
+    """Extreme rewards fit the signed 16-bit unit field: Rock -100, Network 11 machines' worth minus a reboot."""
+    env = make_all(backend, 8)["rock"]
+    s = env.pack([0] * 8, [0] * 8, np.ones((8, 11), int))
+    ns, res = env.simulate(s, torch.full((8,), 2, dtype=torch.int32, device=backend), step_ctr=1, packed=True)   # SOUTH off the board
+    ob, rw, fl = env.unpack_result(res)
+    assert (rw == -100).all() and (fl == 1).all() and (ob == 0).all()
+    net = make_all(backend, 8)["network"]
+    s = torch.full((8,), 1023, dtype=torch.int32, device=backend)
+    a = torch.tensor([20, 0, 1, 3, 20, 20, 5, 7], dtype=torch.int32, device=backend)
+    ref = net.simulate(s, a, step_ctr=1)
+    ns, res = net.simulate(s, a, step_ctr=1, packed=True)
+    ob, rw, fl = net.unpack_result(res)
+    assert torch.equal(rw, ref[2]) and torch.equal(ob, ref[1])
+    assert rw.tolist() == [np.float32(v) for v in (11.0, 10.9, 8.5, 8.5, 11.0, 11.0, 8.5, 8.5)]
