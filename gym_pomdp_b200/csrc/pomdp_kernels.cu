@@ -734,45 +734,54 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 //    addresses).
 // W = 1 states are read four envs per thread (16-byte loads) to keep enough bytes in flight.
 #define POMDP_HIST_MAX_BINS 512
-struct HistAcc {
-    uint32_t acc[4];   // lane l: running count of bit bins l, l+32, l+64, l+96
-    __device__ __forceinline__ void add(int b, unsigned ballot, int lane) {
-        if (lane == (b & 31)) {
-            const uint32_t c = (uint32_t)__popc(ballot);
-            if ((b >> 5) == 0) acc[0] += c; else if ((b >> 5) == 1) acc[1] += c; else if ((b >> 5) == 2) acc[2] += c; else acc[3] += c;
+// Counts, for every bit position b < nb of `bits` (bit b * STRIDE), the lanes of the warp that have it set: one VOTE
+// per bit; lane b keeps ballot b and adds its popcount to its register counter once per word.
+template <int STRIDE>
+__device__ __forceinline__ uint32_t warp_bit_counts(uint32_t bits, int nb, int lane) {
+    uint32_t mine = 0;
+#pragma unroll
+    for (int b = 0; b < 32 / STRIDE; ++b)
+        if (b < nb) {                                        // nb is warp-uniform
+            const unsigned bal = __ballot_sync(0xffffffffu, (bits >> (b * STRIDE)) & 1u);
+            mine = lane == b ? bal : mine;
         }
-    }
-};
-__device__ __forceinline__ void hist_one(int kind, int p0, int n_bits, bool valid, const uint32_t s[4], uint32_t* sh,
-                                         HistAcc& h, int lane) {
-    if (kind == POMDP_KIND_ROCK) {
-        const uint64_t v = (uint64_t)s[0] | ((uint64_t)s[1] << 32);
-        for (int b = 0; b < n_bits; ++b) h.add(b, __ballot_sync(0xffffffffu, ((v >> (8 + 2 * b)) & 3u) == 1u), lane);
-        if (valid) atomicAdd(&sh[p0 + (int)(v & 0xFF)], 1u);
-    } else if (kind == POMDP_KIND_TAG) {
+    return (uint32_t)__popc(mine);
+}
+template <int KIND>
+__device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4], uint32_t* sh, uint32_t acc[4], int lane) {
+    if (KIND == POMDP_KIND_ROCK) {                           // p0 = k rocks; bit 2i of `good` = rock i's status is +1 (code 01)
+        const uint32_t good0 = (s[0] >> 8) & ~(s[0] >> 9) & 0x00555555u;                       // rocks 0..11 (bits 8..31 of word 0)
+        acc[0] += warp_bit_counts<2>(good0, p0 < 12 ? p0 : 12, lane);
+        if (p0 > 12) {                                                                         // rocks 12..15: bits 0..7 of word 1
+            const uint32_t good1 = s[1] & ~(s[1] >> 1) & 0x00000055u;
+            const uint32_t c = warp_bit_counts<2>(good1, p0 - 12, lane);                       // lane j holds rock 12 + j
+            acc[1] += c;
+        }
+        if (valid) atomicAdd(&sh[p0 + (int)(s[0] & 0xFFu)], 1u);
+    } else if (KIND == POMDP_KIND_TAG) {
         if (valid) {
             atomicAdd(&sh[s[0] & 31u], 1u);
             atomicAdd(&sh[TAG_CELLS + ((s[0] >> 5) & 31u)], 1u);
         }
-    } else if (kind == POMDP_KIND_TIGER) {
-        h.add(0, __ballot_sync(0xffffffffu, valid && !(s[0] & 1u)), lane);
-        h.add(1, __ballot_sync(0xffffffffu, valid && (s[0] & 1u)), lane);
-    } else {                                                 // BattleShip / Network: bit b of the first words
-        for (int b = 0; b < n_bits; ++b) {
-            const uint32_t w = (b >> 5) == 0 ? s[0] : (b >> 5) == 1 ? s[1] : (b >> 5) == 2 ? s[2] : s[3];
-            h.add(b, __ballot_sync(0xffffffffu, (w >> (b & 31)) & 1u), lane);
-        }
+    } else if (KIND == POMDP_KIND_TIGER) {
+        acc[0] += warp_bit_counts<1>(valid ? (1u << (s[0] & 1u)) : 0u, 2, lane);
+    } else if (KIND == POMDP_KIND_NETWORK) {                 // p0 = n machines
+        acc[0] += warp_bit_counts<1>(s[0], p0, lane);
+    } else {                                                 // BattleShip: p0 = n_tiles occupied bits over four words
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (32 * j < p0) acc[j] += warp_bit_counts<1>(s[j], p0 - 32 * j < 32 ? p0 - 32 * j : 32, lane);
     }
 }
+template <int KIND>
 __global__ void __launch_bounds__(1024)
-pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
+pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins) {
     __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
     for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int n_bits = kind == POMDP_KIND_TAG ? 0 : kind == POMDP_KIND_TIGER ? 2 : p0;
-    HistAcc h = {{0u, 0u, 0u, 0u}};
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};                      // lane l: running count of bit bin l (+32, +64, +96)
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     int64_t scalar_from = 0;
@@ -787,7 +796,7 @@ pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ s
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t s[4] = {e[j], 0u, 0u, 0u};
-                hist_one(kind, p0, n_bits, valid, s, sh, h, lane);
+                hist_one<KIND>(p0, valid, s, sh, acc, lane);
             }
         }
         scalar_from = n_groups << 2;
@@ -795,6 +804,7 @@ pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ s
     const int64_t rem = n - scalar_from;
     const int64_t r_round = (rem + 31) & ~(int64_t)31;
     const bool aligned8 = (reinterpret_cast<uintptr_t>(state) & 7) == 0;
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(state) & 15) == 0;
     for (int64_t r = tid; r < r_round; r += nthreads) {
         const int64_t i = scalar_from + r;
         const bool valid = r < rem;
@@ -802,13 +812,25 @@ pomdp_belief_hist_kernel(int kind, int p0, int p1, const int32_t* __restrict__ s
         if (valid) {
             if (words == 1) s[0] = (uint32_t)__ldcs(state + i);
             else if (words == 2 && aligned8) { const int2 v = __ldcs(reinterpret_cast<const int2*>(state) + i); s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; }
-            else for (int k = 0; k < 4 && k < words; ++k) s[k] = (uint32_t)state[i * words + k];     // BattleShip: occupied words only
+            else if (words == SHIP_WORDS && aligned16) {     // BattleShip: the four occupied words of the 32-byte board
+                const int4 v = __ldcs(reinterpret_cast<const int4*>(state) + 2 * i);
+                s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; s[2] = (uint32_t)v.z; s[3] = (uint32_t)v.w & 0x00FFFFFFu;
+            } else {
+                for (int k = 0; k < 4 && k < words; ++k) s[k] = (uint32_t)state[i * words + k];
+                if (words == SHIP_WORDS) s[3] &= 0x00FFFFFFu;
+            }
         }
-        hist_one(kind, p0, n_bits, valid, s, sh, h, lane);
+        hist_one<KIND>(p0, valid, s, sh, acc, lane);
     }
+    const int n_bits = KIND == POMDP_KIND_TAG ? 0 : KIND == POMDP_KIND_TIGER ? 2 : p0;
+    if (KIND == POMDP_KIND_ROCK) {                           // acc[1] lane j = rock 12 + j
+        if (acc[0] && lane < n_bits) atomicAdd(&sh[lane], acc[0]);
+        if (acc[1] && 12 + lane < n_bits) atomicAdd(&sh[12 + lane], acc[1]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (h.acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], h.acc[j]);
+        for (int j = 0; j < 4; ++j)
+            if (acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], acc[j]);
+    }
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
@@ -849,7 +871,11 @@ inline int grid_for(K kernel, int64_t n_threads_needed, int threads = POMDP_THRE
     int64_t need = (n_threads_needed + threads - 1) / threads;
     const int64_t cap = (int64_t)device_sms() * per_sm;
     if (need < 1) need = 1;
-    return (int)(need < cap ? need : cap);
+    if (need <= cap) return (int)need;
+    // balanced persistent loop: every thread runs the same number of grid-stride iterations (a 2^20-env batch on 296
+    // resident CTAs would otherwise give 73 % of the threads two iterations and the rest one)
+    const int64_t iters = (need + cap - 1) / cap;
+    return (int)((need + iters - 1) / iters);
 }
 
 inline int finish(const char* what) {
@@ -1462,12 +1488,16 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     if (rc) return rc;
     const int bins = host::hist_bins(kind, p0, p1);
     if (n == 0) return 0;
-    auto k = pomdp_belief_hist_kernel;
+    auto k = kind == POMDP_KIND_ROCK ? pomdp_belief_hist_kernel<POMDP_KIND_ROCK>
+             : kind == POMDP_KIND_TAG ? pomdp_belief_hist_kernel<POMDP_KIND_TAG>
+             : kind == POMDP_KIND_TIGER ? pomdp_belief_hist_kernel<POMDP_KIND_TIGER>
+             : kind == POMDP_KIND_NETWORK ? pomdp_belief_hist_kernel<POMDP_KIND_NETWORK>
+                                          : pomdp_belief_hist_kernel<POMDP_KIND_BATTLESHIP>;
     // one 1024-thread CTA per SM: every CTA ends with one global atomic per non-empty bin, all CTAs on the same few
     // hundred addresses, so the CTA count (not the batch) sets that cost
     const int64_t want = (n + 4095) / 4096;
     const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());
-    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(kind, p0, p1, state, words, n, (unsigned long long*)hist, bins);
+    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)hist, bins);
     return finish("pomdp_belief_hist");
 }
 

@@ -245,7 +245,7 @@ class BatchedPomdpEnv(object):
                             self._discount if discount is None else discount)
         return final_state, ret, steps, flags
 
-    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False):
+    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False, n_streams=3):
         """G(s, a) on HOST buffers (pinned CPU tensors): what a numpy-holding caller of the
         reference does.  The batch is cut into chunks that are copied in, stepped and copied
         out on three rotating CUDA streams, so the H2D copy, the kernel and the D2H copy of
@@ -255,7 +255,7 @@ class BatchedPomdpEnv(object):
         Returns after all results have landed."""
         n = action.shape[0]
         ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
-        ws = self._host_ws(min(chunk, max(n, 1)))
+        ws = self._host_ws(min(chunk, max(n, 1)), n_streams)
         n_out = 2 if packed else 4
         base_off = self.global_offset
         with self._guard():
@@ -283,15 +283,15 @@ class BatchedPomdpEnv(object):
             cur.synchronize()
         return out
 
-    def _host_ws(self, chunk):
+    def _host_ws(self, chunk, n_streams=3):
         ws = getattr(self, "_hws", None)
-        if ws is None or ws["chunk"] < chunk:
+        if ws is None or ws["chunk"] != chunk or len(ws["streams"]) != n_streams:
             sshape = (chunk, self.state_words) if self.state_words > 1 else (chunk,)
             slots = [(self._empty(sshape, torch.int32), self._empty((chunk,), torch.int32),
                       self._empty(sshape, torch.int32), self._empty((chunk,), torch.int32),
-                      self._empty((chunk,), torch.float32), self._empty((chunk,), torch.int32)) for _ in range(3)]
+                      self._empty((chunk,), torch.float32), self._empty((chunk,), torch.int32)) for _ in range(n_streams)]
             ws = self._hws = {"chunk": chunk, "slots": slots,
-                              "streams": [torch.cuda.Stream(self.device) for _ in range(3)]}
+                              "streams": [torch.cuda.Stream(self.device) for _ in range(n_streams)]}
         return ws
 
     # ------------------------------------------------------------------ gym surface ---

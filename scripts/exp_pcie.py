@@ -53,15 +53,18 @@ hs, ha = s.cpu().pin_memory(), a.cpu().pin_memory()
 pin = dict(device="cpu", pin_memory=True)
 ho = (torch.empty(B, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.float32, **pin),
       torch.empty(B, dtype=torch.int32, **pin))
+hp = (torch.empty(B, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin))
 res = {}
-for chunk in (1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22):
-    env._hws = None
-    for _ in range(3):
-        env.simulate_host(hs, ha, ho, step_ctr=1, chunk=chunk)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(20):
-        env.simulate_host(hs, ha, ho, step_ctr=1, chunk=chunk)
-    dt = (time.perf_counter() - t0) / 20
-    res["chunk_2^%d" % (chunk.bit_length() - 1)] = {"ms": dt * 1e3, "steps_per_s": B / dt, "GBps_total": 24 * B / dt / 1e9}
-print(json.dumps(res))
+for packed in (False, True):
+    for ns in (2, 3, 4):
+        for chunk in (1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21):
+            o = hp if packed else ho
+            for _ in range(3):
+                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns)
+            dt = (time.perf_counter() - t0) / 20
+            res["packed=%d streams=%d chunk=2^%d" % (packed, ns, chunk.bit_length() - 1)] = round(dt * 1e3, 3)
+print(json.dumps(res, indent=0))
