@@ -724,39 +724,38 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 }
 
 // ---------------------------------------------------------------- belief histogram ---
-// Shared-memory histogram per CTA (<= 512 bins), then one 64-bit global atomic per non-empty bin per CTA
+// Shared-memory histogram per CTA (<= 512 bins), then one 64-bit global atomic per non-empty bin per CTA; one
+// 1024-thread CTA per SM, because that final step costs one same-address global atomic per bin per CTA
 // (pomdp_core.h: belief_bins is the definition the tests check against).  Two kinds of bins:
-//  * bit bins (Rock "rock i still good", Tiger door, BattleShip occupied cells, Network "machine m up"), which
-//    every particle hits with probability ~1/2 -- as shared-memory atomics these are 32-way same-address conflicts.
-//    Instead: one __ballot_sync per bit per warp iteration, and lane (b & 31) keeps the running popcount of bit b in a
-//    register; no atomic until the warp is done;
-//  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (spread over many
-//    addresses).
-// W = 1 states are read four envs per thread (16-byte loads) to keep enough bytes in flight.
+//  * bit bins (Rock "rock i still good", Tiger door, BattleShip occupied cells, Network "machine m up"), which every
+//    particle hits with probability ~1/2 -- as shared-memory atomics these are 32-way same-address conflicts, and as
+//    warp ballots they are VOTE-throughput-bound (both measured: 30 us and 25-37 us for 2^22 Rock states).  Instead
+//    every thread keeps PACKED BYTE COUNTERS in registers: four bits of the state are spread to the four bytes of
+//    a word with one multiply ((x & 0xF) * 0x00204081 & 0x01010101) and added -- three instructions per four bins
+//    per particle, no cross-lane traffic.  Counters are flushed (warp shuffle reduction of the 16-bit halves, then
+//    one shared-memory atomic per bin per warp) before a byte can overflow, normally once at the end;
+//  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (many addresses).
+// W = 1 states are read four envs per thread (16-byte loads).
 #define POMDP_HIST_MAX_BINS 512
-// Counts, for every bit position b < nb of `bits` (bit b * STRIDE), the lanes of the warp that have it set: one VOTE
-// per bit; lane b keeps ballot b and adds its popcount to its register counter once per word.
-template <int STRIDE>
-__device__ __forceinline__ uint32_t warp_bit_counts(uint32_t bits, int nb, int lane) {
-    uint32_t mine = 0;
-#pragma unroll
-    for (int b = 0; b < 32 / STRIDE; ++b)
-        if (b < nb) {                                        // nb is warp-uniform
-            const unsigned bal = __ballot_sync(0xffffffffu, (bits >> (b * STRIDE)) & 1u);
-            mine = lane == b ? bal : mine;
-        }
-    return (uint32_t)__popc(mine);
-}
+template <int KIND> struct HistShape;                        // NW = packed counter words per thread (4 bins each)
+template <> struct HistShape<POMDP_KIND_ROCK> { static constexpr int NW = 4; };
+template <> struct HistShape<POMDP_KIND_TAG> { static constexpr int NW = 1; };
+template <> struct HistShape<POMDP_KIND_TIGER> { static constexpr int NW = 1; };
+template <> struct HistShape<POMDP_KIND_NETWORK> { static constexpr int NW = 8; };
+template <> struct HistShape<POMDP_KIND_BATTLESHIP> { static constexpr int NW = 30; };
+
+__device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }        // bit i -> byte i
+__device__ __forceinline__ uint32_t spread4_even(uint32_t byte) { return ((byte & 0x55u) * 0x00041041u) & 0x01010101u; }  // bit 2i -> byte i
+
 template <int KIND>
-__device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4], uint32_t* sh, uint32_t acc[4], int lane) {
-    if (KIND == POMDP_KIND_ROCK) {                           // p0 = k rocks; bit 2i of `good` = rock i's status is +1 (code 01)
-        const uint32_t good0 = (s[0] >> 8) & ~(s[0] >> 9) & 0x00555555u;                       // rocks 0..11 (bits 8..31 of word 0)
-        acc[0] += warp_bit_counts<2>(good0, p0 < 12 ? p0 : 12, lane);
-        if (p0 > 12) {                                                                         // rocks 12..15: bits 0..7 of word 1
-            const uint32_t good1 = s[1] & ~(s[1] >> 1) & 0x00000055u;
-            const uint32_t c = warp_bit_counts<2>(good1, p0 - 12, lane);                       // lane j holds rock 12 + j
-            acc[1] += c;
-        }
+__device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4], uint32_t* sh, uint32_t (&acc)[HistShape<KIND>::NW]) {
+    if (KIND == POMDP_KIND_ROCK) {                           // bit 2i of `good` = rock i's status is +1 (code 01)
+        const uint32_t good0 = (s[0] >> 8) & ~(s[0] >> 9) & 0x00555555u;   // rocks 0..11: bits 8..31 of word 0
+        const uint32_t good1 = s[1] & ~(s[1] >> 1) & 0x00000055u;          // rocks 12..15: bits 0..7 of word 1
+        acc[0] += spread4_even(good0);
+        acc[1] += spread4_even(good0 >> 8);
+        acc[2] += spread4_even(good0 >> 16);
+        acc[3] += spread4_even(good1);
         if (valid) atomicAdd(&sh[p0 + (int)(s[0] & 0xFFu)], 1u);
     } else if (KIND == POMDP_KIND_TAG) {
         if (valid) {
@@ -764,30 +763,56 @@ __device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4]
             atomicAdd(&sh[TAG_CELLS + ((s[0] >> 5) & 31u)], 1u);
         }
     } else if (KIND == POMDP_KIND_TIGER) {
-        acc[0] += warp_bit_counts<1>(valid ? (1u << (s[0] & 1u)) : 0u, 2, lane);
-    } else if (KIND == POMDP_KIND_NETWORK) {                 // p0 = n machines
-        acc[0] += warp_bit_counts<1>(s[0], p0, lane);
-    } else {                                                 // BattleShip: p0 = n_tiles occupied bits over four words
+        acc[0] += valid ? (1u << (8u * (s[0] & 1u))) : 0u;
+    } else if (KIND == POMDP_KIND_NETWORK) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (32 * j < p0) acc[j] += warp_bit_counts<1>(s[j], p0 - 32 * j < 32 ? p0 - 32 * j : 32, lane);
+        for (int j = 0; j < 8; ++j) acc[j] += spread4((s[0] >> (4 * j)) & 0xFu);
+    } else {                                                 // BattleShip: 120 occupied bits over four words
+#pragma unroll
+        for (int j = 0; j < 30; ++j) acc[j] += spread4((s[j >> 3] >> (4 * (j & 7))) & 0xFu);
+    }
+}
+// adds the warp's packed byte counters to the shared histogram (bins 4j + c < n_bits) and clears them
+template <int NW>
+__device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, int n_bits, int lane) {
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        if (4 * j >= n_bits) break;
+        uint32_t lo = acc[j] & 0x00FF00FFu, hi = (acc[j] >> 8) & 0x00FF00FFu;      // bytes 0,2 and 1,3 as 16-bit fields
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, d);
+            hi += __shfl_xor_sync(0xffffffffu, hi, d);
+        }
+        if (lane == 0) {
+            const uint32_t c[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c[k] && 4 * j + k < n_bits) atomicAdd(&sh[4 * j + k], c[k]);
+        }
+        acc[j] = 0;
     }
 }
 template <int KIND>
 __global__ void __launch_bounds__(1024)
 pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins) {
+    constexpr int NW = HistShape<KIND>::NW;
     __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
     for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};                      // lane l: running count of bit bin l (+32, +64, +96)
+    const int n_bits = KIND == POMDP_KIND_TAG ? 0 : KIND == POMDP_KIND_TIGER ? 2 : p0;
+    uint32_t acc[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) acc[j] = 0;
+    int pending = 0;                                         // particles added since the last flush (warp-uniform)
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     int64_t scalar_from = 0;
     if (words == 1 && (reinterpret_cast<uintptr_t>(state) & 15) == 0) {
         const int64_t n_groups = n >> 2;
-        const int64_t g_round = (n_groups + 31) & ~(int64_t)31;          // whole warps iterate together (ballots)
+        const int64_t g_round = (n_groups + 31) & ~(int64_t)31;          // whole warps iterate together (flush shuffles)
         for (int64_t g = tid; g < g_round; g += nthreads) {
             const bool valid = g < n_groups;
             int4 v = make_int4(0, 0, 0, 0);
@@ -796,8 +821,10 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t s[4] = {e[j], 0u, 0u, 0u};
-                hist_one<KIND>(p0, valid, s, sh, acc, lane);
+                hist_one<KIND>(p0, valid, s, sh, acc);
             }
+            pending += 4;
+            if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
         }
         scalar_from = n_groups << 2;
     }
@@ -820,17 +847,10 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
                 if (words == SHIP_WORDS) s[3] &= 0x00FFFFFFu;
             }
         }
-        hist_one<KIND>(p0, valid, s, sh, acc, lane);
+        hist_one<KIND>(p0, valid, s, sh, acc);
+        if (++pending > 254) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
     }
-    const int n_bits = KIND == POMDP_KIND_TAG ? 0 : KIND == POMDP_KIND_TIGER ? 2 : p0;
-    if (KIND == POMDP_KIND_ROCK) {                           // acc[1] lane j = rock 12 + j
-        if (acc[0] && lane < n_bits) atomicAdd(&sh[lane], acc[0]);
-        if (acc[1] && 12 + lane < n_bits) atomicAdd(&sh[12 + lane], acc[1]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (acc[j] && 32 * j + lane < n_bits) atomicAdd(&sh[32 * j + lane], acc[j]);
-    }
+    hist_flush<NW>(acc, sh, n_bits, lane);
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
