@@ -336,12 +336,16 @@ POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t grou
 
 // ---- uniform-legal policy: np.random.choice(env._generate_legal()) --------------------
 POMDP_HD int nth_set_bit(uint32_t m, uint32_t j) {   // index of the (j+1)-th set bit of m (j < popc(m))
-#if defined(__CUDA_ARCH__)
-    return (int)__fns(m, 0u, (int)j + 1);
-#else
-    for (uint32_t i = 0; i < j; ++i) m &= m - 1;
-    return __builtin_ctz(m);
-#endif
+    // five-step binary search on masked popcounts (branch-free; CUDA's __fns is a loop)
+    uint32_t pos = 0;
+    POMDP_UNROLL
+    for (uint32_t half = 16; half >= 1; half >>= 1) {
+        const uint32_t c = (uint32_t)popc32(m & (((1u << half) - 1u) << pos));
+        const bool right = j >= c;
+        j -= right ? c : 0u;
+        pos += right ? half : 0u;
+    }
+    return (int)pos;
 }
 // bits 0, 2, 4, ... of v gathered into the low half
 POMDP_HD uint32_t compress_even(uint32_t v) {

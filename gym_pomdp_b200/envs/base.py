@@ -245,16 +245,32 @@ class BatchedPomdpEnv(object):
                             self._discount if discount is None else discount)
         return final_state, ret, steps, flags
 
-    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False, n_streams=3):
+    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False, n_streams=3, zero_copy=False):
         """G(s, a) on HOST buffers (pinned CPU tensors): what a numpy-holding caller of the
         reference does.  The batch is cut into chunks that are copied in, stepped and copied
         out on three rotating CUDA streams, so the H2D copy, the kernel and the D2H copy of
         neighbouring chunks overlap (PCIe is full duplex).  ``out`` = (next_state, obs,
         reward, flags) pinned CPU tensors -- or, with ``packed=True``, (next_state, result):
         8 instead of 16 bytes per env come back over PCIe (``unpack_result`` decodes).
-        Returns after all results have landed."""
+        Returns after all results have landed.
+
+        ``zero_copy=True``: no staging at all -- ONE kernel launch whose loads and stores go straight
+        to the pinned host buffers over PCIe (pinned memory is mapped into the device address space
+        under unified addressing), so reading the inputs and writing the results overlap at the
+        granularity of a warp instead of a chunk."""
         n = action.shape[0]
         ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
+        if zero_copy:
+            for t in (state, action) + tuple(out[:2 if packed else 4]):
+                if not t.is_pinned():
+                    raise ValueError("zero_copy needs pinned host tensors")
+            with self._guard():
+                if packed:
+                    self._c_step_packed(state, action, out[0], out[1], n, ctr)
+                else:
+                    self._c_step(state, action, out[0], out[1], out[2], out[3], n, ctr)
+                torch.cuda.current_stream(self.device).synchronize()
+            return out
         ws = self._host_ws(min(chunk, max(n, 1)), n_streams)
         n_out = 2 if packed else 4
         base_off = self.global_offset
