@@ -30,8 +30,20 @@ def peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+QUICK = False
+
+
 def time_graph(fn, K, dev):
     """fn(i) enqueues launch i; returns ms per launch over K launches replayed from one graph."""
+    if QUICK:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(0)
+        e0.record()
+        for i in range(2):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 2
     for i in range(3):
         fn(i)
     torch.cuda.synchronize()
@@ -103,7 +115,10 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default=None, help="substring filter on the label")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="few launches per kernel (for runs under ncu)")
     args = ap.parse_args()
+    global QUICK
+    QUICK = args.quick
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     peak, peak_src = peak_gbs()

@@ -8,7 +8,7 @@ for pair in "RockSample(11,11):rock11" "RockSample(15,15) B=2^22:rock15" "Tag-v0
   echo "== ncu $short"
   # -s skips the warm-up launches; each kernel family appears several times, keep a handful of every name
   timeout 600 ncu --metrics $M --clock-control none -k regex:pomdp_ --csv --log-file $OUT/ncu_$short.csv \
-      python scripts/bench_configs.py --steps 20 --only "$label" > $OUT/ncu_$short.log 2>&1
+      python scripts/bench_configs.py --quick --only "$label" > $OUT/ncu_$short.log 2>&1
   grep -c pomdp_ $OUT/ncu_$short.csv
 done
 ls -la $OUT
