@@ -3,18 +3,21 @@
 // Data movement design:
 //  * W=1/W=2 envs (Rock, Tag, Tiger, Network): SoA int32 streams.  One thread owns FOUR
 //    consecutive env instances: 16-byte vector loads of state/action, 16-byte vector
-//    stores of next_state/obs/reward/flags, fully coalesced (a warp moves 512 B per
-//    instruction).  Persistent grid-stride loop, grid = min(work, SMs x resident CTAs).
-//  * Rock's static maps (rock-id grid, rock coordinates, sensor thresholds; 400 B) are
-//    copied global -> shared once per CTA with ONE TMA bulk copy (cp.async.bulk +
-//    mbarrier complete_tx); the first global loads are issued before the wait so the
-//    table fetch hides under them.  Lookups are per-thread divergent, which is what
-//    shared memory (not the constant bank) is for.
-//  * BattleShip (W=8, 32 B per board): board tiles are moved global -> shared and
-//    shared -> global with TMA bulk copies (8 KB per 256-env tile), compute reads/writes
-//    the tile in shared memory; reset is one WARP per env (ballot scan over the 4*n_tiles
-//    placement candidates).
-//  * Philox4x32-10 in registers; no RNG state in memory.
+//    stores of next_state/obs/reward/flags (or next_state + one packed result word),
+//    fully coalesced (a warp moves 512 B per instruction).  Persistent grid-stride loop
+//    with a balanced trip count, at most SMs x resident CTAs.
+//  * Static maps -- Rock's header + transition LUT (17.6 KB for Rock(11,11)), Tag's board
+//    tables (4.2 KB) -- are built on the host, owned by the caller and copied global ->
+//    shared once per CTA with ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx);
+//    in the step kernel the first global loads are issued before the wait so the table
+//    fetch hides under them.  Lookups are per-thread divergent, which is what shared
+//    memory (not the constant bank) is for.
+//  * BattleShip (W=8, 32 B per board): the step kernel moves board tiles global -> shared
+//    and shared -> global with TMA bulk copies (8 KB per 256-env tile); reset is one
+//    THREAD per env on 128-bit bitboards (and, as an alternative with identical results,
+//    one WARP per env with a ballot scan over the 4*n_tiles placement candidates).
+//  * Philox4x32-10 in registers, one block per draw slot per four envs; no RNG state in memory.
+//  * policy / rollout / obs_prob / legal_mask / belief_hist: see the comments at each kernel.
 //
 // There is no CPU path in this file: every entry point launches a kernel.
 #include <cuda_runtime.h>
