@@ -108,6 +108,7 @@ _PROTOTYPES = {
     "pomdp_tiger_legal_mask": (c_int32, [POINTER(TigerParams), _P, _P, c_int64, c_void_p]),
     "pomdp_network_obs_prob": (c_int32, [POINTER(NetworkParams), _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_network_legal_mask": (c_int32, [POINTER(NetworkParams), _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_belief_update": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),

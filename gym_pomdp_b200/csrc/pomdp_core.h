@@ -896,6 +896,20 @@ POMDP_HD double dsub_rn(double a, double b) {
     return a - b;
 #endif
 }
+POMDP_HD double dmul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+POMDP_HD double dadd_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
 // rock.py:250-264
 template <typename S>
 POMDP_HD double rock_obs_prob(const RockDev& p, const RockTableHdr* __restrict__ hdr, S s, int32_t a, int32_t ob) {
@@ -958,6 +972,33 @@ POMDP_HD int32_t reward_units_tenths(float rw) {
     return (int32_t)(t < 0.f ? t - 0.5f : t + 0.5f);
 }
 
+// rock.py:177-191 (and 486-500): the per-rock belief side-statistics a check updates -- measured, count and the
+// likelihood products lkv / lkw with prob_valuable = .5 lkv / (.5 lkv + .5 lkw) -- in the reference's own operation
+// order with separately rounded double operations, so the values (including the NaN the reference reaches once
+// both products underflow) are the reference's bit for bit.  Applies when the action is a check AND produced a
+// reading (StochasticRock's failed p_move gate returns obs NULL and touches nothing, rock.py:443).
+POMDP_HD double ddiv_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+template <typename S>
+POMDP_HD bool rock_belief_update(const RockDev& p, const RockTableHdr* __restrict__ hdr, S s, int32_t a, int32_t ob,
+                                 int32_t& count, int32_t& measured, double& lkv, double& lkw, double& pv) {
+    if (a <= 4 || a >= (int32_t)p.n_actions || ob == 0) return false;
+    const uint32_t rp = hdr->rock_pos[a - 5];
+    const double eff = hdr->eff[l1_distance((int)((uint32_t)s & 15u), (int)(((uint32_t)s >> 4) & 15u), (int)(rp & 15u), (int)(rp >> 4)) & 31];
+    const double om = dsub_rn(1.0, eff);
+    ++measured;
+    if (ob == 2) { ++count; lkv = dmul_rn(lkv, eff); lkw = dmul_rn(lkw, om); }
+    else { --count; lkw = dmul_rn(lkw, eff); lkv = dmul_rn(lkv, om); }
+    const double denom = dadd_rn(dmul_rn(.5, lkv), dmul_rn(.5, lkw));
+    pv = ddiv_rn(dmul_rn(.5, lkv), denom);
+    return true;
+}
+
 // ========================================================================= rollouts ===
 // what a POMCP simulation does with these envs (the loops at rock.py:563-572 and
 // tag.py:310-316): until done or T steps,  a = np.random.choice(env._generate_legal());  ob, rw, done = env.step(a);
@@ -965,20 +1006,6 @@ POMDP_HD int32_t reward_units_tenths(float rw) {
 // for BOTH its policy draw (domain POLICY, slot 0) and the step's own draws (domain STEP), so a fused rollout is, draw
 // for draw, T launches of `policy` + `step` with step_ctr = c, c+1, ...  The return is accumulated in IEEE doubles
 // with separately rounded multiply and add, exactly as CPython does.
-POMDP_HD double dmul_rn(double a, double b) {
-#if defined(__CUDA_ARCH__)
-    return __dmul_rn(a, b);
-#else
-    return a * b;
-#endif
-}
-POMDP_HD double dadd_rn(double a, double b) {
-#if defined(__CUDA_ARCH__)
-    return __dadd_rn(a, b);
-#else
-    return a + b;
-#endif
-}
 struct RolloutAcc {
     double ret, disc;
     int32_t steps, flags;

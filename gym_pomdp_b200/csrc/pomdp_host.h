@@ -305,6 +305,17 @@ inline int check_obs_prob(const void* state, const void* action, const void* obs
         return fail(POMDP_E_ALIGN, "%s: int32 arrays must be 4-byte and the float64 array 8-byte aligned", what);
     return 0;
 }
+inline int check_belief(const void* state, const void* action, const void* obs, const void* count, const void* measured,
+                        const void* lkv, const void* lkw, const void* pv, int64_t n) {
+    if (n < 0) return fail(POMDP_E_BADARG, "pomdp_rock_belief_update: n = %lld is negative", (long long)n);
+    if (n == 0) return 0;
+    if (!state || !action || !obs || !count || !measured || !lkv || !lkw || !pv)
+        return fail(POMDP_E_BADARG, "pomdp_rock_belief_update: a required array pointer is NULL");
+    if ((((uintptr_t)state | (uintptr_t)action | (uintptr_t)obs | (uintptr_t)count | (uintptr_t)measured) & 3) ||
+        (((uintptr_t)lkv | (uintptr_t)lkw | (uintptr_t)pv) & 7))
+        return fail(POMDP_E_ALIGN, "pomdp_rock_belief_update: int32 arrays must be 4-byte and float64 arrays 8-byte aligned");
+    return 0;
+}
 inline int check_rollout(const void* state, const void* final_state, const void* ret, const void* steps, const void* flags,
                          int64_t n, int64_t goff, int32_t max_steps, const char* what) {
     if (n < 0) return fail(POMDP_E_BADARG, "%s: n = %lld is negative", what, (long long)n);

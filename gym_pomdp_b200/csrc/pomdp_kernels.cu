@@ -441,6 +441,30 @@ pomdp_legal_mask_kernel(const __grid_constant__ typename Env::Params p, const vo
         if (words > 1) mask[i * words + 1] = m[1];
     }
 }
+// Rock belief side-statistics (rock.py:177-191): one thread per env touches the one rock its check action read.
+template <typename S>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rock_belief_update_kernel(const __grid_constant__ RockDev p, const void* __restrict__ g_table,
+                                const int32_t* __restrict__ state, const int32_t* __restrict__ action,
+                                const int32_t* __restrict__ obs, int32_t* __restrict__ count, int32_t* __restrict__ measured,
+                                double* __restrict__ lkv, double* __restrict__ lkw, double* __restrict__ pv, int64_t n,
+                                uint32_t table_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<RockEnvT<S, false>>(smem_table, g_table, table_bytes, &bar);
+    const RockTableHdr* hdr = reinterpret_cast<const RockTableHdr*>(smem_table);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const int32_t a = __ldcs(action + i), ob = __ldcs(obs + i);
+        if (a <= 4 || a >= (int32_t)p.n_actions || ob == 0) continue;
+        const int64_t j = i * p.k + (a - 5);
+        int32_t c = count[j], m = measured[j];
+        double v = lkv[j], w = lkw[j], q = pv[j];
+        rock_belief_update<S>(p, hdr, load_state1(state, i, S()), a, ob, c, m, v, w, q);
+        count[j] = c; measured[j] = m; lkv[j] = v; lkw[j] = w; pv[j] = q;
+    }
+}
+
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_battleship_obs_prob_kernel(const __grid_constant__ ShipDev p, const int32_t* __restrict__ state,
                                  const int32_t* __restrict__ action, const int32_t* __restrict__ obs,
@@ -1490,6 +1514,31 @@ int pomdp_battleship_legal_mask(const PomdpBattleshipParams* q, const int32_t* s
     auto k = pomdp_battleship_legal_mask_kernel;
     k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, mask, n);
     return finish("pomdp_battleship_legal_mask");
+}
+
+int pomdp_rock_belief_update(const PomdpRockParams* q, const void* d_table, const int32_t* next_state, const int32_t* action,
+                             const int32_t* obs, int32_t* count, int32_t* measured, double* lkv, double* lkw,
+                             double* prob_valuable, int64_t n, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_belief(next_state, action, obs, count, measured, lkv, lkw, prob_valuable, n))) return rc;
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15))
+        return host::fail(POMDP_E_BADARG, "pomdp_rock_belief_update: d_table must be a 16-byte aligned device pointer");
+    const size_t smem = d.smem_bytes;
+    if (host::rock_words(q) == 1) {
+        auto k = pomdp_rock_belief_update_kernel<uint32_t>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, next_state, action, obs, count, measured, lkv, lkw, prob_valuable, n, d.table_bytes);
+    } else {
+        auto k = pomdp_rock_belief_update_kernel<uint64_t>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, next_state, action, obs, count, measured, lkv, lkw, prob_valuable, n, d.table_bytes);
+    }
+    return finish("pomdp_rock_belief_update");
 }
 
 // ---- helpers

@@ -19,14 +19,40 @@ NULL, BAD, GOOD = 0, 1, 2          # rock.py:12-15
 SAMPLE = 4                         # rock.py:18-23
 
 
+class RockBeliefStats(object):
+    """Per-rock belief side-statistics of a batch (rock.py:78-86): ``count``, ``measured`` int32[n, k];
+    ``lkv``, ``lkw``, ``prob_valuable`` float64[n, k].  Fresh values as in ``Rock.__init__``."""
+
+    def __init__(self, n, k, device):
+        self.count = torch.zeros((n, k), dtype=torch.int32, device=device)
+        self.measured = torch.zeros((n, k), dtype=torch.int32, device=device)
+        self.lkv = torch.ones((n, k), dtype=torch.float64, device=device)
+        self.lkw = torch.ones((n, k), dtype=torch.float64, device=device)
+        self.prob_valuable = torch.full((n, k), .5, dtype=torch.float64, device=device)
+
+    def reset(self, mask=None):
+        """Back to the fresh values, for all envs or those selected by ``mask`` (bool[n])."""
+        sel = slice(None) if mask is None else mask.to(self.count.device).bool()
+        self.count[sel] = 0
+        self.measured[sel] = 0
+        self.lkv[sel] = 1.
+        self.lkw[sel] = 1.
+        self.prob_valuable[sel] = .5
+
+    def arrays(self):
+        return self.count, self.measured, self.lkv, self.lkw, self.prob_valuable
+
+
 class RockEnv(BatchedPomdpEnv):
     kind = _lib.KIND_ROCK
     _abi = "rock"
     _stochastic = False
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, batch_size=None, device="cuda", seed=0,
-                 global_offset=0, p_move=0.8):
+                 global_offset=0, p_move=0.8, track_belief_stats=False):
         super().__init__(batch_size, device, seed, global_offset)
+        self.track_belief_stats = bool(track_belief_stats)   # batched mode: keep rock.py's per-rock side-stats current
+        self.belief_stats = None
         self.num_rocks = num_rocks
         self._use_heuristic = use_heuristic
         self._params = _lib.RockParams(board_size, num_rocks, int(self._stochastic), 0, float(p_move))
@@ -73,6 +99,23 @@ class RockEnv(BatchedPomdpEnv):
     def _hist_args(self):
         return self.num_rocks, self.state_words
 
+    # ------------------------------------------------- belief side-statistics (batched) ---
+    def new_belief_stats(self, n=None):
+        return RockBeliefStats(self.batch_size if n is None else int(n), self.num_rocks, self.device)
+
+    def update_belief_stats(self, stats, next_state, action, obs):
+        """rock.py:177-191 for a whole batch: every env whose ``action`` was a check that produced a reading updates
+        that rock's measured / count / lkv / lkw / prob_valuable in ``stats`` (in place; one kernel)."""
+        n = action.shape[0]
+        action = torch.as_tensor(action, device=self.device).to(torch.int32).contiguous()
+        obs = torch.as_tensor(obs, device=self.device).to(torch.int32).contiguous()
+        with self._guard():
+            _lib.check(_lib.lib().pomdp_rock_belief_update(
+                ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(next_state), _lib.ptr(action), _lib.ptr(obs),
+                _lib.ptr(stats.count), _lib.ptr(stats.measured), _lib.ptr(stats.lkv), _lib.ptr(stats.lkw),
+                _lib.ptr(stats.prob_valuable), n, self._stream()), "pomdp_rock_belief_update")
+        return stats
+
     # ---------------------------------------------------------------------- codec ---
     def pack(self, x, y, status, done=None):
         """x, y int[n]; status int[n, k] in {-1, 0, +1} -> packed int32[n] / int32[n, 2]."""
@@ -116,6 +159,22 @@ class RockEnv(BatchedPomdpEnv):
         return torch.cat([idx[:, None], status], dim=1)
 
     # ---------------------------------------------------------------- scalar mode ---
+    def reset(self, mask=None):
+        obs = super().reset(mask)
+        if self.track_belief_stats and not self._scalar:
+            if self.belief_stats is None:
+                self.belief_stats = self.new_belief_stats()
+            else:
+                self.belief_stats.reset(mask)
+        return obs
+
+    def step(self, action):
+        out = super().step(action)
+        if self.track_belief_stats and not self._scalar:
+            self.update_belief_stats(self.belief_stats, self.state, action, out[0])
+            out[3]["belief_stats"] = self.belief_stats
+        return out
+
     def _on_reset(self):
         self._query = 0
         self.last_action = SAMPLE
@@ -219,6 +278,7 @@ class StochasticRockEnv(RockEnv):
     _stochastic = True
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, p_move=.8, batch_size=None, device="cuda",
-                 seed=0, global_offset=0):
-        super().__init__(board_size, num_rocks, use_heuristic, batch_size, device, seed, global_offset, p_move)
+                 seed=0, global_offset=0, track_belief_stats=False):
+        super().__init__(board_size, num_rocks, use_heuristic, batch_size, device, seed, global_offset, p_move,
+                         track_belief_stats)
         self.p_move = p_move

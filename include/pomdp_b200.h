@@ -325,6 +325,20 @@ int pomdp_network_obs_prob(const PomdpNetworkParams* params,
                            int64_t n, void* stream);
 int pomdp_network_legal_mask(const PomdpNetworkParams* params, const int32_t* state, uint32_t* mask, int64_t n, void* stream);
 
+/* ----------------------------------------------- RockSample belief side-statistics --- */
+/* rock.py:78-86, 177-191: every check of rock r updates that rock's `measured`, `count`, the
+ * likelihood products `lkv` / `lkw` and `prob_valuable` = .5 lkv / (.5 lkv + .5 lkw); they are read
+ * by _generate_preferred (rock.py:368) and _select_target (rock.py:394).  Batched: five arrays
+ * shaped [n, num_rocks] (count, measured int32; lkv, lkw, prob_valuable float64; fresh values
+ * 0, 0, 1, 1, .5 as in Rock.__init__), updated in place for every env whose `action` was a check
+ * that produced a reading (obs != 0), from the post-step state.  Same double operations in the same
+ * order as the reference, so the values -- including the NaN the reference itself reaches when both
+ * products underflow -- are bit-identical.                                                     */
+int pomdp_rock_belief_update(const PomdpRockParams* params, const void* d_table,
+                             const int32_t* next_state, const int32_t* action, const int32_t* obs,
+                             int32_t* count, int32_t* measured, double* lkv, double* lkw, double* prob_valuable,
+                             int64_t n, void* stream);
+
 /* ------------------------------------------------------------ Grid / Coord helpers --- */
 /* coord.py:7-114 and tag.py:36-66 as batched device functions (bit-exact integer work).
  * Coordinates travel as int32 pairs (x, y), i.e. arrays shaped [n, 2].

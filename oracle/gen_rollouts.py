@@ -205,5 +205,59 @@ def main():
     print("wrote rollouts.npz")
 
 
+
+
+def gen_rock_stats(E, out, tag, n, k, stochastic, M, T):
+    """Belief side-statistics (rock.py:177-191) along check-heavy action sequences, recorded after every step."""
+    import warnings
+    warnings.simplefilter("ignore")
+    d = ref_shim.draws()
+    env = E.StochasticRockEnv(n, k) if stochastic else E.RockEnv(n, k)
+    rs = np.random.RandomState(1000 + n + int(stochastic))
+    acts = np.where(rs.rand(M, T) < 0.8, rs.randint(5, 5 + k, (M, T)), rs.randint(0, 4, (M, T)))
+    acts[:, 5:] = np.where(rs.rand(M, T - 5) < 0.9, 5 + (np.arange(M)[:, None] % k), acts[:, 5:])
+    acts[:, 5:][acts[:, 5:] < 5] = 5                # after five free steps only checks, 90 % of them hammering ONE rock:
+                                                    # drives its lkv and lkw to underflow, where the reference's 0/0 gives NaN
+    keys = ("count", "measured", "lkv", "lkw", "prob_valuable")
+    rec = {key: np.zeros((M, T, k), np.float64) for key in keys}
+    obs, alive = np.zeros((M, T), np.int32), np.zeros((M, T), bool)
+    x0, y0, st0 = [], [], []
+    for e in range(M):
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (k + 7) // 8)
+        d.clear(); d.feed([rock_reset_word(int(rw[r >> 3]), r) for r in range(k)])
+        env.reset()
+        d.clear()
+        x0.append(env.state.agent_pos.x); y0.append(env.state.agent_pos.y); st0.append([r.status for r in env.state.rocks])
+        for t in range(T):
+            w = W(e, FIRST_CTR + t, philox.DOMAIN_STEP, 2)
+            d.clear(); d.feed([w[0], w[1]] if stochastic else [w[1]])
+            ob, rw_, done, _ = env.step(int(acts[e, t]))
+            d.clear()
+            obs[e, t], alive[e, t] = ob, True
+            for key in keys:
+                rec[key][e, t] = [getattr(r, key) for r in env.state.rocks]
+            if done:
+                break
+    out[f"{tag}_cfg"] = np.array([n, k, int(stochastic), T])
+    out[f"{tag}_acts"], out[f"{tag}_obs"], out[f"{tag}_alive"] = acts.astype(np.int32), obs, alive
+    out[f"{tag}_x0"], out[f"{tag}_y0"], out[f"{tag}_st0"] = np.array(x0), np.array(y0), np.array(st0)
+    for key in keys:
+        out[f"{tag}_{key}"] = rec[key]
+    print(tag, "nan prob_valuable entries:", int(np.isnan(rec["prob_valuable"]).sum()), "min lkv", rec["lkv"][alive].min())
+
+
+def main_stats():
+    E = ref_shim.load_reference()
+    out = {"seed": SEED, "reset_ctr": RESET_CTR, "first_ctr": FIRST_CTR}
+    with ref_shim.scripted_numpy():
+        gen_rock_stats(E, out, "rock_7_8", 7, 8, False, 16, 3200)
+        gen_rock_stats(E, out, "rock_15_15", 15, 15, False, 24, 200)
+        gen_rock_stats(E, out, "srock_11_11", 11, 11, True, 24, 200)
+    np.savez_compressed(os.path.join(GOLDEN, "rock_stats.npz"), **out)
+    print("wrote rock_stats.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--stats-only" not in sys.argv:
+        main()
+    main_stats()

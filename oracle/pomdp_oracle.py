@@ -202,6 +202,26 @@ def rock_reset(cfg, draw):
     return cfg.start[0], cfg.start[1], status, 0
 
 
+def rock_belief_update(cfg, x, y, action, ob, side):
+    """rock.py:177-191: the checked rock's side-statistics (``side`` = list of dicts with count, measured, lkv, lkw,
+    prob_valuable; mutated).  (x, y) is the agent position, which a check does not change."""
+    if action <= 4 or ob == 0:
+        return
+    r = side[action - 5]
+    eff = cfg.efficiency(l1_distance(x, y, *cfg.rock_pos[action - 5]))
+    r["measured"] += 1
+    if ob == 2:
+        r["count"] += 1
+        r["lkv"] *= eff
+        r["lkw"] *= (1 - eff)
+    else:
+        r["count"] -= 1
+        r["lkw"] *= eff
+        r["lkv"] *= (1 - eff)
+    denom = (.5 * r["lkv"]) + (.5 * r["lkw"])
+    r["prob_valuable"] = (.5 * r["lkv"]) / denom if denom != 0 else float("nan")   # numpy: 0/0 -> nan (+ warning)
+
+
 def rock_compute_prob(cfg, action, x, y, status, ob):
     """rock.py:250-264 (evaluated on the post-step state)."""
     if action <= 4:

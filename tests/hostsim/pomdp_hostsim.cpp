@@ -596,6 +596,25 @@ int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state,
         }, state, action, next, result, n);
 }
 
+int pomdp_rock_belief_update(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action,
+                             const int32_t* obs, int32_t* count, int32_t* measured, double* lkv, double* lkw, double* pv,
+                             int64_t n, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_belief(state, action, obs, count, measured, lkv, lkw, pv, n))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    const RockTableHdr* hdr = (const RockTableHdr*)table;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t a = action[i];
+        if (a <= 4 || a >= (int32_t)d.n_actions) continue;
+        const int64_t j = i * d.k + (a - 5);
+        if (host::rock_words(q) == 1) rock_belief_update<uint32_t>(d, hdr, load_state<uint32_t>(state, i), a, obs[i], count[j], measured[j], lkv[j], lkw[j], pv[j]);
+        else rock_belief_update<uint64_t>(d, hdr, load_state<uint64_t>(state, i), a, obs[i], count[j], measured[j], lkv[j], lkw[j], pv[j]);
+    }
+    return 0;
+}
+
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
     const int rc = host::check_coord_op(op, xs, a, b, out, n);
     if (rc) return rc;
