@@ -172,6 +172,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 must print exactly ONE line: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) off stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     B, n, k = args.batch, args.board, args.rocks

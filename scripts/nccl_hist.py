@@ -19,6 +19,8 @@ def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
     B = (1 << 25) // world
     env = gp.make("Rock-v0", board_size=15, num_rocks=15, batch_size=B, device=dev, seed=0x5EED, global_offset=rank * B)
