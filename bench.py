@@ -26,6 +26,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# rank 0 must print exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image)
+# away from it -- lower the level before anything reads it, and route fd 1 to stderr while the communicator is built
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+
+class _StdoutToStderr(object):
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
 METRIC = "env-steps/sec RockSample(11,11) batch=2^22 per B200"
 UNIT = "env-steps/s"
 BYTES_PER_STEP = 24          # read state 4 + action 4, write next_state 4 + obs 4 + reward 4 + flags 4
@@ -172,10 +190,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 must print exactly ONE line: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) off stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                      # builds the communicator (and prints NCCL's banner, if any) now
     n_gpus = world
     B, n, k = args.batch, args.board, args.rocks
     K, W = args.steps, args.warmup
