@@ -372,7 +372,7 @@ def run_b200(args):
     per_launch_ms = ms / K
     achieved = B * bytes_per_step / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
+                "traffic": ncu_traffic(), "traffic_l2": ncu_traffic("l2_bytes_from_sms_per_launch"), "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
                 "algorithmic_bytes_per_launch": B * bytes_per_step, "avg_launch_us": per_launch_ms * 1e3,
                 "peak_source": peak_src,
                 "read_only_frac": (B * (4 * words + 4) / (per_launch_ms * 1e-3) / 1e9) / peak}
@@ -414,12 +414,14 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+def ncu_traffic(key="dram_bytes_per_launch"):
+    """Per-launch traffic of the step kernel from the committed ncu capture (profiles/rock_step_ncu_summary.json), if any:
+    dram__bytes_read + dram__bytes_write (a single profiled launch leaves most of its 67 MB of writes in the 126 MB L2,
+    so this undercounts the writes), or the bytes the SMs moved through L2 (= the algorithmic bytes when nothing is re-read)."""
     p = os.path.join(ROOT, "profiles", "rock_step_ncu_summary.json")
     try:
         with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f).get(key)
     except Exception:  # noqa: BLE001
         return None
 

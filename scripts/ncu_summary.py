@@ -19,7 +19,7 @@ src = os.path.join(ROOT, "gpurun_out", tag)
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEYS = ["lts__t_sectors_srcunit_tex.sum", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -72,7 +72,10 @@ if os.path.exists(rp):
             "dram_bytes_read_per_launch": sum(rd) / len(rd), "dram_bytes_write_per_launch": sum(wr) / len(wr),
             "dram_bytes_per_launch": (sum(rd) + sum(wr)) / len(rd),
             "gpu_time_us_under_ncu": sum(t) / len(t),
-            "note": "writes still resident in the 126 MB L2 at kernel end are not in dram__bytes_write"}
+            "l2_bytes_from_sms_per_launch": (32.0 * sum(col("lts__t_sectors_srcunit_tex.sum")) / len(rd)
+                                             if "lts__t_sectors_srcunit_tex.sum" in hdr else None),
+            "note": "writes still resident in the 126 MB L2 at kernel end are not in dram__bytes_write; "
+                    "l2_bytes_from_sms = 32 B x lts__t_sectors_srcunit_tex.sum (every byte the SMs moved through L2)"}
     name = "rock_step_ncu_summary.json" if rep_name == "rock_step" else rep_name + "_ncu_summary.json"
     with open(os.path.join(dst, name), "w") as f:
         json.dump(summ, f, indent=1)
