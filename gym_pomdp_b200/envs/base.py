@@ -320,7 +320,42 @@ class BatchedPomdpEnv(object):
         self._step_ctr = 0
         return [seed]
 
+    # scalar (drop-in) mode keeps its one instance in a small PINNED HOST buffer that the kernels read and write
+    # directly (zero-copy over PCIe): [state(W) | next_state(W) | action | obs | reward | flags] as int32.  A step is
+    # then one launch + one stream synchronize, and every conversion to the reference's state formats is plain
+    # Python on host integers -- no device tensors, no extra copies.
+    def _ensure_io(self):
+        if getattr(self, "_io", None) is not None:
+            return
+        W = self.state_words
+        io = torch.zeros(2 * W + 4, dtype=torch.int32)
+        if self.device.type == "cuda":
+            io = io.pin_memory()
+        self._io, self._io_np, self._io_f = io, io.numpy(), io.view(torch.float32)
+        shape = (1, W) if W > 1 else (1,)
+        self._io_state, self._io_next = io[:W].view(shape), io[W:2 * W].view(shape)
+        self._io_act, self._io_obs = io[2 * W:2 * W + 1], io[2 * W + 1:2 * W + 2]
+        self._io_rw, self._io_fl = self._io_f[2 * W + 2:2 * W + 3], io[2 * W + 3:2 * W + 4]
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def _host_words(self):
+        """the scalar instance's packed state as unsigned Python ints"""
+        return [int(w) & 0xFFFFFFFF for w in self._io_np[:self.state_words]]
+
     def reset(self, mask=None):
+        if self._scalar:
+            self._ensure_io()
+            with self._guard():
+                self._c_reset(self._io_state, self._io_obs, None, 1, self._next_ctr())
+                self._sync()
+            self.state, self.flags = self._io_state, self._io_fl
+            self._io_np[2 * self.state_words + 3] = 0
+            self._on_reset()
+            self.done = False
+            return int(self._io_np[2 * self.state_words + 1])
         if self.state is None or mask is None:
             self.state, obs = self.init_states(self.batch_size)
             self.flags = torch.zeros(self.batch_size, dtype=torch.int32, device=self.device)
@@ -330,9 +365,6 @@ class BatchedPomdpEnv(object):
             self.init_states(self.batch_size, out=(self.state, obs), mask=m)
             self.flags = torch.where(m.bool(), torch.zeros_like(self.flags), self.flags)
         self._on_reset()
-        if self._scalar:
-            self.done = False
-            return int(obs[0].item())
         return obs
 
     def _on_reset(self):
@@ -357,28 +389,35 @@ class BatchedPomdpEnv(object):
         assert self.done is False
         if self.state is None:
             raise AttributeError("%s has no state: call reset() first" % type(self).__name__)
-        a = torch.tensor([int(action)], dtype=torch.int32, device=self.device)
-        next_state, obs, reward, flags = self.simulate(self.state, a)
-        fl = int(flags[0].item())
-        self._raise_for_flags(fl)
-        self.state, self.flags = next_state, flags
+        W, io = self.state_words, self._io_np
+        io[2 * W] = int(action)
+        with self._guard():
+            self._c_step(self._io_state, self._io_act, self._io_next, self._io_obs, self._io_rw, self._io_fl, 1, self._next_ctr())
+            self._sync()
+        fl = int(io[2 * W + 3])
+        self._raise_for_flags(fl)                 # the state is still the pre-step one if this raises
+        io[:W] = io[W:2 * W]
         self.last_action = int(action)
         self.done = bool(fl & _lib.FLAG_DONE)
-        ob = int(obs[0].item())
+        ob = int(io[2 * W + 1])
         self._after_scalar_step(int(action), ob)
-        return ob, self._reward_to_py(float(reward[0].item()), int(action)), self.done, {"state": self._info_state()}
+        return ob, self._reward_to_py(float(self._io_f[2 * W + 2]), int(action)), self.done, {"state": self._info_state()}
 
     def _after_scalar_step(self, action, ob):
         pass
 
     def _info_state(self):
-        return self._state_to_ref(self.state[0])
+        return self._state_to_ref(self._host_words())
 
     def _set_state(self, state):
         """Batched: packed int32 tensor (copied).  Scalar: the reference's own state format."""
         if self._scalar:
             self.done = False
-            self.state = self._state_from_ref(state)
+            self._ensure_io()
+            self._io_state.copy_(self._state_from_ref(state).reshape(self._io_state.shape))
+            self.state, self.flags = self._io_state, self._io_fl
+            self._io_np[2 * self.state_words + 3] = 0
+            return
         else:
             state = torch.as_tensor(state, device=self.device).to(torch.int32)
             expect = (self.batch_size, self.state_words) if self.state_words > 1 else (self.batch_size,)
@@ -390,7 +429,7 @@ class BatchedPomdpEnv(object):
     def _get_init_state(self):
         state, _ = self.init_states(self.batch_size)
         if self._scalar:
-            return self._state_to_ref(state[0])
+            return self._state_to_ref([int(w) & 0xFFFFFFFF for w in state.reshape(-1).tolist()])
         return state
 
     def render(self, mode="ansi", close=False):

@@ -107,11 +107,13 @@ class BattleShipEnv(BatchedPomdpEnv):
         self.last_action = -1
 
     def _state_to_ref(self, words):
-        occ, vis, rem, _ = self.unpack(words.reshape(1, 8))
+        X, Y = self.grid.x_size, self.grid.y_size
+        occ_bits = words[0] | (words[1] << 32) | (words[2] << 64) | ((words[3] & 0x00FFFFFF) << 96)
+        vis_bits = words[4] | (words[5] << 32) | (words[6] << 64) | (words[7] << 96)
         st = ShipState()
-        st.total_remaining = int(rem[0])
-        st.occupied = occ[0].cpu().numpy()
-        st.visited = vis[0].cpu().numpy()
+        st.total_remaining = (words[3] >> 24) & 0x7F
+        st.occupied = np.array([[(occ_bits >> (X * y + x)) & 1 for y in range(Y)] for x in range(X)], dtype=bool)
+        st.visited = np.array([[(vis_bits >> (X * y + x)) & 1 for y in range(Y)] for x in range(X)], dtype=bool)
         return st
 
     def _state_from_ref(self, state):
@@ -131,10 +133,11 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _generate_legal(self, state=None):
         """battleship.py:157-165: the unvisited cells."""
-        unvisited = self.legal_mask(None if state is None else state.reshape(-1, 8))   # action index = x_size * y + x
         if self._scalar and state is None:
-            return [int(a) for a in torch.nonzero(unvisited[0])[:, 0]]
-        return unvisited
+            w = self._host_words()
+            vis_bits = w[4] | (w[5] << 32) | (w[6] << 64) | (w[7] << 96)
+            return [a for a in range(self.grid.n_tiles) if not (vis_bits >> a) & 1]     # action index = x_size * y + x
+        return self.legal_mask(None if state is None else state.reshape(-1, 8))
 
     def _generate_preferred(self, history):
         return self._generate_legal()

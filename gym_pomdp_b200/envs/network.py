@@ -78,7 +78,7 @@ class NetworkEnv(BatchedPomdpEnv):
         self._server = 0
 
     def _state_to_ref(self, words):
-        return self.unpack(words.reshape(1))[0].cpu().numpy().astype(np.int8)
+        return np.array([(words[0] >> m) & 1 for m in range(self._n_machines)], dtype=np.int8)
 
     def _state_from_ref(self, state):
         return self.pack(np.asarray(state).reshape(1, -1))

@@ -181,14 +181,19 @@ class RockEnv(BatchedPomdpEnv):
         if self._scalar:
             self._side = [dict(count=0, measured=0, lkw=1., lkv=1., prob_valuable=.5) for _ in range(self.num_rocks)]
 
+    def _decode_py(self, words):
+        """host ints -> (x, y, [status...])"""
+        v = words[0] | (words[1] << 32 if len(words) > 1 else 0)
+        return v & 15, (v >> 4) & 15, [(0, 1, 0, -1)[(v >> (8 + 2 * i)) & 3] for i in range(self.num_rocks)]
+
     def _state_to_ref(self, words):
         """The reference's ``_encode_dict`` layout (rock.py:507-516)."""
-        x, y, status, _ = self.unpack(words.reshape(1, -1) if self.state_words > 1 else words.reshape(1))
+        x, y, status = self._decode_py(words)
         side = self._side or [dict(count=0, measured=0, lkw=1., lkv=1., prob_valuable=.5)] * self.num_rocks
-        rocks = [{"status": int(status[0, i]), "pos": self._rock_pos[i], "count": side[i]["count"],
+        rocks = [{"status": status[i], "pos": self._rock_pos[i], "count": side[i]["count"],
                   "measured": side[i]["measured"], "lkw": side[i]["lkw"], "lkv": side[i]["lkv"],
                   "prob_valuable": side[i]["prob_valuable"]} for i in range(self.num_rocks)]
-        return {"agent_pos": Coord(int(x[0]), int(y[0])), "rocks": rocks, "target": -1}
+        return {"agent_pos": Coord(x, y), "rocks": rocks, "target": -1}
 
     def _state_from_ref(self, state):
         ax, ay = state["agent_pos"]
@@ -214,8 +219,8 @@ class RockEnv(BatchedPomdpEnv):
         self._query += 1
         if action > SAMPLE and ob != NULL:        # rock.py:177-191: belief side-stats of the checked rock
             r = self._side[action - SAMPLE - 1]
-            x, y, _, _ = self.unpack(self.state)
-            eff = self._efficiency((int(x[0]), int(y[0])), self._rock_pos[action - SAMPLE - 1])
+            x, y, _ = self._decode_py(self._host_words())
+            eff = self._efficiency((x, y), self._rock_pos[action - SAMPLE - 1])
             r["measured"] += 1
             if ob == GOOD:
                 r["count"] += 1
@@ -234,8 +239,7 @@ class RockEnv(BatchedPomdpEnv):
         mask [n, n_actions] (a set; the reference's duplicate entries for Rock(15,15)'s
         doubled rock collapse)."""
         if self._scalar and state is None:
-            x, y, status, _ = (t[0] for t in self.unpack(self.state))
-            x, y = int(x), int(y)
+            x, y, status = self._decode_py(self._host_words())
             n = self.grid.x_size
             legal = [1]
             if y + 1 < n:

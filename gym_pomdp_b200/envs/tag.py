@@ -110,10 +110,11 @@ class TagEnv(BatchedPomdpEnv):
         self.last_action = 4
 
     def _state_to_ref(self, words):
-        agent, opp, nop, _ = self.unpack(words.reshape(1))
-        st = TagState(self.grid.get_tag_coord(int(agent[0])))
-        st.opponent_pos = [self.grid.get_tag_coord(int(o)) for o in opp[0]]
-        st.num_opp = int(nop[0])
+        v = words[0]
+        st = TagState(self.grid.get_tag_coord(v & 31))
+        st.opponent_pos = [self.grid.get_tag_coord((v >> (5 + 5 * j)) & 31) for j in range(self.num_opponents)]
+        nop = (v >> 25) & 63
+        st.num_opp = nop - 64 if nop >= 32 else nop
         return st
 
     def _state_from_ref(self, state):

@@ -62,7 +62,7 @@ class TigerEnv(BatchedPomdpEnv):
         self.last_action = LISTEN
 
     def _state_to_ref(self, words):
-        return int(words.reshape(1)[0].item()) & 1          # tiger.py:107-109: the state is a plain int
+        return words[0] & 1          # tiger.py:107-109: the state is a plain int
 
     def _state_from_ref(self, state):
         return self.pack([int(state)])
