@@ -6,7 +6,7 @@ cpu_baseline leg; never by gym_pomdp_b200/.  Build with ``make -C oracle``.
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import c_double, c_int, c_int64, c_uint32, c_uint64, c_void_p
 
 import numpy as np
 

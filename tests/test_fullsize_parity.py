@@ -12,7 +12,6 @@ The ``gpu`` run uses those sizes through the CUDA library; the CPU suite runs th
 at 2^14 on the host build of the functors.
 """
 import numpy as np
-import pytest
 import torch
 
 import gym_pomdp_b200 as gp
