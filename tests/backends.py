@@ -17,6 +17,8 @@ GOLDEN_SEED = 0x5EED
 
 
 def build_hostsim():
+    if os.environ.get("POMDP_HOSTSIM_SO"):          # an instrumented build (tests/test_hostsim_ubsan.py)
+        return os.environ["POMDP_HOSTSIM_SO"]
     src = os.path.join(HOSTSIM_DIR, "pomdp_hostsim.cpp")
     deps = [src, os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_core.h"), os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_envs.h"),
             os.path.join(ROOT, "gym_pomdp_b200", "csrc", "pomdp_host.h"), os.path.join(ROOT, "include", "pomdp_b200.h")]
