@@ -14,10 +14,13 @@
  *
  * Conventions (all entry points)
  * ------------------------------
- *  - Plain pointers and sizes only; every array pointer is DEVICE memory owned by the
- *    caller (torch tensors on the Python side).  The library never allocates, frees or
- *    keeps a pointer past the call's stream ordering.  `params` structs are HOST memory,
- *    read during the call only.
+ *  - Plain pointers and sizes only; every array pointer is DEVICE-ACCESSIBLE memory owned by
+ *    the caller: device memory (torch tensors on the Python side), or pinned host memory
+ *    mapped into the device address space (cudaHostAlloc under unified addressing) -- the
+ *    kernels then stream over PCIe directly ("zero-copy"; used by the single-instance Python
+ *    mode and by simulate_host(zero_copy=True)).  The library never allocates, frees or keeps a
+ *    pointer past the call's stream ordering.  `params` structs are HOST memory, read during
+ *    the call only.  Static tables (`d_table`) should live in device memory.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
  *    asynchronous on it.  The caller selects the device (cudaSetDevice / torch device
  *    guard) -- pointers, stream and current device must agree.
