@@ -6,7 +6,7 @@ env.step(a)`` is here three kernel launches per real step, whatever the number o
     python examples/rock_particle_filter.py [--particles 1048576] [--steps 40] [--device cuda:0]
 
 Per real step:  for each candidate action, ONE fused rollout launch evaluates it from every particle (first step with
-that action, then uniform-legal rollouts);  the real env steps;  ``simulate`` moves all particles with the chosen
+that action, then a uniform-legal rollout: ``rollout(first_action=a)``);  the real env steps;  ``simulate`` moves all particles with the chosen
 action, ``observation_prob`` (the reference's ``_compute_prob``) weights them by the real observation, and
 ``torch.multinomial`` resamples.  ``belief_histogram`` summarises the belief (per-rock "still good" counts).
 """
@@ -35,10 +35,8 @@ def run(n_particles=1 << 20, steps=40, device="cuda:0", seed=7, rollout_depth=20
         legal = sim.legal_mask(sub).float().mean(0) > 0.5
         best, best_q = 1, -1e30
         for a in torch.nonzero(legal)[:, 0].tolist():
-            act = torch.full((sub.shape[0],), a, dtype=torch.int32, device=sub.device)
-            s1, _, r1, f1 = sim.simulate(sub, act)
-            _, ret, _, _ = sim.rollout(s1, max_steps=rollout_depth)
-            q = float((r1.double() + sim._discount * ret).mean())
+            _, ret, _, _ = sim.rollout(sub, max_steps=rollout_depth, first_action=a)     # Q(s, a) samples: one launch
+            q = float(ret.mean())
             if q > best_q:
                 best, best_q = a, q
         # ---- act in the real env

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -57,7 +57,7 @@ _STEP_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_vo
 _RESET_TAIL = [_P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 
 _POLICY_TAIL = [_P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
-_ROLLOUT_TAIL = [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_int32, c_double, c_void_p]
+_ROLLOUT_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_int32, c_double, c_void_p]
 
 _STEPP_TAIL = [_P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 

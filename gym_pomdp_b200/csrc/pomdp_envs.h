@@ -232,11 +232,12 @@ struct NetworkEnvP {
 template <class Env>
 POMDP_HD void rollout1(const typename Env::Params& p, const unsigned char* tbl, typename Env::State& s,
                        const PhiloxKey& seed, uint64_t env, uint32_t ctr0, int32_t max_steps, double gamma,
-                       RolloutAcc& acc) {
+                       RolloutAcc& acc, bool has_first = false, int32_t first_action = 0) {
     acc.init(Env::is_done(s));
     for (int32_t t = 0; t < max_steps && !Env::is_done(s); ++t) {
         const uint32_t ctr = ctr0 + (uint32_t)t;
-        const int32_t a = Env::policy(p, tbl, s, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
+        const int32_t a = (t == 0 && has_first) ? first_action
+                                                : Env::policy(p, tbl, s, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
         typename Env::State s2;
         int32_t ob, fl;
         float rw;

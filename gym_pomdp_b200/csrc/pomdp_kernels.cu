@@ -335,7 +335,8 @@ pomdp_policy_kernel(const __grid_constant__ typename Env::Params p, const void* 
 template <class Env, bool kVec>
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
-                     const int32_t* state, int32_t* final_state, double* __restrict__ ret, int32_t* __restrict__ steps,
+                     const int32_t* state, const int32_t* __restrict__ first_action, int32_t* final_state,
+                     double* __restrict__ ret, int32_t* __restrict__ steps,
                      int32_t* __restrict__ flags, int64_t n, uint64_t goff, const __grid_constant__ PhiloxKey seed,
                      uint32_t ctr0, int32_t max_steps, double gamma, uint32_t table_bytes) {
     typedef typename Env::State S;
@@ -359,6 +360,10 @@ pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void*
             int32_t nst[4] = {0, 0, 0, 0}, facc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) facc[j] = Env::is_done(s[j]) ? (int32_t)FLAG_DONE : 0;
+            int4 fa = make_int4(0, 0, 0, 0);
+            if (first_action) fa = ((reinterpret_cast<uintptr_t>(first_action) & 15) == 0)
+                                       ? ld_stream4(first_action + i)
+                                       : make_int4(first_action[i], first_action[i + 1], first_action[i + 2], first_action[i + 3]);
             for (int32_t t = 0; t < max_steps; ++t) {
                 bool act[4], any = false;
 #pragma unroll
@@ -366,8 +371,9 @@ pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void*
                 if (!any) break;
                 const uint32_t ctr = ctr0 + (uint32_t)t;
                 const U4 q = draw_quad(seed, group, ctr, DOMAIN_POLICY, 0);
-                const int32_t a[4] = {Env::policy(p, tbl, s[0], q.x), Env::policy(p, tbl, s[1], q.y),
-                                      Env::policy(p, tbl, s[2], q.z), Env::policy(p, tbl, s[3], q.w)};
+                int32_t a[4] = {Env::policy(p, tbl, s[0], q.x), Env::policy(p, tbl, s[1], q.y),
+                                Env::policy(p, tbl, s[2], q.z), Env::policy(p, tbl, s[3], q.w)};
+                if (t == 0 && first_action) { a[0] = fa.x; a[1] = fa.y; a[2] = fa.z; a[3] = fa.w; }   // Q(s, a): the caller's action first
                 S s2[4];
                 int32_t ob[4], fl[4];
                 float rw[4];
@@ -393,7 +399,8 @@ pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void*
     for (int64_t i = scalar_from + tid; i < n; i += nthreads) {
         S s = load_state1(state, i, S());
         RolloutAcc acc;
-        rollout1<Env>(p, tbl, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, acc);
+        rollout1<Env>(p, tbl, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, acc, first_action != nullptr,
+                      first_action ? first_action[i] : 0);
         if (final_state) store_state1(final_state, i, s);
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
@@ -506,7 +513,8 @@ pomdp_battleship_policy_kernel(const __grid_constant__ ShipDev p, const int32_t*
     }
 }
 __global__ void __launch_bounds__(POMDP_THREADS)
-pomdp_battleship_rollout_kernel(const __grid_constant__ ShipDev p, const int32_t* state, int32_t* final_state,
+pomdp_battleship_rollout_kernel(const __grid_constant__ ShipDev p, const int32_t* state,
+                                const int32_t* __restrict__ first_action, int32_t* final_state,
                                 double* __restrict__ ret, int32_t* __restrict__ steps, int32_t* __restrict__ flags,
                                 int64_t n, uint64_t goff, const __grid_constant__ PhiloxKey seed, uint32_t ctr0,
                                 int32_t max_steps, double gamma) {
@@ -518,7 +526,9 @@ pomdp_battleship_rollout_kernel(const __grid_constant__ ShipDev p, const int32_t
         RolloutAcc acc;
         acc.init((w[3] >> 31) != 0);
         for (int32_t t = 0; t < max_steps && !(w[3] >> 31); ++t) {
-            const int32_t a = battleship_policy(p, w, draw_word(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, DOMAIN_POLICY, 0));
+            const int32_t a = (t == 0 && first_action)
+                                  ? first_action[i]
+                                  : battleship_policy(p, w, draw_word(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, DOMAIN_POLICY, 0));
             int32_t ob, fl;
             float rw;
             battleship_step(p, w, a, w2, ob, rw, fl);
@@ -1040,11 +1050,13 @@ int launch_policy(const typename Env::Params& p, const void* d_table, uint32_t t
 
 template <class Env>
 int launch_rollout(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
-                   const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags, int64_t n,
+                   const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps,
+                   int32_t* flags, int64_t n,
                    int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps, double discount, void* stream,
                    const char* what) {
     int rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what);
     if (rc) return rc;
+    if ((uintptr_t)first_action & 3) return host::fail(POMDP_E_ALIGN, "%s: first_action must be 4-byte aligned", what);
     if (n == 0) return 0;
     if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
         return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
@@ -1055,14 +1067,14 @@ int launch_rollout(const typename Env::Params& p, const void* d_table, uint32_t 
         auto k = pomdp_rollout_kernel<Env, true>;
         if ((rc = allow_smem(k, smem))) return rc;
         k<<<grid_for(k, (n + 3) >> 2, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
-            p, d_table, state, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps, discount,
-            table_bytes);
+            p, d_table, state, first_action, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps,
+            discount, table_bytes);
     } else {
         auto k = pomdp_rollout_kernel<Env, false>;
         if ((rc = allow_smem(k, smem))) return rc;
         k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
-            p, d_table, state, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps, discount,
-            table_bytes);
+            p, d_table, state, first_action, final_state, ret, steps, flags, n, (uint64_t)goff, key, step_ctr, max_steps,
+            discount, table_bytes);
     }
     return finish(what);
 }
@@ -1343,13 +1355,13 @@ int pomdp_rock_policy(const PomdpRockParams* q, const void* d_table, const int32
     POMDP_ROCK_DISPATCH(launch_policy, d, d_table, d.table_bytes, d.smem_bytes, state, action, n, goff, seed, step_ctr,
                         stream, "pomdp_rock_policy");
 }
-int pomdp_rock_rollout(const PomdpRockParams* q, const void* d_table, const int32_t* state, int32_t* final_state,
+int pomdp_rock_rollout(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* first_action, int32_t* final_state,
                        double* ret, int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
                        uint32_t step_ctr, int32_t max_steps, double discount, void* stream) {
     RockDev d;
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
-    POMDP_ROCK_DISPATCH(launch_rollout, d, d_table, d.table_bytes, d.smem_bytes, state, final_state, ret, steps, flags, n,
+    POMDP_ROCK_DISPATCH(launch_rollout, d, d_table, d.table_bytes, d.smem_bytes, state, first_action, final_state, ret, steps, flags, n,
                         goff, seed, step_ctr, max_steps, discount, stream, "pomdp_rock_rollout");
 }
 #undef POMDP_ROCK_DISPATCH
@@ -1362,7 +1374,7 @@ int pomdp_tag_policy(const PomdpTagParams* q, const void* d_table, const int32_t
     const uint32_t tb = (uint32_t)sizeof(TagTables);
     return launch_policy<TagEnvT<1>>(d, d_table, tb, tb, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
 }
-int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                       int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                       int32_t max_steps, double discount, void* stream) {
     TagDev d;
@@ -1370,9 +1382,9 @@ int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_
     if (rc) return rc;
     const uint32_t tb = (uint32_t)sizeof(TagTables);
     if (d.n_opp == 1)
-        return launch_rollout<TagEnvT<1>>(d, d_table, tb, tb, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+        return launch_rollout<TagEnvT<1>>(d, d_table, tb, tb, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                           max_steps, discount, stream, "pomdp_tag_rollout");
-    return launch_rollout<TagEnvT<4>>(d, d_table, tb, tb, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+    return launch_rollout<TagEnvT<4>>(d, d_table, tb, tb, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                       max_steps, discount, stream, "pomdp_tag_rollout");
 }
 int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -1382,13 +1394,13 @@ int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t*
     if (rc) return rc;
     return launch_policy<TigerEnvP>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_tiger_policy");
 }
-int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                         int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                         int32_t max_steps, double discount, void* stream) {
     TigerDev d;
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
-    return launch_rollout<TigerEnvP>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+    return launch_rollout<TigerEnvP>(d, nullptr, 0, 0, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                      max_steps, discount, stream, "pomdp_tiger_rollout");
 }
 int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -1398,13 +1410,13 @@ int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int3
     if (rc) return rc;
     return launch_policy<NetworkEnvP>(d, nullptr, 0, 0, state, action, n, goff, seed, step_ctr, stream, "pomdp_network_policy");
 }
-int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                           int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                           int32_t max_steps, double discount, void* stream) {
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
-    return launch_rollout<NetworkEnvP>(d, nullptr, 0, 0, state, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+    return launch_rollout<NetworkEnvP>(d, nullptr, 0, 0, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                        max_steps, discount, stream, "pomdp_network_rollout");
 }
 int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state, int32_t* action, int64_t n,
@@ -1418,7 +1430,7 @@ int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state
     k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, action, n, (uint64_t)goff, philox_key(seed), step_ctr);
     return finish("pomdp_battleship_policy");
 }
-int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                              int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                              int32_t max_steps, double discount, void* stream) {
     ShipDev d;
@@ -1428,8 +1440,8 @@ int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* stat
         return rc;
     if (n == 0) return 0;
     auto k = pomdp_battleship_rollout_kernel;
-    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, final_state, ret, steps, flags, n, (uint64_t)goff,
-                                                                philox_key(seed), step_ctr, max_steps, discount);
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, first_action, final_state, ret, steps, flags, n,
+                                                                (uint64_t)goff, philox_key(seed), step_ctr, max_steps, discount);
     return finish("pomdp_battleship_rollout");
 }
 

@@ -87,9 +87,9 @@ class BatchedPomdpEnv(object):
         _lib.check(fn(*self._c_head(), _lib.ptr(state), _lib.ptr(action), n, self.global_offset, self._seed, ctr,
                       self._stream()), "pomdp_%s_policy" % self._abi)
 
-    def _c_rollout(self, state, final_state, ret, steps, flags, n, ctr, max_steps, discount):
+    def _c_rollout(self, state, final_state, ret, steps, flags, n, ctr, max_steps, discount, first_action=None):
         fn = getattr(_lib.lib(), "pomdp_%s_rollout" % self._abi)
-        _lib.check(fn(*self._c_head(), _lib.ptr(state), _lib.ptr(final_state), _lib.ptr(ret), _lib.ptr(steps),
+        _lib.check(fn(*self._c_head(), _lib.ptr(state), _lib.ptr(first_action), _lib.ptr(final_state), _lib.ptr(ret), _lib.ptr(steps),
                       _lib.ptr(flags), n, self.global_offset, self._seed, ctr, int(max_steps), float(discount),
                       self._stream()), "pomdp_%s_rollout" % self._abi)
 
@@ -221,14 +221,16 @@ class BatchedPomdpEnv(object):
             self._c_policy(state, action, n, ctr)
         return action
 
-    def rollout(self, state=None, max_steps=100, discount=None, out=None, step_ctr=None):
+    def rollout(self, state=None, max_steps=100, discount=None, out=None, step_ctr=None, first_action=None):
         """Monte-Carlo rollouts under the uniform-legal policy, fused into ONE kernel (states stay
         in registers): until done or ``max_steps``,
         ``a = choice(_generate_legal()); ob, rw, done = step(a); ret += rw * disc; disc *= discount``.
 
         Returns (final_state, ret float64[n], steps int32[n], flags int32[n]).  ``discount`` defaults
         to the env's ``_discount``.  Draw for draw identical to ``max_steps`` rounds of
-        ``sample_legal_actions`` + ``simulate`` with counters step_ctr, step_ctr + 1, ..."""
+        ``sample_legal_actions`` + ``simulate`` with counters step_ctr, step_ctr + 1, ...
+        ``first_action`` (int32[n]): step 0 takes these actions instead of a policy draw, so ``ret`` is a
+        Monte-Carlo sample of Q(s, a) -- POMCP's "simulate a, then roll out" in one launch."""
         state = self.state if state is None else state
         n = state.shape[0]
         if out is None:
@@ -240,9 +242,11 @@ class BatchedPomdpEnv(object):
             self._step_ctr = (self._step_ctr + int(max_steps)) & 0xFFFFFFFF
         else:
             ctr = int(step_ctr)
+        if first_action is not None:
+            first_action = torch.as_tensor(first_action, device=state.device).to(torch.int32).expand(n).contiguous()
         with self._guard():
             self._c_rollout(state, final_state, ret, steps, flags, n, ctr, max_steps,
-                            self._discount if discount is None else discount)
+                            self._discount if discount is None else discount, first_action)
         return final_state, ret, steps, flags
 
     def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False, n_streams=3, zero_copy=False):

@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 3
+#define POMDP_ABI_VERSION 4
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -254,7 +254,9 @@ int pomdp_network_step_packed(const PomdpNetworkParams* params,
  *                   _generate_legal list IN ITS ORDER (rock.py:273-291; tag.py:228-229;
  *                   battleship.py:157-165; tiger.py:111-112; network.py:129-130), u from draw
  *                   (domain 2 = POLICY, slot 0) of `step_ctr`.
- * pomdp_E_rollout : the whole loop in ONE kernel, states in registers.  Step t uses counter
+ * pomdp_E_rollout : the whole loop in ONE kernel, states in registers.  `first_action` (int32[n], may be NULL):
+ *                   when given, step 0 takes the caller's action instead of a policy draw -- the Monte-Carlo
+ *                   estimate of Q(s, a) a POMCP simulation needs (act, then roll out).  Step t uses counter
  *                   step_ctr + t for its policy draw and for the step's own draws, so it equals,
  *                   draw for draw, max_steps launches of pomdp_E_policy + pomdp_E_step with
  *                   step_ctr, step_ctr+1, ...  Outputs per env: final_state (may be NULL, may alias
@@ -268,31 +270,31 @@ int pomdp_rock_policy(const PomdpRockParams* params, const void* d_table,
                       const int32_t* state, int32_t* action,
                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
 int pomdp_rock_rollout(const PomdpRockParams* params, const void* d_table,
-                       const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                       const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                        int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                        int32_t max_steps, double discount, void* stream);
 int pomdp_tag_policy(const PomdpTagParams* params, const void* d_table, const int32_t* state, int32_t* action,
                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
 int pomdp_tag_rollout(const PomdpTagParams* params, const void* d_table,
-                      const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                      const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                       int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                       int32_t max_steps, double discount, void* stream);
 int pomdp_battleship_policy(const PomdpBattleshipParams* params, const int32_t* state, int32_t* action,
                             int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
 int pomdp_battleship_rollout(const PomdpBattleshipParams* params,
-                             const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                             const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                              int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                              int32_t max_steps, double discount, void* stream);
 int pomdp_tiger_policy(const PomdpTigerParams* params, const int32_t* state, int32_t* action,
                        int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
 int pomdp_tiger_rollout(const PomdpTigerParams* params,
-                        const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                        const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                         int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                         int32_t max_steps, double discount, void* stream);
 int pomdp_network_policy(const PomdpNetworkParams* params, const int32_t* state, int32_t* action,
                          int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
 int pomdp_network_rollout(const PomdpNetworkParams* params,
-                          const int32_t* state, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                          const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                           int32_t max_steps, double discount, void* stream);
 

@@ -185,7 +185,11 @@ def rock_legal(n, k, x, y, status):
     return legal[:cnt].tolist()
 
 
-def rock_rollout(n, k, stochastic, p_move, x, y, status, seed, goff, ctr0, max_steps, gamma):
+def _fa(first_action):
+    return None if first_action is None else _p(_c(first_action, np.int32))
+
+
+def rock_rollout(n, k, stochastic, p_move, x, y, status, seed, goff, ctr0, max_steps, gamma, first_action=None):
     """Returns (x, y, status, ret, steps, done, err) after the rollouts; inputs are not modified."""
     N = len(x)
     x, y = _c(x, np.int32).copy(), _c(y, np.int32).copy()
@@ -194,48 +198,48 @@ def rock_rollout(n, k, stochastic, p_move, x, y, status, seed, goff, ctr0, max_s
     done, err = np.empty(N, np.uint8), np.empty(N, np.uint8)
     rc = lib().oracle_rock_rollout(c_int(n), c_int(k), c_int(int(stochastic)), c_double(p_move), c_int64(N), _p(x), _p(y),
                                    _p(status), c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps),
-                                   c_double(gamma), _p(ret), _p(steps), _p(done), _p(err))
+                                   c_double(gamma), _fa(first_action), _p(ret), _p(steps), _p(done), _p(err))
     assert rc == 0
     return x, y, status, ret, steps, done.astype(bool), err
 
 
-def tag_rollout(n_opp, move_prob, agent, opp, num_opp, seed, goff, ctr0, max_steps, gamma):
+def tag_rollout(n_opp, move_prob, agent, opp, num_opp, seed, goff, ctr0, max_steps, gamma, first_action=None):
     N = len(agent)
     agent = _c(agent, np.int32).copy()
     opp = _c(opp, np.int32).copy().reshape(N, n_opp)
     num_opp = _c(num_opp, np.int32).copy()
     ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
     lib().oracle_tag_rollout(c_int(n_opp), c_double(move_prob), c_int64(N), _p(agent), _p(opp), _p(num_opp), c_uint64(seed),
-                             c_uint64(goff), c_uint32(ctr0), c_int(max_steps), c_double(gamma), _p(ret), _p(steps), _p(done))
+                             c_uint64(goff), c_uint32(ctr0), c_int(max_steps), c_double(gamma), _fa(first_action), _p(ret), _p(steps), _p(done))
     return agent, opp, num_opp, ret, steps, done.astype(bool)
 
 
-def tiger_rollout(listen_prob, state, seed, goff, ctr0, max_steps, gamma):
+def tiger_rollout(listen_prob, state, seed, goff, ctr0, max_steps, gamma, first_action=None):
     N = len(state)
     state = _c(state, np.int32).copy()
     ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
     lib().oracle_tiger_rollout(c_double(listen_prob), c_int64(N), _p(state), c_uint64(seed), c_uint64(goff), c_uint32(ctr0),
-                               c_int(max_steps), c_double(gamma), _p(ret), _p(steps), _p(done))
+                               c_int(max_steps), c_double(gamma), _fa(first_action), _p(ret), _p(steps), _p(done))
     return state, ret, steps, done.astype(bool)
 
 
-def network_rollout(n, problem_type, machines, seed, goff, ctr0, max_steps, gamma, p=0.1, q=0.33, p_ob=0.95):
+def network_rollout(n, problem_type, machines, seed, goff, ctr0, max_steps, gamma, p=0.1, q=0.33, p_ob=0.95, first_action=None):
     N = len(machines)
     machines = _c(machines, np.int8).copy().reshape(N, n)
     ret, steps = np.empty(N, np.float64), np.empty(N, np.int32)
     rc = lib().oracle_network_rollout(c_int(n), c_int(problem_type), c_double(p), c_double(q), c_double(p_ob), c_int64(N),
                                       _p(machines), c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps),
-                                      c_double(gamma), _p(ret), _p(steps))
+                                      c_double(gamma), _fa(first_action), _p(ret), _p(steps))
     assert rc == 0
     return machines, ret, steps
 
 
-def battleship_rollout(xs, ys, occ, vis, remaining, seed, goff, ctr0, max_steps, gamma):
+def battleship_rollout(xs, ys, occ, vis, remaining, seed, goff, ctr0, max_steps, gamma, first_action=None):
     N = len(remaining)
     vis = _c(vis, np.uint8).copy().reshape(N, xs, ys)
     remaining = _c(remaining, np.int32).copy()
     ret, steps, done = np.empty(N, np.float64), np.empty(N, np.int32), np.empty(N, np.uint8)
     lib().oracle_battleship_rollout(c_int(xs), c_int(ys), c_int64(N), _p(_c(occ, np.uint8)), _p(vis), _p(remaining),
                                     c_uint64(seed), c_uint64(goff), c_uint32(ctr0), c_int(max_steps), c_double(gamma),
-                                    _p(ret), _p(steps), _p(done))
+                                    _fa(first_action), _p(ret), _p(steps), _p(done))
     return vis.astype(bool), remaining, ret, steps, done.astype(bool)

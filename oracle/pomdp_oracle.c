@@ -511,7 +511,7 @@ int oracle_rock_legal(int n, int k, int x, int y, const int8_t* status, int32_t*
 }
 
 int oracle_rock_rollout(int n, int k, int stochastic, double p_move, int64_t N, int32_t* x, int32_t* y, int8_t* status,
-                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, const int32_t* first_action, double* ret,
                         int32_t* steps, uint8_t* done, uint8_t* err) {
     for (int64_t i = 0; i < N; ++i) {
         double r = 0., disc = 1.;
@@ -525,6 +525,7 @@ int oracle_rock_rollout(int n, int k, int stochastic, double p_move, int64_t N, 
             const int cnt = oracle_rock_legal(n, k, x[i], y[i], status + i * k, legal);
             if (cnt < 0) return -1;
             a = legal[below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), cnt)];
+            if (t == 0 && first_action) a = first_action[i];           /* the caller's action first: Q(s, a) */
             dr[0] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 0);
             dr[1] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 1);
             if (oracle_rock_step(n, k, stochastic, p_move, 1, x + i, y + i, status + i * k, &a, dr, &ob, &rw, &fin, &e1))
@@ -540,7 +541,7 @@ int oracle_rock_rollout(int n, int k, int stochastic, double p_move, int64_t N, 
 }
 
 void oracle_tag_rollout(int n_opp, double move_prob, int64_t N, int32_t* agent, int32_t* opp, int32_t* num_opp,
-                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                        uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, const int32_t* first_action, double* ret,
                         int32_t* steps, uint8_t* done) {
     for (int64_t i = 0; i < N; ++i) {
         double r = 0., disc = 1.;
@@ -550,6 +551,7 @@ void oracle_tag_rollout(int n_opp, double move_prob, int64_t N, int32_t* agent, 
             uint32_t dr[8];
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 5), ob;   /* tag.py:228-229 */
             double rw;
+            if (t == 0 && first_action) a = first_action[i];
             for (int s = 0; s < 2 * n_opp; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
             oracle_tag_step(n_opp, move_prob, 1, agent + i, opp + i * n_opp, num_opp + i, &a, dr, &ob, &rw, &fin);
             r += rw * disc;
@@ -561,7 +563,7 @@ void oracle_tag_rollout(int n_opp, double move_prob, int64_t N, int32_t* agent, 
 }
 
 void oracle_tiger_rollout(double listen_prob, int64_t N, int32_t* state, uint64_t seed, uint64_t goff, uint32_t ctr0,
-                          int max_steps, double gamma, double* ret, int32_t* steps, uint8_t* done) {
+                          int max_steps, double gamma, const int32_t* first_action, double* ret, int32_t* steps, uint8_t* done) {
     for (int64_t i = 0; i < N; ++i) {
         double r = 0., disc = 1.;
         int t = 0;
@@ -570,6 +572,7 @@ void oracle_tiger_rollout(double listen_prob, int64_t N, int32_t* state, uint64_
             uint32_t dr[2];
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 3), ob;   /* tiger.py:111-112 */
             double rw;
+            if (t == 0 && first_action) a = first_action[i];
             dr[0] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 0);
             dr[1] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 1);
             oracle_tiger_step(listen_prob, 1, state + i, &a, dr, &ob, &rw, &fin);
@@ -582,7 +585,7 @@ void oracle_tiger_rollout(double listen_prob, int64_t N, int32_t* state, uint64_
 }
 
 int oracle_network_rollout(int n, int problem_type, double p, double q, double p_ob, int64_t N, int8_t* machines,
-                           uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                           uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, const int32_t* first_action, double* ret,
                            int32_t* steps) {
     for (int64_t i = 0; i < N; ++i) {
         double r = 0., disc = 1.;
@@ -590,6 +593,7 @@ int oracle_network_rollout(int n, int problem_type, double p, double q, double p
             uint32_t dr[65];
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 2 * n + 1), ob;   /* network.py:129-130 */
             double rw;
+            if (t == 0 && first_action) a = first_action[i];
             for (int s = 0; s <= n; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
             if (oracle_network_step(n, problem_type, p, q, p_ob, 1, machines + i * n, &a, dr, &ob, &rw)) return -1;
             r += rw * disc;
@@ -602,7 +606,7 @@ int oracle_network_rollout(int n, int problem_type, double p, double q, double p
 
 /* battleship.py:157-165: legal = unvisited cells in increasing action order */
 void oracle_battleship_rollout(int xs, int ys, int64_t N, const uint8_t* occ, uint8_t* vis, int32_t* remaining,
-                               uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, double* ret,
+                               uint64_t seed, uint64_t goff, uint32_t ctr0, int max_steps, double gamma, const int32_t* first_action, double* ret,
                                int32_t* steps, uint8_t* done) {
     const int n_tiles = xs * ys;
     for (int64_t i = 0; i < N; ++i) {
@@ -618,6 +622,7 @@ void oracle_battleship_rollout(int xs, int ys, int64_t N, const uint8_t* occ, ui
                 if (!vis[i * n_tiles + x * ys + y]) legal[cnt++] = act;
             }
             a = cnt ? legal[below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), cnt)] : 0;
+            if (t == 0 && first_action) a = first_action[i];
             oracle_battleship_step(xs, ys, 1, occ + i * n_tiles, vis + i * n_tiles, remaining + i, &a, &ob, &rw, &fin);
             r += rw * disc;
             disc *= gamma;

@@ -62,7 +62,8 @@ int policy_host(const typename Env::Params& d, const void* table, const int32_t*
     return 0;
 }
 template <class Env>
-int rollout_host(const typename Env::Params& d, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+int rollout_host(const typename Env::Params& d, const void* table, const int32_t* state, const int32_t* first_action,
+                 int32_t* final_state, double* ret,
                  int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
                  double gamma, const char* what) {
     int rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what);
@@ -72,7 +73,8 @@ int rollout_host(const typename Env::Params& d, const void* table, const int32_t
     for (int64_t i = 0; i < n; ++i) {
         typename Env::State s = load_any<typename Env::State>(state, i);
         RolloutAcc acc;
-        rollout1<Env>(d, tbl, s, key, (uint64_t)(goff + i), step, max_steps, gamma, acc);
+        rollout1<Env>(d, tbl, s, key, (uint64_t)(goff + i), step, max_steps, gamma, acc, first_action != nullptr,
+                      first_action ? first_action[i] : 0);
         if (final_state) store_state(final_state, i, s);
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
     }
@@ -382,13 +384,13 @@ int pomdp_rock_policy(const PomdpRockParams* q, const void* table, const int32_t
     if (rc) return rc;
     HOSTSIM_ROCK_DISPATCH(policy_host, d, table, state, action, n, goff, seed, step, "pomdp_rock_policy");
 }
-int pomdp_rock_rollout(const PomdpRockParams* q, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_rock_rollout(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                        int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
                        int32_t max_steps, double gamma, void*) {
     RockDev d;
     int rc = host::make_rock(q, &d, nullptr);
     if (rc) return rc;
-    HOSTSIM_ROCK_DISPATCH(rollout_host, d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+    HOSTSIM_ROCK_DISPATCH(rollout_host, d, table, state, first_action, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                           "pomdp_rock_rollout");
 }
 int pomdp_tag_policy(const PomdpTagParams* q, const void* table, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -398,7 +400,7 @@ int pomdp_tag_policy(const PomdpTagParams* q, const void* table, const int32_t* 
     if (rc) return rc;
     return policy_host<TagEnvT<1>>(d, table, state, action, n, goff, seed, step, "pomdp_tag_policy");
 }
-int pomdp_tag_rollout(const PomdpTagParams* q, const void* table, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_tag_rollout(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                       int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
                       double gamma, void*) {
     TagDev d;
@@ -406,9 +408,9 @@ int pomdp_tag_rollout(const PomdpTagParams* q, const void* table, const int32_t*
     if (rc) return rc;
     if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
     if (d.n_opp == 1)
-        return rollout_host<TagEnvT<1>>(d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+        return rollout_host<TagEnvT<1>>(d, table, state, first_action, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                                         "pomdp_tag_rollout");
-    return rollout_host<TagEnvT<4>>(d, table, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+    return rollout_host<TagEnvT<4>>(d, table, state, first_action, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                                     "pomdp_tag_rollout");
 }
 int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -418,13 +420,13 @@ int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t*
     if (rc) return rc;
     return policy_host<TigerEnvP>(d, nullptr, state, action, n, goff, seed, step, "pomdp_tiger_policy");
 }
-int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, int32_t* final_state, double* ret, int32_t* steps,
+int pomdp_tiger_rollout(const PomdpTigerParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps,
                         int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
                         double gamma, void*) {
     TigerDev d;
     int rc = host::make_tiger(q, &d);
     if (rc) return rc;
-    return rollout_host<TigerEnvP>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+    return rollout_host<TigerEnvP>(d, nullptr, state, first_action, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                                    "pomdp_tiger_rollout");
 }
 int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -434,13 +436,13 @@ int pomdp_network_policy(const PomdpNetworkParams* q, const int32_t* state, int3
     if (rc) return rc;
     return policy_host<NetworkEnvP>(d, nullptr, state, action, n, goff, seed, step, "pomdp_network_policy");
 }
-int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                           int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
                           int32_t max_steps, double gamma, void*) {
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
-    return rollout_host<NetworkEnvP>(d, nullptr, state, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
+    return rollout_host<NetworkEnvP>(d, nullptr, state, first_action, final_state, ret, steps, flags, n, goff, seed, step, max_steps, gamma,
                                      "pomdp_network_rollout");
 }
 int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -455,7 +457,7 @@ int pomdp_battleship_policy(const PomdpBattleshipParams* q, const int32_t* state
                                       draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0));
     return 0;
 }
-int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, int32_t* final_state, double* ret,
+int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                              int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
                              int32_t max_steps, double gamma, void*) {
     ShipDev d;
@@ -470,7 +472,9 @@ int pomdp_battleship_rollout(const PomdpBattleshipParams* q, const int32_t* stat
         RolloutAcc acc;
         acc.init((w[3] >> 31) != 0);
         for (int32_t t = 0; t < max_steps && !(w[3] >> 31); ++t) {
-            const int32_t a = battleship_policy(d, w, draw_word(key, (uint64_t)(goff + i), step + (uint32_t)t, DOMAIN_POLICY, 0));
+            const int32_t a = (t == 0 && first_action)
+                                  ? first_action[i]
+                                  : battleship_policy(d, w, draw_word(key, (uint64_t)(goff + i), step + (uint32_t)t, DOMAIN_POLICY, 0));
             int32_t ob, fl;
             float rw;
             battleship_step(d, w, a, w2, ob, rw, fl);

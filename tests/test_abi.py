@@ -144,9 +144,9 @@ def test_error_convention(which):
     assert L.pomdp_tag_table_bytes() == 4224 and L.pomdp_tag_build_table(None) == E_BADARG
     # rollouts / policy: same conventions
     d8 = np.zeros(8, np.float64).ctypes.data
-    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, p, p, d8, p, p, 4, 0, 0, 0, -1, .95, None) == E_BADARG      # max_steps < 0
-    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, p, p, d8 + 4, p, p, 4, 0, 0, 0, 5, .95, None) == E_ALIGN    # float64 returns
-    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, None, None, None, None, None, 0, 0, 0, 0, 5, .95, None) == 0
+    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, p, None, p, d8, p, p, 4, 0, 0, 0, -1, .95, None) == E_BADARG      # max_steps < 0
+    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, p, None, p, d8 + 4, p, p, 4, 0, 0, 0, 5, .95, None) == E_ALIGN    # float64 returns
+    assert L.pomdp_rock_rollout(ctypes.byref(ok), p, None, None, None, None, None, None, 0, 0, 0, 0, 5, .95, None) == 0
     assert L.pomdp_tiger_policy(ctypes.byref(_lib.TigerParams(.85)), p, None, 4, 0, 0, 0, None) == E_BADARG
     assert L.pomdp_tiger_policy(ctypes.byref(_lib.TigerParams(.85)), p, p, 4, -4, 0, 0, None) == E_BADARG         # global_offset < 0
     assert L.pomdp_network_step(ctypes.byref(_lib.NetworkParams(31, 3, .1, .33, .95)), p, p, p, p, p, p, 4, 0, 0, 0,

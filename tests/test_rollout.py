@@ -231,3 +231,33 @@ def test_fused_rollout_equals_policy_plus_step_launches(backend, name, kw, goff)
     # max_steps = 0 is the identity
     f3, r3, s3, fl3 = env.rollout(s0, max_steps=0, step_ctr=10)
     assert torch.equal(f3, s0) and not r3.any() and not s3.any()
+
+
+@pytest.mark.parametrize("name,kw", [("Rock-v0", dict(board_size=11, num_rocks=11)), ("Tag-v0", {}), ("Tiger-v0", {}),
+                                     ("Network-v0", {}), ("Battleship-v0", dict(board_size=(10, 10)))])
+def test_rollout_with_first_action_is_simulate_then_rollout(backend, name, kw):
+    """Q(s, a) samples: ``rollout(first_action=a)`` == ``simulate(s, a)`` at counter c, then a policy rollout from c + 1,
+    with the first reward undiscounted and the rest discounted once more -- and it matches the C oracle."""
+    N, T = 1001, 25
+    env = gp.make(name, batch_size=N, device=backend, seed=SEED, **kw)
+    s0, _ = env.init_states(N, step_ctr=1)
+    rs = np.random.RandomState(5)
+    a0 = torch.as_tensor(rs.randint(0, env.action_space.n, N), device=backend).int()
+    final, ret, steps, flags = env.rollout(s0, max_steps=T, step_ctr=10, first_action=a0)
+    s1, _, r1, f1 = env.simulate(s0, a0, step_ctr=10)
+    f2, ret2, steps2, fl2 = env.rollout(s1, max_steps=T - 1, step_ctr=11)
+    assert torch.equal(final, f2) and torch.equal(steps, steps2 + 1) and torch.equal(flags, f1 | fl2)
+    if name == "Rock-v0":
+        # same value through the oracle (the Python-side recombination r1 + gamma * ret2 rounds differently)
+        x, y, st, _ = (v.cpu().numpy() for v in env.unpack(s0))
+        ex, ey, est, eret, esteps, edone, err = C.rock_rollout(11, 11, False, 0.8, x, y, st, SEED, 0, 10, T, env._discount,
+                                                               first_action=a0.cpu().numpy())
+        assert np.array_equal(ret.cpu().numpy(), eret) and np.array_equal(steps.cpu().numpy(), esteps)
+    elif name == "Tag-v0":
+        ag, op, nop, _ = (v.cpu().numpy() for v in env.unpack(s0))
+        _, _, _, eret, esteps, _ = C.tag_rollout(1, 0.8, ag, op, nop, SEED, 0, 10, T, env._discount, first_action=a0.cpu().numpy())
+        assert np.array_equal(ret.cpu().numpy(), eret) and np.array_equal(steps.cpu().numpy(), esteps)
+    else:
+        r1d = torch.round(r1.double().cpu() * 10) / 10 if name == "Network-v0" else r1.double().cpu()
+        approx = r1d + env._discount * ret2.cpu() * ((f1.cpu() & 1) == 0)
+        assert torch.allclose(ret.cpu(), approx, rtol=1e-12, atol=1e-9)
