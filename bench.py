@@ -52,7 +52,8 @@ L2_BYTES = 126 * 2 ** 20
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=10000,
+                    help="timed launches (default: ~175 ms of timed region, long enough to sample clocks inside it)")
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--board", type=int, default=11)
@@ -65,7 +66,7 @@ def parse():
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off; "
                          "measured to slow graph replay by ~8%, so never on for a reported number)")
-    ap.add_argument("--clock-period", type=float, default=0.01, help="NVML polling period (s) during the timed region")
+    ap.add_argument("--clock-period", type=float, default=0.005, help="NVML polling period (s) during the timed region")
     return ap.parse_args()
 
 
