@@ -250,6 +250,9 @@ int pomdp_network_step_packed(const PomdpNetworkParams* params,
  *         ob, rw, done, _ = env.step(a)                       # pomdp_E_step
  *         r += rw * discount;  discount *= gamma;  t += 1
  *
+ * (rock.py:563 draws from _generate_preferred(history), which IS _generate_legal() unless the env was built
+ * with use_heuristic=True -- rock.py:293-295; the history-dependent heuristic is not batched.)
+ *
  * pomdp_E_policy  : action[i] = legal_i[floor(u * len(legal_i))], legal_i = the reference's
  *                   _generate_legal list IN ITS ORDER (rock.py:273-291; tag.py:228-229;
  *                   battleship.py:157-165; tiger.py:111-112; network.py:129-130), u from draw

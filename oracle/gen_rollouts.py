@@ -1,5 +1,6 @@
 """Record ROLLOUTS of the unmodified reference under its own ``_generate_legal`` + ``step``
-(the loops at rock.py:563-572 and tag.py:310-316) into tests/golden/rollouts.npz.
+(the loops at rock.py:563-572 and tag.py:310-316; rock.py:563's ``_generate_preferred(history)`` is
+``_generate_legal()`` for the default ``use_heuristic=False``, rock.py:293-295) into tests/golden/rollouts.npz.
 
 TEST INFRASTRUCTURE ONLY; runs in the build container (the GPU box has no /root/reference).
 Run:  python oracle/gen_rollouts.py         (deterministic, about 10 s)
