@@ -383,8 +383,10 @@ POMDP_HD int32_t rock_policy(const RockDev& p, const RockTableHdr* __restrict__ 
 // ============================================================================= Tag ===
 struct TagDev {
     int32_t n_opp;
-    int32_t pad;
-    uint64_t move_T;  // ceil(move_prob * 2^32)
+    uint32_t move_on;      // move_prob > 0
+    uint64_t move_T;       // ceil(move_prob * 2^32)
+    uint32_t move_thr_m1;  // move_T - 1 (valid when move_on): binomial(1, move_prob) = [r <= move_thr_m1]
+    uint32_t pad;
 };
 constexpr uint32_t TAG_DONE = 0x80000000u;
 constexpr int TAG_CELLS = 29;
@@ -413,7 +415,7 @@ POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
 
 // Static maps of the fixed 29-cell board, derived from the functions above on the host (pomdp_host.h:
 // make_tag_table) and staged into shared memory by ONE TMA bulk copy per CTA, like Rock's.
-//   pair[agent * 32 + opp]  bits 5c..5c+4 (c = 0..3): the opponent's cell if element c of the reference's move
+//   pair[opp * 32 + agent]  (= pair[state & 1023] for the one-opponent env)  bits 5c..5c+4 (c = 0..3): the opponent's cell if element c of the reference's move
 //                           multiset (tag.py:260-280) is drawn -- the move's target, or `opp` itself when the target
 //                           is off the board (tag.py:206-207);  bits 20-22: the multiset's length
 //   mv[agent]               bits 5a..5a+4 (a = 0..3): the agent's cell after move a (tag.py:133-137)
@@ -453,8 +455,8 @@ POMDP_HD uint32_t tag_mv_entry(int agent) {
 }
 POMDP_HD void tag_build_tables(TagTables* T) {
     for (int i = 0; i < 32 * 32; ++i) {
-        const int agent = i >> 5, opp = i & 31;
-        T->pair[i] = (agent < TAG_CELLS && opp < TAG_CELLS) ? tag_pair_entry(agent, opp) : 0u;
+        const int opp = i >> 5, agent = i & 31;
+        T->pair[i] = (agent < TAG_CELLS && opp < TAG_CELLS) ? tag_pair_entry(agent, opp) : 0u;   // never 0 for a valid pair
     }
     for (int i = 0; i < 32; ++i) T->mv[i] = i < TAG_CELLS ? tag_mv_entry(i) : 0u;
 }
@@ -465,29 +467,30 @@ POMDP_HD void tag_build_tables(TagTables* T) {
 POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w_move,
                             uint32_t w_pick, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     const uint32_t agent = s & 31u, opp = (s >> 5) & 31u;
-    const int nopp = tag_num_opp(s);
-    const uint32_t e = T->pair[agent * 32u + opp];
+    const uint32_t e = T->pair[s & 1023u];                                                // 0 <=> a cell id outside the board
     const uint32_t mvw = T->mv[agent];
     const bool is_tag = a == 4;
     const bool hit = opp == agent;                                                        // tag.py:122-126
-    const bool moves = is_tag && !hit && nopp > 0 && bern(w_move, p.move_T);              // tag.py:128, 204
+    const bool alive = (s & (63u << 25)) != 0u && !(s >> 30 & 1u);                        // num_opp > 0 (6-bit two's complement)
+    const bool moves = is_tag && !hit && alive && p.move_on && w_move <= p.move_thr_m1;   // tag.py:128, 204
     const uint32_t opp_t = (e >> (5u * rand_below(w_pick, e >> 20))) & 31u;               // tag.py:205-207
     const uint32_t agent2 = is_tag ? agent : ((mvw >> (5u * ((uint32_t)a & 3u))) & 31u);  // tag.py:133-137
     const uint32_t opp2 = moves ? opp_t : opp;
-    const int nopp2 = nopp - ((is_tag && hit) ? 1 : 0);
-    const bool done = nopp2 == 0;                                                         // tag.py:142
-    uint32_t ns = tag_set_num_opp((s & ~1023u) | agent2 | (opp2 << 5), nopp2) | (done ? TAG_DONE : 0u);
-    float reward = is_tag ? (hit ? 10.f : -10.f) : -1.f;
-    int32_t o = (!is_tag && agent2 == opp2) ? TAG_CELLS : (int32_t)agent2;                // tag.py:219-226
-    int32_t f = done ? (int32_t)FLAG_DONE : 0;
+    // num_opp lives in bits 25-30: a successful TAG subtracts one in place (6-bit wrap as tag_set_num_opp does)
+    uint32_t ns = (s & ~1023u) | agent2 | (opp2 << 5);
+    ns = (is_tag && hit) ? ((ns & ~(63u << 25)) | ((ns - (1u << 25)) & (63u << 25))) : ns;
+    const bool done = (ns & (63u << 25)) == 0u;                                           // tag.py:142
+    ns |= done ? TAG_DONE : 0u;
+    const float reward = is_tag ? (hit ? 10.f : -10.f) : -1.f;
+    const int32_t o = (!is_tag && agent2 == opp2) ? TAG_CELLS : (int32_t)agent2;          // tag.py:219-226
     // the reference's asserts (tag.py:109-110, 116-117): flagged, state untouched, obs = reward = 0
     const int32_t err = (s & TAG_DONE) ? (int32_t)(FLAG_DONE | FLAG_STEPPED_DONE)
                         : ((uint32_t)a >= 5u) ? (int32_t)FLAG_BAD_ACTION
-                        : (agent >= (uint32_t)TAG_CELLS || opp >= (uint32_t)TAG_CELLS) ? (int32_t)FLAG_BAD_STATE : 0;
+                        : (e == 0u) ? (int32_t)FLAG_BAD_STATE : 0;
     s2 = err ? s : ns;
     ob = err ? 0 : o;
     rw = err ? 0.f : reward;
-    fl = err ? err : f;
+    fl = err ? err : (done ? (int32_t)FLAG_DONE : 0);
 }
 
 // tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).
@@ -517,7 +520,7 @@ POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_
                 tagged = true;
                 --nopp;
             } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
-                const uint32_t e = T->pair[agent * 32u + o];
+                const uint32_t e = T->pair[o * 32u + agent];
                 if (bern(draw(2 * j), p.move_T)) {                                // tag.py:204
                     const uint32_t pick = rand_below(draw(2 * j + 1), e >> 20);   // tag.py:205
                     s2 = (s2 & ~(31u << sh)) | (((e >> (5u * pick)) & 31u) << sh);  // tag.py:206-207

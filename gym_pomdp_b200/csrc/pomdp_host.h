@@ -193,6 +193,8 @@ inline int make_tag(const PomdpTagParams* q, TagDev* d) {
     memset(d, 0, sizeof(*d));
     d->n_opp = q->num_opponents;
     d->move_T = bern_T(q->move_prob);
+    d->move_on = d->move_T != 0;
+    d->move_thr_m1 = d->move_T ? (uint32_t)(d->move_T - 1) : 0u;
     return 0;
 }
 
