@@ -10,6 +10,9 @@
 Bar (BASELINE.json north_star): p > 0.01 for every case.  The CPU suite runs the same
 cases at N = 2*10^5 on the host build of the functors; the ``gpu`` run uses N = 10^7.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -27,6 +30,15 @@ P_MIN = 0.01
 @pytest.fixture
 def N(backend):
     return 10_000_000 if backend.startswith("cuda") else 200_000
+
+
+def report(name, backend, N, **pools):
+    """With POMDP_DIST_REPORT=<file> set, append the pooled statistics (chi-square, dof, p) of a test as a JSON line."""
+    path = os.environ.get("POMDP_DIST_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": name, "backend": backend, "draws_per_case": N, "seed": SEED,
+                                "pools": {k: {"chi2": v.chi, "dof": v.dof, "p": v.p} for k, v in pools.items()}}) + "\n")
 
 
 class Pool(object):
@@ -100,6 +112,7 @@ def test_rock_sensor(golden, backend, N):
         vs_ref.two(counts, ref["rock_obs_counts"][c])
         if d == 0:
             assert counts[2 if status == 1 else 1] == N              # eff(0) == 1.0 exactly
+    report("rock_sensor", backend, N, analytic=analytic, vs_reference=vs_ref)
     assert analytic.p > P_MIN and vs_ref.p > P_MIN, (analytic.p, vs_ref.p)
 
 
@@ -129,6 +142,7 @@ def test_rock_sensor_every_distance_and_action(backend, N):
             eff = cfg.efficiency(dd)
             if tab[dd].sum():
                 pool.one(tab[dd], [1 - eff, eff])
+        report("rock_check_action_%d" % (5 + a), backend, N, analytic=pool)
         assert pool.p > P_MIN, (a, pool.chi, pool.dof)
 
 
@@ -144,13 +158,15 @@ def test_rock_reset_and_stochastic_gate(golden, backend, N):
     for i in range(8):                                                    # rock.py:78-80
         analytic.one([N - good[i], good[i]], [.5, .5])
         vs_ref.two([N - good[i], good[i]], [R - ref["rock_reset_good"][i], ref["rock_reset_good"][i]])
+    report("rock_reset_status", backend, N, analytic=analytic, vs_reference=vs_ref)
     assert analytic.p > P_MIN and vs_ref.p > P_MIN, (analytic.p, vs_ref.p)
     env = gp.make("StochasticRock-v0", board_size=7, num_rocks=8, batch_size=N, device=backend, seed=SEED)
     state = env.pack([3], [3], torch.ones((1, 8), dtype=torch.int64)).expand(N).contiguous()
     ns, ob, rw, fl = env.simulate(state, full(N, 0, backend), step_ctr=4)
     moved = int((env.unpack(ns)[1] == 4).sum())
-    assert one_sample_p([N - moved, moved], [.2, .8]) > P_MIN              # rock.py:429, 443
-    assert two_sample_p([N - moved, moved], ref["srock_moved"]) > P_MIN
+    gate_a, gate_r = Pool().one([N - moved, moved], [.2, .8]), Pool().two([N - moved, moved], ref["srock_moved"])
+    report("stochastic_rock_p_move_gate", backend, N, analytic=gate_a, vs_reference=gate_r)
+    assert gate_a.p > P_MIN and gate_r.p > P_MIN                          # rock.py:429, 443
 
 
 def tag_move_probs(a, o):
@@ -177,6 +193,7 @@ def test_tag_opponent_move(golden, backend, N):
         counts = bincount(env.unpack(ns)[1][:, 0], 29)
         analytic.one(counts, tag_move_probs(a, o))
         vs_ref.two(counts, ref["tag_opp_counts"][c])
+    report("tag_opponent_move_probes", backend, N, analytic=analytic, vs_reference=vs_ref)
     assert analytic.p > P_MIN and vs_ref.p > P_MIN, (analytic.p, vs_ref.p)
 
 
@@ -194,6 +211,7 @@ def test_tag_all_pairs(backend, N):
         for oi in range(29):
             if ai != oi:
                 pool.one(tab[ai, oi], tag_move_probs(ai, oi))
+    report("tag_opponent_move_all_812_pairs", backend, N, analytic=pool)
     assert pool.p > P_MIN, (pool.chi, pool.dof)
 
 
@@ -205,6 +223,7 @@ def test_tag_reset(golden, backend, N):
     ca, co, cob = bincount(agent, 29), bincount(opp[:, 0], 29), bincount(ob, 30)
     analytic = Pool().one(ca, np.full(29, 1 / 29)).one(co, np.full(29, 1 / 29))      # tag.py:43-44, 181-193
     vs_ref = Pool().two(ca, ref["tag_reset_agent"]).two(co, ref["tag_reset_opp"])
+    report("tag_reset_cells", backend, N, analytic=analytic, vs_reference=vs_ref)
     assert analytic.p > P_MIN and vs_ref.p > P_MIN, (analytic.p, vs_ref.p)
     # the reset observation is 29 exactly when agent and opponent coincide (tag.py:101, 219-226)
     assert torch.equal(ob == 29, agent == opp[:, 0]) and torch.equal(ob[ob != 29], agent[ob != 29])
@@ -231,6 +250,8 @@ def test_tiger(golden, backend, N):
     counts = bincount(env.unpack(st)[0], 2)
     samp_a.one(counts, [.5, .5])
     samp_r.two(counts, ref["tiger_reset"])
+    report("tiger", backend, N, listen_analytic=listen_a, listen_vs_reference=listen_r, resample_analytic=samp_a,
+           resample_vs_reference=samp_r)
     ps = [q.p for q in (listen_a, listen_r, samp_a, samp_r)]
     assert min(ps) > P_MIN, ps
 
@@ -252,6 +273,7 @@ def test_network(golden, backend, N):
             p_fail = .33 if any(not (s >> j) & 1 for j in nb[m]) else .1             # network.py:94-99
             fail_a.one([N - up, up], [p_fail, 1 - p_fail])
             fail_r.two([N - up, up], [T - ref["network_up"][c, m], ref["network_up"][c, m]])
+    report("network_failures", backend, N, analytic=fail_a, vs_reference=fail_r)
     assert fail_a.p > P_MIN and fail_r.p > P_MIN, (fail_a.p, fail_r.p)
     allup = full(N, 1023, backend)
     ns, ob, rw, fl = env.simulate(allup, full(N, 2, backend), step_ctr=30)           # ping machine 1
@@ -266,6 +288,7 @@ def test_network(golden, backend, N):
     counts = bincount(ob, 3)
     ob_a.one(counts, [.05, .95, 0])                                                 # network.py:101-105
     ob_r.two(counts, ref["network_reboot"])
+    report("network_ping_reboot_obs", backend, N, analytic=ob_a, vs_reference=ob_r)
     assert ob_a.p > P_MIN and ob_r.p > P_MIN, (ob_a.p, ob_r.p)
 
 
@@ -298,8 +321,11 @@ def test_battleship_first_ship_placement(golden, backend, N, size):
         mul[ix] += 1
     kc, rc = np.concatenate([hc.ravel(), vc.ravel()]), np.concatenate([rh.ravel(), rv.ravel()])
     assert ((kc > 0) == (rc > 0)).all()                                # exactly the reference's support
-    assert two_sample_p(kc, rc) > P_MIN
+    ship_r = Pool().two(kc, rc)
+    assert ship_r.p > P_MIN
     # uniform over the valid (pos, dir) set == each reachable cell set weighted by how many placements cover it
     assert int((first > 0).sum()) == (20 if size == (5, 5) else 240)
     mult = np.concatenate([mh.ravel(), mv.ravel()]).astype(np.float64)
-    assert one_sample_p(kc, mult / mult.sum()) > P_MIN
+    ship_a = Pool().one(kc, mult / mult.sum())
+    report("battleship_first_ship_%dx%d" % size, backend, B, analytic=ship_a, vs_reference=ship_r)
+    assert ship_a.p > P_MIN
