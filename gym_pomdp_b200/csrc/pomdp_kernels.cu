@@ -109,19 +109,34 @@ template <> struct StateVec<uint32_t> {
         st_stream4(base + i, make_int4((int)s[0], (int)s[1], (int)s[2], (int)s[3]));
     }
 };
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): four 64-bit packed states in ONE instruction
+__device__ __forceinline__ void ld_stream_4x64(const void* p, uint64_t s[4]) {
+    asm volatile("ld.global.cs.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_stream_4x64(void* p, const uint64_t s[4]) {
+    asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(s[0]), "l"(s[1]), "l"(s[2]), "l"(s[3]) : "memory");
+}
 template <> struct StateVec<uint64_t> {
-    int4 v0, v1;
+    uint64_t v[4];
     __device__ __forceinline__ void load(const int32_t* base, int64_t i) {
-        v0 = ld_stream4(base + 2 * i);
-        v1 = ld_stream4(base + 2 * i + 4);
+        const int32_t* p = base + 2 * i;
+        if ((reinterpret_cast<uintptr_t>(base) & 31) == 0) {      // uniform: the whole array is 32-byte aligned
+            ld_stream_4x64(p, v);
+        } else {
+            const int4 a = ld_stream4(p), b = ld_stream4(p + 4);
+            v[0] = (uint32_t)a.x | ((uint64_t)(uint32_t)a.y << 32); v[1] = (uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32);
+            v[2] = (uint32_t)b.x | ((uint64_t)(uint32_t)b.y << 32); v[3] = (uint32_t)b.z | ((uint64_t)(uint32_t)b.w << 32);
+        }
     }
-    __device__ __forceinline__ void unpack(uint64_t s[4]) const {
-        s[0] = (uint32_t)v0.x | ((uint64_t)(uint32_t)v0.y << 32); s[1] = (uint32_t)v0.z | ((uint64_t)(uint32_t)v0.w << 32);
-        s[2] = (uint32_t)v1.x | ((uint64_t)(uint32_t)v1.y << 32); s[3] = (uint32_t)v1.z | ((uint64_t)(uint32_t)v1.w << 32);
-    }
+    __device__ __forceinline__ void unpack(uint64_t s[4]) const { s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; s[3] = v[3]; }
     __device__ static __forceinline__ void store(int32_t* base, int64_t i, const uint64_t s[4]) {
-        st_stream4(base + 2 * i, make_int4((int)(uint32_t)s[0], (int)(s[0] >> 32), (int)(uint32_t)s[1], (int)(s[1] >> 32)));
-        st_stream4(base + 2 * i + 4, make_int4((int)(uint32_t)s[2], (int)(s[2] >> 32), (int)(uint32_t)s[3], (int)(s[3] >> 32)));
+        int32_t* p = base + 2 * i;
+        if ((reinterpret_cast<uintptr_t>(base) & 31) == 0) {
+            st_stream_4x64(p, s);
+        } else {
+            st_stream4(p, make_int4((int)(uint32_t)s[0], (int)(s[0] >> 32), (int)(uint32_t)s[1], (int)(s[1] >> 32)));
+            st_stream4(p + 4, make_int4((int)(uint32_t)s[2], (int)(s[2] >> 32), (int)(uint32_t)s[3], (int)(s[3] >> 32)));
+        }
     }
 };
 __device__ __forceinline__ uint32_t load_state1(const int32_t* base, int64_t i, uint32_t) { return (uint32_t)base[i]; }
