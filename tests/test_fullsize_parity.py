@@ -12,6 +12,7 @@ The ``gpu`` run uses those sizes through the CUDA library; the CPU suite runs th
 at 2^14 on the host build of the functors.
 """
 import numpy as np
+import pytest
 import torch
 
 import gym_pomdp_b200 as gp
@@ -206,3 +207,30 @@ def test_belief_histogram_2p22(backend):
     h = env.belief_histogram(st).cpu().numpy()
     x, y, status, _ = (v.cpu().numpy() for v in env.unpack(st))
     assert np.array_equal(h[:11], (status == 1).sum(0)) and h[11 + (0 | 5 << 4)] == B and h[11:].sum() == B
+
+
+@pytest.mark.gpu
+def test_batch_beyond_2p31_envs():
+    """Maximum sizes: 2^31 + 4 Tiger instances in ONE launch (52 GB of arrays): element indices and Philox counters are
+    64-bit end to end.  Windows at the start, around 2^31 and at the ragged end are checked against the C oracle."""
+    dev = "cuda:0"
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 31) + 4
+    if free < 60 * (1 << 30):
+        pytest.skip("needs 60 GB of free device memory")
+    env = gp.make("Tiger-v0", batch_size=n, device=dev, seed=SEED)
+    g = gen_for(dev, 77)
+    state = torch.randint(0, 2, (n,), generator=g, device=dev, dtype=torch.int32)
+    action = torch.randint(0, 3, (n,), generator=g, device=dev, dtype=torch.int32)
+    ns, ob, rw, fl = env.simulate(state, action, step_ctr=3)
+    torch.cuda.synchronize()
+    for lo, hi in [(0, 4096), ((1 << 31) - 4096, (1 << 31) + 4), (n - 3, n)]:
+        es, eob, erw, edone = C.tiger_step(0.85, state[lo:hi].cpu().numpy(), action[lo:hi].cpu().numpy(),
+                                           C.fill_draws(SEED, lo, hi - lo, 3, philox.DOMAIN_STEP, 2))
+        s2, done = (v.cpu().numpy() for v in env.unpack(ns[lo:hi]))
+        assert np.array_equal(s2, es) and np.array_equal(ob[lo:hi].cpu().numpy(), eob) and np.array_equal(done, edone)
+        assert np.array_equal(rw[lo:hi].cpu().numpy(), erw.astype(np.float32))
+    # every element was written: obs in {0, 1, 2}, flags in {0, 1}
+    assert int(ob.max()) <= 2 and int(ob.min()) >= 0 and int(fl.max()) <= 1 and int(fl.min()) >= 0
+    del ns, ob, rw, fl, state, action
+    torch.cuda.empty_cache()
