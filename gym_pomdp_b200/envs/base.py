@@ -27,11 +27,20 @@ import torch
 from .. import _lib
 
 
+try:  # pragma: no cover - neither package is in the build image
+    from gym import Env as _EnvBase                     # the reference's envs subclass gym.Env (rock.py:5, 96)
+except Exception:  # noqa: BLE001
+    try:
+        from gymnasium import Env as _EnvBase
+    except Exception:  # noqa: BLE001
+        _EnvBase = object
+
+
 def _as_device(device):
     return torch.device(device) if not isinstance(device, torch.device) else device
 
 
-class BatchedPomdpEnv(object):
+class BatchedPomdpEnv(_EnvBase):
     metadata = {"render.modes": ["ansi"]}
     kind = -1            # POMDP_KIND_* for the belief histogram
     state_words = 1      # int32 words per instance
