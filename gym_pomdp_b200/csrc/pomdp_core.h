@@ -11,6 +11,7 @@
 // reference); layouts and the draw-slot contract are documented in include/pomdp_b200.h
 // and DESIGN.md.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -603,68 +604,93 @@ struct NetworkDev {
     int32_t n;
     uint32_t deg3;                   // machines with more than 2 neighbours (reward 2, network.py:89-92)
     uint64_t p_T, q_T, ob_T;         // ceil(prob * 2^32)
+    uint32_t pm1, qm1, om1;          // T - 1 (r < T  <=>  r <= T - 1 when T != 0)
+    int32_t all_T_nonzero;           // every T above is in 1..2^32: the 32-bit compares are exact
     double p_ob;
     uint32_t nb[NETWORK_MAX + 2];    // neighbour bit masks (network.py:144-168)
 };
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
 
 
+// tenths / 10 correctly rounded to float32 without a division: one multiply by 0.1f and one
+// Newton correction through two exact FMAs.  Equal to (float)t / 10.0f for every |t| <= 2^20
+// (tests/test_oracle_c_golden.py walks the whole range through the host build of this function).
+POMDP_HD float tenths_to_float(int t) {
+    const float x = (float)t;
+    const float q = x * 0.1f;
+    return fmaf(fmaf(-q, 10.0f, x), 0.1f, q);
+}
+
 // network.py:71-114 for L consecutive envs of ONE draw group (L = 4: a thread's aligned
 // group, lane0 = 0; L = 1: a single env, lane0 = env & 3).  Slot m = machine m's failure
 // draw, slot n = the action's observation draw: one Philox call per slot serves all L envs.
 // Reward is carried as an exact integer number of tenths.
+//
+// The reference draws only for machines that are up (network.py:95); a failure draw for a
+// machine that is down clears a bit that is already clear, so the loop needs no "is up" test.
+// The thresholds are compared as r <= T - 1 in 32 bits; a configuration with a probability of
+// exactly 0 (T = 0, nothing ever fires) takes the 64-bit compare instead (uniform per launch).
 template <int L>
 POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], const PhiloxKey& seed,
                              uint64_t group, int lane0, uint32_t step,
                              uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
     const uint32_t all = (1u << p.n) - 1u;
     uint32_t nw[L], down[L];
-    int tenths[L];
-    bool live[L];
+    bool hit[L];
     POMDP_UNROLL
     for (int j = 0; j < L; ++j) {
-        fl[j] = 0;
-        if (s[j] & NETWORK_DONE) fl[j] = FLAG_DONE | FLAG_STEPPED_DONE;
-        else if ((uint32_t)a[j] >= (uint32_t)(2 * p.n + 1)) fl[j] = FLAG_BAD_ACTION;
-        else if (s[j] & ~all) fl[j] = FLAG_BAD_STATE;
-        live[j] = fl[j] == 0;
         nw[j] = s[j];
         down[j] = ~s[j] & all;
-        tenths[j] = 10 * popc32(s[j]) + 10 * popc32(s[j] & p.deg3);               // network.py:87-92
     }
-    for (int m = 0; m < p.n; ++m) {                                               // network.py:94-99
-        const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) {
-            const uint64_t T = (p.nb[m] & down[j]) ? p.q_T : p.p_T;
-            if (((s[j] >> m) & 1u) && bern(word_of(q, lane0 + j), T)) nw[j] &= ~(1u << m);
-        }
-    }
-    const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
-    POMDP_UNROLL
-    for (int j = 0; j < L; ++j) {
-        int o = 2;
-        if (a[j] < 2 * p.n) {                                                     // network.py:101-112
-            const int machine = (a[j] >> 1) & 31;
-            const int hit = bern(word_of(qa, lane0 + j), p.ob_T) ? 1 : 0;
-            if (a[j] & 1) {
-                tenths[j] -= 25;
-                nw[j] |= 1u << machine;
-                o = hit;
-            } else {
-                tenths[j] -= 1;
-                const int bit = (int)((nw[j] >> machine) & 1u);
-                o = hit ? bit : 1 - bit;
+    if (p.all_T_nonzero) {
+        const uint32_t pm1 = p.pm1, qm1 = p.qm1;
+        for (int m = 0; m < p.n; ++m) {                                           // network.py:94-99
+            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
+            const uint32_t nbm = p.nb[m];
+            const uint32_t keep = ~(1u << m);
+            POMDP_UNROLL
+            for (int j = 0; j < L; ++j) {
+                const uint32_t t = (nbm & down[j]) ? qm1 : pm1;
+                if (word_of(q, lane0 + j) <= t) nw[j] &= keep;
             }
         }
-#if defined(__CUDA_ARCH__)
-        const float r = __fdiv_rn((float)tenths[j], 10.0f);
-#else
-        const float r = (float)tenths[j] / 10.0f;
-#endif
-        s2[j] = live[j] ? nw[j] : s[j];
-        ob[j] = live[j] ? o : 0;
-        rw[j] = live[j] ? r : 0.f;
+        const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
+        POMDP_UNROLL
+        for (int j = 0; j < L; ++j) hit[j] = word_of(qa, lane0 + j) <= p.om1;
+    } else {                                                                      // a probability of exactly 0
+        for (int m = 0; m < p.n; ++m) {
+            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
+            POMDP_UNROLL
+            for (int j = 0; j < L; ++j) {
+                const uint64_t T = (p.nb[m] & down[j]) ? p.q_T : p.p_T;
+                if (bern(word_of(q, lane0 + j), T)) nw[j] &= ~(1u << m);
+            }
+        }
+        const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
+        POMDP_UNROLL
+        for (int j = 0; j < L; ++j) hit[j] = bern(word_of(qa, lane0 + j), p.ob_T);
+    }
+    const uint32_t na = (uint32_t)(2 * p.n);
+    POMDP_UNROLL
+    for (int j = 0; j < L; ++j) {
+        const int f = (s[j] & NETWORK_DONE) ? (FLAG_DONE | FLAG_STEPPED_DONE)
+                      : (uint32_t)a[j] > na ? FLAG_BAD_ACTION
+                      : (s[j] & ~all)       ? FLAG_BAD_STATE : 0;
+        const bool live = f == 0;
+        int tenths = 10 * (popc32(s[j]) + popc32(s[j] & p.deg3));                 // network.py:87-92
+        const bool acts = (uint32_t)a[j] < na;                                    // network.py:101-112
+        const bool restart = (a[j] & 1) != 0;
+        const uint32_t mbit = 1u << ((a[j] >> 1) & 31);
+        const uint32_t h = hit[j] ? 1u : 0u;
+        uint32_t n2 = nw[j];
+        if (acts && restart) n2 |= mbit;
+        const uint32_t bit = (n2 & mbit) ? 1u : 0u;
+        const uint32_t o = acts ? (restart ? h : (bit ^ h ^ 1u)) : 2u;
+        tenths -= acts ? (restart ? 25 : 1) : 0;
+        fl[j] = f;
+        s2[j] = live ? n2 : s[j];
+        ob[j] = live ? (int32_t)o : 0;
+        rw[j] = live ? tenths_to_float(tenths) : 0.f;
     }
 }
 

@@ -215,6 +215,8 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     d->q_T = bern_T(q->q);
     d->ob_T = bern_T(q->p_ob);
     d->p_ob = q->p_ob;
+    d->pm1 = (uint32_t)(d->p_T - 1); d->qm1 = (uint32_t)(d->q_T - 1); d->om1 = (uint32_t)(d->ob_T - 1);
+    d->all_T_nonzero = d->p_T != 0 && d->q_T != 0 && d->ob_T != 0;
     int deg[NETWORK_MAX] = {0};
     auto link = [&](int i, int j) { d->nb[i] |= 1u << j; ++deg[i]; };
     if (q->problem_type == 3) {                     // network.py:153-168

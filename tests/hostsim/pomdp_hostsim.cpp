@@ -656,4 +656,10 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     return 0;
 }
 
+// test-only: the division-free float32 reward conversion of network_step_n, for the exhaustive check in
+// tests/test_edge_cases.py
+void pomdp_hostsim_tenths_to_float(const int32_t* t, float* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = tenths_to_float(t[i]);
+}
+
 }  // extern "C"

@@ -342,3 +342,37 @@ def test_packed_reward_range(backend):
     ob, rw, fl = net.unpack_result(res)
     assert torch.equal(rw, ref[2]) and torch.equal(ob, ref[1])
     assert rw.tolist() == [np.float32(v) for v in (11.0, 10.9, 8.5, 8.5, 11.0, 11.0, 8.5, 8.5)]
+
+
+def test_network_reward_conversion_is_correctly_rounded():
+    """network_step_n turns the integer number of tenths into float32 with a multiply and two FMAs instead of a
+    division; the result must be float32(t) / float32(10) (IEEE division, what the reference's double rounds to) for
+    every value the 16-bit unit field can hold and far beyond."""
+    import ctypes
+    from backends import build_hostsim
+    lib = ctypes.CDLL(build_hostsim())
+    t = np.arange(-(1 << 21), (1 << 21) + 1, dtype=np.int32)
+    out = np.empty(t.size, dtype=np.float32)
+    lib.pomdp_hostsim_tenths_to_float(t.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(t.size))
+    assert np.array_equal(out, t.astype(np.float32) / np.float32(10))
+    assert np.array_equal(out, (t.astype(np.float64) / 10.0).astype(np.float32))     # float32(the reference's double)
+
+
+@pytest.mark.parametrize("probs", [(0.0, 0.5, 1.0), (1.0, 1.0, 0.0), (0.25, 0.0, 0.5)])
+def test_network_probabilities_of_exactly_zero_and_one(backend, probs):
+    """T = 0 (never fires) takes the 64-bit compare, T = 2^32 (always fires) the 32-bit one; both must agree with the
+    oracle.  The reference hard-codes p, q, p_ob (network.py:27-38); the C ABI takes them as parameters."""
+    from oracle import c_oracle as C, philox
+    n, ptype, B = 10, 3, 4096
+    env = gp.make("Network-v0", n_machines=n, problem_type=ptype, batch_size=B, device=backend, seed=11)
+    env._params = _lib.NetworkParams(n, ptype, *probs)
+    g = torch.Generator().manual_seed(5)
+    s0 = torch.randint(0, 1 << n, (B,), generator=g).int()
+    action = torch.randint(0, 2 * n + 1, (B,), generator=g).int()
+    ns, ob, rw, fl = env.simulate(s0.to(backend), action.to(backend), step_ctr=3)
+    bits = ((s0.numpy()[:, None] >> np.arange(n)) & 1).astype(np.int8)
+    em, eob, erw = C.network_step(n, ptype, bits, action.numpy(), C.fill_draws(11, 0, B, 3, philox.DOMAIN_STEP, n + 1), *probs)
+    assert np.array_equal(ns.cpu().numpy(), (em.astype(np.int64) << np.arange(n)).sum(1).astype(np.int32))
+    assert np.array_equal(ob.cpu().numpy(), eob)
+    assert np.array_equal(rw.cpu().numpy(), erw.astype(np.float32))
+    assert not fl.any()

@@ -149,7 +149,7 @@ def test_tiger_and_network_batch_2p20(backend):
     qs, qob = C.tiger_reset(C.fill_draws(SEED, 0, B, 6, philox.DOMAIN_RESET, 1))
     assert np.array_equal(env.unpack(st0)[0].cpu().numpy(), qs) and np.array_equal(ob0.cpu().numpy(), qob)
 
-    for n, ptype in [(10, 3), (16, 3), (12, 0)]:
+    for n, ptype in [(10, 3), (16, 3), (12, 0), (28, 3), (30, 0)]:
         env = gp.make("Network-v0", n_machines=n, problem_type=ptype, batch_size=B, device=backend, seed=SEED)
         s0 = dev_ints(g, 0, 1 << n, (B,), backend)
         action = dev_ints(g, 0, 2 * n + 1, (B,), backend).int()
