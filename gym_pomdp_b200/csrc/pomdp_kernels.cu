@@ -784,10 +784,10 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 //    warp ballots they are VOTE-throughput-bound (both measured: 30 us and 25-37 us for 2^22 Rock states).  Instead
 //    every thread keeps PACKED BYTE COUNTERS in registers: four bits of the state are spread to the four bytes of
 //    a word with one multiply ((x & 0xF) * 0x00204081 & 0x01010101) and added -- three instructions per four bins
-//    per particle, no cross-lane traffic.  Counters are flushed (warp shuffle reduction of the 16-bit halves, then
+//    per particle, no cross-lane traffic.  Counters are flushed (hardware warp reduction of the 16-bit halves, then
 //    one shared-memory atomic per bin per warp) before a byte can overflow, normally once at the end;
 //  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (many addresses).
-// W = 1 states are read four envs per thread (16-byte loads).
+// W = 1 and W = 2 states are read with 16-byte loads (four / two envs per thread per trip).
 #define POMDP_HIST_MAX_BINS 512
 template <int KIND> struct HistShape;                        // NW = packed counter words per thread (4 bins each)
 template <> struct HistShape<POMDP_KIND_ROCK> { static constexpr int NW = 4; };
@@ -824,25 +824,27 @@ __device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4]
         for (int j = 0; j < 30; ++j) acc[j] += spread4((s[j >> 3] >> (4 * (j & 7))) & 0xFu);
     }
 }
-// adds the warp's packed byte counters to the shared histogram (bins 4j + c < n_bits) and clears them
+// adds the warp's packed byte counters to the shared histogram (bins 4j + c < n_bits) and clears them: the bytes of
+// word j are widened to two words of 16-bit fields (32 lanes x 255 fits), each summed over the warp by ONE hardware
+// reduction (REDUX via __reduce_add_sync; a plain 32-bit add never carries between the fields), and lane j keeps
+// word j's totals, so the shared-memory atomics of all words are issued together, four per lane.
 template <int NW>
 __device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, int n_bits, int lane) {
+    static_assert(NW <= 32, "one lane per counter word");
+    uint32_t my_lo = 0, my_hi = 0;
 #pragma unroll
     for (int j = 0; j < NW; ++j) {
         if (4 * j >= n_bits) break;
-        uint32_t lo = acc[j] & 0x00FF00FFu, hi = (acc[j] >> 8) & 0x00FF00FFu;      // bytes 0,2 and 1,3 as 16-bit fields
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            lo += __shfl_xor_sync(0xffffffffu, lo, d);
-            hi += __shfl_xor_sync(0xffffffffu, hi, d);
-        }
-        if (lane == 0) {
-            const uint32_t c[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c[k] && 4 * j + k < n_bits) atomicAdd(&sh[4 * j + k], c[k]);
-        }
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, acc[j] & 0x00FF00FFu);          // bytes 0, 2
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, (acc[j] >> 8) & 0x00FF00FFu);   // bytes 1, 3
+        if (lane == j) { my_lo = lo; my_hi = hi; }
         acc[j] = 0;
+    }
+    if (4 * lane < n_bits) {
+        const uint32_t c[4] = {my_lo & 0xFFFFu, my_hi & 0xFFFFu, my_lo >> 16, my_hi >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k] && 4 * lane + k < n_bits) atomicAdd(&sh[4 * lane + k], c[k]);
     }
 }
 template <int KIND>
@@ -862,23 +864,33 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     int64_t scalar_from = 0;
-    if (words == 1 && (reinterpret_cast<uintptr_t>(state) & 15) == 0) {
-        const int64_t n_groups = n >> 2;
+    if ((words == 1 || words == 2) && (reinterpret_cast<uintptr_t>(state) & 15) == 0) {
+        // one 16-byte load per thread per trip: four W = 1 states or two W = 2 states
+        const int lg = words == 1 ? 2 : 1;
+        const int64_t n_groups = n >> lg;
         const int64_t g_round = (n_groups + 31) & ~(int64_t)31;          // whole warps iterate together (flush shuffles)
         for (int64_t g = tid; g < g_round; g += nthreads) {
             const bool valid = g < n_groups;
             int4 v = make_int4(0, 0, 0, 0);
             if (valid) v = ld_stream4(state + (g << 2));
             const uint32_t e[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+            if (words == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t s[4] = {e[j], 0u, 0u, 0u};
-                hist_one<KIND>(p0, valid, s, sh, acc);
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t s[4] = {e[j], 0u, 0u, 0u};
+                    hist_one<KIND>(p0, valid, s, sh, acc);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t s[4] = {e[2 * j], e[2 * j + 1], 0u, 0u};
+                    hist_one<KIND>(p0, valid, s, sh, acc);
+                }
             }
             pending += 4;
             if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
         }
-        scalar_from = n_groups << 2;
+        scalar_from = n_groups << lg;
     }
     const int64_t rem = n - scalar_from;
     const int64_t r_round = (rem + 31) & ~(int64_t)31;
