@@ -111,6 +111,7 @@ POMDP_HD int popc32(uint32_t v) {
     return __builtin_popcount(v);
 #endif
 }
+POMDP_HD int popc64(uint64_t v) { return popc32((uint32_t)v) + popc32((uint32_t)(v >> 32)); }
 
 // ------------------------------------------------------------------ geometry --------
 // Moves, coord.py:101-106: 0 N(0,+1) 1 E(+1,0) 2 S(0,-1) 3 W(-1,0) 4 NULL(0,0).
@@ -705,6 +706,8 @@ struct ShipDev {
     // [dir][ship index] start cells from which the reference's look-ahead stays on the board: the cell
     // length + 1 steps ahead must be inside (battleship.py:199-201), ship index 0 = the longest ship
     uint64_t inside_lo[4][SHIP_MAX_SHIPS], inside_hi[4][SHIP_MAX_SHIPS];
+    // [ship index] the cells of a vertical ship whose lowest cell is cell 0: bits 0, X, 2X, ... (length - 1) X
+    uint64_t vpat_lo[SHIP_MAX_SHIPS], vpat_hi[SHIP_MAX_SHIPS];
 };
 struct ShipState {
     u128 occ, vis;     // bit c = cell c = X*y + x
@@ -786,37 +789,75 @@ POMDP_HD bool ship_candidate_ok(const ShipDev& p, u128 blocked, int pos, int dir
 }
 
 // ---- bitboard placement: every (pos, dir) candidate of one ship at once ------------------------------------------
+// The board as two explicit 64-bit halves.  (The placement code does NOT use unsigned __int128: nvcc 12.9 lowers
+// `r & (r >> 1)` on a 128-bit value in this code to two independent 64-bit shifts, losing the bit that crosses from
+// the high to the low half -- caught by the GPU parity tests, reproduced in isolation, absent from g++.)
+struct B128 { uint64_t lo, hi; };
+POMDP_HD B128 b128(uint64_t lo, uint64_t hi) { B128 r; r.lo = lo; r.hi = hi; return r; }
+POMDP_HD B128 operator&(B128 a, B128 b) { return b128(a.lo & b.lo, a.hi & b.hi); }
+POMDP_HD B128 operator|(B128 a, B128 b) { return b128(a.lo | b.lo, a.hi | b.hi); }
+POMDP_HD B128 operator~(B128 a) { return b128(~a.lo, ~a.hi); }
+// shifts by 0 <= s; anything pushed past either end is dropped, s >= 128 gives 0
+POMDP_HD B128 shr(B128 v, int s) {
+    if (s >= 128) return b128(0, 0);
+    if (s >= 64) return b128(v.hi >> (s - 64), 0);
+    return b128((v.lo >> s) | ((v.hi << 1) << (63 - s)), v.hi >> s);      // (hi << 1) << (63 - s): s = 0 stays defined
+}
+POMDP_HD B128 shl(B128 v, int s) {
+    if (s >= 128) return b128(0, 0);
+    if (s >= 64) return b128(0, v.lo << (s - 64));
+    return b128(v.lo << s, (v.hi << s) | ((v.lo >> 1) >> (63 - s)));
+}
+POMDP_HD B128 ship_blocked_b(const ShipDev& p, B128 occ) {
+    const B128 col0 = b128(p.col0_lo, p.col0_hi), colL = b128(p.colL_lo, p.colL_hi);
+    // N, S, E, W, NE, SE, SW neighbours (not NW: battleship.py:203-211 never looks there) in four shifts: with
+    // v = occ | N | S, the three eastern neighbours are v >> 1 and the two western ones (occ | S) << 1.  Bits pushed
+    // past cell n_tiles - 1 are off the board and masked by the caller.
+    const B128 south = shl(occ, p.X);                                     // q + S occupied
+    const B128 v = occ | shr(occ, p.X) | south;                           // q, q + N, q + S
+    return v | (shr(v, 1) & ~colL) | (shl(occ | south, 1) & ~col0);
+}
+// AND of o >> (i * st) for i = 0 .. n - 1 (1 <= n <= 16) by doubling: runs of 1, 2, 4, 8 cells, then one overlapping
+// step for the rest -- floor(log2 n) + 1 shifts instead of n - 1.
+POMDP_HD B128 ship_run(B128 o, int st, int n) {
+    B128 r = o;
+    int have = 1;
+    POMDP_UNROLL
+    for (int k = 0; k < 4; ++k)
+        if (2 * have <= n) { r = r & shr(r, have * st); have *= 2; }
+    if (have < n) r = r & shr(r, (n - have) * st);
+    return r;
+}
 // valid[d] bit pos  <=>  collision() is False for Ship(pos, direction d, length)  (battleship.py:195-211): the
 // look-ahead cell is on the board and none of the length + 1 cells pos + i*dir is blocked.
-POMDP_HD void ship_valid_starts(const ShipDev& p, u128 blocked, int ship_index, int length, u128 valid[4]) {
-    const u128 board = ((u128)1 << p.n_tiles) - 1;
-    const u128 open_ = ~blocked & board;
+POMDP_HD void ship_valid_starts(const ShipDev& p, B128 blocked, int ship_index, int length, B128 valid[4]) {
+    const B128 board = p.n_tiles >= 64 ? b128(~0ull, (1ull << (p.n_tiles - 64)) - 1ull) : b128((1ull << p.n_tiles) - 1ull, 0);
+    const B128 open_ = ~blocked & board;
+    // Directions 0 (+X) and 1 (+1) walk up the cell index: bit pos of the run mask = all length + 1 cells
+    // pos, pos + st, ... are open.  Directions 2 (-X) and 3 (-1) walk down from pos, i.e. the same run seen from its
+    // other end: shift the run mask up by length * st.  The `inside` masks keep rows from wrapping (pomdp_host.h).
+    const B128 run_v = ship_run(open_, p.X, length + 1), run_h = ship_run(open_, 1, length + 1);
+    const B128 r[4] = {run_v, run_h, shl(run_v, length * p.X), shl(run_h, length)};
     POMDP_UNROLL
-    for (int d = 0; d < 4; ++d) {
-        const int st = move_dy(d) * p.X + move_dx(d);          // +X, +1, -X, -1
-        u128 v = (u128)p.inside_lo[d][ship_index] | ((u128)p.inside_hi[d][ship_index] << 64);
-        for (int i = 0; i <= length; ++i) v &= st > 0 ? (open_ >> (i * st)) : (open_ << (i * -st));
-        valid[d] = v;
-    }
+    for (int d = 0; d < 4; ++d) valid[d] = r[d] & b128(p.inside_lo[d][ship_index], p.inside_hi[d][ship_index]);
 }
-POMDP_HD uint32_t u128_word(u128 v, int w) { return (uint32_t)(v >> (32 * w)); }
-POMDP_HD int ship_count(const u128 valid[4]) {
+POMDP_HD uint32_t b128_word(B128 v, int w) { return (uint32_t)((w < 2 ? v.lo : v.hi) >> (32 * (w & 1))); }
+POMDP_HD int ship_count(const B128 valid[4]) {
     int total = 0;
     POMDP_UNROLL
-    for (int d = 0; d < 4; ++d)
-        for (int w = 0; w < 4; ++w) total += popc32(u128_word(valid[d], w));
+    for (int d = 0; d < 4; ++d) total += popc64(valid[d].lo) + popc64(valid[d].hi);
     return total;
 }
 // the k-th accepted candidate in increasing c = 4 * pos + dir (k < ship_count): word, then a 5-step binary search on
 // the bit position with masked popcounts, then the direction
-POMDP_HD int ship_pick(const u128 valid[4], int k) {
+POMDP_HD int ship_pick(const B128 valid[4], int k) {
     uint32_t m[4] = {0, 0, 0, 0};
     int base = 0;
     bool found = false;
     POMDP_UNROLL
     for (int w = 0; w < 4; ++w) {
-        const uint32_t a0 = u128_word(valid[0], w), a1 = u128_word(valid[1], w), a2 = u128_word(valid[2], w),
-                       a3 = u128_word(valid[3], w);
+        const uint32_t a0 = b128_word(valid[0], w), a1 = b128_word(valid[1], w), a2 = b128_word(valid[2], w),
+                       a3 = b128_word(valid[3], w);
         const int c = popc32(a0) + popc32(a1) + popc32(a2) + popc32(a3);
         if (!found) {
             if (k < c) { m[0] = a0; m[1] = a1; m[2] = a2; m[3] = a3; base = 32 * w; found = true; }
@@ -839,6 +880,12 @@ POMDP_HD int ship_pick(const u128 valid[4], int k) {
             else --k;
         }
     return 4 * (base + lo) + dir;
+}
+// marks a placement that is known to be valid on an unshot board: one shifted cell pattern
+POMDP_HD B128 ship_cells(const ShipDev& p, int ship_index, int pos, int dir, int length) {
+    const B128 pat = (dir & 1) ? b128((1ull << length) - 1ull, 0) : b128(p.vpat_lo[ship_index], p.vpat_hi[ship_index]);
+    const int st = (dir & 1) ? 1 : p.X;
+    return shl(pat, dir < 2 ? pos : pos - (length - 1) * st);
 }
 
 // battleship.py:182-193
@@ -875,16 +922,20 @@ POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed
 // false when some ship has no placement (the reference would loop forever).
 POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step, ShipState& st) {
     st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+    B128 occ = b128(0, 0);
     int ship = 0;
+    bool ok = true;
     for (int length = p.max_len; length >= 2; --length, ++ship) {
-        u128 valid[4];
-        ship_valid_starts(p, ship_blocked(p, st.occ), ship, length, valid);
+        B128 valid[4];
+        ship_valid_starts(p, ship_blocked_b(p, occ), ship, length, valid);
         const int total = ship_count(valid);
-        if (total == 0) return false;
+        if (total == 0) { ok = false; break; }
         const int c = ship_pick(valid, (int)rand_below(draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total));
-        ship_mark(p, st, c >> 2, c & 3, length);
+        occ = occ | ship_cells(p, ship, c >> 2, c & 3, length);
+        st.remaining += length;
     }
-    return true;
+    st.occ = (u128)occ.lo | ((u128)occ.hi << 64);
+    return ok;
 }
 
 // battleship.py:157-165: _generate_legal = the unvisited cells in increasing action order; the policy draws one

@@ -250,7 +250,10 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
     d->colL_lo = (uint64_t)cL; d->colL_hi = (uint64_t)(cL >> 64);
     if (q->max_len - 1 <= SHIP_MAX_SHIPS) {
         int ship = 0;
-        for (int length = q->max_len; length >= 2; --length, ++ship)
+        for (int length = q->max_len; length >= 2; --length, ++ship) {
+            u128 vp = 0;
+            for (int i = 0; i < length && i * d->X < 128; ++i) vp |= (u128)1 << (i * d->X);
+            d->vpat_lo[ship] = (uint64_t)vp; d->vpat_hi[ship] = (uint64_t)(vp >> 64);
             for (int dir = 0; dir < 4; ++dir) {
                 u128 m = 0;
                 for (int y = 0; y < d->Y; ++y)
@@ -259,6 +262,7 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
                             m |= (u128)1 << (y * d->X + x);
                 d->inside_lo[dir][ship] = (uint64_t)m; d->inside_hi[dir][ship] = (uint64_t)(m >> 64);
             }
+        }
     }
     return 0;
 }

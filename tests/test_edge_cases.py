@@ -282,7 +282,8 @@ def test_belief_histogram_matches_bincount(backend):
             assert np.array_equal(h.reshape(10, 10), occ.sum(0).T)      # bin c = 10*y + x
 
 
-@pytest.mark.parametrize("size,max_len", [((10, 10), 3), ((5, 5), 3), ((10, 10), 5), ((12, 10), 4), ((4, 7), 3), ((3, 3), 3)])
+@pytest.mark.parametrize("size,max_len", [((10, 10), 3), ((5, 5), 3), ((10, 10), 5), ((12, 10), 4), ((4, 7), 3), ((3, 3), 3),
+                                          ((120, 1), 4), ((1, 120), 4), ((2, 60), 5), ((30, 4), 6), ((40, 3), 9), ((8, 15), 9)])
 def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
     """The two fixed-time placement kernels (thread-per-env bitboards, warp-per-env ballot scan) enumerate the same
     accepted (pos, dir) set in the same order, so they must produce identical boards -- including 'no placement
@@ -296,10 +297,13 @@ def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
     if size == (3, 3):
         assert (a.reset_flags == _lib.FLAG_BAD_STATE).all()
     else:
-        assert not a.reset_flags.any()
+        placed = a.reset_flags == 0
+        # a crowded board can run out of placements for the last ships (both kernels flag the same boards)
+        assert placed.all() or max_len >= 9
+        assert placed.float().mean() > 0.5
         occ, vis, rem, done = a.unpack(sa)
         n_cells = sum(range(2, max_len + 1))
-        assert (occ.reshape(B, -1).sum(1) == n_cells).all() and (rem == n_cells).all()
+        assert (occ.reshape(B, -1).sum(1)[placed] == n_cells).all() and (rem[placed] == n_cells).all()
 
 
 @pytest.mark.parametrize("name", [n for n in NAMES if n != "ship"])
