@@ -297,9 +297,11 @@ def run_b200(args):
     value = n_gpus * B * K / (ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------
-    # env.simulate_host(packed=True): pinned host (state, action) -> chunked H2D / kernel / D2H on three streams ->
-    # pinned host (next_state, result) with result = obs | flags << 8 | reward << 16 (include/pomdp_b200.h).  The
-    # unpacked variant (four result arrays, 16 B/env back) is timed too and reported as e2e.unpacked.
+    # env.simulate_host(packed=True) = ONE C-ABI call, pomdp_step_packed_host (include/pomdp_b200.h): pinned host
+    # (state, action) -> the library's chunked H2D / kernel / D2H pipeline on three streams -> pinned host
+    # (next_state, result) with result = obs | flags << 8 | reward << 16.  Timed beside it: the same pipeline driven
+    # from Python through torch (e2e.python_pipeline), the four-array result (e2e.unpacked, 16 B/env back) and the
+    # zero-copy launch (e2e.zero_copy).
     E = max(1, args.e2e_steps)
     pin = dict(device="cpu", pin_memory=True)
     s0, a0, _ = sets[0]
@@ -308,16 +310,16 @@ def run_b200(args):
              torch.empty(B, dtype=torch.float32, **pin), torch.empty(B, dtype=torch.int32, **pin))
     h_packed = (torch.empty(s0.shape, dtype=torch.int32, **pin), torch.empty(B, dtype=torch.int32, **pin))
 
-    def time_e2e(packed):
+    def time_e2e(packed, pipeline=None):
         out = h_packed if packed else h_out
         for i in range(3):
-            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed)
+            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed, pipeline=pipeline)
         barrier()
         t0 = time.perf_counter()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ee0.record()
         for i in range(E):
-            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed)
+            env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed, pipeline=pipeline)
         ee1.record()
         torch.cuda.synchronize()
         ms_ = ee0.elapsed_time(ee1)
@@ -329,7 +331,9 @@ def run_b200(args):
         return ms_, wall
 
     e2e_un_ms, _ = time_e2e(False)
-    e2e_ms, e2e_wall = time_e2e(True)
+    e2e_py_ms, _ = time_e2e(True, "python")
+    h_packed[0].zero_(); h_packed[1].zero_()
+    e2e_ms, e2e_wall = time_e2e(True)                       # the C-ABI host call; its results are checked below
     # zero-copy variant: one launch, the kernel itself reads / writes the pinned host buffers over PCIe
     zc_ms = None
     try:
@@ -398,8 +402,11 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (4 * words + 4),
                 "d2h_bytes_per_step": B * (4 * words + 4), "steps": E, "ms_per_step": e2e_ms / E,
                 "wall_ms_per_step": e2e_wall / E,
-                "path": "env.simulate_host(packed=True): pinned host (state, action) -> 3-stream chunked H2D/kernel/D2H -> "
-                        "pinned host (next_state, result = obs | flags << 8 | reward << 16)",
+                "path": "env.simulate_host(packed=True) = one C-ABI call pomdp_step_packed_host: pinned host (state, action) -> "
+                        "chunks of 2^20 envs, H2D / pomdp_rock_step_packed / D2H on the library's three streams -> pinned host "
+                        "(next_state, result = obs | flags << 8 | reward << 16)",
+                "python_pipeline": {"value": n_gpus * B * E / (e2e_py_ms * 1e-3), "ms_per_step": e2e_py_ms / E,
+                                    "path": "the same pipeline issued from Python through torch, chunks of 2^20 envs"},
                 "unpacked": {"value": n_gpus * B * E / (e2e_un_ms * 1e-3), "ms_per_step": e2e_un_ms / E,
                              "d2h_bytes_per_step": B * (4 * words + 12),
                              "path": "env.simulate_host: four result arrays (next_state, obs, reward, flags) back"},

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -88,6 +88,9 @@ _PROTOTYPES = {
     "pomdp_tag_step_packed": (c_int32, [POINTER(TagParams), _P] + _STEPP_TAIL),
     "pomdp_tiger_step_packed": (c_int32, [POINTER(TigerParams)] + _STEPP_TAIL),
     "pomdp_network_step_packed": (c_int32, [POINTER(NetworkParams)] + _STEPP_TAIL),
+    "pomdp_host_pipe_create": (c_int32, [c_int32, c_int64, c_int32, POINTER(c_void_p)]),
+    "pomdp_host_pipe_destroy": (c_int32, [c_void_p]),
+    "pomdp_step_packed_host": (c_int32, [c_void_p, c_int32, c_void_p, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32]),
     "pomdp_rock_policy": (c_int32, [POINTER(RockParams), _P] + _POLICY_TAIL),
     "pomdp_rock_rollout": (c_int32, [POINTER(RockParams), _P] + _ROLLOUT_TAIL),
     "pomdp_tag_policy": (c_int32, [POINTER(TagParams), _P] + _POLICY_TAIL),

@@ -267,6 +267,28 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
     return 0;
 }
 
+// pomdp_step_packed_host: the pipe, the kind, the state width the pipe was made for and the host pointers
+inline int check_host_step(bool pipe_ok, int pipe_words, int kind, const void* params, const void* h_state, const void* h_action,
+                           const void* h_next, const void* h_result, int64_t n, int64_t goff) {
+    const char* what = "pomdp_step_packed_host";
+    if (!pipe_ok) return fail(POMDP_E_BADARG, "%s: not a pipe (pomdp_host_pipe_create)", what);
+    if (!params) return fail(POMDP_E_BADARG, "%s: params is NULL", what);
+    int words = 1;
+    if (kind == POMDP_KIND_ROCK) {
+        const int rc = make_rock((const PomdpRockParams*)params, nullptr, nullptr);
+        if (rc) return rc;
+        words = rock_words((const PomdpRockParams*)params);
+    } else if (kind != POMDP_KIND_TAG && kind != POMDP_KIND_TIGER && kind != POMDP_KIND_NETWORK) {
+        return fail(POMDP_E_BADARG, "%s: kind %d has no packed step (Rock, Tag, Tiger, Network do)", what, kind);
+    }
+    if (words != pipe_words) return fail(POMDP_E_BADARG, "%s: the pipe was created for %d state words, this env has %d", what, pipe_words, words);
+    if (n < 0 || goff < 0) return fail(POMDP_E_BADARG, "%s: n and global_offset must be >= 0", what);
+    if (n > 0 && (!h_state || !h_action || !h_next || !h_result)) return fail(POMDP_E_BADARG, "%s: NULL host buffer", what);
+    if ((((uintptr_t)h_state | (uintptr_t)h_action | (uintptr_t)h_next | (uintptr_t)h_result) & 3) != 0)
+        return fail(POMDP_E_ALIGN, "%s: host buffers must be 4-byte aligned", what);
+    return 0;
+}
+
 inline int hist_bins(int kind, int p0, int p1) {
     switch (kind) {
         case POMDP_KIND_ROCK: return p0 + 256;

@@ -1363,6 +1363,89 @@ int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state,
                                           step_ctr, stream, "pomdp_network_step_packed");
 }
 
+// ---- the same on HOST buffers: chunked H2D -> step -> D2H on the pipe's streams (include/pomdp_b200.h)
+struct HostPipe {
+    uint32_t magic;
+    int words, n_slots, device;
+    int64_t chunk;
+    int32_t* slot[8];          // [state W*chunk | action chunk | next_state W*chunk | result chunk]
+    cudaStream_t stream[8];
+};
+static const uint32_t kHostPipeMagic = 0x50495045u;
+
+int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, void** pipe_out) {
+    if (!pipe_out) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: pipe_out is NULL");
+    *pipe_out = nullptr;
+    if (state_words < 1 || state_words > SHIP_WORDS || chunk_envs < 4 || (chunk_envs & 3) || chunk_envs > (1ll << 28) ||
+        n_slots < 1 || n_slots > 8)
+        return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: state_words %d, chunk_envs %lld (multiple of 4), n_slots %d (1..8)",
+                          state_words, (long long)chunk_envs, n_slots);
+    HostPipe* hp = new HostPipe();
+    hp->magic = kHostPipeMagic; hp->words = state_words; hp->n_slots = n_slots; hp->chunk = chunk_envs;
+    cudaError_t e = cudaGetDevice(&hp->device);
+    const size_t bytes = (size_t)(2 * state_words + 2) * (size_t)chunk_envs * sizeof(int32_t);
+    for (int k = 0; k < n_slots && e == cudaSuccess; ++k) {
+        e = cudaMalloc((void**)&hp->slot[k], bytes);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->stream[k], cudaStreamNonBlocking);
+    }
+    if (e != cudaSuccess) {
+        for (int k = 0; k < n_slots; ++k) { if (hp->slot[k]) cudaFree(hp->slot[k]); if (hp->stream[k]) cudaStreamDestroy(hp->stream[k]); }
+        delete hp;
+        (void)cudaGetLastError();
+        return host::fail((int)e, "pomdp_host_pipe_create: %s", cudaGetErrorString(e));
+    }
+    *pipe_out = hp;
+    return 0;
+}
+int pomdp_host_pipe_destroy(void* pipe) {
+    HostPipe* hp = (HostPipe*)pipe;
+    if (!hp || hp->magic != kHostPipeMagic) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_destroy: not a pipe");
+    for (int k = 0; k < hp->n_slots; ++k) { cudaStreamSynchronize(hp->stream[k]); cudaFree(hp->slot[k]); cudaStreamDestroy(hp->stream[k]); }
+    hp->magic = 0;
+    delete hp;
+    return 0;
+}
+int pomdp_step_packed_host(void* pipe, int kind, const void* params, const void* d_table, const int32_t* h_state,
+                           const int32_t* h_action, int32_t* h_next_state, int32_t* h_result, int64_t n, int64_t goff,
+                           uint64_t seed, uint32_t step_ctr) {
+    HostPipe* hp = (HostPipe*)pipe;
+    int rc = host::check_host_step(hp && hp->magic == kHostPipeMagic, hp ? hp->words : 0, kind, params, h_state, h_action,
+                                   h_next_state, h_result, n, goff);
+    if (rc || n == 0) return rc;
+    const int W = hp->words;
+    const int64_t C = hp->chunk;
+    cudaError_t e = cudaSuccess;
+    int ci = 0;
+    for (int64_t lo = 0; lo < n && rc == 0 && e == cudaSuccess; lo += C, ++ci) {
+        const int64_t m = n - lo < C ? n - lo : C;
+        const int k = ci % hp->n_slots;
+        cudaStream_t st = hp->stream[k];
+        int32_t* d_state = hp->slot[k];
+        int32_t* d_action = d_state + (size_t)W * C;
+        int32_t* d_next = d_action + C;
+        int32_t* d_result = d_next + (size_t)W * C;
+        e = cudaMemcpyAsync(d_state, h_state + (size_t)lo * W, (size_t)m * W * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_action, h_action + lo, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        switch (kind) {
+            case POMDP_KIND_ROCK: rc = pomdp_rock_step_packed((const PomdpRockParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
+            case POMDP_KIND_TAG: rc = pomdp_tag_step_packed((const PomdpTagParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
+            case POMDP_KIND_TIGER: rc = pomdp_tiger_step_packed((const PomdpTigerParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
+            default: rc = pomdp_network_step_packed((const PomdpNetworkParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
+        }
+        if (rc) break;
+        e = cudaMemcpyAsync(h_next_state + (size_t)lo * W, d_next, (size_t)m * W * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_result + lo, d_result, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    }
+    for (int k = 0; k < hp->n_slots; ++k) {                   // drain even after an error: the slots are reused
+        const cudaError_t es = cudaStreamSynchronize(hp->stream[k]);
+        if (e == cudaSuccess) e = es;
+    }
+    if (rc) return rc;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return host::fail((int)e, "pomdp_step_packed_host: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 // ---- uniform-legal policy and fused rollouts
 #define POMDP_ROCK_DISPATCH(FN, ...)                                                          \
     do {                                                                                      \

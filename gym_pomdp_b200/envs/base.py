@@ -258,7 +258,8 @@ class BatchedPomdpEnv(_EnvBase):
                             self._discount if discount is None else discount, first_action)
         return final_state, ret, steps, flags
 
-    def simulate_host(self, state, action, out, step_ctr=None, chunk=1 << 20, packed=False, n_streams=3, zero_copy=False):
+    def simulate_host(self, state, action, out, step_ctr=None, chunk=None, packed=False, n_streams=3, zero_copy=False,
+                      pipeline=None):
         """G(s, a) on HOST buffers (pinned CPU tensors): what a numpy-holding caller of the
         reference does.  The batch is cut into chunks that are copied in, stepped and copied
         out on three rotating CUDA streams, so the H2D copy, the kernel and the D2H copy of
@@ -266,6 +267,15 @@ class BatchedPomdpEnv(_EnvBase):
         reward, flags) pinned CPU tensors -- or, with ``packed=True``, (next_state, result):
         8 instead of 16 bytes per env come back over PCIe (``unpack_result`` decodes).
         Returns after all results have landed.
+
+        ``pipeline``: who drives the chunks.  ``"c"`` -- ONE C-ABI call, ``pomdp_step_packed_host``
+        (include/pomdp_b200.h): the library owns the staging buffers and streams and issues every copy and
+        launch itself (no interpreter time per chunk).  ``"python"`` -- this method issues the copies and
+        launches through torch.  Default: ``"c"`` for packed results on a CUDA device, ``"python"`` otherwise
+        (the four-array result has no host entry point).  Default chunk: 2^20 envs -- measured on the B200
+        box, smaller chunks lose more to the fixed cost of each copy than they gain in pipeline fill and
+        drain (scripts/exp_host_pipe.py, scripts/exp_pcie_chunks.py), and the link carries ~52 GB/s one
+        way but only ~75 GB/s both ways together, which is what bounds this call.
 
         ``zero_copy=True``: no staging at all -- ONE kernel launch whose loads and stores go straight
         to the pinned host buffers over PCIe (pinned memory is mapped into the device address space
@@ -286,7 +296,24 @@ class BatchedPomdpEnv(_EnvBase):
                     self._c_step(state, action, out[0], out[1], out[2], out[3], n, ctr)
                 torch.cuda.current_stream(self.device).synchronize()
             return out
-        ws = self._host_ws(min(chunk, max(n, 1)), n_streams)
+        if pipeline is None:
+            pipeline = "c" if (packed and self.device.type == "cuda" and self.kind != _lib.KIND_BATTLESHIP) else "python"
+        if pipeline == "c":
+            if not packed:
+                raise ValueError("the C host pipeline returns packed results (packed=True)")
+            for t in (state, action, out[0], out[1]):
+                if t.device.type != "cpu" or not t.is_contiguous() or t.dtype != torch.int32:
+                    raise ValueError("simulate_host(pipeline='c') needs contiguous int32 CPU tensors")
+            pipe = self._host_pipe(chunk or (1 << 20), n_streams)
+            with self._guard():
+                _lib.check(_lib.lib().pomdp_step_packed_host(
+                    pipe, self.kind, ctypes.addressof(self._params), _lib.ptr(getattr(self, "_table", None)),
+                    state.data_ptr(), action.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), n, self.global_offset,
+                    self._seed, ctr), "pomdp_step_packed_host")
+            return out
+        if pipeline != "python":
+            raise ValueError("pipeline must be 'c' or 'python'")
+        ws = self._host_ws(min(chunk or (1 << 20), max(n, 1)), n_streams)
         n_out = 2 if packed else 4
         base_off = self.global_offset
         with self._guard():
@@ -313,6 +340,31 @@ class BatchedPomdpEnv(_EnvBase):
                 cur.wait_stream(st)
             cur.synchronize()
         return out
+
+    def _host_pipe(self, chunk, n_slots=3):
+        """The C library's staging pipe for ``simulate_host(pipeline='c')``, created once per (chunk, n_slots)."""
+        key = (int(chunk), int(n_slots))
+        cur = getattr(self, "_hpipe", None)
+        if cur is not None and cur[0] == key:
+            return cur[1]
+        self._close_host_pipe()
+        h = ctypes.c_void_p()
+        with self._guard():
+            _lib.check(_lib.lib().pomdp_host_pipe_create(self.state_words, key[0], key[1], ctypes.byref(h)), "pomdp_host_pipe_create")
+        self._hpipe = (key, h)
+        return h
+
+    def _close_host_pipe(self):
+        cur = getattr(self, "_hpipe", None)
+        if cur is not None:
+            self._hpipe = None
+            try:
+                _lib.lib().pomdp_host_pipe_destroy(cur[1])
+            except Exception:       # interpreter shutdown
+                pass
+
+    def __del__(self):
+        self._close_host_pipe()
 
     def _host_ws(self, chunk, n_streams=3):
         ws = getattr(self, "_hws", None)
@@ -452,7 +504,7 @@ class BatchedPomdpEnv(_EnvBase):
             print(type(self).__name__, self._info_state())
 
     def close(self):
-        return
+        self._close_host_pipe()
 
     # ------------------------------------------------------------- belief histogram ---
     def _hist_args(self):

@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 4
+#define POMDP_ABI_VERSION 5
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -240,6 +240,28 @@ int pomdp_tiger_step_packed(const PomdpTigerParams* params,
 int pomdp_network_step_packed(const PomdpNetworkParams* params,
                               const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* result,
                               int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+
+/* --------------------------------------------- step on HOST buffers (one call, pipelined) --- */
+/* What a numpy-holding caller of the reference does: its (state, action) arrays live in host memory and
+ * it wants (next_state, result) back in host memory (the loop around env.step at rock.py:563-572 with the
+ * arrays of a whole particle set).  pomdp_step_packed_host is pomdp_E_step_packed for HOST pointers: the
+ * batch is cut into chunks, and for every chunk the H2D copies, the step kernel and the D2H copies are
+ * queued on one of the pipe's streams, so the copies of neighbouring chunks run on both PCIe directions
+ * while the kernels (microseconds) hide under them.  Returns when every result has landed.  Results are
+ * identical to one pomdp_E_step_packed call over the whole batch (Philox is keyed by the global index).
+ *
+ *  - pipe: device staging buffers ((2 * state_words + 2) * chunk_envs * 4 bytes per slot) and one stream
+ *    per slot, created once and reused; chunk_envs must be a positive multiple of 4, 1 <= n_slots <= 8.
+ *    A pipe belongs to the device that was current at creation and is not thread-safe.
+ *  - kind: POMDP_KIND_ROCK / TAG / TIGER / NETWORK; params points at the matching PomdpEParams; d_table as
+ *    for pomdp_E_step_packed (NULL for Tiger / Network), fully built before the call.
+ *  - host pointers should be page-locked (cudaHostAlloc / cudaHostRegister): pageable memory is still
+ *    correct, but its copies are staged by the driver and do not overlap.                               */
+int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, void** pipe_out);
+int pomdp_host_pipe_destroy(void* pipe);
+int pomdp_step_packed_host(void* pipe, int kind, const void* params, const void* d_table,
+                           const int32_t* h_state, const int32_t* h_action, int32_t* h_next_state, int32_t* h_result,
+                           int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr);
 
 /* ------------------------------------------- uniform-legal policy and fused rollouts --- */
 /* What a POMCP / Monte-Carlo caller does with these envs between two tree nodes (the loops at

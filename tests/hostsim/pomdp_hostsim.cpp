@@ -600,6 +600,47 @@ int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state,
         }, state, action, next, result, n);
 }
 
+// host-buffer pipeline: no device, so a "pipe" only remembers its chunking; the chunks go through the packed steps
+// one after the other with the same global offsets the CUDA library uses.
+struct HostPipe { uint32_t magic; int words, n_slots; int64_t chunk; };
+int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, void** pipe_out) {
+    if (!pipe_out) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: pipe_out is NULL");
+    *pipe_out = nullptr;
+    if (state_words < 1 || state_words > SHIP_WORDS || chunk_envs < 4 || (chunk_envs & 3) || chunk_envs > (1ll << 28) ||
+        n_slots < 1 || n_slots > 8)
+        return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: state_words %d, chunk_envs %lld (multiple of 4), n_slots %d (1..8)",
+                          state_words, (long long)chunk_envs, n_slots);
+    *pipe_out = new HostPipe{0x50495045u, state_words, n_slots, chunk_envs};
+    return 0;
+}
+int pomdp_host_pipe_destroy(void* pipe) {
+    HostPipe* hp = (HostPipe*)pipe;
+    if (!hp || hp->magic != 0x50495045u) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_destroy: not a pipe");
+    hp->magic = 0;
+    delete hp;
+    return 0;
+}
+int pomdp_step_packed_host(void* pipe, int kind, const void* params, const void* table, const int32_t* h_state,
+                           const int32_t* h_action, int32_t* h_next, int32_t* h_result, int64_t n, int64_t goff, uint64_t seed,
+                           uint32_t step) {
+    HostPipe* hp = (HostPipe*)pipe;
+    int rc = host::check_host_step(hp && hp->magic == 0x50495045u, hp ? hp->words : 0, kind, params, h_state, h_action, h_next,
+                                   h_result, n, goff);
+    const int W = hp ? hp->words : 1;
+    for (int64_t lo = 0; lo < n && rc == 0; lo += hp->chunk) {
+        const int64_t m = n - lo < hp->chunk ? n - lo : hp->chunk;
+        const int32_t *s = h_state + lo * W, *a = h_action + lo;
+        int32_t *nx = h_next + lo * W, *r = h_result + lo;
+        switch (kind) {
+            case POMDP_KIND_ROCK: rc = pomdp_rock_step_packed((const PomdpRockParams*)params, table, s, a, nx, r, m, goff + lo, seed, step, nullptr); break;
+            case POMDP_KIND_TAG: rc = pomdp_tag_step_packed((const PomdpTagParams*)params, table, s, a, nx, r, m, goff + lo, seed, step, nullptr); break;
+            case POMDP_KIND_TIGER: rc = pomdp_tiger_step_packed((const PomdpTigerParams*)params, s, a, nx, r, m, goff + lo, seed, step, nullptr); break;
+            default: rc = pomdp_network_step_packed((const PomdpNetworkParams*)params, s, a, nx, r, m, goff + lo, seed, step, nullptr); break;
+        }
+    }
+    return rc;
+}
+
 int pomdp_rock_belief_update(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action,
                              const int32_t* obs, int32_t* count, int32_t* measured, double* lkv, double* lkw, double* pv,
                              int64_t n, void*) {
