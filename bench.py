@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--rocks", type=int, default=11)
     ap.add_argument("--batch", type=int, default=1 << 22, help="env instances per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly through ctypes instead of a CUDA graph")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profiler-range", action="store_true",
@@ -312,7 +312,7 @@ def run_b200(args):
 
     def time_e2e(packed, pipeline=None):
         out = h_packed if packed else h_out
-        for i in range(3):
+        for i in range(5):
             env.simulate_host(h_state, h_action, out, step_ctr=i + 1, packed=packed, pipeline=pipeline)
         barrier()
         t0 = time.perf_counter()
