@@ -8,7 +8,7 @@
  * nothing under gym_pomdp_b200/ includes, links or dlopens it.
  *
  * Parity status: PINNED.  tests/test_oracle_c_golden.py checks every function here against
- * tests/golden/*.npz, which oracle/gen_golden.py recorded from the UNMODIFIED reference
+ * tests/golden/ (.npz files), which oracle/gen_golden.py recorded from the UNMODIFIED reference
  * (imported from /root/reference through oracle/ref_shim.py, its numpy draws scripted).
  *
  * Deliberately written differently from the kernels (gym_pomdp_b200/csrc/pomdp_core.h):
