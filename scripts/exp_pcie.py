@@ -60,11 +60,11 @@ for packed in (False, True):
         for chunk in (1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21):
             o = hp if packed else ho
             for _ in range(3):
-                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns)
+                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns, pipeline="python")
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(20):
-                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns)
+                env.simulate_host(hs, ha, o, step_ctr=1, chunk=chunk, packed=packed, n_streams=ns, pipeline="python")
             dt = (time.perf_counter() - t0) / 20
             res["packed=%d streams=%d chunk=2^%d" % (packed, ns, chunk.bit_length() - 1)] = round(dt * 1e3, 3)
 print(json.dumps(res, indent=0))
