@@ -12,7 +12,8 @@
  * stands in for.  INTEGRATION.md shows the ctypes binding a maintainer of the reference
  * would add.
  *
- * Conventions (all entry points)
+ * Conventions (all entry points; the one exception, pomdp_step_packed_host with its pipe, takes plain HOST
+ * pointers, owns staging buffers and streams inside the pipe and is synchronous -- see there)
  * ------------------------------
  *  - Plain pointers and sizes only; every array pointer is DEVICE-ACCESSIBLE memory owned by
  *    the caller: device memory (torch tensors on the Python side), or pinned host memory
