@@ -68,6 +68,14 @@ def _worker(rank, port, out_dir):
             env = _make(name, B, lo)                                    # this rank's shard
             ns, ob, rw, fl = env.simulate(state[lo:hi].contiguous(), action[lo:hi].contiguous(), step_ctr=4)
             st0, ob0 = env.init_states(B, step_ctr=5)
+            # the host-buffer call on this rank's shard (chunks of 64 envs): same packed words as the device-side step
+            hp = (torch.empty_like(ns), torch.empty_like(ob))
+            env.simulate_host(state[lo:hi].contiguous(), action[lo:hi].contiguous(), hp, step_ctr=4, packed=True,
+                              pipeline="c", chunk=64, n_streams=2)
+            p_ob, p_rw, p_fl = env.unpack_result(hp[1])
+            host_ok = torch.tensor([int(torch.equal(hp[0], ns) and torch.equal(p_ob, ob) and torch.equal(p_rw, rw)
+                                        and torch.equal(p_fl, fl))])
+            dist.all_reduce(host_ok, op=dist.ReduceOp.MIN)
             hist = env.belief_histogram(ns, all_reduce=True)            # the only collective
             gathered = [torch.empty_like(ns) for _ in range(WORLD)]
             dist.all_gather(gathered, ns)
@@ -80,7 +88,7 @@ def _worker(rank, port, out_dir):
                 w_st0, _ = whole.init_states(WORLD * B, step_ctr=5)
                 result[name] = bool(torch.equal(torch.cat(gathered), w_ns) and torch.equal(torch.cat(g_ob), w_ob)
                                     and torch.equal(torch.cat(g_st0), w_st0)
-                                    and torch.equal(hist, whole.belief_histogram(w_ns)))
+                                    and torch.equal(hist, whole.belief_histogram(w_ns)) and int(host_ok) == 1)
         # BattleShip: reset shards + histogram of occupied cells
         env = _make("ship", B, rank * B)
         st0, _ = env.init_states(B, step_ctr=6)
