@@ -380,3 +380,21 @@ def test_network_probabilities_of_exactly_zero_and_one(backend, probs):
     assert np.array_equal(ob.cpu().numpy(), eob)
     assert np.array_equal(rw.cpu().numpy(), erw.astype(np.float32))
     assert not fl.any()
+
+
+@pytest.mark.parametrize("size,max_len", [((12, 10), 4), ((4, 7), 3), ((120, 1), 4), ((1, 120), 4), ((2, 60), 5), ((30, 4), 6),
+                                          ((8, 15), 9), ((40, 3), 9), ((11, 10), 5), ((16, 7), 6)])
+def test_battleship_bitboard_reset_equals_oracle_on_odd_boards(backend, size, max_len):
+    """The two-word bitboard placement (run masks by doubling, both directions of an axis from one run mask, boards
+    crossing the 64-bit boundary at every possible column) against the C oracle's cell-by-cell collision walk
+    (battleship.py:195-211): same boards, same `no placement exists` flags, for shapes far from the stock 10 x 10."""
+    from oracle import c_oracle as C, philox
+    B = 2000
+    env = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=21, reset_mode="scan")
+    st, _ = env.init_states(B, step_ctr=9)
+    occ, vis, rem, done = env.unpack(st)
+    eocc, erem, err = C.battleship_reset_scan(size[0], size[1], max_len, C.fill_draws(21, 0, B, 9, philox.DOMAIN_RESET, max_len - 1))
+    assert np.array_equal(occ.cpu().numpy(), eocc)
+    assert np.array_equal(rem.cpu().numpy(), erem)
+    assert np.array_equal(env.reset_flags.cpu().numpy() != 0, err != 0)
+    assert not vis.any() and not done.any()
