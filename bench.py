@@ -160,7 +160,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                         "c_port": C.time_rock_c(args.board, args.rocks)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -388,6 +389,7 @@ def run_b200(args):
         per_proc = max(20000, int(args.cpu_seconds * 7e5))
         cpu = C.time_rock(n, k, per_proc, procs)
         cpu = {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+        cpu["c_port"] = C.time_rock_c(n, k)          # the same algorithm as compiled C on every core (extra, not the arm)
 
     cfg = workload_config(args, n_gpus)
     cfg["l2"] = "%d rotating buffer sets of %.0f MB (%.0f MB total) > 126 MB L2; no flush needed" % (

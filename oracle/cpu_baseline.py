@@ -111,3 +111,42 @@ class RockCpuArm(object):
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+# ---- the C restatement on every core: the strongest CPU form of the same algorithm ------------------
+def _rock_c_loop(args):
+    n, k, count, reps, seed = args
+    from . import c_oracle as C
+    x, y, status, action, words = rock_workload(n, k, count, seed)
+    x, y, action = x.astype(np.int32), y.astype(np.int32), action.astype(np.int32)
+    status, draws = status.astype(np.int8), words.astype(np.uint32)
+    C.rock_step(n, k, False, 0.8, x[:64], y[:64], status[:64], action[:64], draws[:64])      # load the library
+    t0 = time.perf_counter()
+    acc = 0
+    for _ in range(reps):
+        out = C.rock_step(n, k, False, 0.8, x, y, status, action, draws)
+        acc += int(out[3][0])
+    return count * reps, time.perf_counter() - t0, acc
+
+
+def time_rock_c(n, k, count=1 << 20, reps=8, procs=None, seed=0x5EED):
+    """``oracle/pomdp_oracle.c`` (plain C, -O2, scalar) stepping ``count`` sampled envs ``reps`` times on every
+    core, array copies of the ctypes wrapper included.  Reported beside the Python port as ``cpu_baseline.c_port``:
+    the reference's own code is a Python loop, this is what the same algorithm does as compiled code.
+    Returns None when the C oracle has not been built."""
+    try:
+        from . import c_oracle as C
+        C.lib()
+    except Exception:  # noqa: BLE001
+        return None
+    procs = procs or os.cpu_count() or 1
+    jobs = [(n, k, count, reps, seed + 104729 * p) for p in range(procs)]
+    if procs == 1:
+        res = [_rock_c_loop(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_rock_c_loop, jobs)
+    total, slowest = sum(r[0] for r in res), max(r[1] for r in res)
+    return {"value": total / slowest, "unit": "env-steps/s", "cores": procs, "kind": "port",
+            "sample": "%d procs x %d reps x %d RockSample(%d,%d) pairs through oracle/pomdp_oracle.c (oracle_rock_step)"
+                      % (procs, reps, count, n, k)}
