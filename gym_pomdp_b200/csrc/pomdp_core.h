@@ -267,9 +267,11 @@ POMDP_HD void rock_step(const RockDev& p, const RockLut* __restrict__ lut, const
 }
 
 // rock.py:236-241, 266-271, 78-80: status = int(sign(U(0,1) - .5)), one uniform per rock.  Only the comparison with
-// one half matters, so EIGHT rocks share one draw word: rock i's uniform is u = r_i / 2^32 with
-// r_i = rotl32(word of slot i >> 3, 4 * (i & 7)).  The deciding (top) bits of the eight r_i are eight different bits
-// of the slot's word, hence independent fair coins; reset needs ceil(k / 8) Philox calls per four envs, not k.
+// one half matters, so ALL rocks (k <= 16) share ONE draw word, reset slot 0: rock i's uniform is u = r_i / 2^32 with
+// r_i = rotl32(word, 30 - 2i).  The deciding (top) bit of r_i is bit 2i + 1 of the word -- sixteen different bits,
+// hence independent fair coins -- and it sits exactly where the packed state keeps the HIGH bit of rock i's 2-bit
+// status code (01 good, 11 bad), so the sixteen codes of a word are one LOP3: 0x55555555 | (~w & 0xAAAAAAAA).
+// The tie r_i == 2^31 (u == .5, sign() gives 0 = collected) needs the word to be exactly the single bit 2i + 1.
 POMDP_HD uint32_t rotl32(uint32_t v, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_l(v, v, sh);
@@ -278,62 +280,32 @@ POMDP_HD uint32_t rotl32(uint32_t v, uint32_t sh) {
     return sh ? (v << sh) | (v >> (32u - sh)) : v;
 #endif
 }
-POMDP_HD uint32_t rock_reset_word(uint32_t slot_word, int rock) { return rotl32(slot_word, 4u * ((uint32_t)rock & 7u)); }
+POMDP_HD uint32_t rock_reset_word(uint32_t slot_word, int rock) { return rotl32(slot_word, (30u - 2u * (uint32_t)rock) & 31u); }
 POMDP_HD uint32_t rock_status_code(uint32_t w) { return w > 0x80000000u ? 1u : (w < 0x80000000u ? 3u : 0u); }
 
-POMDP_HD uint32_t brev32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __brev(v);
-#else
-    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
-    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
-    return (v >> 16) | (v << 16);
-#endif
-}
-// The eight 2-bit status codes of one reset word at once (rock j of the word in bits 2j..2j+1): rock j's r = rotl32(w, 4j)
-// compares with 2^31 through its top bit = bit 31 - 4j of w: set -> good (01), clear -> bad (11); the tie r == 2^31
-// (collected, 00) needs w to be exactly that single bit.  Equals rock_status_code(rock_reset_word(w, j)) for every w.
-POMDP_HD uint32_t rock_reset_codes8(uint32_t w) {
-    uint32_t x = brev32(w) & 0x11111111u;                  // bit 4j  = deciding bit of rock j
-    x = (x | (x >> 2)) & 0x05050505u;                       // nibble-spaced -> 2-spaced, byte by byte
-    x = (x | (x >> 4)) & 0x00550055u;
-    x = (x | (x >> 8)) & 0x00005555u;                       // bit 2j = deciding bit of rock j
-    uint32_t codes = 0x5555u | ((~x & 0x5555u) << 1);
-    if ((w & (w - 1u)) == 0u && (w & 0x88888888u)) {        // a single bit at a deciding position: that rock ties
-#if defined(__CUDA_ARCH__)
-        const int pos = 31 - __clz((int)w);
-#else
-        const int pos = 31 - __builtin_clz(w);
-#endif
-        codes &= ~(3u << (2 * ((31 - pos) >> 2)));
-    }
+// The sixteen 2-bit status codes of the reset word at once (rock i in bits 2i..2i+1).
+// Equals rock_status_code(rock_reset_word(w, i)) for every w and i (brute-force-checked in tests/test_oracle_c_golden.py).
+POMDP_HD uint32_t rock_reset_codes16(uint32_t w) {
+    uint32_t codes = 0x55555555u | (~w & 0xAAAAAAAAu);
+    if ((w & (w - 1u)) == 0u && (w & 0xAAAAAAAAu)) codes &= ~(3u * (w >> 1));   // a single bit at a deciding position: that rock ties
     return codes;
 }
 
-template <typename S, class D>
-POMDP_HD S rock_reset(const RockDev& p, const D& draw) {
-    S s = (S)p.start;
-    for (int j = 0; 8 * j < p.k; ++j) {
-        const int cnt = p.k - 8 * j < 8 ? p.k - 8 * j : 8;
-        s |= (S)(rock_reset_codes8(draw(j)) & ((1u << (2 * cnt)) - 1u)) << (8 + 16 * j);
-    }
-    return s;
+template <typename S>
+POMDP_HD S rock_reset_from_word(const RockDev& p, uint32_t w) {
+    const uint32_t m = p.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * p.k)) - 1u);
+    return (S)p.start | ((S)(rock_reset_codes16(w) & m) << 8);
 }
-// Four envs of one aligned group: one Philox call per eight rocks.
+template <typename S, class D>
+POMDP_HD S rock_reset(const RockDev& p, const D& draw) { return rock_reset_from_word<S>(p, draw(0)); }
+// Four envs of one aligned group: ONE Philox call.
 template <typename S>
 POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t group, uint32_t step, S out[4]) {
-    out[0] = out[1] = out[2] = out[3] = (S)p.start;
-    for (int j = 0; 8 * j < p.k; ++j) {
-        const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, (uint32_t)j);
-        const int cnt = p.k - 8 * j < 8 ? p.k - 8 * j : 8;
-        const uint32_t m = (1u << (2 * cnt)) - 1u;
-        out[0] |= (S)(rock_reset_codes8(q.x) & m) << (8 + 16 * j);
-        out[1] |= (S)(rock_reset_codes8(q.y) & m) << (8 + 16 * j);
-        out[2] |= (S)(rock_reset_codes8(q.z) & m) << (8 + 16 * j);
-        out[3] |= (S)(rock_reset_codes8(q.w) & m) << (8 + 16 * j);
-    }
+    const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, 0u);
+    out[0] = rock_reset_from_word<S>(p, q.x);
+    out[1] = rock_reset_from_word<S>(p, q.y);
+    out[2] = rock_reset_from_word<S>(p, q.z);
+    out[3] = rock_reset_from_word<S>(p, q.w);
 }
 
 // ---- uniform-legal policy: np.random.choice(env._generate_legal()) --------------------

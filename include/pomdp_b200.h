@@ -104,9 +104,10 @@ int pomdp_rock_step(const PomdpRockParams* params, const void* d_table,
                     int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                     void* stream);
 /* RockEnv.reset rock.py:236-241 (+ _get_init_state 266-271, Rock.__init__ 78-80).
- * Rock i's uniform(0,1) is r_i / 2^32, r_i = rotl32(word of draw slot i >> 3, 4 * (i & 7)): only its
- * comparison with one half matters, so eight rocks share a draw word.  `mask` (device, uint8[n]) may be NULL = reset all; otherwise only
- * envs with mask[i] != 0 are reset (the others keep state and get obs untouched).        */
+ * Rock i's uniform(0,1) is r_i / 2^32, r_i = rotl32(word of draw slot 0, 30 - 2 i): only its comparison
+ * with one half matters, so all rocks (k <= 16) share one draw word through sixteen different deciding
+ * bits.  `mask` (device, uint8[n]) may be NULL = reset all; otherwise only envs with mask[i] != 0 are
+ * reset (the others keep state and get obs untouched).                                   */
 int pomdp_rock_reset(const PomdpRockParams* params, const void* d_table,
                      int32_t* state, int32_t* obs, const uint8_t* mask,
                      int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,

@@ -158,17 +158,23 @@ def gen_rock(E, n, k, stochastic, n_random, tag):
                reward=np.array(res["rw"], np.float64), done=np.array(res["done"]),
                raised=np.array(res["raised"]), ndraw=np.array(res["ndraw"], np.int32),
                prob=np.array(res["prob"], np.float64), legal=np.array(res["legal"], np.int8))
-    # ---- reset (rock.py:236-241): rock i's uniform = rotl32(word of slot i >> 3, 4 * (i & 7)) / 2^32
+    # ---- reset (rock.py:236-241): rock i's uniform = rotl32(word of slot 0, 30 - 2 i) / 2^32
     M = 512
-    rd = philox.draw_slots(SEED, np.arange(M), 0, philox.DOMAIN_RESET, (k + 7) // 8)
-    rd[0, 0] = 1 << 31  # rock 0: u == 0.5 exactly -> sign() gives 0
-    rd[1, :] = (1 << 31) - 1
-    rd[2, :] = (1 << 31) + 1
-    rd[3, :] = 0x88888888  # every rock of the slot exactly at one half
+    rd = philox.draw_slots(SEED, np.arange(M), 0, philox.DOMAIN_RESET, 1)
+    rd[0, 0] = 1 << 1                  # rock 0: u == 0.5 exactly -> sign() gives 0
+    rd[1, 0] = (1 << 31) - 1
+    rd[2, 0] = (1 << 31) + 1
+    rd[3, 0] = 1 << (2 * (k - 1) + 1)  # the last rock exactly at one half
+    rd[4, 0] = 0                       # every rock below one half
+    rd[5, 0] = 0xFFFFFFFF              # every rock above
+    rd[6, 0] = 1                       # a single bit that decides nothing: nobody ties
+    rd[7, 0] = 0xAAAAAAAA
+    rd[8, 0] = 0x55555555
+    rd[9, 0] = 1 << 9                  # rock 4 ties
     rst, rob, rxy = [], [], []
     from oracle.pomdp_oracle import rock_reset_word
     for i in range(M):
-        d.clear(); d.feed([rock_reset_word(int(rd[i, r >> 3]), r) for r in range(k)])
+        d.clear(); d.feed([rock_reset_word(int(rd[i, 0]), r) for r in range(k)])
         rob.append(env.reset())
         rst.append([r.status for r in env.state.rocks]); rxy.append(tuple(env.state.agent_pos))
         assert not d.np_queue

@@ -70,8 +70,8 @@ def gen_rock(E, out, tag, n, k, stochastic, M, T):
     def snap():
         return env.state.agent_pos.x, env.state.agent_pos.y, [r.status for r in env.state.rocks]
     for e in range(M):
-        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (k + 7) // 8)
-        d.clear(); d.feed([rock_reset_word(int(rw[r >> 3]), r) for r in range(k)])   # rock r's uniform(0,1), rock.py:78-80
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, 1)
+        d.clear(); d.feed([rock_reset_word(int(rw[0]), r) for r in range(k)])   # rock r's uniform(0,1), rock.py:78-80
         env.reset()
         d.clear()
         x0, y0, st0 = snap()
@@ -224,8 +224,8 @@ def gen_rock_stats(E, out, tag, n, k, stochastic, M, T):
     obs, alive = np.zeros((M, T), np.int32), np.zeros((M, T), bool)
     x0, y0, st0 = [], [], []
     for e in range(M):
-        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (k + 7) // 8)
-        d.clear(); d.feed([rock_reset_word(int(rw[r >> 3]), r) for r in range(k)])
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, 1)
+        d.clear(); d.feed([rock_reset_word(int(rw[0]), r) for r in range(k)])
         env.reset()
         d.clear()
         x0.append(env.state.agent_pos.x); y0.append(env.state.agent_pos.y); st0.append([r.status for r in env.state.rocks])

@@ -191,17 +191,16 @@ int oracle_rock_step(int n, int k, int stochastic, double p_move, int64_t N, int
 }
 
 /* rock.py:236-241, 266-271, 78-80: status = int(np.sign(uniform(0,1) - .5)), one uniform per rock.  Rock i's
- * uniform is r_i / 2^32 with r_i = rotl32(word of reset slot i >> 3, 4 * (i & 7)); draws is [N, (k + 7) / 8]. */
+ * uniform is r_i / 2^32 with r_i = rotl32(word of reset slot 0, 30 - 2 i); draws is [N, 1]. */
 int oracle_rock_reset(int n, int k, int64_t N, const uint32_t* draws, int32_t* x, int32_t* y,
                       int8_t* status, int32_t* obs) {
     const RockConfig* c = rock_config(n);
-    const int n_slots = (k + 7) / 8;
     if (!c) return -1;
     for (int64_t i = 0; i < N; ++i) {
         x[i] = c->sx; y[i] = c->sy; obs[i] = 0;
         for (int r = 0; r < k; ++r) {
-            const uint32_t w = draws[i * n_slots + (r >> 3)];
-            const int sh = 4 * (r & 7);
+            const uint32_t w = draws[i];
+            const int sh = (30 - 2 * r) & 31;
             const uint32_t ri = sh ? (w << sh) | (w >> (32 - sh)) : w;
             const double v = (double)ri / TWO32 - .5;
             status[i * k + r] = (int8_t)((v > 0) - (v < 0));

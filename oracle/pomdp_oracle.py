@@ -184,20 +184,20 @@ def rock_step(cfg, x, y, status, action, draw):
 
 
 def rock_reset_word(slot_word, rock):
-    """Rock i's uniform is u = r_i / 2**32, r_i = rotl32(word of reset slot i >> 3, 4 * (i & 7)): eight rocks share
-    one draw word (their deciding top bits are eight different bits of it)."""
-    sh = 4 * (rock & 7)
+    """Rock i's uniform is u = r_i / 2**32, r_i = rotl32(word of reset slot 0, 30 - 2 i): all rocks (k <= 16) share
+    one draw word -- the deciding top bit of r_i is bit 2 i + 1 of it, sixteen different bits."""
+    sh = (30 - 2 * rock) & 31
     return ((slot_word << sh) | (slot_word >> (32 - sh))) & 0xFFFFFFFF if sh else slot_word
 
 
 def rock_reset(cfg, draw):
-    """rock.py:236-241, 266-271, 78-80.  Rock i's ``uniform(0,1)`` comes from reset slot i >> 3 (rock_reset_word).
+    """rock.py:236-241, 266-271, 78-80.  Rock i's ``uniform(0,1)`` comes from reset slot 0 (rock_reset_word).
 
     status = int(sign(u - .5)): -1 below one half, +1 above, 0 exactly at u == 0.5.
     """
     status = []
     for i in range(cfg.k):
-        r = rock_reset_word(draw(i >> 3), i)
+        r = rock_reset_word(draw(0), i)
         status.append((r > (1 << 31)) - (r < (1 << 31)))
     return cfg.start[0], cfg.start[1], status, 0
 

@@ -703,4 +703,15 @@ void pomdp_hostsim_tenths_to_float(const int32_t* t, float* out, int64_t n) {
     for (int64_t i = 0; i < n; ++i) out[i] = tenths_to_float(t[i]);
 }
 
+// test-only: the one-LOP3 form of the sixteen reset status codes, for the brute-force check against the per-rock
+// definition (rock_status_code(rock_reset_word(w, i))) in tests/test_edge_cases.py
+void pomdp_hostsim_rock_reset_codes16(const uint32_t* w, uint32_t* fast, uint32_t* per_rock, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        fast[i] = rock_reset_codes16(w[i]);
+        uint32_t c = 0;
+        for (int r = 0; r < 16; ++r) c |= rock_status_code(rock_reset_word(w[i], r)) << (2 * r);
+        per_rock[i] = c;
+    }
+}
+
 }  // extern "C"

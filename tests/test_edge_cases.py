@@ -362,6 +362,31 @@ def test_network_reward_conversion_is_correctly_rounded():
     assert np.array_equal(out, (t.astype(np.float64) / 10.0).astype(np.float32))     # float32(the reference's double)
 
 
+def test_rock_reset_codes_one_lop3_equals_per_rock_definition():
+    """Reset draws every rock's status from ONE word (rock i's uniform = rotl32(w, 30 - 2i) / 2^32): the kernel forms all
+    sixteen 2-bit codes as 0x55555555 | (~w & 0xAAAAAAAA) plus a never-taken tie fix-up.  Checked against the per-rock
+    definition sign(u - .5) on every single-bit word, their neighbours, and 2^22 random words; and against the
+    Python oracle on the special words."""
+    import ctypes
+    from backends import build_hostsim
+    from oracle import pomdp_oracle as O
+    lib = ctypes.CDLL(build_hostsim())
+    special = [0, 0xFFFFFFFF, 0xAAAAAAAA, 0x55555555]
+    for b in range(32):
+        special += [1 << b, (1 << b) - 1, ((1 << b) + 1) & 0xFFFFFFFF, (~(1 << b)) & 0xFFFFFFFF, (3 << b) & 0xFFFFFFFF]
+    w = np.concatenate([np.array(special, dtype=np.uint32),
+                        np.random.RandomState(3).randint(0, 1 << 32, 1 << 22, dtype=np.uint64).astype(np.uint32)])
+    fast, slow = np.empty_like(w), np.empty_like(w)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.pomdp_hostsim_rock_reset_codes16(p(w), p(fast), p(slow), ctypes.c_int64(w.size))
+    assert np.array_equal(fast, slow)
+    cfg = O.RockCfg(15, 15)
+    for i in range(len(special)):
+        _, _, status, _ = O.rock_reset(cfg, lambda s, i=i: int(w[i]))
+        codes = [(0, 1, 0, 3)[st & 3] if st >= 0 else 3 for st in status]      # +1 -> 01, 0 -> 00, -1 -> 11
+        assert [(int(fast[i]) >> (2 * r)) & 3 for r in range(15)] == codes, hex(int(w[i]))
+
+
 @pytest.mark.parametrize("probs", [(0.0, 0.5, 1.0), (1.0, 1.0, 0.0), (0.25, 0.0, 0.5)])
 def test_network_probabilities_of_exactly_zero_and_one(backend, probs):
     """T = 0 (never fires) takes the 64-bit compare, T = 2^32 (always fires) the 32-bit one; both must agree with the

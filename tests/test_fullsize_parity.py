@@ -63,7 +63,7 @@ def rock_case(backend, board, k, B, goff, stochastic=False, ctr=17):
     # reset of the same shard
     st0, ob0 = env.init_states(B, step_ctr=ctr + 1)
     rx, ry, rst, rdone = (v.cpu().numpy() for v in env.unpack(st0))
-    qx, qy, qst, qob = C.rock_reset(board, k, C.fill_draws(SEED, goff, B, ctr + 1, philox.DOMAIN_RESET, (k + 7) // 8))
+    qx, qy, qst, qob = C.rock_reset(board, k, C.fill_draws(SEED, goff, B, ctr + 1, philox.DOMAIN_RESET, 1))
     assert np.array_equal(rx, qx) and np.array_equal(ry, qy) and np.array_equal(rst, qst.astype(np.int32))
     assert not ob0.any() and not rdone.any()
     return env, state, action, (ns, ob, rw, torch.as_tensor(fl))
