@@ -118,8 +118,9 @@ struct TagEnvT {
     }
     static POMDP_HD void reset4(const Params& p, const PhiloxKey& seed, uint64_t group, uint32_t ctr,
                                                   State s[4], int32_t ob[4]) {
-        WordDraw<1 + NOPP> d[4];
-        quad_words<1 + NOPP>(seed, group, ctr, DOMAIN_RESET, 1 + p.n_opp, d);
+        constexpr int NS = (1 + NOPP + TAG_DIGITS_PER_WORD - 1) / TAG_DIGITS_PER_WORD;     // three cells per draw word
+        WordDraw<NS> d[4];
+        quad_words<NS>(seed, group, ctr, DOMAIN_RESET, (1 + p.n_opp + TAG_DIGITS_PER_WORD - 1) / TAG_DIGITS_PER_WORD, d);
         POMDP_UNROLL
         for (int j = 0; j < 4; ++j) tag_reset(p, d[j], s[j], ob[j]);
     }

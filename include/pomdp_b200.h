@@ -137,7 +137,9 @@ int pomdp_tag_step(const PomdpTagParams* params, const void* d_table,
                    int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
                    int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                    void* stream);
-/* TagEnv.reset tag.py:97-102 (+ _get_init_state 181-193).  Slot 0 agent, 1+j opponent j. */
+/* TagEnv.reset tag.py:97-102 (+ _get_init_state 181-193): 1 + num_opponents calls of randint(29), agent
+ * first.  The j-th call returns the (j % 3)-th base-29 digit of draw slot j / 3's uniform, i.e.
+ * floor(u' * 29) with u' = frac(u * 29^(j % 3)): three cells per draw word.                */
 int pomdp_tag_reset(const PomdpTagParams* params,
                     int32_t* state, int32_t* obs, const uint8_t* mask,
                     int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,

@@ -253,14 +253,18 @@ def gen_tag(E, n_opp, tag):
                num_opp2=np.array(res["nop2"], np.int32), obs=np.array(res["ob"], np.int32),
                reward=np.array(res["rw"], np.float64), done=np.array(res["done"]),
                prob=np.array(res["prob"], np.float64))
-    # reset (tag.py:97-102): slot 0 agent, slot 1+j opponent j
+    # reset (tag.py:97-102): the j-th randint(29) (agent, then each opponent) = digit j % 3 of slot j // 3
+    from oracle.pomdp_oracle import tag_reset_word
     env.move_opponent = orig_move
     M = 600
-    rd = philox.draw_slots(SEED, np.arange(M), 0, philox.DOMAIN_RESET, 1 + n_opp)
-    rd[:64, 1] = rd[:64, 0]  # coinciding agent/opponent -> reset ob 29
+    n_cells = 1 + n_opp
+    rd = philox.draw_slots(SEED, np.arange(M), 0, philox.DOMAIN_RESET, (n_cells + 2) // 3)
+    for i in range(64):                # coinciding agent / opponent 0 -> reset ob 29: digits (a, a, i % 29) of slot 0
+        a = i % 29
+        rd[i, 0] = -(-(((a * 29 + a) * 29 + i % 29) * 2 ** 32 + 2 ** 31) // 29 ** 3)
     rob, rag, rop = [], [], []
     for i in range(M):
-        d.clear(); d.feed(rd[i])
+        d.clear(); d.feed([tag_reset_word(int(rd[i, j // 3]), j % 3) for j in range(n_cells)])
         rob.append(env.reset())
         rag.append(g.get_index(env.state.agent_pos)); rop.append([g.get_index(o) for o in env.state.opponent_pos])
         assert not d.np_queue and env.state.num_opp == n_opp

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import philox, ref_shim  # noqa: E402
-from oracle.pomdp_oracle import rock_reset_word  # noqa: E402
+from oracle.pomdp_oracle import rock_reset_word, tag_reset_word  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SEED = 0x5EED
@@ -105,7 +105,8 @@ def gen_tag(E, out, tag, n_opp, M, T):
     def snap():
         return g.get_index(env.state.agent_pos), [g.get_index(o) for o in env.state.opponent_pos], env.state.num_opp
     for e in range(M):
-        d.clear(); d.feed(W(e, RESET_CTR, philox.DOMAIN_RESET, 1 + n_opp))
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (1 + n_opp + 2) // 3)     # the j-th randint(29) = digit j % 3 of slot j // 3
+        d.clear(); d.feed([tag_reset_word(int(rw[j // 3]), j % 3) for j in range(1 + n_opp)])
         env.reset()
         d.clear()
         a0, o0, _ = snap()

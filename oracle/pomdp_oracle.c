@@ -273,15 +273,19 @@ void oracle_tag_step(int n_opp, double move_prob, int64_t N, int32_t* agent, int
     }
 }
 
-/* tag.py:97-102, 181-193, 43-44: slot 0 agent, slot 1+j opponent j; ob = _sample_ob(state, 0). */
-void oracle_tag_reset(int n_opp, int64_t N, const uint32_t* draws /* [N, 1+n_opp] */, int32_t* agent, int32_t* opp,
+/* tag.py:97-102, 181-193, 43-44: 1 + n_opp calls of randint(29), agent first; ob = _sample_ob(state, 0).  The j-th
+ * call is scripted with the word (slot j / 3) * 29^(j % 3) mod 2^32, i.e. it returns the (j % 3)-th base-29 digit of
+ * that slot's uniform; draws is [N, (1 + n_opp + 2) / 3]. */
+static uint32_t tag_reset_word(uint32_t w, int digit) { return digit == 0 ? w : digit == 1 ? w * 29u : w * 841u; }
+void oracle_tag_reset(int n_opp, int64_t N, const uint32_t* draws, int32_t* agent, int32_t* opp,
                       int32_t* num_opp, int32_t* obs) {
+    const int n_slots = (1 + n_opp + 2) / 3;
     for (int64_t i = 0; i < N; ++i) {
-        const uint32_t* dr = draws + i * (1 + n_opp);
-        agent[i] = below(dr[0], 29);
+        const uint32_t* dr = draws + i * n_slots;
+        agent[i] = below(tag_reset_word(dr[0], 0), 29);
         obs[i] = agent[i];
         for (int j = 0; j < n_opp; ++j) {
-            opp[i * n_opp + j] = below(dr[1 + j], 29);
+            opp[i * n_opp + j] = below(tag_reset_word(dr[(1 + j) / 3], (1 + j) % 3), 29);
             if (opp[i * n_opp + j] == agent[i]) obs[i] = 29;
         }
         num_opp[i] = n_opp;

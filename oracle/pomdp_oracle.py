@@ -345,10 +345,18 @@ def tag_step(ax, ay, opps, num_opp, action, draw, move_prob=0.8):
     return ax, ay, opps, num_opp, ob, reward, num_opp == 0
 
 
+def tag_reset_word(slot_word, digit):
+    """The word np.random.randint(29) is scripted with for the ``digit``-th (0..2) cell drawn from one reset slot:
+    floor(u' * 29) with u' = frac(u * 29**digit) is the digit-th base-29 digit of u = slot_word / 2**32."""
+    return (slot_word * 29 ** digit) & 0xFFFFFFFF
+
+
 def tag_reset(num_opponents, draw):
-    """tag.py:97-102, 181-193, 43-44.  Slot 0 = agent cell, slot 1+j = opponent j's cell."""
-    ax, ay = tag_get_coord(rand_below(draw(0), TAG_CELLS))
-    opps = [tag_get_coord(rand_below(draw(1 + j), TAG_CELLS)) for j in range(num_opponents)]
+    """tag.py:97-102, 181-193, 43-44.  The j-th randint(29) (j = 0 agent, 1 + i opponent i) is digit j % 3 of
+    reset slot j // 3 (tag_reset_word)."""
+    cell = lambda j: rand_below(tag_reset_word(draw(j // 3), j % 3), TAG_CELLS)
+    ax, ay = tag_get_coord(cell(0))
+    opps = [tag_get_coord(cell(1 + j)) for j in range(num_opponents)]
     return ax, ay, opps, num_opponents, tag_sample_ob(ax, ay, opps, 0)
 
 

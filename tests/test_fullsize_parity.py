@@ -129,7 +129,7 @@ def test_tag_batch_2p20(backend):
         assert np.array_equal(done, edone) and np.array_equal(fl.cpu().numpy(), edone.astype(np.int32))
         st0, ob0 = env.init_states(B, step_ctr=24)
         ra, ro, rn, _ = (v.cpu().numpy() for v in env.unpack(st0))
-        qa, qo, qn, qob = C.tag_reset(n_opp, C.fill_draws(SEED, 0, B, 24, philox.DOMAIN_RESET, 1 + n_opp))
+        qa, qo, qn, qob = C.tag_reset(n_opp, C.fill_draws(SEED, 0, B, 24, philox.DOMAIN_RESET, (1 + n_opp + 2) // 3))
         assert np.array_equal(ra, qa) and np.array_equal(ro, qo) and np.array_equal(rn, qn)
         assert np.array_equal(ob0.cpu().numpy(), qob)
 
