@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -74,7 +74,9 @@ _PROTOTYPES = {
     "pomdp_tag_step": (c_int32, [POINTER(TagParams), _P] + _STEP_TAIL),
     "pomdp_tag_reset": (c_int32, [POINTER(TagParams)] + _RESET_TAIL),
     "pomdp_battleship_step": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
-    "pomdp_battleship_reset": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64, c_uint64,
+    "pomdp_battleship_table_bytes": (c_int64, [POINTER(BattleshipParams)]),
+    "pomdp_battleship_build_table": (c_int32, [POINTER(BattleshipParams), c_void_p]),
+    "pomdp_battleship_reset": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64,
                                          c_uint32, c_void_p]),
     "pomdp_battleship_reset_warpscan": (c_int32, [POINTER(BattleshipParams), _P, _P, _P, _P, c_int64, c_int64, c_uint64,
                                                   c_uint32, c_void_p]),

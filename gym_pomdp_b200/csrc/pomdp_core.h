@@ -24,8 +24,6 @@
 
 namespace pomdp {
 
-typedef unsigned __int128 u128;
-
 enum : int32_t { FLAG_DONE = 1, FLAG_BAD_ACTION = 2, FLAG_STEPPED_DONE = 4, FLAG_BAD_STATE = 8 };
 enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1, DOMAIN_POLICY = 2 };
 
@@ -693,24 +691,48 @@ struct ShipDev {
     // [ship index] the cells of a vertical ship whose lowest cell is cell 0: bits 0, X, 2X, ... (length - 1) X
     uint64_t vpat_lo[SHIP_MAX_SHIPS], vpat_hi[SHIP_MAX_SHIPS];
 };
+
+// A board of up to 128 cells as two explicit 64-bit halves (bit c = cell c = X*y + x).  Nothing on the device uses
+// unsigned __int128: nvcc 12.9 lowered `r & (r >> 1)` on a 128-bit value in this code to two independent 64-bit
+// shifts, losing the bit that crosses from the high to the low half -- caught by the GPU parity tests, reproduced in
+// isolation, absent from g++.
+struct B128 { uint64_t lo, hi; };
+POMDP_HD B128 b128(uint64_t lo, uint64_t hi) { B128 r; r.lo = lo; r.hi = hi; return r; }
+POMDP_HD B128 operator&(B128 a, B128 b) { return b128(a.lo & b.lo, a.hi & b.hi); }
+POMDP_HD B128 operator|(B128 a, B128 b) { return b128(a.lo | b.lo, a.hi | b.hi); }
+POMDP_HD B128 operator~(B128 a) { return b128(~a.lo, ~a.hi); }
+// shifts by 0 <= s; anything pushed past either end is dropped, s >= 128 gives 0
+POMDP_HD B128 shr(B128 v, int s) {
+    if (s >= 128) return b128(0, 0);
+    if (s >= 64) return b128(v.hi >> (s - 64), 0);
+    return b128((v.lo >> s) | ((v.hi << 1) << (63 - s)), v.hi >> s);      // (hi << 1) << (63 - s): s = 0 stays defined
+}
+POMDP_HD B128 shl(B128 v, int s) {
+    if (s >= 128) return b128(0, 0);
+    if (s >= 64) return b128(0, v.lo << (s - 64));
+    return b128(v.lo << s, (v.hi << s) | ((v.lo >> 1) >> (63 - s)));
+}
+POMDP_HD B128 b128_bit(int i) { return i < 64 ? b128(1ull << i, 0) : b128(0, 1ull << (i - 64)); }        // 0 <= i < 128
+POMDP_HD bool b128_test(B128 v, int i) { return (((i < 64 ? v.lo : v.hi) >> (i & 63)) & 1ull) != 0; }    // 0 <= i < 128
+
 struct ShipState {
-    u128 occ, vis;     // bit c = cell c = X*y + x
+    B128 occ, vis;
     int remaining;
     bool done;
 };
 
 POMDP_HD ShipState ship_unpack(const uint32_t w[SHIP_WORDS]) {
     ShipState st;
-    st.occ = (u128)w[0] | ((u128)w[1] << 32) | ((u128)w[2] << 64) | ((u128)(w[3] & 0x00FFFFFFu) << 96);
-    st.vis = (u128)w[4] | ((u128)w[5] << 32) | ((u128)w[6] << 64) | ((u128)w[7] << 96);
+    st.occ = b128((uint64_t)w[0] | ((uint64_t)w[1] << 32), (uint64_t)w[2] | ((uint64_t)(w[3] & 0x00FFFFFFu) << 32));
+    st.vis = b128((uint64_t)w[4] | ((uint64_t)w[5] << 32), (uint64_t)w[6] | ((uint64_t)w[7] << 32));
     st.remaining = (int)((w[3] >> 24) & 0x7Fu);
     st.done = (w[3] >> 31) != 0;
     return st;
 }
 POMDP_HD void ship_pack(const ShipState& st, uint32_t w[SHIP_WORDS]) {
-    w[0] = (uint32_t)st.occ; w[1] = (uint32_t)(st.occ >> 32); w[2] = (uint32_t)(st.occ >> 64);
-    w[3] = ((uint32_t)(st.occ >> 96) & 0x00FFFFFFu) | ((uint32_t)(st.remaining & 0x7F) << 24) | (st.done ? 0x80000000u : 0u);
-    w[4] = (uint32_t)st.vis; w[5] = (uint32_t)(st.vis >> 32); w[6] = (uint32_t)(st.vis >> 64); w[7] = (uint32_t)(st.vis >> 96);
+    w[0] = (uint32_t)st.occ.lo; w[1] = (uint32_t)(st.occ.lo >> 32); w[2] = (uint32_t)st.occ.hi;
+    w[3] = ((uint32_t)(st.occ.hi >> 32) & 0x00FFFFFFu) | ((uint32_t)(st.remaining & 0x7F) << 24) | (st.done ? 0x80000000u : 0u);
+    w[4] = (uint32_t)st.vis.lo; w[5] = (uint32_t)(st.vis.lo >> 32); w[6] = (uint32_t)st.vis.hi; w[7] = (uint32_t)(st.vis.hi >> 32);
 }
 
 // battleship.py:91-122 on the 8 packed words (the `diagonal` writes at 111-113 are dead state).
@@ -744,54 +766,35 @@ POMDP_HD void battleship_step(const ShipDev& p, const uint32_t w[SHIP_WORDS], in
 
 // Cells a new ship may not touch (battleship.py:195-211): occupied cells and every cell q
 // with an occupied cell at q + {N,E,S,W,NE,SE,SW}.  q + NW is never looked at (range(8)
-// over the Compass enum stops before NorthWest).
-POMDP_HD u128 ship_blocked(const ShipDev& p, u128 occ) {
-    const u128 col0 = (u128)p.col0_lo | ((u128)p.col0_hi << 64);
-    const u128 colL = (u128)p.colL_lo | ((u128)p.colL_hi << 64);
+// over the Compass enum stops before NorthWest).  The literal form: one shift per neighbour (used by the warp
+// scan and the rejection loop; the bitboard placement below factors the same set into four shifts).
+POMDP_HD B128 ship_blocked(const ShipDev& p, B128 occ) {
+    const B128 col0 = b128(p.col0_lo, p.col0_hi), colL = b128(p.colL_lo, p.colL_hi);
     const int X = p.X;
-    u128 b = occ;
-    b |= occ >> X;                    // q + N occupied
-    b |= occ << X;                    // q + S occupied
-    b |= (occ >> 1) & ~colL;          // q + E occupied (q not in the last column)
-    b |= (occ << 1) & ~col0;          // q + W
-    b |= (occ >> (X + 1)) & ~colL;    // q + NE
-    b |= (occ << (X - 1)) & ~colL;    // q + SE
-    b |= (occ << (X + 1)) & ~col0;    // q + SW
+    B128 b = occ;
+    b = b | shr(occ, X);                     // q + N occupied
+    b = b | shl(occ, X);                     // q + S occupied
+    b = b | (shr(occ, 1) & ~colL);           // q + E occupied (q not in the last column)
+    b = b | (shl(occ, 1) & ~col0);           // q + W
+    b = b | (shr(occ, X + 1) & ~colL);       // q + NE
+    b = b | (shl(occ, X - 1) & ~colL);       // q + SE
+    b = b | (shl(occ, X + 1) & ~col0);       // q + SW
     return b;
 }
 
 // Would the reference's collision() accept this (pos, dir, length)?  Walks length + 1
 // cells and needs the cell after each inside the board (battleship.py:199-201).
-POMDP_HD bool ship_candidate_ok(const ShipDev& p, u128 blocked, int pos, int dir, int length) {
+POMDP_HD bool ship_candidate_ok(const ShipDev& p, B128 blocked, int pos, int dir, int length) {
     const int x = pos % p.X, y = pos / p.X;
     const int dx = move_dx(dir), dy = move_dy(dir);   // Compass 0..3 == Moves 0..3
     if (!grid_is_inside(p.X, p.Y, x + (length + 1) * dx, y + (length + 1) * dy)) return false;
     const int stride = dy * p.X + dx;
     bool ok = true;
-    for (int i = 0; i <= length; ++i) ok = ok && !((uint32_t)(blocked >> (pos + i * stride)) & 1u);
+    for (int i = 0; i <= length; ++i) ok = ok && !b128_test(blocked, pos + i * stride);
     return ok;
 }
 
 // ---- bitboard placement: every (pos, dir) candidate of one ship at once ------------------------------------------
-// The board as two explicit 64-bit halves.  (The placement code does NOT use unsigned __int128: nvcc 12.9 lowers
-// `r & (r >> 1)` on a 128-bit value in this code to two independent 64-bit shifts, losing the bit that crosses from
-// the high to the low half -- caught by the GPU parity tests, reproduced in isolation, absent from g++.)
-struct B128 { uint64_t lo, hi; };
-POMDP_HD B128 b128(uint64_t lo, uint64_t hi) { B128 r; r.lo = lo; r.hi = hi; return r; }
-POMDP_HD B128 operator&(B128 a, B128 b) { return b128(a.lo & b.lo, a.hi & b.hi); }
-POMDP_HD B128 operator|(B128 a, B128 b) { return b128(a.lo | b.lo, a.hi | b.hi); }
-POMDP_HD B128 operator~(B128 a) { return b128(~a.lo, ~a.hi); }
-// shifts by 0 <= s; anything pushed past either end is dropped, s >= 128 gives 0
-POMDP_HD B128 shr(B128 v, int s) {
-    if (s >= 128) return b128(0, 0);
-    if (s >= 64) return b128(v.hi >> (s - 64), 0);
-    return b128((v.lo >> s) | ((v.hi << 1) << (63 - s)), v.hi >> s);      // (hi << 1) << (63 - s): s = 0 stays defined
-}
-POMDP_HD B128 shl(B128 v, int s) {
-    if (s >= 128) return b128(0, 0);
-    if (s >= 64) return b128(0, v.lo << (s - 64));
-    return b128(v.lo << s, (v.hi << s) | ((v.lo >> 1) >> (63 - s)));
-}
 POMDP_HD B128 ship_blocked_b(const ShipDev& p, B128 occ) {
     const B128 col0 = b128(p.col0_lo, p.col0_hi), colL = b128(p.colL_lo, p.colL_hi);
     // N, S, E, W, NE, SE, SW neighbours (not NW: battleship.py:203-211 never looks there) in four shifts: with
@@ -876,19 +879,19 @@ POMDP_HD B128 ship_cells(const ShipDev& p, int ship_index, int pos, int dir, int
 POMDP_HD void ship_mark(const ShipDev& p, ShipState& st, int pos, int dir, int length) {
     const int stride = move_dy(dir) * p.X + move_dx(dir);
     for (int i = 0; i < length; ++i) {
-        const u128 bit = (u128)1 << (pos + i * stride);
-        st.occ |= bit;
-        if (!(st.vis & bit)) ++st.remaining;
+        const int c = pos + i * stride;
+        if (!b128_test(st.vis, c)) ++st.remaining;
+        st.occ = st.occ | b128_bit(c);
     }
 }
 
 // battleship.py:167-180 as written: rejection sampling; attempt a -> slots 2a (pos), 2a+1 (dir).
 POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step,
                                          ShipState& st, int max_attempts) {
-    st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+    st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
     int a = 0;
     for (int length = p.max_len; length >= 2; --length) {
-        const u128 blocked = ship_blocked(p, st.occ);
+        const B128 blocked = ship_blocked(p, st.occ);
         for (;;) {
             if (a >= max_attempts) return false;
             const uint32_t w_pos = draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)(2 * a));
@@ -902,24 +905,76 @@ POMDP_HD bool battleship_reset_rejection(const ShipDev& p, const PhiloxKey& seed
 }
 
 // battleship.py:167-180 in fixed time: ship s takes the k-th of its accepted (pos, dir) candidates, k = floor(u * count),
-// u = draw slot s -- the distribution of the reference's rejection loop (uniform over the accepted set).  Returns
-// false when some ship has no placement (the reference would loop forever).
-POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step, ShipState& st) {
-    st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
-    B128 occ = b128(0, 0);
-    int ship = 0;
-    bool ok = true;
-    for (int length = p.max_len; length >= 2; --length, ++ship) {
+// u = draw slot s -- the distribution of the reference's rejection loop (uniform over the accepted set).  Places ships
+// ship_from, ship_from + 1, ... on top of `occ`.  Returns false when some ship has no placement (the reference would
+// loop forever).
+template <class D>
+POMDP_HD bool battleship_place_from(const ShipDev& p, const D& draw, int ship_from, B128& occ, int& remaining) {
+    int ship = ship_from;
+    for (int length = p.max_len - ship_from; length >= 2; --length, ++ship) {
         B128 valid[4];
         ship_valid_starts(p, ship_blocked_b(p, occ), ship, length, valid);
         const int total = ship_count(valid);
-        if (total == 0) { ok = false; break; }
-        const int c = ship_pick(valid, (int)rand_below(draw_word(seed, env, step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total));
+        if (total == 0) return false;
+        const int c = ship_pick(valid, (int)rand_below(draw(ship), (uint32_t)total));
         occ = occ | ship_cells(p, ship, c >> 2, c & 3, length);
-        st.remaining += length;
+        remaining += length;
     }
-    st.occ = (u128)occ.lo | ((u128)occ.hi << 64);
-    return ok;
+    return true;
+}
+POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step, ShipState& st) {
+    st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
+    return battleship_place_from(p, LazyDraw{&seed, env, step, DOMAIN_RESET}, 0, st.occ, st.remaining);
+}
+
+// ---- placement tables: the accepted sets of the first two ships are static --------------------------------------
+// Ship 0 is placed on an empty board, so its accepted (pos, dir) set never changes (240 of 400 candidates on 10x10,
+// 20 of 100 on 5x5); ship 1's accepted set depends only on where ship 0 went.  Both are tabulated on the host
+// (pomdp_host.h: make_ship_table, from the very functions above) into a caller-owned device buffer:
+//   ShipTableHdr (32 B)
+//   first [n0]   uint16  ship 0's accepted candidates c = 4 * pos + dir in increasing order
+//   cnt1  [n0]   uint16  number of accepted candidates of ship 1 given ship 0 = first[k0]
+//   off1  [n0]   uint32  start of that list in second[]
+//   second[...]  uint16  ship 1's accepted candidates per k0, each list in increasing order
+// so a reset is two table reads per ship instead of ~25 128-bit shifts and a masked-popcount search:
+//   ship s takes list_s[floor(u_s * len(list_s))], u_s = draw slot s -- the same candidate the bitboard scan picks.
+// Ships 2.. (max_len > 3) continue with the bitboard scan.
+struct ShipTableHdr { uint32_t magic, n0, n_tabled, off_first, off_cnt1, off_off1, off_second, bytes; };
+constexpr uint32_t SHIP_TABLE_MAGIC = 0x53485054u;
+POMDP_HD uint32_t ld_ro16(const uint16_t* p) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(p);
+#else
+    return (uint32_t)*p;
+#endif
+}
+POMDP_HD uint32_t ld_ro32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+template <class D>
+POMDP_HD bool battleship_reset_table(const ShipDev& p, const unsigned char* __restrict__ tbl, const D& draw, ShipState& st) {
+    st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
+    const ShipTableHdr* h = reinterpret_cast<const ShipTableHdr*>(tbl);
+    const uint32_t n0 = ld_ro32(&h->n0), n_tabled = ld_ro32(&h->n_tabled);
+    if (n0 == 0) return false;
+    const uint32_t k0 = rand_below(draw(0), n0);
+    const uint32_t c0 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_first)) + k0);
+    st.occ = ship_cells(p, 0, (int)(c0 >> 2), (int)(c0 & 3u), p.max_len);
+    st.remaining = p.max_len;
+    if (p.max_len < 3) return true;
+    if (n_tabled < 2) return battleship_place_from(p, draw, 1, st.occ, st.remaining);
+    const uint32_t n1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_cnt1)) + k0);
+    if (n1 == 0) return false;
+    const uint32_t o1 = ld_ro32(reinterpret_cast<const uint32_t*>(tbl + ld_ro32(&h->off_off1)) + k0);
+    const uint32_t k1 = rand_below(draw(1), n1);
+    const uint32_t c1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_second)) + o1 + k1);
+    st.occ = st.occ | ship_cells(p, 1, (int)(c1 >> 2), (int)(c1 & 3u), p.max_len - 1);
+    st.remaining += p.max_len - 1;
+    return battleship_place_from(p, draw, 2, st.occ, st.remaining);
 }
 
 // battleship.py:157-165: _generate_legal = the unvisited cells in increasing action order; the policy draws one

@@ -244,27 +244,82 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
     if (total > 127) return fail(POMDP_E_BADARG, "battleship: total ship length %d does not fit 7 bits", total);
     memset(d, 0, sizeof(*d));
     d->X = q->x_size; d->Y = q->y_size; d->max_len = q->max_len; d->n_tiles = q->x_size * q->y_size;
-    u128 c0 = 0, cL = 0;
-    for (int y = 0; y < d->Y; ++y) { c0 |= (u128)1 << (y * d->X); cL |= (u128)1 << (y * d->X + d->X - 1); }
-    d->col0_lo = (uint64_t)c0; d->col0_hi = (uint64_t)(c0 >> 64);
-    d->colL_lo = (uint64_t)cL; d->colL_hi = (uint64_t)(cL >> 64);
+    B128 c0 = b128(0, 0), cL = b128(0, 0);
+    for (int y = 0; y < d->Y; ++y) { c0 = c0 | b128_bit(y * d->X); cL = cL | b128_bit(y * d->X + d->X - 1); }
+    d->col0_lo = c0.lo; d->col0_hi = c0.hi;
+    d->colL_lo = cL.lo; d->colL_hi = cL.hi;
     if (q->max_len - 1 <= SHIP_MAX_SHIPS) {
         int ship = 0;
         for (int length = q->max_len; length >= 2; --length, ++ship) {
-            u128 vp = 0;
-            for (int i = 0; i < length && i * d->X < 128; ++i) vp |= (u128)1 << (i * d->X);
-            d->vpat_lo[ship] = (uint64_t)vp; d->vpat_hi[ship] = (uint64_t)(vp >> 64);
+            B128 vp = b128(0, 0);
+            for (int i = 0; i < length && i * d->X < 128; ++i) vp = vp | b128_bit(i * d->X);
+            d->vpat_lo[ship] = vp.lo; d->vpat_hi[ship] = vp.hi;
             for (int dir = 0; dir < 4; ++dir) {
-                u128 m = 0;
+                B128 m = b128(0, 0);
                 for (int y = 0; y < d->Y; ++y)
                     for (int x = 0; x < d->X; ++x)
                         if (grid_is_inside(d->X, d->Y, x + (length + 1) * move_dx(dir), y + (length + 1) * move_dy(dir)))
-                            m |= (u128)1 << (y * d->X + x);
-                d->inside_lo[dir][ship] = (uint64_t)m; d->inside_hi[dir][ship] = (uint64_t)(m >> 64);
+                            m = m | b128_bit(y * d->X + x);
+                d->inside_lo[dir][ship] = m.lo; d->inside_hi[dir][ship] = m.hi;
             }
         }
     }
     return 0;
+}
+
+// The placement tables of BattleShip reset (layout: pomdp_core.h, ShipTableHdr).  With tbl == nullptr only the size is
+// computed.  Returns the table's size in bytes (a multiple of 16) or a negative error code.
+inline int64_t make_ship_table(const PomdpBattleshipParams* q, void* tbl) {
+    ShipDev d;
+    const int rc = make_ship(q, &d);
+    if (rc) return rc < 0 ? rc : -rc;
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return fail(POMDP_E_BADARG, "battleship: more than %d ships", SHIP_MAX_SHIPS);
+    auto list_of = [&](const B128 valid[4], uint16_t* out) {     // accepted candidates in increasing c = 4 * pos + dir
+        int n = 0;
+        for (int pos = 0; pos < d.n_tiles; ++pos)
+            for (int dir = 0; dir < 4; ++dir)
+                if (b128_test(valid[dir], pos)) { if (out) out[n] = (uint16_t)(4 * pos + dir); ++n; }
+        return n;
+    };
+    B128 valid0[4];
+    ship_valid_starts(d, ship_blocked_b(d, b128(0, 0)), 0, d.max_len, valid0);
+    uint16_t first[4 * SHIP_MAX_CELLS];
+    const int n0 = list_of(valid0, first);
+    const bool two = d.max_len >= 3;
+    int64_t n_second = 0;
+    if (two)
+        for (int k0 = 0; k0 < n0; ++k0) {
+            B128 v1[4];
+            ship_valid_starts(d, ship_blocked_b(d, ship_cells(d, 0, first[k0] >> 2, first[k0] & 3, d.max_len)), 1, d.max_len - 1, v1);
+            n_second += list_of(v1, nullptr);
+        }
+    auto up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+    ShipTableHdr h;
+    h.magic = SHIP_TABLE_MAGIC; h.n0 = (uint32_t)n0; h.n_tabled = two ? 2u : 1u;
+    h.off_first = (uint32_t)sizeof(ShipTableHdr);
+    h.off_cnt1 = (uint32_t)up16(h.off_first + 2 * (int64_t)n0);
+    h.off_off1 = (uint32_t)up16(h.off_cnt1 + 2 * (int64_t)n0);
+    h.off_second = (uint32_t)up16(h.off_off1 + 4 * (int64_t)n0);
+    h.bytes = (uint32_t)up16(h.off_second + 2 * n_second);
+    if (!tbl) return (int64_t)h.bytes;
+    memset(tbl, 0, h.bytes);
+    memcpy(tbl, &h, sizeof(h));
+    uint16_t* t_first = (uint16_t*)((char*)tbl + h.off_first);
+    uint16_t* t_cnt1 = (uint16_t*)((char*)tbl + h.off_cnt1);
+    uint32_t* t_off1 = (uint32_t*)((char*)tbl + h.off_off1);
+    uint16_t* t_second = (uint16_t*)((char*)tbl + h.off_second);
+    memcpy(t_first, first, 2 * (size_t)n0);
+    uint32_t off = 0;
+    if (two)
+        for (int k0 = 0; k0 < n0; ++k0) {
+            B128 v1[4];
+            ship_valid_starts(d, ship_blocked_b(d, ship_cells(d, 0, first[k0] >> 2, first[k0] & 3, d.max_len)), 1, d.max_len - 1, v1);
+            const int n1 = list_of(v1, t_second + off);
+            t_cnt1[k0] = (uint16_t)n1;
+            t_off1[k0] = off;
+            off += (uint32_t)n1;
+        }
+    return (int64_t)h.bytes;
 }
 
 // pomdp_step_packed_host: the pipe, the kind, the state width the pipe was made for and the host pointers

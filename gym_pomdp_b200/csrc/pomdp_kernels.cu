@@ -649,11 +649,11 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         if (mask && !mask[i]) continue;       // warp-uniform
         ShipState st;
-        st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+        st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
         bool ok_all = true;
         int ship = 0;
         for (int length = p.max_len; length >= 2; --length, ++ship) {
-            const u128 blocked = ship_blocked(p, st.occ);
+            const B128 blocked = ship_blocked(p, st.occ);
             uint32_t mine = 0;                // bit j: candidate lane + 32 j is accepted
             int total = 0;
             for (int j = 0; j < n_iter; ++j) {
@@ -715,6 +715,56 @@ pomdp_battleship_reset_bitboard_kernel(const __grid_constant__ ShipDev p, int32_
         if (obs) obs[i] = 0;                                               // battleship.py:137
         if (flags) flags[i] = ok ? 0 : FLAG_BAD_STATE;
     }
+}
+
+// One thread per env, placements of the first two ships read from the host-built tables (pomdp_core.h:
+// battleship_reset_table) -- two Philox words and four small table reads per board instead of the bitboard scan.
+// kBulk (state 16-byte aligned, no mask): the CTA's tile of boards is assembled in shared memory and leaves with ONE
+// TMA bulk store per tile, like the step kernel's; otherwise every thread stores its own 32 bytes.
+template <bool kBulk>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_battleship_reset_table_kernel(const __grid_constant__ ShipDev p, const unsigned char* __restrict__ tbl,
+                                    int32_t* __restrict__ state, int32_t* __restrict__ obs, int32_t* __restrict__ flags,
+                                    const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
+                                    const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
+    __shared__ alignas(128) uint32_t tile[kBulk ? POMDP_THREADS * SHIP_WORDS : 4];
+    const int64_t n_tiles = (n + POMDP_THREADS - 1) / POMDP_THREADS;
+    for (int64_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+        const int64_t base = tix * POMDP_THREADS;
+        const int cnt = (int)min((int64_t)POMDP_THREADS, n - base);
+        const int64_t i = base + threadIdx.x;
+        if ((int)threadIdx.x < cnt && (kBulk || !mask || mask[i])) {
+            ShipState st;
+            const bool ok = battleship_reset_table(p, tbl, LazyDraw{&seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET}, st);
+            uint32_t w8[SHIP_WORDS];
+            ship_pack(st, w8);
+            if (kBulk) {
+                uint4* mine = reinterpret_cast<uint4*>(tile + threadIdx.x * SHIP_WORDS);
+                mine[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                mine[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            } else if ((reinterpret_cast<uintptr_t>(state) & 15) == 0) {
+                uint4* dst = reinterpret_cast<uint4*>(state + i * SHIP_WORDS);
+                __stcs(dst, make_uint4(w8[0], w8[1], w8[2], w8[3]));
+                __stcs(dst + 1, make_uint4(w8[4], w8[5], w8[6], w8[7]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
+            }
+            if (obs) __stcs(obs + i, 0);                                   // battleship.py:137
+            if (flags) __stcs(flags + i, ok ? 0 : (int32_t)FLAG_BAD_STATE);
+        }
+        if (kBulk) {
+            fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the bulk-copy engine
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tma_bulk_s2g(state + base * SHIP_WORDS, tile, (uint32_t)cnt * SHIP_WORDS * 4u);
+                tma_commit();
+                tma_wait_read0();         // the tile may be overwritten once the engine has read it
+            }
+            __syncthreads();
+        }
+    }
+    if (kBulk && threadIdx.x == 0) tma_wait_all0();
 }
 
 __global__ void __launch_bounds__(POMDP_THREADS)
@@ -1273,7 +1323,13 @@ int pomdp_battleship_step(const PomdpBattleshipParams* q, const int32_t* state, 
     }
     return finish("pomdp_battleship_step");
 }
-int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+int64_t pomdp_battleship_table_bytes(const PomdpBattleshipParams* q) { return host::make_ship_table(q, nullptr); }
+int pomdp_battleship_build_table(const PomdpBattleshipParams* q, void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "battleship: host_table is NULL");
+    const int64_t rc = host::make_ship_table(q, host_table);
+    return rc < 0 ? (int)-rc : 0;
+}
+int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* d_table, int32_t* state, int32_t* obs, int32_t* flags,
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                            void* stream) {
     ShipDev d;
@@ -1281,9 +1337,22 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
     if (rc) return rc;
     if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
     if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset: bad n or NULL state");
+    if (goff < 0) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset: global_offset is negative");
+    if ((uintptr_t)d_table & 15) return host::fail(POMDP_E_ALIGN, "pomdp_battleship_reset: d_table must be 16-byte aligned");
     if (n == 0) return 0;
-    auto k = pomdp_battleship_reset_bitboard_kernel;
-    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_table) {
+        auto k = pomdp_battleship_reset_bitboard_kernel;
+        k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
+    } else if (!mask && (((uintptr_t)state) & 15) == 0) {
+        auto k = pomdp_battleship_reset_table_kernel<true>;
+        k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, (const unsigned char*)d_table, state, obs, flags, mask, n, (uint64_t)goff,
+                                                    philox_key(seed), step_ctr);
+    } else {
+        auto k = pomdp_battleship_reset_table_kernel<false>;
+        k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, (const unsigned char*)d_table, state, obs, flags, mask, n, (uint64_t)goff,
+                                                    philox_key(seed), step_ctr);
+    }
     return finish("pomdp_battleship_reset");
 }
 int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,

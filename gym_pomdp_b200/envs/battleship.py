@@ -33,7 +33,7 @@ class BattleShipEnv(BatchedPomdpEnv):
     state_words = 8
 
     def __init__(self, board_size=(5, 5), max_len=3, batch_size=None, device="cuda", seed=0, global_offset=0,
-                 reset_mode="scan"):
+                 reset_mode="table"):
         super().__init__(batch_size, device, seed, global_offset)
         self.grid = Grid(*board_size)
         self._params = _lib.BattleshipParams(board_size[0], board_size[1], max_len, 0)
@@ -44,13 +44,21 @@ class BattleShipEnv(BatchedPomdpEnv):
         self._discount = 1.
         self.total_remaining = max_len - 1      # battleship.py:74 (an env attribute the reference only asserts on)
         self.max_len = max_len + 1              # battleship.py:75
-        if reset_mode not in ("scan", "warpscan", "rejection"):
-            raise ValueError("reset_mode must be 'scan' (bitboard, thread per env), 'warpscan' (warp per env; same boards) "
-                             "or 'rejection' (the reference's loop)")
+        if reset_mode not in ("table", "scan", "warpscan", "rejection"):
+            raise ValueError("reset_mode must be 'table' (placement tables, thread per env), 'scan' (bitboard scan, thread per "
+                             "env), 'warpscan' (warp per env) -- all three give the same boards -- or 'rejection' (the "
+                             "reference's loop)")
         self.reset_mode = reset_mode
         self.reset_flags = None
         self.t = 0
         self.tot_rw = 0
+        L = _lib.lib()
+        nbytes = L.pomdp_battleship_table_bytes(ctypes.byref(self._params))
+        if nbytes < 0:
+            raise ValueError(L.pomdp_last_error().decode())
+        host = np.zeros(nbytes, dtype=np.uint8)
+        _lib.check(L.pomdp_battleship_build_table(ctypes.byref(self._params), host.ctypes.data), "pomdp_battleship_build_table")
+        self._table = torch.from_numpy(host).to(self.device)      # accepted placements of ships 0 and 1 (static per config)
 
     def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
         _lib.check(_lib.lib().pomdp_battleship_step(
@@ -59,11 +67,29 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _c_reset(self, state, obs, mask, n, ctr):
         L = _lib.lib()
-        fn = {"scan": L.pomdp_battleship_reset, "warpscan": L.pomdp_battleship_reset_warpscan,
-              "rejection": L.pomdp_battleship_reset_rejection}[self.reset_mode]
         self.reset_flags = torch.zeros(n, dtype=torch.int32, device=self.device)
-        _lib.check(fn(ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(obs), _lib.ptr(self.reset_flags),
-                      _lib.ptr(mask), n, self.global_offset, self._seed, ctr, self._stream()), "pomdp_battleship_reset")
+        tail = (_lib.ptr(state), _lib.ptr(obs), _lib.ptr(self.reset_flags), _lib.ptr(mask), n, self.global_offset,
+                self._seed, ctr, self._stream())
+        if self.reset_mode in ("table", "scan"):
+            table = _lib.ptr(self._table) if self.reset_mode == "table" else None
+            rc = L.pomdp_battleship_reset(ctypes.byref(self._params), table, *tail)
+        else:
+            fn = L.pomdp_battleship_reset_warpscan if self.reset_mode == "warpscan" else L.pomdp_battleship_reset_rejection
+            rc = fn(ctypes.byref(self._params), *tail)
+        _lib.check(rc, "pomdp_battleship_reset")
+
+    def reset(self, mask=None):
+        """battleship.py:131-137.  A (board, max_len) with no legal placement makes the reference's rejection loop spin
+        forever; here the kernels flag it: scalar mode raises, batched mode ORs FLAG_BAD_STATE into ``flags``."""
+        obs = super().reset(mask)
+        rf = self.reset_flags
+        if rf is not None:
+            if self._scalar:
+                if int(rf[0]) & _lib.FLAG_BAD_STATE:
+                    raise RuntimeError("BattleShip: no legal ship placement exists on this board (the reference would loop forever)")
+            else:
+                self.flags = self.flags | rf
+        return obs
 
     def _hist_args(self):
         return self.grid.n_tiles, 0

@@ -61,7 +61,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 5
+#define POMDP_ABI_VERSION 6
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -166,10 +166,20 @@ int pomdp_battleship_step(const PomdpBattleshipParams* params,
  * c = 4*pos + dir, k = floor(u * count) from draw slot s -- the same distribution as the
  * reference's rejection loop (uniform over the accepted set).  POMDP_FLAG_BAD_STATE is raised in
  * flags (may be NULL) when no placement exists (the reference would spin forever).
- *   pomdp_battleship_reset          one THREAD per env, candidates as four 128-bit masks (bitboard)
+ *   pomdp_battleship_reset          one THREAD per env.  With `d_table` (device copy of the placement
+ *                                   tables below) the accepted sets of the first two ships are read from
+ *                                   the tables -- ship 0 meets an empty board, ship 1's set depends only on
+ *                                   ship 0's placement -- and boards leave through a TMA tile store; with
+ *                                   d_table == NULL (or for ships 2..) candidates are four 128-bit masks
+ *                                   built with shifts (bitboard scan)
  *   pomdp_battleship_reset_warpscan one WARP per env, lanes test candidates, ballots count them
- * Both produce identical boards.                                                              */
-int pomdp_battleship_reset(const PomdpBattleshipParams* params,
+ * All produce identical boards.                                                               */
+/* Placement tables (host-built, caller-owned, like Rock's): the accepted candidate list of ship 0 and,
+ * per ship-0 placement, the accepted list of ship 1 (~140 KB for 10x10 / max_len 3).  Fill a
+ * host buffer of pomdp_battleship_table_bytes() and upload it (16-byte aligned).              */
+int64_t pomdp_battleship_table_bytes(const PomdpBattleshipParams* params);
+int     pomdp_battleship_build_table(const PomdpBattleshipParams* params, void* host_table);
+int pomdp_battleship_reset(const PomdpBattleshipParams* params, const void* d_table,
                            int32_t* state, int32_t* obs, int32_t* flags, const uint8_t* mask,
                            int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
                            void* stream);

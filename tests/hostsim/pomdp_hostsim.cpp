@@ -298,18 +298,26 @@ int pomdp_battleship_step(const PomdpBattleshipParams* q, const int32_t* state, 
     }
     return 0;
 }
-// Serial stand-in for the warp scan: same candidate order, same k-th-accepted rule.
-int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
+int64_t pomdp_battleship_table_bytes(const PomdpBattleshipParams* q) { return host::make_ship_table(q, nullptr); }
+int pomdp_battleship_build_table(const PomdpBattleshipParams* q, void* host_table) {
+    if (!host_table) return host::fail(POMDP_E_BADARG, "battleship: host_table is NULL");
+    const int64_t rc = host::make_ship_table(q, host_table);
+    return rc < 0 ? (int)-rc : 0;
+}
+// table == NULL: the bitboard scan; otherwise the placement tables (the functors the two kernels inline)
+int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* table, int32_t* state, int32_t* obs, int32_t* flags,
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     ShipDev d;
     const PhiloxKey key = philox_key(seed);
     int rc = host::make_ship(q, &d);
     if (rc) return rc;
     if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
+    if ((uintptr_t)table & 15) return host::fail(POMDP_E_ALIGN, "pomdp_battleship_reset: d_table must be 16-byte aligned");
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         ShipState st;
-        const bool ok = battleship_reset_bitboard(d, key, (uint64_t)(goff + i), step, st);
+        const bool ok = table ? battleship_reset_table(d, (const unsigned char*)table, LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_RESET}, st)
+                              : battleship_reset_bitboard(d, key, (uint64_t)(goff + i), step, st);
         uint32_t w8[SHIP_WORDS];
         ship_pack(st, w8);
         for (int k = 0; k < SHIP_WORDS; ++k) state[i * SHIP_WORDS + k] = (int32_t)w8[k];
@@ -318,6 +326,7 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, int32_t* state, int32
     }
     return 0;
 }
+// Serial stand-in for the warp scan: same candidate order, same k-th-accepted rule.
 int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* state, int32_t* obs, int32_t* flags,
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     ShipDev d;
@@ -327,11 +336,11 @@ int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* sta
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         ShipState st;
-        st.occ = 0; st.vis = 0; st.remaining = 0; st.done = false;
+        st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
         bool ok_all = true;
         int ship = 0;
         for (int length = d.max_len; length >= 2 && ok_all; --length, ++ship) {
-            const u128 blocked = ship_blocked(d, st.occ);
+            const B128 blocked = ship_blocked(d, st.occ);
             int total = 0;
             for (int c = 0; c < 4 * d.n_tiles; ++c) total += ship_candidate_ok(d, blocked, c >> 2, c & 3, length);
             if (total == 0) { ok_all = false; break; }

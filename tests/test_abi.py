@@ -154,8 +154,12 @@ def test_error_convention(which):
     assert L.pomdp_network_step(ctypes.byref(_lib.NetworkParams(9, 3, .1, .33, .95)), p, p, p, p, p, p, 4, 0, 0, 0,
                                 None) == E_BADARG        # network.py:155: n % 3 == 1
     assert L.pomdp_battleship_step(ctypes.byref(_lib.BattleshipParams(20, 20, 3, 0)), p, p, p, p, p, p, 4, None) == E_BADARG
-    assert L.pomdp_battleship_reset(ctypes.byref(_lib.BattleshipParams(5, 5, 1, 0)), p, p, p, None, 4, 0, 0, 0,
+    assert L.pomdp_battleship_reset(ctypes.byref(_lib.BattleshipParams(5, 5, 1, 0)), None, p, p, p, None, 4, 0, 0, 0,
                                     None) == E_BADARG
+    assert L.pomdp_battleship_reset(ctypes.byref(_lib.BattleshipParams(5, 5, 3, 0)), p + 4, p, p, p, None, 4, 0, 0, 0,
+                                    None) == E_ALIGN         # d_table must be 16-byte aligned
+    assert L.pomdp_battleship_table_bytes(ctypes.byref(_lib.BattleshipParams(20, 20, 3, 0))) < 0
+    assert L.pomdp_battleship_build_table(ctypes.byref(_lib.BattleshipParams(5, 5, 3, 0)), None) == E_BADARG
     assert L.pomdp_coord_op(99, 7, 7, p, None, p, 4, None) == E_BADARG
     assert L.pomdp_coord_op(_lib.COORD_L1, 7, 7, p, None, p, 4, None) == E_BADARG     # L1 needs b
     assert L.pomdp_belief_hist(99, 0, 0, p, 1, 4, p, None) == E_BADARG

@@ -291,9 +291,22 @@ def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
     B = 3000
     a = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=9, reset_mode="scan")
     b = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=9, reset_mode="warpscan")
+    c = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=9, reset_mode="table")
     sa, _ = a.init_states(B, step_ctr=4)
     sb, _ = b.init_states(B, step_ctr=4)
     assert torch.equal(sa, sb) and torch.equal(a.reset_flags, b.reset_flags)
+    # the placement tables (accepted lists of ships 0 and 1 read instead of scanned; ships 2.. scanned): the same boards
+    # through the TMA tile store, through per-thread stores (masked reset) and on an unaligned view
+    sc, oc = c.init_states(B, step_ctr=4)
+    assert torch.equal(sa, sc) and torch.equal(a.reset_flags, c.reset_flags) and not oc.any()
+    mask = (torch.arange(B, device=sa.device) % 3 != 0).to(torch.uint8)
+    sm = torch.full_like(sa, -1)
+    c.init_states(B, out=(sm, torch.zeros(B, dtype=torch.int32, device=sa.device)), mask=mask, step_ctr=4)
+    assert torch.equal(sm[mask.bool()], sa[mask.bool()]) and (sm[~mask.bool()] == -1).all()
+    buf = torch.zeros(B * 8 + 1, dtype=torch.int32, device=sa.device)
+    su = buf[1:].view(B, 8)
+    c.init_states(B, out=(su, torch.zeros(B, dtype=torch.int32, device=sa.device)), step_ctr=4)
+    assert torch.equal(su, sa)
     if size == (3, 3):
         assert (a.reset_flags == _lib.FLAG_BAD_STATE).all()
     else:
@@ -415,11 +428,15 @@ def test_battleship_bitboard_reset_equals_oracle_on_odd_boards(backend, size, ma
     (battleship.py:195-211): same boards, same `no placement exists` flags, for shapes far from the stock 10 x 10."""
     from oracle import c_oracle as C, philox
     B = 2000
-    env = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=21, reset_mode="scan")
-    st, _ = env.init_states(B, step_ctr=9)
-    occ, vis, rem, done = env.unpack(st)
     eocc, erem, err = C.battleship_reset_scan(size[0], size[1], max_len, C.fill_draws(21, 0, B, 9, philox.DOMAIN_RESET, max_len - 1))
-    assert np.array_equal(occ.cpu().numpy(), eocc)
-    assert np.array_equal(rem.cpu().numpy(), erem)
-    assert np.array_equal(env.reset_flags.cpu().numpy() != 0, err != 0)
-    assert not vis.any() and not done.any()
+    # all three fixed-time kernels: placement tables + TMA tile store, bitboard scan, warp scan (whose literal
+    # seven-shift neighbour mask, ship_mark and ship_pack work on the same two-word boards -- no 128-bit integers
+    # on the device: ships straddle bits 31/32, 63/64 and 95/96 of the board on these shapes)
+    for mode in ("table", "scan", "warpscan"):
+        env = gp.make("Battleship-v0", board_size=size, max_len=max_len, batch_size=B, device=backend, seed=21, reset_mode=mode)
+        st, _ = env.init_states(B, step_ctr=9)
+        occ, vis, rem, done = env.unpack(st)
+        assert np.array_equal(occ.cpu().numpy(), eocc), mode
+        assert np.array_equal(rem.cpu().numpy(), erem), mode
+        assert np.array_equal(env.reset_flags.cpu().numpy() != 0, err != 0), mode
+        assert not vis.any() and not done.any()
