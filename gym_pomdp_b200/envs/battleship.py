@@ -67,7 +67,8 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _c_reset(self, state, obs, mask, n, ctr):
         L = _lib.lib()
-        self.reset_flags = torch.zeros(n, dtype=torch.int32, device=self.device)
+        # every reset env gets its flag word written by the kernel; only a masked reset needs the others pre-cleared
+        self.reset_flags = (torch.empty if mask is None else torch.zeros)(n, dtype=torch.int32, device=self.device)
         tail = (_lib.ptr(state), _lib.ptr(obs), _lib.ptr(self.reset_flags), _lib.ptr(mask), n, self.global_offset,
                 self._seed, ctr, self._stream())
         if self.reset_mode in ("table", "scan"):
