@@ -296,14 +296,30 @@ POMDP_HD S rock_reset_from_word(const RockDev& p, uint32_t w) {
 }
 template <typename S, class D>
 POMDP_HD S rock_reset(const RockDev& p, const D& draw) { return rock_reset_from_word<S>(p, draw(0)); }
-// Four envs of one aligned group: ONE Philox call.
+POMDP_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// Four envs of one aligned group: ONE Philox call, then per env one shift and one LOP3 -- with
+// C1 = start | (0x55555555 & m) << 8 and C2 = (0xAAAAAAAA & m) << 8 (loop invariants) the packed state is
+// C1 | (~(w << 8) & C2).  The tie (a word that is a single bit) is tested once for the four words and handled out
+// of line: it happens with probability 2^-27 per group.
+template <typename S>
+POMDP_HD void rock_reset4_words(const RockDev& p, const U4& q, S out[4]) {
+    const uint32_t m = p.k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * p.k)) - 1u);
+    const S c1 = (S)p.start | ((S)(0x55555555u & m) << 8), c2 = (S)(0xAAAAAAAAu & m) << 8;
+    out[0] = c1 | (~((S)q.x << 8) & c2);
+    out[1] = c1 | (~((S)q.y << 8) & c2);
+    out[2] = c1 | (~((S)q.z << 8) & c2);
+    out[3] = c1 | (~((S)q.w << 8) & c2);
+    const uint32_t single = umin32(umin32(q.x & (q.x - 1u), q.y & (q.y - 1u)), umin32(q.z & (q.z - 1u), q.w & (q.w - 1u)));
+    if (single == 0u) {                       // some word has at most one bit set: redo the group the careful way
+        out[0] = rock_reset_from_word<S>(p, q.x);
+        out[1] = rock_reset_from_word<S>(p, q.y);
+        out[2] = rock_reset_from_word<S>(p, q.z);
+        out[3] = rock_reset_from_word<S>(p, q.w);
+    }
+}
 template <typename S>
 POMDP_HD void rock_reset4(const RockDev& p, const PhiloxKey& seed, uint64_t group, uint32_t step, S out[4]) {
-    const U4 q = draw_quad(seed, group, step, DOMAIN_RESET, 0u);
-    out[0] = rock_reset_from_word<S>(p, q.x);
-    out[1] = rock_reset_from_word<S>(p, q.y);
-    out[2] = rock_reset_from_word<S>(p, q.z);
-    out[3] = rock_reset_from_word<S>(p, q.w);
+    rock_reset4_words<S>(p, draw_quad(seed, group, step, DOMAIN_RESET, 0u), out);
 }
 
 // ---- uniform-legal policy: np.random.choice(env._generate_legal()) --------------------
@@ -690,6 +706,9 @@ struct ShipDev {
     uint64_t inside_lo[4][SHIP_MAX_SHIPS], inside_hi[4][SHIP_MAX_SHIPS];
     // [ship index] the cells of a vertical ship whose lowest cell is cell 0: bits 0, X, 2X, ... (length - 1) X
     uint64_t vpat_lo[SHIP_MAX_SHIPS], vpat_hi[SHIP_MAX_SHIPS];
+    // layout of the placement tables (ShipTableHdr below; filled by pomdp_host.h: make_ship from the same enumeration
+    // that builds the table, so the kernel never reads the header)
+    uint32_t tbl_n0, tbl_n_tabled, tbl_off_rec, tbl_off_second;
 };
 
 // A board of up to 128 cells as two explicit 64-bit halves (bit c = cell c = X*y + x).  Nothing on the device uses
@@ -932,14 +951,14 @@ POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed,
 // 20 of 100 on 5x5); ship 1's accepted set depends only on where ship 0 went.  Both are tabulated on the host
 // (pomdp_host.h: make_ship_table, from the very functions above) into a caller-owned device buffer:
 //   ShipTableHdr (32 B)
-//   first [n0]   uint16  ship 0's accepted candidates c = 4 * pos + dir in increasing order
-//   cnt1  [n0]   uint16  number of accepted candidates of ship 1 given ship 0 = first[k0]
-//   off1  [n0]   uint32  start of that list in second[]
+//   rec   [n0]   {uint16 c0, uint16 n1, uint32 off1}: ship 0's k0-th accepted candidate c0 = 4 * pos + dir (in
+//                increasing order), the number of candidates ship 1 then has, and where their list starts in second[]
 //   second[...]  uint16  ship 1's accepted candidates per k0, each list in increasing order
-// so a reset is two table reads per ship instead of ~25 128-bit shifts and a masked-popcount search:
+// so a reset is two dependent table reads instead of ~25 128-bit shifts and a masked-popcount search per ship:
 //   ship s takes list_s[floor(u_s * len(list_s))], u_s = draw slot s -- the same candidate the bitboard scan picks.
 // Ships 2.. (max_len > 3) continue with the bitboard scan.
-struct ShipTableHdr { uint32_t magic, n0, n_tabled, off_first, off_cnt1, off_off1, off_second, bytes; };
+struct ShipTableHdr { uint32_t magic, n0, n_tabled, off_rec, off_second, bytes, pad0, pad1; };
+struct alignas(8) ShipRec { uint16_t c0, n1; uint32_t off1; };
 constexpr uint32_t SHIP_TABLE_MAGIC = 0x53485054u;
 POMDP_HD uint32_t ld_ro16(const uint16_t* p) {
 #if defined(__CUDA_ARCH__)
@@ -948,30 +967,28 @@ POMDP_HD uint32_t ld_ro16(const uint16_t* p) {
     return (uint32_t)*p;
 #endif
 }
-POMDP_HD uint32_t ld_ro32(const uint32_t* p) {
+POMDP_HD void ld_rec(const ShipRec* p, uint32_t& c0, uint32_t& n1, uint32_t& off1) {
 #if defined(__CUDA_ARCH__)
-    return __ldg(p);
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    c0 = v.x & 0xFFFFu; n1 = v.x >> 16; off1 = v.y;
 #else
-    return *p;
+    c0 = p->c0; n1 = p->n1; off1 = p->off1;
 #endif
 }
 template <class D>
 POMDP_HD bool battleship_reset_table(const ShipDev& p, const unsigned char* __restrict__ tbl, const D& draw, ShipState& st) {
     st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
-    const ShipTableHdr* h = reinterpret_cast<const ShipTableHdr*>(tbl);
-    const uint32_t n0 = ld_ro32(&h->n0), n_tabled = ld_ro32(&h->n_tabled);
-    if (n0 == 0) return false;
-    const uint32_t k0 = rand_below(draw(0), n0);
-    const uint32_t c0 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_first)) + k0);
+    if (p.tbl_n0 == 0) return false;
+    const uint32_t k0 = rand_below(draw(0), p.tbl_n0);
+    uint32_t c0, n1, off1;
+    ld_rec(reinterpret_cast<const ShipRec*>(tbl + p.tbl_off_rec) + k0, c0, n1, off1);
     st.occ = ship_cells(p, 0, (int)(c0 >> 2), (int)(c0 & 3u), p.max_len);
     st.remaining = p.max_len;
     if (p.max_len < 3) return true;
-    if (n_tabled < 2) return battleship_place_from(p, draw, 1, st.occ, st.remaining);
-    const uint32_t n1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_cnt1)) + k0);
+    if (p.tbl_n_tabled < 2) return battleship_place_from(p, draw, 1, st.occ, st.remaining);
     if (n1 == 0) return false;
-    const uint32_t o1 = ld_ro32(reinterpret_cast<const uint32_t*>(tbl + ld_ro32(&h->off_off1)) + k0);
     const uint32_t k1 = rand_below(draw(1), n1);
-    const uint32_t c1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + ld_ro32(&h->off_second)) + o1 + k1);
+    const uint32_t c1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + p.tbl_off_second) + off1 + k1);
     st.occ = st.occ | ship_cells(p, 1, (int)(c1 >> 2), (int)(c1 & 3u), p.max_len - 1);
     st.remaining += p.max_len - 1;
     return battleship_place_from(p, draw, 2, st.occ, st.remaining);

@@ -267,13 +267,9 @@ inline int make_ship(const PomdpBattleshipParams* q, ShipDev* d) {
     return 0;
 }
 
-// The placement tables of BattleShip reset (layout: pomdp_core.h, ShipTableHdr).  With tbl == nullptr only the size is
-// computed.  Returns the table's size in bytes (a multiple of 16) or a negative error code.
-inline int64_t make_ship_table(const PomdpBattleshipParams* q, void* tbl) {
-    ShipDev d;
-    const int rc = make_ship(q, &d);
-    if (rc) return rc < 0 ? rc : -rc;
-    if (q->max_len - 1 > SHIP_MAX_SHIPS) return fail(POMDP_E_BADARG, "battleship: more than %d ships", SHIP_MAX_SHIPS);
+// The placement tables of BattleShip reset (layout: pomdp_core.h, ShipTableHdr).  With tbl == nullptr only the header
+// is computed.  Returns the table's size in bytes (a multiple of 16) or a negative error code.
+inline int64_t make_ship_table_from(const ShipDev& d, ShipTableHdr* hdr_out, void* tbl) {
     auto list_of = [&](const B128 valid[4], uint16_t* out) {     // accepted candidates in increasing c = 4 * pos + dir
         int n = 0;
         for (int pos = 0; pos < d.n_tiles; ++pos)
@@ -295,31 +291,51 @@ inline int64_t make_ship_table(const PomdpBattleshipParams* q, void* tbl) {
         }
     auto up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
     ShipTableHdr h;
+    memset(&h, 0, sizeof(h));
     h.magic = SHIP_TABLE_MAGIC; h.n0 = (uint32_t)n0; h.n_tabled = two ? 2u : 1u;
-    h.off_first = (uint32_t)sizeof(ShipTableHdr);
-    h.off_cnt1 = (uint32_t)up16(h.off_first + 2 * (int64_t)n0);
-    h.off_off1 = (uint32_t)up16(h.off_cnt1 + 2 * (int64_t)n0);
-    h.off_second = (uint32_t)up16(h.off_off1 + 4 * (int64_t)n0);
+    h.off_rec = (uint32_t)sizeof(ShipTableHdr);
+    h.off_second = (uint32_t)up16(h.off_rec + (int64_t)sizeof(ShipRec) * n0);
     h.bytes = (uint32_t)up16(h.off_second + 2 * n_second);
+    if (hdr_out) *hdr_out = h;
     if (!tbl) return (int64_t)h.bytes;
     memset(tbl, 0, h.bytes);
     memcpy(tbl, &h, sizeof(h));
-    uint16_t* t_first = (uint16_t*)((char*)tbl + h.off_first);
-    uint16_t* t_cnt1 = (uint16_t*)((char*)tbl + h.off_cnt1);
-    uint32_t* t_off1 = (uint32_t*)((char*)tbl + h.off_off1);
+    ShipRec* rec = (ShipRec*)((char*)tbl + h.off_rec);
     uint16_t* t_second = (uint16_t*)((char*)tbl + h.off_second);
-    memcpy(t_first, first, 2 * (size_t)n0);
     uint32_t off = 0;
-    if (two)
-        for (int k0 = 0; k0 < n0; ++k0) {
-            B128 v1[4];
-            ship_valid_starts(d, ship_blocked_b(d, ship_cells(d, 0, first[k0] >> 2, first[k0] & 3, d.max_len)), 1, d.max_len - 1, v1);
-            const int n1 = list_of(v1, t_second + off);
-            t_cnt1[k0] = (uint16_t)n1;
-            t_off1[k0] = off;
-            off += (uint32_t)n1;
-        }
+    for (int k0 = 0; k0 < n0; ++k0) {
+        rec[k0].c0 = first[k0]; rec[k0].n1 = 0; rec[k0].off1 = off;
+        if (!two) continue;
+        B128 v1[4];
+        ship_valid_starts(d, ship_blocked_b(d, ship_cells(d, 0, first[k0] >> 2, first[k0] & 3, d.max_len)), 1, d.max_len - 1, v1);
+        const int n1 = list_of(v1, t_second + off);
+        rec[k0].n1 = (uint16_t)n1;
+        off += (uint32_t)n1;
+    }
     return (int64_t)h.bytes;
+}
+
+// make_ship + the table layout fields of ShipDev (the enumeration takes ~50 us, so the last configuration is cached
+// per thread: reset is called with the same params over and over)
+inline int make_ship_tabled(const PomdpBattleshipParams* q, ShipDev* d) {
+    int rc = make_ship(q, d);
+    if (rc) return rc;
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return fail(POMDP_E_BADARG, "battleship: more than %d ships", SHIP_MAX_SHIPS);
+    static thread_local PomdpBattleshipParams cached_q = {0, 0, 0, 0};
+    static thread_local ShipTableHdr cached_h;
+    if (cached_q.x_size != q->x_size || cached_q.y_size != q->y_size || cached_q.max_len != q->max_len) {
+        make_ship_table_from(*d, &cached_h, nullptr);
+        cached_q = *q;
+    }
+    d->tbl_n0 = cached_h.n0; d->tbl_n_tabled = cached_h.n_tabled; d->tbl_off_rec = cached_h.off_rec; d->tbl_off_second = cached_h.off_second;
+    return 0;
+}
+inline int64_t make_ship_table(const PomdpBattleshipParams* q, void* tbl) {
+    ShipDev d;
+    const int rc = make_ship(q, &d);
+    if (rc) return rc < 0 ? rc : -rc;
+    if (q->max_len - 1 > SHIP_MAX_SHIPS) return fail(POMDP_E_BADARG, "battleship: more than %d ships", SHIP_MAX_SHIPS);
+    return make_ship_table_from(d, nullptr, tbl);
 }
 
 // pomdp_step_packed_host: the pipe, the kind, the state width the pipe was made for and the host pointers

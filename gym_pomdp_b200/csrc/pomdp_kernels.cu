@@ -251,7 +251,10 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
 // ---------------------------------------------------------------- reset (streams) ---
 // kVec (state 16-byte aligned, global_offset % 4 == 0): four envs per thread, one Philox call
 // per draw slot per group, vector stores when the whole group is reset.
-template <class Env, bool kVec>
+// kFast: the common call -- no mask, obs present and 16-byte aligned: the loop body is reset4 + two 16-byte streaming
+// stores and nothing else (the masked variant carries four byte loads and per-element predicates through the loop,
+// which costs more issue slots than the Philox call itself in a kernel that only writes 8 bytes per env).
+template <class Env, bool kVec, bool kFast = false>
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __restrict__ state,
                    int32_t* __restrict__ obs, const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
@@ -260,7 +263,18 @@ pomdp_reset_kernel(const __grid_constant__ typename Env::Params p, int32_t* __re
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     int64_t scalar_from = 0;
-    if (kVec) {
+    if (kVec && kFast) {
+        const int64_t n_groups = n >> 2;
+        const uint64_t group0 = goff >> 2;
+        for (int64_t g = tid; g < n_groups; g += nthreads) {
+            S s[4];
+            int32_t ob[4];
+            Env::reset4(p, seed, group0 + (uint64_t)g, step_ctr, s, ob);
+            StateVec<S>::store(state, g << 2, s);
+            st_stream4(obs + (g << 2), make_int4(ob[0], ob[1], ob[2], ob[3]));
+        }
+        scalar_from = n_groups << 2;
+    } else if (kVec) {
         const int64_t n_groups = n >> 2;
         const bool obs_vec = obs && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
         for (int64_t g = tid; g < n_groups; g += nthreads) {
@@ -1088,7 +1102,11 @@ int launch_reset(const typename Env::Params& p, int32_t* state, int32_t* obs, co
     if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "%s: bad n or NULL state", what);
     if (n == 0) return 0;
     if (goff < 0) return host::fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
-    if ((((uintptr_t)state) & 15) == 0 && (goff & 3) == 0) {
+    if ((((uintptr_t)state) & 15) == 0 && (goff & 3) == 0 && !mask && obs && (((uintptr_t)obs) & 15) == 0) {
+        auto k = pomdp_reset_kernel<Env, true, true>;
+        const int grid = grid_for(k, (n + 3) >> 2);
+        k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
+    } else if ((((uintptr_t)state) & 15) == 0 && (goff & 3) == 0) {
         auto k = pomdp_reset_kernel<Env, true>;
         const int grid = grid_for(k, (n + 3) >> 2);
         k<<<grid, POMDP_THREADS, 0, (cudaStream_t)stream>>>(p, state, obs, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
@@ -1333,7 +1351,7 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* d_table, 
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
                            void* stream) {
     ShipDev d;
-    int rc = host::make_ship(q, &d);
+    int rc = d_table ? host::make_ship_tabled(q, &d) : host::make_ship(q, &d);
     if (rc) return rc;
     if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
     if (n < 0 || (n > 0 && !state)) return host::fail(POMDP_E_BADARG, "pomdp_battleship_reset: bad n or NULL state");

@@ -174,9 +174,9 @@ int pomdp_battleship_step(const PomdpBattleshipParams* params,
  *                                   built with shifts (bitboard scan)
  *   pomdp_battleship_reset_warpscan one WARP per env, lanes test candidates, ballots count them
  * All produce identical boards.                                                               */
-/* Placement tables (host-built, caller-owned, like Rock's): the accepted candidate list of ship 0 and,
- * per ship-0 placement, the accepted list of ship 1 (~140 KB for 10x10 / max_len 3).  Fill a
- * host buffer of pomdp_battleship_table_bytes() and upload it (16-byte aligned).              */
+/* Placement tables (host-built, caller-owned, like Rock's): per accepted placement of ship 0 an 8-byte
+ * record {candidate, count and offset of ship 1's accepted list}, then those lists (~140 KB for 10x10 /
+ * max_len 3).  Fill a host buffer of pomdp_battleship_table_bytes() and upload it (16-byte aligned).   */
 int64_t pomdp_battleship_table_bytes(const PomdpBattleshipParams* params);
 int     pomdp_battleship_build_table(const PomdpBattleshipParams* params, void* host_table);
 int pomdp_battleship_reset(const PomdpBattleshipParams* params, const void* d_table,

@@ -309,7 +309,7 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* table, in
                            const uint8_t* mask, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
     ShipDev d;
     const PhiloxKey key = philox_key(seed);
-    int rc = host::make_ship(q, &d);
+    int rc = table ? host::make_ship_tabled(q, &d) : host::make_ship(q, &d);
     if (rc) return rc;
     if (q->max_len - 1 > SHIP_MAX_SHIPS) return host::fail(POMDP_E_BADARG, "battleship: more than 8 ships");
     if ((uintptr_t)table & 15) return host::fail(POMDP_E_ALIGN, "pomdp_battleship_reset: d_table must be 16-byte aligned");
@@ -721,6 +721,27 @@ void pomdp_hostsim_rock_reset_codes16(const uint32_t* w, uint32_t* fast, uint32_
         for (int r = 0; r < 16; ++r) c |= rock_status_code(rock_reset_word(w[i], r)) << (2 * r);
         per_rock[i] = c;
     }
+}
+
+// test-only: the four-env reset path of the vector kernel (shift + LOP3 per env, ties out of line) on explicit draw
+// words, next to the per-env definition -- the kernels can only be fed Philox words, which never tie
+int pomdp_hostsim_rock_reset4(const PomdpRockParams* q, const uint32_t* words, uint64_t* fast, uint64_t* slow, int64_t n_groups) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    for (int64_t g = 0; g < n_groups; ++g) {
+        const U4 w = {words[4 * g], words[4 * g + 1], words[4 * g + 2], words[4 * g + 3]};
+        if (host::rock_words(q) == 1) {
+            uint32_t o[4];
+            rock_reset4_words<uint32_t>(d, w, o);
+            for (int j = 0; j < 4; ++j) { fast[4 * g + j] = o[j]; slow[4 * g + j] = rock_reset_from_word<uint32_t>(d, words[4 * g + j]); }
+        } else {
+            uint64_t o[4];
+            rock_reset4_words<uint64_t>(d, w, o);
+            for (int j = 0; j < 4; ++j) { fast[4 * g + j] = o[j]; slow[4 * g + j] = rock_reset_from_word<uint64_t>(d, words[4 * g + j]); }
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

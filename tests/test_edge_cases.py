@@ -393,6 +393,14 @@ def test_rock_reset_codes_one_lop3_equals_per_rock_definition():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     lib.pomdp_hostsim_rock_reset_codes16(p(w), p(fast), p(slow), ctypes.c_int64(w.size))
     assert np.array_equal(fast, slow)
+    # the vector kernel's four-env form (one shift + one LOP3 per env, ties handled out of line) on the same words
+    from gym_pomdp_b200 import _lib as L_
+    for board, k in [(7, 8), (11, 11), (15, 15)]:
+        q = L_.RockParams(board, k, 0, 0, 0.8)
+        ww = np.ascontiguousarray(w[: (w.size // 4) * 4])
+        f4, s4 = np.empty(ww.size, np.uint64), np.empty(ww.size, np.uint64)
+        assert lib.pomdp_hostsim_rock_reset4(ctypes.byref(q), p(ww), p(f4), p(s4), ctypes.c_int64(ww.size // 4)) == 0
+        assert np.array_equal(f4, s4), (board, k)
     cfg = O.RockCfg(15, 15)
     for i in range(len(special)):
         _, _, status, _ = O.rock_reset(cfg, lambda s, i=i: int(w[i]))
