@@ -607,18 +607,7 @@ struct NetworkDev {
     int32_t all_T_nonzero;           // every T above is in 1..2^32: the 32-bit compares are exact
     double p_ob;
     uint32_t nb[NETWORK_MAX + 2];    // neighbour bit masks (network.py:144-168)
-    uint64_t cp, cq;                 // 2^32 - p_T, 2^32 - q_T (< 2^32): hi32(r * 1 + c) = [r >= T] (the multiply-add pipe compares)
-    uint32_t one_p, one_q;           // 1 and 1, as two runtime values: keeps each r * one + c ONE IMAD.WIDE (a shared product
-                                     // would be followed by add-with-carry pairs on the logic pipe)
-    int32_t q_ge_p;                  // q_T >= p_T (a failed neighbour never makes a machine safer): the two-compare form is valid
-    // "some neighbour of machine i is down" for all machines at once: the edges i -> j grouped by j - i; class k
-    // contributes (down >> shr[k]) & mask[k] (j > i) or (down << shl[k]) & mask[k] (j < i).  Both topologies of
-    // network.py:144-168 need at most 7 classes (ring: 4; 3-legs: +1 +2 +3 -1 -2 -3 -4).
-    int32_t n_cls;                   // 0: not representable in NETWORK_MAX_CLS classes -> per-machine tests
-    uint8_t cls_shr[8], cls_shl[8];
-    uint32_t cls_mask[8];
 };
-constexpr int NETWORK_MAX_CLS = 8;
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
 
 
@@ -640,35 +629,6 @@ POMDP_HD float tenths_to_float(int t) {
 // machine that is down clears a bit that is already clear, so the loop needs no "is up" test.
 // The thresholds are compared as r <= T - 1 in 32 bits; a configuration with a probability of
 // exactly 0 (T = 0, nothing ever fires) takes the 64-bit compare instead (uniform per launch).
-// tuning knobs of the vector kernel's Network path (scripts/exp_network_variants.sh)
-#ifndef POMDP_NET_FMA
-#define POMDP_NET_FMA 1
-#endif
-#ifndef POMDP_NET_UNROLL
-#define POMDP_NET_UNROLL 1
-#endif
-#define POMDP_STR2(x) #x
-#define POMDP_STR(x) POMDP_STR2(x)
-#if defined(__CUDACC__)
-#define POMDP_NET_UNROLL_PRAGMA _Pragma(POMDP_STR(unroll POMDP_NET_UNROLL))
-#else
-#define POMDP_NET_UNROLL_PRAGMA
-#endif
-#if defined(__CUDA_ARCH__)
-// [r >= T] for c = 2^32 - T as the carry of r * one + c, on the multiply-add pipe (IMAD.WIDE): the logic pipe, which
-// the Philox rounds already keep busy with their LOP3s, does none of the failure decisions.
-__device__ __forceinline__ uint32_t ge_carry(uint32_t r, uint32_t one, uint64_t c) {
-    uint64_t v;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(v) : "r"(r), "r"(one), "l"(c));
-    return (uint32_t)(v >> 32);
-}
-__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t v;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(b), "r"(c));
-    return v;
-}
-#endif
-
 template <int L>
 POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], const PhiloxKey& seed,
                              uint64_t group, int lane0, uint32_t step,
@@ -681,51 +641,6 @@ POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int
         nw[j] = s[j];
         down[j] = ~s[j] & all;
     }
-#if defined(__CUDA_ARCH__)
-    if (POMDP_NET_FMA && L == 4 && p.all_T_nonzero && p.q_ge_p) {
-        // The vector kernel's form of network.py:94-99.  Machine m survives its draw r iff r >= T_sel, T_sel = q_T when a
-        // neighbour is down, else p_T.  With q_T >= p_T that is  [r >= p_T] & ([r >= q_T] | no neighbour down): both
-        // compares are carries of IMAD.WIDE and their bits are gathered per env with one IMAD each (bit m of SA / SB),
-        // so per machine and env the multiply-add pipe issues four instructions and the logic pipe none; the
-        // neighbour-down masks are formed once per env, two logic instructions per edge class.
-        uint32_t SA[L], SB[L], ND[L];
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) { SA[j] = 0u; SB[j] = 0u; ND[j] = 0u; }
-        if (p.n_cls > 0) {
-            for (int k = 0; k < p.n_cls; ++k) {
-                const uint32_t shr_ = p.cls_shr[k], shl_ = p.cls_shl[k], msk = p.cls_mask[k];
-                POMDP_UNROLL
-                for (int j = 0; j < L; ++j) ND[j] |= ((down[j] >> shr_) << shl_) & msk;
-            }
-        } else {
-            for (int m = 0; m < p.n; ++m) {
-                const uint32_t nbm = p.nb[m];
-                POMDP_UNROLL
-                for (int j = 0; j < L; ++j) ND[j] |= (nbm & down[j]) ? (1u << m) : 0u;
-            }
-        }
-        const uint32_t one_p = p.one_p, one_q = p.one_q;
-        uint64_t cp, cq;                                                          // in vector registers, opaque to ptxas: an addend
-        asm volatile("mov.b64 %0, %1;" : "=l"(cp) : "l"(p.cp));                   // it can see through (constant bank, zero high
-        asm volatile("mov.b64 %0, %1;" : "=l"(cq) : "l"(p.cq));                   // word) is split off into IADD3 + IMAD.X again
-        POMDP_NET_UNROLL_PRAGMA
-        for (int m = 0; m < p.n; ++m) {                                           // network.py:94-99
-            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
-            const uint32_t bit = 1u << m;
-            POMDP_UNROLL
-            for (int j = 0; j < L; ++j) {
-                const uint32_t w = word_of(q, j);
-                SA[j] = mad_lo(ge_carry(w, one_p, cp), bit, SA[j]);
-                SB[j] = mad_lo(ge_carry(w, one_q, cq), bit, SB[j]);
-            }
-        }
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) nw[j] = s[j] & SA[j] & (SB[j] | ~ND[j]);
-        const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) hit[j] = word_of(qa, j) <= p.om1;
-    } else
-#endif
     if (p.all_T_nonzero) {
         const uint32_t pm1 = p.pm1, qm1 = p.qm1;
         for (int m = 0; m < p.n; ++m) {                                           // network.py:94-99

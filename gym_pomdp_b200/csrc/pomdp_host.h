@@ -217,10 +217,6 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     d->p_ob = q->p_ob;
     d->pm1 = (uint32_t)(d->p_T - 1); d->qm1 = (uint32_t)(d->q_T - 1); d->om1 = (uint32_t)(d->ob_T - 1);
     d->all_T_nonzero = d->p_T != 0 && d->q_T != 0 && d->ob_T != 0;
-    d->cp = (1ull << 32) - d->p_T;      // T in 1..2^32 -> c in 0..2^32-1 (only used when all_T_nonzero)
-    d->cq = (1ull << 32) - d->q_T;
-    d->one_p = 1u; d->one_q = 1u;
-    d->q_ge_p = d->q_T >= d->p_T;
     int deg[NETWORK_MAX] = {0};
     auto link = [&](int i, int j) { d->nb[i] |= 1u << j; ++deg[i]; };
     if (q->problem_type == 3) {                     // network.py:153-168
@@ -235,24 +231,6 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     }
     for (int i = 0; i < n; ++i)
         if (deg[i] > 2) d->deg3 |= 1u << i;         // len(neighbours) counts duplicates too (network.py:89)
-    // edge classes by j - i for the all-machines-at-once neighbour-down mask (pomdp_core.h: NetworkDev)
-    int n_cls = 0;
-    bool fits = true;
-    for (int delta = -(n - 1); delta <= n - 1 && fits; ++delta) {
-        if (delta == 0) continue;
-        uint32_t mask = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = i + delta;
-            if (j >= 0 && j < n && (d->nb[i] >> j & 1u)) mask |= 1u << i;
-        }
-        if (!mask) continue;
-        if (n_cls == NETWORK_MAX_CLS) { fits = false; break; }
-        d->cls_shr[n_cls] = (uint8_t)(delta > 0 ? delta : 0);
-        d->cls_shl[n_cls] = (uint8_t)(delta < 0 ? -delta : 0);
-        d->cls_mask[n_cls] = mask;
-        ++n_cls;
-    }
-    d->n_cls = fits ? n_cls : 0;
     return 0;
 }
 

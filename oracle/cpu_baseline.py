@@ -1,5 +1,6 @@
-"""CPU baseline leg of bench.py: the oracle's pure-Python RockSample step() loop timed on
-host cores.
+"""CPU baseline leg of bench.py: the reference's own pure-Python RockSample step() loop (when its package is
+reachable: /root/reference in the build container, oracle/_ref on the GPU box -- ``make -C oracle _ref``), else the
+oracle's Python port of it, timed on host cores.
 
 TEST/BENCH INFRASTRUCTURE ONLY -- imported by bench.py's ``cpu_baseline`` leg and by
 ``bench.py --impl reference``; never by gym_pomdp_b200/.
@@ -150,3 +151,98 @@ def time_rock_c(n, k, count=1 << 20, reps=8, procs=None, seed=0x5EED):
     return {"value": total / slowest, "unit": "env-steps/s", "cores": procs, "kind": "port",
             "sample": "%d procs x %d reps x %d RockSample(%d,%d) pairs through oracle/pomdp_oracle.c (oracle_rock_step)"
                       % (procs, reps, count, n, k)}
+
+
+# ---- the UNMODIFIED reference: RockEnv._set_state + RockEnv.step (rock.py:243-245, 123-194) ----------------------
+def _ref_states(E, n, k, count, seed):
+    """The benchmark's synthetic (state, action) sample as the reference's own state dicts (rock.py:507-516)."""
+    from gym_pomdp.envs.coord import Coord
+    from gym_pomdp.envs.rock import config
+    rock_pos = config[n]["rock_pos"]
+    x, y, status, action, _ = rock_workload(n, k, count, seed)
+    states = [{"agent_pos": (int(x[i]), int(y[i])), "target": -1,
+               "rocks": [{"status": int(s), "pos": Coord(*rock_pos[j]), "count": 0, "measured": 0, "lkw": 1., "lkv": 1.,
+                          "prob_valuable": .5} for j, s in enumerate(status[i])]} for i in range(count)]
+    return states, action.tolist()
+
+
+def _ref_pass(env, states, acts):
+    """One pass of the planner pattern over the sample: env._set_state(s); env.step(a)."""
+    set_state, step = env._set_state, env.step
+    acc = 0
+    t0 = time.perf_counter()
+    for s, a in zip(states, acts):
+        set_state(s)
+        try:
+            acc += step(a)[1]
+        except IndexError:                       # Rock(15,15)'s dangling grid id at (12,2), rock.py:162
+            pass
+    return time.perf_counter() - t0, acc
+
+
+def _ref_loop(args):
+    n, k, count, seed = args
+    from . import ref_shim
+    E = ref_shim.load_reference()
+    env = E.RockEnv(board_size=n, num_rocks=k)
+    np.random.seed(seed & 0x7FFFFFFF)
+    states, acts = _ref_states(E, n, k, count, seed)
+    dt, acc = _ref_pass(env, states, acts)
+    return count, dt, acc
+
+
+def reference_available():
+    from . import ref_shim
+    return ref_shim.reference_available()
+
+
+def time_rock_reference(n, k, steps_per_proc, procs=None, seed=0x5EED):
+    """The reference's own RockEnv driven through ``_set_state`` + ``step`` on ``procs`` worker processes, each over
+    its own sample of ``steps_per_proc`` (state, action) pairs, numpy's own RNG (unscripted).  kind = "reference"."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(n, k, steps_per_proc, seed + 7919 * p) for p in range(procs)]
+    if procs == 1:
+        res = [_ref_loop(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_ref_loop, jobs)
+    total, slowest = sum(r[0] for r in res), max(r[1] for r in res)
+    return {"value": total / slowest, "unit": "env-steps/s", "cores": procs, "kind": "reference",
+            "sample": "%d procs x %d RockSample(%d,%d) (state, action) pairs through the unmodified reference: "
+                      "RockEnv._set_state(s); RockEnv.step(a) (rock.py:243-245, 123-194), numpy RNG"
+                      % (procs, steps_per_proc, n, k),
+            "loop_seconds": slowest, "steps": total}
+
+
+def _ref_arm_init(n, k, count, seed_base):
+    from . import ref_shim
+    ident = mp.current_process()._identity
+    rank = ident[0] if ident else 0
+    E = ref_shim.load_reference()
+    np.random.seed((seed_base + 7919 * rank) & 0x7FFFFFFF)
+    states, acts = _ref_states(E, n, k, count, seed_base + 7919 * rank)
+    _W.update(env=E.RockEnv(board_size=n, num_rocks=k), states=states, acts=acts)
+
+
+def _ref_arm_step(_):
+    return _ref_pass(_W["env"], _W["states"], _W["acts"])
+
+
+class RockReferenceArm(object):
+    """``bench.py --impl reference``: every host core runs the unmodified reference over its own fixed sample of
+    ``count`` (state, action) pairs per step()."""
+    kind = "reference"
+
+    def __init__(self, n, k, count, procs=None, seed=0x5EED):
+        self.procs = procs or os.cpu_count() or 1
+        self.count = count
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_ref_arm_init, initargs=(n, k, count, seed))
+
+    def step(self):
+        t0 = time.perf_counter()
+        self.pool.map(_ref_arm_step, range(self.procs), chunksize=1)
+        return self.procs * self.count, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

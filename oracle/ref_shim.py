@@ -140,17 +140,29 @@ def _install_stubs():
     sys.modules["pygame"] = pygame
 
 
+def reference_root():
+    """Where the unmodified reference package lies: /root/reference in the build container, else the copy that
+    ``make -C oracle _ref`` put under oracle/_ref/ (git-ignored; it travels to the GPU box with the snapshot)."""
+    import os
+    for root in (REFERENCE_ROOT, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")):
+        if os.path.isdir(os.path.join(root, "gym_pomdp", "envs")):
+            return root
+    return None
+
+
 def load_reference():
     """Returns the reference's ``gym_pomdp.envs`` package (imported, not copied)."""
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise ImportError("the reference is neither at %s nor under oracle/_ref (make -C oracle _ref)" % REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     return importlib.import_module("gym_pomdp.envs")
 
 
 def reference_available():
-    import os
-    return os.path.isdir(REFERENCE_ROOT + "/gym_pomdp")
+    return reference_root() is not None
 
 
 @contextlib.contextmanager

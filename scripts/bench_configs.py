@@ -109,22 +109,41 @@ CONFIGS = [
 ]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--out", default=None)
-    ap.add_argument("--only", default=None, help="substring filter on the label")
-    ap.add_argument("--no-rollout", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="few launches per kernel (for runs under ncu)")
-    args = ap.parse_args()
-    global QUICK
-    QUICK = args.quick
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+def issue_roofline(label, kernel, B, ms, sm_mhz=1965.0, sms=148):
+    """For the kernels that are bound by instruction issue, not by HBM (Network's step: one Philox call per machine):
+    warp instructions per launch from the committed ncu capture (profiles/issue_counts.json, keyed by config/kernel,
+    counted at the batch size given there and scaled linearly) against the SMs' issue capacity -- one warp instruction
+    per cycle per scheduler for the whole kernel, one per two cycles for each of the logic (ALU) and multiply-add
+    (FMA) pipes."""
+    try:
+        counts = json.load(open(os.path.join(ROOT, "profiles", "issue_counts.json")))
+    except Exception:  # noqa: BLE001
+        return None
+    for c in counts.get("kernels", []):
+        if c["config"] in label and c["kernel"] == kernel:
+            scale = B / float(c["batch"])
+            cycles = ms * 1e-3 * sm_mhz * 1e6 * sms * 4              # scheduler-cycles available during the launch
+            inst, alu, fma = c["inst_executed"] * scale, c["pipe_alu"] * scale, c["pipe_fma"] * scale
+            return {"bound": "int-issue", "unit": "warp-inst/s", "achieved": inst / (ms * 1e-3),
+                    "peak": sm_mhz * 1e6 * sms * 4, "frac": inst / cycles,
+                    "alu_pipe_frac": 2 * alu / cycles, "fma_pipe_frac": 2 * fma / cycles,
+                    "warp_inst_per_env_step": inst / B, "alu_inst_per_env_step": alu / B, "fma_inst_per_env_step": fma / B,
+                    "sm_mhz_assumed": sm_mhz, "source": counts.get("source")}
+    return None
+
+
+def run_configs(dev, steps=400, only=None, kernels=("step", "step_packed", "reset", "belief_hist", "rollout"), configs=None,
+                emit=None):
+    """Times the named kernels of every configuration (or those whose label contains ``only``); returns the rows."""
     peak, peak_src = peak_gbs()
     rows = []
-    for name, env_id, kw, lg, label in CONFIGS:
-        if args.only and args.only not in label:
+
+    def add(row):
+        rows.append(row)
+        if emit:
+            emit(row)
+    for name, env_id, kw, lg, label in (configs or CONFIGS):
+        if only and only not in label:
             continue
         B = 1 << lg
         env = gp.make(env_id, batch_size=B, device=dev, seed=0x5EED, **kw)
@@ -139,19 +158,23 @@ def main():
             out = (torch.empty_like(s), torch.empty(B, dtype=torch.int32, device=dev),
                    torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.int32, device=dev))
             sets.append((s, a, out))
-        K = max(20, min(args.steps, int(args.steps * (1 << 22) / B)))
+        K = max(20, min(steps, int(steps * (1 << 22) / B)))
 
-        def step(i):
-            s, a, o = sets[i % n_sets]
-            env.simulate(s, a, out=o, step_ctr=i + 1)
-        ms = time_graph(step, K, dev)
-        gbs = B * step_bytes / (ms * 1e-3) / 1e9
-        rows.append({"config": label, "kernel": "step", "batch": B, "state_words": W, "bytes_per_unit": step_bytes,
-                     "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
-                     "launches": K, "buffer_sets": n_sets})
-        print(json.dumps(rows[-1]), flush=True)
+        if "step" in kernels:
+            def step(i):
+                s, a, o = sets[i % n_sets]
+                env.simulate(s, a, out=o, step_ctr=i + 1)
+            ms = time_graph(step, K, dev)
+            gbs = B * step_bytes / (ms * 1e-3) / 1e9
+            row = {"config": label, "kernel": "step", "batch": B, "state_words": W, "bytes_per_unit": step_bytes,
+                   "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+                   "launches": K, "buffer_sets": n_sets}
+            ir = issue_roofline(label, "step", B, ms)
+            if ir:
+                row["issue_roofline"] = ir
+            add(row)
 
-        if name != "battleship":
+        if "step_packed" in kernels and name != "battleship":
             psets = [(torch.empty_like(sets[0][0]), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
 
             def step_packed(i):
@@ -160,36 +183,35 @@ def main():
             ms = time_graph(step_packed, K, dev)
             pb = 8 * W + 8
             gbs = B * pb / (ms * 1e-3) / 1e9
-            rows.append({"config": label, "kernel": "step_packed", "batch": B, "state_words": W, "bytes_per_unit": pb,
-                         "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
-                         "note": "obs|flags|reward in one int32 stream: 8W+8 bytes per env-step"})
-            print(json.dumps(rows[-1]), flush=True)
+            add({"config": label, "kernel": "step_packed", "batch": B, "state_words": W, "bytes_per_unit": pb,
+                 "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+                 "note": "obs|flags|reward in one int32 stream: 8W+8 bytes per env-step"})
             del psets
 
-        # reset: bytes written = state words + obs (+ flags for BattleShip)
-        reset_bytes = 4 * W + 4 + (4 if name == "battleship" else 0)
-        rsets = [(torch.empty_like(sets[0][0]), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
+        if "reset" in kernels:
+            # reset: bytes written = state words + obs (+ flags for BattleShip)
+            reset_bytes = 4 * W + 4 + (4 if name == "battleship" else 0)
+            rsets = [(torch.empty_like(sets[0][0]), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
 
-        def reset(i):
-            env.init_states(B, out=rsets[i % n_sets], step_ctr=i + 1)
-        ms = time_graph(reset, max(20, K // 4), dev)
-        gbs = B * reset_bytes / (ms * 1e-3) / 1e9
-        rows.append({"config": label, "kernel": "reset", "batch": B, "state_words": W, "bytes_per_unit": reset_bytes,
-                     "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak})
-        print(json.dumps(rows[-1]), flush=True)
+            def reset(i):
+                env.init_states(B, out=rsets[i % n_sets], step_ctr=i + 1)
+            ms = time_graph(reset, max(20, K // 4), dev)
+            gbs = B * reset_bytes / (ms * 1e-3) / 1e9
+            add({"config": label, "kernel": "reset", "batch": B, "state_words": W, "bytes_per_unit": reset_bytes,
+                 "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak})
+            del rsets
 
-        # belief histogram: reads the state words
-        hist_bytes = 4 * W
+        if "belief_hist" in kernels:
+            hist_bytes = 4 * W
 
-        def hist(i):
-            env.belief_histogram(sets[i % n_sets][0])
-        ms = time_graph(hist, max(20, K // 4), dev)
-        gbs = B * hist_bytes / (ms * 1e-3) / 1e9
-        rows.append({"config": label, "kernel": "belief_hist", "batch": B, "bytes_per_unit": hist_bytes,
-                     "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak})
-        print(json.dumps(rows[-1]), flush=True)
+            def hist(i):
+                env.belief_histogram(sets[i % n_sets][0])
+            ms = time_graph(hist, max(20, K // 4), dev)
+            gbs = B * hist_bytes / (ms * 1e-3) / 1e9
+            add({"config": label, "kernel": "belief_hist", "batch": B, "bytes_per_unit": hist_bytes,
+                 "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_peak": gbs / peak})
         # fused uniform-legal rollout: states stay in registers for T steps
-        if not args.no_rollout:
+        if "rollout" in kernels:
             T = 32
             s0 = sets[0][0]
             ro = (torch.empty_like(s0), torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
@@ -206,14 +228,30 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             nsteps = int(ro[2].sum().item())
-            rows.append({"config": label, "kernel": "rollout(T=%d)" % T, "batch": B, "env_steps_per_launch": nsteps,
-                         "us_per_launch": ms * 1e3, "units_per_s": nsteps / (ms * 1e-3),
-                         "bytes_per_unit": (8 * W + 16) * B / max(nsteps, 1), "achieved_gbs": B * (8 * W + 16) / (ms * 1e-3) / 1e9,
-                         "frac_of_peak": B * (8 * W + 16) / (ms * 1e-3) / 1e9 / peak,
-                         "note": "compute-bound (Philox + transition logic in registers); units = env-steps actually taken"})
-            print(json.dumps(rows[-1]), flush=True)
-        del sets, rsets, env
+            add({"config": label, "kernel": "rollout(T=%d)" % T, "batch": B, "env_steps_per_launch": nsteps,
+                 "us_per_launch": ms * 1e3, "units_per_s": nsteps / (ms * 1e-3),
+                 "bytes_per_unit": (8 * W + 16) * B / max(nsteps, 1), "achieved_gbs": B * (8 * W + 16) / (ms * 1e-3) / 1e9,
+                 "frac_of_peak": B * (8 * W + 16) / (ms * 1e-3) / 1e9 / peak,
+                 "note": "compute-bound (Philox + transition logic in registers); units = env-steps actually taken"})
+        del sets, env
         torch.cuda.empty_cache()
+    return rows, peak, peak_src
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="substring filter on the label")
+    ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="few launches per kernel (for runs under ncu)")
+    args = ap.parse_args()
+    global QUICK
+    QUICK = args.quick
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    kernels = ("step", "step_packed", "reset", "belief_hist") + (() if args.no_rollout else ("rollout",))
+    rows, peak, peak_src = run_configs(dev, args.steps, args.only, kernels, emit=lambda r: print(json.dumps(r), flush=True))
     res = {"peak_gbs": peak, "peak_source": peak_src, "gpu": torch.cuda.get_device_name(0), "rows": rows}
     if args.out:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)

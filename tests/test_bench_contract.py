@@ -19,9 +19,19 @@ def test_reference_arm_runs_on_host_cores():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert BASE_KEYS <= set(line) and line["impl"] == "reference"
     assert line["metric"].startswith("env-steps/sec RockSample(11,11) batch=2^22") and line["unit"] == "env-steps/s"
-    assert line["value"] > 1e5 and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["value"] > 1e3 and line["higher_is_better"] is True and line["scaling"] == "weak"
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == line["value"] and "sample" in cb
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    # the unmodified reference's own step() loop wherever its package is reachable (/root/reference here, oracle/_ref on
+    # the GPU box), the oracle's port of it otherwise
+    if ref_shim.reference_available():
+        assert cb["kind"] == "reference" and "RockEnv._set_state" in cb["sample"]
+        assert cb["single_core"]["cores"] == 1 and cb["single_core"]["kind"] == "reference" and cb["single_core"]["value"] > 1e3
+        assert cb["python_port"]["kind"] == "port"
+    else:
+        assert cb["kind"] == "port"
+    assert cb["cores"] == os.cpu_count() and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("RockSample(11,11) step()")
 
