@@ -35,6 +35,12 @@ class RockParams(ctypes.Structure):
                 ("reserved", c_int32), ("p_move", c_double)]
 
 
+class RockHeuristicPlanes(ctypes.Structure):
+    """PomdpRockHeuristicPlanes: device pointers (0 = the fresh value / an empty history)"""
+    _fields_ = [("count", c_void_p), ("measured", c_void_p), ("lkv", c_void_p), ("lkw", c_void_p), ("prob_valuable", c_void_p),
+                ("check_totals", c_void_p), ("prev_obs", c_void_p)]
+
+
 class TagParams(ctypes.Structure):
     _fields_ = [("num_opponents", c_int32), ("reserved", c_int32), ("move_prob", c_double)]
 
@@ -114,6 +120,17 @@ _PROTOTYPES = {
     "pomdp_network_obs_prob": (c_int32, [POINTER(NetworkParams), _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_network_legal_mask": (c_int32, [POINTER(NetworkParams), _P, _P, c_int64, c_void_p]),
     "pomdp_rock_belief_update": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_history_update": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_preferred_mask": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_policy_preferred": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64,
+                                              c_uint32, c_void_p]),
+    "pomdp_rock_rollout_preferred": (c_int32, [POINTER(RockParams), _P, _P, _P, POINTER(RockHeuristicPlanes), _P, _P, _P, _P,
+                                               c_int64, c_int64, c_uint64, c_uint32, c_int32, c_double, c_int32, c_void_p]),
+    "pomdp_tag_preferred_mask": (c_int32, [POINTER(TagParams), _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_tag_policy_preferred": (c_int32, [POINTER(TagParams), _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32,
+                                             c_void_p]),
+    "pomdp_tag_rollout_preferred": (c_int32, [POINTER(TagParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64,
+                                              c_uint32, c_int32, c_double, c_void_p]),
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),

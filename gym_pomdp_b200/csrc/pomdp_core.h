@@ -368,6 +368,74 @@ POMDP_HD int32_t rock_policy(const RockDev& p, const RockTableHdr* __restrict__ 
     return (int32_t)hdr->legal_act[nth_set_bit(m, rand_below(w, (uint32_t)popc32(m)))];
 }
 
+// ---- heuristic action sets: RockEnv._generate_preferred(history), rock.py:293-374 ------
+// What the reference computes from the caller's History on every call -- two per-rock totals over the transitions
+// whose action checked that rock -- is kept as running sums, updated once per step (rock_history_update):
+//   tot_sample[i] = #(next_observation == GOOD) - #(next_observation == BAD)                       rock.py:302-309
+//   tot_dir[i]    = #(next_observation == GOOD) - #(next_observation != GOOD and observation == BAD) rock.py:325-331
+// (the second loop really reads `transition.observation` in its elif, rock.py:330).  The fields are taken as the
+// caller's transitions hold them: a caller that builds Transition(ob, action, next_ob, rw, done) positionally -- as the
+// reference's own loop does, rock.py:566 -- has the REWARD in `next_observation`; that is the caller's business and is
+// selected by `next_obs_field` below, not interpreted here.  The per-rock belief side-statistics (count, measured,
+// prob_valuable; rock.py:177-191) are the env's own state (rock_belief_update).
+// H provides tot_sample(i), tot_dir(i), count(i), measured(i), pv(i).
+// Returns a bit mask over ACTION ids -- the reference's lists are in increasing action order (NORTH 0, EAST 1, SOUTH 2,
+// WEST 3, then the checks 5 + i) -- or 0 when the list came out empty and the reference falls back to _generate_legal().
+template <typename S, class H>
+POMDP_HD uint32_t rock_preferred_mask(const RockDev& p, const RockTableHdr* __restrict__ hdr, S s, const H& h) {
+    s &= ~RockBits<S>::DONE;
+    const int x = (int)((uint32_t)s & 15u), y = (int)(((uint32_t)s >> 4) & 15u);
+    const int rock = hdr->grid[(uint32_t)s & 0xFFu];                                       // rock.py:300
+    // sample a rock whose checks came out good more often than bad (rock.py:301-311); a dangling grid id (Rock(15,15),
+    // Rock(7,7): the reference raises IndexError at rock.py:301) counts as no rock
+    if (rock >= 0 && rock < p.k && ((uint32_t)(s >> (8 + 2 * rock)) & 3u) != 0u && h.tot_sample(rock) > 0) return 1u << 4;
+    bool all_bad = true, north = false, south = false, west = false, east = false;
+    for (int i = 0; i < p.k; ++i) {                                                        // rock.py:322-343
+        if (((uint32_t)(s >> (8 + 2 * i)) & 3u) == 0u) continue;
+        if (h.tot_dir(i) >= 0) {
+            all_bad = false;
+            const int rx = hdr->rock_pos[i] & 15, ry = hdr->rock_pos[i] >> 4;
+            if (ry > y) north = true;
+            else if (ry < y) south = true;
+            else if (rx < x) west = true;
+            else if (rx > x) east = true;
+        }
+    }
+    if (all_bad) return 1u << 1;                                                           // rock.py:345-347: [EAST]
+    uint32_t m = 0;
+    if (y + 1 < p.n && north) m |= 1u << 0;                                                // rock.py:356-366
+    if (east) m |= 1u << 1;
+    if (y - 1 >= 0 && south) m |= 1u << 2;
+    if (x - 1 >= 0 && west) m |= 1u << 3;
+    for (int i = 0; i < p.k; ++i) {                                                        // rock.py:368-370
+        const double pv = h.pv(i);
+        const int c = h.count(i);
+        if (((uint32_t)(s >> (8 + 2 * i)) & 3u) != 0u && h.measured(i) < 5 && (c < 0 ? -c : c) < 2 && 0.0 < pv && pv < 1.0)
+            m |= 1u << (5 + i);
+    }
+    return m;                                                                              // 0: rock.py:372-373
+}
+// np.random.choice(env._generate_preferred(history)) from one draw word
+template <typename S, class H>
+POMDP_HD int32_t rock_policy_preferred(const RockDev& p, const RockTableHdr* __restrict__ hdr, const RockLut* __restrict__ lut, S s,
+                                       const H& h, uint32_t w) {
+    const uint32_t m = rock_preferred_mask<S>(p, hdr, s, h);
+    if (m == 0u) return rock_policy<S>(p, hdr, lut, s, w);
+    return (int32_t)nth_set_bit(m, rand_below(w, (uint32_t)popc32(m)));
+}
+// one transition (observation field, action, next_observation field) appended to the history: the checked rock's totals
+POMDP_HD void rock_history_update(int32_t a, int32_t obs_field, int32_t next_obs_field, int32_t& tot_sample, int32_t& tot_dir) {
+    tot_sample += (next_obs_field == 2) - (next_obs_field == 1);
+    tot_dir += next_obs_field == 2 ? 1 : (obs_field == 1 ? -1 : 0);
+    (void)a;
+}
+// the two totals of a rock share one int32 of the check_totals plane: low half tot_sample, high half tot_dir (both signed)
+POMDP_HD int32_t rock_totals_pack(int32_t tot_sample, int32_t tot_dir) {
+    return (int32_t)(((uint32_t)tot_sample & 0xFFFFu) | ((uint32_t)tot_dir << 16));
+}
+POMDP_HD int32_t rock_totals_sample(int32_t packed) { return (int32_t)(int16_t)(packed & 0xFFFF); }
+POMDP_HD int32_t rock_totals_dir(int32_t packed) { return packed >> 16; }
+
 // ============================================================================= Tag ===
 struct TagDev {
     int32_t n_opp;
@@ -556,6 +624,35 @@ POMDP_HD void tag_reset(const TagDev& p, const D& draw, uint32_t& s, int32_t& ob
         if (o == agent) ob = TAG_CELLS;
     }
     s = tag_set_num_opp(s, p.n_opp);
+}
+
+// TagGrid.is_corner, tag.py:68-74
+POMDP_HD bool tag_is_corner(int x, int y) {
+    if (!tag_is_inside(x, y)) return false;
+    return y < 2 ? (x == 0 || x == 9) : (y == 4 && (x == 5 || x == 7));
+}
+// TagEnv._generate_preferred(history), tag.py:231-243, as a bit mask over action ids (its lists are in increasing action
+// order).  last_action < 0 stands for an empty history (all five actions).  Otherwise: TAG alone when the last
+// observation was 29 (an opponent on the agent's cell) and the agent stands in a corner; else every move that stays on
+// the board and does not undo the last action.  0 (the reference's `assert len(actions) > 0`) cannot happen on this
+// board: every cell has at least two on-board neighbours.
+POMDP_HD uint32_t tag_preferred_mask(const TagTables* __restrict__ T, uint32_t s, int32_t last_ob, int32_t last_action) {
+    if (last_action < 0) return 31u;
+    const uint32_t agent = s & 31u;
+    int x, y;
+    tag_get_coord(agent < (uint32_t)TAG_CELLS ? agent : 0u, x, y);
+    if (last_ob == TAG_CELLS && tag_is_corner(x, y)) return 1u << 4;
+    const uint32_t mv = T->mv[agent];
+    uint32_t m = 0;
+    POMDP_UNROLL
+    for (int d = 0; d < 4; ++d)
+        if (last_action != ((d + 2) & 3) && ((mv >> (5 * d)) & 31u) != agent) m |= 1u << d;
+    return m;
+}
+POMDP_HD int32_t tag_policy_preferred(const TagTables* __restrict__ T, uint32_t s, int32_t last_ob, int32_t last_action, uint32_t w) {
+    const uint32_t m = tag_preferred_mask(T, s, last_ob, last_action);
+    if (m == 0u) return 0;
+    return (int32_t)nth_set_bit(m, rand_below(w, (uint32_t)popc32(m)));
 }
 
 // =========================================================================== Tiger ===

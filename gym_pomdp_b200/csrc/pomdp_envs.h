@@ -248,4 +248,96 @@ POMDP_HD void rollout1(const typename Env::Params& p, const unsigned char* tbl, 
     }
 }
 
+// ---- heuristic policies and rollouts: shared by the kernels and tests/hostsim ----------------
+// Read-only view of one env's rows of the per-rock planes; a NULL plane stands for its fresh value.
+struct RockPlanesView {
+    const int32_t* cnt_p; const int32_t* meas_p; const double* pv_p; const int32_t* tot_p;
+    int64_t base;
+    POMDP_HD int32_t tot_sample(int i) const { return tot_p ? rock_totals_sample(tot_p[base + i]) : 0; }
+    POMDP_HD int32_t tot_dir(int i) const { return tot_p ? rock_totals_dir(tot_p[base + i]) : 0; }
+    POMDP_HD int32_t count(int i) const { return cnt_p ? cnt_p[base + i] : 0; }
+    POMDP_HD int32_t measured(int i) const { return meas_p ? meas_p[base + i] : 0; }
+    POMDP_HD double pv(int i) const { return pv_p ? pv_p[base + i] : .5; }
+};
+struct RockPlanesPtr { int32_t* count; int32_t* measured; double* lkv; double* lkw; double* pv; int32_t* totals; int32_t* prev_obs; };
+// One env's planes for the length of a rollout (local memory on the device: k <= 16 rocks x 40 B)
+struct RockHeurLocal {
+    int32_t cnt[16], meas[16], ts[16], td[16];
+    double lkv[16], lkw[16], pvv[16];
+    POMDP_HD int32_t tot_sample(int i) const { return ts[i]; }
+    POMDP_HD int32_t tot_dir(int i) const { return td[i]; }
+    POMDP_HD int32_t count(int i) const { return cnt[i]; }
+    POMDP_HD int32_t measured(int i) const { return meas[i]; }
+    POMDP_HD double pv(int i) const { return pvv[i]; }
+    POMDP_HD void load(const RockPlanesPtr& pl, int64_t base, int k) {
+        for (int r = 0; r < k; ++r) {
+            cnt[r] = pl.count ? pl.count[base + r] : 0;
+            meas[r] = pl.measured ? pl.measured[base + r] : 0;
+            lkv[r] = pl.lkv ? pl.lkv[base + r] : 1.0;
+            lkw[r] = pl.lkw ? pl.lkw[base + r] : 1.0;
+            pvv[r] = pl.pv ? pl.pv[base + r] : .5;
+            const int32_t t = pl.totals ? pl.totals[base + r] : 0;
+            ts[r] = rock_totals_sample(t);
+            td[r] = rock_totals_dir(t);
+        }
+    }
+    POMDP_HD void store(const RockPlanesPtr& pl, int64_t base, int k) const {
+        for (int r = 0; r < k; ++r) {
+            if (pl.count) pl.count[base + r] = cnt[r];
+            if (pl.measured) pl.measured[base + r] = meas[r];
+            if (pl.lkv) pl.lkv[base + r] = lkv[r];
+            if (pl.lkw) pl.lkw[base + r] = lkw[r];
+            if (pl.pv) pl.pv[base + r] = pvv[r];
+            if (pl.totals) pl.totals[base + r] = rock_totals_pack(ts[r], td[r]);
+        }
+    }
+};
+// The reference's heuristic rollout loop (rock.py:557-572 with use_heuristic=True) for one env:
+//   a = choice(_generate_preferred(history)); next_ob, rw, done = step(a); history.append(Transition(...)); ob = next_ob;
+//   r += rw * disc; disc *= gamma.
+// next_is_reward: the transition's `next_observation` field holds the reward (the reference's own positional
+// Transition(ob, action, next_ob, rw, done), rock.py:566), otherwise the next observation.
+template <typename S, bool STOCH>
+POMDP_HD void rock_rollout_preferred1(const RockDev& p, const unsigned char* tbl, S& s, const PhiloxKey& seed, uint64_t env,
+                                      uint32_t ctr0, int32_t max_steps, double gamma, bool next_is_reward, bool has_first,
+                                      int32_t first_action, RockHeurLocal& h, int32_t& prev_ob, RolloutAcc& acc) {
+    typedef RockEnvT<S, STOCH> Env;
+    const RockTableHdr* hdr = reinterpret_cast<const RockTableHdr*>(tbl);
+    const RockLut* lut = reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET);
+    acc.init(Env::is_done(s));
+    for (int32_t t = 0; t < max_steps && !Env::is_done(s); ++t) {
+        const uint32_t ctr = ctr0 + (uint32_t)t;
+        const int32_t a = (t == 0 && has_first) ? first_action
+                                                : rock_policy_preferred<S>(p, hdr, lut, s, h, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
+        S s2; int32_t ob, fl; float rw;
+        Env::step1(p, tbl, s, a, seed, env, ctr, s2, ob, rw, fl);
+        s = s2;
+        if (a >= 5 && a < (int32_t)p.n_actions) {
+            const int r = a - 5;
+            rock_belief_update<S>(p, hdr, s, a, ob, h.cnt[r], h.meas[r], h.lkv[r], h.lkw[r], h.pvv[r]);   // rock.py:177-191
+            rock_history_update(a, prev_ob, next_is_reward ? (int32_t)rw : ob, h.ts[r], h.td[r]);         // rock.py:566
+        }
+        prev_ob = ob;                                                                                  // rock.py:567
+        acc.add(Env::reward64(rw), gamma, fl);
+    }
+}
+// tag.py:303-316 with the heuristic: a = choice(_generate_preferred(history)); ob, rw, done = step(a); history.append(a, ob)
+template <int NOPP>
+POMDP_HD void tag_rollout_preferred1(const TagDev& p, const unsigned char* tbl, uint32_t& s, const PhiloxKey& seed, uint64_t env,
+                                     uint32_t ctr0, int32_t max_steps, double gamma, bool has_first, int32_t first_action,
+                                     int32_t& last_ob, int32_t& last_action, RolloutAcc& acc) {
+    typedef TagEnvT<NOPP> Env;
+    const TagTables* T = reinterpret_cast<const TagTables*>(tbl);
+    acc.init(Env::is_done(s));
+    for (int32_t t = 0; t < max_steps && !Env::is_done(s); ++t) {
+        const uint32_t ctr = ctr0 + (uint32_t)t;
+        const int32_t a = (t == 0 && has_first) ? first_action
+                                                : tag_policy_preferred(T, s, last_ob, last_action, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
+        uint32_t s2; int32_t ob, fl; float rw;
+        Env::step1(p, tbl, s, a, seed, env, ctr, s2, ob, rw, fl);
+        s = s2; last_ob = ob; last_action = a;
+        acc.add((double)rw, gamma, fl);
+    }
+}
+
 }  // namespace pomdp

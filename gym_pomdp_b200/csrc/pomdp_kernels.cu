@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pomdp_core.h"
 #include "pomdp_envs.h"
@@ -498,6 +499,124 @@ pomdp_rock_belief_update_kernel(const __grid_constant__ RockDev p, const void* _
         double v = lkv[j], w = lkw[j], q = pv[j];
         rock_belief_update<S>(p, hdr, load_state1(state, i, S()), a, ob, c, m, v, w, q);
         count[j] = c; measured[j] = m; lkv[j] = v; lkw[j] = w; pv[j] = q;
+    }
+}
+
+// ------------------------------------------------ heuristic policies ---
+// RockEnv._generate_preferred (rock.py:293-374) on the per-rock planes: belief side-statistics (count, measured,
+// prob_valuable: the env's own state, pomdp_rock_belief_update) and the history totals (check_totals:
+// pomdp_rock_history_update).  A NULL plane stands for its fresh value (Rock.__init__ rock.py:78-86 / an empty history).
+// kPolicy: action[i] = np.random.choice(_generate_preferred(history)) (draw: domain POLICY, slot 0, as the uniform-legal
+// policy); else out[i] = the preferred set as a bit mask over action ids, 0 = "fall back to _generate_legal()".
+template <typename S, bool kPolicy>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rock_preferred_kernel(const __grid_constant__ RockDev p, const void* __restrict__ g_table, const int32_t* __restrict__ state,
+                            const int32_t* __restrict__ count, const int32_t* __restrict__ measured, const double* __restrict__ pv,
+                            const int32_t* __restrict__ totals, int32_t* __restrict__ out, int64_t n, uint64_t goff,
+                            const __grid_constant__ PhiloxKey seed, uint32_t step_ctr, uint32_t table_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<RockEnvT<S, false>>(smem_table, g_table, table_bytes, &bar);
+    const RockTableHdr* hdr = reinterpret_cast<const RockTableHdr*>(smem_table);
+    const RockLut* lut = reinterpret_cast<const RockLut*>(smem_table + ROCK_LUT_OFFSET);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const RockPlanesView h = {count, measured, pv, totals, i * p.k};
+        const S s = load_state1(state, i, S());
+        if (kPolicy) out[i] = rock_policy_preferred<S>(p, hdr, lut, s, h, draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_POLICY, 0));
+        else out[i] = (int32_t)rock_preferred_mask<S>(p, hdr, s, h);
+    }
+}
+// One transition appended to every env's history (rock.py:302-309, 325-331): the checked rock's two totals.
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rock_history_update_kernel(int k, const int32_t* __restrict__ obs_field, const int32_t* __restrict__ action,
+                                 const int32_t* __restrict__ next_obs_field, int32_t* __restrict__ totals, int64_t n) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const int32_t a = __ldcs(action + i);
+        if (a < 5 || a >= 5 + k) continue;
+        const int64_t j = i * k + (a - 5);
+        const int32_t t = totals[j];
+        int32_t ts = rock_totals_sample(t), td = rock_totals_dir(t);
+        rock_history_update(a, __ldcs(obs_field + i), __ldcs(next_obs_field + i), ts, td);
+        totals[j] = rock_totals_pack(ts, td);
+    }
+}
+// The reference's heuristic rollout loop (rock.py:557-572 with use_heuristic=True) fused into one kernel, one thread per
+// env: a = choice(_generate_preferred(history)); next_ob, rw, done = step(a); history.append(Transition(...)); ob = next_ob;
+// r += rw * disc; disc *= gamma.  The per-rock planes live in local memory for the whole rollout (k <= 16 rocks x 40 B);
+// planes that were passed in are updated in place at the end.  next_is_reward: the transition's `next_observation`
+// field holds the reward (the reference's own positional Transition(ob, action, next_ob, rw, done), rock.py:566),
+// otherwise the next observation.
+template <typename S, bool STOCH>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rock_rollout_preferred_kernel(const __grid_constant__ RockDev p, const void* __restrict__ g_table, const int32_t* state,
+                                    const int32_t* __restrict__ first_action, const __grid_constant__ RockPlanesPtr pl,
+                                    int32_t* final_state, double* __restrict__ ret, int32_t* __restrict__ steps,
+                                    int32_t* __restrict__ flags, int64_t n, uint64_t goff, const __grid_constant__ PhiloxKey seed,
+                                    uint32_t ctr0, int32_t max_steps, double gamma, int32_t next_is_reward, uint32_t table_bytes) {
+    typedef RockEnvT<S, STOCH> Env;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const int64_t base = i * p.k;
+        RockHeurLocal h;
+        h.load(pl, base, p.k);
+        int32_t prev_ob = pl.prev_obs ? pl.prev_obs[i] : 0;                     // RockEnv.reset returns Obs.NULL (rock.py:241)
+        S s = load_state1(state, i, S());
+        RolloutAcc acc;
+        rock_rollout_preferred1<S, STOCH>(p, smem_table, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, next_is_reward != 0,
+                                          first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        if (final_state) store_state1(final_state, i, s);
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
+        h.store(pl, base, p.k);
+        if (pl.prev_obs) pl.prev_obs[i] = prev_ob;
+    }
+}
+
+// TagEnv._generate_preferred (tag.py:231-243): needs only the last (observation, action) of the history.
+template <bool kPolicy>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_tag_preferred_kernel(const void* __restrict__ g_table, const int32_t* __restrict__ state, const int32_t* __restrict__ last_obs,
+                           const int32_t* __restrict__ last_action, int32_t* __restrict__ out, int64_t n, uint64_t goff,
+                           const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<TagEnvT<1>>(smem_table, g_table, (uint32_t)sizeof(TagTables), &bar);
+    const TagTables* T = reinterpret_cast<const TagTables*>(smem_table);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const uint32_t s = (uint32_t)state[i];
+        const int32_t lo = last_obs ? last_obs[i] : 0, la = last_action ? last_action[i] : -1;
+        if (kPolicy) out[i] = tag_policy_preferred(T, s, lo, la, draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_POLICY, 0));
+        else out[i] = (int32_t)tag_preferred_mask(T, s, lo, la);
+    }
+}
+// tag.py:303-316 with the heuristic: a = choice(_generate_preferred(history)); ob, rw, done = step(a); history.append(a, ob)
+template <int NOPP>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_tag_rollout_preferred_kernel(const __grid_constant__ TagDev p, const void* __restrict__ g_table, const int32_t* state,
+                                   int32_t* __restrict__ last_obs, int32_t* __restrict__ last_action,
+                                   const int32_t* __restrict__ first_action, int32_t* final_state, double* __restrict__ ret,
+                                   int32_t* __restrict__ steps, int32_t* __restrict__ flags, int64_t n, uint64_t goff,
+                                   const __grid_constant__ PhiloxKey seed, uint32_t ctr0, int32_t max_steps, double gamma) {
+    typedef TagEnvT<NOPP> Env;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<Env>(smem_table, g_table, (uint32_t)sizeof(TagTables), &bar);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        uint32_t s = (uint32_t)state[i];
+        int32_t lo = last_obs ? last_obs[i] : 0, la = last_action ? last_action[i] : -1;
+        RolloutAcc acc;
+        tag_rollout_preferred1<NOPP>(p, smem_table, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, first_action != nullptr,
+                                     first_action ? first_action[i] : 0, lo, la, acc);
+        if (final_state) final_state[i] = (int32_t)s;
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
+        if (last_obs) last_obs[i] = lo;
+        if (last_action) last_action[i] = la;
     }
 }
 
@@ -1451,14 +1570,35 @@ int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state,
 }
 
 // ---- the same on HOST buffers: chunked H2D -> step -> D2H on the pipe's streams (include/pomdp_b200.h)
+// Three streams -- one per engine: host-to-device copies, kernels, device-to-host copies -- linked by events, so each
+// copy engine sees ONE ordered queue and is never held up by another chunk's kernel or by the opposite direction.
+// Slot k = the staging buffers chunk c uses when c % n_slots == k; two events per slot guard their reuse (inputs may be
+// overwritten once the slot's kernel has run, outputs once they have been copied out).  Measured against one stream per
+// slot (scripts/exp_host_pipe2.cu, B200): 0.925 vs 0.97-0.99 ms per 2^22-env call at 4 chunks; every copy costs ~7 us
+// on top of its bytes on this box, which is why smaller chunks lose (8 chunks: 1.01 ms) although they fill faster.
 struct HostPipe {
     uint32_t magic;
     int words, n_slots, device;
     int64_t chunk;
     int32_t* slot[8];          // [state W*chunk | action chunk | next_state W*chunk | result chunk]
-    cudaStream_t stream[8];
+    cudaStream_t s_in, s_k, s_out;
+    cudaEvent_t ev_in[8], ev_k[8], ev_out[8];
 };
 static const uint32_t kHostPipeMagic = 0x50495045u;
+
+static void host_pipe_free(HostPipe* hp) {
+    for (int k = 0; k < 8; ++k) {
+        if (hp->slot[k]) cudaFree(hp->slot[k]);
+        if (hp->ev_in[k]) cudaEventDestroy(hp->ev_in[k]);
+        if (hp->ev_k[k]) cudaEventDestroy(hp->ev_k[k]);
+        if (hp->ev_out[k]) cudaEventDestroy(hp->ev_out[k]);
+    }
+    if (hp->s_in) cudaStreamDestroy(hp->s_in);
+    if (hp->s_k) cudaStreamDestroy(hp->s_k);
+    if (hp->s_out) cudaStreamDestroy(hp->s_out);
+    hp->magic = 0;
+    delete hp;
+}
 
 int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, void** pipe_out) {
     if (!pipe_out) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: pipe_out is NULL");
@@ -1468,16 +1608,21 @@ int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, voi
         return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_create: state_words %d, chunk_envs %lld (multiple of 4), n_slots %d (1..8)",
                           state_words, (long long)chunk_envs, n_slots);
     HostPipe* hp = new HostPipe();
+    memset(hp, 0, sizeof(*hp));
     hp->magic = kHostPipeMagic; hp->words = state_words; hp->n_slots = n_slots; hp->chunk = chunk_envs;
     cudaError_t e = cudaGetDevice(&hp->device);
     const size_t bytes = (size_t)(2 * state_words + 2) * (size_t)chunk_envs * sizeof(int32_t);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_k, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking);
     for (int k = 0; k < n_slots && e == cudaSuccess; ++k) {
         e = cudaMalloc((void**)&hp->slot[k], bytes);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->stream[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->ev_in[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->ev_k[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->ev_out[k], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
-        for (int k = 0; k < n_slots; ++k) { if (hp->slot[k]) cudaFree(hp->slot[k]); if (hp->stream[k]) cudaStreamDestroy(hp->stream[k]); }
-        delete hp;
+        host_pipe_free(hp);
         (void)cudaGetLastError();
         return host::fail((int)e, "pomdp_host_pipe_create: %s", cudaGetErrorString(e));
     }
@@ -1487,11 +1632,17 @@ int pomdp_host_pipe_create(int state_words, int64_t chunk_envs, int n_slots, voi
 int pomdp_host_pipe_destroy(void* pipe) {
     HostPipe* hp = (HostPipe*)pipe;
     if (!hp || hp->magic != kHostPipeMagic) return host::fail(POMDP_E_BADARG, "pomdp_host_pipe_destroy: not a pipe");
-    for (int k = 0; k < hp->n_slots; ++k) { cudaStreamSynchronize(hp->stream[k]); cudaFree(hp->slot[k]); cudaStreamDestroy(hp->stream[k]); }
-    hp->magic = 0;
-    delete hp;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(hp->device);
+    cudaStreamSynchronize(hp->s_in); cudaStreamSynchronize(hp->s_k); cudaStreamSynchronize(hp->s_out);
+    host_pipe_free(hp);
+    cudaSetDevice(prev);
     return 0;
 }
+// The host buffers must be host-complete when the call is made (it does not order itself after work the caller queued
+// on its own streams); the call returns when every result has landed.  Runs on the pipe's device whatever the caller's
+// current device is (restored on return).
 int pomdp_step_packed_host(void* pipe, int kind, const void* params, const void* d_table, const int32_t* h_state,
                            const int32_t* h_action, int32_t* h_next_state, int32_t* h_result, int64_t n, int64_t goff,
                            uint64_t seed, uint32_t step_ctr) {
@@ -1499,35 +1650,44 @@ int pomdp_step_packed_host(void* pipe, int kind, const void* params, const void*
     int rc = host::check_host_step(hp && hp->magic == kHostPipeMagic, hp ? hp->words : 0, kind, params, h_state, h_action,
                                    h_next_state, h_result, n, goff);
     if (rc || n == 0) return rc;
-    const int W = hp->words;
+    int prev_dev = 0;
+    cudaError_t e = cudaGetDevice(&prev_dev);
+    if (e == cudaSuccess && prev_dev != hp->device) e = cudaSetDevice(hp->device);
+    const int W = hp->words, S = hp->n_slots;
     const int64_t C = hp->chunk;
-    cudaError_t e = cudaSuccess;
     int ci = 0;
     for (int64_t lo = 0; lo < n && rc == 0 && e == cudaSuccess; lo += C, ++ci) {
         const int64_t m = n - lo < C ? n - lo : C;
-        const int k = ci % hp->n_slots;
-        cudaStream_t st = hp->stream[k];
+        const int k = ci % S;
         int32_t* d_state = hp->slot[k];
         int32_t* d_action = d_state + (size_t)W * C;
         int32_t* d_next = d_action + C;
         int32_t* d_result = d_next + (size_t)W * C;
-        e = cudaMemcpyAsync(d_state, h_state + (size_t)lo * W, (size_t)m * W * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_action, h_action + lo, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (ci >= S) e = cudaStreamWaitEvent(hp->s_in, hp->ev_k[k], 0);               // the slot's inputs have been consumed
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_state, h_state + (size_t)lo * W, (size_t)m * W * sizeof(int32_t), cudaMemcpyHostToDevice, hp->s_in);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_action, h_action + lo, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, hp->s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(hp->ev_in[k], hp->s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->s_k, hp->ev_in[k], 0);
+        if (e == cudaSuccess && ci >= S) e = cudaStreamWaitEvent(hp->s_k, hp->ev_out[k], 0);   // the slot's outputs have been drained
         if (e != cudaSuccess) break;
         switch (kind) {
-            case POMDP_KIND_ROCK: rc = pomdp_rock_step_packed((const PomdpRockParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
-            case POMDP_KIND_TAG: rc = pomdp_tag_step_packed((const PomdpTagParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
-            case POMDP_KIND_TIGER: rc = pomdp_tiger_step_packed((const PomdpTigerParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
-            default: rc = pomdp_network_step_packed((const PomdpNetworkParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, st); break;
+            case POMDP_KIND_ROCK: rc = pomdp_rock_step_packed((const PomdpRockParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, hp->s_k); break;
+            case POMDP_KIND_TAG: rc = pomdp_tag_step_packed((const PomdpTagParams*)params, d_table, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, hp->s_k); break;
+            case POMDP_KIND_TIGER: rc = pomdp_tiger_step_packed((const PomdpTigerParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, hp->s_k); break;
+            default: rc = pomdp_network_step_packed((const PomdpNetworkParams*)params, d_state, d_action, d_next, d_result, m, goff + lo, seed, step_ctr, hp->s_k); break;
         }
         if (rc) break;
-        e = cudaMemcpyAsync(h_next_state + (size_t)lo * W, d_next, (size_t)m * W * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h_result + lo, d_result, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        e = cudaEventRecord(hp->ev_k[k], hp->s_k);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->s_out, hp->ev_k[k], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_next_state + (size_t)lo * W, d_next, (size_t)m * W * sizeof(int32_t), cudaMemcpyDeviceToHost, hp->s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_result + lo, d_result, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, hp->s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(hp->ev_out[k], hp->s_out);
     }
-    for (int k = 0; k < hp->n_slots; ++k) {                   // drain even after an error: the slots are reused
-        const cudaError_t es = cudaStreamSynchronize(hp->stream[k]);
-        if (e == cudaSuccess) e = es;
+    {   // drain even after an error: the slots are reused by the next call
+        const cudaError_t e1 = cudaStreamSynchronize(hp->s_in), e2 = cudaStreamSynchronize(hp->s_k), e3 = cudaStreamSynchronize(hp->s_out);
+        if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
     }
+    if (prev_dev != hp->device) cudaSetDevice(prev_dev);
     if (rc) return rc;
     if (e != cudaSuccess) { (void)cudaGetLastError(); return host::fail((int)e, "pomdp_step_packed_host: %s", cudaGetErrorString(e)); }
     return 0;
@@ -1748,6 +1908,168 @@ int pomdp_rock_belief_update(const PomdpRockParams* q, const void* d_table, cons
             d, d_table, next_state, action, obs, count, measured, lkv, lkw, prob_valuable, n, d.table_bytes);
     }
     return finish("pomdp_rock_belief_update");
+}
+
+// ---- heuristic action sets and rollouts
+int pomdp_rock_history_update(const PomdpRockParams* q, const int32_t* obs_field, const int32_t* action,
+                              const int32_t* next_obs_field, int32_t* check_totals, int64_t n, void* stream) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    if (rc) return rc;
+    if (n < 0) return host::fail(POMDP_E_BADARG, "pomdp_rock_history_update: n is negative");
+    if (n == 0) return 0;
+    if (!obs_field || !action || !next_obs_field || !check_totals)
+        return host::fail(POMDP_E_BADARG, "pomdp_rock_history_update: a required array pointer is NULL");
+    if (((uintptr_t)obs_field | (uintptr_t)action | (uintptr_t)next_obs_field | (uintptr_t)check_totals) & 3)
+        return host::fail(POMDP_E_ALIGN, "pomdp_rock_history_update: array pointers must be 4-byte aligned");
+    auto k = pomdp_rock_history_update_kernel;
+    k<<<grid_for(k, n), POMDP_THREADS, 0, (cudaStream_t)stream>>>(q->num_rocks, obs_field, action, next_obs_field, check_totals, n);
+    return finish("pomdp_rock_history_update");
+}
+extern "C++" {
+namespace {
+template <bool kPolicy>
+int launch_rock_preferred(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* count,
+                          const int32_t* measured, const double* pv, const int32_t* totals, int32_t* out, int64_t n, int64_t goff,
+                          uint64_t seed, uint32_t step_ctr, void* stream, const char* what) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, out, n, goff, what))) return rc;
+    if ((((uintptr_t)count | (uintptr_t)measured | (uintptr_t)totals) & 3) || ((uintptr_t)pv & 7))
+        return host::fail(POMDP_E_ALIGN, "%s: int32 planes must be 4-byte and the float64 plane 8-byte aligned", what);
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = d.smem_bytes;
+    const PhiloxKey key = philox_key(seed);
+    if (host::rock_words(q) == 1) {
+        auto k = pomdp_rock_preferred_kernel<uint32_t, kPolicy>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, state, count, measured, pv, totals, out, n, (uint64_t)goff, key, step_ctr, d.table_bytes);
+    } else {
+        auto k = pomdp_rock_preferred_kernel<uint64_t, kPolicy>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, state, count, measured, pv, totals, out, n, (uint64_t)goff, key, step_ctr, d.table_bytes);
+    }
+    return finish(what);
+}
+template <typename S, bool STOCH>
+int launch_rock_rollout_preferred(const RockDev& d, const void* d_table, const int32_t* state, const int32_t* first_action,
+                                  const RockPlanesPtr& pl, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                                  int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps, double discount,
+                                  int32_t next_is_reward, void* stream) {
+    auto k = pomdp_rock_rollout_preferred_kernel<S, STOCH>;
+    int rc = allow_smem(k, d.smem_bytes);
+    if (rc) return rc;
+    k<<<grid_for(k, n, POMDP_THREADS, d.smem_bytes), POMDP_THREADS, d.smem_bytes, (cudaStream_t)stream>>>(
+        d, d_table, state, first_action, pl, final_state, ret, steps, flags, n, (uint64_t)goff, philox_key(seed), step_ctr,
+        max_steps, discount, next_is_reward, d.table_bytes);
+    return finish("pomdp_rock_rollout_preferred");
+}
+}  // namespace
+}  // extern "C++"
+int pomdp_rock_preferred_mask(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* count,
+                              const int32_t* measured, const double* pv, const int32_t* totals, uint32_t* mask, int64_t n,
+                              void* stream) {
+    return launch_rock_preferred<false>(q, d_table, state, count, measured, pv, totals, (int32_t*)mask, n, 0, 0, 0, stream,
+                                        "pomdp_rock_preferred_mask");
+}
+int pomdp_rock_policy_preferred(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* count,
+                                const int32_t* measured, const double* pv, const int32_t* totals, int32_t* action, int64_t n,
+                                int64_t goff, uint64_t seed, uint32_t step_ctr, void* stream) {
+    return launch_rock_preferred<true>(q, d_table, state, count, measured, pv, totals, action, n, goff, seed, step_ctr, stream,
+                                       "pomdp_rock_policy_preferred");
+}
+int pomdp_rock_rollout_preferred(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* first_action,
+                                 const PomdpRockHeuristicPlanes* planes, int32_t* final_state, double* ret, int32_t* steps,
+                                 int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps,
+                                 double discount, int32_t next_is_reward, void* stream) {
+    const char* what = "pomdp_rock_rollout_preferred";
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what))) return rc;
+    if ((uintptr_t)first_action & 3) return host::fail(POMDP_E_ALIGN, "%s: first_action must be 4-byte aligned", what);
+    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (planes) {
+        pl.count = planes->count; pl.measured = planes->measured; pl.lkv = planes->lkv; pl.lkw = planes->lkw;
+        pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs;
+        if ((((uintptr_t)pl.count | (uintptr_t)pl.measured | (uintptr_t)pl.totals | (uintptr_t)pl.prev_obs) & 3) ||
+            (((uintptr_t)pl.lkv | (uintptr_t)pl.lkw | (uintptr_t)pl.pv) & 7))
+            return host::fail(POMDP_E_ALIGN, "%s: int32 planes must be 4-byte and float64 planes 8-byte aligned", what);
+    }
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+#define POMDP_RRP(S, STOCH)                                                                                              \
+    return launch_rock_rollout_preferred<S, STOCH>(d, d_table, state, first_action, pl, final_state, ret, steps, flags, n, goff, \
+                                                   seed, step_ctr, max_steps, discount, next_is_reward, stream)
+    if (host::rock_words(q) == 1) {
+        if (d.stochastic) POMDP_RRP(uint32_t, true);
+        POMDP_RRP(uint32_t, false);
+    }
+    if (d.stochastic) POMDP_RRP(uint64_t, true);
+    POMDP_RRP(uint64_t, false);
+#undef POMDP_RRP
+}
+extern "C++" {
+namespace {
+template <bool kPolicy>
+int launch_tag_preferred(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* last_obs,
+                         const int32_t* last_action, int32_t* out, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                         void* stream, const char* what) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, out, n, goff, what))) return rc;
+    if (((uintptr_t)last_obs | (uintptr_t)last_action) & 3) return host::fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = sizeof(TagTables);
+    auto k = pomdp_tag_preferred_kernel<kPolicy>;
+    k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(d_table, state, last_obs, last_action, out, n,
+                                                                                           (uint64_t)goff, philox_key(seed), step_ctr);
+    return finish(what);
+}
+}  // namespace
+}  // extern "C++"
+int pomdp_tag_preferred_mask(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* last_obs,
+                             const int32_t* last_action, uint32_t* mask, int64_t n, void* stream) {
+    return launch_tag_preferred<false>(q, d_table, state, last_obs, last_action, (int32_t*)mask, n, 0, 0, 0, stream,
+                                       "pomdp_tag_preferred_mask");
+}
+int pomdp_tag_policy_preferred(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* last_obs,
+                               const int32_t* last_action, int32_t* action, int64_t n, int64_t goff, uint64_t seed,
+                               uint32_t step_ctr, void* stream) {
+    return launch_tag_preferred<true>(q, d_table, state, last_obs, last_action, action, n, goff, seed, step_ctr, stream,
+                                      "pomdp_tag_policy_preferred");
+}
+int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* d_table, const int32_t* state, int32_t* last_obs,
+                                int32_t* last_action, const int32_t* first_action, int32_t* final_state, double* ret,
+                                int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
+                                int32_t max_steps, double discount, void* stream) {
+    const char* what = "pomdp_tag_rollout_preferred";
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what))) return rc;
+    if (((uintptr_t)first_action | (uintptr_t)last_obs | (uintptr_t)last_action) & 3)
+        return host::fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const size_t smem = sizeof(TagTables);
+    if (d.n_opp == 1) {
+        auto k = pomdp_tag_rollout_preferred_kernel<1>;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, state, last_obs, last_action, first_action, final_state, ret, steps, flags, n, (uint64_t)goff, philox_key(seed),
+            step_ctr, max_steps, discount);
+    } else {
+        auto k = pomdp_tag_rollout_preferred_kernel<4>;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
+            d, d_table, state, last_obs, last_action, first_action, final_state, ret, steps, flags, n, (uint64_t)goff, philox_key(seed),
+            step_ctr, max_steps, discount);
+    }
+    return finish(what);
 }
 
 // ---- helpers

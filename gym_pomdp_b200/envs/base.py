@@ -230,7 +230,8 @@ class BatchedPomdpEnv(_EnvBase):
             self._c_policy(state, action, n, ctr)
         return action
 
-    def rollout(self, state=None, max_steps=100, discount=None, out=None, step_ctr=None, first_action=None):
+    def rollout(self, state=None, max_steps=100, discount=None, out=None, step_ctr=None, first_action=None, policy="legal",
+                **policy_kw):
         """Monte-Carlo rollouts under the uniform-legal policy, fused into ONE kernel (states stay
         in registers): until done or ``max_steps``,
         ``a = choice(_generate_legal()); ob, rw, done = step(a); ret += rw * disc; disc *= discount``.
@@ -239,7 +240,12 @@ class BatchedPomdpEnv(_EnvBase):
         to the env's ``_discount``.  Draw for draw identical to ``max_steps`` rounds of
         ``sample_legal_actions`` + ``simulate`` with counters step_ctr, step_ctr + 1, ...
         ``first_action`` (int32[n]): step 0 takes these actions instead of a policy draw, so ``ret`` is a
-        Monte-Carlo sample of Q(s, a) -- POMCP's "simulate a, then roll out" in one launch."""
+        Monte-Carlo sample of Q(s, a) -- POMCP's "simulate a, then roll out" in one launch.
+        ``policy="preferred"``: actions are drawn from ``_generate_preferred(history)`` instead (RockSample with
+        ``use_heuristic``, Tag; the other envs' preferred set is the legal set); see ``_c_rollout_preferred`` of the
+        env for the extra keywords."""
+        if policy not in ("legal", "preferred"):
+            raise ValueError("policy must be 'legal' or 'preferred'")
         state = self.state if state is None else state
         n = state.shape[0]
         if out is None:
@@ -254,9 +260,19 @@ class BatchedPomdpEnv(_EnvBase):
         if first_action is not None:
             first_action = torch.as_tensor(first_action, device=state.device).to(torch.int32).expand(n).contiguous()
         with self._guard():
-            self._c_rollout(state, final_state, ret, steps, flags, n, ctr, max_steps,
-                            self._discount if discount is None else discount, first_action)
+            if policy == "preferred" and self._has_preferred_kernel():
+                self._c_rollout_preferred(state, final_state, ret, steps, flags, n, ctr, max_steps,
+                                          self._discount if discount is None else discount, first_action, **policy_kw)
+            else:
+                if policy_kw:
+                    raise TypeError("unexpected keywords for the uniform-legal rollout: %s" % sorted(policy_kw))
+                self._c_rollout(state, final_state, ret, steps, flags, n, ctr, max_steps,
+                                self._discount if discount is None else discount, first_action)
         return final_state, ret, steps, flags
+
+    def _has_preferred_kernel(self):
+        """True where ``_generate_preferred`` differs from ``_generate_legal`` (RockSample with use_heuristic, Tag)."""
+        return False
 
     def simulate_host(self, state, action, out, step_ctr=None, chunk=None, packed=False, n_streams=3, zero_copy=False,
                       pipeline=None):

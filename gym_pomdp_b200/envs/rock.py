@@ -43,16 +43,81 @@ class RockBeliefStats(object):
         return self.count, self.measured, self.lkv, self.lkw, self.prob_valuable
 
 
+class RockHistory(object):
+    """What ``_generate_preferred`` needs from the caller's History, for a whole batch: per rock the two running totals
+    of rock.py:302-309 / 325-331 over the transitions that checked it (``check_totals`` int32[n, k]: low 16 bits
+    #GOOD - #BAD of ``next_observation``, high 16 bits #(next_observation == GOOD) - #(next_observation != GOOD and
+    observation == BAD)) and the observation the next transition will record as ``observation`` (``prev_obs`` int32[n])."""
+
+    def __init__(self, n, k, device):
+        self.check_totals = torch.zeros((n, k), dtype=torch.int32, device=device)
+        self.prev_obs = torch.zeros(n, dtype=torch.int32, device=device)          # RockEnv.reset returns Obs.NULL
+
+    def reset(self, mask=None):
+        sel = slice(None) if mask is None else mask.to(self.prev_obs.device).bool()
+        self.check_totals[sel] = 0
+        self.prev_obs[sel] = 0
+
+    def totals(self):
+        """(tot_sample, tot_dir) int32[n, k]"""
+        t = self.check_totals
+        return ((t << 16) >> 16), (t >> 16)
+
+
+class Transition(tuple):
+    """rock.py:525-530: NamedTuple(observation, action, reward, next_observation, done)"""
+    __slots__ = ()
+    _fields = ("observation", "action", "reward", "next_observation", "done")
+
+    def __new__(cls, observation, action, reward, next_observation, done):
+        return tuple.__new__(cls, (observation, action, reward, next_observation, done))
+
+    observation = property(lambda self: self[0])
+    action = property(lambda self: self[1])
+    reward = property(lambda self: self[2])
+    next_observation = property(lambda self: self[3])
+    done = property(lambda self: self[4])
+
+
+class History(object):
+    """rock.py:533-551"""
+
+    def __init__(self, max_size=None):
+        self._max_size = max_size
+        self._history = []
+
+    def __getitem__(self, item):
+        return self._history[item]
+
+    def append(self, transition):
+        if self._max_size is not None and self.size > self._max_size:
+            self._history.pop(0)
+        self._history.append(transition)
+
+    @property
+    def size(self):
+        return len(self._history)
+
+    def __repr__(self):
+        return "size:%d" % self.size
+
+
 class RockEnv(BatchedPomdpEnv):
     kind = _lib.KIND_ROCK
     _abi = "rock"
     _stochastic = False
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, batch_size=None, device="cuda", seed=0,
-                 global_offset=0, p_move=0.8, track_belief_stats=False):
+                 global_offset=0, p_move=0.8, track_belief_stats=False, track_history=False, history_next_is_reward=False):
         super().__init__(batch_size, device, seed, global_offset)
-        self.track_belief_stats = bool(track_belief_stats)   # batched mode: keep rock.py's per-rock side-stats current
+        # batched mode: keep rock.py's per-rock side-stats current; track_history also keeps the per-rock totals
+        # _generate_preferred reads from the History (as if every step appended Transition(ob, a, rw, next_ob, done); with
+        # history_next_is_reward the reference's own positional Transition(ob, a, next_ob, rw, done) of rock.py:566)
+        self.track_history = bool(track_history)
+        self.track_belief_stats = bool(track_belief_stats) or self.track_history
+        self.history_next_is_reward = bool(history_next_is_reward)
         self.belief_stats = None
+        self.history = None
         self.num_rocks = num_rocks
         self._use_heuristic = use_heuristic
         self._params = _lib.RockParams(board_size, num_rocks, int(self._stochastic), 0, float(p_move))
@@ -106,15 +171,89 @@ class RockEnv(BatchedPomdpEnv):
     def update_belief_stats(self, stats, next_state, action, obs):
         """rock.py:177-191 for a whole batch: every env whose ``action`` was a check that produced a reading updates
         that rock's measured / count / lkv / lkw / prob_valuable in ``stats`` (in place; one kernel)."""
-        n = action.shape[0]
+        n = next_state.shape[0]
         action = torch.as_tensor(action, device=self.device).to(torch.int32).contiguous()
         obs = torch.as_tensor(obs, device=self.device).to(torch.int32).contiguous()
+        if action.shape != (n,) or obs.shape != (n,):
+            raise ValueError("action and obs must have shape (%d,), got %s and %s" % (n, tuple(action.shape), tuple(obs.shape)))
         with self._guard():
             _lib.check(_lib.lib().pomdp_rock_belief_update(
                 ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(next_state), _lib.ptr(action), _lib.ptr(obs),
                 _lib.ptr(stats.count), _lib.ptr(stats.measured), _lib.ptr(stats.lkv), _lib.ptr(stats.lkw),
                 _lib.ptr(stats.prob_valuable), n, self._stream()), "pomdp_rock_belief_update")
         return stats
+
+    # ------------------------------------------------------ heuristic action sets (batched) ---
+    def new_history(self, n=None):
+        return RockHistory(self.batch_size if n is None else int(n), self.num_rocks, self.device)
+
+    def update_history(self, history, action, next_obs_field, obs_field=None):
+        """One transition appended to every env's history: the checked rock's totals (rock.py:302-309, 325-331) from the
+        two fields as the caller's Transition holds them -- ``obs_field`` defaults to ``history.prev_obs``,
+        ``next_obs_field`` is the next observation (or the reward, for the reference's positional Transition) -- then
+        ``prev_obs`` advances to the step's observation if ``next_obs_field`` is that (pass ``obs_field`` explicitly
+        otherwise and set ``history.prev_obs`` yourself)."""
+        n = history.prev_obs.shape[0]
+        action = torch.as_tensor(action, device=self.device).to(torch.int32).contiguous()
+        nf = torch.as_tensor(next_obs_field, device=self.device).to(torch.int32).contiguous()
+        of = history.prev_obs if obs_field is None else torch.as_tensor(obs_field, device=self.device).to(torch.int32).contiguous()
+        with self._guard():
+            _lib.check(_lib.lib().pomdp_rock_history_update(
+                ctypes.byref(self._params), _lib.ptr(of), _lib.ptr(action), _lib.ptr(nf), _lib.ptr(history.check_totals), n,
+                self._stream()), "pomdp_rock_history_update")
+        return history
+
+    def _preferred_call(self, fn_name, state, stats, history, out, *tail):
+        n = state.shape[0]
+        fn = getattr(_lib.lib(), fn_name)
+        with self._guard():
+            _lib.check(fn(ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state.contiguous()),
+                          _lib.ptr(None if stats is None else stats.count), _lib.ptr(None if stats is None else stats.measured),
+                          _lib.ptr(None if stats is None else stats.prob_valuable),
+                          _lib.ptr(None if history is None else history.check_totals), _lib.ptr(out), n, *tail, self._stream()),
+                       fn_name)
+        return out
+
+    def preferred_mask_words(self, state=None, stats=None, history=None):
+        """``_generate_preferred(history)`` (rock.py:293-374, use_heuristic=True) for every particle as one bit mask over
+        action ids, int32[n]; 0 = the preferred list is empty and the reference returns ``_generate_legal()``.  ``stats``
+        (RockBeliefStats) / ``history`` (RockHistory) default to the env's own planes, None = fresh / empty."""
+        state = self.state if state is None else state
+        stats = self.belief_stats if stats is None else stats
+        history = self.history if history is None else history
+        return self._preferred_call("pomdp_rock_preferred_mask", state, stats, history,
+                                    self._empty((state.shape[0],), torch.int32))
+
+    def sample_preferred_actions(self, state=None, stats=None, history=None, out=None, step_ctr=None):
+        """Batched ``np.random.choice(env._generate_preferred(history))``: int32[n], the POLICY draw of ``step_ctr`` (default:
+        the counter the next ``simulate``/``step`` call uses, like ``sample_legal_actions``)."""
+        state = self.state if state is None else state
+        stats = self.belief_stats if stats is None else stats
+        history = self.history if history is None else history
+        action = self._empty((state.shape[0],), torch.int32) if out is None else out
+        ctr = ((self._step_ctr + 1) & 0xFFFFFFFF) if step_ctr is None else int(step_ctr)
+        return self._preferred_call("pomdp_rock_policy_preferred", state, stats, history, action, self.global_offset,
+                                    self._seed, ctr)
+
+    def _has_preferred_kernel(self):
+        return bool(self._use_heuristic)
+
+    def _c_rollout_preferred(self, state, final_state, ret, steps, flags, n, ctr, max_steps, discount, first_action=None,
+                             stats=None, history=None, next_is_reward=None):
+        """rock.py:557-572 with use_heuristic=True, fused: ``stats`` / ``history`` planes (read at the start, updated in
+        place; None = fresh Rock.__init__ values / an empty history); ``next_is_reward`` selects what the transitions'
+        ``next_observation`` field holds (default: the env's ``history_next_is_reward``)."""
+        planes = _lib.RockHeuristicPlanes()
+        if stats is not None:
+            planes.count, planes.measured = stats.count.data_ptr(), stats.measured.data_ptr()
+            planes.lkv, planes.lkw, planes.prob_valuable = stats.lkv.data_ptr(), stats.lkw.data_ptr(), stats.prob_valuable.data_ptr()
+        if history is not None:
+            planes.check_totals, planes.prev_obs = history.check_totals.data_ptr(), history.prev_obs.data_ptr()
+        nir = self.history_next_is_reward if next_is_reward is None else bool(next_is_reward)
+        _lib.check(_lib.lib().pomdp_rock_rollout_preferred(
+            ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(first_action), ctypes.byref(planes),
+            _lib.ptr(final_state), _lib.ptr(ret), _lib.ptr(steps), _lib.ptr(flags), n, self.global_offset, self._seed, ctr,
+            int(max_steps), float(discount), int(nir), self._stream()), "pomdp_rock_rollout_preferred")
 
     # ---------------------------------------------------------------------- codec ---
     def pack(self, x, y, status, done=None):
@@ -166,13 +305,25 @@ class RockEnv(BatchedPomdpEnv):
                 self.belief_stats = self.new_belief_stats()
             else:
                 self.belief_stats.reset(mask)
+        if self.track_history and not self._scalar:
+            if self.history is None:
+                self.history = self.new_history()
+            else:
+                self.history.reset(mask)
         return obs
 
     def step(self, action):
+        if not self._scalar and (self.track_belief_stats or self.track_history):
+            action = torch.as_tensor(action, device=self.device).to(torch.int32).contiguous()
         out = super().step(action)
         if self.track_belief_stats and not self._scalar:
             self.update_belief_stats(self.belief_stats, self.state, action, out[0])
             out[3]["belief_stats"] = self.belief_stats
+        if self.track_history and not self._scalar:
+            nf = out[1].to(torch.int32) if self.history_next_is_reward else out[0]
+            self.update_history(self.history, action, nf)
+            self.history.prev_obs.copy_(out[0])
+            out[3]["history"] = self.history
         return out
 
     def _on_reset(self):
@@ -259,9 +410,56 @@ class RockEnv(BatchedPomdpEnv):
         return self.legal_mask(state)
 
     def _generate_preferred(self, history):
+        """rock.py:293-374.  Without ``use_heuristic``: ``_generate_legal()``.  Scalar mode: ``history`` is the caller's
+        History of Transitions, read field by field exactly as the reference reads it (``action``, ``next_observation``
+        and -- in the second loop's elif, rock.py:330 -- ``observation``); returns the reference's list.  Batched mode:
+        ``history`` is a RockHistory (or None for the env's own / an empty one); returns bool[n, n_actions]."""
         if not self._use_heuristic:
             return self._generate_legal()
-        raise NotImplementedError("use_heuristic=True rollouts are not on the device path yet (SURVEY.md §8f rank 3)")
+        if not self._scalar:
+            words = self.preferred_mask_words(history=history).to(torch.int64) & 0xFFFFFFFF
+            a = torch.arange(self.action_space.n, device=words.device)
+            pref = ((words[:, None] >> a) & 1).bool()
+            return torch.where((words == 0)[:, None], self.legal_mask(), pref)
+        # the two per-rock totals the reference recomputes from the whole history on every call
+        k = self.num_rocks
+        ts, td = [0] * k, [0] * k
+        for tr in history:
+            r = tr.action - SAMPLE - 1
+            if 0 <= r < k:
+                if tr.next_observation == GOOD:
+                    ts[r] += 1
+                    td[r] += 1
+                else:
+                    if tr.next_observation == BAD:
+                        ts[r] -= 1
+                    if tr.observation == BAD:
+                        td[r] -= 1
+        side = self._side
+        stats = RockBeliefStats(1, k, self.device)
+        stats.count.copy_(torch.tensor([[r["count"] for r in side]], dtype=torch.int32))
+        stats.measured.copy_(torch.tensor([[r["measured"] for r in side]], dtype=torch.int32))
+        stats.prob_valuable.copy_(torch.tensor([[r["prob_valuable"] for r in side]], dtype=torch.float64))
+        hist = RockHistory(1, k, self.device)
+        hist.check_totals.copy_(torch.tensor([[(s_ & 0xFFFF) | ((d_ & 0xFFFF) << 16) for s_, d_ in zip(ts, td)]],
+                                             dtype=torch.int64).to(torch.int32))
+        state = self._io_state.to(self.device) if self._io_state.device != self.device else self._io_state
+        word = int(self.preferred_mask_words(state.reshape(self._io_state.shape), stats, hist)[0]) & 0xFFFFFFFF
+        if word == 0:
+            return self._generate_legal()
+        return [a for a in range(self.action_space.n) if (word >> a) & 1]
+
+    @staticmethod
+    def _select_target(rock_state, x_size):
+        """rock.py:389-399: the nearest (2-norm: ``Grid.manhattan_distance`` is the Euclidean one) rock that is not
+        collected and whose check count is not negative; -1 if none within 2 * x_size."""
+        best_dist, best_rock = x_size * 2, -1
+        for idx, rock in enumerate(rock_state.rocks):
+            if rock.status != 0 and rock.count >= 0:
+                d = Grid.manhattan_distance(rock_state.agent_pos, rock.pos)
+                if d < best_dist:
+                    best_dist, best_rock = d, idx
+        return best_rock
 
     def _compute_prob(self, action, next_state, ob):
         """rock.py:250-264.  Scalar: floats.  Batched: float64 tensor (action/ob tensors)."""
@@ -282,7 +480,7 @@ class StochasticRockEnv(RockEnv):
     _stochastic = True
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, p_move=.8, batch_size=None, device="cuda",
-                 seed=0, global_offset=0, track_belief_stats=False):
+                 seed=0, global_offset=0, track_belief_stats=False, track_history=False, history_next_is_reward=False):
         super().__init__(board_size, num_rocks, use_heuristic, batch_size, device, seed, global_offset, p_move,
-                         track_belief_stats)
+                         track_belief_stats, track_history, history_next_is_reward)
         self.p_move = p_move

@@ -131,18 +131,58 @@ class TagEnv(BatchedPomdpEnv):
             return list(range(self.action_space.n))
         return self.legal_mask(state)
 
+    # ------------------------------------------------------------ heuristic action sets ---
+    def _preferred_call(self, fn_name, state, last_obs, last_action, out, *tail):
+        n = state.shape[0]
+        conv = lambda t: None if t is None else torch.as_tensor(t, device=state.device).to(torch.int32).expand(n).contiguous()
+        last_obs, last_action = conv(last_obs), conv(last_action)
+        with self._guard():
+            _lib.check(getattr(_lib.lib(), fn_name)(ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state.contiguous()),
+                                                   _lib.ptr(last_obs), _lib.ptr(last_action), _lib.ptr(out), n, *tail,
+                                                   self._stream()), fn_name)
+        return out
+
+    def preferred_mask_words(self, state=None, last_obs=None, last_action=None):
+        """``_generate_preferred(history)`` (tag.py:231-243) for every particle as a bit mask over the five actions,
+        int32[n].  The set depends on the history's last (ob, action) only; ``last_action`` None (or < 0) = empty history."""
+        state = self.state if state is None else state
+        return self._preferred_call("pomdp_tag_preferred_mask", state, last_obs, last_action,
+                                    self._empty((state.shape[0],), torch.int32))
+
+    def sample_preferred_actions(self, state=None, last_obs=None, last_action=None, out=None, step_ctr=None):
+        """Batched ``np.random.choice(env._generate_preferred(history))``: int32[n], the POLICY draw of ``step_ctr``."""
+        state = self.state if state is None else state
+        action = self._empty((state.shape[0],), torch.int32) if out is None else out
+        ctr = ((self._step_ctr + 1) & 0xFFFFFFFF) if step_ctr is None else int(step_ctr)
+        return self._preferred_call("pomdp_tag_policy_preferred", state, last_obs, last_action, action, self.global_offset,
+                                    self._seed, ctr)
+
+    def _has_preferred_kernel(self):
+        return True
+
+    def _c_rollout_preferred(self, state, final_state, ret, steps, flags, n, ctr, max_steps, discount, first_action=None,
+                             last_obs=None, last_action=None):
+        """tag.py:303-316 with ``_generate_preferred``, fused.  ``last_obs`` / ``last_action`` int32[n] tensors: the
+        history's last entry at the start (updated in place); None = an empty history."""
+        _lib.check(_lib.lib().pomdp_tag_rollout_preferred(
+            ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(last_obs), _lib.ptr(last_action),
+            _lib.ptr(first_action), _lib.ptr(final_state), _lib.ptr(ret), _lib.ptr(steps), _lib.ptr(flags), n,
+            self.global_offset, self._seed, ctr, int(max_steps), float(discount), self._stream()), "pomdp_tag_rollout_preferred")
+
     def _generate_preferred(self, history):
-        """tag.py:231-243 (scalar mode)"""
+        """tag.py:231-243.  Scalar mode: ``history`` is the caller's History (``.size``, ``[-1].ob``, ``[-1].action``);
+        returns the reference's list.  Batched: ``history`` = (last_obs, last_action) int32[n] tensors or None for an empty
+        history; returns bool[n, 5]."""
         if not self._scalar:
-            raise NotImplementedError("history-dependent heuristics are host-side, single-instance only")
+            lo, la = (None, None) if history is None else history
+            words = self.preferred_mask_words(None, lo, la).to(torch.int64)
+            a = torch.arange(self.action_space.n, device=words.device)
+            return ((words[:, None] >> a) & 1).bool()
         if history.size == 0:
             return self._generate_legal()
-        st = self._info_state()
-        if history[-1].ob == self.grid.n_tiles and self.grid.is_corner(st.agent_pos):
-            return [TAG]
-        from ..geometry import Moves
-        actions = [d for d in range(4) if history[-1].action != self.grid.opposite(d)
-                   and self.grid.is_inside(st.agent_pos + Moves.get_coord(d))]
+        state = self._io_state.to(self.device) if self._io_state.device != self.device else self._io_state
+        word = int(self.preferred_mask_words(state.reshape(-1), [int(history[-1].ob)], [int(history[-1].action)])[0])
+        actions = [a for a in range(self.action_space.n) if (word >> a) & 1]
         assert len(actions) > 0
         return actions
 

@@ -260,13 +260,19 @@ int pomdp_network_step_packed(const PomdpNetworkParams* params,
  * it wants (next_state, result) back in host memory (the loop around env.step at rock.py:563-572 with the
  * arrays of a whole particle set).  pomdp_step_packed_host is pomdp_E_step_packed for HOST pointers: the
  * batch is cut into chunks, and for every chunk the H2D copies, the step kernel and the D2H copies are
- * queued on one of the pipe's streams, so the copies of neighbouring chunks run on both PCIe directions
- * while the kernels (microseconds) hide under them.  Returns when every result has landed.  Results are
- * identical to one pomdp_E_step_packed call over the whole batch (Philox is keyed by the global index).
+ * queued on the pipe's three streams (one per engine: copies in, kernels, copies out; events order a
+ * chunk's three stages and guard the reuse of its staging slot), so the copies of neighbouring chunks run
+ * on both PCIe directions while the kernels (microseconds) hide under them.  Returns when every result
+ * has landed.  Results are identical to one pomdp_E_step_packed call over the whole batch (Philox is keyed
+ * by the global index).
  *
- *  - pipe: device staging buffers ((2 * state_words + 2) * chunk_envs * 4 bytes per slot) and one stream
- *    per slot, created once and reused; chunk_envs must be a positive multiple of 4, 1 <= n_slots <= 8.
- *    A pipe belongs to the device that was current at creation and is not thread-safe.
+ *  - pipe: device staging buffers ((2 * state_words + 2) * chunk_envs * 4 bytes per slot), three streams
+ *    and three events per slot, created once and reused; chunk_envs must be a positive multiple of 4,
+ *    1 <= n_slots <= 8.  A pipe belongs to the device that was current at creation -- the call switches to
+ *    it and restores the caller's current device on return -- and is not thread-safe.
+ *  - the host buffers must be HOST-COMPLETE when the call is made: it runs on the pipe's own non-blocking
+ *    streams and does not order itself after work the caller has queued on other streams (an asynchronous
+ *    copy into h_state, a table upload still in flight: synchronize those first).
  *  - kind: POMDP_KIND_ROCK / TAG / TIGER / NETWORK; params points at the matching PomdpEParams; d_table as
  *    for pomdp_E_step_packed (NULL for Tiger / Network), fully built before the call.
  *  - host pointers should be page-locked (cudaHostAlloc / cudaHostRegister): pageable memory is still
@@ -382,6 +388,65 @@ int pomdp_rock_belief_update(const PomdpRockParams* params, const void* d_table,
                              const int32_t* next_state, const int32_t* action, const int32_t* obs,
                              int32_t* count, int32_t* measured, double* lkv, double* lkw, double* prob_valuable,
                              int64_t n, void* stream);
+
+/* ------------------------------------------------- heuristic action sets and rollouts --- */
+/* RockEnv._generate_preferred(history) rock.py:293-374 (with use_heuristic=True) and the rollout loop that draws from
+ * it, rock.py:557-572; TagEnv._generate_preferred(history) tag.py:231-243.
+ *
+ * RockSample.  The reference recomputes, from the caller's History on every call, two totals per rock over the
+ * transitions whose action checked that rock (rock.py:302-309 and 325-331); here they are running sums in one int32
+ * plane `check_totals[n, num_rocks]` (low 16 bits: #GOOD - #BAD of `next_observation`; high 16 bits:
+ * #(next_observation == GOOD) - #(next_observation != GOOD and observation == BAD), both signed), advanced by
+ * pomdp_rock_history_update with the two fields exactly as the caller's Transition holds them.  The belief
+ * side-statistics it also reads (count, measured, prob_valuable) are the planes of pomdp_rock_belief_update.
+ * Any plane pointer may be NULL = its fresh value (Rock.__init__ rock.py:78-86; an empty history).
+ *   pomdp_rock_preferred_mask    out[i] = the preferred set as a bit mask over action ids (the reference's lists are in
+ *                                increasing action order), 0 = the list came out empty and the reference returns
+ *                                _generate_legal() (rock.py:372-373).  A dangling grid id under the agent
+ *                                (Rock(15,15), Rock(7,7): IndexError at rock.py:301) counts as "no rock".
+ *   pomdp_rock_policy_preferred  action[i] = np.random.choice(that list) (or of _generate_legal()), u from draw slot 0 of
+ *                                the POLICY domain at step_ctr, like pomdp_rock_policy.
+ *   pomdp_rock_rollout_preferred the whole loop for up to max_steps steps in one kernel (one thread per env, planes in
+ *                                local memory): planes that are passed are read at the start and updated in place.
+ *                                next_is_reward != 0: the transition's `next_observation` field holds the REWARD, which is
+ *                                what the reference's own loop stores (positional Transition(ob, action, next_ob, rw,
+ *                                done) against the field order (observation, action, reward, next_observation, done),
+ *                                rock.py:525-530, 566); 0: it holds the next observation.                      */
+typedef struct PomdpRockHeuristicPlanes {
+    int32_t* count;          /* [n, num_rocks]  rock.py:83 */
+    int32_t* measured;       /* [n, num_rocks]  rock.py:84 */
+    double*  lkv;            /* [n, num_rocks]  rock.py:86 */
+    double*  lkw;            /* [n, num_rocks]  rock.py:85 */
+    double*  prob_valuable;  /* [n, num_rocks]  rock.py:87 */
+    int32_t* check_totals;   /* [n, num_rocks]  see above */
+    int32_t* prev_obs;       /* [n] the observation the next transition records as `observation` (reset: 0) */
+} PomdpRockHeuristicPlanes;
+int pomdp_rock_history_update(const PomdpRockParams* params, const int32_t* observation_field, const int32_t* action,
+                              const int32_t* next_observation_field, int32_t* check_totals, int64_t n, void* stream);
+int pomdp_rock_preferred_mask(const PomdpRockParams* params, const void* d_table, const int32_t* state,
+                              const int32_t* count, const int32_t* measured, const double* prob_valuable,
+                              const int32_t* check_totals, uint32_t* mask, int64_t n, void* stream);
+int pomdp_rock_policy_preferred(const PomdpRockParams* params, const void* d_table, const int32_t* state,
+                                const int32_t* count, const int32_t* measured, const double* prob_valuable,
+                                const int32_t* check_totals, int32_t* action, int64_t n, int64_t global_offset,
+                                uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_rock_rollout_preferred(const PomdpRockParams* params, const void* d_table, const int32_t* state,
+                                 const int32_t* first_action, const PomdpRockHeuristicPlanes* planes /* may be NULL */,
+                                 int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                                 int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                                 int32_t max_steps, double discount, int32_t next_is_reward, void* stream);
+/* Tag: the set depends on the last (observation, action) of the history only.  last_action[i] < 0 (or a NULL array) = an
+ * empty history.  The rollout updates last_obs / last_action in place when they are passed.                    */
+int pomdp_tag_preferred_mask(const PomdpTagParams* params, const void* d_table, const int32_t* state,
+                             const int32_t* last_obs, const int32_t* last_action, uint32_t* mask, int64_t n, void* stream);
+int pomdp_tag_policy_preferred(const PomdpTagParams* params, const void* d_table, const int32_t* state,
+                               const int32_t* last_obs, const int32_t* last_action, int32_t* action,
+                               int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr, void* stream);
+int pomdp_tag_rollout_preferred(const PomdpTagParams* params, const void* d_table, const int32_t* state,
+                                int32_t* last_obs, int32_t* last_action, const int32_t* first_action,
+                                int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
+                                int64_t n, int64_t global_offset, uint64_t seed, uint32_t step_ctr,
+                                int32_t max_steps, double discount, void* stream);
 
 /* ------------------------------------------------------------ Grid / Coord helpers --- */
 /* coord.py:7-114 and tag.py:36-66 as batched device functions (bit-exact integer work).

@@ -248,6 +248,177 @@ def gen_rock_stats(E, out, tag, n, k, stochastic, M, T):
     print(tag, "nan prob_valuable entries:", int(np.isnan(rec["prob_valuable"]).sum()), "min lkv", rec["lkv"][alive].min())
 
 
+def gen_rock_heur(E, out, tag, n, k, stochastic, M, T, positional):
+    """Heuristic rollouts (rock.py:557-572 with use_heuristic=True) played by the unmodified reference: its own
+    History / Transition classes, ``np.random.choice(env._generate_preferred(history))`` scripted from the POLICY word.
+    positional: transitions are built as the reference's own loop builds them, Transition(ob, action, next_ob, rw, done)
+    (rock.py:566), which puts the reward into ``next_observation``; otherwise by field name.  Recorded per step: the
+    preferred list (as a bit mask over action ids; the lists are in increasing action order) and whether it was the
+    fallback to _generate_legal(), the action, the observation; per episode the return, steps and the final state."""
+    import gym_pomdp.envs.rock as R
+    d = ref_shim.draws()
+    env = (E.StochasticRockEnv if stochastic else E.RockEnv)(n, k, use_heuristic=True)
+    res = {key: [] for key in ("x0", "y0", "st0", "ret", "steps", "done", "x1", "y1", "st1")}
+    masks, fallback, acts, obs = (-np.ones((M, T), np.int64) for _ in range(4))
+    n_sample_branch = n_east_branch = n_fallback = 0
+    for e in range(M):
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, 1)
+        d.clear(); d.feed([rock_reset_word(int(rw[0]), r) for r in range(k)])
+        ob = env.reset()
+        d.clear()
+        res["x0"].append(env.state.agent_pos.x); res["y0"].append(env.state.agent_pos.y)
+        res["st0"].append([r.status for r in env.state.rocks])
+        history = R.History()
+        r, disc, t, done = 0.0, 1.0, 0, False
+        while t < T and not done:
+            ctr = FIRST_CTR + t
+            calls = []
+            orig_legal = env._generate_legal
+            env._generate_legal = lambda: (calls.append(1), orig_legal())[1]     # with use_heuristic it is only reached by the
+            pref = env._generate_preferred(history)                              # fallback `return self._generate_legal()`
+            env._generate_legal = orig_legal
+            is_fb = bool(calls)
+            masks[e, t] = sum(1 << int(a) for a in set(pref))
+            fallback[e, t] = int(is_fb)
+            n_fallback += int(is_fb)
+            n_sample_branch += int(list(pref) == [4])
+            n_east_branch += int(list(pref) == [1])
+            d.clear(); d.feed([W(e, ctr, philox.DOMAIN_POLICY, 1)[0]])
+            a = int(np.random.choice(pref))
+            d.clear()
+            w = W(e, ctr, philox.DOMAIN_STEP, 2)
+            d.feed([w[0], w[1]] if stochastic else [w[1]])
+            next_ob, rw_, done, info = env.step(a)
+            d.clear()
+            if positional:
+                history.append(R.Transition(ob, a, next_ob, rw_, done))           # rock.py:566 as written
+            else:
+                history.append(R.Transition(observation=ob, action=a, reward=rw_, next_observation=next_ob, done=done))
+            ob = next_ob
+            acts[e, t], obs[e, t] = a, next_ob
+            r += rw_ * disc
+            disc *= env._discount
+            t += 1
+        res["ret"].append(r); res["steps"].append(t); res["done"].append(bool(done))
+        res["x1"].append(env.state.agent_pos.x); res["y1"].append(env.state.agent_pos.y)
+        res["st1"].append([r_.status for r_ in env.state.rocks])
+    for key in res:
+        out[f"{tag}_{key}"] = np.array(res[key])
+    out[f"{tag}_mask"], out[f"{tag}_fallback"], out[f"{tag}_acts"], out[f"{tag}_obs"] = masks, fallback, acts.astype(np.int32), obs.astype(np.int32)
+    out[f"{tag}_cfg"] = np.array([n, k, int(stochastic), T, int(positional)])
+    out[f"{tag}_discount"] = env._discount
+    print(tag, "mean steps", np.mean(res["steps"]), "done", int(np.sum(res["done"])), "mean ret", np.mean(res["ret"]),
+          "[SAMPLE]-only", n_sample_branch, "[EAST]-only", n_east_branch, "fallbacks", n_fallback)
+
+
+class _TagHistory(object):
+    """The History the reference's Tag loop expects (tag.py:303-313: ``history.append(action, ob)``, ``.size``,
+    ``history[-1].ob`` / ``.action``); its module gym_pomdp.envs.history is not part of the repository."""
+
+    class _E(object):
+        def __init__(self, action, ob):
+            self.action, self.ob = action, ob
+
+    def __init__(self):
+        self._h = []
+
+    def append(self, action, ob):
+        self._h.append(self._E(action, ob))
+
+    def __getitem__(self, i):
+        return self._h[i]
+
+    @property
+    def size(self):
+        return len(self._h)
+
+
+def gen_tag_heur(E, out, tag, n_opp, M, T):
+    """tag.py:303-316 with ``env._generate_preferred(history)`` as the policy."""
+    d = ref_shim.draws()
+    env = E.TagEnv(num_opponents=n_opp)
+    g = env.grid
+    orig_move = env.move_opponent
+    cur = {}
+
+    def move_opponent(opp):
+        d.clear(); d.feed([cur["w"][2 * opp], cur["w"][2 * opp + 1]])
+        orig_move(opp)
+        d.clear()
+    env.move_opponent = move_opponent
+    res = {key: [] for key in ("agent0", "opp0", "ob0", "ret", "steps", "done", "agent1", "opp1", "nopp1")}
+    masks, acts, obs = (-np.ones((M, T), np.int64) for _ in range(3))
+    n_tag_only = 0
+    for e in range(M):
+        rw = W(e, RESET_CTR, philox.DOMAIN_RESET, (1 + n_opp + 2) // 3)
+        d.clear(); d.feed([tag_reset_word(int(rw[j // 3]), j % 3) for j in range(1 + n_opp)])
+        ob0 = env.reset()
+        d.clear()
+        res["agent0"].append(g.get_index(env.state.agent_pos)); res["opp0"].append([g.get_index(o) for o in env.state.opponent_pos])
+        res["ob0"].append(ob0)
+        history = _TagHistory()
+        r, disc, t, done = 0.0, 1.0, 0, False
+        while t < T and not done:
+            ctr = FIRST_CTR + t
+            pref = env._generate_preferred(history)
+            masks[e, t] = sum(1 << int(a) for a in pref)
+            n_tag_only += int(list(pref) == [4])
+            d.clear(); d.feed([W(e, ctr, philox.DOMAIN_POLICY, 1)[0]])
+            a = int(np.random.choice(pref))
+            d.clear()
+            cur["w"] = W(e, ctr, philox.DOMAIN_STEP, 2 * n_opp)
+            ob, rw_, done, info = env.step(a)
+            d.clear()
+            history.append(a, ob)
+            acts[e, t], obs[e, t] = a, ob
+            r += rw_ * disc
+            disc *= env._discount
+            t += 1
+        res["ret"].append(r); res["steps"].append(t); res["done"].append(bool(done))
+        res["agent1"].append(g.get_index(env.state.agent_pos)); res["opp1"].append([g.get_index(o) for o in env.state.opponent_pos])
+        res["nopp1"].append(env.state.num_opp)
+    for key in res:
+        out[f"{tag}_{key}"] = np.array(res[key])
+    out[f"{tag}_mask"], out[f"{tag}_acts"], out[f"{tag}_obs"] = masks, acts.astype(np.int32), obs.astype(np.int32)
+    out[f"{tag}_cfg"] = np.array([n_opp, T])
+    out[f"{tag}_discount"] = env._discount
+    print(tag, "mean steps", np.mean(res["steps"]), "done", int(np.sum(res["done"])), "mean ret", np.mean(res["ret"]), "[TAG]-only", n_tag_only)
+
+
+def main_heur():
+    E = ref_shim.load_reference()
+    out = {"seed": SEED, "reset_ctr": RESET_CTR, "first_ctr": FIRST_CTR}
+    with ref_shim.scripted_numpy():
+        gen_rock_heur(E, out, "rock_7_8_fields", 7, 8, False, 96, 80, False)
+        gen_rock_heur(E, out, "rock_7_8_main", 7, 8, False, 96, 80, True)
+        gen_rock_heur(E, out, "rock_11_11_fields", 11, 11, False, 64, 100, False)
+        gen_rock_heur(E, out, "rock_11_11_main", 11, 11, False, 64, 100, True)
+        gen_rock_heur(E, out, "rock_4_3_fields", 4, 3, False, 64, 60, False)
+        gen_rock_heur(E, out, "srock_7_8_fields", 7, 8, True, 64, 80, False)
+        gen_tag_heur(E, out, "tag_1opp", 1, 96, 90)
+        gen_tag_heur(E, out, "tag_2opp", 2, 48, 90)
+    # RockEnv._select_target (rock.py:389-399) on random rock states of Rock(11,11)
+    from gym_pomdp.envs.coord import Coord
+    from gym_pomdp.envs.rock import config
+    rs = np.random.RandomState(77)
+    N = 400
+    ax, ay = rs.randint(0, 11, N), rs.randint(0, 11, N)
+    status, count = rs.randint(-1, 2, (N, 11)), rs.randint(-2, 3, (N, 11))
+    tgt = []
+    for i in range(N):
+        st = type("S", (), {})()
+        st.agent_pos = Coord(int(ax[i]), int(ay[i]))
+        st.rocks = []
+        for j in range(11):
+            r = type("R", (), {})()
+            r.status, r.count, r.pos = int(status[i, j]), int(count[i, j]), Coord(*config[11]["rock_pos"][j])
+            st.rocks.append(r)
+        tgt.append(E.RockEnv._select_target(st, 11))
+    out.update(select_ax=ax, select_ay=ay, select_status=status, select_count=count, select_target=np.array(tgt))
+    np.savez_compressed(os.path.join(GOLDEN, "heuristic_rollouts.npz"), **out)
+    print("wrote heuristic_rollouts.npz")
+
+
 def main_stats():
     E = ref_shim.load_reference()
     out = {"seed": SEED, "reset_ctr": RESET_CTR, "first_ctr": FIRST_CTR}
@@ -260,6 +431,10 @@ def main_stats():
 
 
 if __name__ == "__main__":
-    if "--stats-only" not in sys.argv:
-        main()
-    main_stats()
+    if "--heur-only" in sys.argv:
+        main_heur()
+    else:
+        if "--stats-only" not in sys.argv:
+            main()
+            main_heur()
+        main_stats()

@@ -669,6 +669,151 @@ int pomdp_rock_belief_update(const PomdpRockParams* q, const void* table, const 
     return 0;
 }
 
+// ---- heuristic action sets and rollouts: the functors the kernels inline (pomdp_core.h / pomdp_envs.h)
+int pomdp_rock_history_update(const PomdpRockParams* q, const int32_t* obs_field, const int32_t* action,
+                              const int32_t* next_obs_field, int32_t* check_totals, int64_t n, void*) {
+    int rc = host::make_rock(q, nullptr, nullptr);
+    if (rc) return rc;
+    if (n < 0) return host::fail(POMDP_E_BADARG, "pomdp_rock_history_update: n is negative");
+    if (n > 0 && (!obs_field || !action || !next_obs_field || !check_totals))
+        return host::fail(POMDP_E_BADARG, "pomdp_rock_history_update: a required array pointer is NULL");
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t a = action[i];
+        if (a < 5 || a >= 5 + q->num_rocks) continue;
+        const int64_t j = i * q->num_rocks + (a - 5);
+        int32_t ts = rock_totals_sample(check_totals[j]), td = rock_totals_dir(check_totals[j]);
+        rock_history_update(a, obs_field[i], next_obs_field[i], ts, td);
+        check_totals[j] = rock_totals_pack(ts, td);
+    }
+    return 0;
+}
+extern "C++" {
+namespace {
+template <typename S>
+void rock_preferred_host(const RockDev& d, const void* table, const int32_t* state, const int32_t* count, const int32_t* measured,
+                         const double* pv, const int32_t* totals, int32_t* out, int64_t n, bool policy, int64_t goff, uint64_t seed,
+                         uint32_t step) {
+    const RockTableHdr* hdr = (const RockTableHdr*)table;
+    const RockLut* lut = (const RockLut*)((const char*)table + ROCK_LUT_OFFSET);
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        const RockPlanesView h = {count, measured, pv, totals, i * d.k};
+        const S s = load_state<S>(state, i);
+        out[i] = policy ? rock_policy_preferred<S>(d, hdr, lut, s, h, draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0))
+                        : (int32_t)rock_preferred_mask<S>(d, hdr, s, h);
+    }
+}
+int rock_preferred_entry(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* count,
+                         const int32_t* measured, const double* pv, const int32_t* totals, int32_t* out, int64_t n, bool policy,
+                         int64_t goff, uint64_t seed, uint32_t step, const char* what) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, out, n, goff, what))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    if (host::rock_words(q) == 1) rock_preferred_host<uint32_t>(d, table, state, count, measured, pv, totals, out, n, policy, goff, seed, step);
+    else rock_preferred_host<uint64_t>(d, table, state, count, measured, pv, totals, out, n, policy, goff, seed, step);
+    return 0;
+}
+template <typename S, bool STOCH>
+void rock_rollout_preferred_host(const RockDev& d, const void* table, const int32_t* state, const int32_t* first_action,
+                                 const RockPlanesPtr& pl, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags, int64_t n,
+                                 int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps, double gamma, bool next_is_reward) {
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        RockHeurLocal h;
+        h.load(pl, i * d.k, d.k);
+        int32_t prev_ob = pl.prev_obs ? pl.prev_obs[i] : 0;
+        S s = load_state<S>(state, i);
+        RolloutAcc acc;
+        rock_rollout_preferred1<S, STOCH>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma,
+                                          next_is_reward, first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        if (final_state) store_state(final_state, i, s);
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
+        h.store(pl, i * d.k, d.k);
+        if (pl.prev_obs) pl.prev_obs[i] = prev_ob;
+    }
+}
+}  // namespace
+}  // extern "C++"
+int pomdp_rock_preferred_mask(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* count,
+                              const int32_t* measured, const double* pv, const int32_t* totals, uint32_t* mask, int64_t n, void*) {
+    return rock_preferred_entry(q, table, state, count, measured, pv, totals, (int32_t*)mask, n, false, 0, 0, 0, "pomdp_rock_preferred_mask");
+}
+int pomdp_rock_policy_preferred(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* count,
+                                const int32_t* measured, const double* pv, const int32_t* totals, int32_t* action, int64_t n,
+                                int64_t goff, uint64_t seed, uint32_t step, void*) {
+    return rock_preferred_entry(q, table, state, count, measured, pv, totals, action, n, true, goff, seed, step, "pomdp_rock_policy_preferred");
+}
+int pomdp_rock_rollout_preferred(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* first_action,
+                                 const PomdpRockHeuristicPlanes* planes, int32_t* final_state, double* ret, int32_t* steps,
+                                 int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
+                                 double discount, int32_t next_is_reward, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, "pomdp_rock_rollout_preferred"))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (planes) { pl.count = planes->count; pl.measured = planes->measured; pl.lkv = planes->lkv; pl.lkw = planes->lkw;
+                  pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs; }
+#define HS_RRP(S, ST) rock_rollout_preferred_host<S, ST>(d, table, state, first_action, pl, final_state, ret, steps, flags, n, goff, seed, \
+                                                         step, max_steps, discount, next_is_reward != 0)
+    if (host::rock_words(q) == 1) { if (d.stochastic) HS_RRP(uint32_t, true); else HS_RRP(uint32_t, false); }
+    else { if (d.stochastic) HS_RRP(uint64_t, true); else HS_RRP(uint64_t, false); }
+#undef HS_RRP
+    return 0;
+}
+int pomdp_tag_preferred_mask(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* last_obs,
+                             const int32_t* last_action, uint32_t* mask, int64_t n, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, mask, n, 0, "pomdp_tag_preferred_mask"))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
+    for (int64_t i = 0; i < n; ++i)
+        mask[i] = tag_preferred_mask((const TagTables*)table, (uint32_t)state[i], last_obs ? last_obs[i] : 0, last_action ? last_action[i] : -1);
+    return 0;
+}
+int pomdp_tag_policy_preferred(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* last_obs,
+                               const int32_t* last_action, int32_t* action, int64_t n, int64_t goff, uint64_t seed, uint32_t step, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, action, n, goff, "pomdp_tag_policy_preferred"))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i)
+        action[i] = tag_policy_preferred((const TagTables*)table, (uint32_t)state[i], last_obs ? last_obs[i] : 0,
+                                         last_action ? last_action[i] : -1, draw_word(key, (uint64_t)(goff + i), step, DOMAIN_POLICY, 0));
+    return 0;
+}
+int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* table, const int32_t* state, int32_t* last_obs,
+                                int32_t* last_action, const int32_t* first_action, int32_t* final_state, double* ret, int32_t* steps,
+                                int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps,
+                                double discount, void*) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, "pomdp_tag_rollout_preferred"))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "tag: table is NULL");
+    const PhiloxKey key = philox_key(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t s = (uint32_t)state[i];
+        int32_t lo = last_obs ? last_obs[i] : 0, la = last_action ? last_action[i] : -1;
+        RolloutAcc acc;
+        if (d.n_opp == 1) tag_rollout_preferred1<1>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, discount,
+                                                     first_action != nullptr, first_action ? first_action[i] : 0, lo, la, acc);
+        else tag_rollout_preferred1<4>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, discount,
+                                       first_action != nullptr, first_action ? first_action[i] : 0, lo, la, acc);
+        if (final_state) final_state[i] = (int32_t)s;
+        ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
+        if (last_obs) last_obs[i] = lo;
+        if (last_action) last_action[i] = la;
+    }
+    return 0;
+}
+
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
     const int rc = host::check_coord_op(op, xs, a, b, out, n);
     if (rc) return rc;
