@@ -120,6 +120,7 @@ _PROTOTYPES = {
     "pomdp_network_obs_prob": (c_int32, [POINTER(NetworkParams), _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_network_legal_mask": (c_int32, [POINTER(NetworkParams), _P, _P, c_int64, c_void_p]),
     "pomdp_rock_belief_update": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_rock_legal_list": (c_int32, [POINTER(RockParams), _P, _P, _P, c_int64, c_void_p]),
     "pomdp_rock_history_update": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_rock_preferred_mask": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_rock_policy_preferred": (c_int32, [POINTER(RockParams), _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64,
@@ -171,11 +172,15 @@ def is_hostsim():
 
 
 def _inject_for_tests(path):
-    """TESTS ONLY: bind the g++-compiled host simulation of the kernels instead."""
+    """TESTS ONLY: bind the g++-compiled host simulation of the kernels instead.  Refused outside a pytest run (pytest
+    sets PYTEST_CURRENT_TEST for the duration of every test; worker processes a test spawns inherit it), so no product
+    process can end up on a CPU library."""
     global _lib, _is_hostsim
     if path is None:
         _lib, _is_hostsim = None, False
         return
+    if "PYTEST_CURRENT_TEST" not in os.environ:
+        raise RuntimeError("_inject_for_tests is only available inside a pytest run; gym_pomdp_b200 has no CPU path")
     cand = _bind(path)
     assert hasattr(cand, "pomdp_is_hostsim"), "refusing to inject a library that is not the hostsim"
     _lib, _is_hostsim = cand, True

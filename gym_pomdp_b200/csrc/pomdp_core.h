@@ -598,6 +598,72 @@ POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_
     rw = reward;
 }
 
+// tag_step for the FOUR envs of one draw group with 2..4 opponents: the opponents are walked in the outer loop, so only
+// the two draw blocks of the current opponent (slots 2j, 2j+1; one Philox call each for the four envs) are live at a
+// time -- precomputing all eight blocks (32 words) spilled registers.  Same semantics, env by env, as tag_step.
+POMDP_HD void tag_step4_multi(const TagDev& p, const TagTables* __restrict__ T, const uint32_t s[4], const int32_t a[4],
+                              const PhiloxKey& seed, uint64_t group, uint32_t step, uint32_t s2[4], int32_t ob[4], float rw[4],
+                              int32_t fl[4]) {
+    int32_t err[4], nopp[4];
+    bool tagged[4];
+    POMDP_UNROLL
+    for (int e = 0; e < 4; ++e) {
+        s2[e] = s[e];
+        bool bad = (s[e] & 31u) >= (uint32_t)TAG_CELLS;
+        for (int j = 0; j < p.n_opp; ++j) bad = bad || ((s[e] >> (5 + 5 * j)) & 31u) >= (uint32_t)TAG_CELLS;
+        err[e] = (s[e] & TAG_DONE) ? (int32_t)(FLAG_DONE | FLAG_STEPPED_DONE)                    // tag.py:110
+                 : ((uint32_t)a[e] >= 5u) ? (int32_t)FLAG_BAD_ACTION                             // tag.py:109
+                 : bad ? (int32_t)FLAG_BAD_STATE : 0;                                            // tag.py:116-117
+        nopp[e] = tag_num_opp(s[e]);
+        tagged[e] = false;
+    }
+    for (int j = 0; j < p.n_opp; ++j) {                                                          // tag.py:119-131
+        const bool any_tag = (a[0] == 4 && !err[0]) || (a[1] == 4 && !err[1]) || (a[2] == 4 && !err[2]) || (a[3] == 4 && !err[3]);
+        if (!any_tag) break;
+        const U4 qm = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)(2 * j));
+        const U4 qp = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)(2 * j + 1));
+        const int sh = 5 + 5 * j;
+        POMDP_UNROLL
+        for (int e = 0; e < 4; ++e) {
+            if (err[e] || a[e] != 4) continue;
+            const uint32_t agent = s[e] & 31u;
+            const uint32_t o = (s2[e] >> sh) & 31u;
+            if (o == agent) {
+                tagged[e] = true;
+                --nopp[e];
+            } else if (nopp[e] > 0) {                                                            // tag.py:128
+                const uint32_t en = T->pair[o * 32u + agent];
+                if (bern(word_of(qm, e), p.move_T)) {                                            // tag.py:204
+                    const uint32_t pick = rand_below(word_of(qp, e), en >> 20);                  // tag.py:205
+                    s2[e] = (s2[e] & ~(31u << sh)) | (((en >> (5u * pick)) & 31u) << sh);        // tag.py:206-207
+                }
+            }
+        }
+    }
+    POMDP_UNROLL
+    for (int e = 0; e < 4; ++e) {
+        if (err[e]) { s2[e] = s[e]; ob[e] = 0; rw[e] = 0.f; fl[e] = err[e]; continue; }
+        uint32_t agent = s[e] & 31u;
+        float reward;
+        if (a[e] == 4) {
+            reward = tagged[e] ? 10.f : -10.f;
+        } else {                                                                                 // tag.py:133-137
+            reward = -1.f;
+            agent = (T->mv[agent] >> (5 * a[e])) & 31u;
+            s2[e] = (s2[e] & ~31u) | agent;
+        }
+        int32_t o_ = (int32_t)agent;                                                             // tag.py:219-226
+        if (a[e] < 4)
+            for (int j = 0; j < p.n_opp; ++j)
+                if (((s2[e] >> (5 + 5 * j)) & 31u) == agent) o_ = TAG_CELLS;
+        s2[e] = tag_set_num_opp(s2[e], nopp[e]);
+        fl[e] = 0;
+        if (nopp[e] == 0) { s2[e] |= TAG_DONE; fl[e] = FLAG_DONE; }                              // tag.py:142
+        ob[e] = o_;
+        rw[e] = reward;
+    }
+}
+
 // tag.py:97-102, 181-193: the reference draws 1 + n_opp cells with np.random.randint(29) (agent first, then each
 // opponent); ob = _sample_ob(state, 0).  The j-th of those draws (j = 0 agent, 1 + i opponent i) is the (j % 3)-th
 // base-29 DIGIT of the uniform u = w / 2^32 of reset slot j / 3:  floor(frac(u * 29^d) * 29), i.e. randint's rule

@@ -106,10 +106,7 @@ struct TagEnvT {
             tag_step_1opp(p, T, s[3], a[3], qm.w, qp.w, s2[3], ob[3], rw[3], fl[3]);
             return;
         }
-        WordDraw<2 * NOPP> d[4];
-        quad_words<2 * NOPP>(seed, group, ctr, DOMAIN_STEP, 2 * p.n_opp, d);
-        POMDP_UNROLL
-        for (int j = 0; j < 4; ++j) tag_step(p, T, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
+        tag_step4_multi(p, T, s, a, seed, group, ctr, s2, ob, rw, fl);
     }
     static POMDP_HD void step1(const Params& p, const unsigned char* tbl, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,

@@ -478,6 +478,19 @@ pomdp_legal_mask_kernel(const __grid_constant__ typename Env::Params p, const vo
         if (words > 1) mask[i * words + 1] = m[1];
     }
 }
+// rock.py:273-291 in the reference's list order (pomdp_core.h: rock_legal_list)
+template <typename S>
+__global__ void __launch_bounds__(POMDP_THREADS)
+pomdp_rock_legal_list_kernel(const __grid_constant__ RockDev p, const void* __restrict__ g_table, const int32_t* __restrict__ state,
+                             uint32_t* __restrict__ list, int64_t n, uint32_t table_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    stage_table_sync<RockEnvT<S, false>>(smem_table, g_table, table_bytes, &bar);
+    const RockLut* lut = reinterpret_cast<const RockLut*>(smem_table + ROCK_LUT_OFFSET);
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads)
+        list[i] = rock_legal_list<S>(p, lut, load_state1(state, i, S()));
+}
 // Rock belief side-statistics (rock.py:177-191): one thread per env touches the one rock its check action read.
 template <typename S>
 __global__ void __launch_bounds__(POMDP_THREADS)
@@ -1824,6 +1837,26 @@ int pomdp_rock_legal_mask(const PomdpRockParams* q, const void* d_table, const i
     POMDP_ROCK_DISPATCH2(launch_legal_mask, d, d_table, d.table_bytes, d.smem_bytes, state, mask, n, stream, "pomdp_rock_legal_mask");
 }
 #undef POMDP_ROCK_DISPATCH2
+int pomdp_rock_legal_list(const PomdpRockParams* q, const void* d_table, const int32_t* state, uint32_t* list, int64_t n,
+                          void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, list, n, 0, "pomdp_rock_legal_list"))) return rc;
+    if (n == 0) return 0;
+    if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "pomdp_rock_legal_list: d_table must be a 16-byte aligned device pointer");
+    const size_t smem = d.smem_bytes;
+    if (host::rock_words(q) == 1) {
+        auto k = pomdp_rock_legal_list_kernel<uint32_t>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(d, d_table, state, list, n, d.table_bytes);
+    } else {
+        auto k = pomdp_rock_legal_list_kernel<uint64_t>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(d, d_table, state, list, n, d.table_bytes);
+    }
+    return finish("pomdp_rock_legal_list");
+}
 int pomdp_tag_obs_prob(const PomdpTagParams* q, const int32_t* next_state, const int32_t* action, const int32_t* obs,
                        double* prob, int64_t n, void* stream) {
     TagDev d;

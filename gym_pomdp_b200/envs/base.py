@@ -21,19 +21,32 @@ on caller-owned particle tensors: what a POMCP / particle-filter caller does wit
 ``_set_state(s); step(a)`` in a Python loop, as one launch.
 """
 import ctypes
+import os
 
 import torch
 
 from .. import _lib
 
 
-try:  # pragma: no cover - neither package is in the build image
-    from gym import Env as _EnvBase                     # the reference's envs subclass gym.Env (rock.py:5, 96)
-except Exception:  # noqa: BLE001
-    try:
-        from gymnasium import Env as _EnvBase
+def _env_base():
+    """The reference's envs subclass gym.Env (rock.py:5, 96) and speak the OLD gym protocol (reset() -> ob; four values from
+    step).  Subclass gym.Env only where that protocol is gym's own (gym < 0.26); newer gym / gymnasium get an adapter
+    around these classes instead (registration.NewApiAdapter), because their wrappers call reset(seed=, options=)."""
+    try:  # pragma: no cover - gym is not in the build image
+        import gym
+        from ..registration import uses_new_api
+        if not uses_new_api("gym", gym):
+            return gym.Env
     except Exception:  # noqa: BLE001
-        _EnvBase = object
+        pass
+    return object
+
+
+_EnvBase = _env_base()
+
+
+def _fresh_seed():
+    return int.from_bytes(os.urandom(8), "little")
 
 
 def _as_device(device):
@@ -45,7 +58,7 @@ class BatchedPomdpEnv(_EnvBase):
     kind = -1            # POMDP_KIND_* for the belief histogram
     state_words = 1      # int32 words per instance
 
-    def __init__(self, batch_size=None, device="cuda", seed=0, global_offset=0):
+    def __init__(self, batch_size=None, device="cuda", seed=None, global_offset=0):
         self._scalar = batch_size is None
         self.batch_size = 1 if self._scalar else int(batch_size)
         if self.batch_size < 0:
@@ -56,7 +69,10 @@ class BatchedPomdpEnv(_EnvBase):
             raise RuntimeError("gym_pomdp_b200 runs on CUDA devices only (no CPU path); got device=%r" % (device,))
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        # The reference draws from numpy's unseeded global RNG, so two env objects are independent; a fixed default seed
+        # would make every default-constructed env replay the same rock layouts and sensor noise.  seed=None (the default)
+        # therefore draws a fresh 64-bit key; pass a seed (or call seed()) for reproducible runs.
+        self._seed = _fresh_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self._step_ctr = 0
         self.global_offset = int(global_offset)   # index of instance 0 in the global batch (multi-GPU shards)
         self.state = None
@@ -180,6 +196,10 @@ class BatchedPomdpEnv(_EnvBase):
 
     def simulate(self, state, action, out=None, step_ctr=None, packed=False):
         """G(s, a): one transition for every particle.
+
+        The draws of a call are a pure function of (seed, global env index, step_ctr): two calls with the same explicit
+        ``step_ctr`` repeat each other's randomness.  Leave ``step_ctr`` unset (the env's own counter advances) unless the
+        repetition is wanted (tests, common random numbers).
 
         state int32[n, words] (or [n] when words == 1), action int32[n].  Returns
         (next_state, obs, reward, flags); ``out`` may supply those four tensors
@@ -397,7 +417,7 @@ class BatchedPomdpEnv(_EnvBase):
     def seed(self, seed=None):
         """The reference seeds numpy's global RNG (e.g. rock.py:120-121); here the seed keys
         the stateless Philox stream and restarts the step counter."""
-        self._seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self._seed = _fresh_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self._step_ctr = 0
         return [seed]
 
@@ -426,7 +446,13 @@ class BatchedPomdpEnv(_EnvBase):
         """the scalar instance's packed state as unsigned Python ints"""
         return [int(w) & 0xFFFFFFFF for w in self._io_np[:self.state_words]]
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, seed=None, options=None):
+        """``reset() -> ob`` (the reference's protocol).  ``seed`` / ``options`` are accepted for callers written against
+        newer gym versions: a seed is applied through ``seed()``; options may carry ``{"mask": ...}``."""
+        if seed is not None:
+            self.seed(seed)
+        if mask is None and isinstance(options, dict):
+            mask = options.get("mask")
         if self._scalar:
             self._ensure_io()
             with self._guard():

@@ -32,7 +32,7 @@ class BattleShipEnv(BatchedPomdpEnv):
     _abi = "battleship"
     state_words = 8
 
-    def __init__(self, board_size=(5, 5), max_len=3, batch_size=None, device="cuda", seed=0, global_offset=0,
+    def __init__(self, board_size=(5, 5), max_len=3, batch_size=None, device="cuda", seed=None, global_offset=0,
                  reset_mode="table"):
         super().__init__(batch_size, device, seed, global_offset)
         self.grid = Grid(*board_size)
@@ -79,10 +79,10 @@ class BattleShipEnv(BatchedPomdpEnv):
             rc = fn(ctypes.byref(self._params), *tail)
         _lib.check(rc, "pomdp_battleship_reset")
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, seed=None, options=None):
         """battleship.py:131-137.  A (board, max_len) with no legal placement makes the reference's rejection loop spin
         forever; here the kernels flag it: scalar mode raises, batched mode ORs FLAG_BAD_STATE into ``flags``."""
-        obs = super().reset(mask)
+        obs = super().reset(mask, seed, options)
         rf = self.reset_flags
         if rf is not None:
             if self._scalar:
@@ -171,11 +171,6 @@ class BattleShipEnv(BatchedPomdpEnv):
 
     def _compute_prob(self, action, next_state, ob):
         """battleship.py:80-89"""
-        if self._scalar:
-            x, y = self.grid.get_coord(action)
-            if ob == 0 and next_state.visited[x][y]:
-                return 1
-            if ob == 1 and next_state.occupied[x][y]:
-                return 1
-            return int(ob == 0)
+        if self._scalar:                              # the same kernel, one particle: next_state is a ShipState
+            return float(self.observation_prob([int(action)], self._state_from_ref(next_state), [int(ob)])[0])
         return self.observation_prob(action, next_state, ob)

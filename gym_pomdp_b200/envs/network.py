@@ -20,7 +20,7 @@ class NetworkEnv(BatchedPomdpEnv):
     _abi = "network"
     _reward_unit = 10          # packed results carry the reward in tenths (network.py:104, 108)
 
-    def __init__(self, n_machines=10, problem_type=3, depth=60, batch_size=None, device="cuda", seed=0,
+    def __init__(self, n_machines=10, problem_type=3, depth=60, batch_size=None, device="cuda", seed=None,
                  global_offset=0):
         super().__init__(batch_size, device, seed, global_offset)
         self._p = 0.1
@@ -106,10 +106,8 @@ class NetworkEnv(BatchedPomdpEnv):
 
     def _compute_prob(self, action, next_state, ob):
         """network.py:43-55"""
-        if self._scalar:
-            if action < self._n_machines * 2:
-                return self._p_ob if next_state[action // 2] == ob else 1 - self._p_ob
-            return 1. if ob == NULL else 0
+        if self._scalar:                              # the same kernel, one particle: next_state is the int8[n] machine array
+            return float(self.observation_prob([int(action)], self._state_from_ref(next_state), [int(ob)])[0])
         return self.observation_prob(action, next_state, ob)
 
     @staticmethod

@@ -23,12 +23,15 @@ class RockBeliefStats(object):
     """Per-rock belief side-statistics of a batch (rock.py:78-86): ``count``, ``measured`` int32[n, k];
     ``lkv``, ``lkw``, ``prob_valuable`` float64[n, k].  Fresh values as in ``Rock.__init__``."""
 
-    def __init__(self, n, k, device):
-        self.count = torch.zeros((n, k), dtype=torch.int32, device=device)
-        self.measured = torch.zeros((n, k), dtype=torch.int32, device=device)
-        self.lkv = torch.ones((n, k), dtype=torch.float64, device=device)
-        self.lkw = torch.ones((n, k), dtype=torch.float64, device=device)
-        self.prob_valuable = torch.full((n, k), .5, dtype=torch.float64, device=device)
+    def __init__(self, n, k, device, pinned_host=False):
+        """pinned_host: page-locked HOST tensors the kernels update in place over PCIe (the single-instance mode keeps its
+        one env's planes there, next to its pinned state buffer)."""
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=device)
+        self.count = torch.zeros((n, k), dtype=torch.int32, **kw)
+        self.measured = torch.zeros((n, k), dtype=torch.int32, **kw)
+        self.lkv = torch.ones((n, k), dtype=torch.float64, **kw)
+        self.lkw = torch.ones((n, k), dtype=torch.float64, **kw)
+        self.prob_valuable = torch.full((n, k), .5, dtype=torch.float64, **kw)
 
     def reset(self, mask=None):
         """Back to the fresh values, for all envs or those selected by ``mask`` (bool[n])."""
@@ -107,7 +110,7 @@ class RockEnv(BatchedPomdpEnv):
     _abi = "rock"
     _stochastic = False
 
-    def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, batch_size=None, device="cuda", seed=0,
+    def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, batch_size=None, device="cuda", seed=None,
                  global_offset=0, p_move=0.8, track_belief_stats=False, track_history=False, history_next_is_reward=False):
         super().__init__(batch_size, device, seed, global_offset)
         # batched mode: keep rock.py's per-rock side-stats current; track_history also keeps the per-rock totals
@@ -136,13 +139,17 @@ class RockEnv(BatchedPomdpEnv):
         thr_m1 = host[272:400].view(np.uint32)
         self._eff_T = thr_m1.astype(np.int64) + 1                     # ceil(eff(d) * 2^32)
         self.grid = Grid(board_size, board_size)
+        for x in range(board_size):                                   # rock.py:110-111: rock ids in the board (later ids win)
+            for y in range(board_size):
+                self.grid.board[x, y] = self._grid_map[x | (y << 4)]
         self.action_space = Discrete(5 + num_rocks)                   # rock.py:113
         self.observation_space = Discrete(3)                          # rock.py:114
         self._discount = .95
         self._reward_range = 20
         self._penalization = 0 if self._stochastic else -100
         self._query = 0
-        self._side = None   # scalar mode: per-rock belief side-stats (rock.py:82-86)
+        self._sstats = None   # scalar mode: per-rock belief side-stats (rock.py:82-86) as pinned host planes the kernel updates
+        self._legal_act = host[400:432].copy()                        # list position of _generate_legal -> action id
 
     # -------------------------------------------------------------------- C calls ---
     def _c_head(self):
@@ -155,6 +162,14 @@ class RockEnv(BatchedPomdpEnv):
             ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state),
             _lib.ptr(obs), _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, self._stream()),
             "pomdp_rock_step")
+        if self._scalar and self._sstats is not None and next_state is self._io_next:
+            # the single instance's belief side-statistics (rock.py:177-191): the same kernel as in batched mode, queued
+            # behind the step on the same stream, on the pinned planes
+            st = self._sstats
+            _lib.check(_lib.lib().pomdp_rock_belief_update(
+                ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(next_state), _lib.ptr(action), _lib.ptr(obs),
+                _lib.ptr(st.count), _lib.ptr(st.measured), _lib.ptr(st.lkv), _lib.ptr(st.lkw), _lib.ptr(st.prob_valuable), 1,
+                self._stream()), "pomdp_rock_belief_update")
 
     def _c_reset(self, state, obs, mask, n, ctr):
         _lib.check(_lib.lib().pomdp_rock_reset(
@@ -298,8 +313,10 @@ class RockEnv(BatchedPomdpEnv):
         return torch.cat([idx[:, None], status], dim=1)
 
     # ---------------------------------------------------------------- scalar mode ---
-    def reset(self, mask=None):
-        obs = super().reset(mask)
+    def reset(self, mask=None, seed=None, options=None):
+        if mask is None and isinstance(options, dict):
+            mask = options.get("mask")
+        obs = super().reset(mask, seed)
         if self.track_belief_stats and not self._scalar:
             if self.belief_stats is None:
                 self.belief_stats = self.new_belief_stats()
@@ -330,7 +347,20 @@ class RockEnv(BatchedPomdpEnv):
         self._query = 0
         self.last_action = SAMPLE
         if self._scalar:
-            self._side = [dict(count=0, measured=0, lkw=1., lkv=1., prob_valuable=.5) for _ in range(self.num_rocks)]
+            if self._sstats is None:
+                self._sstats = RockBeliefStats(1, self.num_rocks, self.device, pinned_host=self.device.type == "cuda")
+            else:
+                self._sstats.reset()
+
+    @property
+    def _side(self):
+        """the single instance's per-rock side-statistics as the reference's Rock attributes (rock.py:82-86)"""
+        st = self._sstats
+        if st is None:
+            return None
+        c, m = st.count[0].tolist(), st.measured[0].tolist()
+        v, w, p = st.lkv[0].tolist(), st.lkw[0].tolist(), st.prob_valuable[0].tolist()
+        return [dict(count=c[i], measured=m[i], lkw=w[i], lkv=v[i], prob_valuable=p[i]) for i in range(self.num_rocks)]
 
     def _decode_py(self, words):
         """host ints -> (x, y, [status...])"""
@@ -346,12 +376,20 @@ class RockEnv(BatchedPomdpEnv):
                   "prob_valuable": side[i]["prob_valuable"]} for i in range(self.num_rocks)]
         return {"agent_pos": Coord(x, y), "rocks": rocks, "target": -1}
 
-    def _state_from_ref(self, state):
+    def _pack_ref(self, state):
         ax, ay = state["agent_pos"]
-        status = [[int(r["status"]) for r in state["rocks"]]]
-        self._side = [dict(count=r.get("count", 0), measured=r.get("measured", 0), lkw=r.get("lkw", 1.),
-                           lkv=r.get("lkv", 1.), prob_valuable=r.get("prob_valuable", .5)) for r in state["rocks"]]
-        return self.pack([ax], [ay], status)
+        return self.pack([ax], [ay], [[int(r["status"]) for r in state["rocks"]]])
+
+    def _state_from_ref(self, state):
+        if self._sstats is None:
+            self._sstats = RockBeliefStats(1, self.num_rocks, self.device, pinned_host=self.device.type == "cuda")
+        st, rocks = self._sstats, state["rocks"]
+        st.count[0] = torch.tensor([int(r.get("count", 0)) for r in rocks], dtype=torch.int32)
+        st.measured[0] = torch.tensor([int(r.get("measured", 0)) for r in rocks], dtype=torch.int32)
+        st.lkw[0] = torch.tensor([float(r.get("lkw", 1.)) for r in rocks], dtype=torch.float64)
+        st.lkv[0] = torch.tensor([float(r.get("lkv", 1.)) for r in rocks], dtype=torch.float64)
+        st.prob_valuable[0] = torch.tensor([float(r.get("prob_valuable", .5)) for r in rocks], dtype=torch.float64)
+        return self._pack_ref(state)
 
     def _reward_to_py(self, reward, action):
         return int(reward)
@@ -363,26 +401,16 @@ class RockEnv(BatchedPomdpEnv):
 
     @staticmethod
     def _efficiency(agent_pos, rock_pos, hed=20):
+        """rock.py:383-387 (the kernels read eff(d) from the table built with this same formula on the host)"""
         d = Grid.euclidean_distance(agent_pos, rock_pos)
         return (1 + pow(2, -d / hed)) * .5
 
     def _after_scalar_step(self, action, ob):
         self._query += 1
-        if action > SAMPLE and ob != NULL:        # rock.py:177-191: belief side-stats of the checked rock
-            r = self._side[action - SAMPLE - 1]
-            x, y, _ = self._decode_py(self._host_words())
-            eff = self._efficiency((x, y), self._rock_pos[action - SAMPLE - 1])
-            r["measured"] += 1
-            if ob == GOOD:
-                r["count"] += 1
-                r["lkv"] *= eff
-                r["lkw"] *= (1 - eff)
-            else:
-                r["count"] -= 1
-                r["lkw"] *= eff
-                r["lkv"] *= (1 - eff)
-            denom = (.5 * r["lkv"]) + (.5 * r["lkw"])
-            r["prob_valuable"] = (.5 * r["lkv"]) / denom if denom else float("nan")
+
+    def _scalar_state_tensor(self):
+        """the single instance's packed state where the kernels can read it"""
+        return self._io_state
 
     # ------------------------------------------------------------- planner hooks ---
     def _generate_legal(self, state=None):
@@ -390,23 +418,13 @@ class RockEnv(BatchedPomdpEnv):
         mask [n, n_actions] (a set; the reference's duplicate entries for Rock(15,15)'s
         doubled rock collapse)."""
         if self._scalar and state is None:
-            x, y, status = self._decode_py(self._host_words())
-            n = self.grid.x_size
-            legal = [1]
-            if y + 1 < n:
-                legal.append(0)
-            if y - 1 >= 0:
-                legal.append(2)
-            if x - 1 >= 0:
-                legal.append(3)
-            rock = int(self._grid_map[x | (y << 4)])
-            if rock >= 0 and int(status[rock]) != 0:
-                legal.append(SAMPLE)
-            for i in range(self.num_rocks):
-                if int(status[i]) != 0:
-                    p = self._rock_pos[i]
-                    legal.append(int(self._grid_map[p.x | (p.y << 4)]) + 1 + SAMPLE)
-            return legal
+            lst = torch.zeros(1, dtype=torch.int32, device=self.device)
+            with self._guard():
+                _lib.check(_lib.lib().pomdp_rock_legal_list(ctypes.byref(self._params), _lib.ptr(self._table),
+                                                            _lib.ptr(self._scalar_state_tensor()), _lib.ptr(lst), 1, self._stream()),
+                           "pomdp_rock_legal_list")
+            word = int(lst[0]) & 0xFFFFFFFF
+            return [int(self._legal_act[b]) for b in range(5 + self.num_rocks) if (word >> b) & 1]
         return self.legal_mask(state)
 
     def _generate_preferred(self, history):
@@ -435,16 +453,10 @@ class RockEnv(BatchedPomdpEnv):
                         ts[r] -= 1
                     if tr.observation == BAD:
                         td[r] -= 1
-        side = self._side
-        stats = RockBeliefStats(1, k, self.device)
-        stats.count.copy_(torch.tensor([[r["count"] for r in side]], dtype=torch.int32))
-        stats.measured.copy_(torch.tensor([[r["measured"] for r in side]], dtype=torch.int32))
-        stats.prob_valuable.copy_(torch.tensor([[r["prob_valuable"] for r in side]], dtype=torch.float64))
         hist = RockHistory(1, k, self.device)
         hist.check_totals.copy_(torch.tensor([[(s_ & 0xFFFF) | ((d_ & 0xFFFF) << 16) for s_, d_ in zip(ts, td)]],
                                              dtype=torch.int64).to(torch.int32))
-        state = self._io_state.to(self.device) if self._io_state.device != self.device else self._io_state
-        word = int(self.preferred_mask_words(state.reshape(self._io_state.shape), stats, hist)[0]) & 0xFFFFFFFF
+        word = int(self.preferred_mask_words(self._scalar_state_tensor(), self._sstats, hist)[0]) & 0xFFFFFFFF
         if word == 0:
             return self._generate_legal()
         return [a for a in range(self.action_space.n) if (word >> a) & 1]
@@ -463,14 +475,8 @@ class RockEnv(BatchedPomdpEnv):
 
     def _compute_prob(self, action, next_state, ob):
         """rock.py:250-264.  Scalar: floats.  Batched: float64 tensor (action/ob tensors)."""
-        if self._scalar:
-            if action <= SAMPLE:
-                return int(ob == NULL)
-            rock = next_state["rocks"][action - SAMPLE - 1]
-            eff = self._efficiency(next_state["agent_pos"], rock["pos"])
-            if (ob == GOOD and rock["status"] == 1) or (ob == BAD and rock["status"] == -1):
-                return eff
-            return 1 - eff
+        if self._scalar:                              # the same kernel, one particle: next_state in the reference's dict format
+            return float(self.observation_prob([int(action)], self._pack_ref(next_state), [int(ob)])[0])
         return self.observation_prob(action, next_state, ob)
 
 
@@ -480,7 +486,7 @@ class StochasticRockEnv(RockEnv):
     _stochastic = True
 
     def __init__(self, board_size=7, num_rocks=8, use_heuristic=False, p_move=.8, batch_size=None, device="cuda",
-                 seed=0, global_offset=0, track_belief_stats=False, track_history=False, history_next_is_reward=False):
+                 seed=None, global_offset=0, track_belief_stats=False, track_history=False, history_next_is_reward=False):
         super().__init__(board_size, num_rocks, use_heuristic, batch_size, device, seed, global_offset, p_move,
                          track_belief_stats, track_history, history_next_is_reward)
         self.p_move = p_move

@@ -33,7 +33,7 @@ class TagEnv(BatchedPomdpEnv):
     _abi = "tag"
 
     def __init__(self, num_opponents=1, move_prob=.8, obs_cells=29, board_size=(10, 5), batch_size=None,
-                 device="cuda", seed=0, global_offset=0):
+                 device="cuda", seed=None, global_offset=0):
         super().__init__(batch_size, device, seed, global_offset)
         if obs_cells != 29 or tuple(board_size) != (10, 5):
             # TagGrid hard-codes the 29-cell board whatever these say (tag.py:46-66)
@@ -188,11 +188,6 @@ class TagEnv(BatchedPomdpEnv):
 
     def _compute_prob(self, action, next_state, ob):
         """tag.py:209-217"""
-        if self._scalar:
-            p_ob = int(ob == self.grid.get_index(next_state.agent_pos))
-            if ob == self.grid.n_tiles:
-                for opp_pos in next_state.opponent_pos:
-                    if opp_pos == next_state.agent_pos:
-                        return 1.
-            return p_ob
+        if self._scalar:                              # the same kernel, one particle: next_state is a TagState
+            return float(self.observation_prob([int(action)], self._state_from_ref(next_state), [int(ob)])[0])
         return self.observation_prob(action, next_state, ob)

@@ -18,7 +18,7 @@ class TigerEnv(BatchedPomdpEnv):
     kind = _lib.KIND_TIGER
     _abi = "tiger"
 
-    def __init__(self, seed=0, correct_prob=.85, batch_size=None, device="cuda", global_offset=0):
+    def __init__(self, seed=None, correct_prob=.85, batch_size=None, device="cuda", global_offset=0):
         super().__init__(batch_size, device, seed, global_offset)
         self.correct_prob = correct_prob
         # the reference's _sample_ob never reads self.correct_prob: its default argument .85 is
@@ -84,11 +84,6 @@ class TigerEnv(BatchedPomdpEnv):
 
     def _compute_prob(self, action, next_state, ob, correct_prob=.85):
         """tiger.py:125-138"""
-        if self._scalar:
-            p_ob = 0.0
-            if action == LISTEN and ob != 2:
-                p_ob = correct_prob if next_state == ob else 1 - correct_prob
-            elif action != LISTEN and ob == 2:
-                p_ob = 1.
-            return p_ob
+        if self._scalar:                              # the same kernel, one particle
+            return float(self.observation_prob([int(action)], self._state_from_ref(next_state), [int(ob)], float(correct_prob))[0])
         return self.observation_prob(action, next_state, ob, float(correct_prob))

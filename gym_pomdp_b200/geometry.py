@@ -11,6 +11,7 @@ import math
 from collections import namedtuple
 from enum import Enum
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -44,6 +45,11 @@ class Moves(Enum):
     def get_coord(idx):
         return Coord(*MOVE_DELTAS[idx])
 
+    @staticmethod
+    def sample():
+        """coord.py:112-114"""
+        return np.random.randint(len(Moves))
+
 
 def opposite(move):
     """coord.py:75-77"""
@@ -56,6 +62,32 @@ class Grid(object):
     def __init__(self, x_size=10, y_size=5):
         self.x_size, self.y_size = x_size, y_size
         self.n_tiles = x_size * y_size
+        self.build_board()
+
+    # the host-side ``board`` of the reference (coord.py:36-52): an int8 (x_size, y_size) array of -1 that callers index
+    # with a Coord -- ``grid[pos]`` (rock.py:161); out-of-range reads give None, negative indices wrap as numpy's do.
+    # The kernels do not read it: RockSample's rock-id map travels in the TMA-staged table.
+    def __iter__(self):
+        return iter(self.board)
+
+    def __setitem__(self, idx, value):
+        try:
+            self.board[idx] = value
+        except IndexError:
+            raise IndexError()
+
+    def __getitem__(self, idx):
+        try:
+            return self.board[idx]
+        except IndexError:
+            return None
+
+    def build_board(self, value=1):
+        self.board = np.zeros(self.get_size, dtype=np.int8) - value
+
+    def sample(self):
+        """coord.py:68-69"""
+        return self.get_coord(np.random.randint(self.n_tiles))
 
     @property
     def get_size(self):
@@ -85,6 +117,19 @@ class Grid(object):
         """... and this one is the 2-norm (coord.py:83-85)."""
         return math.hypot(c1[0] - c2[0], c1[1] - c2[1])
 
+    @staticmethod
+    def directional_distance(c1, c2, d):
+        """coord.py:87-98, as written there (direction 2 mixes c2.y with c1.x)."""
+        if d == 0:
+            return c1[1] - c2[1]
+        elif d == 1:
+            return c1[0] - c2[0]
+        elif d == 2:
+            return c2[1] - c1[0]
+        elif d == 3:
+            return c2[0] - c1[0]
+        raise NotImplementedError()
+
 
 class TagGrid(Grid):
     """The fixed 29-cell Tag board (tag.py:36-78): rows y=0,1 are 10 wide, then a 3x3 block."""
@@ -93,6 +138,10 @@ class TagGrid(Grid):
     def __init__(self, board_size=(10, 5), obs_cells=29):
         Grid.__init__(self, *board_size)
         self.n_tiles = obs_cells
+
+    def sample(self):
+        """tag.py:43-44"""
+        return self.get_tag_coord(np.random.randint(0, 29))
 
     def is_inside(self, coord):
         x, y = coord

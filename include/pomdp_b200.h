@@ -357,6 +357,12 @@ int pomdp_rock_obs_prob(const PomdpRockParams* params, const void* d_table,
                         int64_t n, void* stream);
 int pomdp_rock_legal_mask(const PomdpRockParams* params, const void* d_table,
                           const int32_t* state, uint32_t* mask, int64_t n, void* stream);
+/* RockEnv._generate_legal() as the reference's LIST (rock.py:273-291): bit b of list[i] = the b-th candidate of the
+ * list's fixed order is present -- b = 0..4: EAST, NORTH, SOUTH, WEST, SAMPLE; b = 5 + r: the check the reference
+ * appends for rock r, i.e. action grid[rock_pos[r]] + 5 (Rock(15,15)'s two rocks at (1,2) both give action 8, twice
+ * in the list).  The header of the static table (`legal_act`, byte 400..431) maps b to its action id.          */
+int pomdp_rock_legal_list(const PomdpRockParams* params, const void* d_table, const int32_t* state, uint32_t* list,
+                          int64_t n, void* stream);
 int pomdp_tag_obs_prob(const PomdpTagParams* params,
                        const int32_t* next_state, const int32_t* action, const int32_t* obs, double* prob,
                        int64_t n, void* stream);

@@ -669,6 +669,18 @@ int pomdp_rock_belief_update(const PomdpRockParams* q, const void* table, const 
     return 0;
 }
 
+int pomdp_rock_legal_list(const PomdpRockParams* q, const void* table, const int32_t* state, uint32_t* list, int64_t n, void*) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+    if ((rc = host::check_policy(state, list, n, 0, "pomdp_rock_legal_list"))) return rc;
+    if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
+    const RockLut* lut = (const RockLut*)((const char*)table + ROCK_LUT_OFFSET);
+    for (int64_t i = 0; i < n; ++i)
+        list[i] = host::rock_words(q) == 1 ? rock_legal_list<uint32_t>(d, lut, load_state<uint32_t>(state, i))
+                                           : rock_legal_list<uint64_t>(d, lut, load_state<uint64_t>(state, i));
+    return 0;
+}
 // ---- heuristic action sets and rollouts: the functors the kernels inline (pomdp_core.h / pomdp_envs.h)
 int pomdp_rock_history_update(const PomdpRockParams* q, const int32_t* obs_field, const int32_t* action,
                               const int32_t* next_obs_field, int32_t* check_totals, int64_t n, void*) {

@@ -235,3 +235,111 @@ def test_batched_step_protocol(backend):
         env.step(torch.ones(B + 1, dtype=torch.int32))
     arr = env.to_array_form(info["state"])                            # rock.py:205-210
     assert arr.shape == (B, 12) and (arr[:, 0] == 11 * 5 + 1).all()
+
+
+# ------------------------------------------------------------ gym / gymnasium registration ---
+def _stub_gym(name, version):
+    """A stand-in for the parts of gym / gymnasium that registration touches (neither package is in the image): Env,
+    envs.registration.register / make, and -- for the new API -- the behaviour that broke old-API envs: make() wraps the
+    env in a checker that calls reset(seed=..., options=...) and insists on (ob, info) and five values from step()."""
+    import types
+    mod = types.ModuleType(name)
+    mod.__version__ = version
+
+    class Env(object):
+        metadata = {}
+    mod.Env = Env
+    reg = types.ModuleType(name + ".envs.registration")
+    reg.specs = {}
+
+    def register(id, entry_point=None, **kw):
+        reg.specs[id] = (entry_point, kw)
+    reg.register = register
+    new_api = name == "gymnasium" or tuple(int(p) for p in version.split(".")[:2]) >= (0, 26)
+
+    class OrderEnforcing(Env):
+        def __init__(self, env):
+            assert isinstance(env, Env), "gym.make wraps only gym.Env instances"
+            self.env = env
+
+        def reset(self, *, seed=None, options=None):
+            out = self.env.reset(seed=seed, options=options)
+            assert isinstance(out, tuple) and len(out) == 2 and isinstance(out[1], dict)
+            return out
+
+        def step(self, a):
+            out = self.env.step(a)
+            assert len(out) == 5
+            return out
+
+    def make(id, **kw):
+        entry, spec_kw = reg.specs[id]
+        if callable(entry):
+            env = entry(**kw)
+        else:
+            import importlib
+            m, _, cls = entry.partition(":")
+            env = getattr(importlib.import_module(m), cls)(**kw)
+        if new_api:
+            assert spec_kw.get("disable_env_checker") is True          # the passive checker would reject batched outputs
+            return OrderEnforcing(env)
+        return env
+    reg.make = make
+    envs = types.ModuleType(name + ".envs")
+    envs.registration = reg
+    mod.envs = envs
+    return {name: mod, name + ".envs": envs, name + ".envs.registration": reg}
+
+
+@pytest.mark.parametrize("pkg,version", [("gymnasium", "0.29.1"), ("gym", "0.26.2"), ("gym", "0.21.0")])
+def test_registration_with_old_and_new_gym_apis(backend, monkeypatch, pkg, version):
+    """the envs speak the reference's old-gym protocol; gym >= 0.26 / gymnasium call reset(seed=, options=) and
+    expect (ob, info) and a 5-tuple.  They get an adapter; old gym gets the classes themselves."""
+    import sys
+    from gym_pomdp_b200 import registration
+    stubs = _stub_gym(pkg, version)
+    for k in ("gym", "gym.envs", "gym.envs.registration", "gymnasium", "gymnasium.envs", "gymnasium.envs.registration"):
+        monkeypatch.delitem(sys.modules, k, raising=False)
+    for k, v in stubs.items():
+        monkeypatch.setitem(sys.modules, k, v)
+    registration._adapter_class.cache_clear()
+    assert registration.register_with_gym() == pkg
+    reg = stubs[pkg + ".envs.registration"]
+    assert sorted(reg.specs) == sorted(gp.registry)
+    new_api = registration.uses_new_api(pkg)
+    assert new_api == (pkg == "gymnasium" or version.startswith("0.26"))
+    env = reg.make("Tiger-v0", device=backend, seed=SEED)
+    if new_api:
+        ob, info = env.reset(seed=11, options=None)
+        assert ob == 2 and info == {}
+        ob, rw, terminated, truncated, info = env.step(2)
+        assert ob in (0, 1) and rw == -1 and terminated is False and truncated is False and "state" in info
+        inner = env.env
+        assert isinstance(inner, stubs[pkg].Env) and inner._generate_legal() == [0, 1, 2] and inner._discount == .95
+        assert inner.env._seed == 11                                   # reset(seed=) reached env.seed()
+        benv = reg.make("Tiger-v0", device=backend, batch_size=8).env
+        ob, info = benv.reset(seed=3)
+        out = benv.step(torch.full((8,), 2, dtype=torch.int32))
+        assert len(out) == 5 and out[3].shape == out[2].shape and not out[3].any()
+    else:
+        assert isinstance(env, gp.envs.TigerEnv) and env.reset() == 2 and len(env.step(2)) == 4
+    # the env classes subclass gym.Env only where the old protocol is gym's own
+    from gym_pomdp_b200.envs import base
+    assert (base._env_base() is stubs[pkg].Env) == (pkg == "gym" and not new_api)
+    registration._adapter_class.cache_clear()
+    # reset() itself tolerates the new keywords (a caller that skips gym.make)
+    plain = gp.make("Tiger-v0", device=backend)
+    assert plain.reset(seed=5, options={}) == 2 and plain._seed == 5
+
+
+def test_default_seed_is_fresh_and_explicit_seed_reproduces(backend):
+    """ADVICE r1: the reference draws from numpy's unseeded global RNG, so two default-constructed envs are independent;
+    here the default seed is a fresh 64-bit key, an explicit one reproduces."""
+    a = gp.make("Rock-v0", board_size=11, num_rocks=11, batch_size=256, device=backend)
+    b = gp.make("Rock-v0", board_size=11, num_rocks=11, batch_size=256, device=backend)
+    assert a._seed != b._seed and not torch.equal(a.reset() * 0 + a.state, b.reset() * 0 + b.state)
+    c = gp.make("Rock-v0", board_size=11, num_rocks=11, batch_size=256, device=backend, seed=5)
+    d = gp.make("Rock-v0", board_size=11, num_rocks=11, batch_size=256, device=backend, seed=5)
+    c.reset(), d.reset()
+    assert torch.equal(c.state, d.state)
+    assert a.seed(9) == [9] and a._seed == 9 and a.seed() == [None] and a._seed != 9

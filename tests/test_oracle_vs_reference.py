@@ -69,3 +69,45 @@ def test_tiger_and_network_steps_live(E):
             es, eob, tenths, _ = O.network_step(bits.tolist(), a, lambda k: int(w[k]), nb)
             assert (list(map(int, info["state"])), int(ob), rw) == (es, eob, tenths / 10.0)
         d.clear()
+
+
+def test_host_geometry_mirror_live(E):
+    """gym_pomdp_b200.geometry's host classes next to the reference's coord.py / tag.py ones: board, indexing (including
+    numpy's negative-index wrap and the out-of-range None), codecs, the three distances, directional_distance as written
+    (coord.py:87-98) and the sampling helpers under the same numpy seed."""
+    import gym_pomdp.envs.coord as RC
+    from gym_pomdp.envs.tag import TagGrid as RefTagGrid
+    from gym_pomdp_b200 import geometry as G
+    for xs, ys in [(7, 7), (10, 5), (11, 11)]:
+        a, b = RC.Grid(xs, ys), G.Grid(xs, ys)
+        assert np.array_equal(a.board, b.board) and a.board.dtype == b.board.dtype and a.get_size == b.get_size
+        a[RC.Coord(1, 2)] = 5
+        b[G.Coord(1, 2)] = 5
+        for c in [(1, 2), (0, 0), (-1, 0), (xs, 0), (0, ys), (xs - 1, ys - 1), (-xs, -ys), (-xs - 1, 0)]:
+            ra, rb = a[RC.Coord(*c)], b[G.Coord(*c)]
+            assert (ra is None and rb is None) or ra == rb, c
+        assert [list(r) for r in a] == [list(r) for r in b]
+        for i in range(xs * ys):
+            assert tuple(a.get_coord(i)) == tuple(b.get_coord(i)) and a.get_index(a.get_coord(i)) == b.get_index(b.get_coord(i))
+        rs = np.random.RandomState(3)
+        for _ in range(200):
+            c1, c2 = rs.randint(-2, 16, 2).tolist(), rs.randint(-2, 16, 2).tolist()
+            assert a.is_inside(RC.Coord(*c1)) == b.is_inside(G.Coord(*c1))
+            assert RC.Grid.euclidean_distance(RC.Coord(*c1), RC.Coord(*c2)) == G.Grid.euclidean_distance(G.Coord(*c1), G.Coord(*c2))
+            assert RC.Grid.manhattan_distance(RC.Coord(*c1), RC.Coord(*c2)) == G.Grid.manhattan_distance(G.Coord(*c1), G.Coord(*c2))
+            for d in range(4):
+                assert RC.Grid.directional_distance(RC.Coord(*c1), RC.Coord(*c2), d) == \
+                    G.Grid.directional_distance(G.Coord(*c1), G.Coord(*c2), d)
+        with pytest.raises(NotImplementedError):
+            G.Grid.directional_distance(G.Coord(0, 0), G.Coord(1, 1), 4)
+        np.random.seed(7)
+        ra = [tuple(a.sample()) for _ in range(20)] + [RC.Moves.sample() for _ in range(20)]
+        np.random.seed(7)
+        rb = [tuple(b.sample()) for _ in range(20)] + [G.Moves.sample() for _ in range(20)]
+        assert ra == rb
+    ta, tb = RefTagGrid((10, 5)), G.TagGrid((10, 5))
+    np.random.seed(9)
+    sa = [tuple(ta.sample()) for _ in range(50)]
+    np.random.seed(9)
+    assert sa == [tuple(tb.sample()) for _ in range(50)]
+    assert np.array_equal(ta.board, tb.board)

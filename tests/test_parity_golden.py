@@ -34,6 +34,8 @@ def test_rock_step_vs_reference(golden, backend, tag):
     # static maps built by the C library == the reference's grid / efficiency table
     grid = env._grid_map.reshape(16, 16)[:n, :n].T      # [y, x] -> [x, y]
     assert np.array_equal(grid, g["grid"])
+    assert np.array_equal(env.grid.board, g["grid"]) and env.grid.board.dtype == np.int8       # coord.py:51-52, rock.py:110-111
+    assert env.grid[(0, 0)] == g["grid"][0, 0] and env.grid[(n, 0)] is None                    # coord.py:45-49
     assert np.array_equal(env._eff_T[: 2 * (n - 1) + 1], np.ceil(g["eff"] * 2.0 ** 32).astype(np.int64))
     assert [tuple(p) for p in env._rock_pos] == [tuple(p) for p in g["rock_pos"][:k]]
     state = env.pack(g["x"], g["y"], g["status"])
