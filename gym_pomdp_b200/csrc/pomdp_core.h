@@ -25,7 +25,7 @@
 namespace pomdp {
 
 enum : int32_t { FLAG_DONE = 1, FLAG_BAD_ACTION = 2, FLAG_STEPPED_DONE = 4, FLAG_BAD_STATE = 8 };
-enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1, DOMAIN_POLICY = 2 };
+enum : uint32_t { DOMAIN_STEP = 0, DOMAIN_RESET = 1, DOMAIN_POLICY = 2, DOMAIN_SHIP = 3 };
 
 // ------------------------------------------------------------------ Philox4x32-10 ----
 struct U4 { uint32_t x, y, z, w; };
@@ -90,6 +90,23 @@ struct LazyDraw {          // scalar paths: one Philox call per requested slot
     uint64_t env;
     uint32_t step, domain;
     POMDP_HD uint32_t operator()(int slot) const { return draw_word(*key, env, step, domain, (uint32_t)slot); }
+};
+// BattleShip's fixed-time placement draws are keyed by the env itself, not by its group of four: a board is one thread's
+// (or one warp's) work, so a block whose four words serve four ENVS would be computed four times over.  Instead
+//   word(env, ship) = philox(key = seed, ctr = (lo32(env), hi32(env), step, DOMAIN_SHIP << 24 | ship >> 2))[ship & 3]
+// -- ONE Philox call per board covers ships 0..3 (the stock game has two).
+struct ShipDraw {
+    const PhiloxKey* key;
+    uint64_t env;
+    uint32_t step;
+    U4 q0;
+    POMDP_HD ShipDraw(const PhiloxKey& k, uint64_t env_, uint32_t step_) : key(&k), env(env_), step(step_) {
+        q0 = draw_quad(k, env_, step_, DOMAIN_SHIP, 0u);
+    }
+    POMDP_HD uint32_t operator()(int ship) const {
+        if (ship < 4) return word_of(q0, ship);
+        return word_of(draw_quad(*key, env, step, DOMAIN_SHIP, (uint32_t)(ship >> 2)), ship & 3);
+    }
 };
 template <int N>
 struct WordDraw {          // vector path: words precomputed from the group's quads
@@ -1106,7 +1123,7 @@ POMDP_HD bool battleship_place_from(const ShipDev& p, const D& draw, int ship_fr
 }
 POMDP_HD bool battleship_reset_bitboard(const ShipDev& p, const PhiloxKey& seed, uint64_t env, uint32_t step, ShipState& st) {
     st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
-    return battleship_place_from(p, LazyDraw{&seed, env, step, DOMAIN_RESET}, 0, st.occ, st.remaining);
+    return battleship_place_from(p, ShipDraw(seed, env, step), 0, st.occ, st.remaining);
 }
 
 // ---- placement tables: the accepted sets of the first two ships are static --------------------------------------
@@ -1138,7 +1155,9 @@ POMDP_HD void ld_rec(const ShipRec* p, uint32_t& c0, uint32_t& n1, uint32_t& off
     c0 = p->c0; n1 = p->n1; off1 = p->off1;
 #endif
 }
-template <class D>
+// kLean: every ship comes from the tables (max_len <= 3, the stock game): no scan code is instantiated, which keeps
+// the kernel small enough for full occupancy.
+template <bool kLean, class D>
 POMDP_HD bool battleship_reset_table(const ShipDev& p, const unsigned char* __restrict__ tbl, const D& draw, ShipState& st) {
     st.occ = b128(0, 0); st.vis = b128(0, 0); st.remaining = 0; st.done = false;
     if (p.tbl_n0 == 0) return false;
@@ -1148,12 +1167,13 @@ POMDP_HD bool battleship_reset_table(const ShipDev& p, const unsigned char* __re
     st.occ = ship_cells(p, 0, (int)(c0 >> 2), (int)(c0 & 3u), p.max_len);
     st.remaining = p.max_len;
     if (p.max_len < 3) return true;
-    if (p.tbl_n_tabled < 2) return battleship_place_from(p, draw, 1, st.occ, st.remaining);
+    if (!kLean && p.tbl_n_tabled < 2) return battleship_place_from(p, draw, 1, st.occ, st.remaining);
     if (n1 == 0) return false;
     const uint32_t k1 = rand_below(draw(1), n1);
     const uint32_t c1 = ld_ro16(reinterpret_cast<const uint16_t*>(tbl + p.tbl_off_second) + off1 + k1);
     st.occ = st.occ | ship_cells(p, 1, (int)(c1 >> 2), (int)(c1 & 3u), p.max_len - 1);
     st.remaining += p.max_len - 1;
+    if (kLean) return true;
     return battleship_place_from(p, draw, 2, st.occ, st.remaining);
 }
 

@@ -809,7 +809,7 @@ pomdp_battleship_reset_scan_kernel(const __grid_constant__ ShipDev p, int32_t* _
                 total += __popc(__ballot_sync(0xffffffffu, ok));
             }
             if (total == 0) { ok_all = false; break; }   // the reference would loop forever
-            const uint32_t w = draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET, (uint32_t)ship);   // warp-uniform
+            const uint32_t w = ShipDraw(seed, goff + (uint64_t)i, step_ctr)(ship);                            // warp-uniform
             int k = (int)rand_below(w, (uint32_t)total);
             int chosen = -1;
             for (int j = 0; j < n_iter; ++j) {
@@ -864,24 +864,30 @@ pomdp_battleship_reset_bitboard_kernel(const __grid_constant__ ShipDev p, int32_
 }
 
 // One thread per env, placements of the first two ships read from the host-built tables (pomdp_core.h:
-// battleship_reset_table) -- two Philox words and four small table reads per board instead of the bitboard scan.
+// battleship_reset_table) -- one Philox call and two dependent table reads per board instead of the bitboard scan.
 // kBulk (state 16-byte aligned, no mask): the CTA's tile of boards is assembled in shared memory and leaves with ONE
 // TMA bulk store per tile, like the step kernel's; otherwise every thread stores its own 32 bytes.
-template <bool kBulk>
-__global__ void __launch_bounds__(POMDP_THREADS)
+// kLean: the stock two-ship game -- no scan code in the kernel.  CTAs are 128 threads (4 KB tiles): 2^18 boards are 2048
+// tiles, which all fit on the machine at once, so every CTA runs its one chain of Philox -> record -> list -> store once.
+#ifndef POMDP_SHIP_RESET_THREADS
+#define POMDP_SHIP_RESET_THREADS 128
+#endif
+template <bool kBulk, bool kLean>
+__global__ void __launch_bounds__(POMDP_SHIP_RESET_THREADS)
 pomdp_battleship_reset_table_kernel(const __grid_constant__ ShipDev p, const unsigned char* __restrict__ tbl,
                                     int32_t* __restrict__ state, int32_t* __restrict__ obs, int32_t* __restrict__ flags,
                                     const uint8_t* __restrict__ mask, int64_t n, uint64_t goff,
                                     const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
-    __shared__ alignas(128) uint32_t tile[kBulk ? POMDP_THREADS * SHIP_WORDS : 4];
-    const int64_t n_tiles = (n + POMDP_THREADS - 1) / POMDP_THREADS;
+    constexpr int T = POMDP_SHIP_RESET_THREADS;
+    __shared__ alignas(128) uint32_t tile[kBulk ? T * SHIP_WORDS : 4];
+    const int64_t n_tiles = (n + T - 1) / T;
     for (int64_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
-        const int64_t base = tix * POMDP_THREADS;
-        const int cnt = (int)min((int64_t)POMDP_THREADS, n - base);
+        const int64_t base = tix * T;
+        const int cnt = (int)min((int64_t)T, n - base);
         const int64_t i = base + threadIdx.x;
         if ((int)threadIdx.x < cnt && (kBulk || !mask || mask[i])) {
             ShipState st;
-            const bool ok = battleship_reset_table(p, tbl, LazyDraw{&seed, goff + (uint64_t)i, step_ctr, DOMAIN_RESET}, st);
+            const bool ok = battleship_reset_table<kLean>(p, tbl, ShipDraw(seed, goff + (uint64_t)i, step_ctr), st);
             uint32_t w8[SHIP_WORDS];
             ship_pack(st, w8);
             if (kBulk) {
@@ -905,9 +911,9 @@ pomdp_battleship_reset_table_kernel(const __grid_constant__ ShipDev p, const uns
             if (threadIdx.x == 0) {
                 tma_bulk_s2g(state + base * SHIP_WORDS, tile, (uint32_t)cnt * SHIP_WORDS * 4u);
                 tma_commit();
-                tma_wait_read0();         // the tile may be overwritten once the engine has read it
+                if (tix + gridDim.x < n_tiles) tma_wait_read0();   // another tile follows: the engine must have read this one
             }
-            __syncthreads();
+            if (tix + gridDim.x < n_tiles) __syncthreads();
         }
     }
     if (kBulk && threadIdx.x == 0) tma_wait_all0();
@@ -1494,14 +1500,13 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* d_table, 
     if (!d_table) {
         auto k = pomdp_battleship_reset_bitboard_kernel;
         k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
-    } else if (!mask && (((uintptr_t)state) & 15) == 0) {
-        auto k = pomdp_battleship_reset_table_kernel<true>;
-        k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, (const unsigned char*)d_table, state, obs, flags, mask, n, (uint64_t)goff,
-                                                    philox_key(seed), step_ctr);
     } else {
-        auto k = pomdp_battleship_reset_table_kernel<false>;
-        k<<<grid_for(k, n), POMDP_THREADS, 0, st>>>(d, (const unsigned char*)d_table, state, obs, flags, mask, n, (uint64_t)goff,
-                                                    philox_key(seed), step_ctr);
+        const bool bulk = !mask && (((uintptr_t)state) & 15) == 0;
+        const bool lean = d.max_len <= 3 && d.tbl_n_tabled >= (uint32_t)(d.max_len - 1);
+        auto k = bulk ? (lean ? pomdp_battleship_reset_table_kernel<true, true> : pomdp_battleship_reset_table_kernel<true, false>)
+                      : (lean ? pomdp_battleship_reset_table_kernel<false, true> : pomdp_battleship_reset_table_kernel<false, false>);
+        k<<<grid_for(k, n, POMDP_SHIP_RESET_THREADS), POMDP_SHIP_RESET_THREADS, 0, st>>>(
+            d, (const unsigned char*)d_table, state, obs, flags, mask, n, (uint64_t)goff, philox_key(seed), step_ctr);
     }
     return finish("pomdp_battleship_reset");
 }

@@ -41,7 +41,8 @@
  *    Rock sample is treated as "no rock here").
  *  - Randomness: stateless Philox4x32-10.  The word for draw slot j of env i is
  *        philox(key = seed, ctr = (lo32(g>>2), hi32(g>>2), step_ctr, (domain<<24) | j))[g & 3]
- *    with g = global_offset + i, domain 0 for step, 1 for reset and 2 for the policy draw: one Philox block holds
+ *    with g = global_offset + i, domain 0 for step, 1 for reset and 2 for the policy draw (3: BattleShip's placement
+ *    draws, keyed per env -- see pomdp_battleship_reset): one Philox block holds
  *    the same slot of four consecutive envs, so a thread that owns an aligned group of
  *    four pays one Philox call per slot.  Results do not depend on how a batch is sharded
  *    across GPUs (shards whose global_offset is a multiple of 4 take the vector path; any
@@ -163,8 +164,11 @@ int pomdp_battleship_step(const PomdpBattleshipParams* params,
 /* BattleShipEnv.reset battleship.py:131-137 (+ _get_init_state 167-180, collision 195-211,
  * mark_ship 182-193) in fixed time: all 4*n_tiles (pos, dir) candidates of a ship are tested with
  * the reference's collision rule and ship s takes the k-th accepted one in increasing
- * c = 4*pos + dir, k = floor(u * count) from draw slot s -- the same distribution as the
- * reference's rejection loop (uniform over the accepted set).  POMDP_FLAG_BAD_STATE is raised in
+ * c = 4*pos + dir, k = floor(u * count), u = ship s's draw word -- the same distribution as the
+ * reference's rejection loop (uniform over the accepted set).  These placement draws are keyed by the
+ * env itself, not by its group of four (a board is one thread's work):
+ *     word(env, s) = philox(key = seed, ctr = (lo32(g), hi32(g), step_ctr, 3 << 24 | s >> 2))[s & 3],  g = global_offset + i
+ * (domain 3), so one Philox call covers a board's first four ships.  POMDP_FLAG_BAD_STATE is raised in
  * flags (may be NULL) when no placement exists (the reference would spin forever).
  *   pomdp_battleship_reset          one THREAD per env.  With `d_table` (device copy of the placement
  *                                   tables below) the accepted sets of the first two ships are read from

@@ -42,6 +42,13 @@ def fill_draws(seed, global_offset, n, step, domain, n_slots):
     return out
 
 
+def fill_env_draws(seed, global_offset, n, step, domain, n_slots):
+    out = np.empty((n, n_slots), np.uint32)
+    lib().oracle_fill_env_draws(c_uint64(seed), c_uint64(global_offset), c_int64(n), c_uint32(step), c_uint32(domain),
+                            c_int(n_slots), _p(out))
+    return out
+
+
 def philox(ctr, key):
     out = np.zeros(4, np.uint32)
     lib().oracle_philox_kat(_p(_c(ctr, np.uint32)), _p(_c(key, np.uint32)), _p(out))

@@ -79,6 +79,20 @@ def draw_slots(seed, env, step, domain, n_slots):
     return out
 
 
+DOMAIN_SHIP = 3
+
+
+def draw_env_slots(seed, env, step, domain, n_slots):
+    """uint32 [len(env), n_slots] for draws keyed by the ENV itself (BattleShip's fixed-time placement, domain SHIP):
+    word(env, slot) = philox(key=seed, ctr=(lo32(env), hi32(env), step, domain << 24 | slot >> 2))[slot & 3] -- one block
+    holds four consecutive SLOTS of one env."""
+    env = np.atleast_1d(np.asarray(env, dtype=np.uint64))
+    out = np.empty((env.shape[0], n_slots), dtype=np.uint32)
+    for s in range(n_slots):
+        out[:, s] = draw_quad(seed, env, step, domain, s >> 2)[s & 3]
+    return out
+
+
 def kat():
     """Known-answer vectors of Random123 (kat_vectors, philox4x32 10 rounds)."""
     vecs = [

@@ -67,6 +67,20 @@ void oracle_fill_draws(uint64_t seed, uint64_t global_offset, int64_t n, uint32_
     }
 }
 
+/* Draws keyed by the env itself (BattleShip's fixed-time placement, domain 3): one Philox block holds four consecutive
+ * SLOTS of one env -- counter = env, word = slot & 3, block index slot >> 2.  out is [n, n_slots]. */
+void oracle_fill_env_draws(uint64_t seed, uint64_t global_offset, int64_t n, uint32_t step, uint32_t domain,
+                           int n_slots, uint32_t* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t env = global_offset + (uint64_t)i;
+        for (int slot = 0; slot < n_slots; ++slot) {
+            uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), step, (domain << 24) | (uint32_t)(slot >> 2)};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            out[i * n_slots + slot] = c[slot & 3];
+        }
+    }
+}
+
 static int bern(uint32_t r, double p) { return (double)r / TWO32 < p; }          /* np.random.binomial(1, p) */
 static int below(uint32_t r, int n) { return (int)(((uint64_t)r * (uint64_t)n) >> 32); } /* randint(n) */
 

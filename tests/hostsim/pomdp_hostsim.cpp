@@ -316,7 +316,9 @@ int pomdp_battleship_reset(const PomdpBattleshipParams* q, const void* table, in
     for (int64_t i = 0; i < n; ++i) {
         if (mask && !mask[i]) continue;
         ShipState st;
-        const bool ok = table ? battleship_reset_table(d, (const unsigned char*)table, LazyDraw{&key, (uint64_t)(goff + i), step, DOMAIN_RESET}, st)
+        const bool lean = d.max_len <= 3 && d.tbl_n_tabled >= (uint32_t)(d.max_len - 1);
+        const bool ok = table ? (lean ? battleship_reset_table<true>(d, (const unsigned char*)table, ShipDraw(key, (uint64_t)(goff + i), step), st)
+                                      : battleship_reset_table<false>(d, (const unsigned char*)table, ShipDraw(key, (uint64_t)(goff + i), step), st))
                               : battleship_reset_bitboard(d, key, (uint64_t)(goff + i), step, st);
         uint32_t w8[SHIP_WORDS];
         ship_pack(st, w8);
@@ -344,7 +346,7 @@ int pomdp_battleship_reset_warpscan(const PomdpBattleshipParams* q, int32_t* sta
             int total = 0;
             for (int c = 0; c < 4 * d.n_tiles; ++c) total += ship_candidate_ok(d, blocked, c >> 2, c & 3, length);
             if (total == 0) { ok_all = false; break; }
-            int k = (int)rand_below(draw_word(key, (uint64_t)(goff + i), step, DOMAIN_RESET, (uint32_t)ship), (uint32_t)total);
+            int k = (int)rand_below(ShipDraw(key, (uint64_t)(goff + i), step)(ship), (uint32_t)total);
             for (int c = 0; c < 4 * d.n_tiles; ++c)
                 if (ship_candidate_ok(d, blocked, c >> 2, c & 3, length) && k-- == 0) { ship_mark(d, st, c >> 2, c & 3, length); break; }
         }

@@ -436,7 +436,7 @@ def test_battleship_bitboard_reset_equals_oracle_on_odd_boards(backend, size, ma
     (battleship.py:195-211): same boards, same `no placement exists` flags, for shapes far from the stock 10 x 10."""
     from oracle import c_oracle as C, philox
     B = 2000
-    eocc, erem, err = C.battleship_reset_scan(size[0], size[1], max_len, C.fill_draws(21, 0, B, 9, philox.DOMAIN_RESET, max_len - 1))
+    eocc, erem, err = C.battleship_reset_scan(size[0], size[1], max_len, C.fill_env_draws(21, 0, B, 9, philox.DOMAIN_SHIP, max_len - 1))
     # all three fixed-time kernels: placement tables + TMA tile store, bitboard scan, warp scan (whose literal
     # seven-shift neighbour mask, ship_mark and ship_pack work on the same two-word boards -- no 128-bit integers
     # on the device: ships straddle bits 31/32, 63/64 and 95/96 of the board on these shapes)

@@ -168,7 +168,7 @@ def test_battleship_10x10_batch_2p18(backend):
     env = gp.make("Battleship-v0", board_size=(10, 10), batch_size=B, device=backend, seed=SEED)
     st, ob0 = env.init_states(B, step_ctr=2)
     occ, vis, rem, done = (v.cpu().numpy() for v in env.unpack(st))
-    eocc, erem, err = C.battleship_reset_scan(10, 10, 3, C.fill_draws(SEED, 0, B, 2, philox.DOMAIN_RESET, 2))
+    eocc, erem, err = C.battleship_reset_scan(10, 10, 3, C.fill_env_draws(SEED, 0, B, 2, philox.DOMAIN_SHIP, 2))
     assert np.array_equal(occ.reshape(B, 10, 10), eocc) and np.array_equal(rem, erem) and not err.any()
     assert not vis.any() and not done.any() and not ob0.any() and not env.reset_flags.any()
     # synthetic visited pattern ~ Bernoulli(0.3), total_remaining recomputed, then four shots

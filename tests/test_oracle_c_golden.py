@@ -20,6 +20,13 @@ def test_philox_kat_and_fill():
         a = C.fill_draws(seed, off, 257, step, dom, slots)
         b = philox.draw_slots(seed, np.arange(257, dtype=np.uint64) + np.uint64(off), step, dom, slots)
         assert np.array_equal(a, b)
+    # env-keyed draws (BattleShip's fixed-time placement): one block = four consecutive slots of ONE env
+    for (seed, off, step, slots) in [(0x5EED, 0, 2, 2), (2 ** 63 + 5, 2 ** 33 + 12, 7, 8), (1, 3, 0, 5)]:
+        a = C.fill_env_draws(seed, off, 257, step, philox.DOMAIN_SHIP, slots)
+        b = philox.draw_env_slots(seed, np.arange(257, dtype=np.uint64) + np.uint64(off), step, philox.DOMAIN_SHIP, slots)
+        assert np.array_equal(a, b)
+        blk = C.philox((int(off) & 0xFFFFFFFF, int(off) >> 32, step, philox.DOMAIN_SHIP << 24), (seed & 0xFFFFFFFF, seed >> 32))
+        assert a[0, :min(4, slots)].tolist() == blk.tolist()[:min(4, slots)]
 
 
 @pytest.mark.parametrize("tag", ROCKS)
