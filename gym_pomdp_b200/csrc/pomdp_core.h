@@ -779,14 +779,29 @@ POMDP_HD void tiger_reset(const D& draw, uint32_t& s, int32_t& ob) {
 
 // ========================================================================= Network ===
 constexpr int NETWORK_MAX = 30;
+constexpr int NET_GROUP = 5;                                   // machines whose failures ONE draw word decides
+constexpr int NET_MAX_GROUPS = NETWORK_MAX / NET_GROUP;        // 6
+constexpr int NET_CODES = 243;                                 // 3^5 joint outcomes of a group
+constexpr int NET_COLS = 256;                                  // alias columns (the word's low 8 bits)
+// One alias column (Walker/Vose): the word's upper 24 bits against `thr` pick the column's own outcome or its alias.
+// masks: bits 0-4 own "fails whatever the neighbours do" machines, 5-9 own "fails under the larger probability" machines
+// (a superset of bits 0-4), bits 16-20 / 21-25 the same for the alias outcome.
+struct NetAlias { uint32_t thr, masks; };
+// The per-configuration tables of the step, copied from the kernel parameters to shared memory once per CTA (lookups are
+// per-thread divergent, which the constant bank would serialise).
+struct NetworkTables {
+    NetAlias alias[NET_COLS];                                  // 2 KB
+    uint32_t nbd[NET_MAX_GROUPS][32];                          // OR-linear map "down machines of group g" -> machines with a down neighbour
+};
 struct NetworkDev {
-    int32_t n;
+    int32_t n, groups;               // groups = ceil(n / 5)
     uint32_t deg3;                   // machines with more than 2 neighbours (reward 2, network.py:89-92)
+    uint32_t cond_flip;              // all-ones when q < p: the larger probability then belongs to "no neighbour down"
     uint64_t p_T, q_T, ob_T;         // ceil(prob * 2^32)
-    uint32_t pm1, qm1, om1;          // T - 1 (r < T  <=>  r <= T - 1 when T != 0)
-    int32_t all_T_nonzero;           // every T above is in 1..2^32: the 32-bit compares are exact
+    uint32_t om1, ob_any;            // the observation draw as a 32-bit compare: hit = ob_any && w <= om1 (om1 = ob_T - 1)
     double p_ob;
     uint32_t nb[NETWORK_MAX + 2];    // neighbour bit masks (network.py:144-168)
+    NetworkTables t;
 };
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
 
@@ -800,76 +815,121 @@ POMDP_HD float tenths_to_float(int t) {
     return fmaf(fmaf(-q, 10.0f, x), 0.1f, q);
 }
 
+// Table access for network_step_n.  NetTabPtr: plain pointers (tests/hostsim, and wherever the tables sit in generic
+// memory).  NetTabSmem (device): the tables in shared memory behind ONE 32-bit base address kept in a register -- through
+// a generic pointer the compiler re-derives the shared window base (S2UR + UMOV + ULEA) before every lookup.
+struct NetTabPtr {
+    const NetworkTables* T;
+    POMDP_HD NetAlias alias(uint32_t col) const { return T->alias[col]; }
+    POMDP_HD uint32_t nbd(int g, uint32_t v) const { return T->nbd[g][v]; }
+};
+#if defined(__CUDACC__)
+struct NetTabSmem {
+    uint32_t base;                                               // shared-space address of a NetworkTables
+    __device__ __forceinline__ NetAlias alias(uint32_t col) const {
+        NetAlias e;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.thr), "=r"(e.masks) : "r"(base + col * (uint32_t)sizeof(NetAlias)));
+        return e;
+    }
+    __device__ __forceinline__ uint32_t nbd(int g, uint32_t v) const {
+        uint32_t r;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(base + (uint32_t)(sizeof(NetAlias) * NET_COLS) + ((uint32_t)g * 32u + v) * 4u));
+        return r;
+    }
+};
+#endif
+
+// The failures among the five machines of one group from ONE draw word (include/pomdp_b200.h, "Network draws"):
+// column = w & 255; the column's own outcome if w < thr (thr = 24-bit threshold << 8, so the column bits never decide),
+// its alias otherwise; cond5 = which of the five machines face the larger probability.
+template <class Tab>
+POMDP_HD uint32_t network_group_fail(const Tab& T, uint32_t w, uint32_t cond5) {
+    const NetAlias e = T.alias(w & (NET_COLS - 1));
+    const uint32_t m = w < e.thr ? e.masks : e.masks >> 16;      // bits 0-4 fail either way, 5-9 fail under the larger one
+    return (m | (cond5 & (m >> NET_GROUP))) & 31u;
+}
+
+// The action and the outputs of one env (network.py:87-92, 101-112) once its failures are known.
+// kClean: the caller has established that this env raises no flag (not done, action in range, no stray state bits).
+// Two identities keep it short: the no-op action 2n is even, so `a & 1` alone says "reboot"; and a rebooted machine
+// is up, so its observation `hit` equals the ping's `bit ^ hit ^ 1` -- one expression serves both actions.
+template <bool kClean>
+POMDP_HD void network_finish(const NetworkDev& p, uint32_t all, uint32_t na, uint32_t s, int32_t a, uint32_t fail,
+                             uint32_t h, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    int f = 0;
+    if (!kClean) {
+        f = (s & ~all & ~NETWORK_DONE) ? FLAG_BAD_STATE : 0;
+        f = (uint32_t)a > na ? FLAG_BAD_ACTION : f;
+        f = (s & NETWORK_DONE) ? (FLAG_DONE | FLAG_STEPPED_DONE) : f;
+    }
+    const bool live = kClean || f == 0;
+    const bool acts = (uint32_t)a < na;
+    const uint32_t m = ((uint32_t)a >> 1) & 31u;
+    const uint32_t reboot = (uint32_t)a & 1u;
+    const uint32_t n2 = (s & ~fail) | (((kClean || acts) ? reboot : 0u) << m);      // kClean: a <= 2n, and 2n is even
+    const uint32_t o = acts ? (((n2 >> m) ^ h ^ 1u) & 1u) : 2u;
+    const int tenths = 10 * (popc32(s) + popc32(s & p.deg3)) - (acts ? 1 + 24 * (int)reboot : 0);
+    fl = f;
+    s2 = live ? n2 : s;
+    ob = live ? (int32_t)o : 0;
+    rw = live ? tenths_to_float(tenths) : 0.f;
+}
+
 // network.py:71-114 for L consecutive envs of ONE draw group (L = 4: a thread's aligned
-// group, lane0 = 0; L = 1: a single env, lane0 = env & 3).  Slot m = machine m's failure
-// draw, slot n = the action's observation draw: one Philox call per slot serves all L envs.
-// Reward is carried as an exact integer number of tenths.
+// group, lane0 = 0; L = 1: a single env, lane0 = env & 3).  Slot g < groups = the joint failure
+// draw of machines 5g..5g+4, slot `groups` = the action's observation draw: one Philox call per
+// slot serves all L envs.  Reward is carried as an exact integer number of tenths.
 //
-// The reference draws only for machines that are up (network.py:95); a failure draw for a
-// machine that is down clears a bit that is already clear, so the loop needs no "is up" test.
-// The thresholds are compared as r <= T - 1 in 32 bits; a configuration with a probability of
-// exactly 0 (T = 0, nothing ever fires) takes the 64-bit compare instead (uniform per launch).
-template <int L>
-POMDP_HD void network_step_n(const NetworkDev& p, const uint32_t s[L], const int32_t a[L], const PhiloxKey& seed,
-                             uint64_t group, int lane0, uint32_t step,
+// The reference draws binomial(1, p or q) once per machine that is up (network.py:94-99), q when a
+// neighbour is down in the OLD state.  Per machine that is one uniform u against two thresholds, i.e.
+// three outcomes (u < lo: fails either way; lo <= u < hi: fails under the larger probability only;
+// else: stays up), independent across machines; the 3^5 joint outcomes of a group are sampled from
+// one word through an alias table, and which machines face the larger probability (`cond`) selects
+// between the outcome's two masks.  A failure of a machine that is already down clears a clear bit.
+template <int L, class Tab>
+POMDP_HD void network_step_n(const NetworkDev& p, const Tab& T, const uint32_t s[L], const int32_t a[L],
+                             const PhiloxKey& seed, uint64_t group, int lane0, uint32_t step,
                              uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
     const uint32_t all = (1u << p.n) - 1u;
-    uint32_t nw[L], down[L];
-    bool hit[L];
+    uint32_t fail[L], cond[L];
     POMDP_UNROLL
-    for (int j = 0; j < L; ++j) {
-        nw[j] = s[j];
-        down[j] = ~s[j] & all;
-    }
-    if (p.all_T_nonzero) {
-        const uint32_t pm1 = p.pm1, qm1 = p.qm1;
-        for (int m = 0; m < p.n; ++m) {                                           // network.py:94-99
-            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
-            const uint32_t nbm = p.nb[m];
-            const uint32_t keep = ~(1u << m);
+    for (int j = 0; j < L; ++j) { cond[j] = 0; fail[j] = 0; }
+    POMDP_UNROLL
+    for (int g = 0; g < NET_MAX_GROUPS; ++g)
+        if (g < p.groups) {                                                           // uniform branch; network.py:81-84
             POMDP_UNROLL
-            for (int j = 0; j < L; ++j) {
-                const uint32_t t = (nbm & down[j]) ? qm1 : pm1;
-                if (word_of(q, lane0 + j) <= t) nw[j] &= keep;
-            }
+            for (int j = 0; j < L; ++j) cond[j] |= T.nbd(g, ((~s[j] & all) >> (NET_GROUP * g)) & 31u);
         }
-        const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) hit[j] = word_of(qa, lane0 + j) <= p.om1;
-    } else {                                                                      // a probability of exactly 0
-        for (int m = 0; m < p.n; ++m) {
-            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)m);
+    POMDP_UNROLL
+    for (int j = 0; j < L; ++j) cond[j] ^= p.cond_flip;         // machines that face the larger of the two probabilities
+    POMDP_UNROLL
+    for (int g = 0; g < NET_MAX_GROUPS; ++g)
+        if (g < p.groups) {                                                           // network.py:94-99
+            const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)g);
             POMDP_UNROLL
-            for (int j = 0; j < L; ++j) {
-                const uint64_t T = (p.nb[m] & down[j]) ? p.q_T : p.p_T;
-                if (bern(word_of(q, lane0 + j), T)) nw[j] &= ~(1u << m);
-            }
+            for (int j = 0; j < L; ++j)
+                fail[j] |= network_group_fail(T, word_of(q, lane0 + j), cond[j] >> (NET_GROUP * g)) << (NET_GROUP * g);
         }
-        const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.n);
-        POMDP_UNROLL
-        for (int j = 0; j < L; ++j) hit[j] = bern(word_of(qa, lane0 + j), p.ob_T);
-    }
+    const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.groups);
     const uint32_t na = (uint32_t)(2 * p.n);
+    uint32_t stray = 0, amax = 0;
     POMDP_UNROLL
     for (int j = 0; j < L; ++j) {
-        const int f = (s[j] & NETWORK_DONE) ? (FLAG_DONE | FLAG_STEPPED_DONE)
-                      : (uint32_t)a[j] > na ? FLAG_BAD_ACTION
-                      : (s[j] & ~all)       ? FLAG_BAD_STATE : 0;
-        const bool live = f == 0;
-        int tenths = 10 * (popc32(s[j]) + popc32(s[j] & p.deg3));                 // network.py:87-92
-        const bool acts = (uint32_t)a[j] < na;                                    // network.py:101-112
-        const bool restart = (a[j] & 1) != 0;
-        const uint32_t mbit = 1u << ((a[j] >> 1) & 31);
-        const uint32_t h = hit[j] ? 1u : 0u;
-        uint32_t n2 = nw[j];
-        if (acts && restart) n2 |= mbit;
-        const uint32_t bit = (n2 & mbit) ? 1u : 0u;
-        const uint32_t o = acts ? (restart ? h : (bit ^ h ^ 1u)) : 2u;
-        tenths -= acts ? (restart ? 25 : 1) : 0;
-        fl[j] = f;
-        s2[j] = live ? n2 : s[j];
-        ob[j] = live ? (int32_t)o : 0;
-        rw[j] = live ? tenths_to_float(tenths) : 0.f;
+        stray |= s[j];
+        amax = (uint32_t)a[j] > amax ? (uint32_t)a[j] : amax;
+    }
+    if (((stray & ~all) == 0) & (amax <= na)) {            // nothing to flag in any of the L envs: the common case
+        POMDP_UNROLL
+        for (int j = 0; j < L; ++j) {
+            const uint32_t h = (p.ob_any && word_of(qa, lane0 + j) <= p.om1) ? 1u : 0u;
+            network_finish<true>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
+        }
+    } else {
+        POMDP_UNROLL
+        for (int j = 0; j < L; ++j) {
+            const uint32_t h = (p.ob_any && word_of(qa, lane0 + j) <= p.om1) ? 1u : 0u;
+            network_finish<false>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
+        }
     }
 }
 

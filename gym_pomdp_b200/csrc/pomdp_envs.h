@@ -17,6 +17,7 @@ struct RockEnvT {
     typedef RockDev Params;
     typedef S State;
     static constexpr bool kTable = true;             // table built on the host, staged per CTA by one TMA bulk copy
+    static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params& p, const unsigned char* tbl, S s, uint32_t w) {   // rock.py:273-291
         return rock_policy<S>(p, reinterpret_cast<const RockTableHdr*>(tbl),
                               reinterpret_cast<const RockLut*>(tbl + ROCK_LUT_OFFSET), s, w);
@@ -83,6 +84,7 @@ struct TagEnvT {
     typedef TagDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = true;             // TagTables: built on the host, staged per CTA by one TMA bulk copy
+    static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tag.py:228-229
         return (int32_t)rand_below(w, 5u);
     }
@@ -132,6 +134,7 @@ struct TagNoTable {
     typedef TagDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
+    static constexpr bool kParamTable = false;
     static POMDP_HD double obs_prob(const Params& p, const unsigned char*, State s, int32_t, int32_t ob, double) {
         return tag_obs_prob(p, s, ob);
     }
@@ -143,6 +146,7 @@ struct TigerEnvP {
     typedef TigerDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
+    static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tiger.py:111-112
         return (int32_t)rand_below(w, 3u);
     }
@@ -184,6 +188,24 @@ struct NetworkEnvP {
     typedef NetworkDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
+    // the step's tables (alias columns of the joint failure draw, neighbour-down map: 2.8 KB) travel inside the kernel
+    // parameters and are copied to shared memory once per CTA by the kernels that step (step, rollout)
+    static constexpr bool kParamTable = true;
+    static constexpr uint32_t kParamTableBytes = (uint32_t)sizeof(NetworkTables);
+    static POMDP_HD const void* param_table(const Params& p) { return &p.t; }
+#if defined(__CUDA_ARCH__)
+    typedef NetTabSmem Tab;
+    static __device__ __forceinline__ Tab tables(const Params&, const unsigned char* tbl) {      // staged in shared memory
+        uint32_t base;                                           // opaque to the optimiser, or it is re-derived per lookup
+        asm("mov.u32 %0, %1;" : "=r"(base) : "r"((uint32_t)__cvta_generic_to_shared(tbl)));
+        return Tab{base};
+    }
+#else
+    typedef NetTabPtr Tab;
+    static POMDP_HD Tab tables(const Params& p, const unsigned char* tbl) {
+        return Tab{tbl ? reinterpret_cast<const NetworkTables*>(tbl) : &p.t};
+    }
+#endif
     static POMDP_HD int32_t policy(const Params& p, const unsigned char*, State, uint32_t w) {     // network.py:129-130
         return (int32_t)rand_below(w, (uint32_t)(2 * p.n + 1));
     }
@@ -204,15 +226,15 @@ struct NetworkEnvP {
         const double t = (double)rw * 10.0;
         return (double)(long long)(t < 0 ? t - 0.5 : t + 0.5) / 10.0;
     }
-    static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
+    static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
-        network_step_n<4>(p, s, a, seed, group, 0, ctr, s2, ob, rw, fl);
+        network_step_n<4, Tab>(p, tables(p, tbl), s, a, seed, group, 0, ctr, s2, ob, rw, fl);
     }
-    static POMDP_HD void step1(const Params& p, const unsigned char*, State s, int32_t a, const PhiloxKey& seed,
+    static POMDP_HD void step1(const Params& p, const unsigned char* tbl, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
-        network_step_n<1>(p, &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
+        network_step_n<1, Tab>(p, tables(p, tbl), &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
     }
     static POMDP_HD void reset4(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State s[4],
                                                   int32_t ob[4]) {

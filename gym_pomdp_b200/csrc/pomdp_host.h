@@ -205,6 +205,51 @@ inline int make_tiger(const PomdpTigerParams* q, TigerDev* d) {
     return 0;
 }
 
+// The alias table of the joint failure draw (include/pomdp_b200.h, "Network draws"), in integer arithmetic only so that
+// every implementation of the contract (this one, oracle/philox.py, oracle/pomdp_oracle.c) produces the same 256 columns.
+//   digit counts  c0 = lo, c1 = hi - lo, c2 = 2^32 - hi          (lo = min(T_p, T_q), hi = max: u < lo / lo <= u < hi / else)
+//   outcome k = sum d_i 3^i (d_i = digit of machine 5g + i), weight W[k] = (((c[d0] * c[d1] >> 32) * c[d2] >> 32) ...)
+//   Vose over 256 columns with V[k] = 256 W[k] (0 for k >= 243) against the column mean S = sum W: small columns
+//   (V < S, ascending k) and large ones are paired from the END of their lists; thr24 = floor(V * 2^24 / S).
+inline void network_alias_table(uint64_t T_p, uint64_t T_q, NetAlias out[NET_COLS]) {
+    const uint64_t lo = T_p < T_q ? T_p : T_q, hi = T_p < T_q ? T_q : T_p;
+    const uint64_t c[3] = {lo, hi - lo, (1ull << 32) - hi};
+    uint64_t V[NET_COLS] = {0}, S = 0;
+    uint32_t own[NET_COLS] = {0};
+    for (int k = 0; k < NET_CODES; ++k) {
+        uint64_t a = 1ull << 32;
+        uint32_t m_lo = 0, m_hi = 0;
+        for (int i = 0, r = k; i < NET_GROUP; ++i, r /= 3) {
+            const int d = r % 3;
+            a = c[d] == (1ull << 32) ? a : (a * c[d]) >> 32;      // a <= 2^32 and c[d] < 2^32 here: no overflow
+            if (d == 0) m_lo |= 1u << i;
+            if (d <= 1) m_hi |= 1u << i;
+        }
+        V[k] = a;
+        S += a;
+        own[k] = m_lo | (m_hi << NET_GROUP);
+    }
+    int small[NET_COLS], large[NET_COLS], ns = 0, nl = 0, alias[NET_COLS];
+    uint32_t thr24[NET_COLS];
+    for (int k = 0; k < NET_COLS; ++k) {
+        V[k] *= NET_COLS;
+        alias[k] = k;
+        thr24[k] = 0;                                              // a column that keeps its own outcome: alias = itself
+        if (V[k] < S) small[ns++] = k; else large[nl++] = k;
+    }
+    while (ns > 0 && nl > 0) {
+        const int sidx = small[--ns], lidx = large[--nl];
+        thr24[sidx] = (uint32_t)((V[sidx] << 24) / S);              // V < S <= 2^32: fits
+        alias[sidx] = lidx;
+        V[lidx] -= S - V[sidx];
+        if (V[lidx] < S) small[ns++] = lidx; else large[nl++] = lidx;
+    }
+    for (int k = 0; k < NET_COLS; ++k) {
+        out[k].thr = thr24[k] << 8;
+        out[k].masks = own[k] | (own[alias[k]] << 16);
+    }
+}
+
 inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     if (!q) return fail(POMDP_E_BADARG, "network: params is NULL");
     const int n = q->n_machines;
@@ -215,8 +260,8 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     d->q_T = bern_T(q->q);
     d->ob_T = bern_T(q->p_ob);
     d->p_ob = q->p_ob;
-    d->pm1 = (uint32_t)(d->p_T - 1); d->qm1 = (uint32_t)(d->q_T - 1); d->om1 = (uint32_t)(d->ob_T - 1);
-    d->all_T_nonzero = d->p_T != 0 && d->q_T != 0 && d->ob_T != 0;
+    d->ob_any = d->ob_T != 0;
+    d->om1 = (uint32_t)(d->ob_T - 1);
     int deg[NETWORK_MAX] = {0};
     auto link = [&](int i, int j) { d->nb[i] |= 1u << j; ++deg[i]; };
     if (q->problem_type == 3) {                     // network.py:153-168
@@ -231,6 +276,19 @@ inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
     }
     for (int i = 0; i < n; ++i)
         if (deg[i] > 2) d->deg3 |= 1u << i;         // len(neighbours) counts duplicates too (network.py:89)
+    d->groups = (n + NET_GROUP - 1) / NET_GROUP;
+    d->cond_flip = d->q_T < d->p_T ? 0xFFFFFFFFu : 0u;
+    // nbd[g][v]: the machines with a neighbour among the DOWN machines {5g + i : bit i of v} (network.py:81-84 is an OR
+    // over neighbours, hence OR-linear in the down set: one lookup per group of five machines instead of one test per machine)
+    for (int g = 0; g < d->groups; ++g)
+        for (uint32_t v = 0; v < 32; ++v) {
+            const uint32_t down = v << (NET_GROUP * g);
+            uint32_t m = 0;
+            for (int i = 0; i < n; ++i)
+                if (d->nb[i] & down) m |= 1u << i;
+            d->t.nbd[g][v] = m;
+        }
+    network_alias_table(d->p_T, d->q_T, d->t.alias);
     return 0;
 }
 

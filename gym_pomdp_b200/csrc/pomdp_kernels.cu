@@ -150,6 +150,18 @@ __device__ __forceinline__ void store_state1(int32_t* base, int64_t i, uint64_t 
     base[2 * i + 1] = (int32_t)(s >> 32);
 }
 
+// Envs whose static tables travel inside the kernel parameters (Network: 2.8 KB) copy them to shared memory once per
+// CTA: the lookups are per-thread divergent, which the constant bank would serialise.
+template <class Env>
+__device__ __forceinline__ void stage_param_table(unsigned char* smem_table, const typename Env::Params& p) {
+    if constexpr (Env::kParamTable) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Env::param_table(p));
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_table);
+        for (uint32_t i = threadIdx.x; i < Env::kParamTableBytes / 4; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------- step (streams) ---
 // kVec: all six arrays are 16-byte aligned and global_offset is a multiple of 4 -> every
 // thread owns aligned groups of FOUR envs (16-byte vector loads/stores, one Philox call per
@@ -177,6 +189,7 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
         }
         __syncthreads();   // barrier object initialised before anyone polls it
     }
+    stage_param_table<Env>(smem_table, p);
 
     pdl_wait();                // everything above overlapped the previous kernel's tail; state/action may be its outputs
     pdl_launch_dependents();
@@ -373,6 +386,7 @@ pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void*
     extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
     stage_table_sync<Env>(smem_table, g_table, table_bytes, &bar);
+    stage_param_table<Env>(smem_table, p);
     const unsigned char* tbl = smem_table;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -1203,6 +1217,11 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t s
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+template <class Env>
+constexpr size_t param_table_smem() {
+    if constexpr (Env::kParamTable) return Env::kParamTableBytes; else return 0;
+}
+
 template <class Env, bool kPacked = false>
 int launch_step(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
                 const int32_t* state,
@@ -1216,7 +1235,7 @@ int launch_step(const typename Env::Params& p, const void* d_table, uint32_t tab
     if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
         return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = Env::kTable ? smem_bytes : 0;
+    const size_t smem = Env::kTable ? smem_bytes : param_table_smem<Env>();
     const PhiloxKey key = philox_key(seed);
     if (aligned16(state, action, next_state, obs, reward, flags) && (goff & 3) == 0) {
         auto k = pomdp_step_kernel<Env, true, kPacked>;
@@ -1293,7 +1312,7 @@ int launch_rollout(const typename Env::Params& p, const void* d_table, uint32_t 
     if (n == 0) return 0;
     if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
         return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
-    const size_t smem = Env::kTable ? smem_bytes : 0;
+    const size_t smem = Env::kTable ? smem_bytes : param_table_smem<Env>();
     const PhiloxKey key = philox_key(seed);
     const uintptr_t any = (uintptr_t)state | (uintptr_t)final_state | (uintptr_t)ret | (uintptr_t)steps | (uintptr_t)flags;
     if ((any & 15) == 0 && (goff & 3) == 0) {

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 6
+#define POMDP_ABI_VERSION 7
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -224,8 +224,24 @@ typedef struct PomdpNetworkParams {
     double  p, q, p_ob;     /* .1, .33, .95 (network.py:28-29, 57-59)                    */
 } PomdpNetworkParams;
 /* State: 1 word, bit m = machine m is up; bit 31 done (never set: network.py never ends).
- * NetworkEnv.step network.py:71-114.  Slot m = machine m's failure draw, slot n = the
- * action's observation draw.  reward is float32 of (tenths / 10).                         */
+ * NetworkEnv.step network.py:71-114.  reward is float32 of (tenths / 10).
+ *
+ * Network draws.  The reference draws binomial(1, p) -- or binomial(1, q) when a neighbour is down -- once per
+ * machine (network.py:94-99).  For one machine that is one uniform u against the two thresholds T_p = ceil(p 2^32),
+ * T_q = ceil(q 2^32), i.e. three outcomes ("digits"): 0 = u < lo (fails either way), 1 = lo <= u < hi (fails only
+ * under the larger probability), 2 = stays up, with lo = min(T_p, T_q), hi = max.  Machines are independent, so the
+ * 3^5 = 243 joint outcomes of FIVE machines are drawn from ONE 32-bit word through an alias table:
+ *   slot g (g < G = ceil(n / 5)) decides machines 5g .. 5g+4;  slot G is the action's observation draw ([w < T_ob]).
+ *   column = w & 255;  outcome = column if w < thr24[column] << 8 (or the column is its own alias) else alias[column];
+ *   outcome k = sum d_i 3^i, d_i = digit of machine 5g + i.
+ * The table is built in integer arithmetic only (every implementation produces the same 256 columns):
+ *   counts c = (lo, hi - lo, 2^32 - hi);  weight W[k] = chained product a <- (a * c[d_i]) >> 32 from a = 2^32;
+ *   V[k] = 256 W[k] (0 for k >= 243), S = sum W;  Vose's pairing with the small (V < S) and the large columns listed
+ *   in ascending k and paired from the END of both lists: thr24[s] = floor(V[s] 2^24 / S), alias[s] = l,
+ *   V[l] -= S - V[s], l re-listed as small or large.
+ * The outcome probabilities differ from the exact products by < 2^-24 (each of the 256 columns' 24-bit thresholds is
+ * off by < 2^-32 of probability mass); 7.5e-9 at the reference's p = .1, q = .33 -- computed in exact rational
+ * arithmetic by tests/test_network_draws.py.  3 Philox calls per four 10-machine envs instead of 11.             */
 int pomdp_network_step(const PomdpNetworkParams* params,
                        const int32_t* state, const int32_t* action,
                        int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,

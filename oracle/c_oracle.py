@@ -49,6 +49,20 @@ def fill_env_draws(seed, global_offset, n, step, domain, n_slots):
     return out
 
 
+def network_draws(seed, global_offset, n, step, n_machines, p=0.1, q=0.33):
+    """uint32 [n, n_machines + 1]: the per-machine words + the observation word of Network's joint failure draw."""
+    out = np.empty((n, n_machines + 1), np.uint32)
+    lib().oracle_network_draws(c_uint64(seed), c_uint64(global_offset), c_int64(n), c_uint32(step), c_int(n_machines),
+                               c_double(p), c_double(q), _p(out))
+    return out
+
+
+def network_alias(p=0.1, q=0.33):
+    thr24, alias = np.empty(256, np.uint32), np.empty(256, np.int32)
+    lib().oracle_network_alias(c_double(p), c_double(q), _p(thr24), _p(alias))
+    return thr24, alias
+
+
 def philox(ctr, key):
     out = np.zeros(4, np.uint32)
     lib().oracle_philox_kat(_p(_c(ctr, np.uint32)), _p(_c(key, np.uint32)), _p(out))

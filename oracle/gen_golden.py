@@ -423,7 +423,8 @@ def gen_network(E, n, ptype, tag, exhaustive):
     rs = rng_ints(R, 1 << n, 31); ra = rng_ints(R, A, 32)
     sts += [int(v) for v in rs]; acts += [int(v) for v in ra]
     N = len(sts)
-    dr = words(N, n + 1, stream=14)
+    # the per-machine words of the joint failure draw (slot g = machines 5g..5g+4) + the observation draw's word
+    dr = philox.network_draws(SEED, np.arange(N), 14, n, env._p, env._q)
     s2, ob, rw, prob = [], [], [], []
     for i in range(N):
         bits = np.array([(sts[i] >> m) & 1 for m in range(n)], np.int8)

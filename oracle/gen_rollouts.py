@@ -34,8 +34,9 @@ def W(e, ctr, domain, n_slots):
     return philox.draw_slots(SEED, np.array([e]), ctr, domain, n_slots)[0]
 
 
-def run(env, d, e, T, n_step_slots, feed_step, snapshot, gamma=None):
-    """One episode of the reference's loop.  feed_step(words, action) scripts the step's draws."""
+def run(env, d, e, T, n_step_slots, feed_step, snapshot, gamma=None, step_words=None):
+    """One episode of the reference's loop.  feed_step(words, action) scripts the step's draws; step_words(e, ctr)
+    replaces the plain slot words (Network: the per-machine words of the joint failure draw)."""
     gamma = env._discount if gamma is None else gamma
     r, disc, t, acts, done = 0.0, 1.0, 0, [], False
     while t < T and not done:
@@ -45,7 +46,7 @@ def run(env, d, e, T, n_step_slots, feed_step, snapshot, gamma=None):
         d.feed([W(e, ctr, philox.DOMAIN_POLICY, 1)[0]])
         a = int(np.random.choice(legal))                       # scripted: legal[floor(u * len)]
         d.clear()
-        feed_step(W(e, ctr, philox.DOMAIN_STEP, n_step_slots), a)
+        feed_step(step_words(e, ctr) if step_words else W(e, ctr, philox.DOMAIN_STEP, n_step_slots), a)
         ob, rw, done, info = env.step(a)
         d.clear()
         r += rw * disc
@@ -155,7 +156,8 @@ def gen_network(E, out, M, T):
 
         def feed_step(w, a):                                    # one draw per UP machine in index order, then the action's
             d.feed([w[m] for m in range(n) if env.state[m]] + ([w[n]] if a < 2 * n else []))
-        r, t, acts, done, s1 = run(env, d, e, T, n + 1, feed_step, lambda: int(sum(int(v) << m for m, v in enumerate(env.state))))
+        r, t, acts, done, s1 = run(env, d, e, T, n + 1, feed_step, lambda: int(sum(int(v) << m for m, v in enumerate(env.state))),
+                                   step_words=lambda e_, ctr: philox.network_draws(SEED, np.array([e_]), ctr, n, env._p, env._q)[0])
         assert not done
         for key, v in zip(res, (r, t, acts, s1)):
             res[key].append(v)

@@ -93,6 +93,100 @@ def draw_env_slots(seed, env, step, domain, n_slots):
     return out
 
 
+# ---------------------------------------------------------------------------------------
+# Network: the joint failure draw (include/pomdp_b200.h, "Network draws")
+# ---------------------------------------------------------------------------------------
+# The reference draws binomial(1, p or q) once per machine (network.py:94-99).  One machine is
+# one uniform u against the two thresholds T_p, T_q -- three outcomes ("digits"): 0 = u < lo
+# (fails either way), 1 = lo <= u < hi (fails only under the larger probability), 2 = stays up,
+# with lo = min(T_p, T_q), hi = max.  The kernels sample the 3^5 joint outcomes of FIVE machines
+# from ONE 32-bit word through a 256-column alias table built in integer arithmetic; slot g of
+# the step domain decides machines 5g..5g+4, slot ceil(n/5) is the observation draw.
+NET_GROUP = 5
+NET_CODES = 243
+NET_COLS = 256
+
+
+def bern_T(p):
+    """ceil(p * 2^32) clipped to [0, 2^32] (p * 2^32 is exact in a double)."""
+    import math
+    return max(0, min(1 << 32, math.ceil(p * 4294967296.0)))
+
+
+def network_alias(T_p, T_q):
+    """The alias columns: (thr24[256], alias[256]) with column k's own outcome = code k.
+
+    Integer arithmetic only, so every implementation of the contract builds the same table:
+    digit counts c = (lo, hi - lo, 2^32 - hi); weight of code k = sum d_i 3^i is the chained
+    product ((c[d0] * c[d1] >> 32) * c[d2] >> 32) ...; Vose's pairing over V[k] = 256 W[k]
+    against the column mean S = sum W, small (V < S) and large columns listed in ascending k
+    and paired from the END of their lists; thr24 = floor(V * 2^24 / S)."""
+    lo, hi = min(T_p, T_q), max(T_p, T_q)
+    c = (lo, hi - lo, (1 << 32) - hi)
+    V = [0] * NET_COLS
+    for k in range(NET_CODES):
+        a, r = 1 << 32, k
+        for _ in range(NET_GROUP):
+            a = (a * c[r % 3]) >> 32
+            r //= 3
+        V[k] = a
+    S = sum(V)
+    V = [v * NET_COLS for v in V]
+    alias = list(range(NET_COLS))
+    thr24 = [0] * NET_COLS
+    small = [k for k in range(NET_COLS) if V[k] < S]
+    large = [k for k in range(NET_COLS) if V[k] >= S]
+    while small and large:
+        s_, l_ = small.pop(), large.pop()
+        thr24[s_] = (V[s_] << 24) // S
+        alias[s_] = l_
+        V[l_] -= S - V[s_]
+        (small if V[l_] < S else large).append(l_)
+    return thr24, alias
+
+
+def network_alias_distribution(T_p, T_q):
+    """Exact probability (a Fraction) of every code under the alias table: the distribution the kernels sample."""
+    from fractions import Fraction
+    thr24, alias = network_alias(T_p, T_q)
+    q = [Fraction(0)] * NET_COLS
+    for k in range(NET_COLS):
+        f = Fraction(thr24[k], 1 << 24) if alias[k] != k else Fraction(1)
+        q[k] += f / NET_COLS
+        if alias[k] != k:
+            q[alias[k]] += (1 - f) / NET_COLS
+    return q
+
+
+def network_digits(words, T_p, T_q):
+    """uint32 [N, G] joint draw words -> int [N, 5 G] digits (machine 5g + i <- digit i of word g's code)."""
+    thr24, alias = network_alias(T_p, T_q)
+    thr = np.asarray(thr24, dtype=np.uint64) << np.uint64(8)
+    own = np.arange(NET_COLS)
+    al = np.asarray(alias)
+    words = np.asarray(words, dtype=np.uint64)
+    col = (words & np.uint64(NET_COLS - 1)).astype(np.int64)
+    code = np.where((words < thr[col]) | (al[col] == own[col]), own[col], al[col])
+    digits = np.stack([(code // 3 ** i) % 3 for i in range(NET_GROUP)], axis=-1)      # [N, G, 5]
+    return digits.reshape(words.shape[0], -1)
+
+
+def network_draws(seed, env, step, n_machines, p=0.1, q=0.33):
+    """uint32 [len(env), n_machines + 1]: per-machine words that make ``word / 2^32 < p`` (resp. ``< q``) reproduce the
+    joint draw's digits -- 0 for digit 0, lo for digit 1, hi for digit 2 -- followed by the observation draw's word.
+    This is what the oracle's network_step (one binomial per machine, like the reference) consumes."""
+    T_p, T_q = bern_T(p), bern_T(q)
+    lo, hi = min(T_p, T_q), max(T_p, T_q)
+    G = (n_machines + NET_GROUP - 1) // NET_GROUP
+    w = draw_slots(seed, env, step, DOMAIN_STEP, G + 1)
+    digits = network_digits(w[:, :G], T_p, T_q)[:, :n_machines]
+    rep = np.array([0, lo, min(hi, 0xFFFFFFFF)], dtype=np.uint64)     # digit 2 has probability 0 when hi = 2^32
+    out = np.empty((w.shape[0], n_machines + 1), dtype=np.uint32)
+    out[:, :n_machines] = rep[digits].astype(np.uint32)
+    out[:, n_machines] = w[:, G]
+    return out
+
+
 def kat():
     """Known-answer vectors of Random123 (kat_vectors, philox4x32 10 rounds)."""
     vecs = [

@@ -81,6 +81,70 @@ void oracle_fill_env_draws(uint64_t seed, uint64_t global_offset, int64_t n, uin
     }
 }
 
+/* ---- Network: the joint failure draw (include/pomdp_b200.h, "Network draws") ----------------------------------
+ * The reference draws binomial(1, p or q) once per machine (network.py:94-99): per machine one uniform against the
+ * two thresholds, i.e. three outcomes ("digits": 0 = below both, 1 = between them, 2 = above both).  The kernels
+ * sample the 3^5 joint outcomes of five machines from ONE draw word through a 256-column alias table; this is the
+ * same table built the same way (integer arithmetic only), and oracle_network_draws() turns the words into
+ * per-machine words (0 / lo / hi) that make `word / 2^32 < p` reproduce the digits for oracle_network_step(). */
+static uint64_t bern_T(double p) {
+    if (!(p > 0.0)) return 0;
+    if (p >= 1.0) return 1ull << 32;
+    return (uint64_t)ceil(p * TWO32);
+}
+void oracle_network_alias(double p, double q, uint32_t thr24[256], int32_t alias[256]) {
+    const uint64_t Tp = bern_T(p), Tq = bern_T(q), lo = Tp < Tq ? Tp : Tq, hi = Tp < Tq ? Tq : Tp;
+    const uint64_t c[3] = {lo, hi - lo, (1ull << 32) - hi};
+    uint64_t V[256], S = 0;
+    int small[256], large[256], ns = 0, nl = 0;
+    for (int k = 0; k < 256; ++k) {
+        uint64_t a = 0;
+        if (k < 243) {
+            a = 1ull << 32;
+            for (int i = 0, r = k; i < 5; ++i, r /= 3)
+                a = (uint64_t)(((unsigned __int128)a * c[r % 3]) >> 32);
+        }
+        V[k] = a;
+        S += a;
+    }
+    for (int k = 0; k < 256; ++k) {
+        V[k] *= 256;
+        alias[k] = k;
+        thr24[k] = 0;
+        if (V[k] < S) small[ns++] = k; else large[nl++] = k;
+    }
+    while (ns > 0 && nl > 0) {
+        const int s_ = small[--ns], l_ = large[--nl];
+        thr24[s_] = (uint32_t)((V[s_] << 24) / S);
+        alias[s_] = l_;
+        V[l_] -= S - V[s_];
+        if (V[l_] < S) small[ns++] = l_; else large[nl++] = l_;
+    }
+}
+/* out: uint32 [N, n_machines + 1] -- per-machine words, then the observation draw's word (slot ceil(n / 5)). */
+void oracle_network_draws(uint64_t seed, uint64_t global_offset, int64_t N, uint32_t step, int n_machines, double p,
+                          double q, uint32_t* out) {
+    uint32_t thr24[256];
+    int32_t alias[256];
+    const uint64_t Tp = bern_T(p), Tq = bern_T(q), lo = Tp < Tq ? Tp : Tq, hi = Tp < Tq ? Tq : Tp;
+    const uint32_t rep[3] = {0u, (uint32_t)lo, hi > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)hi};
+    const int G = (n_machines + 4) / 5;
+    oracle_network_alias(p, q, thr24, alias);
+    for (int64_t i = 0; i < N; ++i) {
+        const uint64_t env = global_offset + (uint64_t)i, group = env >> 2;
+        uint32_t* o = out + i * (n_machines + 1);
+        for (int g = 0; g <= G; ++g) {
+            uint32_t cc[4] = {(uint32_t)group, (uint32_t)(group >> 32), step, (uint32_t)g};      /* domain 0 (step) */
+            philox4x32_10(cc, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t w = cc[env & 3];
+            if (g == G) { o[n_machines] = w; break; }
+            const int col = (int)(w & 255u);
+            int code = (alias[col] == col || (uint64_t)w < ((uint64_t)thr24[col] << 8)) ? col : alias[col];
+            for (int k = 0; k < 5 && 5 * g + k < n_machines; ++k, code /= 3) o[5 * g + k] = rep[code % 3];
+        }
+    }
+}
+
 static int bern(uint32_t r, double p) { return (double)r / TWO32 < p; }          /* np.random.binomial(1, p) */
 static int below(uint32_t r, int n) { return (int)(((uint64_t)r * (uint64_t)n) >> 32); } /* randint(n) */
 
@@ -611,7 +675,7 @@ int oracle_network_rollout(int n, int problem_type, double p, double q, double p
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 2 * n + 1), ob;   /* network.py:129-130 */
             double rw;
             if (t == 0 && first_action) a = first_action[i];
-            for (int s = 0; s <= n; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
+            oracle_network_draws(seed, goff + (uint64_t)i, 1, ctr0 + (uint32_t)t, n, p, q, dr);
             if (oracle_network_step(n, problem_type, p, q, p_ob, 1, machines + i * n, &a, dr, &ob, &rw)) return -1;
             r += rw * disc;
             disc *= gamma;

@@ -260,13 +260,13 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
         if ((env & 3) == 0 && i + 4 <= n && ((i >> 2) & 1) == 0) {
             uint32_t s4[4], s2[4];
             for (int j = 0; j < 4; ++j) s4[j] = (uint32_t)state[i + j];
-            network_step_n<4>(d, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
+            network_step_n<4>(d, NetTabPtr{&d.t}, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
             for (int j = 0; j < 4; ++j) next[i + j] = (int32_t)s2[j];
             i += 3;
             continue;
         }
         uint32_t s1 = (uint32_t)state[i], s2;
-        network_step_n<1>(d, &s1, action + i, key, env >> 2, (int)(env & 3), step, &s2, obs + i, rw + i, fl + i);
+        network_step_n<1>(d, NetTabPtr{&d.t}, &s1, action + i, key, env >> 2, (int)(env & 3), step, &s2, obs + i, rw + i, fl + i);
         next[i] = (int32_t)s2;
     }
     return 0;

@@ -408,10 +408,12 @@ def test_rock_reset_codes_one_lop3_equals_per_rock_definition():
         assert [(int(fast[i]) >> (2 * r)) & 3 for r in range(15)] == codes, hex(int(w[i]))
 
 
-@pytest.mark.parametrize("probs", [(0.0, 0.5, 1.0), (1.0, 1.0, 0.0), (0.25, 0.0, 0.5)])
+@pytest.mark.parametrize("probs", [(0.0, 0.5, 1.0), (1.0, 1.0, 0.0), (0.25, 0.0, 0.5), (0.33, 0.1, 0.95), (1.0, 0.0, 0.5),
+                                   (0.0, 0.0, 0.0), (0.5, 0.5, 0.5)])
 def test_network_probabilities_of_exactly_zero_and_one(backend, probs):
-    """T = 0 (never fires) takes the 64-bit compare, T = 2^32 (always fires) the 32-bit one; both must agree with the
-    oracle.  The reference hard-codes p, q, p_ob (network.py:27-38); the C ABI takes them as parameters."""
+    """Probabilities of exactly 0 and 1 (alias columns of weight 0, an outcome of weight 1), q < p (the larger
+    probability then belongs to "no neighbour down") and p == q must agree with the oracle.  The reference hard-codes
+    p, q, p_ob (network.py:27-38); the C ABI takes them as parameters."""
     from oracle import c_oracle as C, philox
     n, ptype, B = 10, 3, 4096
     env = gp.make("Network-v0", n_machines=n, problem_type=ptype, batch_size=B, device=backend, seed=11)
@@ -421,7 +423,7 @@ def test_network_probabilities_of_exactly_zero_and_one(backend, probs):
     action = torch.randint(0, 2 * n + 1, (B,), generator=g).int()
     ns, ob, rw, fl = env.simulate(s0.to(backend), action.to(backend), step_ctr=3)
     bits = ((s0.numpy()[:, None] >> np.arange(n)) & 1).astype(np.int8)
-    em, eob, erw = C.network_step(n, ptype, bits, action.numpy(), C.fill_draws(11, 0, B, 3, philox.DOMAIN_STEP, n + 1), *probs)
+    em, eob, erw = C.network_step(n, ptype, bits, action.numpy(), C.network_draws(11, 0, B, 3, n, probs[0], probs[1]), *probs)
     assert np.array_equal(ns.cpu().numpy(), (em.astype(np.int64) << np.arange(n)).sum(1).astype(np.int32))
     assert np.array_equal(ob.cpu().numpy(), eob)
     assert np.array_equal(rw.cpu().numpy(), erw.astype(np.float32))

@@ -155,7 +155,7 @@ def test_tiger_and_network_batch_2p20(backend):
         action = dev_ints(g, 0, 2 * n + 1, (B,), backend).int()
         ns, ob, rw, fl = env.simulate(s0.int(), action, step_ctr=7)
         bits = ((s0.cpu().numpy()[:, None] >> np.arange(n)) & 1).astype(np.int8)
-        em, eob, erw = C.network_step(n, ptype, bits, action.cpu().numpy(), C.fill_draws(SEED, 0, B, 7, philox.DOMAIN_STEP, n + 1))
+        em, eob, erw = C.network_step(n, ptype, bits, action.cpu().numpy(), C.network_draws(SEED, 0, B, 7, n))
         assert np.array_equal(ns.cpu().numpy(), (em.astype(np.int64) << np.arange(n)).sum(1).astype(np.int32))
         assert np.array_equal(ob.cpu().numpy(), eob)
         assert np.array_equal(rw.cpu().numpy(), erw.astype(np.float32))       # float32(the reference's double)

@@ -193,7 +193,8 @@ def test_network_episode_matches_oracle(backend):
         a = int(rs.randint(0, 21))
         ctr += 1
         ob, rw, done, info = env.step(a)
-        state, eob, tenths, _ = O.network_step(state, a, words(ctr, philox.DOMAIN_STEP), nb)
+        w = philox.network_draws(SEED, np.arange(1), ctr, 10)[0]
+        state, eob, tenths, _ = O.network_step(state, a, lambda slot: int(w[slot]), nb)
         assert (ob, done) == (eob, False)
         assert rw == tenths / 10.0                                  # the reference's double, exactly
         assert list(info["state"]) == state
