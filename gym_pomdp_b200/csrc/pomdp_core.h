@@ -891,14 +891,14 @@ POMDP_HD void network_step_n(const NetworkDev& p, const Tab& T, const uint32_t s
                              const PhiloxKey& seed, uint64_t group, int lane0, uint32_t step,
                              uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
     const uint32_t all = (1u << p.n) - 1u;
-    uint32_t fail[L], cond[L];
+    uint32_t fail[L], cond[L], down[L];
     POMDP_UNROLL
-    for (int j = 0; j < L; ++j) { cond[j] = 0; fail[j] = 0; }
+    for (int j = 0; j < L; ++j) { cond[j] = 0; fail[j] = 0; down[j] = ~s[j] & all; }
     POMDP_UNROLL
     for (int g = 0; g < NET_MAX_GROUPS; ++g)
         if (g < p.groups) {                                                           // uniform branch; network.py:81-84
             POMDP_UNROLL
-            for (int j = 0; j < L; ++j) cond[j] |= T.nbd(g, ((~s[j] & all) >> (NET_GROUP * g)) & 31u);
+            for (int j = 0; j < L; ++j) cond[j] |= T.nbd(g, (down[j] >> (NET_GROUP * g)) & 31u);
         }
     POMDP_UNROLL
     for (int j = 0; j < L; ++j) cond[j] ^= p.cond_flip;         // machines that face the larger of the two probabilities
