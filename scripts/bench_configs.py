@@ -245,12 +245,15 @@ def main():
     ap.add_argument("--only", default=None, help="substring filter on the label")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--quick", action="store_true", help="few launches per kernel (for runs under ncu)")
+    ap.add_argument("--kernels", default=None, help="comma-separated subset of step,step_packed,reset,belief_hist,rollout")
     args = ap.parse_args()
     global QUICK
     QUICK = args.quick
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     kernels = ("step", "step_packed", "reset", "belief_hist") + (() if args.no_rollout else ("rollout",))
+    if args.kernels:
+        kernels = tuple(k for k in kernels if k in args.kernels.split(","))
     rows, peak, peak_src = run_configs(dev, args.steps, args.only, kernels, emit=lambda r: print(json.dumps(r), flush=True))
     res = {"peak_gbs": peak, "peak_source": peak_src, "gpu": torch.cuda.get_device_name(0), "rows": rows}
     if args.out:
