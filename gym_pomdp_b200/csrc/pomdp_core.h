@@ -804,6 +804,9 @@ struct NetworkDev {
     NetworkTables t;
 };
 constexpr uint32_t NETWORK_DONE = 0x80000000u;
+// NetworkDev travels by value as a __grid_constant__ kernel parameter next to ~200 bytes of other arguments; the
+// classic parameter space is 4 KB
+static_assert(sizeof(NetworkDev) <= 3584, "NetworkDev no longer fits the 4 KB kernel parameter space with the other arguments");
 
 
 // tenths / 10 correctly rounded to float32 without a division: one multiply by 0.1f and one

@@ -79,13 +79,16 @@ int main() {
     CK(cudaStreamCreate(&st));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-    const int64_t sizes[] = {1 << 22, 1 << 24, 1 << 26};
+    const int64_t sizes[] = {1 << 20, 1 << 22, 1 << 24, 1 << 26};
     for (int64_t n : sizes) {
-        const int sets = n == (1 << 22) ? 6 : 2;
+        const int sets = n == (1 << 20) ? 24 : n == (1 << 22) ? 6 : 2;      // rotating sets: > 126 MB of L2 in every case
         std::vector<int4*> bufs(6 * sets);
         for (auto& p : bufs) { CK(cudaMalloc(&p, n * 4)); CK(cudaMemset(p, 1, n * 4)); }
-        const int grid = sms * 2;
-        const int iters = n == (1 << 22) ? 2000 : 400;
+        // the product's grid: at most 2 CTAs of 512 per SM, balanced so that every thread runs the same number of trips
+        const int64_t need = (n / 4 + 511) / 512, cap = (int64_t)sms * 2;
+        const int64_t trips = (need + cap - 1) / cap;
+        const int grid = (int)(need <= cap ? need : (need + trips - 1) / trips);
+        const int iters = n <= (1 << 22) ? 2000 : 400;
         const float t0 = run<false>(n, sets, iters, bufs.data(), st, grid);
         const float t1 = run<true>(n, sets, iters, bufs.data(), st, grid);
         const float t2 = run<false>(n, sets, iters, bufs.data(), st, grid, true);
