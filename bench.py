@@ -480,6 +480,7 @@ def run_b200(args):
                 "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
                 "algorithmic_bytes_per_launch": B * bytes_per_step, "avg_launch_us": per_launch_ms * 1e3,
                 "peak_source": peak_src,
+                "pattern_roof": pattern_roof(22) if (B == 1 << 22 and words == 1) else None,
                 "read_only_frac": (B * (4 * words + 4) / (per_launch_ms * 1e-3) / 1e9) / peak}
 
     cpu = None
@@ -612,6 +613,22 @@ def ncu_traffic(key="dram_bytes_per_launch"):
             return json.load(f).get(key)
     except Exception:  # noqa: BLE001
         return None
+
+
+def pattern_roof(log2_batch=22):
+    """The compute-free probe of the step's traffic pattern (scripts/exp_stream_probe.cu: two read + four write streams, 24 B
+    per env, the product's grid, PDL + graph) from the committed B200 run: what this read:write mix reaches on the part."""
+    import re
+    name = "r04f_stream_probe.log"
+    try:
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            m = re.match(r"n=2\^(\d+) .*graph\+PDL ([0-9.]+) us", line)
+            if m and int(m.group(1)) == log2_batch:
+                return {"us_per_launch": float(m.group(2)), "source": "NOT measured in this run: profiles/" + name +
+                        " (compute-free kernel with the same six streams, graph + PDL)"}
+    except Exception:  # noqa: BLE001
+        pass
+    return None
 
 
 if __name__ == "__main__":
