@@ -64,12 +64,14 @@ inline const RockLayout* rock_layout(int board) {
 inline int rock_words(const PomdpRockParams* q) { return q->num_rocks <= 11 ? 1 : 2; }
 
 inline int rock_rows(const PomdpRockParams* q) { return 16 * (q->board_size - 1) + q->board_size; }  // cells x | y << 4 with x, y < n
+inline int rock_lut_stride(const PomdpRockParams* q) { return (5 + q->num_rocks) | 1; }              // odd row pitch (rock_lut_index)
 inline int64_t rock_table_bytes(const PomdpRockParams* q) {   // what pomdp_rock_build_table fills and the TMA copy moves
-    const int64_t b = (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + (int64_t)rock_rows(q) * (5 + q->num_rocks));
+    const int64_t b = (int64_t)ROCK_LUT_OFFSET +
+                      8 * ((int64_t)ROCK_SPECIALS + (int64_t)rock_rows(q) * rock_lut_stride(q) + ROCK_LUT_SKEW_MAX);
     return (b + 15) & ~(int64_t)15;
 }
 inline int64_t rock_smem_bytes(const PomdpRockParams* q) {
-    return (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + (int64_t)256 * (5 + q->num_rocks));
+    return (int64_t)ROCK_LUT_OFFSET + 8 * ((int64_t)ROCK_SPECIALS + (int64_t)256 * rock_lut_stride(q) + ROCK_LUT_SKEW_MAX + 1);
 }
 inline uint32_t float_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
 inline RockRes rock_result(int reward, int flags, int obs, bool done) {
@@ -105,6 +107,7 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         d->penal = penal;
         d->start = (uint32_t)(L->sx | (L->sy << 4));
         d->n_actions = (uint32_t)n_act;
+        d->lut_stride = (uint32_t)rock_lut_stride(q);
         d->table_bytes = (uint32_t)rock_table_bytes(q);
         d->smem_bytes = (uint32_t)rock_smem_bytes(q);
         const uint64_t T = bern_T(q->p_move);
@@ -163,7 +166,7 @@ inline int make_rock(const PomdpRockParams* q, RockDev* d, void* tbl) {
         const int rows = rock_rows(q);
         for (int cell = 0; cell < rows; ++cell) {
             const int x = cell & 15, y = cell >> 4;
-            RockLut* row = lut + ROCK_SPECIALS + (size_t)cell * n_act;
+            RockLut* row = lut + ROCK_SPECIALS + (size_t)cell * rock_lut_stride(q) + (cell >> 4);        // rock_lut_index(cell, 0)
             for (int a = 0; a < 4; ++a) {                                // rock.py:134-158
                 const int nx = x + move_dx(a), ny = y + move_dy(a);
                 if ((unsigned)nx < (unsigned)n && (unsigned)ny < (unsigned)n)

@@ -1015,16 +1015,17 @@ template <> struct HistShape<POMDP_KIND_BATTLESHIP> { static constexpr int NW = 
 __device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }        // bit i -> byte i
 __device__ __forceinline__ uint32_t spread4_even(uint32_t byte) { return ((byte & 0x55u) * 0x00041041u) & 0x01010101u; }  // bit 2i -> byte i
 
-// n_bits (warp-uniform): the bit bins in use -- counter words past them are skipped (Network-v0 has 10 machines, not 32)
+// (Skipping the counter words past the bins in use -- Network-v0 has 10 machines, not 32 -- was measured and is SLOWER:
+// the uniform branches cost the unrolled loop its instruction-level parallelism, profiles/r04g_hist_guard_variant.log.)
 template <int KIND>
-__device__ __forceinline__ void hist_one(int p0, int n_bits, bool valid, const uint32_t s[4], uint32_t* sh, uint32_t (&acc)[HistShape<KIND>::NW]) {
+__device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4], uint32_t* sh, uint32_t (&acc)[HistShape<KIND>::NW]) {
     if (KIND == POMDP_KIND_ROCK) {                           // bit 2i of `good` = rock i's status is +1 (code 01)
         const uint32_t good0 = (s[0] >> 8) & ~(s[0] >> 9) & 0x00555555u;   // rocks 0..11: bits 8..31 of word 0
         const uint32_t good1 = s[1] & ~(s[1] >> 1) & 0x00000055u;          // rocks 12..15: bits 0..7 of word 1
         acc[0] += spread4_even(good0);
-        if (n_bits > 4) acc[1] += spread4_even(good0 >> 8);
-        if (n_bits > 8) acc[2] += spread4_even(good0 >> 16);
-        if (n_bits > 12) acc[3] += spread4_even(good1);
+        acc[1] += spread4_even(good0 >> 8);
+        acc[2] += spread4_even(good0 >> 16);
+        acc[3] += spread4_even(good1);
         if (valid) atomicAdd(&sh[p0 + (int)(s[0] & 0xFFu)], 1u);
     } else if (KIND == POMDP_KIND_TAG) {
         if (valid) {
@@ -1035,12 +1036,10 @@ __device__ __forceinline__ void hist_one(int p0, int n_bits, bool valid, const u
         acc[0] += valid ? (1u << (8u * (s[0] & 1u))) : 0u;
     } else if (KIND == POMDP_KIND_NETWORK) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (4 * j < n_bits) acc[j] += spread4((s[0] >> (4 * j)) & 0xFu);
+        for (int j = 0; j < 8; ++j) acc[j] += spread4((s[0] >> (4 * j)) & 0xFu);
     } else {                                                 // BattleShip: 120 occupied bits over four words
 #pragma unroll
-        for (int j = 0; j < 30; ++j)
-            if (4 * j < n_bits) acc[j] += spread4((s[j >> 3] >> (4 * (j & 7))) & 0xFu);
+        for (int j = 0; j < 30; ++j) acc[j] += spread4((s[j >> 3] >> (4 * (j & 7))) & 0xFu);
     }
 }
 // adds the warp's packed byte counters to the shared histogram (bins 4j + c < n_bits) and clears them: the bytes of
@@ -1109,13 +1108,13 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t s[4] = {e[j], 0u, 0u, 0u};
-                        hist_one<KIND>(p0, n_bits, valid[u], s, sh, acc);
+                        hist_one<KIND>(p0, valid[u], s, sh, acc);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t s[4] = {e[2 * j], e[2 * j + 1], 0u, 0u};
-                        hist_one<KIND>(p0, n_bits, valid[u], s, sh, acc);
+                        hist_one<KIND>(p0, valid[u], s, sh, acc);
                     }
                 }
                 pending += 4;
@@ -1143,7 +1142,7 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
                 if (words == SHIP_WORDS) s[3] &= 0x00FFFFFFu;
             }
         }
-        hist_one<KIND>(p0, n_bits, valid, s, sh, acc);
+        hist_one<KIND>(p0, valid, s, sh, acc);
         if (++pending > 254) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
     }
     hist_flush<NW>(acc, sh, n_bits, lane);

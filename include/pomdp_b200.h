@@ -92,7 +92,9 @@ int     pomdp_rock_state_words(const PomdpRockParams* params);
 /* Static per-config maps that the step kernel stages into shared memory with one TMA bulk
  * copy per CTA: a 688-byte header (rock-id grid, rock coordinates, sensor thresholds and efficiencies,
  * order of the legal-action list: the reference's own tables) followed by the transition LUT indexed by (agent cell, action)
- * (16.4 KB for <= 11 rocks, 32.8 KB otherwise; layout in gym_pomdp_b200/csrc/pomdp_core.h).
+ * with an odd row pitch and a per-row skew, so that a batch stepped with ONE action does not put every lane on the same
+ * shared-memory bank (12.6 KB for Rock(7,8), 25.1 KB for Rock(11,11), 42.0 KB for Rock(15,15); layout in
+ * gym_pomdp_b200/csrc/pomdp_core.h: rock_lut_index).
  * The caller uploads the filled buffer to the device (16-byte aligned) and passes it as
  * `d_table`.                                                                              */
 int64_t pomdp_rock_table_bytes(const PomdpRockParams* params);
