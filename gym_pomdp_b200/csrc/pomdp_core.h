@@ -499,13 +499,20 @@ POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
 
 // Static maps of the fixed 29-cell board, derived from the functions above on the host (pomdp_host.h:
 // make_tag_table) and staged into shared memory by ONE TMA bulk copy per CTA, like Rock's.
-//   pair[opp * 32 + agent]  (= pair[state & 1023] for the one-opponent env)  bits 5c..5c+4 (c = 0..3): the opponent's cell if element c of the reference's move
+//   pair[opp * 33 + agent]  (= pair[(state & 1023) + opp] for the one-opponent env)  bits 5c..5c+4 (c = 0..3): the opponent's cell if element c of the reference's move
 //                           multiset (tag.py:260-280) is drawn -- the move's target, or `opp` itself when the target
 //                           is off the board (tag.py:206-207);  bits 20-22: the multiset's length
 //   mv[agent]               bits 5a..5a+4 (a = 0..3): the agent's cell after move a (tag.py:133-137)
-// 32 x 32 pair entries so that a corrupt 5-bit cell id reads a zero entry instead of faulting.
+// 32 x 32 pair entries so that a corrupt 5-bit cell id reads a zero entry instead of faulting, at a row pitch of 33:
+// the agent's cell is observed, so the particles of a belief share it and differ in the opponent's cell -- with a
+// pitch of 32 every lane of such a batch would read a different word of the SAME shared-memory bank.
+#ifndef POMDP_TAG_PAIR_PITCH          // 32 reproduces the conflicting layout for the measurement in profiles/
+#define POMDP_TAG_PAIR_PITCH 33
+#endif
+constexpr uint32_t TAG_PAIR_PITCH = POMDP_TAG_PAIR_PITCH;
+POMDP_HD uint32_t tag_pair_index(uint32_t agent, uint32_t opp) { return opp * TAG_PAIR_PITCH + agent; }
 struct TagTables {
-    uint32_t pair[32 * 32];
+    uint32_t pair[32 * TAG_PAIR_PITCH];
     uint32_t mv[32];
 };
 static_assert(sizeof(TagTables) % 16 == 0, "TMA bulk copy needs 16 B multiples");
@@ -538,10 +545,10 @@ POMDP_HD uint32_t tag_mv_entry(int agent) {
     return e;
 }
 POMDP_HD void tag_build_tables(TagTables* T) {
-    for (int i = 0; i < 32 * 32; ++i) {
-        const int opp = i >> 5, agent = i & 31;
-        T->pair[i] = (agent < TAG_CELLS && opp < TAG_CELLS) ? tag_pair_entry(agent, opp) : 0u;   // never 0 for a valid pair
-    }
+    for (uint32_t i = 0; i < 32 * TAG_PAIR_PITCH; ++i) T->pair[i] = 0u;
+    for (int opp = 0; opp < TAG_CELLS; ++opp)
+        for (int agent = 0; agent < TAG_CELLS; ++agent)
+            T->pair[tag_pair_index((uint32_t)agent, (uint32_t)opp)] = tag_pair_entry(agent, opp);   // never 0 for a valid pair
     for (int i = 0; i < 32; ++i) T->mv[i] = i < TAG_CELLS ? tag_mv_entry(i) : 0u;
 }
 
@@ -551,7 +558,7 @@ POMDP_HD void tag_build_tables(TagTables* T) {
 POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w_move,
                             uint32_t w_pick, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     const uint32_t agent = s & 31u, opp = (s >> 5) & 31u;
-    const uint32_t e = T->pair[s & 1023u];                                                // 0 <=> a cell id outside the board
+    const uint32_t e = T->pair[(s & 1023u) + (TAG_PAIR_PITCH - 32u) * opp];               // tag_pair_index; 0 <=> a cell id outside the board
     const uint32_t mvw = T->mv[agent];
     const bool is_tag = a == 4;
     const bool hit = opp == agent;                                                        // tag.py:122-126
@@ -604,7 +611,7 @@ POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_
                 tagged = true;
                 --nopp;
             } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
-                const uint32_t e = T->pair[o * 32u + agent];
+                const uint32_t e = T->pair[tag_pair_index(agent, o)];
                 if (bern(draw(2 * j), p.move_T)) {                                // tag.py:204
                     const uint32_t pick = rand_below(draw(2 * j + 1), e >> 20);   // tag.py:205
                     s2 = (s2 & ~(31u << sh)) | (((e >> (5u * pick)) & 31u) << sh);  // tag.py:206-207
@@ -660,7 +667,7 @@ POMDP_HD void tag_step4_multi(const TagDev& p, const TagTables* __restrict__ T, 
                 tagged[e] = true;
                 --nopp[e];
             } else if (nopp[e] > 0) {                                                            // tag.py:128
-                const uint32_t en = T->pair[o * 32u + agent];
+                const uint32_t en = T->pair[tag_pair_index(agent, o)];
                 if (bern(word_of(qm, e), p.move_T)) {                                            // tag.py:204
                     const uint32_t pick = rand_below(word_of(qp, e), en >> 20);                  // tag.py:205
                     s2[e] = (s2[e] & ~(31u << sh)) | (((en >> (5u * pick)) & 31u) << sh);        // tag.py:206-207

@@ -7,7 +7,7 @@
 //    fully coalesced (a warp moves 512 B per instruction).  Persistent grid-stride loop
 //    with a balanced trip count, at most SMs x resident CTAs.
 //  * Static maps -- Rock's header + transition LUT (17.6 KB for Rock(11,11)), Tag's board
-//    tables (4.2 KB) -- are built on the host, owned by the caller and copied global ->
+//    tables (4.3 KB) -- are built on the host, owned by the caller and copied global ->
 //    shared once per CTA with ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx);
 //    in the step kernel the first global loads are issued before the wait so the table
 //    fetch hides under them.  Lookups are per-thread divergent, which is what shared

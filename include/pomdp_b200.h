@@ -126,7 +126,7 @@ typedef struct PomdpTagParams {
 /* State: 1 word.  bits 0-4 agent cell, bits 5+5j..9+5j opponent j's cell (0..28),
  * bits 25-30 num_opp (6-bit two's complement; the reference lets it go negative with
  * several opponents), bit 31 done.                                                       */
-/* Static maps of the 29-cell board (4224 bytes: for every (agent, opponent) pair the cells the
+/* Static maps of the 29-cell board (4352 bytes: for every (agent, opponent) pair the cells the
  * opponent can reach through the move multiset of tag.py:260-280, and the agent's cell after each
  * move; layout in gym_pomdp_b200/csrc/pomdp_core.h: TagTables).  Filled on the host, uploaded by
  * the caller (16-byte aligned) and passed as `d_table`; the kernels stage it into shared memory

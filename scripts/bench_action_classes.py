@@ -42,12 +42,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="substring filter on the label")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     peak, peak_src = BC.peak_gbs()
     rows = []
     for name, env_id, kw, lg, label, classes in CASES:
+        if args.only and args.only not in label:
+            continue
         B = 1 << lg
         env = gp.make(env_id, batch_size=B, device=dev, seed=0x5EED, **kw)
         nbytes = 8 * env.state_words + 16
@@ -55,6 +58,15 @@ def main():
         gen = torch.Generator(device=dev)
         gen.manual_seed(0x5EED)
         states = [BC.synth(env, name, B, gen, dev)[0] for _ in range(n_sets)]
+        # the agent's own position is observed in RockSample and Tag: the particles of a belief share it
+        shared = None
+        if name == "rock":
+            k = env.num_rocks
+            shared = [env.pack(torch.full((B,), 3, device=dev), torch.full((B,), 5, device=dev),
+                               torch.randint(-1, 2, (B, k), generator=gen, device=dev)) for _ in range(n_sets)]
+        elif name == "tag":
+            shared = [env.pack(torch.full((B,), 7, device=dev), torch.randint(0, 29, (B, 1), generator=gen, device=dev))
+                      for _ in range(n_sets)]
         outs = [(torch.empty_like(states[0]), torch.empty(B, dtype=torch.int32, device=dev),
                  torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
         for cls, (lo, hi) in classes.items():
@@ -67,6 +79,14 @@ def main():
             row = {"config": label, "actions": cls, "us_per_launch": ms * 1e3, "units_per_s": B / (ms * 1e-3), "frac_of_peak": gbs / peak}
             rows.append(row)
             print(json.dumps(row), flush=True)
+            if shared is not None and cls != "uniform" and (hi - lo == 1 or name == "tag"):
+                def step_shared(i):
+                    env.simulate(shared[i % n_sets], acts[i % n_sets], out=outs[i % n_sets], step_ctr=i + 1)
+                ms = BC.time_graph(step_shared, args.steps, dev)
+                row = {"config": label, "actions": cls + ", one agent cell for the whole batch", "us_per_launch": ms * 1e3,
+                       "units_per_s": B / (ms * 1e-3), "frac_of_peak": B * nbytes / (ms * 1e-3) / 1e9 / peak}
+                rows.append(row)
+                print(json.dumps(row), flush=True)
         del env, states, outs
         torch.cuda.empty_cache()
     if args.out:
