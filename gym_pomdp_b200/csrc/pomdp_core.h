@@ -409,38 +409,42 @@ POMDP_HD int32_t rock_policy(const RockDev& p, const RockTableHdr* __restrict__ 
 // H provides tot_sample(i), tot_dir(i), count(i), measured(i), pv(i).
 // Returns a bit mask over ACTION ids -- the reference's lists are in increasing action order (NORTH 0, EAST 1, SOUTH 2,
 // WEST 3, then the checks 5 + i) -- or 0 when the list came out empty and the reference falls back to _generate_legal().
+// The three per-rock predicates the rule reads from the side-state.  They change only when that rock is checked, so a
+// fused rollout keeps them as three bit masks in registers (RockHeurLocal) instead of re-reading five planes per rock
+// per step.
+POMDP_HD bool rock_pred_sample(int32_t tot_sample) { return tot_sample > 0; }                       // rock.py:310
+POMDP_HD bool rock_pred_dir(int32_t tot_dir) { return tot_dir >= 0; }                               // rock.py:333
+POMDP_HD bool rock_pred_check(int32_t measured, int32_t count, double pv) {                        // rock.py:368-369
+    return measured < 5 && (count < 0 ? -count : count) < 2 && 0.0 < pv && pv < 1.0;
+}
+
+// H provides sample_mask(k), dir_mask(k), check_mask(k): bit i = the predicate above for rock i.
 template <typename S, class H>
 POMDP_HD uint32_t rock_preferred_mask(const RockDev& p, const RockTableHdr* __restrict__ hdr, S s, const H& h) {
     s &= ~RockBits<S>::DONE;
     const int x = (int)((uint32_t)s & 15u), y = (int)(((uint32_t)s >> 4) & 15u);
     const int rock = hdr->grid[(uint32_t)s & 0xFFu];                                       // rock.py:300
+    const uint32_t alive = rock_alive_bits(s) & ((1u << p.k) - 1u);                        // status != 0
     // sample a rock whose checks came out good more often than bad (rock.py:301-311); a dangling grid id (Rock(15,15),
     // Rock(7,7): the reference raises IndexError at rock.py:301) counts as no rock
-    if (rock >= 0 && rock < p.k && ((uint32_t)(s >> (8 + 2 * rock)) & 3u) != 0u && h.tot_sample(rock) > 0) return 1u << 4;
-    bool all_bad = true, north = false, south = false, west = false, east = false;
-    for (int i = 0; i < p.k; ++i) {                                                        // rock.py:322-343
-        if (((uint32_t)(s >> (8 + 2 * i)) & 3u) == 0u) continue;
-        if (h.tot_dir(i) >= 0) {
-            all_bad = false;
-            const int rx = hdr->rock_pos[i] & 15, ry = hdr->rock_pos[i] >> 4;
-            if (ry > y) north = true;
-            else if (ry < y) south = true;
-            else if (rx < x) west = true;
-            else if (rx > x) east = true;
-        }
+    if (rock >= 0 && rock < p.k && ((alive & h.sample_mask(p.k)) >> rock & 1u)) return 1u << 4;
+    bool north = false, south = false, west = false, east = false;
+    const uint32_t cand = alive & h.dir_mask(p.k);                                         // rock.py:322-343
+    for (int i = 0; i < p.k; ++i) {
+        if (!((cand >> i) & 1u)) continue;
+        const int rx = hdr->rock_pos[i] & 15, ry = hdr->rock_pos[i] >> 4;
+        if (ry > y) north = true;
+        else if (ry < y) south = true;
+        else if (rx < x) west = true;
+        else if (rx > x) east = true;
     }
-    if (all_bad) return 1u << 1;                                                           // rock.py:345-347: [EAST]
+    if (cand == 0u) return 1u << 1;                                                        // rock.py:345-347: all_bad -> [EAST]
     uint32_t m = 0;
     if (y + 1 < p.n && north) m |= 1u << 0;                                                // rock.py:356-366
     if (east) m |= 1u << 1;
     if (y - 1 >= 0 && south) m |= 1u << 2;
     if (x - 1 >= 0 && west) m |= 1u << 3;
-    for (int i = 0; i < p.k; ++i) {                                                        // rock.py:368-370
-        const double pv = h.pv(i);
-        const int c = h.count(i);
-        if (((uint32_t)(s >> (8 + 2 * i)) & 3u) != 0u && h.measured(i) < 5 && (c < 0 ? -c : c) < 2 && 0.0 < pv && pv < 1.0)
-            m |= 1u << (5 + i);
-    }
+    m |= (alive & h.check_mask(p.k)) << 5;                                                 // rock.py:368-370
     return m;                                                                              // 0: rock.py:372-373
 }
 // np.random.choice(env._generate_preferred(history)) from one draw word

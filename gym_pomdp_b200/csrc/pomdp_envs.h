@@ -277,18 +277,40 @@ struct RockPlanesView {
     POMDP_HD int32_t count(int i) const { return cnt_p ? cnt_p[base + i] : 0; }
     POMDP_HD int32_t measured(int i) const { return meas_p ? meas_p[base + i] : 0; }
     POMDP_HD double pv(int i) const { return pv_p ? pv_p[base + i] : .5; }
+    // the rule's three per-rock predicates as bit masks (rock_preferred_mask)
+    POMDP_HD uint32_t sample_mask(int k) const {
+        uint32_t m = 0;
+        for (int i = 0; i < k; ++i) m |= (rock_pred_sample(tot_sample(i)) ? 1u : 0u) << i;
+        return m;
+    }
+    POMDP_HD uint32_t dir_mask(int k) const {
+        uint32_t m = 0;
+        for (int i = 0; i < k; ++i) m |= (rock_pred_dir(tot_dir(i)) ? 1u : 0u) << i;
+        return m;
+    }
+    POMDP_HD uint32_t check_mask(int k) const {
+        uint32_t m = 0;
+        for (int i = 0; i < k; ++i) m |= (rock_pred_check(measured(i), count(i), pv(i)) ? 1u : 0u) << i;
+        return m;
+    }
 };
 struct RockPlanesPtr { int32_t* count; int32_t* measured; double* lkv; double* lkw; double* pv; int32_t* totals; int32_t* prev_obs; };
 // One env's planes for the length of a rollout (local memory on the device: k <= 16 rocks x 40 B)
 struct RockHeurLocal {
     int32_t cnt[16], meas[16], ts[16], td[16];
     double lkv[16], lkw[16], pvv[16];
-    POMDP_HD int32_t tot_sample(int i) const { return ts[i]; }
-    POMDP_HD int32_t tot_dir(int i) const { return td[i]; }
-    POMDP_HD int32_t count(int i) const { return cnt[i]; }
-    POMDP_HD int32_t measured(int i) const { return meas[i]; }
-    POMDP_HD double pv(int i) const { return pvv[i]; }
+    uint32_t m_sample, m_dir, m_check;      // the rule's per-rock predicates, kept current: registers, not local memory
+    POMDP_HD uint32_t sample_mask(int) const { return m_sample; }
+    POMDP_HD uint32_t dir_mask(int) const { return m_dir; }
+    POMDP_HD uint32_t check_mask(int) const { return m_check; }
+    POMDP_HD void refresh(int r) {          // after rock r's planes changed (it was checked)
+        const uint32_t bit = 1u << r;
+        m_sample = (m_sample & ~bit) | (rock_pred_sample(ts[r]) ? bit : 0u);
+        m_dir = (m_dir & ~bit) | (rock_pred_dir(td[r]) ? bit : 0u);
+        m_check = (m_check & ~bit) | (rock_pred_check(meas[r], cnt[r], pvv[r]) ? bit : 0u);
+    }
     POMDP_HD void load(const RockPlanesPtr& pl, int64_t base, int k) {
+        m_sample = m_dir = m_check = 0u;
         for (int r = 0; r < k; ++r) {
             cnt[r] = pl.count ? pl.count[base + r] : 0;
             meas[r] = pl.measured ? pl.measured[base + r] : 0;
@@ -298,6 +320,7 @@ struct RockHeurLocal {
             const int32_t t = pl.totals ? pl.totals[base + r] : 0;
             ts[r] = rock_totals_sample(t);
             td[r] = rock_totals_dir(t);
+            refresh(r);
         }
     }
     POMDP_HD void store(const RockPlanesPtr& pl, int64_t base, int k) const {
@@ -335,6 +358,7 @@ POMDP_HD void rock_rollout_preferred1(const RockDev& p, const unsigned char* tbl
             const int r = a - 5;
             rock_belief_update<S>(p, hdr, s, a, ob, h.cnt[r], h.meas[r], h.lkv[r], h.lkw[r], h.pvv[r]);   // rock.py:177-191
             rock_history_update(a, prev_ob, next_is_reward ? (int32_t)rw : ob, h.ts[r], h.td[r]);         // rock.py:566
+            h.refresh(r);
         }
         prev_ob = ob;                                                                                  // rock.py:567
         acc.add(Env::reward64(rw), gamma, fl);
