@@ -619,7 +619,7 @@ def pattern_roof(log2_batch=22):
     """The compute-free probe of the step's traffic pattern (scripts/exp_stream_probe.cu: two read + four write streams, 24 B
     per env, the product's grid, PDL + graph) from the committed B200 run: what this read:write mix reaches on the part."""
     import re
-    name = "r04f_stream_probe.log"
+    name = "r04k_stream_probe.log"
     try:
         for line in open(os.path.join(ROOT, "profiles", name)):
             m = re.match(r"n=2\^(\d+) .*graph\+PDL ([0-9.]+) us", line)

@@ -31,6 +31,42 @@ __global__ void __launch_bounds__(512, 2) probe(const int4* __restrict__ s, cons
     }
 }
 
+// reset pattern: nothing read, two streams written (state + obs: 8 B per env), 256-thread CTAs like pomdp_reset_kernel
+__global__ void __launch_bounds__(256) probe_reset(int4* __restrict__ o0, int4* __restrict__ o1, int64_t ng) {
+    const int64_t nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += nt) {
+        const int4 v = make_int4((int)g, (int)g + 1, (int)g + 2, (int)g + 3);
+        __stcs(o0 + g, v); __stcs(o1 + g, v);
+    }
+}
+static float run_reset(int64_t n, int sets, int iters, int4** bufs, cudaStream_t st, int sms) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int64_t ng = n / 4;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_reset, 256, 0);
+    const int64_t need = (ng + 255) / 256, cap = (int64_t)sms * per_sm, trips = (need + cap - 1) / cap;
+    const int grid = (int)(need <= cap ? need : (need + trips - 1) / trips);
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    for (int i = 0; i < iters; ++i) {
+        int4** b = bufs + 6 * (i % sets);
+        probe_reset<<<grid, 256, 0, st>>>(b[2], b[3], ng);
+    }
+    cudaStreamEndCapture(st, &g);
+    cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphLaunch(ge, st);
+    cudaStreamSynchronize(st);
+    cudaEventRecord(e0, st);
+    cudaGraphLaunch(ge, st);
+    cudaEventRecord(e1, st);
+    cudaStreamSynchronize(st);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms / iters * 1e3f;
+}
+
 template <bool PDL>
 static float run(int64_t n, int sets, int iters, int4** bufs, cudaStream_t st, int grid, bool graph = false) {
     cudaEvent_t e0, e1;
@@ -95,6 +131,9 @@ int main() {
         const float t3 = run<true>(n, sets, iters, bufs.data(), st, grid, true);
         printf("n=2^%d  24 B/env = %.1f MB/launch: plain %.2f us (%.0f GB/s)   PDL %.2f us (%.0f GB/s)   graph %.2f us   graph+PDL %.2f us\n",
                (int)__builtin_ctzll(n), n * 24 / 1e6, t0, n * 24.0 / t0 / 1e3, t1, n * 24.0 / t1 / 1e3, t2, t3);
+        const float t4 = run_reset(n, sets, iters, bufs.data(), st, sms);
+        printf("n=2^%d  reset pattern, 8 B/env written = %.1f MB/launch: graph %.2f us (%.0f GB/s)\n", (int)__builtin_ctzll(n), n * 8 / 1e6, t4,
+               n * 8.0 / t4 / 1e3);
         for (auto& p : bufs) cudaFree(p);
     }
     return 0;
