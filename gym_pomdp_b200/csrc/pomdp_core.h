@@ -878,7 +878,8 @@ POMDP_HD uint32_t network_group_fail(const Tab& T, uint32_t w, uint32_t cond5) {
 // kClean: the caller has established that this env raises no flag (not done, action in range, no stray state bits).
 // Two identities keep it short: the no-op action 2n is even, so `a & 1` alone says "reboot"; and a rebooted machine
 // is up, so its observation `hit` equals the ping's `bit ^ hit ^ 1` -- one expression serves both actions.
-template <bool kClean>
+// kNarrow: at most 15 machines (known at compile time), so both population counts of the reward fit one word.
+template <bool kClean, bool kNarrow = false>
 POMDP_HD void network_finish(const NetworkDev& p, uint32_t all, uint32_t na, uint32_t s, int32_t a, uint32_t fail,
                              uint32_t h, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
     int f = 0;
@@ -893,7 +894,9 @@ POMDP_HD void network_finish(const NetworkDev& p, uint32_t all, uint32_t na, uin
     const uint32_t reboot = (uint32_t)a & 1u;
     const uint32_t n2 = (s & ~fail) | (((kClean || acts) ? reboot : 0u) << m);      // kClean: a <= 2n, and 2n is even
     const uint32_t o = acts ? (((n2 >> m) ^ h ^ 1u) & 1u) : 2u;
-    const int tenths = 10 * (popc32(s) + popc32(s & p.deg3)) - (acts ? 1 + 24 * (int)reboot : 0);
+    const int up = kNarrow ? popc32((kClean ? s : (s & 0xFFFFu)) + (s & p.deg3) * 65536u)   // network.py:87-92: 1 per machine that is
+                           : popc32(s) + popc32(s & p.deg3);                        // up, 2 if it has more than two neighbours
+    const int tenths = 10 * up - (acts ? 1 + 24 * (int)reboot : 0);
     fl = f;
     s2 = live ? n2 : s;
     ob = live ? (int32_t)o : 0;
@@ -911,17 +914,20 @@ POMDP_HD void network_finish(const NetworkDev& p, uint32_t all, uint32_t na, uin
 // else: stays up), independent across machines; the 3^5 joint outcomes of a group are sampled from
 // one word through an alias table, and which machines face the larger probability (`cond`) selects
 // between the outcome's two masks.  A failure of a machine that is already down clears a clear bit.
-template <int L, class Tab>
+// G: the number of five-machine groups when it is known at compile time (2 for the stock 10-machine Network-v0: the
+// group blocks then carry no uniform branches and the compiler interleaves their Philox chains), 0 = read p.groups.
+template <int L, class Tab, int G = 0>
 POMDP_HD void network_step_n(const NetworkDev& p, const Tab& T, const uint32_t s[L], const int32_t a[L],
                              const PhiloxKey& seed, uint64_t group, int lane0, uint32_t step,
                              uint32_t s2[L], int32_t ob[L], float rw[L], int32_t fl[L]) {
+    const int groups = G ? G : p.groups;
     const uint32_t all = (1u << p.n) - 1u;
     uint32_t fail[L], cond[L], down[L];
     POMDP_UNROLL
     for (int j = 0; j < L; ++j) { cond[j] = 0; fail[j] = 0; down[j] = ~s[j] & all; }
     POMDP_UNROLL
     for (int g = 0; g < NET_MAX_GROUPS; ++g)
-        if (g < p.groups) {                                                           // uniform branch; network.py:81-84
+        if (g < groups) {                                                           // uniform branch; network.py:81-84
             POMDP_UNROLL
             for (int j = 0; j < L; ++j) cond[j] |= T.nbd(g, (down[j] >> (NET_GROUP * g)) & 31u);
         }
@@ -929,13 +935,13 @@ POMDP_HD void network_step_n(const NetworkDev& p, const Tab& T, const uint32_t s
     for (int j = 0; j < L; ++j) cond[j] ^= p.cond_flip;         // machines that face the larger of the two probabilities
     POMDP_UNROLL
     for (int g = 0; g < NET_MAX_GROUPS; ++g)
-        if (g < p.groups) {                                                           // network.py:94-99
+        if (g < groups) {                                                           // network.py:94-99
             const U4 q = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)g);
             POMDP_UNROLL
             for (int j = 0; j < L; ++j)
                 fail[j] |= network_group_fail(T, word_of(q, lane0 + j), cond[j] >> (NET_GROUP * g)) << (NET_GROUP * g);
         }
-    const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)p.groups);
+    const U4 qa = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)groups);
     const uint32_t na = (uint32_t)(2 * p.n);
     uint32_t stray = 0, amax = 0;
     POMDP_UNROLL
@@ -947,13 +953,13 @@ POMDP_HD void network_step_n(const NetworkDev& p, const Tab& T, const uint32_t s
         POMDP_UNROLL
         for (int j = 0; j < L; ++j) {
             const uint32_t h = (p.ob_any && word_of(qa, lane0 + j) <= p.om1) ? 1u : 0u;
-            network_finish<true>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
+            network_finish<true, (G >= 1 && G <= 3)>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
         }
     } else {
         POMDP_UNROLL
         for (int j = 0; j < L; ++j) {
             const uint32_t h = (p.ob_any && word_of(qa, lane0 + j) <= p.om1) ? 1u : 0u;
-            network_finish<false>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
+            network_finish<false, (G >= 1 && G <= 3)>(p, all, na, s[j], a[j], fail[j], h, s2[j], ob[j], rw[j], fl[j]);
         }
     }
 }

@@ -184,7 +184,9 @@ struct TigerEnvP {
     }
 };
 
-struct NetworkEnvP {
+// G: compile-time number of five-machine groups for the step (0 = runtime, network_step_n)
+template <int G>
+struct NetworkEnvT {
     typedef NetworkDev Params;
     typedef uint32_t State;
     static constexpr bool kTable = false;
@@ -229,12 +231,12 @@ struct NetworkEnvP {
     static POMDP_HD void step4(const Params& p, const unsigned char* tbl, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
-        network_step_n<4, Tab>(p, tables(p, tbl), s, a, seed, group, 0, ctr, s2, ob, rw, fl);
+        network_step_n<4, Tab, G>(p, tables(p, tbl), s, a, seed, group, 0, ctr, s2, ob, rw, fl);
     }
     static POMDP_HD void step1(const Params& p, const unsigned char* tbl, State s, int32_t a, const PhiloxKey& seed,
                                                  uint64_t env, uint32_t ctr, State& s2, int32_t& ob, float& rw,
                                                  int32_t& fl) {
-        network_step_n<1, Tab>(p, tables(p, tbl), &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
+        network_step_n<1, Tab, G>(p, tables(p, tbl), &s, &a, seed, env >> 2, (int)(env & 3), ctr, &s2, &ob, &rw, &fl);
     }
     static POMDP_HD void reset4(const Params& p, const PhiloxKey&, uint64_t, uint32_t, State s[4],
                                                   int32_t ob[4]) {
@@ -246,6 +248,8 @@ struct NetworkEnvP {
         ob = 0;
     }
 };
+typedef NetworkEnvT<0> NetworkEnvP;      // any n_machines
+typedef NetworkEnvT<2> NetworkEnv10;     // 6..10 machines (the stock Network-v0): two groups
 
 
 // One env through a whole rollout (scalar kernel path; tests/hostsim runs the same function).

@@ -1481,6 +1481,9 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
+    if (d.groups == 2)
+        return launch_step<NetworkEnv10>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                         stream, "pomdp_network_step");
     return launch_step<NetworkEnvP>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                     stream, "pomdp_network_step");
 }
@@ -1617,6 +1620,9 @@ int pomdp_network_step_packed(const PomdpNetworkParams* q, const int32_t* state,
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
+    if (d.groups == 2)
+        return launch_step<NetworkEnv10, true>(d, nullptr, 0, 0, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
+                                               step_ctr, stream, "pomdp_network_step_packed");
     return launch_step<NetworkEnvP, true>(d, nullptr, 0, 0, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
                                           step_ctr, stream, "pomdp_network_step_packed");
 }
@@ -1825,6 +1831,9 @@ int pomdp_network_rollout(const PomdpNetworkParams* q, const int32_t* state, con
     NetworkDev d;
     int rc = host::make_network(q, &d);
     if (rc) return rc;
+    if (d.groups == 2)
+        return launch_rollout<NetworkEnv10>(d, nullptr, 0, 0, state, first_action, final_state, ret, steps, flags, n, goff, seed,
+                                            step_ctr, max_steps, discount, stream, "pomdp_network_rollout");
     return launch_rollout<NetworkEnvP>(d, nullptr, 0, 0, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                        max_steps, discount, stream, "pomdp_network_rollout");
 }

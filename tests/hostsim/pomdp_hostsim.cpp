@@ -260,7 +260,10 @@ int pomdp_network_step(const PomdpNetworkParams* q, const int32_t* state, const 
         if ((env & 3) == 0 && i + 4 <= n && ((i >> 2) & 1) == 0) {
             uint32_t s4[4], s2[4];
             for (int j = 0; j < 4; ++j) s4[j] = (uint32_t)state[i + j];
-            network_step_n<4>(d, NetTabPtr{&d.t}, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
+            if (d.groups == 2)      // the compile-time two-group flavour the kernels use for the stock 10-machine network
+                network_step_n<4, NetTabPtr, 2>(d, NetTabPtr{&d.t}, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
+            else
+                network_step_n<4>(d, NetTabPtr{&d.t}, s4, action + i, key, env >> 2, 0, step, s2, obs + i, rw + i, fl + i);
             for (int j = 0; j < 4; ++j) next[i + j] = (int32_t)s2[j];
             i += 3;
             continue;
