@@ -480,7 +480,8 @@ def run_b200(args):
                 "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
                 "algorithmic_bytes_per_launch": B * bytes_per_step, "avg_launch_us": per_launch_ms * 1e3,
                 "peak_source": peak_src,
-                "pattern_roof": pattern_roof(22) if (B == 1 << 22 and words == 1) else None,
+                "pattern_roof": live_pattern_roof(torch, env, sets, n_sets, B, K, stream, peak, per_launch_ms)
+                if (words == 1 and B % 4 == 0) else (pattern_roof(22) if B == 1 << 22 else None),
                 "read_only_frac": (B * (4 * words + 4) / (per_launch_ms * 1e-3) / 1e9) / peak}
 
     cpu = None
@@ -613,6 +614,50 @@ def ncu_traffic(key="dram_bytes_per_launch"):
             return json.load(f).get(key)
     except Exception:  # noqa: BLE001
         return None
+
+
+def live_pattern_roof(torch, env, sets, n_sets, B, K, stream, peak, step_ms):
+    """Measured in THIS run: pomdp_stream_probe -- the step kernel's six memory streams with no table, no draws and no
+    transition -- timed exactly like the step (the same rotating buffer sets, one CUDA graph, PDL, CUDA events on the
+    launching stream).  `step_vs_roof` = probe time / step time: 1.0 means the step adds nothing to its own memory traffic."""
+    import statistics as st
+    from gym_pomdp_b200 import _lib
+    L = _lib.lib()
+    Kp = max(20, min(K, 2000))
+
+    def launch(i):
+        s, a, o = sets[i % n_sets]
+        _lib.check(L.pomdp_stream_probe(s.data_ptr(), a.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                        o[3].data_ptr(), B, torch.cuda.current_stream(s.device).cuda_stream), "pomdp_stream_probe")
+    try:
+        for i in range(3):
+            launch(i)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(Kp):
+                    launch(i)
+            g.replay()                                   # graph upload
+            torch.cuda.synchronize()
+            times = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                g.replay()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1) / Kp)
+        ms = st.median(times)
+        return {"us_per_launch": ms * 1e3, "gbs": B * 24 / (ms * 1e-3) / 1e9, "frac_of_peak": B * 24 / (ms * 1e-3) / 1e9 / peak,
+                "step_vs_roof": ms / step_ms, "launches": Kp, "replays": 5,
+                "source": "measured in this run: pomdp_stream_probe (compute-free kernel with the step's two read + four write "
+                          "streams, same grid, graph + PDL), median of 5 graph replays"}
+    except Exception as e:  # noqa: BLE001
+        r = pattern_roof(22) if B == 1 << 22 else None
+        if r:
+            r["live_error"] = repr(e)
+        return r
 
 
 def pattern_roof(log2_batch=22):

@@ -262,6 +262,35 @@ pomdp_step_kernel(const __grid_constant__ typename Env::Params p, const void* __
     if (!table_ready) mbar_wait(&bar, 0);
 }
 
+// ------------------------------------------------------------- diagnostics: stream probe ---
+// The step kernels' memory behaviour and nothing else: per group of four envs two 16-byte streaming loads (state,
+// action) and four 16-byte streaming stores, the same persistent grid, software pipelining and PDL -- no table, no
+// Philox, no transition.  bench.py times it next to the real step: what this 1:2 read:write mix over six streams reaches
+// on the part is the roof the RockSample step is measured against.  W = 1 layouts only.
+__global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
+pomdp_stream_probe_kernel(const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
+                          int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_groups = n >> 2;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int4 cs = make_int4(0, 0, 0, 0), ca = cs;
+    if (g < n_groups) { cs = ld_stream4(state + (g << 2)); ca = ld_stream4(action + (g << 2)); }
+    while (g < n_groups) {
+        const int64_t gn = g + nthreads;
+        int4 ns = cs, na = ca;
+        if (gn < n_groups) { ns = ld_stream4(state + (gn << 2)); na = ld_stream4(action + (gn << 2)); }
+        const int4 v = make_int4(cs.x ^ ca.x, cs.y ^ ca.y, cs.z ^ ca.z, cs.w ^ ca.w);
+        const int64_t i = g << 2;
+        st_stream4(next_state + i, v);
+        st_stream4(obs + i, ca);
+        st_stream4(reward + i, make_float4(__int_as_float(cs.x), __int_as_float(cs.y), __int_as_float(cs.z), __int_as_float(cs.w)));
+        st_stream4(flags + i, v);
+        cs = ns; ca = na; g = gn;
+    }
+}
+
 // ---------------------------------------------------------------- reset (streams) ---
 // kVec (state 16-byte aligned, global_offset % 4 == 0): four envs per thread, one Philox call
 // per draw slot per group, vector stores when the whole group is reset.
@@ -2154,6 +2183,20 @@ int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* d_table, co
 }
 
 // ---- helpers
+// Diagnostic (include/pomdp_b200.h): the compute-free probe of the step kernels' traffic pattern.
+int pomdp_stream_probe(const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* obs, float* reward,
+                       int32_t* flags, int64_t n, void* stream) {
+    int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!aligned16(state, action, next_state, obs, reward, flags) || (n & 3))
+        return host::fail(POMDP_E_ALIGN, "pomdp_stream_probe: arrays must be 16-byte aligned and n a multiple of 4");
+    auto k = pomdp_stream_probe_kernel;
+    const int grid = grid_for(k, n >> 2, POMDP_STEP_THREADS, 0);
+    launch_pdl(k, grid, POMDP_STEP_THREADS, 0, (cudaStream_t)stream, state, action, next_state, obs, reward, flags, n);
+    return finish("pomdp_stream_probe");
+}
+
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n,
                    void* stream) {
     const int rc = host::check_coord_op(op, xs, a, b, out, n);

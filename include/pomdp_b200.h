@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 7
+#define POMDP_ABI_VERSION 8
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -498,6 +498,15 @@ int pomdp_tag_rollout_preferred(const PomdpTagParams* params, const void* d_tabl
 #define POMDP_COORD_TAG_IS_INSIDE  7
 int pomdp_coord_op(int32_t op, int32_t x_size, int32_t y_size,
                    const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ diagnostics ---- */
+/* The step kernels' memory behaviour and nothing else (no reference counterpart): per env 4 + 4 bytes read from two
+ * streams and 4 x 4 bytes written to four, with the step kernels' grid, vector widths, cache hints and PDL -- no table,
+ * no draws, no transition.  bench.py times it next to pomdp_rock_step as the roof of this read:write mix.  All arrays
+ * int32/float32 [n], 16-byte aligned, n a multiple of 4; the outputs receive meaningless values.                  */
+int pomdp_stream_probe(const int32_t* state, const int32_t* action,
+                       int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                       int64_t n, void* stream);
 
 /* ----------------------------------------------------------- belief histogram ------ */
 /* Per-shard counts over a batch of packed states, accumulated into int64 hist[bins]

@@ -831,6 +831,14 @@ int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* table, cons
     return 0;
 }
 
+// diagnostic of the CUDA library (a memory-traffic probe): nothing to simulate on the host
+int pomdp_stream_probe(const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs, float* rw, int32_t* fl, int64_t n,
+                       void*) {
+    int rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) { next[i] = state[i] ^ action[i]; obs[i] = action[i]; memcpy(rw + i, state + i, 4); fl[i] = next[i]; }
+    return 0;
+}
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
     const int rc = host::check_coord_op(op, xs, a, b, out, n);
     if (rc) return rc;
