@@ -592,16 +592,46 @@ def collective_row(gp, torch, dist, dev, rank, world):
     h1.record()
     torch.cuda.synchronize()
     hist_us = h0.elapsed_time(h1) * 1e3 / reps
+    # the same reduction made inside the histogram kernel over NVLink peer memory (pomdp_belief_hist_allreduce)
+    fused_us, fused_ok, fused_err = None, None, None
     if world > 1:
-        t = torch.tensor([us, hist_us], device=dev, dtype=torch.float64)
+        try:
+            fused = env.belief_histogram(nxt, all_reduce="fused")
+            fused_ok = bool(torch.equal(fused, red))
+            for _ in range(3):
+                fused_ok = fused_ok and bool(torch.equal(env.belief_histogram(nxt, all_reduce="fused"), red))
+            torch.cuda.synchronize()
+            dist.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                env.belief_histogram(nxt, all_reduce="fused")
+            f1.record()
+            torch.cuda.synchronize()
+            fused_us = f0.elapsed_time(f1) * 1e3 / reps
+        except Exception as e:  # noqa: BLE001
+            fused_err = repr(e)[:200]
+    if world > 1:
+        t = torch.tensor([us, hist_us, fused_us if fused_us is not None else -1.0, 1.0 if fused_ok else 0.0], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us, hist_us = (float(v) for v in t.tolist())
+        us, hist_us, fmax, _ = (float(v) for v in t.tolist())
+        tmin = torch.tensor([1.0 if fused_ok else 0.0, 0.0 if fused_us is None else 1.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        fused_ok = bool(tmin[0].item() == 1.0)
+        fused_us = fmax if tmin[1].item() == 1.0 else None
     del nxt, env
     torch.cuda.empty_cache()
-    return {"workload": "RockSample(15,15) global batch 2^25 over %d rank(s): belief histogram%s" % (
-                world, " + ncclAllReduce(sum)" if world > 1 else " (one rank: no collective)"),
-            "batch_per_gpu": B, "bins": int(red.numel()), "hist_plus_allreduce_us": us, "hist_only_us": hist_us, "ok": ok,
-            "note": "eager launches (zero-fill + histogram kernel + all-reduce), CUDA events, max over ranks"}
+    row = {"workload": "RockSample(15,15) global batch 2^25 over %d rank(s): belief histogram%s" % (
+               world, " + ncclAllReduce(sum)" if world > 1 else " (one rank: no collective)"),
+           "batch_per_gpu": B, "bins": int(red.numel()), "hist_plus_allreduce_us": us, "hist_only_us": hist_us, "ok": ok,
+           "note": "eager launches (zero-fill + histogram kernel + all-reduce), CUDA events, max over ranks"}
+    if world > 1:
+        row["fused"] = {"hist_allreduce_us": fused_us, "equals_nccl": fused_ok, "error": fused_err,
+                        "what": "pomdp_belief_hist_allreduce: ONE kernel -- the last CTA of every rank adds the rank's counts into "
+                                "every rank's buffer over NVLink peer memory, signals its arrival to every peer and waits for "
+                                "theirs -- then the copy that hands the counts out; no NCCL call, no separate barrier"}
+    return row
 
 
 def ncu_traffic(key="dram_bytes_per_launch"):

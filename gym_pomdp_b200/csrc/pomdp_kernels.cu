@@ -1033,7 +1033,6 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 //    one shared-memory atomic per bin per warp) before a byte can overflow, normally once at the end;
 //  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (many addresses).
 // W = 1 and W = 2 states are read with 16-byte loads (four / two envs per thread per trip).
-#define POMDP_HIST_MAX_BINS 512
 template <int KIND> struct HistShape;                        // NW = packed counter words per thread (4 bins each)
 template <> struct HistShape<POMDP_KIND_ROCK> { static constexpr int NW = 4; };
 template <> struct HistShape<POMDP_KIND_TAG> { static constexpr int NW = 1; };
@@ -1097,7 +1096,9 @@ __device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, in
 template <int KIND>
 __global__ void __launch_bounds__(1024)
 pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
-                         unsigned long long* __restrict__ hist, int bins) {
+                         unsigned long long* __restrict__ hist, int bins,
+                         unsigned long long* const* __restrict__ peers, int world, int rank, int wait,
+                         unsigned long long* __restrict__ hist_out) {
     constexpr int NW = HistShape<KIND>::NW;
     __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
     for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
@@ -1179,6 +1180,68 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
     (void)p1;
+    // Fused all-reduce (pomdp_belief_hist_allreduce): `hist` is this rank's scratch -- hist[bins] a ticket counter,
+    // hist[bins + 1] the number of calls made so far.  The CTA that takes the last ticket owns the rank's complete counts.
+    // Call e (1, 2, ...) uses result slot (e - 1) & 1 of every rank's symmetric buffer [slot 0 | slot 1 | arrivals]:
+    //   1. clear this rank's OTHER slot for call e + 1 (nobody adds into it before having seen this rank's arrival of
+    //      call e, and its previous contents -- the result of call e - 1 -- were handed out by that call),
+    //   2. add the counts into EVERY rank's slot through the peer mappings: system-scope reductions over NVLink/NVSwitch,
+    //   3. announce the arrival in row [rank] of every peer's arrival counters (release, system scope: the reductions are
+    //      ordered before it) and wait until all counters of this rank's own row block have reached e (acquire),
+    //   4. copy the slot -- now the GLOBAL counts -- to hist_out.
+    // One kernel instead of zero-fill + histogram + a collective; the epoch lives in device memory, so the launch is
+    // identical call after call and can be replayed from a CUDA graph.
+    if (peers) {
+        __shared__ bool last;
+        __shared__ unsigned long long epoch_s;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last = atomicAdd(&hist[bins], 1ull) == (unsigned long long)gridDim.x - 1ull;
+            epoch_s = hist[bins + 1] + 1ull;
+        }
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            const unsigned long long epoch = epoch_s;
+            const int64_t slot_off = (int64_t)((epoch - 1ull) & 1ull) * POMDP_HIST_MAX_BINS * 8;
+            const int64_t other_off = POMDP_HIST_MAX_BINS * 8 - slot_off;
+            const int64_t signal_off = 2 * POMDP_HIST_MAX_BINS * 8;
+            char* own = reinterpret_cast<char*>(peers[rank]);
+            for (int b = threadIdx.x; b < POMDP_HIST_MAX_BINS; b += blockDim.x)
+                reinterpret_cast<unsigned long long*>(own + other_off)[b] = 0ull;
+            for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+                const unsigned long long v = atomicExch(&hist[b], 0ull);
+                if (v)
+                    for (int r = 0; r < world; ++r)
+                        atomicAdd_system(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + slot_off) + b, v);
+            }
+            if (wait) {
+                __threadfence_system();
+                __syncthreads();
+                if ((int)threadIdx.x < world) {
+                    const int r = (int)threadIdx.x;
+                    unsigned long long* there = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + signal_off) + rank;
+                    const unsigned long long* here = reinterpret_cast<const unsigned long long*>(own + signal_off) + r;
+                    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(there), "l"(1ull) : "memory");
+                    unsigned long long seen = 0, t0, t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(here) : "memory");
+                        if (seen >= epoch) break;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 10000000000ull) __trap();            // a peer never made the call: fail, do not hang
+                    }
+                }
+                __syncthreads();
+            }
+            if (hist_out)
+                for (int b = threadIdx.x; b < bins; b += blockDim.x)
+                    hist_out[b] = __ldcv(reinterpret_cast<const unsigned long long*>(own + slot_off) + b);
+            __syncthreads();
+            if (threadIdx.x == 0) { hist[bins] = 0ull; hist[bins + 1] = epoch; }
+        }
+    }
 }
 
 // ============================================================================ host ===
@@ -2224,8 +2287,31 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     // hundred addresses, so the CTA count (not the batch) sets that cost
     const int64_t want = (n + 4095) / 4096;
     const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());
-    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)hist, bins);
+    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)hist, bins, nullptr, 0, 0, 0,
+                                               nullptr);
     return finish("pomdp_belief_hist");
+}
+// The histogram fused with its all-reduce over peer memory (include/pomdp_b200.h).
+int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                                long long* scratch, const void* const* d_peer_bufs, int32_t world, int32_t rank, int32_t wait,
+                                long long* hist_out, void* stream) {
+    const int rc = host::check_hist(kind, p0, p1, state, words, n, scratch, POMDP_HIST_MAX_BINS);
+    if (rc) return rc;
+    if (!scratch || !d_peer_bufs || world < 1 || world > POMDP_HIST_MAX_RANKS || rank < 0 || rank >= world || ((uintptr_t)hist_out & 7))
+        return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_allreduce: bad peer table, world size, rank or output");
+    const int bins = host::hist_bins(kind, p0, p1);
+    auto k = kind == POMDP_KIND_ROCK ? pomdp_belief_hist_kernel<POMDP_KIND_ROCK>
+             : kind == POMDP_KIND_TAG ? pomdp_belief_hist_kernel<POMDP_KIND_TAG>
+             : kind == POMDP_KIND_TIGER ? pomdp_belief_hist_kernel<POMDP_KIND_TIGER>
+             : kind == POMDP_KIND_NETWORK ? pomdp_belief_hist_kernel<POMDP_KIND_NETWORK>
+                                          : pomdp_belief_hist_kernel<POMDP_KIND_BATTLESHIP>;
+    // n == 0 still launches: an empty shard contributes nothing but must not leave its peers waiting
+    const int64_t want = (n + 4095) / 4096;
+    const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());
+    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)scratch, bins,
+                                               (unsigned long long* const*)d_peer_bufs, world, rank, wait != 0,
+                                               (unsigned long long*)hist_out);
+    return finish("pomdp_belief_hist_allreduce");
 }
 
 }  // extern "C"

@@ -553,10 +553,15 @@ class BatchedPomdpEnv(_EnvBase):
         raise NotImplementedError
 
     def belief_histogram(self, state=None, all_reduce=False):
-        """int64 counts over the particle set (bins: include/pomdp_b200.h); with
-        ``all_reduce`` the counts are summed over all ranks of the default process group
-        (NCCL on GPUs) -- the only collective on the path."""
+        """int64 counts over the particle set (bins: include/pomdp_b200.h).  ``all_reduce=True``: the counts are summed
+        over all ranks of the default process group by NCCL -- the only collective on the path.  ``all_reduce="fused"``:
+        the same sum, but made INSIDE the histogram kernel over NVLink / NVSwitch peer memory
+        (``pomdp_belief_hist_allreduce``: the last CTA of every rank adds the rank's counts into every rank's buffer,
+        signals its arrival to every peer and waits for theirs; torch symmetric memory provides the peer mappings) --
+        ONE kernel, no collective launch."""
         state = self.state if state is None else state
+        if all_reduce == "fused":
+            return self._belief_histogram_fused(state)
         p0, p1 = self._hist_args()
         L = _lib.lib()
         bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
@@ -570,6 +575,47 @@ class BatchedPomdpEnv(_EnvBase):
             if dist.is_available() and dist.is_initialized():
                 dist.all_reduce(hist, op=dist.ReduceOp.SUM)
         return hist
+
+    _FUSED_HIST_BINS = 512          # POMDP_HIST_MAX_BINS
+    _FUSED_HIST_RANKS = 64          # POMDP_HIST_MAX_RANKS
+
+    def _fused_hist_state(self):
+        """One symmetric buffer per rank (two alternating result slots + a row of arrival counters: POMDP_HIST_SYMM_WORDS),
+        its peer table and this rank's scratch, created once.  A COLLECTIVE call: every rank of the default group must
+        reach it."""
+        st = getattr(self, "_fhist", None)
+        if st is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("belief_histogram(all_reduce='fused') needs an initialised torch.distributed process group")
+            buf = symm_mem.empty((2 * self._FUSED_HIST_BINS + self._FUSED_HIST_RANKS,), dtype=torch.int64, device=self.device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if hdl.world_size > self._FUSED_HIST_RANKS:
+                raise RuntimeError("belief_histogram(all_reduce='fused') supports at most %d ranks" % self._FUSED_HIST_RANKS)
+            buf.zero_()
+            hdl.barrier(channel=0)          # every rank's slots and counters are zero before any rank touches them
+            scratch = torch.zeros(self._FUSED_HIST_BINS + 2, dtype=torch.int64, device=self.device)
+            st = self._fhist = {"buf": buf, "hdl": hdl, "scratch": scratch}
+        return st
+
+    def _belief_histogram_fused(self, state, out=None):
+        """ONE launch: the kernel counts, adds the counts into every rank's buffer over NVLink, signals and waits for its
+        peers and writes the global counts to ``out``.  Nothing about the launch changes from call to call (the epoch is
+        kept in device memory), so it can be captured in a CUDA graph."""
+        p0, p1 = self._hist_args()
+        L = _lib.lib()
+        bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
+        st = self._fused_hist_state()
+        hdl = st["hdl"]
+        if out is None:
+            out = torch.empty(bins, dtype=torch.int64, device=self.device)
+        n = state.shape[0]
+        with self._guard():
+            _lib.check(L.pomdp_belief_hist_allreduce(
+                self.kind, p0, p1, _lib.ptr(state), self.state_words, n, _lib.ptr(st["scratch"]), hdl.buffer_ptrs_dev,
+                hdl.world_size, hdl.rank, 1, _lib.ptr(out), self._stream()), "pomdp_belief_hist_allreduce")
+        return out
 
 
 class _NullCtx(object):

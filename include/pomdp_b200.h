@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 8
+#define POMDP_ABI_VERSION 9
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -524,6 +524,28 @@ int pomdp_stream_probe(const int32_t* state, const int32_t* action,
 int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1);
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
                       int64_t n, long long* hist, void* stream);
+/* The same histogram FUSED with its all-reduce over NVLink / NVSwitch peer memory: ONE kernel -- no zero-fill before it,
+ * no collective after it.  Every rank passes the same device-resident table `d_peer_bufs[world]` of symmetric buffers,
+ * one per rank, each mapped into this process (e.g. torch symmetric memory: _SymmetricMemory.buffer_ptrs_dev).  A
+ * buffer is POMDP_HIST_SYMM_WORDS int64: result slot 0 | result slot 1 (POMDP_HIST_MAX_BINS each) | POMDP_HIST_MAX_RANKS
+ * arrival counters; all zero before the first call.  `scratch[POMDP_HIST_MAX_BINS + 2]` is this rank's own: zero before
+ * the first call, it carries the counts while the CTAs accumulate, a ticket counter and the number of calls made.
+ * The CTA that takes the last ticket owns the rank's complete counts; call e = 1, 2, ... uses slot (e - 1) & 1:
+ *   1. it clears this rank's other slot (for call e + 1),
+ *   2. adds the counts into every rank's slot with system-scope reductions,
+ *   3. wait != 0: announces its arrival in every peer's arrival counters (release, system scope) and waits until all
+ *      `world` counters of its own buffer have reached e (acquire); a peer that never makes the call trips a 10 s
+ *      timeout (the kernel traps) instead of hanging the device.  wait == 0: no signalling (the caller orders a
+ *      cross-rank barrier after the kernel and reads the slot itself),
+ *   4. copies the slot -- after the wait: the GLOBAL counts -- to hist_out[bins] (may be NULL).
+ * The epoch lives in device memory, so the launch arguments never change and the call can be replayed from a CUDA
+ * graph.  All ranks must make the same sequence of calls (an empty shard passes n = 0); world <= POMDP_HIST_MAX_RANKS. */
+#define POMDP_HIST_MAX_BINS 512
+#define POMDP_HIST_MAX_RANKS 64
+#define POMDP_HIST_SYMM_WORDS (2 * POMDP_HIST_MAX_BINS + POMDP_HIST_MAX_RANKS)
+int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
+                                int64_t n, long long* scratch, const void* const* d_peer_bufs,
+                                int32_t world, int32_t rank, int32_t wait, long long* hist_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -876,6 +876,32 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     return 0;
 }
 
+// host stand-in of the fused histogram + all-reduce: the peer table holds host pointers; arrivals are counted, nobody waits
+// (the "ranks" of a test call one after the other), hist_out receives the slot as it stands after this rank's additions
+int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                                long long* scratch, const void* const* peer_bufs, int32_t world, int32_t rank, int32_t wait,
+                                long long* hist_out, void*) {
+    int rc = host::check_hist(kind, p0, p1, state, words, n, scratch, POMDP_HIST_MAX_BINS);
+    if (rc) return rc;
+    if (!scratch || !peer_bufs || world < 1 || world > POMDP_HIST_MAX_RANKS || rank < 0 || rank >= world) return host::fail(POMDP_E_BADARG, "bad peer table");
+    const int bins = host::hist_bins(kind, p0, p1);
+    rc = pomdp_belief_hist(kind, p0, p1, state, words, n, scratch, nullptr);
+    if (rc) return rc;
+    const long long epoch = scratch[bins + 1] + 1;
+    const int slot = (int)((epoch - 1) & 1);
+    long long* own = (long long*)peer_bufs[rank];
+    memset(own + (slot ^ 1) * POMDP_HIST_MAX_BINS, 0, POMDP_HIST_MAX_BINS * sizeof(long long));
+    for (int b = 0; b < bins; ++b) {
+        for (int r = 0; r < world; ++r) ((long long*)peer_bufs[r])[slot * POMDP_HIST_MAX_BINS + b] += scratch[b];
+        scratch[b] = 0;
+    }
+    if (wait)
+        for (int r = 0; r < world; ++r) ((long long*)peer_bufs[r])[2 * POMDP_HIST_MAX_BINS + rank] += 1;
+    if (hist_out) memcpy(hist_out, own + slot * POMDP_HIST_MAX_BINS, bins * sizeof(long long));
+    scratch[bins + 1] = epoch;
+    return 0;
+}
+
 // test-only: the division-free float32 reward conversion of network_step_n, for the exhaustive check in
 // tests/test_edge_cases.py
 void pomdp_hostsim_tenths_to_float(const int32_t* t, float* out, int64_t n) {

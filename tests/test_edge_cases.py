@@ -282,6 +282,85 @@ def test_belief_histogram_matches_bincount(backend):
             assert np.array_equal(h.reshape(10, 10), occ.sum(0).T)      # bin c = 10*y + x
 
 
+def _fused_world_on_one_device(backend, env, state, world, calls, wait):
+    """`world` ranks played on ONE device: each has its own symmetric buffer (slot 0 | slot 1 | arrivals) and scratch, all
+    in one peer table.  wait=1 on CUDA: every rank's call goes to its own stream, so the kernels run concurrently and every
+    kernel's last CTA waits for the arrivals of the others (hostsim counts arrivals but cannot wait: ranks run in turn)."""
+    from gym_pomdp_b200 import _lib
+    L = _lib.lib()
+    p0, p1 = env._hist_args()
+    bins = L.pomdp_belief_hist_bins(env.kind, p0, p1)
+    n = state.shape[0]
+    shard = [state[r * n // world:(r + 1) * n // world] for r in range(world)]
+    bufs = [torch.zeros(2 * 512 + 64, dtype=torch.int64, device=backend) for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=backend)
+    scratch = [torch.zeros(514, dtype=torch.int64, device=backend) for _ in range(world)]
+    outs = [torch.full((bins,), -1, dtype=torch.int64, device=backend) for _ in range(world)]
+    cuda = torch.device(backend).type == "cuda"
+    streams = [torch.cuda.Stream(backend) for _ in range(world)] if cuda else [None] * world
+    if cuda:
+        torch.cuda.synchronize()
+    results = []
+    for i in range(calls):
+        used = []
+        for r in range(world):
+            sh = shard[r] if i % 3 != 2 or r != 1 else shard[r][:0]      # now and then a rank has an empty shard
+            used.append(sh)
+            h = streams[r].cuda_stream if cuda else None
+            _lib.check(L.pomdp_belief_hist_allreduce(env.kind, p0, p1, _lib.ptr(sh), env.state_words, sh.shape[0],
+                                                     _lib.ptr(scratch[r]), table.data_ptr(), world, r, wait, _lib.ptr(outs[r]), h),
+                       "pomdp_belief_hist_allreduce")
+        if cuda:
+            torch.cuda.synchronize()
+        slot = i & 1
+        results.append({"slots": [b[slot * 512:(slot + 1) * 512].clone() for b in bufs], "other": [b[(slot ^ 1) * 512:(slot ^ 1) * 512 + 512].clone() for b in bufs],
+                        "outs": [o.clone() for o in outs], "expected": torch.stack([env.belief_histogram(u) for u in used]).sum(0)})
+    return results, bufs, scratch
+
+
+@pytest.mark.parametrize("name", ["rock15", "tag", "network", "tiger", "ship"])
+def test_fused_histogram_allreduce_adds_the_counts_into_every_peer_buffer(backend, name):
+    """pomdp_belief_hist_allreduce without signalling (wait = 0: the caller would barrier): after every rank's call the
+    current slot of EVERY rank's buffer holds the sum of the ranks' plain histograms, the other slot is cleared for the next
+    call, the scratch comes back with zero counts and tickets and the call count, call after call."""
+    N = 70001
+    env = make_all(backend, N)[name]
+    state, _ = random_inputs(env, name, N, np.random.RandomState(5), backend)
+    world, calls = 3, 4
+    results, bufs, scratch = _fused_world_on_one_device(backend, env, state, world, calls, wait=0)
+    for i, res in enumerate(results):
+        exp = res["expected"]
+        for r in range(world):
+            assert torch.equal(res["slots"][r][:exp.numel()], exp), (name, i, r)
+            assert not res["slots"][r][exp.numel():].any() and not res["other"][r].any(), (name, i, r)
+    for r in range(world):
+        nb = exp.numel()                                                  # scratch: counts[bins] | tickets | calls made
+        assert not scratch[r][:nb + 1].any() and int(scratch[r][nb + 1]) == calls and not scratch[r][nb + 2:].any()
+        assert not bufs[r][1024:].any()                                   # nobody signalled
+
+
+def test_fused_histogram_allreduce_with_in_kernel_signalling(backend):
+    """wait = 1: three ranks on three streams.  Every call hands every rank the SAME global counts through hist_out
+    (copied out by the kernel after it has seen all arrivals), and the arrival counters stand at the number of calls."""
+    N = 3 * 4096 * 5 + 17
+    envs = make_all(backend, N)
+    rs = np.random.RandomState(6)
+    for name in ("rock", "network"):
+        env = envs[name]
+        state, _ = random_inputs(env, name, N, rs, backend)
+        world, calls = 3, 5
+        results, bufs, _ = _fused_world_on_one_device(backend, env, state, world, calls, wait=1)
+        for i, res in enumerate(results):
+            exp = res["expected"]
+            for r in range(world):
+                assert torch.equal(res["slots"][r][:exp.numel()], exp), (name, i, r)
+                if torch.device(backend).type == "cuda":                  # hostsim ranks run in turn: only the last one sees the total
+                    assert torch.equal(res["outs"][r], exp), (name, i, r)
+            assert torch.equal(res["outs"][world - 1], exp)
+        for b in bufs:
+            assert (b[1024:1024 + world] == calls).all() and not b[1024 + world:].any()
+
+
 @pytest.mark.parametrize("size,max_len", [((10, 10), 3), ((5, 5), 3), ((10, 10), 5), ((12, 10), 4), ((4, 7), 3), ((3, 3), 3),
                                           ((120, 1), 4), ((1, 120), 4), ((2, 60), 5), ((30, 4), 6), ((40, 3), 9), ((8, 15), 9)])
 def test_battleship_bitboard_reset_equals_warp_scan(backend, size, max_len):
