@@ -480,6 +480,7 @@ def run_b200(args):
                 "kernel": "pomdp_step_kernel<RockEnv%d,true>" % words,
                 "algorithmic_bytes_per_launch": B * bytes_per_step, "avg_launch_us": per_launch_ms * 1e3,
                 "peak_source": peak_src,
+                "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0,     # both peaks stated
                 "pattern_roof": live_pattern_roof(torch, env, sets, n_sets, B, K, stream, peak, per_launch_ms)
                 if (words == 1 and B % 4 == 0) else (pattern_roof(22) if B == 1 << 22 else None),
                 "read_only_frac": (B * (4 * words + 4) / (per_launch_ms * 1e-3) / 1e9) / peak}
