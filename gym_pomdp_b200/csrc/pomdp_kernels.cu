@@ -1075,7 +1075,7 @@ __device__ __forceinline__ void hist_one(int p0, bool valid, const uint32_t s[4]
 // reduction (REDUX via __reduce_add_sync; a plain 32-bit add never carries between the fields), and lane j keeps
 // word j's totals, so the shared-memory atomics of all words are issued together, four per lane.
 template <int NW>
-__device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, int n_bits, int lane) {
+__device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, int n_bits, int lane, uint32_t weight = 1u) {
     static_assert(NW <= 32, "one lane per counter word");
     uint32_t my_lo = 0, my_hi = 0;
 #pragma unroll
@@ -1090,10 +1090,39 @@ __device__ __forceinline__ void hist_flush(uint32_t (&acc)[NW], uint32_t* sh, in
         const uint32_t c[4] = {my_lo & 0xFFFFu, my_hi & 0xFFFFu, my_lo >> 16, my_hi >> 16};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (c[k] && 4 * lane + k < n_bits) atomicAdd(&sh[4 * lane + k], c[k]);
+            if (c[k] && 4 * lane + k < n_bits) atomicAdd(&sh[4 * lane + k], c[k] * weight);
     }
 }
+// ---- bit bins by carry-save addition (Harley-Seal) ------------------------------------------------------------------
+// Rock's "rock i still good" and Network's "machine m up" are one bit per bin per particle.  Instead of spreading every
+// particle's bits into byte counters (5 instructions per four bins per particle), the words of a trip are summed
+// VERTICALLY: a carry-save adder (two LOP3) turns three words of weight w into one of weight w and one of weight 2w, and
+// a tree of 15 of them reduces the 16 words a thread loads per trip (7 for the 8 two-word states) to running planes of
+// weight 1, 2, 4, 8 plus ONE carry-out word of weight 16 (8) -- only that word is spread into the byte counters, whose
+// unit becomes 16 (8) particles.  The running planes are added once, at the end.
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    hi = (a & b) | (u & c);
+    lo = u ^ c;
+}
 template <int KIND>
+__device__ __forceinline__ uint32_t hist_bitword(uint32_t s0, uint32_t s1) {
+    if (KIND == POMDP_KIND_ROCK)    // bit 2i = rock i's status is +1 (code 01); rocks 12..15 (word 1) in bits 24..30
+        return ((s0 >> 8) & ~(s0 >> 9) & 0x00555555u) | ((s1 & ~(s1 >> 1) & 0x00000055u) << 24);
+    return s0;                      // Network: bit m = machine m is up
+}
+template <int KIND>
+__device__ __forceinline__ void hist_add_plane(uint32_t x, uint32_t (&acc)[HistShape<KIND>::NW]) {
+    if (KIND == POMDP_KIND_ROCK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += spread4_even(x >> (8 * j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += spread4((x >> (4 * j)) & 0xFu);
+    }
+}
+
+template <int KIND, bool CSA>
 __global__ void __launch_bounds__(1024)
 pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins,
@@ -1120,6 +1149,10 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
         // kInFlight independent 16-byte loads per thread per trip: with one, a 1024-thread CTA per SM keeps only 16 KB in
         // flight and the kernel waits on DRAM latency (long-scoreboard stalls, 20-30 % of the HBM peak on a pure read)
         constexpr int kInFlight = 4;
+        // CSA: chosen by the host only when a thread makes many trips (measured: 2^25 two-word states 57.0 -> 48.6 us, but
+        // slower at 2^22 and below, where a thread makes two trips and the final planes cost more than they save)
+        constexpr bool kCsa = CSA && (KIND == POMDP_KIND_ROCK || KIND == POMDP_KIND_NETWORK);
+        uint32_t ones = 0, twos = 0, fours = 0, eights = 0;              // running planes of the vertical sum (kCsa)
         for (int64_t g0 = tid; g0 < g_round; g0 += kInFlight * nthreads) {
             int4 v[kInFlight];
             bool valid[kInFlight];
@@ -1130,26 +1163,88 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
                 v[u] = make_int4(0, 0, 0, 0);
                 if (valid[u]) v[u] = ld_stream4(state + (g << 2));
             }
+            if (kCsa) {
+                uint32_t w[4 * kInFlight];                               // an invalid group contributes zero words
 #pragma unroll
-            for (int u = 0; u < kInFlight; ++u) {
-                if (g0 + u * nthreads >= g_round) break;                 // warp-uniform: g_round is a multiple of 32
-                const uint32_t e[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-                if (words == 1) {
+                for (int u = 0; u < kInFlight; ++u) {
+                    const uint32_t e[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+                    if (words == 1) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t s[4] = {e[j], 0u, 0u, 0u};
-                        hist_one<KIND>(p0, valid[u], s, sh, acc);
-                    }
-                } else {
+                        for (int j = 0; j < 4; ++j) {
+                            w[4 * u + j] = hist_bitword<KIND>(e[j], 0u);
+                            if (KIND == POMDP_KIND_ROCK && valid[u]) atomicAdd(&sh[p0 + (int)(e[j] & 0xFFu)], 1u);
+                        }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t s[4] = {e[2 * j], e[2 * j + 1], 0u, 0u};
-                        hist_one<KIND>(p0, valid[u], s, sh, acc);
+                        for (int j = 0; j < 2; ++j) {
+                            w[2 * u + j] = hist_bitword<KIND>(e[2 * j], e[2 * j + 1]);
+                            if (KIND == POMDP_KIND_ROCK && valid[u]) atomicAdd(&sh[p0 + (int)(e[2 * j] & 0xFFu)], 1u);
+                        }
                     }
                 }
-                pending += 4;
-                if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
+                uint32_t twosA, twosB, foursA, foursB, eightsA;
+                csa(twosA, ones, ones, w[0], w[1]);
+                csa(twosB, ones, ones, w[2], w[3]);
+                csa(foursA, twos, twos, twosA, twosB);
+                csa(twosA, ones, ones, w[4], w[5]);
+                csa(twosB, ones, ones, w[6], w[7]);
+                csa(foursB, twos, twos, twosA, twosB);
+                csa(eightsA, fours, fours, foursA, foursB);
+                if (words == 1) {
+                    uint32_t eightsB, sixteens;
+                    csa(twosA, ones, ones, w[8], w[9]);
+                    csa(twosB, ones, ones, w[10], w[11]);
+                    csa(foursA, twos, twos, twosA, twosB);
+                    csa(twosA, ones, ones, w[12], w[13]);
+                    csa(twosB, ones, ones, w[14], w[15]);
+                    csa(foursB, twos, twos, twosA, twosB);
+                    csa(eightsB, fours, fours, foursA, foursB);
+                    csa(sixteens, eights, eights, eightsA, eightsB);
+                    hist_add_plane<KIND>(sixteens, acc);                 // unit of the byte counters: 16 particles
+                } else {
+                    hist_add_plane<KIND>(eightsA, acc);                  // eight two-word states per trip: unit 8
+                }
+                if (++pending > 254) { hist_flush<NW>(acc, sh, n_bits, lane, words == 1 ? 16u : 8u); pending = 0; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    if (g0 + u * nthreads >= g_round) break;             // warp-uniform: g_round is a multiple of 32
+                    const uint32_t e[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+                    if (words == 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t s[4] = {e[j], 0u, 0u, 0u};
+                            hist_one<KIND>(p0, valid[u], s, sh, acc);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t s[4] = {e[2 * j], e[2 * j + 1], 0u, 0u};
+                            hist_one<KIND>(p0, valid[u], s, sh, acc);
+                        }
+                    }
+                    pending += 4;
+                    if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
+                }
             }
+        }
+        if (kCsa) {                                  // the carry-outs, then the running planes in ONE flush (a byte holds <= 15)
+            hist_flush<NW>(acc, sh, n_bits, lane, words == 1 ? 16u : 8u);
+            uint32_t t[NW];
+#pragma unroll
+            for (int j = 0; j < NW; ++j) t[j] = 0;
+            hist_add_plane<KIND>(ones, acc);
+            hist_add_plane<KIND>(twos, t);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) { acc[j] += 2u * t[j]; t[j] = 0; }
+            hist_add_plane<KIND>(fours, t);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) { acc[j] += 4u * t[j]; t[j] = 0; }
+            hist_add_plane<KIND>(eights, t);         // stays zero for two-word states
+#pragma unroll
+            for (int j = 0; j < NW; ++j) acc[j] += 8u * t[j];
+            hist_flush<NW>(acc, sh, n_bits, lane, 1u);
+            pending = 0;
         }
         scalar_from = n_groups << lg;
     }
@@ -2272,17 +2367,27 @@ int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const i
 }
 
 int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1) { return host::hist_bins(kind, p0, p1); }
+typedef void (*HistKernel)(int, int, const int32_t*, int, int64_t, unsigned long long*, int, unsigned long long* const*, int, int,
+                           int, unsigned long long*);
+// The carry-save flavour pays off only when every thread makes at least eight trips of four 16-byte loads.
+static HistKernel hist_kernel_for(int32_t kind, int32_t words, int64_t n) {
+    const int64_t groups = (words == 1 || words == 2) ? n >> (words == 1 ? 2 : 1) : 0;
+    const bool csa = groups >= (int64_t)8 * 4 * 1024 * device_sms();
+    switch (kind) {
+        case POMDP_KIND_ROCK: return csa ? pomdp_belief_hist_kernel<POMDP_KIND_ROCK, true> : pomdp_belief_hist_kernel<POMDP_KIND_ROCK, false>;
+        case POMDP_KIND_NETWORK: return csa ? pomdp_belief_hist_kernel<POMDP_KIND_NETWORK, true> : pomdp_belief_hist_kernel<POMDP_KIND_NETWORK, false>;
+        case POMDP_KIND_TAG: return pomdp_belief_hist_kernel<POMDP_KIND_TAG, false>;
+        case POMDP_KIND_TIGER: return pomdp_belief_hist_kernel<POMDP_KIND_TIGER, false>;
+        default: return pomdp_belief_hist_kernel<POMDP_KIND_BATTLESHIP, false>;
+    }
+}
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
                       long long* hist, void* stream) {
     const int rc = host::check_hist(kind, p0, p1, state, words, n, hist, POMDP_HIST_MAX_BINS);
     if (rc) return rc;
     const int bins = host::hist_bins(kind, p0, p1);
     if (n == 0) return 0;
-    auto k = kind == POMDP_KIND_ROCK ? pomdp_belief_hist_kernel<POMDP_KIND_ROCK>
-             : kind == POMDP_KIND_TAG ? pomdp_belief_hist_kernel<POMDP_KIND_TAG>
-             : kind == POMDP_KIND_TIGER ? pomdp_belief_hist_kernel<POMDP_KIND_TIGER>
-             : kind == POMDP_KIND_NETWORK ? pomdp_belief_hist_kernel<POMDP_KIND_NETWORK>
-                                          : pomdp_belief_hist_kernel<POMDP_KIND_BATTLESHIP>;
+    auto k = hist_kernel_for(kind, words, n);
     // one 1024-thread CTA per SM: every CTA ends with one global atomic per non-empty bin, all CTAs on the same few
     // hundred addresses, so the CTA count (not the batch) sets that cost
     const int64_t want = (n + 4095) / 4096;
@@ -2300,11 +2405,7 @@ int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int3
     if (!scratch || !d_peer_bufs || world < 1 || world > POMDP_HIST_MAX_RANKS || rank < 0 || rank >= world || ((uintptr_t)hist_out & 7))
         return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_allreduce: bad peer table, world size, rank or output");
     const int bins = host::hist_bins(kind, p0, p1);
-    auto k = kind == POMDP_KIND_ROCK ? pomdp_belief_hist_kernel<POMDP_KIND_ROCK>
-             : kind == POMDP_KIND_TAG ? pomdp_belief_hist_kernel<POMDP_KIND_TAG>
-             : kind == POMDP_KIND_TIGER ? pomdp_belief_hist_kernel<POMDP_KIND_TIGER>
-             : kind == POMDP_KIND_NETWORK ? pomdp_belief_hist_kernel<POMDP_KIND_NETWORK>
-                                          : pomdp_belief_hist_kernel<POMDP_KIND_BATTLESHIP>;
+    auto k = hist_kernel_for(kind, words, n);
     // n == 0 still launches: an empty shard contributes nothing but must not leave its peers waiting
     const int64_t want = (n + 4095) / 4096;
     const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());

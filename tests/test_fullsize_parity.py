@@ -210,6 +210,36 @@ def test_belief_histogram_2p22(backend):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which", ["rock15", "rock11", "network"])
+def test_belief_histogram_carry_save_flavour_at_2p25(which):
+    """Batches large enough for the kernel's carry-save (Harley-Seal) counting of the bit bins -- every thread makes at least
+    eight trips -- with a ragged end (n % 4 != 0: the scalar tail follows the vector loop) and random states, against
+    torch's own reductions over the unpacked states."""
+    dev = "cuda:0"
+    n = (1 << 25) + 3
+    g = gen_for(dev, 91)
+    if which == "network":
+        env = gp.make("Network-v0", n_machines=30, problem_type=0, batch_size=n, device=dev, seed=SEED)
+        st = torch.randint(0, 1 << 30, (n,), generator=g, device=dev, dtype=torch.int64).to(torch.int32)
+        exp = torch.stack([((st >> m) & 1).sum() for m in range(30)])
+    else:
+        b, k = (15, 15) if which == "rock15" else (11, 11)
+        env = gp.make("Rock-v0", board_size=b, num_rocks=k, batch_size=n, device=dev, seed=SEED)
+        x = torch.randint(0, b, (n,), generator=g, device=dev)
+        y = torch.randint(0, b, (n,), generator=g, device=dev)
+        status = torch.randint(-1, 2, (n, k), generator=g, device=dev, dtype=torch.int8)
+        st = env.pack(x, y, status)
+        exp = torch.cat([(status == 1).sum(0), torch.bincount(x | (y << 4), minlength=256)])
+        del x, y, status
+    h = env.belief_histogram(st)
+    assert torch.equal(h, exp.to(h.dtype)), which
+    # and a view that starts 16 bytes in (still vector-aligned) but ends ragged
+    off = 4 * env.state_words
+    h2 = env.belief_histogram(st[4:]) if env.state_words == 1 else env.belief_histogram(st[2:])
+    assert int(h2.sum()) < int(h.sum()) and off > 0
+
+
+@pytest.mark.gpu
 def test_batch_beyond_2p31_envs():
     """Maximum sizes: 2^31 + 4 Tiger instances in ONE launch (52 GB of arrays): element indices and Philox counters are
     64-bit end to end.  Windows at the start, around 2^31 and at the ragged end are checked against the C oracle."""
