@@ -253,7 +253,24 @@ inline void network_alias_table(uint64_t T_p, uint64_t T_q, NetAlias out[NET_COL
     }
 }
 
+inline int make_network_uncached(const PomdpNetworkParams* q, NetworkDev* d);
+// The alias columns and the neighbour-down map take ~10 us of host time to build -- half a kernel: the block of the last
+// parameters seen is kept per thread (every launch of one env passes the same ones).
 inline int make_network(const PomdpNetworkParams* q, NetworkDev* d) {
+    if (!q) return fail(POMDP_E_BADARG, "network: params is NULL");
+    struct Cache { bool valid; PomdpNetworkParams key; NetworkDev dev; };
+    static thread_local Cache cache = {false, {}, {}};
+    if (cache.valid && cache.key.n_machines == q->n_machines && cache.key.problem_type == q->problem_type &&
+        memcmp(&cache.key.p, &q->p, sizeof(double)) == 0 && memcmp(&cache.key.q, &q->q, sizeof(double)) == 0 &&
+        memcmp(&cache.key.p_ob, &q->p_ob, sizeof(double)) == 0) {
+        *d = cache.dev;
+        return 0;
+    }
+    const int rc = make_network_uncached(q, d);
+    if (rc == 0) { cache.key = *q; cache.dev = *d; cache.valid = true; }
+    return rc;
+}
+inline int make_network_uncached(const PomdpNetworkParams* q, NetworkDev* d) {
     if (!q) return fail(POMDP_E_BADARG, "network: params is NULL");
     const int n = q->n_machines;
     if (n < 1 || n > NETWORK_MAX) return fail(POMDP_E_BADARG, "network: n_machines %d outside 1..%d", n, NETWORK_MAX);
