@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -38,7 +38,7 @@ class RockParams(ctypes.Structure):
 class RockHeuristicPlanes(ctypes.Structure):
     """PomdpRockHeuristicPlanes: device pointers (0 = the fresh value / an empty history)"""
     _fields_ = [("count", c_void_p), ("measured", c_void_p), ("lkv", c_void_p), ("lkw", c_void_p), ("prob_valuable", c_void_p),
-                ("check_totals", c_void_p), ("prev_obs", c_void_p)]
+                ("check_totals", c_void_p), ("prev_obs", c_void_p), ("scratch", c_void_p)]
 
 
 class TagParams(ctypes.Structure):

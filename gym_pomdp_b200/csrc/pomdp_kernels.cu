@@ -604,7 +604,7 @@ pomdp_rock_history_update_kernel(int k, const int32_t* __restrict__ obs_field, c
 // planes that were passed in are updated in place at the end.  next_is_reward: the transition's `next_observation`
 // field holds the reward (the reference's own positional Transition(ob, action, next_ob, rw, done), rock.py:566),
 // otherwise the next observation.
-template <typename S, bool STOCH>
+template <typename S, bool STOCH, bool kRecords>
 __global__ void __launch_bounds__(POMDP_THREADS)
 pomdp_rock_rollout_preferred_kernel(const __grid_constant__ RockDev p, const void* __restrict__ g_table, const int32_t* state,
                                     const int32_t* __restrict__ first_action, const __grid_constant__ RockPlanesPtr pl,
@@ -618,16 +618,23 @@ pomdp_rock_rollout_preferred_kernel(const __grid_constant__ RockDev p, const voi
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
         const int64_t base = i * p.k;
-        RockHeurLocal h;
-        h.load(pl, base, p.k);
         int32_t prev_ob = pl.prev_obs ? pl.prev_obs[i] : 0;                     // RockEnv.reset returns Obs.NULL (rock.py:241)
         S s = load_state1(state, i, S());
         RolloutAcc acc;
-        rock_rollout_preferred1<S, STOCH>(p, smem_table, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, next_is_reward != 0,
-                                          first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        if (kRecords) {         // fresh planes in, none out: one lazily touched 32-byte record per rock in the caller's scratch
+            RockHeurRecords h;
+            h.init(reinterpret_cast<RockRec*>(pl.scratch) + base);
+            rock_rollout_preferred1<S, STOCH>(p, smem_table, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, next_is_reward != 0,
+                                              first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        } else {
+            RockHeurLocal h;
+            h.load(pl, base, p.k);
+            rock_rollout_preferred1<S, STOCH>(p, smem_table, s, seed, goff + (uint64_t)i, ctr0, max_steps, gamma, next_is_reward != 0,
+                                              first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+            h.store(pl, base, p.k);
+        }
         if (final_state) store_state1(final_state, i, s);
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
-        h.store(pl, base, p.k);
         if (pl.prev_obs) pl.prev_obs[i] = prev_ob;
     }
 }
@@ -2227,7 +2234,9 @@ int launch_rock_rollout_preferred(const RockDev& d, const void* d_table, const i
                                   const RockPlanesPtr& pl, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags,
                                   int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, int32_t max_steps, double discount,
                                   int32_t next_is_reward, void* stream) {
-    auto k = pomdp_rock_rollout_preferred_kernel<S, STOCH>;
+    // the record flavour: no plane comes in or goes out, a scratch is there, and the 16-bit fields of a record cannot overflow
+    const bool records = pl.scratch && !pl.count && !pl.measured && !pl.lkv && !pl.lkw && !pl.pv && !pl.totals && max_steps <= 32767;
+    auto k = records ? pomdp_rock_rollout_preferred_kernel<S, STOCH, true> : pomdp_rock_rollout_preferred_kernel<S, STOCH, false>;
     int rc = allow_smem(k, d.smem_bytes);
     if (rc) return rc;
     k<<<grid_for(k, n, POMDP_THREADS, d.smem_bytes), POMDP_THREADS, d.smem_bytes, (cudaStream_t)stream>>>(
@@ -2259,13 +2268,13 @@ int pomdp_rock_rollout_preferred(const PomdpRockParams* q, const void* d_table, 
     if (rc) return rc;
     if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, what))) return rc;
     if ((uintptr_t)first_action & 3) return host::fail(POMDP_E_ALIGN, "%s: first_action must be 4-byte aligned", what);
-    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (planes) {
         pl.count = planes->count; pl.measured = planes->measured; pl.lkv = planes->lkv; pl.lkw = planes->lkw;
-        pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs;
+        pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs; pl.scratch = planes->scratch;
         if ((((uintptr_t)pl.count | (uintptr_t)pl.measured | (uintptr_t)pl.totals | (uintptr_t)pl.prev_obs) & 3) ||
-            (((uintptr_t)pl.lkv | (uintptr_t)pl.lkw | (uintptr_t)pl.pv) & 7))
-            return host::fail(POMDP_E_ALIGN, "%s: int32 planes must be 4-byte and float64 planes 8-byte aligned", what);
+            (((uintptr_t)pl.lkv | (uintptr_t)pl.lkw | (uintptr_t)pl.pv) & 7) || ((uintptr_t)pl.scratch & 31))
+            return host::fail(POMDP_E_ALIGN, "%s: int32 planes must be 4-byte, float64 planes 8-byte and the scratch 32-byte aligned", what);
     }
     if (n == 0) return 0;
     if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);

@@ -264,6 +264,13 @@ class RockEnv(BatchedPomdpEnv):
             planes.lkv, planes.lkw, planes.prob_valuable = stats.lkv.data_ptr(), stats.lkw.data_ptr(), stats.prob_valuable.data_ptr()
         if history is not None:
             planes.check_totals, planes.prev_obs = history.check_totals.data_ptr(), history.prev_obs.data_ptr()
+        if stats is None and history is None:
+            # fresh planes in, none out: the kernel keeps its per-rock side-state as 32-byte records in this scratch
+            need = n * self.num_rocks * 32
+            buf = getattr(self, "_heur_scratch", None)
+            if buf is None or buf.numel() < need or buf.device != state.device:
+                buf = self._heur_scratch = torch.empty(max(need, 32), dtype=torch.uint8, device=state.device)
+            planes.scratch = buf.data_ptr()
         nir = self.history_next_is_reward if next_is_reward is None else bool(next_is_reward)
         _lib.check(_lib.lib().pomdp_rock_rollout_preferred(
             ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(first_action), ctypes.byref(planes),

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 9
+#define POMDP_ABI_VERSION 10
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -448,6 +448,10 @@ typedef struct PomdpRockHeuristicPlanes {
     double*  prob_valuable;  /* [n, num_rocks]  rock.py:87 */
     int32_t* check_totals;   /* [n, num_rocks]  see above */
     int32_t* prev_obs;       /* [n] the observation the next transition records as `observation` (reset: 0) */
+    void*    scratch;        /* optional, 32-byte aligned, n * num_rocks * 32 bytes, contents irrelevant: when none of the six
+                                [n, num_rocks] planes above is passed (fresh planes in, none out) and max_steps <= 32767, the
+                                rollout keeps its per-rock side-state here as one lazily touched 32-byte record per rock
+                                instead of in thread-local arrays (one sector in and out per check instead of ~14)          */
 } PomdpRockHeuristicPlanes;
 int pomdp_rock_history_update(const PomdpRockParams* params, const int32_t* observation_field, const int32_t* action,
                               const int32_t* next_observation_field, int32_t* check_totals, int64_t n, void* stream);

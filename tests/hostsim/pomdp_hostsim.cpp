@@ -737,17 +737,25 @@ void rock_rollout_preferred_host(const RockDev& d, const void* table, const int3
                                  const RockPlanesPtr& pl, int32_t* final_state, double* ret, int32_t* steps, int32_t* flags, int64_t n,
                                  int64_t goff, uint64_t seed, uint32_t step, int32_t max_steps, double gamma, bool next_is_reward) {
     const PhiloxKey key = philox_key(seed);
+    const bool records = pl.scratch && !pl.count && !pl.measured && !pl.lkv && !pl.lkw && !pl.pv && !pl.totals && max_steps <= 32767;
     for (int64_t i = 0; i < n; ++i) {
-        RockHeurLocal h;
-        h.load(pl, i * d.k, d.k);
         int32_t prev_ob = pl.prev_obs ? pl.prev_obs[i] : 0;
         S s = load_state<S>(state, i);
         RolloutAcc acc;
-        rock_rollout_preferred1<S, STOCH>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma,
-                                          next_is_reward, first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        if (records) {
+            RockHeurRecords h;
+            h.init((RockRec*)pl.scratch + i * d.k);
+            rock_rollout_preferred1<S, STOCH>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma,
+                                              next_is_reward, first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+        } else {
+            RockHeurLocal h;
+            h.load(pl, i * d.k, d.k);
+            rock_rollout_preferred1<S, STOCH>(d, (const unsigned char*)table, s, key, (uint64_t)(goff + i), step, max_steps, gamma,
+                                              next_is_reward, first_action != nullptr, first_action ? first_action[i] : 0, h, prev_ob, acc);
+            h.store(pl, i * d.k, d.k);
+        }
         if (final_state) store_state(final_state, i, s);
         ret[i] = acc.ret; steps[i] = acc.steps; flags[i] = acc.flags;
-        h.store(pl, i * d.k, d.k);
         if (pl.prev_obs) pl.prev_obs[i] = prev_ob;
     }
 }
@@ -771,9 +779,9 @@ int pomdp_rock_rollout_preferred(const PomdpRockParams* q, const void* table, co
     if (rc) return rc;
     if ((rc = host::check_rollout(state, final_state, ret, steps, flags, n, goff, max_steps, "pomdp_rock_rollout_preferred"))) return rc;
     if (n > 0 && !table) return host::fail(POMDP_E_BADARG, "rock: table is NULL");
-    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    RockPlanesPtr pl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (planes) { pl.count = planes->count; pl.measured = planes->measured; pl.lkv = planes->lkv; pl.lkw = planes->lkw;
-                  pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs; }
+                  pl.pv = planes->prob_valuable; pl.totals = planes->check_totals; pl.prev_obs = planes->prev_obs; pl.scratch = planes->scratch; }
 #define HS_RRP(S, ST) rock_rollout_preferred_host<S, ST>(d, table, state, first_action, pl, final_state, ret, steps, flags, n, goff, seed, \
                                                          step, max_steps, discount, next_is_reward != 0)
     if (host::rock_words(q) == 1) { if (d.stochastic) HS_RRP(uint32_t, true); else HS_RRP(uint32_t, false); }
