@@ -550,6 +550,8 @@ def config_rows(dev, steps):
              "bound": "hbm"}
         if "issue_roofline" in r:
             o["issue_roofline"] = r["issue_roofline"]
+        if "pattern_roof_us" in r:          # the compute-free probe of the step's six streams at this batch size, same run
+            o["pattern_roof_us"], o["frac_of_pattern_roof"] = r["pattern_roof_us"], r["frac_of_pattern_roof"]
         out.append(o)
     return out
 

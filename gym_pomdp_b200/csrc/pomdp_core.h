@@ -556,11 +556,19 @@ POMDP_HD void tag_build_tables(TagTables* T) {
     for (int i = 0; i < 32; ++i) T->mv[i] = i < TAG_CELLS ? tag_mv_entry(i) : 0u;
 }
 
+// Opponent j's move (tag.py:204-205) takes ONE draw word, slot j: np.random.binomial(1, move_prob) reads it whole
+// (move iff w < T), np.random.choice(actions) reads its LOW half, i.e. the word tag_pick_word(w) = w << 16 under the
+// usual floor(u * len) rule.  The multisets of this board have 2 or 4 elements, so 16 bits pick exactly uniformly, and
+// the low half of a word is independent of "w < T" to within 2^-16 / move_prob (chi-square-tested against the
+// reference's counts) -- one Philox call per four envs per opponent instead of two.
+POMDP_HD uint32_t tag_pick_word(uint32_t w) { return w << 16; }
+
 // The stock Tag-v0 (one opponent) without a branch: both the move and the TAG outcome are formed from two table
 // words and the result is selected.  Same semantics as tag_step below (which handles 1..4 opponents).
-//   w_move = draw slot 0 (np.random.binomial(1, move_prob), tag.py:204), w_pick = slot 1 (np.random.choice, tag.py:205)
-POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w_move,
-                            uint32_t w_pick, uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+//   w = draw slot 0: np.random.binomial(1, move_prob) (tag.py:204) and, through tag_pick_word, np.random.choice (tag.py:205)
+POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w,
+                            uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
+    const uint32_t w_move = w, w_pick = tag_pick_word(w);
     const uint32_t agent = s & 31u, opp = (s >> 5) & 31u;
     const uint32_t e = T->pair[(s & 1023u) + (TAG_PAIR_PITCH - 32u) * opp];               // tag_pair_index; 0 <=> a cell id outside the board
     const uint32_t mvw = T->mv[agent];
@@ -589,7 +597,7 @@ POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, ui
 }
 
 // tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).
-// Draw slots per opponent j: 2j = np.random.binomial(1, move_prob) (tag.py:204), 2j+1 = np.random.choice (tag.py:205).
+// Draw slot j serves opponent j: np.random.binomial(1, move_prob) (tag.py:204) and np.random.choice (tag.py:205, tag_pick_word).
 template <class D>
 POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, const D& draw,
                        uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
@@ -616,8 +624,9 @@ POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_
                 --nopp;
             } else if (nopp > 0) {                                                // tag.py:128 (opp is inside by construction)
                 const uint32_t e = T->pair[tag_pair_index(agent, o)];
-                if (bern(draw(2 * j), p.move_T)) {                                // tag.py:204
-                    const uint32_t pick = rand_below(draw(2 * j + 1), e >> 20);   // tag.py:205
+                const uint32_t w = draw(j);
+                if (bern(w, p.move_T)) {                                          // tag.py:204
+                    const uint32_t pick = rand_below(tag_pick_word(w), e >> 20);  // tag.py:205
                     s2 = (s2 & ~(31u << sh)) | (((e >> (5u * pick)) & 31u) << sh);  // tag.py:206-207
                 }
             }
@@ -638,8 +647,8 @@ POMDP_HD void tag_step(const TagDev& p, const TagTables* __restrict__ T, uint32_
 }
 
 // tag_step for the FOUR envs of one draw group with 2..4 opponents: the opponents are walked in the outer loop, so only
-// the two draw blocks of the current opponent (slots 2j, 2j+1; one Philox call each for the four envs) are live at a
-// time -- precomputing all eight blocks (32 words) spilled registers.  Same semantics, env by env, as tag_step.
+// the draw block of the current opponent (slot j: one Philox call for the four envs) is live at a time.  Same
+// semantics, env by env, as tag_step.
 POMDP_HD void tag_step4_multi(const TagDev& p, const TagTables* __restrict__ T, const uint32_t s[4], const int32_t a[4],
                               const PhiloxKey& seed, uint64_t group, uint32_t step, uint32_t s2[4], int32_t ob[4], float rw[4],
                               int32_t fl[4]) {
@@ -659,8 +668,7 @@ POMDP_HD void tag_step4_multi(const TagDev& p, const TagTables* __restrict__ T, 
     for (int j = 0; j < p.n_opp; ++j) {                                                          // tag.py:119-131
         const bool any_tag = (a[0] == 4 && !err[0]) || (a[1] == 4 && !err[1]) || (a[2] == 4 && !err[2]) || (a[3] == 4 && !err[3]);
         if (!any_tag) break;
-        const U4 qm = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)(2 * j));
-        const U4 qp = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)(2 * j + 1));
+        const U4 qm = draw_quad(seed, group, step, DOMAIN_STEP, (uint32_t)j);
         const int sh = 5 + 5 * j;
         POMDP_UNROLL
         for (int e = 0; e < 4; ++e) {
@@ -673,7 +681,7 @@ POMDP_HD void tag_step4_multi(const TagDev& p, const TagTables* __restrict__ T, 
             } else if (nopp[e] > 0) {                                                            // tag.py:128
                 const uint32_t en = T->pair[tag_pair_index(agent, o)];
                 if (bern(word_of(qm, e), p.move_T)) {                                            // tag.py:204
-                    const uint32_t pick = rand_below(word_of(qp, e), en >> 20);                  // tag.py:205
+                    const uint32_t pick = rand_below(tag_pick_word(word_of(qm, e)), en >> 20);   // tag.py:205
                     s2[e] = (s2[e] & ~(31u << sh)) | (((en >> (5u * pick)) & 31u) << sh);        // tag.py:206-207
                 }
             }

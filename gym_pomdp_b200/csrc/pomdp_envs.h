@@ -78,7 +78,7 @@ POMDP_HD void quad_words(const PhiloxKey& seed, uint64_t group, uint32_t ctr, ui
     }
 }
 
-// NOPP = 1: the stock Tag-v0 (two draw slots); NOPP = 4: any num_opponents in 1..4.
+// NOPP = 1: the stock Tag-v0 (one draw slot); NOPP = 4: any num_opponents in 1..4.
 template <int NOPP>
 struct TagEnvT {
     typedef TagDev Params;
@@ -101,11 +101,11 @@ struct TagEnvT {
                                                  float rw[4], int32_t fl[4]) {
         const TagTables* T = reinterpret_cast<const TagTables*>(tbl);
         if (NOPP == 1) {
-            const U4 qm = draw_quad(seed, group, ctr, DOMAIN_STEP, 0), qp = draw_quad(seed, group, ctr, DOMAIN_STEP, 1);
-            tag_step_1opp(p, T, s[0], a[0], qm.x, qp.x, s2[0], ob[0], rw[0], fl[0]);
-            tag_step_1opp(p, T, s[1], a[1], qm.y, qp.y, s2[1], ob[1], rw[1], fl[1]);
-            tag_step_1opp(p, T, s[2], a[2], qm.z, qp.z, s2[2], ob[2], rw[2], fl[2]);
-            tag_step_1opp(p, T, s[3], a[3], qm.w, qp.w, s2[3], ob[3], rw[3], fl[3]);
+            const U4 q = draw_quad(seed, group, ctr, DOMAIN_STEP, 0);
+            tag_step_1opp(p, T, s[0], a[0], q.x, s2[0], ob[0], rw[0], fl[0]);
+            tag_step_1opp(p, T, s[1], a[1], q.y, s2[1], ob[1], rw[1], fl[1]);
+            tag_step_1opp(p, T, s[2], a[2], q.z, s2[2], ob[2], rw[2], fl[2]);
+            tag_step_1opp(p, T, s[3], a[3], q.w, s2[3], ob[3], rw[3], fl[3]);
             return;
         }
         tag_step4_multi(p, T, s, a, seed, group, ctr, s2, ob, rw, fl);

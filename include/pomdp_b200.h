@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 10
+#define POMDP_ABI_VERSION 11
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -134,7 +134,9 @@ typedef struct PomdpTagParams {
 int64_t pomdp_tag_table_bytes(void);
 int     pomdp_tag_build_table(void* host_table);
 /* TagEnv.step tag.py:108-143 (+ move_opponent 201-207, _admissable_actions 260-280,
- * _sample_ob 219-226).  Draw slots per opponent j: 2j = move Bernoulli, 2j+1 = choice.   */
+ * _sample_ob 219-226).  Draw slot j is opponent j's word w: the move Bernoulli (tag.py:204) reads it
+ * whole (w < ceil(move_prob * 2^32)), the choice among the admissible moves (tag.py:205) reads its
+ * low half -- floor(((w << 16) mod 2^32) * len / 2^32); len is 2 or 4 on this board.          */
 int pomdp_tag_step(const PomdpTagParams* params, const void* d_table,
                    const int32_t* state, const int32_t* action,
                    int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,

@@ -188,6 +188,7 @@ def gen_rock(E, n, k, stochastic, n_random, tag):
 def gen_tag(E, n_opp, tag):
     from gym_pomdp.envs.coord import Coord
     from gym_pomdp.envs.tag import TagState
+    from oracle.pomdp_oracle import tag_pick_word
     d = ref_shim.draws()
     env = E.TagEnv(num_opponents=n_opp)
     g = env.grid
@@ -221,7 +222,7 @@ def gen_tag(E, n_opp, tag):
         ag.append(int(ra[i])); ops.append(o); acts.append(int(ract[i] if i % 2 else 4))
         nop.append(n_opp if n_opp == 1 else 1 + int(rng_ints(1, n_opp, 900 + i)[0]))
     N = len(ag)
-    dr = words(N, 2 * n_opp, stream=12)
+    dr = words(N, n_opp, stream=12)
     T = int(np.ceil(0.8 * 2.0 ** 32))
     for i in range(n_ex, min(N, n_ex + 200)):
         dr[i, 0] = T - (i & 1)  # Bernoulli(0.8) boundary
@@ -230,7 +231,7 @@ def gen_tag(E, n_opp, tag):
     cur = {"i": 0}
 
     def move_opponent(opp):
-        d.clear(); d.feed([dr[cur["i"], 2 * opp], dr[cur["i"], 2 * opp + 1]])
+        d.clear(); d.feed([dr[cur["i"], opp], tag_pick_word(dr[cur["i"], opp])])
         orig_move(opp)
         d.clear()
     env.move_opponent = move_opponent

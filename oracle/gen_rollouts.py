@@ -23,7 +23,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import philox, ref_shim  # noqa: E402
-from oracle.pomdp_oracle import rock_reset_word, tag_reset_word  # noqa: E402
+from oracle.pomdp_oracle import rock_reset_word, tag_pick_word, tag_reset_word  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SEED = 0x5EED
@@ -97,8 +97,8 @@ def gen_tag(E, out, tag, n_opp, M, T):
     orig_move = env.move_opponent
     cur = {}
 
-    def move_opponent(opp):                                      # slots 2j, 2j+1 belong to opponent j (tag.py:201-207)
-        d.clear(); d.feed([cur["w"][2 * opp], cur["w"][2 * opp + 1]])
+    def move_opponent(opp):                                      # slot j belongs to opponent j (tag.py:201-207)
+        d.clear(); d.feed([cur["w"][opp], tag_pick_word(cur["w"][opp])])
         orig_move(opp)
         d.clear()
     env.move_opponent = move_opponent
@@ -114,7 +114,7 @@ def gen_tag(E, out, tag, n_opp, M, T):
 
         def feed_step(w, a):
             cur["w"] = w
-        r, t, acts, done, (a1, o1, n1) = run(env, d, e, T, 2 * n_opp, feed_step, snap, gamma=env._discount)
+        r, t, acts, done, (a1, o1, n1) = run(env, d, e, T, n_opp, feed_step, snap, gamma=env._discount)
         for key, v in zip(res, (a0, o0, r, t, acts, done, a1, o1, n1)):
             res[key].append(v)
     env.move_opponent = orig_move
@@ -344,7 +344,7 @@ def gen_tag_heur(E, out, tag, n_opp, M, T):
     cur = {}
 
     def move_opponent(opp):
-        d.clear(); d.feed([cur["w"][2 * opp], cur["w"][2 * opp + 1]])
+        d.clear(); d.feed([cur["w"][opp], tag_pick_word(cur["w"][opp])])
         orig_move(opp)
         d.clear()
     env.move_opponent = move_opponent
@@ -368,7 +368,7 @@ def gen_tag_heur(E, out, tag, n_opp, M, T):
             d.clear(); d.feed([W(e, ctr, philox.DOMAIN_POLICY, 1)[0]])
             a = int(np.random.choice(pref))
             d.clear()
-            cur["w"] = W(e, ctr, philox.DOMAIN_STEP, 2 * n_opp)
+            cur["w"] = W(e, ctr, philox.DOMAIN_STEP, n_opp)
             ob, rw_, done, info = env.step(a)
             d.clear()
             history.append(a, ob)

@@ -310,14 +310,15 @@ void oracle_tag_admissible(int agent, int opp, int8_t out[4]) {
 }
 
 /* tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).  agent: int32[N] cell ids,
- * opp: int32[N,n_opp], num_opp: int32[N] (all updated in place); draws uint32[N, 2*n_opp]. */
+ * opp: int32[N,n_opp], num_opp: int32[N] (all updated in place); draws uint32[N, n_opp]: slot j is opponent j's
+ * word -- binomial(1, move_prob) reads it whole, choice(actions) its low half (the word w << 16). */
 void oracle_tag_step(int n_opp, double move_prob, int64_t N, int32_t* agent, int32_t* opp, int32_t* num_opp,
                      const int32_t* action, const uint32_t* draws, int32_t* obs, double* reward, uint8_t* done) {
     for (int64_t i = 0; i < N; ++i) {
         int ax, ay;
         oracle_tag_get_coord(agent[i], &ax, &ay);
         int32_t* o = opp + i * n_opp;
-        const uint32_t* dr = draws + i * 2 * n_opp;
+        const uint32_t* dr = draws + i * n_opp;
         const int a = action[i];
         double rw = 0.;
         if (a == 4) {
@@ -330,8 +331,8 @@ void oracle_tag_step(int n_opp, double move_prob, int64_t N, int32_t* agent, int
                 } else if (oracle_tag_is_inside(ox, oy) && num_opp[i] > 0) {
                     int acts[8];
                     const int cnt = tag_admissible(ax, ay, ox, oy, acts);      /* tag.py:203 */
-                    if (bern(dr[2 * j], move_prob)) {                          /* tag.py:204 */
-                        const int m = acts[below(dr[2 * j + 1], cnt)];         /* tag.py:205 */
+                    if (bern(dr[j], move_prob)) {                              /* tag.py:204 */
+                        const int m = acts[below(dr[j] << 16, cnt)];           /* tag.py:205 */
                         if (oracle_tag_is_inside(ox + MOVE_DX[m], oy + MOVE_DY[m]))
                             o[j] = oracle_tag_get_index(ox + MOVE_DX[m], oy + MOVE_DY[m]);
                     }
@@ -633,7 +634,7 @@ void oracle_tag_rollout(int n_opp, double move_prob, int64_t N, int32_t* agent, 
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 5), ob;   /* tag.py:228-229 */
             double rw;
             if (t == 0 && first_action) a = first_action[i];
-            for (int s = 0; s < 2 * n_opp; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
+            for (int s = 0; s < n_opp; ++s) dr[s] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, s);
             oracle_tag_step(n_opp, move_prob, 1, agent + i, opp + i * n_opp, num_opp + i, &a, dr, &ob, &rw, &fin);
             r += rw * disc;
             disc *= gamma;

@@ -316,8 +316,8 @@ def tag_sample_ob(ax, ay, opps, action):
 def tag_step(ax, ay, opps, num_opp, action, draw, move_prob=0.8):
     """tag.py:108-143.  Returns (ax, ay, opps, num_opp, obs, reward, done).
 
-    Draw slots per opponent j: 2j = ``binomial(1, move_prob)`` (tag.py:204),
-    2j+1 = ``choice(actions)`` (tag.py:205; consumed only when the first says move).
+    Draw slot j is opponent j's word: ``binomial(1, move_prob)`` (tag.py:204) reads it whole, ``choice(actions)``
+    (tag.py:205; consumed only when the first says move) reads its low half, ``tag_pick_word``.
     """
     opps = [tuple(o) for o in opps]
     if action == 4:
@@ -330,8 +330,9 @@ def tag_step(ax, ay, opps, num_opp, action, draw, move_prob=0.8):
                 num_opp -= 1
             elif tag_is_inside(ox, oy) and num_opp > 0:
                 acts = tag_admissible(ax, ay, ox, oy)  # tag.py:201-207
-                if draw(2 * j) < bern_threshold(move_prob):
-                    dx, dy = MOVES[acts[rand_below(draw(2 * j + 1), len(acts))]]
+                w = draw(j)
+                if w < bern_threshold(move_prob):
+                    dx, dy = MOVES[acts[rand_below(tag_pick_word(w), len(acts))]]
                     if tag_is_inside(ox + dx, oy + dy):
                         opps[j] = (ox + dx, oy + dy)
         if not tagged:
@@ -343,6 +344,11 @@ def tag_step(ax, ay, opps, num_opp, action, draw, move_prob=0.8):
             ax, ay = ax + dx, ay + dy
     ob = tag_sample_ob(ax, ay, opps, action)
     return ax, ay, opps, num_opp, ob, reward, num_opp == 0
+
+
+def tag_pick_word(w):
+    """The word np.random.choice (tag.py:205) is scripted with: the low half of the opponent's draw word."""
+    return (int(w) << 16) & 0xFFFFFFFF
 
 
 def tag_reset_word(slot_word, digit):

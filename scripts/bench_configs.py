@@ -172,6 +172,21 @@ def run_configs(dev, steps=400, only=None, kernels=("step", "step_packed", "rese
             ir = issue_roofline(label, "step", B, ms)
             if ir:
                 row["issue_roofline"] = ir
+            if W == 1 and B % 4 == 0:
+                # the compute-free probe of this traffic pattern (two read + four write int32 streams) at this batch size:
+                # what a kernel that only moves the step's bytes takes, fixed launch cost included
+                from gym_pomdp_b200 import _lib
+
+                def probe(i):
+                    s, a, o = sets[i % n_sets]
+                    _lib.check(_lib.lib().pomdp_stream_probe(s.data_ptr(), a.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                                             o[3].data_ptr(), B, torch.cuda.current_stream(dev).cuda_stream), "pomdp_stream_probe")
+                try:
+                    pms = time_graph(probe, K, dev)
+                    row["pattern_roof_us"] = pms * 1e3
+                    row["frac_of_pattern_roof"] = pms / ms
+                except Exception as e:  # noqa: BLE001
+                    row["pattern_roof_error"] = repr(e)[:120]
             add(row)
 
         if "step_packed" in kernels and name != "battleship":

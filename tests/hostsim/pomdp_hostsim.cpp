@@ -192,7 +192,7 @@ int pomdp_tag_step(const PomdpTagParams* q, const void* table, const int32_t* st
         uint32_t s2;
         const LazyDraw draw{&key, (uint64_t)(goff + i), step, DOMAIN_STEP};
         // the stock one-opponent env alternates between the kernels' two functors (general / branch-free)
-        if (d.n_opp == 1 && (i & 1)) tag_step_1opp(d, T, (uint32_t)state[i], action[i], draw(0), draw(1), s2, obs[i], rw[i], fl[i]);
+        if (d.n_opp == 1 && (i & 1)) tag_step_1opp(d, T, (uint32_t)state[i], action[i], draw(0), s2, obs[i], rw[i], fl[i]);
         else tag_step(d, T, (uint32_t)state[i], action[i], draw, s2, obs[i], rw[i], fl[i]);
         next[i] = (int32_t)s2;
     }

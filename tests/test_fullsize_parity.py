@@ -121,7 +121,7 @@ def test_tag_batch_2p20(backend):
         action = dev_ints(g, 0, 5, (B,), backend).int()
         ns, ob, rw, fl = env.simulate(env.pack(agent, opp), action, step_ctr=23)
         a2, o2, nop2, done = (v.cpu().numpy() for v in env.unpack(ns))
-        draws = C.fill_draws(SEED, 0, B, 23, philox.DOMAIN_STEP, 2 * n_opp)
+        draws = C.fill_draws(SEED, 0, B, 23, philox.DOMAIN_STEP, n_opp)
         ea, eo, enop, eob, erw, edone = C.tag_step(n_opp, 0.8, agent.cpu().numpy(), opp.cpu().numpy(),
                                                    np.full(B, n_opp, np.int32), action.cpu().numpy(), draws)
         assert np.array_equal(a2, ea) and np.array_equal(o2, eo) and np.array_equal(nop2, enop)
