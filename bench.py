@@ -660,7 +660,7 @@ def collective_row(gp, torch, dist, dev, rank, world):
     row = {"workload": "RockSample(15,15) global batch 2^25 over %d rank(s): belief histogram%s" % (
                world, " + ncclAllReduce(sum)" if world > 1 else " (one rank: no collective)"),
            "batch_per_gpu": B, "bins": int(red.numel()), "hist_plus_allreduce_us": us, "hist_only_us": hist_us, "ok": ok,
-           "note": "eager launches (zero-fill + histogram kernel + all-reduce), CUDA events, max over ranks"}
+           "note": "eager launches (self-cleaning histogram kernel + all-reduce), CUDA events, max over ranks"}
     if world > 1:
         row["fused"] = {"hist_allreduce_us": fused_us, "equals_nccl": fused_ok, "error": fused_err,
                         "what": "pomdp_belief_hist_allreduce: ONE kernel -- the last CTA of every rank adds the rank's counts into "

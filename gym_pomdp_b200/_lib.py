@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -136,6 +136,7 @@ _PROTOTYPES = {
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),
+    "pomdp_belief_hist_once": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, _P, c_void_p]),
     "pomdp_belief_hist_allreduce": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, _P, c_int32, c_int32, c_int32,
                                               _P, c_void_p]),
 }

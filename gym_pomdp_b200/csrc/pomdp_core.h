@@ -325,6 +325,7 @@ POMDP_HD S rock_reset_from_word(const RockDev& p, uint32_t w) {
 template <typename S, class D>
 POMDP_HD S rock_reset(const RockDev& p, const D& draw) { return rock_reset_from_word<S>(p, draw(0)); }
 POMDP_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+POMDP_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 // Four envs of one aligned group: ONE Philox call, then per env one shift and one LOP3 -- with
 // C1 = start | (0x55555555 & m) << 8 and C2 = (0xAAAAAAAA & m) << 8 (loop invariants) the packed state is
 // C1 | (~(w << 8) & C2).  The tie (a word that is a single bit) is tested once for the four words and handled out
@@ -515,11 +516,24 @@ POMDP_HD int tag_admissible(int ax, int ay, int ox, int oy, uint32_t& list) {
 #endif
 constexpr uint32_t TAG_PAIR_PITCH = POMDP_TAG_PAIR_PITCH;
 POMDP_HD uint32_t tag_pair_index(uint32_t agent, uint32_t opp) { return opp * TAG_PAIR_PITCH + agent; }
+//   lut[a * 32 * 33 + pair index]   the WHOLE transition of the stock one-opponent env for (agent, opp, action a), as
+//                           differences to XOR into the state word:
+//                           bits 0-19: (the opponent's next cell ^ opp) for each value 0..3 of the TOP TWO bits of the
+//                           pick word (a two-element multiset appears as [c0, c0, c1, c1], so floor(u * len) and "top
+//                           two bits" name the same element) -- all zero when the opponent cannot move (a move action,
+//                           or a TAG that hits: tag.py:122-128);  bits 20-24: the agent's next cell ^ agent;
+//                           bits 25-29: the observation (tag.py:219-226) ^ 31, which is never 0;  bit 30: a == TAG;
+//                           bit 31: the TAG hits.  0 <=> not a valid (agent, opp, action).  tag_step_1opp reads nothing else.
+constexpr uint32_t TAG_LUT_PLANE = 32 * TAG_PAIR_PITCH;
 struct TagTables {
     uint32_t pair[32 * TAG_PAIR_PITCH];
     uint32_t mv[32];
+    uint32_t lut[5 * TAG_LUT_PLANE];
 };
 static_assert(sizeof(TagTables) % 16 == 0, "TMA bulk copy needs 16 B multiples");
+// pair + mv: all that the general functor (1..4 opponents), the heuristics and the queries read
+constexpr uint32_t TAG_TABLES_BASE_BYTES = (uint32_t)((32 * TAG_PAIR_PITCH + 32) * sizeof(uint32_t));
+static_assert(TAG_TABLES_BASE_BYTES % 16 == 0, "TMA bulk copy needs 16 B multiples");
 POMDP_HD uint32_t tag_pair_entry(int agent, int opp) {
     int ax, ay, ox, oy;
     tag_get_coord((uint32_t)agent, ax, ay);
@@ -548,12 +562,29 @@ POMDP_HD uint32_t tag_mv_entry(int agent) {
     }
     return e;
 }
+POMDP_HD uint32_t tag_lut_entry(int agent, int opp, int a) {
+    const bool is_tag = a == 4, hit = is_tag && opp == agent;                     // tag.py:119-126
+    const uint32_t agent2 = is_tag ? (uint32_t)agent : ((tag_mv_entry(agent) >> (5 * a)) & 31u);      // tag.py:133-137
+    uint32_t cells = 0;                                                           // the opponent stays
+    if (is_tag && !hit) {                                                         // tag.py:128, 201-207
+        const uint32_t e = tag_pair_entry(agent, opp), len = e >> 20;             // len is 2 or 4 on this board
+        for (uint32_t top2 = 0; top2 < 4; ++top2)
+            cells |= (((e >> (5u * ((top2 * len) >> 2))) & 31u) ^ (uint32_t)opp) << (5u * top2);
+    }
+    const uint32_t ob = (!is_tag && agent2 == (uint32_t)opp) ? (uint32_t)TAG_CELLS : agent2;           // tag.py:219-226
+    return cells | ((agent2 ^ (uint32_t)agent) << 20) | ((ob ^ 31u) << 25) | ((uint32_t)is_tag << 30) | ((uint32_t)hit << 31);
+}
 POMDP_HD void tag_build_tables(TagTables* T) {
     for (uint32_t i = 0; i < 32 * TAG_PAIR_PITCH; ++i) T->pair[i] = 0u;
     for (int opp = 0; opp < TAG_CELLS; ++opp)
         for (int agent = 0; agent < TAG_CELLS; ++agent)
             T->pair[tag_pair_index((uint32_t)agent, (uint32_t)opp)] = tag_pair_entry(agent, opp);   // never 0 for a valid pair
     for (int i = 0; i < 32; ++i) T->mv[i] = i < TAG_CELLS ? tag_mv_entry(i) : 0u;
+    for (uint32_t i = 0; i < 5 * TAG_LUT_PLANE; ++i) T->lut[i] = 0u;
+    for (int a = 0; a < 5; ++a)
+        for (int opp = 0; opp < TAG_CELLS; ++opp)
+            for (int agent = 0; agent < TAG_CELLS; ++agent)
+                T->lut[(uint32_t)a * TAG_LUT_PLANE + tag_pair_index((uint32_t)agent, (uint32_t)opp)] = tag_lut_entry(agent, opp, a);
 }
 
 // Opponent j's move (tag.py:204-205) takes ONE draw word, slot j: np.random.binomial(1, move_prob) reads it whole
@@ -563,37 +594,38 @@ POMDP_HD void tag_build_tables(TagTables* T) {
 // reference's counts) -- one Philox call per four envs per opponent instead of two.
 POMDP_HD uint32_t tag_pick_word(uint32_t w) { return w << 16; }
 
-// The stock Tag-v0 (one opponent) without a branch: both the move and the TAG outcome are formed from two table
-// words and the result is selected.  Same semantics as tag_step below (which handles 1..4 opponents).
+// The stock Tag-v0 (one opponent) without a branch: ONE table word holds the whole transition of (agent, opp, action);
+// the draw only selects which of its four opponent cells is taken.  Same semantics as tag_step below (which handles
+// 1..4 opponents).  _fast is the transition alone; the caller has ruled out done states, bad actions and bad cells.
 //   w = draw slot 0: np.random.binomial(1, move_prob) (tag.py:204) and, through tag_pick_word, np.random.choice (tag.py:205)
+POMDP_HD uint32_t tag_lut_word(const TagTables* __restrict__ T, uint32_t s, int32_t a) {
+    const uint32_t ac = (uint32_t)a < 4u ? (uint32_t)a : 4u;                              // clamps the index; a > 4 is flagged by the caller
+    return T->lut[ac * TAG_LUT_PLANE + (s & 1023u) + (TAG_PAIR_PITCH - 32u) * ((s >> 5) & 31u)];
+}
+// the transition of an env that is neither done nor flagged (e != 0, 0 <= a <= 4); anything else: tag_step_1opp
+POMDP_HD void tag_step_1opp_fast(const TagDev& p, uint32_t e, uint32_t s, uint32_t w, uint32_t& s2, int32_t& ob, float& rw,
+                                 int32_t& fl) {
+    const bool alive = (int32_t)(s << 1) >= (1 << 26);                                    // num_opp > 0 (6-bit two's complement, bits 25-30)
+    const bool moves = alive && p.move_on && w <= p.move_thr_m1;                          // tag.py:128, 204 (TAG and miss are in the entry)
+    const uint32_t d_opp = moves ? ((e >> (5u * ((w >> 14) & 3u))) & 31u) : 0u;           // tag.py:205-207: top two bits of tag_pick_word(w)
+    // num_opp lives in bits 25-30: a successful TAG subtracts one in place (6-bit wrap as tag_set_num_opp does; the borrow
+    // can only reach bit 31, the done bit, which is clear on this path)
+    const uint32_t ns = ((s ^ ((e >> 20) & 31u) ^ (d_opp << 5)) - ((e >> 6) & (1u << 25))) & 0x7FFFFFFFu;   // tag.py:133-137
+    const bool done = (ns & (63u << 25)) == 0u;                                           // tag.py:142
+    s2 = ns | (done ? TAG_DONE : 0u);
+    ob = (int32_t)((~e >> 25) & 31u);                                                     // tag.py:219-226
+    rw = bits_to_float(((e & (1u << 30)) ? 0xC1200000u : 0xBF800000u) ^ (e & 0x80000000u));   // -1; TAG: -10, +10 when it hits (tag.py:122-131)
+    fl = done ? (int32_t)FLAG_DONE : 0;
+}
 POMDP_HD void tag_step_1opp(const TagDev& p, const TagTables* __restrict__ T, uint32_t s, int32_t a, uint32_t w,
                             uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
-    const uint32_t w_move = w, w_pick = tag_pick_word(w);
-    const uint32_t agent = s & 31u, opp = (s >> 5) & 31u;
-    const uint32_t e = T->pair[(s & 1023u) + (TAG_PAIR_PITCH - 32u) * opp];               // tag_pair_index; 0 <=> a cell id outside the board
-    const uint32_t mvw = T->mv[agent];
-    const bool is_tag = a == 4;
-    const bool hit = opp == agent;                                                        // tag.py:122-126
-    const bool alive = (s & (63u << 25)) != 0u && !(s >> 30 & 1u);                        // num_opp > 0 (6-bit two's complement)
-    const bool moves = is_tag && !hit && alive && p.move_on && w_move <= p.move_thr_m1;   // tag.py:128, 204
-    const uint32_t opp_t = (e >> (5u * rand_below(w_pick, e >> 20))) & 31u;               // tag.py:205-207
-    const uint32_t agent2 = is_tag ? agent : ((mvw >> (5u * ((uint32_t)a & 3u))) & 31u);  // tag.py:133-137
-    const uint32_t opp2 = moves ? opp_t : opp;
-    // num_opp lives in bits 25-30: a successful TAG subtracts one in place (6-bit wrap as tag_set_num_opp does)
-    uint32_t ns = (s & ~1023u) | agent2 | (opp2 << 5);
-    ns = (is_tag && hit) ? ((ns & ~(63u << 25)) | ((ns - (1u << 25)) & (63u << 25))) : ns;
-    const bool done = (ns & (63u << 25)) == 0u;                                           // tag.py:142
-    ns |= done ? TAG_DONE : 0u;
-    const float reward = is_tag ? (hit ? 10.f : -10.f) : -1.f;
-    const int32_t o = (!is_tag && agent2 == opp2) ? TAG_CELLS : (int32_t)agent2;          // tag.py:219-226
+    const uint32_t e = tag_lut_word(T, s, a);
     // the reference's asserts (tag.py:109-110, 116-117): flagged, state untouched, obs = reward = 0
     const int32_t err = (s & TAG_DONE) ? (int32_t)(FLAG_DONE | FLAG_STEPPED_DONE)
                         : ((uint32_t)a >= 5u) ? (int32_t)FLAG_BAD_ACTION
                         : (e == 0u) ? (int32_t)FLAG_BAD_STATE : 0;
-    s2 = err ? s : ns;
-    ob = err ? 0 : o;
-    rw = err ? 0.f : reward;
-    fl = err ? err : (done ? (int32_t)FLAG_DONE : 0);
+    if (err) { s2 = s; ob = 0; rw = 0.f; fl = err; return; }
+    tag_step_1opp_fast(p, e, s, w, s2, ob, rw, fl);
 }
 
 // tag.py:108-143 (+ move_opponent 201-207, _sample_ob 219-226).

@@ -20,6 +20,7 @@
 //  * policy / rollout / obs_prob / legal_mask / belief_hist: see the comments at each kernel.
 //
 // There is no CPU path in this file: every entry point launches a kernel.
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -400,6 +401,10 @@ pomdp_policy_kernel(const __grid_constant__ typename Env::Params p, const void* 
         action[i] = Env::policy(p, tbl, load_state1(state, i, S()), draw_word(seed, goff + (uint64_t)i, step_ctr, DOMAIN_POLICY, 0));
 }
 
+// An env may give the rollouts their own flavour of step4 (same results; Tag: pomdp_envs.h)
+template <class Env, class = void> struct HasRolloutStep : std::false_type {};
+template <class Env> struct HasRolloutStep<Env, std::void_t<decltype(&Env::step4_rollout)>> : std::true_type {};
+
 // Fused T-step rollout under the uniform-legal policy: the packed states stay in registers for the whole
 // rollout; per env the kernel reads 4W bytes and writes 4W + 16 (final state, float64 return, steps, flags).
 // One thread owns an aligned group of four envs, so every Philox call (one policy word + the step's own
@@ -450,7 +455,8 @@ pomdp_rollout_kernel(const __grid_constant__ typename Env::Params p, const void*
                 S s2[4];
                 int32_t ob[4], fl[4];
                 float rw[4];
-                Env::step4(p, tbl, s, a, seed, group, ctr, s2, ob, rw, fl);
+                if constexpr (HasRolloutStep<Env>::value) Env::step4_rollout(p, tbl, s, a, seed, group, ctr, s2, ob, rw, fl);
+                else Env::step4(p, tbl, s, a, seed, group, ctr, s2, ob, rw, fl);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (act[j]) {
@@ -647,7 +653,7 @@ pomdp_tag_preferred_kernel(const void* __restrict__ g_table, const int32_t* __re
                            const __grid_constant__ PhiloxKey seed, uint32_t step_ctr) {
     extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
-    stage_table_sync<TagEnvT<1>>(smem_table, g_table, (uint32_t)sizeof(TagTables), &bar);
+    stage_table_sync<TagEnvT<1>>(smem_table, g_table, TAG_TABLES_BASE_BYTES, &bar);
     const TagTables* T = reinterpret_cast<const TagTables*>(smem_table);
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
@@ -668,7 +674,7 @@ pomdp_tag_rollout_preferred_kernel(const __grid_constant__ TagDev p, const void*
     typedef TagEnvT<NOPP> Env;
     extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
-    stage_table_sync<Env>(smem_table, g_table, (uint32_t)sizeof(TagTables), &bar);
+    stage_table_sync<Env>(smem_table, g_table, TAG_TABLES_BASE_BYTES, &bar);
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
         uint32_t s = (uint32_t)state[i];
@@ -1293,7 +1299,9 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
     //   4. copy the slot -- now the GLOBAL counts -- to hist_out.
     // One kernel instead of zero-fill + histogram + a collective; the epoch lives in device memory, so the launch is
     // identical call after call and can be replayed from a CUDA graph.
-    if (peers) {
+    // Self-cleaning local call (pomdp_belief_hist_once: no peers): the same ticket; the last CTA MOVES the counts from the
+    // scratch to hist_out -- no zero-fill launch before the kernel, the scratch is all zero again after it.
+    if (peers || hist_out) {
         __shared__ bool last;
         __shared__ unsigned long long epoch_s;
         __threadfence();
@@ -1303,7 +1311,11 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
             epoch_s = hist[bins + 1] + 1ull;
         }
         __syncthreads();
-        if (last) {
+        if (last && !peers) {
+            __threadfence();
+            for (int b = threadIdx.x; b < bins; b += blockDim.x) hist_out[b] = atomicExch(&hist[b], 0ull);
+            if (threadIdx.x == 0) hist[bins] = 0ull;
+        } else if (last) {
             __threadfence();
             const unsigned long long epoch = epoch_s;
             const int64_t slot_off = (int64_t)((epoch - 1ull) & 1ull) * POMDP_HIST_MAX_BINS * 8;
@@ -1633,11 +1645,11 @@ int pomdp_tag_step(const PomdpTagParams* q, const void* d_table, const int32_t* 
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    const uint32_t tb = (uint32_t)sizeof(TagTables);
+    const uint32_t tb = (uint32_t)sizeof(TagTables), tbs = TAG_TABLES_BASE_BYTES;   // one opponent: + the transition LUT
     if (d.n_opp == 1)
         return launch_step<TagEnvT<1>>(d, d_table, tb, tb, state, action, next_state, obs, reward, flags, n, goff, seed,
                                        step_ctr, stream, "pomdp_tag_step");
-    return launch_step<TagEnvT<4>>(d, d_table, tb, tb, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+    return launch_step<TagEnvT<4>>(d, d_table, tbs, tbs, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
                                    stream, "pomdp_tag_step");
 }
 int pomdp_tag_reset(const PomdpTagParams* q, int32_t* state, int32_t* obs, const uint8_t* mask, int64_t n, int64_t goff,
@@ -1794,11 +1806,11 @@ int pomdp_tag_step_packed(const PomdpTagParams* q, const void* d_table, const in
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    const uint32_t tb = (uint32_t)sizeof(TagTables);
+    const uint32_t tb = (uint32_t)sizeof(TagTables), tbs = TAG_TABLES_BASE_BYTES;   // one opponent: + the transition LUT
     if (d.n_opp == 1)
         return launch_step<TagEnvT<1>, true>(d, d_table, tb, tb, state, action, next_state, result, nullptr, nullptr, n, goff,
                                              seed, step_ctr, stream, "pomdp_tag_step_packed");
-    return launch_step<TagEnvT<4>, true>(d, d_table, tb, tb, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
+    return launch_step<TagEnvT<4>, true>(d, d_table, tbs, tbs, state, action, next_state, result, nullptr, nullptr, n, goff, seed,
                                          step_ctr, stream, "pomdp_tag_step_packed");
 }
 int pomdp_tiger_step_packed(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
@@ -1980,8 +1992,8 @@ int pomdp_tag_policy(const PomdpTagParams* q, const void* d_table, const int32_t
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    const uint32_t tb = (uint32_t)sizeof(TagTables);
-    return launch_policy<TagEnvT<1>>(d, d_table, tb, tb, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
+    const uint32_t tbs = TAG_TABLES_BASE_BYTES;
+    return launch_policy<TagEnvT<1>>(d, d_table, tbs, tbs, state, action, n, goff, seed, step_ctr, stream, "pomdp_tag_policy");
 }
 int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* first_action, int32_t* final_state, double* ret,
                       int32_t* steps, int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr,
@@ -1989,11 +2001,11 @@ int pomdp_tag_rollout(const PomdpTagParams* q, const void* d_table, const int32_
     TagDev d;
     int rc = host::make_tag(q, &d);
     if (rc) return rc;
-    const uint32_t tb = (uint32_t)sizeof(TagTables);
+    const uint32_t tb = (uint32_t)sizeof(TagTables), tbs = TAG_TABLES_BASE_BYTES;   // one opponent: + the transition LUT
     if (d.n_opp == 1)
         return launch_rollout<TagEnvT<1>>(d, d_table, tb, tb, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                           max_steps, discount, stream, "pomdp_tag_rollout");
-    return launch_rollout<TagEnvT<4>>(d, d_table, tb, tb, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
+    return launch_rollout<TagEnvT<4>>(d, d_table, tbs, tbs, state, first_action, final_state, ret, steps, flags, n, goff, seed, step_ctr,
                                       max_steps, discount, stream, "pomdp_tag_rollout");
 }
 int pomdp_tiger_policy(const PomdpTigerParams* q, const int32_t* state, int32_t* action, int64_t n, int64_t goff,
@@ -2302,7 +2314,7 @@ int launch_tag_preferred(const PomdpTagParams* q, const void* d_table, const int
     if (((uintptr_t)last_obs | (uintptr_t)last_action) & 3) return host::fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
     if (n == 0) return 0;
     if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
-    const size_t smem = sizeof(TagTables);
+    const size_t smem = TAG_TABLES_BASE_BYTES;
     auto k = pomdp_tag_preferred_kernel<kPolicy>;
     k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(d_table, state, last_obs, last_action, out, n,
                                                                                            (uint64_t)goff, philox_key(seed), step_ctr);
@@ -2334,7 +2346,7 @@ int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* d_table, co
         return host::fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
     if (n == 0) return 0;
     if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
-    const size_t smem = sizeof(TagTables);
+    const size_t smem = TAG_TABLES_BASE_BYTES;
     if (d.n_opp == 1) {
         auto k = pomdp_tag_rollout_preferred_kernel<1>;
         k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
@@ -2404,6 +2416,22 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)hist, bins, nullptr, 0, 0, 0,
                                                nullptr);
     return finish("pomdp_belief_hist");
+}
+// One launch, no zero-fill before it: the CTA that takes the last ticket moves the counts from the scratch to hist_out.
+int pomdp_belief_hist_once(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                           long long* scratch, long long* hist_out, void* stream) {
+    const int rc = host::check_hist(kind, p0, p1, state, words, n, scratch, POMDP_HIST_MAX_BINS);
+    if (rc) return rc;
+    if (!scratch) return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_once: scratch is NULL");
+    if (!hist_out || ((uintptr_t)hist_out & 7)) return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_once: hist_out is NULL or not 8-byte aligned");
+    const int bins = host::hist_bins(kind, p0, p1);
+    auto k = hist_kernel_for(kind, words, n);
+    // n == 0 still launches: hist_out must come back all zero
+    const int64_t want = (n + 4095) / 4096;
+    const int grid = (int)(want < device_sms() ? (want < 1 ? 1 : want) : device_sms());
+    k<<<grid, 1024, 0, (cudaStream_t)stream>>>(p0, p1, state, words, n, (unsigned long long*)scratch, bins, nullptr, 0, 0, 0,
+                                               (unsigned long long*)hist_out);
+    return finish("pomdp_belief_hist_once");
 }
 // The histogram fused with its all-reduce over peer memory (include/pomdp_b200.h).
 int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,

@@ -565,11 +565,18 @@ class BatchedPomdpEnv(_EnvBase):
         p0, p1 = self._hist_args()
         L = _lib.lib()
         bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
-        hist = torch.zeros(bins, dtype=torch.int64, device=self.device)
+        # ONE launch (pomdp_belief_hist_once): the kernel's last CTA moves the counts from a self-cleaning scratch to the
+        # result, so no zero-fill kernel runs before it.  One scratch per stream: calls on one stream are ordered.
+        stream = self._stream()
+        scratches = self.__dict__.setdefault("_hist_scratch", {})
+        scratch = scratches.get(stream)
+        if scratch is None:
+            scratch = scratches[stream] = torch.zeros(self._FUSED_HIST_BINS + 2, dtype=torch.int64, device=self.device)
+        hist = torch.empty(bins, dtype=torch.int64, device=self.device)
         n = state.shape[0]
         with self._guard():
-            _lib.check(L.pomdp_belief_hist(self.kind, p0, p1, _lib.ptr(state), self.state_words, n, _lib.ptr(hist),
-                                           self._stream()), "pomdp_belief_hist")
+            _lib.check(L.pomdp_belief_hist_once(self.kind, p0, p1, _lib.ptr(state), self.state_words, n, _lib.ptr(scratch),
+                                                _lib.ptr(hist), stream), "pomdp_belief_hist_once")
         if all_reduce:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 11
+#define POMDP_ABI_VERSION 12
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -126,9 +126,10 @@ typedef struct PomdpTagParams {
 /* State: 1 word.  bits 0-4 agent cell, bits 5+5j..9+5j opponent j's cell (0..28),
  * bits 25-30 num_opp (6-bit two's complement; the reference lets it go negative with
  * several opponents), bit 31 done.                                                       */
-/* Static maps of the 29-cell board (4352 bytes: for every (agent, opponent) pair the cells the
- * opponent can reach through the move multiset of tag.py:260-280, and the agent's cell after each
- * move; layout in gym_pomdp_b200/csrc/pomdp_core.h: TagTables).  Filled on the host, uploaded by
+/* Static maps of the 29-cell board (25472 bytes: for every (agent, opponent) pair the cells the
+ * opponent can reach through the move multiset of tag.py:260-280, the agent's cell after each
+ * move, and -- for the stock one-opponent env -- the whole transition of every (agent, opponent,
+ * action) as one word; layout in gym_pomdp_b200/csrc/pomdp_core.h: TagTables).  Filled on the host, uploaded by
  * the caller (16-byte aligned) and passed as `d_table`; the kernels stage it into shared memory
  * with one TMA bulk copy per CTA.                                                             */
 int64_t pomdp_tag_table_bytes(void);
@@ -530,6 +531,12 @@ int pomdp_stream_probe(const int32_t* state, const int32_t* action,
 int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1);
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
                       int64_t n, long long* hist, void* stream);
+/* The same counts in ONE launch, no zero-fill before it: `scratch[POMDP_HIST_MAX_BINS + 2]` int64 is the caller's, zero
+ * before the first call; the CTAs accumulate into it, the CTA that takes the last ticket MOVES the counts to
+ * hist_out[bins] (overwritten, not accumulated) and leaves the scratch all zero for the next call.  One scratch serves
+ * one call at a time (calls on one stream; a second stream needs its own).  n = 0 writes zeros.                      */
+int pomdp_belief_hist_once(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
+                           int64_t n, long long* scratch, long long* hist_out, void* stream);
 /* The same histogram FUSED with its all-reduce over NVLink / NVSwitch peer memory: ONE kernel -- no zero-fill before it,
  * no collective after it.  Every rank passes the same device-resident table `d_peer_bufs[world]` of symmetric buffers,
  * one per rank, each mapped into this process (e.g. torch symmetric memory: _SymmetricMemory.buffer_ptrs_dev).  A

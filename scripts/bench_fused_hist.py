@@ -2,7 +2,7 @@
 """Config 5's collective on N GPUs (torchrun): belief histogram + all-reduce, three ways, eager and as a CUDA graph of 20 calls
 (the graph removes the interpreter from between the launches, so the GPU-side cost of each variant shows):
   hist        the histogram kernel alone (local counts)
-  nccl        zero-fill + histogram kernel + ncclAllReduce           belief_histogram(all_reduce=True)
+  nccl        histogram kernel (self-cleaning) + ncclAllReduce         belief_histogram(all_reduce=True)
   fused       ONE kernel: histogram + reductions into every rank's buffer over NVLink peer memory + arrive/wait,
               then the copy that hands the counts out               belief_histogram(all_reduce="fused")
     torchrun --nproc-per-node N scripts/bench_fused_hist.py [--out file.json]"""

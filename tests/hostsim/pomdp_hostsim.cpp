@@ -884,6 +884,19 @@ int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state
     return 0;
 }
 
+int pomdp_belief_hist_once(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,
+                           long long* scratch, long long* hist_out, void*) {
+    int rc = host::check_hist(kind, p0, p1, state, words, n, scratch, POMDP_HIST_MAX_BINS);
+    if (rc) return rc;
+    if (!scratch) return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_once: scratch is NULL");
+    if (!hist_out || ((uintptr_t)hist_out & 7)) return host::fail(POMDP_E_BADARG, "pomdp_belief_hist_once: hist_out is NULL or not 8-byte aligned");
+    const int bins = host::hist_bins(kind, p0, p1);
+    rc = pomdp_belief_hist(kind, p0, p1, state, words, n, scratch, nullptr);
+    if (rc) return rc;
+    for (int b = 0; b < bins; ++b) { hist_out[b] = scratch[b]; scratch[b] = 0; }
+    return 0;
+}
+
 // host stand-in of the fused histogram + all-reduce: the peer table holds host pointers; arrivals are counted, nobody waits
 // (the "ranks" of a test call one after the other), hist_out receives the slot as it stands after this rank's additions
 int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words, int64_t n,

@@ -141,7 +141,7 @@ def test_error_convention(which):
     assert L.pomdp_tag_step(ctypes.byref(_lib.TagParams(1, 0, .8)), None, None, None, None, None, None, None, 0, 0, 0, 0,
                             None) == 0
     assert L.pomdp_tag_step(ctypes.byref(_lib.TagParams(7, 0, .8)), p, p, p, p, p, p, p, 4, 0, 0, 0, None) == E_BADARG
-    assert L.pomdp_tag_table_bytes() == 4352 and L.pomdp_tag_build_table(None) == E_BADARG
+    assert L.pomdp_tag_table_bytes() == 25472 and L.pomdp_tag_build_table(None) == E_BADARG
     # rollouts / policy: same conventions
     d8 = np.zeros(8, np.float64).ctypes.data
     assert L.pomdp_rock_rollout(ctypes.byref(ok), p, p, None, p, d8, p, p, 4, 0, 0, 0, -1, .95, None) == E_BADARG      # max_steps < 0

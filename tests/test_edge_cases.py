@@ -282,6 +282,37 @@ def test_belief_histogram_matches_bincount(backend):
             assert np.array_equal(h.reshape(10, 10), occ.sum(0).T)      # bin c = 10*y + x
 
 
+def test_belief_histogram_once_is_self_cleaning(backend):
+    """pomdp_belief_hist_once (what belief_histogram calls): one launch, the result OVERWRITES hist_out, the scratch is
+    all zero again afterwards -- repeated calls over different particle sets and sizes (one CTA, many CTAs, ragged
+    ends, an empty set onto a dirty output) equal the accumulate-into-zeroed-array entry point every time."""
+    from gym_pomdp_b200 import _lib
+    L = _lib.lib()
+    envs = make_all(backend, 8)
+    rs = np.random.RandomState(5)
+    for name in NAMES:
+        env = envs[name]
+        p0, p1 = env._hist_args()
+        bins = L.pomdp_belief_hist_bins(env.kind, p0, p1)
+        scratch = torch.zeros(512 + 2, dtype=torch.int64, device=backend)
+        out = torch.full((bins,), -7, dtype=torch.int64, device=backend)
+        for n in (3000, 1, 0, 70001, 4096, 0, 5):
+            state, _ = random_inputs(env, name, max(n, 1), rs, backend)
+            state = state[:n]
+            with env._guard():
+                _lib.check(L.pomdp_belief_hist_once(env.kind, p0, p1, _lib.ptr(state), env.state_words, n, _lib.ptr(scratch),
+                                                    _lib.ptr(out), env._stream()), "pomdp_belief_hist_once")
+            exp = torch.zeros(bins, dtype=torch.int64, device=backend)
+            with env._guard():
+                _lib.check(L.pomdp_belief_hist(env.kind, p0, p1, _lib.ptr(state), env.state_words, n, _lib.ptr(exp), env._stream()),
+                           "pomdp_belief_hist")
+            assert torch.equal(out, exp), (name, n)
+            assert not scratch.any(), (name, n)
+            assert torch.equal(env.belief_histogram(state), exp), (name, n)
+        assert L.pomdp_belief_hist_once(env.kind, p0, p1, _lib.ptr(state), env.state_words, 5, None, _lib.ptr(out), None) == -1
+        assert L.pomdp_belief_hist_once(env.kind, p0, p1, _lib.ptr(state), env.state_words, 5, _lib.ptr(scratch), None, None) == -1
+
+
 def _fused_world_on_one_device(backend, env, state, world, calls, wait):
     """`world` ranks played on ONE device: each has its own symmetric buffer (slot 0 | slot 1 | arrivals) and scratch, all
     in one peer table.  wait=1 on CUDA: every rank's call goes to its own stream, so the kernels run concurrently and every
