@@ -1046,6 +1046,12 @@ pomdp_coord_kernel(int op, int xs, int ys, const int32_t* __restrict__ a, const 
 //    one shared-memory atomic per bin per warp) before a byte can overflow, normally once at the end;
 //  * categorical bins (Rock agent cell, Tag agent/opponent cell): plain shared-memory atomics (many addresses).
 // W = 1 and W = 2 states are read with 16-byte loads (four / two envs per thread per trip).
+#ifndef POMDP_HIST_INFLIGHT
+#define POMDP_HIST_INFLIGHT 4
+#endif
+#ifndef POMDP_HIST_PREFETCH
+#define POMDP_HIST_PREFETCH 0
+#endif
 template <int KIND> struct HistShape;                        // NW = packed counter words per thread (4 bins each)
 template <> struct HistShape<POMDP_KIND_ROCK> { static constexpr int NW = 4; };
 template <> struct HistShape<POMDP_KIND_TAG> { static constexpr int NW = 1; };
@@ -1136,7 +1142,7 @@ __device__ __forceinline__ void hist_add_plane(uint32_t x, uint32_t (&acc)[HistS
 }
 
 template <int KIND, bool CSA>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)      // one CTA per SM is all the host launches: no reason to squeeze into 32 registers
 pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
                          unsigned long long* __restrict__ hist, int bins,
                          unsigned long long* const* __restrict__ peers, int world, int rank, int wait,
@@ -1161,20 +1167,34 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
         const int64_t g_round = (n_groups + 31) & ~(int64_t)31;          // whole warps iterate together (flush shuffles)
         // kInFlight independent 16-byte loads per thread per trip: with one, a 1024-thread CTA per SM keeps only 16 KB in
         // flight and the kernel waits on DRAM latency (long-scoreboard stalls, 20-30 % of the HBM peak on a pure read)
-        constexpr int kInFlight = 4;
+        constexpr int kInFlight = POMDP_HIST_INFLIGHT;
+        // kPrefetch: the loads of a thread's NEXT trip are issued before the current trip is counted (software pipelining,
+        // as in the step kernels).  Measured with 2, 4 and 8 loads per trip, with and without (profiles/r05e_hist_loop_variants.log):
+        // nothing moves below 2^22 states -- there the kernel is a fixed ~4 us (launch, the REDs' round trip, the ticket and
+        // the last CTA's read-back) plus 0.7 us per 2^20 one-word states, i.e. the marginal rate is already the HBM rate --
+        // and at 2^25 four plain loads per trip are the fastest (49 us; 54-64 us for the others).
+        constexpr bool kPrefetch = POMDP_HIST_PREFETCH != 0;
         // CSA: chosen by the host only when a thread makes many trips (measured: 2^25 two-word states 57.0 -> 48.6 us, but
         // slower at 2^22 and below, where a thread makes two trips and the final planes cost more than they save)
-        constexpr bool kCsa = CSA && (KIND == POMDP_KIND_ROCK || KIND == POMDP_KIND_NETWORK);
+        constexpr bool kCsa = CSA && kInFlight == 4 && (KIND == POMDP_KIND_ROCK || KIND == POMDP_KIND_NETWORK);   // the tree below sums 16 words
         uint32_t ones = 0, twos = 0, fours = 0, eights = 0;              // running planes of the vertical sum (kCsa)
-        for (int64_t g0 = tid; g0 < g_round; g0 += kInFlight * nthreads) {
-            int4 v[kInFlight];
-            bool valid[kInFlight];
+        int4 v[kInFlight], nv[kInFlight];
+        bool valid[kInFlight], nvalid[kInFlight];
+        auto load_trip = [&](int64_t g0, int4 (&vv)[kInFlight], bool (&ok)[kInFlight]) {
 #pragma unroll
             for (int u = 0; u < kInFlight; ++u) {
                 const int64_t g = g0 + u * nthreads;
-                valid[u] = g < n_groups;
-                v[u] = make_int4(0, 0, 0, 0);
-                if (valid[u]) v[u] = ld_stream4(state + (g << 2));
+                ok[u] = g < n_groups;
+                vv[u] = make_int4(0, 0, 0, 0);
+                if (ok[u]) vv[u] = ld_stream4(state + (g << 2));
+            }
+        };
+        if (kPrefetch && tid < g_round) load_trip(tid, v, valid);
+        for (int64_t g0 = tid; g0 < g_round; g0 += kInFlight * nthreads) {
+            if (kPrefetch) {
+                if (g0 + kInFlight * nthreads < g_round) load_trip(g0 + kInFlight * nthreads, nv, nvalid);
+            } else {
+                load_trip(g0, v, valid);
             }
             if (kCsa) {
                 uint32_t w[4 * kInFlight];                               // an invalid group contributes zero words
@@ -1239,6 +1259,10 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
                     pending += 4;
                     if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
                 }
+            }
+            if (kPrefetch) {
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) { v[u] = nv[u]; valid[u] = nvalid[u]; }
             }
         }
         if (kCsa) {                                  // the carry-outs, then the running planes in ONE flush (a byte holds <= 15)
