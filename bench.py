@@ -655,6 +655,69 @@ def collective_row(gp, torch, dist, dev, rank, world):
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         fused_ok = bool(tmin[0].item() == 1.0)
         fused_us = fmax if tmin[1].item() == 1.0 else None
+    # Config 5's whole step -- transition of the shard, counts of the next states, sum over the ranks -- as separate
+    # launches and as ONE kernel (pomdp_rock_step_hist: the step kernel counts the next states in its epilogue and the
+    # all-reduce rides in the same launch over NVLink peer memory).  Graph-captured, median of 5 replays, max over ranks.
+    pipeline = None
+    try:
+        state2, _ = env.init_states(B, step_ctr=1)
+        action2 = env.sample_legal_actions(state2, step_ctr=2)
+        sout = (nxt, torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.float32, device=dev),
+                torch.empty(B, dtype=torch.int32, device=dev))
+        fused_mode = "fused" if (world > 1 and fused_err is None) else False
+
+        def separate(all_reduce):
+            env.simulate(state2, action2, out=sout, step_ctr=2)
+            return env.belief_histogram(sout[0], all_reduce=all_reduce)
+
+        def graph_us_of(fn, n_calls=10):
+            gs = torch.cuda.Stream(dev)
+            with torch.cuda.stream(gs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=gs):
+                    for _ in range(n_calls):
+                        fn()
+                g.replay()
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                ts = []
+                for _ in range(5):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(gs)
+                    g.replay()
+                    b.record(gs)
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) * 1e3 / n_calls)
+            tt = torch.tensor([sorted(ts)[2]], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            del g
+            return float(tt.item())
+
+        want = separate(world > 1)
+        got = env.simulate_hist(state2, action2, out=sout, step_ctr=2, all_reduce=fused_mode)[4]
+        pipe_ok = bool(torch.equal(got, want)) and bool(torch.equal(red, want))
+        pipeline = {"step_only_us": graph_us_of(lambda: env.simulate(state2, action2, out=sout, step_ctr=2))}
+        if world > 1:
+            pipeline["step_hist_allreduce_three_launches_us"] = graph_us_of(lambda: separate(True))
+            if fused_mode:
+                pipeline["step_fusedhist_two_launches_us"] = graph_us_of(lambda: separate("fused"))
+        else:
+            pipeline["step_hist_two_launches_us"] = graph_us_of(lambda: separate(False))
+        pipeline["step_hist%s_one_launch_us" % ("_allreduce" if fused_mode else "")] = graph_us_of(
+            lambda: env.simulate_hist(state2, action2, out=sout, step_ctr=2, all_reduce=fused_mode))
+        if world > 1:
+            tk = torch.tensor([1.0 if pipe_ok else 0.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(tk, op=dist.ReduceOp.MIN)
+            pipe_ok = bool(tk.item() == 1.0)
+        pipeline["equal_counts"] = pipe_ok
+        pipeline["what"] = ("simulate_hist = pomdp_rock_step_hist: the step kernel counts next_state in its epilogue (it is never "
+                            "read back from HBM) and hands the counts out -- with all_reduce='fused' summed over the ranks in the "
+                            "same launch; 10 calls per CUDA graph, median of 5 replays, max over ranks")
+        del state2, action2, sout
+    except Exception as e:  # noqa: BLE001
+        pipeline = {"error": repr(e)[:200]}
     del nxt, env
     torch.cuda.empty_cache()
     row = {"workload": "RockSample(15,15) global batch 2^25 over %d rank(s): belief histogram%s" % (
@@ -667,6 +730,7 @@ def collective_row(gp, torch, dist, dev, rank, world):
                                 "every rank's buffer over NVLink peer memory, signals its arrival to every peer, waits for "
                                 "theirs and writes the global counts out; no zero-fill, no NCCL call, no separate barrier"}
         row["graph_us"] = graph_us
+    row["step_pipeline"] = pipeline
     return row
 
 

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -58,8 +58,15 @@ class NetworkParams(ctypes.Structure):
                 ("p_ob", c_double)]
 
 
+class HistSink(ctypes.Structure):
+    """PomdpHistSink: where a step kernel with the histogram epilogue (pomdp_E_step_hist) hands its counts"""
+    _fields_ = [("scratch", c_void_p), ("d_peer_bufs", c_void_p), ("world", c_int32), ("rank", c_int32), ("wait", c_int32),
+                ("pad_", c_int32), ("hist_out", c_void_p)]
+
+
 _P = c_void_p  # device (or, under hostsim, host) array pointers travel as raw addresses
 _STEP_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
+_STEP_HIST_TAIL = [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, POINTER(HistSink), c_void_p]
 _RESET_TAIL = [_P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
 
 _POLICY_TAIL = [_P, _P, c_int64, c_int64, c_uint64, c_uint32, c_void_p]
@@ -136,6 +143,10 @@ _PROTOTYPES = {
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),
+    "pomdp_rock_step_hist": (c_int32, [POINTER(RockParams), _P] + _STEP_HIST_TAIL),
+    "pomdp_tag_step_hist": (c_int32, [POINTER(TagParams), _P] + _STEP_HIST_TAIL),
+    "pomdp_tiger_step_hist": (c_int32, [POINTER(TigerParams)] + _STEP_HIST_TAIL),
+    "pomdp_network_step_hist": (c_int32, [POINTER(NetworkParams)] + _STEP_HIST_TAIL),
     "pomdp_belief_hist_once": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, _P, c_void_p]),
     "pomdp_belief_hist_allreduce": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, _P, c_int32, c_int32, c_int32,
                                               _P, c_void_p]),

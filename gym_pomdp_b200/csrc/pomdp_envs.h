@@ -16,6 +16,8 @@ template <typename S, bool STOCH>
 struct RockEnvT {
     typedef RockDev Params;
     typedef S State;
+    static constexpr int kHistKind = 0;              // POMDP_KIND_ROCK: the belief-histogram bins of this env's states
+    static POMDP_HD int hist_p0(const Params& p) { return p.k; }
     static constexpr bool kTable = true;             // table built on the host, staged per CTA by one TMA bulk copy
     static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params& p, const unsigned char* tbl, S s, uint32_t w) {   // rock.py:273-291
@@ -83,6 +85,8 @@ template <int NOPP>
 struct TagEnvT {
     typedef TagDev Params;
     typedef uint32_t State;
+    static constexpr int kHistKind = 1;              // POMDP_KIND_TAG
+    static POMDP_HD int hist_p0(const Params&) { return 0; }
     static constexpr bool kTable = true;             // TagTables: built on the host, staged per CTA by one TMA bulk copy
     static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tag.py:228-229
@@ -187,6 +191,8 @@ struct TagNoTable {
 struct TigerEnvP {
     typedef TigerDev Params;
     typedef uint32_t State;
+    static constexpr int kHistKind = 3;              // POMDP_KIND_TIGER
+    static POMDP_HD int hist_p0(const Params&) { return 0; }
     static constexpr bool kTable = false;
     static constexpr bool kParamTable = false;
     static POMDP_HD int32_t policy(const Params&, const unsigned char*, State, uint32_t w) {       // tiger.py:111-112
@@ -231,6 +237,8 @@ template <int G>
 struct NetworkEnvT {
     typedef NetworkDev Params;
     typedef uint32_t State;
+    static constexpr int kHistKind = 4;              // POMDP_KIND_NETWORK
+    static POMDP_HD int hist_p0(const Params& p) { return p.n; }
     static constexpr bool kTable = false;
     // the step's tables (alias columns of the joint failure draw, neighbour-down map: 2.8 KB) travel inside the kernel
     // parameters and are copied to shared memory once per CTA by the kernels that step (step, rollout)

@@ -103,6 +103,7 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterp
 template <typename S> struct StateVec;
 template <> struct StateVec<uint32_t> {
     int4 v;
+    __device__ __forceinline__ void zero() { v = make_int4(0, 0, 0, 0); }
     __device__ __forceinline__ void load(const int32_t* base, int64_t i) { v = ld_stream4(base + i); }
     __device__ __forceinline__ void unpack(uint32_t s[4]) const {
         s[0] = (uint32_t)v.x; s[1] = (uint32_t)v.y; s[2] = (uint32_t)v.z; s[3] = (uint32_t)v.w;
@@ -120,6 +121,7 @@ __device__ __forceinline__ void st_stream_4x64(void* p, const uint64_t s[4]) {
 }
 template <> struct StateVec<uint64_t> {
     uint64_t v[4];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0; }
     __device__ __forceinline__ void load(const int32_t* base, int64_t i) {
         const int32_t* p = base + 2 * i;
         if ((reinterpret_cast<uintptr_t>(base) & 31) == 0) {      // uniform: the whole array is 32-byte aligned
@@ -1141,6 +1143,81 @@ __device__ __forceinline__ void hist_add_plane(uint32_t x, uint32_t (&acc)[HistS
     }
 }
 
+// The end of every kernel that counts a belief histogram (pomdp_belief_hist_kernel, pomdp_step_hist_kernel): the CTA's
+// counts are already added to `hist`; called by ALL threads of the CTA.
+// Fused all-reduce (pomdp_belief_hist_allreduce): `hist` is this rank's scratch -- hist[bins] a ticket counter,
+// hist[bins + 1] the number of calls made so far.  The CTA that takes the last ticket owns the rank's complete counts.
+// Call e (1, 2, ...) uses result slot (e - 1) & 1 of every rank's symmetric buffer [slot 0 | slot 1 | arrivals]:
+//   1. clear this rank's OTHER slot for call e + 1 (nobody adds into it before having seen this rank's arrival of
+//      call e, and its previous contents -- the result of call e - 1 -- were handed out by that call),
+//   2. add the counts into EVERY rank's slot through the peer mappings: system-scope reductions over NVLink/NVSwitch,
+//   3. announce the arrival in row [rank] of every peer's arrival counters (release, system scope: the reductions are
+//      ordered before it) and wait until all counters of this rank's own row block have reached e (acquire),
+//   4. copy the slot -- now the GLOBAL counts -- to hist_out.
+// One kernel instead of zero-fill + histogram + a collective; the epoch lives in device memory, so the launch is
+// identical call after call and can be replayed from a CUDA graph.
+__device__ __forceinline__ void hist_finish(unsigned long long* __restrict__ hist, int bins,
+                                            unsigned long long* const* __restrict__ peers, int world, int rank, int wait,
+                                            unsigned long long* __restrict__ hist_out) {
+    // Self-cleaning local call (pomdp_belief_hist_once: no peers): the same ticket; the last CTA MOVES the counts from the
+    // scratch to hist_out -- no zero-fill launch before the kernel, the scratch is all zero again after it.
+    if (peers || hist_out) {
+        __shared__ bool last;
+        __shared__ unsigned long long epoch_s;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last = atomicAdd(&hist[bins], 1ull) == (unsigned long long)gridDim.x - 1ull;
+            epoch_s = hist[bins + 1] + 1ull;
+        }
+        __syncthreads();
+        if (last && !peers) {
+            __threadfence();
+            for (int b = threadIdx.x; b < bins; b += blockDim.x) hist_out[b] = atomicExch(&hist[b], 0ull);
+            if (threadIdx.x == 0) hist[bins] = 0ull;
+        } else if (last) {
+            __threadfence();
+            const unsigned long long epoch = epoch_s;
+            const int64_t slot_off = (int64_t)((epoch - 1ull) & 1ull) * POMDP_HIST_MAX_BINS * 8;
+            const int64_t other_off = POMDP_HIST_MAX_BINS * 8 - slot_off;
+            const int64_t signal_off = 2 * POMDP_HIST_MAX_BINS * 8;
+            char* own = reinterpret_cast<char*>(peers[rank]);
+            for (int b = threadIdx.x; b < POMDP_HIST_MAX_BINS; b += blockDim.x)
+                reinterpret_cast<unsigned long long*>(own + other_off)[b] = 0ull;
+            for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+                const unsigned long long v = atomicExch(&hist[b], 0ull);
+                if (v)
+                    for (int r = 0; r < world; ++r)
+                        atomicAdd_system(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + slot_off) + b, v);
+            }
+            if (wait) {
+                __threadfence_system();
+                __syncthreads();
+                if ((int)threadIdx.x < world) {
+                    const int r = (int)threadIdx.x;
+                    unsigned long long* there = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + signal_off) + rank;
+                    const unsigned long long* here = reinterpret_cast<const unsigned long long*>(own + signal_off) + r;
+                    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(there), "l"(1ull) : "memory");
+                    unsigned long long seen = 0, t0, t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(here) : "memory");
+                        if (seen >= epoch) break;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 10000000000ull) __trap();            // a peer never made the call: fail, do not hang
+                    }
+                }
+                __syncthreads();
+            }
+            if (hist_out)
+                for (int b = threadIdx.x; b < bins; b += blockDim.x)
+                    hist_out[b] = __ldcv(reinterpret_cast<const unsigned long long*>(own + slot_off) + b);
+            __syncthreads();
+            if (threadIdx.x == 0) { hist[bins] = 0ull; hist[bins + 1] = epoch; }
+        }
+    }
+}
+
 template <int KIND, bool CSA>
 __global__ void __launch_bounds__(1024, 1)      // one CTA per SM is all the host launches: no reason to squeeze into 32 registers
 pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int words, int64_t n,
@@ -1312,74 +1389,135 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
         if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
     (void)p1;
-    // Fused all-reduce (pomdp_belief_hist_allreduce): `hist` is this rank's scratch -- hist[bins] a ticket counter,
-    // hist[bins + 1] the number of calls made so far.  The CTA that takes the last ticket owns the rank's complete counts.
-    // Call e (1, 2, ...) uses result slot (e - 1) & 1 of every rank's symmetric buffer [slot 0 | slot 1 | arrivals]:
-    //   1. clear this rank's OTHER slot for call e + 1 (nobody adds into it before having seen this rank's arrival of
-    //      call e, and its previous contents -- the result of call e - 1 -- were handed out by that call),
-    //   2. add the counts into EVERY rank's slot through the peer mappings: system-scope reductions over NVLink/NVSwitch,
-    //   3. announce the arrival in row [rank] of every peer's arrival counters (release, system scope: the reductions are
-    //      ordered before it) and wait until all counters of this rank's own row block have reached e (acquire),
-    //   4. copy the slot -- now the GLOBAL counts -- to hist_out.
-    // One kernel instead of zero-fill + histogram + a collective; the epoch lives in device memory, so the launch is
-    // identical call after call and can be replayed from a CUDA graph.
-    // Self-cleaning local call (pomdp_belief_hist_once: no peers): the same ticket; the last CTA MOVES the counts from the
-    // scratch to hist_out -- no zero-fill launch before the kernel, the scratch is all zero again after it.
-    if (peers || hist_out) {
-        __shared__ bool last;
-        __shared__ unsigned long long epoch_s;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            last = atomicAdd(&hist[bins], 1ull) == (unsigned long long)gridDim.x - 1ull;
-            epoch_s = hist[bins + 1] + 1ull;
+    hist_finish(hist, bins, peers, world, rank, wait, hist_out);
+}
+
+
+// ------------------------------------------------- step with the belief histogram in its epilogue ---
+// the counts of the NEXT states are accumulated by the step kernel itself -- the states are in registers
+// when they are counted, so the particle set is never read back from HBM by a second kernel -- and the all-reduce of the
+// counts can ride in the same launch (hist_finish: local move to hist_out, or the additions into every rank's buffer over
+// NVLink peer memory).  Same loads, stores, draws and transition as pomdp_step_kernel; the loop runs whole warps
+// together (an out-of-range lane idles) because the flush of the packed byte counters is a warp-wide reduction.
+__device__ __forceinline__ void state_hist_words(uint32_t s, uint32_t w[4]) { w[0] = s; w[1] = 0u; w[2] = 0u; w[3] = 0u; }
+__device__ __forceinline__ void state_hist_words(uint64_t s, uint32_t w[4]) { w[0] = (uint32_t)s; w[1] = (uint32_t)(s >> 32); w[2] = 0u; w[3] = 0u; }
+
+template <class Env, bool kVec>
+__global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
+pomdp_step_hist_kernel(const __grid_constant__ typename Env::Params p, const void* __restrict__ g_table,
+                       const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
+                       int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n,
+                       uint64_t goff, const __grid_constant__ PhiloxKey seed, uint32_t step_ctr, uint32_t table_bytes,
+                       unsigned long long* __restrict__ hist, int bins, unsigned long long* const* __restrict__ peers,
+                       int world, int rank, int wait, unsigned long long* __restrict__ hist_out) {
+    typedef typename Env::State S;
+    constexpr int KIND = Env::kHistKind;
+    constexpr int NW = HistShape<KIND>::NW;
+    extern __shared__ __align__(128) unsigned char smem_table[];
+    __shared__ alignas(8) uint64_t bar;
+    __shared__ uint32_t sh[POMDP_HIST_MAX_BINS];
+    const unsigned char* lut = smem_table;
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0;
+    if (Env::kTable && threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bar, table_bytes);
+        tma_bulk_g2s(smem_table, g_table, table_bytes, &bar);
+    }
+    __syncthreads();           // barrier object initialised and counters cleared before anyone touches them
+    stage_param_table<Env>(smem_table, p);
+
+    pdl_wait();
+    pdl_launch_dependents();
+    const int hp0 = Env::hist_p0(p);
+    const int n_bits = KIND == POMDP_KIND_TAG ? 0 : KIND == POMDP_KIND_TIGER ? 2 : hp0;
+    const int lane = threadIdx.x & 31;
+    uint32_t acc[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) acc[j] = 0;
+    int pending = 0;                                         // particles counted since the last flush (warp-uniform)
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    bool table_ready = !Env::kTable;
+    if (kVec) {
+        const int64_t n_groups = n >> 2;
+        const int64_t g_round = (n_groups + 31) & ~(int64_t)31;
+        const uint64_t group0 = goff >> 2;
+        int64_t g = tid;
+        StateVec<S> cur_s;
+        cur_s.zero();
+        int4 cur_a = make_int4(0, 0, 0, 0);
+        if (g < n_groups) {
+            cur_s.load(state, g << 2);
+            cur_a = ld_stream4(action + (g << 2));
         }
-        __syncthreads();
-        if (last && !peers) {
-            __threadfence();
-            for (int b = threadIdx.x; b < bins; b += blockDim.x) hist_out[b] = atomicExch(&hist[b], 0ull);
-            if (threadIdx.x == 0) hist[bins] = 0ull;
-        } else if (last) {
-            __threadfence();
-            const unsigned long long epoch = epoch_s;
-            const int64_t slot_off = (int64_t)((epoch - 1ull) & 1ull) * POMDP_HIST_MAX_BINS * 8;
-            const int64_t other_off = POMDP_HIST_MAX_BINS * 8 - slot_off;
-            const int64_t signal_off = 2 * POMDP_HIST_MAX_BINS * 8;
-            char* own = reinterpret_cast<char*>(peers[rank]);
-            for (int b = threadIdx.x; b < POMDP_HIST_MAX_BINS; b += blockDim.x)
-                reinterpret_cast<unsigned long long*>(own + other_off)[b] = 0ull;
-            for (int b = threadIdx.x; b < bins; b += blockDim.x) {
-                const unsigned long long v = atomicExch(&hist[b], 0ull);
-                if (v)
-                    for (int r = 0; r < world; ++r)
-                        atomicAdd_system(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + slot_off) + b, v);
+        if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
+        while (g < g_round) {
+            const int64_t gn = g + nthreads;
+            StateVec<S> nxt_s = cur_s;
+            int4 nxt_a = cur_a;
+            if (gn < n_groups) {
+                nxt_s.load(state, gn << 2);
+                nxt_a = ld_stream4(action + (gn << 2));
             }
-            if (wait) {
-                __threadfence_system();
-                __syncthreads();
-                if ((int)threadIdx.x < world) {
-                    const int r = (int)threadIdx.x;
-                    unsigned long long* there = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[r]) + signal_off) + rank;
-                    const unsigned long long* here = reinterpret_cast<const unsigned long long*>(own + signal_off) + r;
-                    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(there), "l"(1ull) : "memory");
-                    unsigned long long seen = 0, t0, t1;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                    for (;;) {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(here) : "memory");
-                        if (seen >= epoch) break;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 10000000000ull) __trap();            // a peer never made the call: fail, do not hang
-                    }
+            if (g < n_groups) {
+                const int64_t i = g << 2;
+                S s[4], s2[4];
+                cur_s.unpack(s);
+                const int32_t a[4] = {cur_a.x, cur_a.y, cur_a.z, cur_a.w};
+                int32_t ob[4], fl[4];
+                float rw[4];
+                Env::step4(p, lut, s, a, seed, group0 + (uint64_t)g, step_ctr, s2, ob, rw, fl);
+                StateVec<S>::store(next_state, i, s2);
+                st_stream4(obs + i, make_int4(ob[0], ob[1], ob[2], ob[3]));
+                st_stream4(reward + i, make_float4(rw[0], rw[1], rw[2], rw[3]));
+                st_stream4(flags + i, make_int4(fl[0], fl[1], fl[2], fl[3]));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+                    state_hist_words(s2[j], w);
+                    hist_one<KIND>(hp0, true, w, sh, acc);
                 }
-                __syncthreads();
             }
-            if (hist_out)
-                for (int b = threadIdx.x; b < bins; b += blockDim.x)
-                    hist_out[b] = __ldcv(reinterpret_cast<const unsigned long long*>(own + slot_off) + b);
-            __syncthreads();
-            if (threadIdx.x == 0) { hist[bins] = 0ull; hist[bins + 1] = epoch; }
+            pending += 4;
+            if (pending > 251) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
+            cur_s = nxt_s;
+            cur_a = nxt_a;
+            g = gn;
+        }
+        const int64_t i = (n_groups << 2) + tid;             // tail (n % 4 envs): the first few threads of the grid
+        if (i < n) {
+            S s2; int32_t ob, fl; float rw;
+            Env::step1(p, lut, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+            store_state1(next_state, i, s2);
+            obs[i] = ob; reward[i] = rw; flags[i] = fl;
+            uint32_t w[4];
+            state_hist_words(s2, w);
+            hist_one<KIND>(hp0, true, w, sh, acc);
+        }
+    } else {
+        const int64_t r_round = (n + 31) & ~(int64_t)31;
+        for (int64_t i = tid; i < r_round; i += nthreads) {
+            if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }
+            if (i < n) {
+                S s2; int32_t ob, fl; float rw;
+                Env::step1(p, lut, load_state1(state, i, S()), action[i], seed, goff + (uint64_t)i, step_ctr, s2, ob, rw, fl);
+                store_state1(next_state, i, s2);
+                obs[i] = ob; reward[i] = rw; flags[i] = fl;
+                uint32_t w[4];
+                state_hist_words(s2, w);
+                hist_one<KIND>(hp0, true, w, sh, acc);
+            }
+            if (++pending > 254) { hist_flush<NW>(acc, sh, n_bits, lane); pending = 0; }
         }
     }
+    __syncwarp();
+    hist_flush<NW>(acc, sh, n_bits, lane);
+    if (!table_ready) mbar_wait(&bar, 0);      // a CTA must not exit while its bulk copy may still be in flight
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+    hist_finish(hist, bins, peers, world, rank, wait, hist_out);
 }
 
 // ============================================================================ host ===
@@ -1494,6 +1632,52 @@ int launch_step(const typename Env::Params& p, const void* d_table, uint32_t tab
         const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
         launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
                    (uint64_t)goff, key, step_ctr, table_bytes);
+    }
+    return finish(what);
+}
+
+// pomdp_E_step_hist: the step with the belief histogram of the next states in its epilogue (pomdp_step_hist_kernel)
+template <class Env>
+int launch_step_hist(const typename Env::Params& p, const void* d_table, uint32_t table_bytes, uint32_t smem_bytes,
+                     const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* obs, float* reward,
+                     int32_t* flags, int64_t n, int64_t goff, uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink,
+                     void* stream, const char* what) {
+    int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
+    if (rc) return rc;
+    if (goff < 0) return host::fail(POMDP_E_BADARG, "%s: global_offset is negative", what);
+    if (!sink || !sink->scratch || ((uintptr_t)sink->scratch & 7) || ((uintptr_t)sink->hist_out & 7))
+        return host::fail(POMDP_E_BADARG, "%s: the histogram sink needs an 8-byte aligned scratch (and hist_out)", what);
+    if (sink->d_peer_bufs) {
+        if (sink->world < 1 || sink->world > POMDP_HIST_MAX_RANKS || sink->rank < 0 || sink->rank >= sink->world)
+            return host::fail(POMDP_E_BADARG, "%s: bad world size or rank in the histogram sink", what);
+    } else if (!sink->hist_out) {
+        return host::fail(POMDP_E_BADARG, "%s: a local histogram sink (no peer table) needs hist_out", what);
+    }
+    if (Env::kTable && (!d_table || ((uintptr_t)d_table & 15)))
+        return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
+    const int bins = host::hist_bins(Env::kHistKind, Env::hist_p0(p), 0);
+    if (bins <= 0 || bins > POMDP_HIST_MAX_BINS) return host::fail(POMDP_E_BADARG, "%s: bad histogram shape", what);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = Env::kTable ? smem_bytes : param_table_smem<Env>();
+    const PhiloxKey key = philox_key(seed);
+    unsigned long long* scratch = (unsigned long long*)sink->scratch;
+    unsigned long long* const* peers = (unsigned long long* const*)sink->d_peer_bufs;
+    unsigned long long* out = (unsigned long long*)sink->hist_out;
+    // n == 0 still launches: an empty shard hands out zeros / must not leave its peers waiting
+    if (n == 0 || (aligned16(state, action, next_state, obs, reward, flags) && (goff & 3) == 0)) {
+        auto k = pomdp_step_hist_kernel<Env, true>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        const int grid = grid_for(k, (n + 3) >> 2, POMDP_STEP_THREADS, smem);
+        launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
+                   (uint64_t)goff, key, step_ctr, table_bytes, scratch, bins, peers, (int)sink->world, (int)sink->rank,
+                   (int)(sink->wait != 0), out);
+    } else {
+        auto k = pomdp_step_hist_kernel<Env, false>;
+        if ((rc = allow_smem(k, smem))) return rc;
+        const int grid = grid_for(k, n, POMDP_STEP_THREADS, smem);
+        launch_pdl(k, grid, POMDP_STEP_THREADS, smem, st, p, d_table, state, action, next_state, obs, reward, flags, n,
+                   (uint64_t)goff, key, step_ctr, table_bytes, scratch, bins, peers, (int)sink->world, (int)sink->rank,
+                   (int)(sink->wait != 0), out);
     }
     return finish(what);
 }
@@ -2474,6 +2658,59 @@ int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int3
                                                (unsigned long long* const*)d_peer_bufs, world, rank, wait != 0,
                                                (unsigned long long*)hist_out);
     return finish("pomdp_belief_hist_allreduce");
+}
+
+// ---- step + belief histogram of the next states in ONE kernel (include/pomdp_b200.h)
+int pomdp_rock_step_hist(const PomdpRockParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                         int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
+                         uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream) {
+    RockDev d;
+    int rc = host::make_rock(q, &d, nullptr);
+    if (rc) return rc;
+#define POMDP_ROCK_STEP_HIST(S, STOCH)                                                                                \
+    return launch_step_hist<RockEnvT<S, STOCH>>(d, d_table, d.table_bytes, d.smem_bytes, state, action, next_state,   \
+                                                obs, reward, flags, n, goff, seed, step_ctr, sink, stream, "pomdp_rock_step_hist")
+    if (host::rock_words(q) == 1) {
+        if (d.stochastic) POMDP_ROCK_STEP_HIST(uint32_t, true);
+        POMDP_ROCK_STEP_HIST(uint32_t, false);
+    }
+    if (d.stochastic) POMDP_ROCK_STEP_HIST(uint64_t, true);
+    POMDP_ROCK_STEP_HIST(uint64_t, false);
+#undef POMDP_ROCK_STEP_HIST
+}
+int pomdp_tag_step_hist(const PomdpTagParams* q, const void* d_table, const int32_t* state, const int32_t* action,
+                        int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff,
+                        uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream) {
+    TagDev d;
+    int rc = host::make_tag(q, &d);
+    if (rc) return rc;
+    const uint32_t tb = (uint32_t)sizeof(TagTables), tbs = TAG_TABLES_BASE_BYTES;
+    if (d.n_opp == 1)
+        return launch_step_hist<TagEnvT<1>>(d, d_table, tb, tb, state, action, next_state, obs, reward, flags, n, goff, seed,
+                                            step_ctr, sink, stream, "pomdp_tag_step_hist");
+    return launch_step_hist<TagEnvT<4>>(d, d_table, tbs, tbs, state, action, next_state, obs, reward, flags, n, goff, seed,
+                                        step_ctr, sink, stream, "pomdp_tag_step_hist");
+}
+int pomdp_tiger_step_hist(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                          int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                          uint32_t step_ctr, const PomdpHistSink* sink, void* stream) {
+    TigerDev d;
+    int rc = host::make_tiger(q, &d);
+    if (rc) return rc;
+    return launch_step_hist<TigerEnvP>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                       sink, stream, "pomdp_tiger_step_hist");
+}
+int pomdp_network_step_hist(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next_state,
+                            int32_t* obs, float* reward, int32_t* flags, int64_t n, int64_t goff, uint64_t seed,
+                            uint32_t step_ctr, const PomdpHistSink* sink, void* stream) {
+    NetworkDev d;
+    int rc = host::make_network(q, &d);
+    if (rc) return rc;
+    if (d.groups == 2)
+        return launch_step_hist<NetworkEnv10>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed,
+                                              step_ctr, sink, stream, "pomdp_network_step_hist");
+    return launch_step_hist<NetworkEnvP>(d, nullptr, 0, 0, state, action, next_state, obs, reward, flags, n, goff, seed, step_ctr,
+                                         sink, stream, "pomdp_network_step_hist");
 }
 
 }  // extern "C"

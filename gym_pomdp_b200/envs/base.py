@@ -225,6 +225,51 @@ class BatchedPomdpEnv(_EnvBase):
             self._c_step(state, action, next_state, obs, reward, flags, n, ctr)
         return next_state, obs, reward, flags
 
+    def simulate_hist(self, state, action, out=None, step_ctr=None, all_reduce=False, hist_out=None):
+        """``simulate`` and ``belief_histogram(next_state)`` in ONE kernel (``pomdp_E_step_hist``): the next states are
+        counted while they are still in registers, so the particle set is not read back from HBM by a second kernel
+        ("accumulated in the step kernel epilogue").  ``all_reduce`` as in ``belief_histogram``: False
+        -- this shard's counts; True -- summed over the ranks by NCCL afterwards; ``"fused"`` -- summed INSIDE the same
+        launch over NVLink / NVSwitch peer memory (step + histogram + all-reduce: one kernel, replayable from a CUDA
+        graph).  Returns (next_state, obs, reward, flags, counts).  BattleShip's step kernel (TMA board tiles) has no
+        histogram epilogue: there the two kernels run back to back."""
+        n = action.shape[0]
+        if out is None:
+            out = (torch.empty_like(state), self._empty((n,), torch.int32), self._empty((n,), torch.float32),
+                   self._empty((n,), torch.int32))
+        next_state, obs, reward, flags = out
+        if not hasattr(self, "_c_step_hist"):
+            self.simulate(state, action, out=out, step_ctr=step_ctr)
+            return next_state, obs, reward, flags, self.belief_histogram(next_state, all_reduce=all_reduce)
+        p0, p1 = self._hist_args()
+        bins = _lib.lib().pomdp_belief_hist_bins(self.kind, p0, p1)
+        hist = self._empty((bins,), torch.int64) if hist_out is None else hist_out
+        sink = _lib.HistSink()
+        sink.hist_out = _lib.ptr(hist)
+        if all_reduce == "fused":
+            st = self._fused_hist_state()
+            sink.scratch, sink.d_peer_bufs = _lib.ptr(st["scratch"]), st["hdl"].buffer_ptrs_dev
+            sink.world, sink.rank, sink.wait = st["hdl"].world_size, st["hdl"].rank, 1
+        else:
+            sink.scratch = _lib.ptr(self._local_hist_scratch())
+        ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
+        with self._guard():
+            self._c_step_hist(state, action, next_state, obs, reward, flags, n, ctr, sink)
+        if all_reduce is True:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        return next_state, obs, reward, flags, hist
+
+    def _local_hist_scratch(self):
+        """The self-cleaning scratch of the one-launch histogram calls, one per stream (calls on one stream are ordered)."""
+        stream = self._stream()
+        scratches = self.__dict__.setdefault("_hist_scratch", {})
+        scratch = scratches.get(stream)
+        if scratch is None:
+            scratch = scratches[stream] = torch.zeros(self._FUSED_HIST_BINS + 2, dtype=torch.int64, device=self.device)
+        return scratch
+
     def init_states(self, n=None, out=None, mask=None, step_ctr=None):
         """Batched ``_get_init_state``: fresh initial states (and the reset observation)."""
         n = self.batch_size if n is None else int(n)
@@ -567,16 +612,12 @@ class BatchedPomdpEnv(_EnvBase):
         bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
         # ONE launch (pomdp_belief_hist_once): the kernel's last CTA moves the counts from a self-cleaning scratch to the
         # result, so no zero-fill kernel runs before it.  One scratch per stream: calls on one stream are ordered.
-        stream = self._stream()
-        scratches = self.__dict__.setdefault("_hist_scratch", {})
-        scratch = scratches.get(stream)
-        if scratch is None:
-            scratch = scratches[stream] = torch.zeros(self._FUSED_HIST_BINS + 2, dtype=torch.int64, device=self.device)
+        scratch = self._local_hist_scratch()
         hist = torch.empty(bins, dtype=torch.int64, device=self.device)
         n = state.shape[0]
         with self._guard():
             _lib.check(L.pomdp_belief_hist_once(self.kind, p0, p1, _lib.ptr(state), self.state_words, n, _lib.ptr(scratch),
-                                                _lib.ptr(hist), stream), "pomdp_belief_hist_once")
+                                                _lib.ptr(hist), self._stream()), "pomdp_belief_hist_once")
         if all_reduce:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():

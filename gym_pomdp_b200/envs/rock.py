@@ -157,6 +157,12 @@ class RockEnv(BatchedPomdpEnv):
 
     _c_query_head = _c_head
 
+    def _c_step_hist(self, state, action, next_state, obs, reward, flags, n, ctr, sink):
+        _lib.check(_lib.lib().pomdp_rock_step_hist(
+            ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state),
+            _lib.ptr(obs), _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, ctypes.byref(sink),
+            self._stream()), "pomdp_rock_step_hist")
+
     def _c_step(self, state, action, next_state, obs, reward, flags, n, ctr):
         _lib.check(_lib.lib().pomdp_rock_step(
             ctypes.byref(self._params), _lib.ptr(self._table), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state),

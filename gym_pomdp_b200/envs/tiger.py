@@ -38,6 +38,12 @@ class TigerEnv(BatchedPomdpEnv):
             _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, self._stream()),
             "pomdp_tiger_step")
 
+    def _c_step_hist(self, state, action, next_state, obs, reward, flags, n, ctr, sink):
+        _lib.check(_lib.lib().pomdp_tiger_step_hist(
+            ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(action), _lib.ptr(next_state), _lib.ptr(obs),
+            _lib.ptr(reward), _lib.ptr(flags), n, self.global_offset, self._seed, ctr, ctypes.byref(sink), self._stream()),
+            "pomdp_tiger_step_hist")
+
     def _c_reset(self, state, obs, mask, n, ctr):
         _lib.check(_lib.lib().pomdp_tiger_reset(
             ctypes.byref(self._params), _lib.ptr(state), _lib.ptr(obs), _lib.ptr(mask), n, self.global_offset,

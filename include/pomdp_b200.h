@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 12
+#define POMDP_ABI_VERSION 13
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -559,6 +559,34 @@ int pomdp_belief_hist_once(int32_t kind, int32_t p0, int32_t p1, const int32_t* 
 int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
                                 int64_t n, long long* scratch, const void* const* d_peer_bufs,
                                 int32_t world, int32_t rank, int32_t wait, long long* hist_out, void* stream);
+
+/* The step with the belief histogram of the NEXT states in its epilogue: ONE kernel does
+ * pomdp_E_step (same arrays, draws and results) and counts next_state while it is still in registers -- the particle
+ * set is not read back from HBM by a second kernel -- and hands the counts to the sink:
+ *   d_peer_bufs == NULL : local.  `scratch` as for pomdp_belief_hist_once; hist_out[bins] is overwritten.
+ *   d_peer_bufs != NULL : the all-reduce rides in the same launch, exactly as in pomdp_belief_hist_allreduce
+ *                         (same scratch, peer table, world, rank, wait, hist_out -- may be NULL -- and call discipline).
+ * n = 0 still launches (zeros / the peers are not left waiting).  BattleShip has no such variant (its step kernel moves
+ * whole boards with TMA tiles; call pomdp_belief_hist_once after pomdp_battleship_step).                              */
+typedef struct {
+    long long*         scratch;       /* int64[POMDP_HIST_MAX_BINS + 2], zero before the first call                */
+    const void* const* d_peer_bufs;   /* device table of `world` symmetric buffers, or NULL                        */
+    int32_t            world, rank, wait;
+    int32_t            pad_;
+    long long*         hist_out;      /* int64[bins] or NULL (peers only)                                          */
+} PomdpHistSink;
+int pomdp_rock_step_hist(const PomdpRockParams* params, const void* d_table, const int32_t* state, const int32_t* action,
+                         int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
+                         int64_t global_offset, uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream);
+int pomdp_tag_step_hist(const PomdpTagParams* params, const void* d_table, const int32_t* state, const int32_t* action,
+                        int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
+                        int64_t global_offset, uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream);
+int pomdp_tiger_step_hist(const PomdpTigerParams* params, const int32_t* state, const int32_t* action,
+                          int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
+                          int64_t global_offset, uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream);
+int pomdp_network_step_hist(const PomdpNetworkParams* params, const int32_t* state, const int32_t* action,
+                            int32_t* next_state, int32_t* obs, float* reward, int32_t* flags, int64_t n,
+                            int64_t global_offset, uint64_t seed, uint32_t step_ctr, const PomdpHistSink* sink, void* stream);
 
 #ifdef __cplusplus
 }

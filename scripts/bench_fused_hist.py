@@ -5,6 +5,8 @@
   nccl        histogram kernel (self-cleaning) + ncclAllReduce         belief_histogram(all_reduce=True)
   fused       ONE kernel: histogram + reductions into every rank's buffer over NVLink peer memory + arrive/wait,
               then the copy that hands the counts out               belief_histogram(all_reduce="fused")
+and the whole step of config 5 -- transition, counts of the next states, sum over the ranks -- as three launches
+(step, histogram, ncclAllReduce), two (step, fused histogram) and ONE (simulate_hist(all_reduce="fused"): pomdp_rock_step_hist).
     torchrun --nproc-per-node N scripts/bench_fused_hist.py [--out file.json]"""
 import argparse
 import json
@@ -38,9 +40,29 @@ fused = env.belief_histogram(state, all_reduce="fused")
 ok = bool(torch.equal(ref, fused)) and int(ref[15:].sum()) == G
 variants = {"hist": lambda: env.belief_histogram(state), "nccl": lambda: env.belief_histogram(state, all_reduce=True),
             "fused": lambda: env.belief_histogram(state, all_reduce="fused")}
+# the whole config-5 step: transition of the shard, counts of the next states, sum over the ranks
+action = torch.randint(0, 20, (B,), device=dev, dtype=torch.int32)
+sout = (torch.empty_like(state), torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.float32, device=dev),
+        torch.empty(B, dtype=torch.int32, device=dev))
+
+
+def step_then(all_reduce):
+    env.simulate(state, action, out=sout, step_ctr=7)
+    return env.belief_histogram(sout[0], all_reduce=all_reduce)
+
+
+step_ref = step_then(True)
+ok = ok and bool(torch.equal(step_then("fused"), step_ref)) and int(step_ref[15:].sum()) == G
+ok = ok and bool(torch.equal(env.simulate_hist(state, action, out=sout, step_ctr=7, all_reduce="fused")[4], step_ref))
+ok = ok and bool(torch.equal(env.simulate_hist(state, action, out=sout, step_ctr=7, all_reduce=True)[4], step_ref))
+step_variants = {"step": lambda: env.simulate(state, action, out=sout, step_ctr=7)[0],
+                 "step_then_hist_nccl": lambda: step_then(True),                   # three launches: step, histogram, ncclAllReduce
+                 "step_then_hist_fused": lambda: step_then("fused"),               # two: step, histogram + all-reduce
+                 "step_hist_local": lambda: env.simulate_hist(state, action, out=sout, step_ctr=7)[4],      # one, no collective
+                 "step_hist_fused": lambda: env.simulate_hist(state, action, out=sout, step_ctr=7, all_reduce="fused")[4]}   # ONE
 REPS = 20
 res = {}
-for name, fn in variants.items():
+for name, fn in list(variants.items()) + list(step_variants.items()):
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
@@ -71,8 +93,10 @@ for name, fn in variants.items():
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b) * 1e3 / REPS)
         row["graph_us"] = sorted(times)[len(times) // 2]
-        if name != "hist":
+        if name in ("nccl", "fused"):
             ok = ok and bool(torch.equal(out, ref))
+        elif name in ("step_then_hist_nccl", "step_then_hist_fused", "step_hist_fused"):
+            ok = ok and bool(torch.equal(out, step_ref))
     except Exception as e:  # noqa: BLE001
         row["graph_error"] = repr(e)[:160]
     t = torch.tensor([row["eager_us"], row.get("graph_us", -1.0)], device=dev, dtype=torch.float64)
@@ -85,7 +109,9 @@ flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     out = {"workload": "RockSample(15,15) belief histogram, global batch 2^%d over %d rank(s)" % (args.log2_global, world),
-           "batch_per_gpu": B, "bins": int(ref.numel()), "all_variants_equal": bool(flag.item() == 1.0), "us_per_call_max_over_ranks": res}
+           "batch_per_gpu": B, "bins": int(ref.numel()), "all_variants_equal": bool(flag.item() == 1.0),
+           "us_per_call_max_over_ranks": {k: v for k, v in res.items() if k in variants},
+           "step_pipeline_us_max_over_ranks": {k: v for k, v in res.items() if k in step_variants}}
     print(json.dumps(out))
     if args.out:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)

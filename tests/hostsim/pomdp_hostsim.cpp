@@ -923,6 +923,45 @@ int pomdp_belief_hist_allreduce(int32_t kind, int32_t p0, int32_t p1, const int3
     return 0;
 }
 
+// host stand-ins of the step kernels with the histogram epilogue: the step, then the counts of next_state through the sink
+static int hist_sink_host(int kind, int p0, int p1, const int32_t* next, int words, int64_t n, const PomdpHistSink* sink, const char* what) {
+    if (!sink || !sink->scratch || ((uintptr_t)sink->scratch & 7) || ((uintptr_t)sink->hist_out & 7))
+        return host::fail(POMDP_E_BADARG, "%s: the histogram sink needs an 8-byte aligned scratch (and hist_out)", what);
+    if (sink->d_peer_bufs)
+        return pomdp_belief_hist_allreduce(kind, p0, p1, next, words, n, sink->scratch, sink->d_peer_bufs, sink->world, sink->rank,
+                                           sink->wait, sink->hist_out, nullptr);
+    if (!sink->hist_out) return host::fail(POMDP_E_BADARG, "%s: a local histogram sink (no peer table) needs hist_out", what);
+    return pomdp_belief_hist_once(kind, p0, p1, next, words, n, sink->scratch, sink->hist_out, nullptr);
+}
+int pomdp_rock_step_hist(const PomdpRockParams* q, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
+                         int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                         const PomdpHistSink* sink, void*) {
+    int rc = pomdp_rock_step(q, table, state, action, next, obs, rw, fl, n, goff, seed, step, nullptr);
+    if (rc) return rc;
+    return hist_sink_host(POMDP_KIND_ROCK, q->num_rocks, host::rock_words(q), next, host::rock_words(q), n, sink, "pomdp_rock_step_hist");
+}
+int pomdp_tag_step_hist(const PomdpTagParams* q, const void* table, const int32_t* state, const int32_t* action, int32_t* next,
+                        int32_t* obs, float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step,
+                        const PomdpHistSink* sink, void*) {
+    int rc = pomdp_tag_step(q, table, state, action, next, obs, rw, fl, n, goff, seed, step, nullptr);
+    if (rc) return rc;
+    return hist_sink_host(POMDP_KIND_TAG, 0, 0, next, 1, n, sink, "pomdp_tag_step_hist");
+}
+int pomdp_tiger_step_hist(const PomdpTigerParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
+                          float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, const PomdpHistSink* sink,
+                          void*) {
+    int rc = pomdp_tiger_step(q, state, action, next, obs, rw, fl, n, goff, seed, step, nullptr);
+    if (rc) return rc;
+    return hist_sink_host(POMDP_KIND_TIGER, 0, 0, next, 1, n, sink, "pomdp_tiger_step_hist");
+}
+int pomdp_network_step_hist(const PomdpNetworkParams* q, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs,
+                            float* rw, int32_t* fl, int64_t n, int64_t goff, uint64_t seed, uint32_t step, const PomdpHistSink* sink,
+                            void*) {
+    int rc = pomdp_network_step(q, state, action, next, obs, rw, fl, n, goff, seed, step, nullptr);
+    if (rc) return rc;
+    return hist_sink_host(POMDP_KIND_NETWORK, q->n_machines, 0, next, 1, n, sink, "pomdp_network_step_hist");
+}
+
 // test-only: the division-free float32 reward conversion of network_step_n, for the exhaustive check in
 // tests/test_edge_cases.py
 void pomdp_hostsim_tenths_to_float(const int32_t* t, float* out, int64_t n) {

@@ -313,6 +313,28 @@ def test_belief_histogram_once_is_self_cleaning(backend):
         assert L.pomdp_belief_hist_once(env.kind, p0, p1, _lib.ptr(state), env.state_words, 5, _lib.ptr(scratch), None, None) == -1
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_step_with_histogram_epilogue(backend, name):
+    """simulate_hist (pomdp_E_step_hist: the step kernel counts the next states in its epilogue) returns exactly what
+    simulate followed by belief_histogram(next_state) returns -- same draws, same results, same counts -- for aligned
+    batches (four envs per thread), ragged ends, odd views (thread-per-env path), a single env, an empty batch, and call
+    after call on the same self-cleaning scratch.  BattleShip runs its two kernels back to back behind the same call."""
+    rs = np.random.RandomState(21)
+    for n in (70001, 4096, 5, 1, 0, 33):
+        env = make_all(backend, max(n, 1))[name]
+        state, action = random_inputs(env, name, n + 1, rs, backend)
+        for view in (slice(0, n), slice(1, n + 1)):              # the second view is not 16-byte aligned
+            s, a = state[view], action[view]
+            ref = env.simulate(s, a, step_ctr=9)
+            ref_h = env.belief_histogram(ref[0])
+            got = env.simulate_hist(s, a, step_ctr=9)
+            assert eq(got[:4], ref), (name, n, view)
+            assert torch.equal(got[4], ref_h), (name, n, view)
+            assert int(got[4].sum()) == int(ref_h.sum())
+        if hasattr(env, "_c_step_hist"):
+            assert not env._local_hist_scratch().any()
+
+
 def _fused_world_on_one_device(backend, env, state, world, calls, wait):
     """`world` ranks played on ONE device: each has its own symmetric buffer (slot 0 | slot 1 | arrivals) and scratch, all
     in one peer table.  wait=1 on CUDA: every rank's call goes to its own stream, so the kernels run concurrently and every

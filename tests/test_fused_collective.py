@@ -25,3 +25,7 @@ def test_fused_histogram_through_the_public_call_in_a_one_rank_world():
     assert out["all_variants_equal"] is True and out["bins"] == 271
     t = out["us_per_call_max_over_ranks"]
     assert set(t) == {"hist", "nccl", "fused"} and all("graph_us" in v for v in t.values()), t
+    # the step with the histogram (and the all-reduce) in its epilogue: pomdp_rock_step_hist, eager and graph-replayed
+    p = out["step_pipeline_us_max_over_ranks"]
+    assert {"step", "step_then_hist_nccl", "step_then_hist_fused", "step_hist_local", "step_hist_fused"} == set(p)
+    assert all("graph_us" in v for v in p.values()), p
