@@ -77,6 +77,10 @@ def _worker(rank, port, out_dir):
                                         and torch.equal(p_fl, fl))])
             dist.all_reduce(host_ok, op=dist.ReduceOp.MIN)
             hist = env.belief_histogram(ns, all_reduce=True)            # the only collective
+            # the same step with the histogram in its epilogue (pomdp_E_step_hist), counts summed over the ranks
+            sh = env.simulate_hist(state[lo:hi].contiguous(), action[lo:hi].contiguous(), step_ctr=4, all_reduce=True)
+            host_ok &= int(torch.equal(sh[0], ns) and torch.equal(sh[1], ob) and torch.equal(sh[4], hist))
+            dist.all_reduce(host_ok, op=dist.ReduceOp.MIN)
             gathered = [torch.empty_like(ns) for _ in range(WORLD)]
             dist.all_gather(gathered, ns)
             g_ob = [torch.empty_like(ob) for _ in range(WORLD)]
