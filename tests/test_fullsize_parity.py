@@ -240,6 +240,54 @@ def test_belief_histogram_carry_save_flavour_at_2p25(which):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which", ["rock15_2p25", "rock11_2p26", "tag_2p20", "network_2p22", "tiger_2p22"])
+def test_step_with_histogram_epilogue_at_baseline_sizes(which):
+    """pomdp_E_step_hist at the BASELINE batch sizes (the whole Rock(15,15) 2^25 batch of config 5 included, ragged by 3):
+    every output array equal to the plain step's, the counts equal to torch's own reductions over the unpacked next states.
+    Rock(11,11) runs at 2^26: a thread then counts 4 x 111 particles, so the byte counters are flushed INSIDE the loop."""
+    dev = "cuda:0"
+    g = gen_for(dev, 17)
+    if which.startswith("rock"):
+        b, k, lg = (15, 15, 25) if which == "rock15_2p25" else (11, 11, 26)
+        n = (1 << lg) + 3
+        env = gp.make("Rock-v0", board_size=b, num_rocks=k, batch_size=n, device=dev, seed=SEED)
+        st = env.pack(torch.randint(0, b, (n,), generator=g, device=dev), torch.randint(0, b, (n,), generator=g, device=dev),
+                      torch.randint(-1, 2, (n, k), generator=g, device=dev, dtype=torch.int8))
+        act = torch.randint(0, 5 + k, (n,), generator=g, device=dev, dtype=torch.int32)
+    elif which.startswith("tag"):
+        n = (1 << 20) + 3
+        env = gp.make("Tag-v0", batch_size=n, device=dev, seed=SEED)
+        st = env.pack(torch.randint(0, 29, (n,), generator=g, device=dev), torch.randint(0, 29, (n, 1), generator=g, device=dev))
+        act = torch.randint(0, 5, (n,), generator=g, device=dev, dtype=torch.int32)
+    elif which.startswith("network"):
+        n = (1 << 22) + 3
+        env = gp.make("Network-v0", batch_size=n, device=dev, seed=SEED)
+        st = torch.randint(0, 1024, (n,), generator=g, device=dev, dtype=torch.int32)
+        act = torch.randint(0, 21, (n,), generator=g, device=dev, dtype=torch.int32)
+    else:
+        n = (1 << 22) + 3
+        env = gp.make("Tiger-v0", batch_size=n, device=dev, seed=SEED)
+        st = env.pack(torch.randint(0, 2, (n,), generator=g, device=dev))
+        act = torch.randint(0, 3, (n,), generator=g, device=dev, dtype=torch.int32)
+    ref = env.simulate(st, act, step_ctr=3)
+    got = env.simulate_hist(st, act, step_ctr=3)
+    assert all(torch.equal(a, b) for a, b in zip(got[:4], ref)), which
+    ns = ref[0]
+    if which.startswith("rock"):
+        x, y, status, _ = env.unpack(ns)
+        exp = torch.cat([(status == 1).sum(0), torch.bincount((x | (y << 4)).long(), minlength=256)])
+    elif which.startswith("tag"):
+        ag, op, _, _ = env.unpack(ns)
+        exp = torch.cat([torch.bincount(ag.long(), minlength=29), torch.bincount(op[:, 0].long(), minlength=29)])
+    elif which.startswith("network"):
+        exp = torch.stack([((ns >> m) & 1).sum() for m in range(10)])
+    else:
+        exp = torch.bincount((ns & 1).long(), minlength=2)
+    assert torch.equal(got[4], exp.to(got[4].dtype)), which
+    assert torch.equal(env.simulate_hist(st, act, step_ctr=3)[4], got[4])          # the scratch was left clean
+
+
+@pytest.mark.gpu
 def test_batch_beyond_2p31_envs():
     """Maximum sizes: 2^31 + 4 Tiger instances in ONE launch (52 GB of arrays): element indices and Philox counters are
     64-bit end to end.  Windows at the start, around 2^31 and at the ragged end are checked against the C oracle."""
