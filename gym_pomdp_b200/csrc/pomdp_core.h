@@ -808,7 +808,10 @@ struct TigerDev {
 constexpr uint32_t TIGER_DONE = 0x80000000u;
 
 // tiger.py:72-88 (+ _compute_rw 164-172, _is_terminal 155-162, _sample_state 117-119, _sample_ob 140-149)
-// Draw slot 0 = state_space.sample() (tiger.py:118-119), slot 1 = np.random.uniform() (tiger.py:143).
+// ONE draw word, slot 0, serves both call sites: state_space.sample() (tiger.py:118-119, after a door was opened: the word's
+// top bit) and np.random.uniform() (tiger.py:143, compared with correct_prob).  The reference draws the uniform on every
+// non-terminal step but reads it only after LISTEN, and draws the sample only after an OPEN: a step never consumes both, so
+// sharing the word changes no distribution, joint or marginal.
 template <class D>
 POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, const D& draw,
                          uint32_t& s2, int32_t& ob, float& rw, int32_t& fl) {
@@ -825,8 +828,9 @@ POMDP_HD void tiger_step(const TigerDev& p, uint32_t s, int32_t a, const D& draw
         fl = FLAG_DONE;
         return;
     }
-    if (a < 2) st = rand_below(draw(0), 2);   // state_space.sample(), tiger.py:118-119
-    const bool flip = (uint64_t)draw(1) > p.listen_G;   // p > correct_prob, tiger.py:143-148
+    const uint32_t w = draw(0);
+    if (a < 2) st = rand_below(w, 2);         // state_space.sample(), tiger.py:118-119
+    const bool flip = (uint64_t)w > p.listen_G;         // p > correct_prob, tiger.py:143-148 (read only when a == LISTEN)
     ob = 2;
     if (a == 2) ob = (int32_t)(flip ? 1u - st : st);
     s2 = st;

@@ -209,8 +209,8 @@ struct TigerEnvP {
     static POMDP_HD void step4(const Params& p, const unsigned char*, const State s[4], const int32_t a[4],
                                                  const PhiloxKey& seed, uint64_t group, uint32_t ctr, State s2[4], int32_t ob[4],
                                                  float rw[4], int32_t fl[4]) {
-        WordDraw<2> d[4];
-        quad_words<2>(seed, group, ctr, DOMAIN_STEP, 2, d);
+        WordDraw<1> d[4];
+        quad_words<1>(seed, group, ctr, DOMAIN_STEP, 1, d);
     POMDP_UNROLL
         for (int j = 0; j < 4; ++j) tiger_step(p, s[j], a[j], d[j], s2[j], ob[j], rw[j], fl[j]);
     }

@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 13
+#define POMDP_ABI_VERSION 14
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -209,7 +209,9 @@ typedef struct PomdpTigerParams {
     double listen_prob;  /* tiger.py:141: _sample_ob's default .85 (self.correct_prob is unused there) */
 } PomdpTigerParams;
 /* State: 1 word, bit 0 = tiger door, bit 31 done.
- * TigerEnv.step tiger.py:72-88.  Slot 0 = state resample (actions 0/1), slot 1 = uniform. */
+ * TigerEnv.step tiger.py:72-88.  ONE draw word (slot 0) serves the state resample after an OPEN (its top bit) and the
+ * uniform read after a LISTEN (the reference draws the uniform on every step but reads it only then): a step never
+ * consumes both. */
 int pomdp_tiger_step(const PomdpTigerParams* params,
                      const int32_t* state, const int32_t* action,
                      int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,

@@ -374,20 +374,20 @@ def gen_tiger(E):
     R = 300
     G = int(np.floor(0.85 * 2.0 ** 32))
     st, ac, dr = [], [], []
-    w = words(6 * R, 2, stream=13)
+    w = words(6 * R, 1, stream=13)
     i = 0
     for s in range(2):
         for a in range(3):
             for j in range(R):
                 ww = w[i].copy()
                 if j < 4:
-                    ww[1] = G + (j - 1)  # around the ``p > .85`` boundary
+                    ww[0] = G + (j - 1)  # around the ``p > .85`` boundary
                 st.append(s); ac.append(a); dr.append(ww); i += 1
     dr = np.array(dr, np.uint32)
     res = {k_: [] for k_ in ("s2", "ob", "rw", "done", "prob")}
     for i in range(len(st)):
         env._set_state(st[i])
-        d.clear(); d.feed_gym([dr[i, 0]]); d.feed([dr[i, 1]])
+        d.clear(); d.feed_gym([dr[i, 0]]); d.feed([dr[i, 0]])        # ONE word serves sample() and uniform()
         ob, rw, done, info = env.step(ac[i])
         res["s2"].append(env.state); res["ob"].append(ob); res["rw"].append(rw); res["done"].append(bool(done))
         res["prob"].append([float(E.TigerEnv._compute_prob(ac[i], env.state, o)) for o in range(3)])

@@ -135,8 +135,8 @@ def gen_tiger(E, out, M, T):
         s0 = env.state
 
         def feed_step(w, a):
-            d.feed_gym([w[0]]); d.feed([w[1]])                  # tiger.py:118-119 (gym's RNG), 143
-        r, t, acts, done, s1 = run(env, d, e, T, 2, feed_step, lambda: env.state)
+            d.feed_gym([w[0]]); d.feed([w[0]])                  # tiger.py:118-119 (gym's RNG), 143: ONE word serves both
+        r, t, acts, done, s1 = run(env, d, e, T, 1, feed_step, lambda: env.state)
         for key, v in zip(res, (s0, r, t, acts, done, s1)):
             res[key].append(v)
     for key in res:

@@ -481,7 +481,8 @@ void oracle_battleship_step(int xs, int ys, int64_t N, const uint8_t* occ, uint8
 }
 
 /* ------------------------------------------------------------------- Tiger ------ */
-/* tiger.py:72-88, 117-119, 140-172.  slot 0 = state_space.sample() (a in {0,1}), slot 1 = uniform(). */
+/* tiger.py:72-88, 117-119, 140-172.  draws: uint32[N], ONE word per env: state_space.sample() after an OPEN and uniform()
+ * after a LISTEN read the same word (a step never consumes both). */
 void oracle_tiger_step(double listen_prob, int64_t N, int32_t* state, const int32_t* action, const uint32_t* draws,
                        int32_t* obs, double* reward, uint8_t* done) {
     for (int64_t i = 0; i < N; ++i) {
@@ -489,8 +490,8 @@ void oracle_tiger_step(double listen_prob, int64_t N, int32_t* state, const int3
         const int terminal = a != 2 && ((a == 0 && state[i] == 0) || (a == 1 && state[i] == 1));   /* 155-162 */
         reward[i] = a == 2 ? -1 : (!terminal ? 10 : -20);                                          /* 164-172 */
         if (terminal) { done[i] = 1; obs[i] = state[i]; continue; }                               /* 81-83 */
-        if (a == 1 || a == 0) state[i] = below(draws[2 * i], 2);                                   /* 117-119 */
-        const double p = (double)draws[2 * i + 1] / TWO32;                                         /* 143 */
+        if (a == 1 || a == 0) state[i] = below(draws[i], 2);                                       /* 117-119 */
+        const double p = (double)draws[i] / TWO32;                 /* 143: the same word; read only when a == 2 */
         int ob = 2;
         if (a == 2) {
             if (state[i] == 0) ob = p > listen_prob ? 1 : 0;
@@ -651,12 +652,11 @@ void oracle_tiger_rollout(double listen_prob, int64_t N, int32_t* state, uint64_
         int t = 0;
         uint8_t fin = 0;
         while (t < max_steps && !fin) {
-            uint32_t dr[2];
+            uint32_t dr[1];
             int32_t a = below(draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 2, 0), 3), ob;   /* tiger.py:111-112 */
             double rw;
             if (t == 0 && first_action) a = first_action[i];
             dr[0] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 0);
-            dr[1] = draw_word1(seed, goff + (uint64_t)i, ctr0 + (uint32_t)t, 0, 1);
             oracle_tiger_step(listen_prob, 1, state + i, &a, dr, &ob, &rw, &fin);
             r += rw * disc;
             disc *= gamma;

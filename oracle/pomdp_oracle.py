@@ -520,8 +520,9 @@ def battleship_compute_prob(board, action, ob):
 def tiger_step(state, action, draw, listen_prob=0.85):
     """tiger.py:72-88, 117-119, 140-172.  Returns (state, obs, reward, done).
 
-    Slot 0 = ``state_space.sample()`` (gym's RNG; only for a in {0,1}, tiger.py:118-119),
-    slot 1 = ``np.random.uniform()`` (always drawn when not terminal, tiger.py:143).
+    Slot 0 serves both ``state_space.sample()`` (gym's RNG; only for a in {0,1}, tiger.py:118-119) and
+    ``np.random.uniform()`` (always drawn when not terminal, tiger.py:143, but read only after LISTEN): a step never
+    consumes both.
     ``_sample_ob`` ignores ``self.correct_prob`` (default argument .85, tiger.py:141).
     """
     if action == 2:
@@ -535,7 +536,7 @@ def tiger_step(state, action, draw, listen_prob=0.85):
     if action in (0, 1):
         state = rand_below(draw(0), 2)
     ob = 2
-    flip = draw(1) > gt_threshold(listen_prob)
+    flip = draw(0) > gt_threshold(listen_prob)
     if action == 2:
         if state == 0:
             ob = 1 if flip else 0

@@ -142,7 +142,7 @@ def test_tiger_and_network_batch_2p20(backend):
     ns, ob, rw, fl = env.simulate(env.pack(s0), action, step_ctr=5)
     s2, done = (v.cpu().numpy() for v in env.unpack(ns))
     es, eob, erw, edone = C.tiger_step(0.85, s0.cpu().numpy(), action.cpu().numpy(),
-                                       C.fill_draws(SEED, 0, B, 5, philox.DOMAIN_STEP, 2))
+                                       C.fill_draws(SEED, 0, B, 5, philox.DOMAIN_STEP, 1))
     assert np.array_equal(s2, es) and np.array_equal(ob.cpu().numpy(), eob) and np.array_equal(done, edone)
     assert np.array_equal(rw.cpu().numpy(), erw.astype(np.float32))
     st0, ob0 = env.init_states(B, step_ctr=6)
@@ -304,7 +304,7 @@ def test_batch_beyond_2p31_envs():
     torch.cuda.synchronize()
     for lo, hi in [(0, 4096), ((1 << 31) - 4096, (1 << 31) + 4), (n - 3, n)]:
         es, eob, erw, edone = C.tiger_step(0.85, state[lo:hi].cpu().numpy(), action[lo:hi].cpu().numpy(),
-                                           C.fill_draws(SEED, lo, hi - lo, 3, philox.DOMAIN_STEP, 2))
+                                           C.fill_draws(SEED, lo, hi - lo, 3, philox.DOMAIN_STEP, 1))
         s2, done = (v.cpu().numpy() for v in env.unpack(ns[lo:hi]))
         assert np.array_equal(s2, es) and np.array_equal(ob[lo:hi].cpu().numpy(), eob) and np.array_equal(done, edone)
         assert np.array_equal(rw[lo:hi].cpu().numpy(), erw.astype(np.float32))

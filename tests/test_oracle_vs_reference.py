@@ -51,9 +51,9 @@ def test_tiger_and_network_steps_live(E):
         d.feed_gym([0]); env.reset()
         for i in range(300):
             s, a = int(rs.randint(2)), int(rs.randint(3))
-            w = philox.draw_slots(98, np.array([i]), 1, philox.DOMAIN_STEP, 2)[0]
+            w = philox.draw_slots(98, np.array([i]), 1, philox.DOMAIN_STEP, 1)[0]
             env._set_state(s)
-            d.clear(); d.feed_gym([w[0]]); d.feed([w[1]])
+            d.clear(); d.feed_gym([w[0]]); d.feed([w[0]])            # ONE word serves state_space.sample() and uniform()
             ob, rw, done, _ = env.step(a)
             assert (env.state, ob, rw, bool(done)) == O.tiger_step(s, a, lambda k: int(w[k]))
         env = E.NetworkEnv()
