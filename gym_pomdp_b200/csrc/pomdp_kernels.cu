@@ -1144,7 +1144,7 @@ __device__ __forceinline__ void hist_add_plane(uint32_t x, uint32_t (&acc)[HistS
 }
 
 // The end of every kernel that counts a belief histogram (pomdp_belief_hist_kernel, pomdp_step_hist_kernel): the CTA's
-// counts are already added to `hist`; called by ALL threads of the CTA.
+// counts are complete in shared memory (`sh`, after a __syncthreads); called by ALL threads of the CTA.
 // Fused all-reduce (pomdp_belief_hist_allreduce): `hist` is this rank's scratch -- hist[bins] a ticket counter,
 // hist[bins + 1] the number of calls made so far.  The CTA that takes the last ticket owns the rank's complete counts.
 // Call e (1, 2, ...) uses result slot (e - 1) & 1 of every rank's symmetric buffer [slot 0 | slot 1 | arrivals]:
@@ -1156,12 +1156,28 @@ __device__ __forceinline__ void hist_add_plane(uint32_t x, uint32_t (&acc)[HistS
 //   4. copy the slot -- now the GLOBAL counts -- to hist_out.
 // One kernel instead of zero-fill + histogram + a collective; the epoch lives in device memory, so the launch is
 // identical call after call and can be replayed from a CUDA graph.
-__device__ __forceinline__ void hist_finish(unsigned long long* __restrict__ hist, int bins,
+__device__ __forceinline__ void hist_finish(const uint32_t* __restrict__ sh, unsigned long long* __restrict__ hist, int bins,
                                             unsigned long long* const* __restrict__ peers, int world, int rank, int wait,
                                             unsigned long long* __restrict__ hist_out) {
-    // Self-cleaning local call (pomdp_belief_hist_once: no peers): the same ticket; the last CTA MOVES the counts from the
-    // scratch to hist_out -- no zero-fill launch before the kernel, the scratch is all zero again after it.
-    if (peers || hist_out) {
+    // Self-cleaning local call (pomdp_belief_hist_once, a local sink of pomdp_E_step_hist: no peers): ONE atomic per bin per
+    // CTA both adds the CTA's count (low 48 bits) and counts the CTA's arrival at that bin (high 16 bits); the thread whose
+    // atomic returns the last arrival owns the bin's complete count: it writes hist_out[b] and clears the scratch word.  One
+    // L2 round trip ends the kernel -- no fence, ticket and read-back in sequence (three round trips, measured ~1.4 us) --
+    // no zero-fill launch precedes it, and the scratch is all zero again after it.
+    if (!peers && hist_out) {
+        const unsigned long long arrivals = (unsigned long long)gridDim.x - 1ull;
+        for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+            const unsigned long long old = atomicAdd(&hist[b], (1ull << 48) | (unsigned long long)sh[b]);
+            if ((old >> 48) == arrivals) {
+                hist_out[b] = (old + sh[b]) & ((1ull << 48) - 1ull);
+                hist[b] = 0ull;
+            }
+        }
+        return;
+    }
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+    if (peers) {
         __shared__ bool last;
         __shared__ unsigned long long epoch_s;
         __threadfence();
@@ -1171,11 +1187,7 @@ __device__ __forceinline__ void hist_finish(unsigned long long* __restrict__ his
             epoch_s = hist[bins + 1] + 1ull;
         }
         __syncthreads();
-        if (last && !peers) {
-            __threadfence();
-            for (int b = threadIdx.x; b < bins; b += blockDim.x) hist_out[b] = atomicExch(&hist[b], 0ull);
-            if (threadIdx.x == 0) hist[bins] = 0ull;
-        } else if (last) {
+        if (last) {
             __threadfence();
             const unsigned long long epoch = epoch_s;
             const int64_t slot_off = (int64_t)((epoch - 1ull) & 1ull) * POMDP_HIST_MAX_BINS * 8;
@@ -1386,10 +1398,8 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
     }
     hist_flush<NW>(acc, sh, n_bits, lane);
     __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += blockDim.x)
-        if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
     (void)p1;
-    hist_finish(hist, bins, peers, world, rank, wait, hist_out);
+    hist_finish(sh, hist, bins, peers, world, rank, wait, hist_out);
 }
 
 
@@ -1515,9 +1525,7 @@ pomdp_step_hist_kernel(const __grid_constant__ typename Env::Params p, const voi
     hist_flush<NW>(acc, sh, n_bits, lane);
     if (!table_ready) mbar_wait(&bar, 0);      // a CTA must not exit while its bulk copy may still be in flight
     __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += blockDim.x)
-        if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
-    hist_finish(hist, bins, peers, world, rank, wait, hist_out);
+    hist_finish(sh, hist, bins, peers, world, rank, wait, hist_out);
 }
 
 // ============================================================================ host ===

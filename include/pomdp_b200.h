@@ -534,9 +534,10 @@ int pomdp_belief_hist_bins(int32_t kind, int32_t p0, int32_t p1);
 int pomdp_belief_hist(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
                       int64_t n, long long* hist, void* stream);
 /* The same counts in ONE launch, no zero-fill before it: `scratch[POMDP_HIST_MAX_BINS + 2]` int64 is the caller's, zero
- * before the first call; the CTAs accumulate into it, the CTA that takes the last ticket MOVES the counts to
- * hist_out[bins] (overwritten, not accumulated) and leaves the scratch all zero for the next call.  One scratch serves
- * one call at a time (calls on one stream; a second stream needs its own).  n = 0 writes zeros.                      */
+ * before the first call.  Every CTA adds its count to a scratch word with ONE atomic that also counts the CTA's arrival
+ * at that bin (count in the low 48 bits, arrivals above); the thread that sees the last arrival writes hist_out[bin]
+ * (overwritten, not accumulated) and clears the word, so the scratch is all zero again for the next call.  One scratch
+ * serves one call at a time (calls on one stream; a second stream needs its own).  n = 0 writes zeros.               */
 int pomdp_belief_hist_once(int32_t kind, int32_t p0, int32_t p1, const int32_t* state, int32_t words,
                            int64_t n, long long* scratch, long long* hist_out, void* stream);
 /* The same histogram FUSED with its all-reduce over NVLink / NVSwitch peer memory: ONE kernel -- no zero-fill before it,
