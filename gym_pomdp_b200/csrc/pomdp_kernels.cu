@@ -1259,9 +1259,10 @@ pomdp_belief_hist_kernel(int p0, int p1, const int32_t* __restrict__ state, int 
         constexpr int kInFlight = POMDP_HIST_INFLIGHT;
         // kPrefetch: the loads of a thread's NEXT trip are issued before the current trip is counted (software pipelining,
         // as in the step kernels).  Measured with 2, 4 and 8 loads per trip, with and without (profiles/r05e_hist_loop_variants.log):
-        // nothing moves below 2^22 states -- there the kernel is a fixed ~4 us (launch, the REDs' round trip, the ticket and
-        // the last CTA's read-back) plus 0.7 us per 2^20 one-word states, i.e. the marginal rate is already the HBM rate --
-        // and at 2^25 four plain loads per trip are the fastest (49 us; 54-64 us for the others).
+        // nothing moves below 2^22 states -- there the kernel is a fixed cost (launch and the ending: ~4 us with the fence +
+        // ticket + read-back ending of that measurement, ~2.6 us with hist_finish's one-atomic ending) plus 0.7 us per 2^20
+        // one-word states, i.e. the marginal rate is already the HBM rate -- and at 2^25 four plain loads per trip are the
+        // fastest (49 us; 54-64 us for the others).
         constexpr bool kPrefetch = POMDP_HIST_PREFETCH != 0;
         // CSA: chosen by the host only when a thread makes many trips (measured: 2^25 two-word states 57.0 -> 48.6 us, but
         // slower at 2^22 and below, where a thread makes two trips and the final planes cost more than they save)
