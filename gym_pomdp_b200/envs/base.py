@@ -244,6 +244,8 @@ class BatchedPomdpEnv(_EnvBase):
         p0, p1 = self._hist_args()
         bins = _lib.lib().pomdp_belief_hist_bins(self.kind, p0, p1)
         hist = self._empty((bins,), torch.int64) if hist_out is None else hist_out
+        if hist.dtype != torch.int64 or hist.numel() != bins or not hist.is_contiguous() or hist.device != self.device:
+            raise ValueError("hist_out must be a contiguous int64[%d] tensor on %s" % (bins, self.device))
         sink = _lib.HistSink()
         sink.hist_out = _lib.ptr(hist)
         if all_reduce == "fused":

@@ -48,3 +48,22 @@ def test_every_entry_is_the_reference_transition(which):
                         assert (10. if hit else -10. if is_tag else -1.) == rw
                         assert (nop2 == 0) == bool(hit) == bool(done)
     assert not lut[~valid].any()                      # cell ids off the board (and the pitch column) read 0: flagged BAD_STATE
+
+
+def test_one_word_serves_the_move_coin_and_the_move_choice():
+    """The draw contract of Tag's opponent move (pomdp_core.h: tag_pick_word): the coin reads the word whole (w < T), the
+    choice reads bits 15-14 (= floor(u' * len) for the word w << 16 and len in {2, 4}).  Counted exactly over all 2^32
+    words: given that the opponent moves, every pick has probability 1/len to within 2^14 / T -- the two outcomes are
+    independent far below anything 10^7 draws can resolve -- and the marginal of the coin is T / 2^32 exactly."""
+    for move_prob in (0.8, 0.5, 0.05, 1.0, 1e-4):
+        T = O.bern_threshold(move_prob)
+        full, rest = divmod(T, 1 << 16)
+        counts = [full * (1 << 14) + min(max(rest - v * (1 << 14), 0), 1 << 14) for v in range(4)]      # w < T with bits 15-14 == v
+        assert sum(counts) == T
+        for v in range(4):
+            assert abs(counts[v] / T - 0.25) <= (1 << 14) / T
+        for first in (0, 1):                                                                              # len == 2: bit 15 alone
+            assert abs((counts[2 * first] + counts[2 * first + 1]) / T - 0.5) <= (1 << 15) / T
+    # the rule the oracle states it with
+    for w in (0, 1 << 14, 3 << 14, 0xFFFFFFFF, 0x12345678):
+        assert O.rand_below(O.tag_pick_word(w), 4) == (w >> 14) & 3 and O.rand_below(O.tag_pick_word(w), 2) == (w >> 15) & 1
