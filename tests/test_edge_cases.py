@@ -255,6 +255,32 @@ def test_battleship_sink_everything(backend):
     assert (rw == -10).all() and (ob == 0).all() and not done.any()
 
 
+def test_tag_table_step_equals_the_general_functor_on_arbitrary_words(backend):
+    """Stock Tag-v0: the one-table-word step (aligned batches: four envs per thread) against the general functor (the
+    thread-per-env path an odd global offset selects) on ARBITRARY state words -- any num_opp field (0, negative in its
+    6-bit two's complement, > 1), stray bits in the unused opponent fields, cell ids off the board, done states -- and
+    actions 0..6.  Same global indices, hence the same draws; every output must agree."""
+    n = 20000
+    rs = np.random.RandomState(33)
+    words = rs.randint(0, 1 << 32, n + 1, dtype=np.uint64)
+    words[rs.rand(n + 1) < 0.5] &= 0x7FFFFFFF                     # half of them not done
+    plausible = rs.rand(n + 1) < 0.6                               # most with cells on the board
+    cells = rs.randint(0, 29, n + 1).astype(np.uint64) | (rs.randint(0, 29, n + 1).astype(np.uint64) << 5)
+    words[plausible] = (words[plausible] & ~np.uint64(1023)) | cells[plausible]
+    state = torch.from_numpy(words.astype(np.uint32).view(np.int32)).to(backend)
+    action = torch.from_numpy(rs.randint(0, 7, n + 1).astype(np.int32)).to(backend)
+    whole = gp.make("Tag-v0", batch_size=n + 1, device=backend, seed=77)
+    shifted = gp.make("Tag-v0", batch_size=n, device=backend, seed=77, global_offset=1)
+    a = whole.simulate(state, action, step_ctr=5)
+    b = shifted.simulate(state[1:], action[1:], step_ctr=5)
+    for x, y in zip(a, b):
+        assert torch.equal(x[1:], y)
+    fl = a[3].cpu().numpy()
+    assert (fl & 2).any() and (fl & 4).any() and (fl & 8).any() and (fl == 0).any() and (fl == 1).any()   # every kind of flag occurred
+    ap, bp = whole.simulate(state, action, step_ctr=5, packed=True), shifted.simulate(state[1:], action[1:], step_ctr=5, packed=True)
+    assert torch.equal(ap[0][1:], bp[0]) and torch.equal(ap[1][1:], bp[1])
+
+
 def test_belief_histogram_matches_bincount(backend):
     N = 5000
     envs = make_all(backend, N)
