@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # POMDP_B200_LIB lets kernel-tuning experiments (scripts/exp_variants.sh) point at another build of the SAME library
 LIB_PATH = os.environ.get("POMDP_B200_LIB") or os.path.join(_HERE, "csrc", "libpomdp_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 FLAG_DONE = 1
 FLAG_BAD_ACTION = 2
 FLAG_STEPPED_DONE = 4
@@ -140,6 +140,7 @@ _PROTOTYPES = {
     "pomdp_tag_rollout_preferred": (c_int32, [POINTER(TagParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64,
                                               c_uint32, c_int32, c_double, c_void_p]),
     "pomdp_stream_probe": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
+    "pomdp_stream_probe_words": (c_int32, [c_int32, _P, _P, _P, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_coord_op": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, c_int64, c_void_p]),
     "pomdp_belief_hist_bins": (c_int32, [c_int32, c_int32, c_int32]),
     "pomdp_belief_hist": (c_int32, [c_int32, c_int32, c_int32, _P, c_int32, c_int64, _P, c_void_p]),

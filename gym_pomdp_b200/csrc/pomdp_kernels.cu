@@ -294,6 +294,37 @@ pomdp_stream_probe_kernel(const int32_t* state, const int32_t* __restrict__ acti
     }
 }
 
+// The same probe for two-word states (Rock(15,15)): 32 bytes of state per group move as ONE 256-bit access each way, like
+// StateVec<uint64_t> does in the step kernel; 12 bytes read and 20 written per env.
+__global__ void __launch_bounds__(POMDP_STEP_THREADS, POMDP_STEP_MINB)
+pomdp_stream_probe2_kernel(const int32_t* state, const int32_t* __restrict__ action, int32_t* next_state,
+                           int32_t* __restrict__ obs, float* __restrict__ reward, int32_t* __restrict__ flags, int64_t n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_groups = n >> 2;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    StateVec<uint64_t> cs;
+    cs.zero();
+    int4 ca = make_int4(0, 0, 0, 0);
+    if (g < n_groups) { cs.load(state, g << 2); ca = ld_stream4(action + (g << 2)); }
+    while (g < n_groups) {
+        const int64_t gn = g + nthreads;
+        StateVec<uint64_t> ns = cs;
+        int4 na = ca;
+        if (gn < n_groups) { ns.load(state, gn << 2); na = ld_stream4(action + (gn << 2)); }
+        uint64_t s[4];
+        cs.unpack(s);
+        const uint64_t s2[4] = {s[0] ^ (uint32_t)ca.x, s[1] ^ (uint32_t)ca.y, s[2] ^ (uint32_t)ca.z, s[3] ^ (uint32_t)ca.w};
+        const int64_t i = g << 2;
+        StateVec<uint64_t>::store(next_state, i, s2);
+        st_stream4(obs + i, ca);
+        st_stream4(reward + i, make_float4(__int_as_float((int)s[0]), __int_as_float((int)s[1]), __int_as_float((int)s[2]), __int_as_float((int)s[3])));
+        st_stream4(flags + i, make_int4((int)(s[0] >> 32), (int)(s[1] >> 32), (int)(s[2] >> 32), (int)(s[3] >> 32)));
+        cs = ns; ca = na; g = gn;
+    }
+}
+
 // ---------------------------------------------------------------- reset (streams) ---
 // kVec (state 16-byte aligned, global_offset % 4 == 0): four envs per thread, one Philox call
 // per draw slot per group, vector stores when the whole group is reset.
@@ -2591,6 +2622,21 @@ int pomdp_stream_probe(const int32_t* state, const int32_t* action, int32_t* nex
     const int grid = grid_for(k, n >> 2, POMDP_STEP_THREADS, 0);
     launch_pdl(k, grid, POMDP_STEP_THREADS, 0, (cudaStream_t)stream, state, action, next_state, obs, reward, flags, n);
     return finish("pomdp_stream_probe");
+}
+
+int pomdp_stream_probe_words(int32_t state_words, const int32_t* state, const int32_t* action, int32_t* next_state, int32_t* obs,
+                             float* reward, int32_t* flags, int64_t n, void* stream) {
+    if (state_words == 1) return pomdp_stream_probe(state, action, next_state, obs, reward, flags, n, stream);
+    if (state_words != 2) return host::fail(POMDP_E_BADARG, "pomdp_stream_probe_words: state_words must be 1 or 2");
+    int rc = host::check_io(state, action, next_state, obs, reward, flags, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!aligned16(state, action, next_state, obs, reward, flags) || (n & 3))
+        return host::fail(POMDP_E_ALIGN, "pomdp_stream_probe_words: arrays must be 16-byte aligned and n a multiple of 4");
+    auto k = pomdp_stream_probe2_kernel;
+    const int grid = grid_for(k, n >> 2, POMDP_STEP_THREADS, 0);
+    launch_pdl(k, grid, POMDP_STEP_THREADS, 0, (cudaStream_t)stream, state, action, next_state, obs, reward, flags, n);
+    return finish("pomdp_stream_probe_words");
 }
 
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n,

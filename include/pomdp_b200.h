@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define POMDP_ABI_VERSION 14
+#define POMDP_ABI_VERSION 15
 
 #define POMDP_FLAG_DONE          1
 #define POMDP_FLAG_BAD_ACTION    2
@@ -516,6 +516,10 @@ int pomdp_coord_op(int32_t op, int32_t x_size, int32_t y_size,
 int pomdp_stream_probe(const int32_t* state, const int32_t* action,
                        int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
                        int64_t n, void* stream);
+/* The same for state_words = 1 or 2 (Rock(15,15): state / next_state int32[2n], moved 256 bits at a time like the step does). */
+int pomdp_stream_probe_words(int32_t state_words, const int32_t* state, const int32_t* action,
+                             int32_t* next_state, int32_t* obs, float* reward, int32_t* flags,
+                             int64_t n, void* stream);
 
 /* ----------------------------------------------------------- belief histogram ------ */
 /* Per-shard counts over a batch of packed states, accumulated into int64 hist[bins]

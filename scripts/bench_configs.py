@@ -172,15 +172,16 @@ def run_configs(dev, steps=400, only=None, kernels=("step", "step_packed", "rese
             ir = issue_roofline(label, "step", B, ms)
             if ir:
                 row["issue_roofline"] = ir
-            if W == 1 and B % 4 == 0:
-                # the compute-free probe of this traffic pattern (two read + four write int32 streams) at this batch size:
-                # what a kernel that only moves the step's bytes takes, fixed launch cost included
+            if W in (1, 2) and B % 4 == 0:
+                # the compute-free probe of this traffic pattern (two read + four write streams; two-word states as 256-bit
+                # accesses) at this batch size: what a kernel that only moves the step's bytes takes, fixed launch cost included
                 from gym_pomdp_b200 import _lib
 
                 def probe(i):
                     s, a, o = sets[i % n_sets]
-                    _lib.check(_lib.lib().pomdp_stream_probe(s.data_ptr(), a.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
-                                                             o[3].data_ptr(), B, torch.cuda.current_stream(dev).cuda_stream), "pomdp_stream_probe")
+                    _lib.check(_lib.lib().pomdp_stream_probe_words(W, s.data_ptr(), a.data_ptr(), o[0].data_ptr(), o[1].data_ptr(),
+                                                                   o[2].data_ptr(), o[3].data_ptr(), B,
+                                                                   torch.cuda.current_stream(dev).cuda_stream), "pomdp_stream_probe_words")
                 try:
                     pms = time_graph(probe, K, dev)
                     row["pattern_roof_us"] = pms * 1e3

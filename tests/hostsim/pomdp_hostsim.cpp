@@ -847,6 +847,18 @@ int pomdp_stream_probe(const int32_t* state, const int32_t* action, int32_t* nex
     for (int64_t i = 0; i < n; ++i) { next[i] = state[i] ^ action[i]; obs[i] = action[i]; memcpy(rw + i, state + i, 4); fl[i] = next[i]; }
     return 0;
 }
+int pomdp_stream_probe_words(int32_t state_words, const int32_t* state, const int32_t* action, int32_t* next, int32_t* obs, float* rw,
+                             int32_t* fl, int64_t n, void*) {
+    if (state_words == 1) return pomdp_stream_probe(state, action, next, obs, rw, fl, n, nullptr);
+    if (state_words != 2) return host::fail(POMDP_E_BADARG, "pomdp_stream_probe_words: state_words must be 1 or 2");
+    int rc = host::check_io(state, action, next, obs, rw, fl, n);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        next[2 * i] = state[2 * i] ^ action[i]; next[2 * i + 1] = state[2 * i + 1];
+        obs[i] = action[i]; memcpy(rw + i, state + 2 * i, 4); fl[i] = state[2 * i + 1];
+    }
+    return 0;
+}
 int pomdp_coord_op(int32_t op, int32_t xs, int32_t ys, const int32_t* a, const int32_t* b, int32_t* out, int64_t n, void*) {
     const int rc = host::check_coord_op(op, xs, a, b, out, n);
     if (rc) return rc;
