@@ -489,7 +489,8 @@ POMDP_HD void tag_rollout_preferred1(const TagDev& p, const unsigned char* tbl, 
         const int32_t a = (t == 0 && has_first) ? first_action
                                                 : tag_policy_preferred(T, s, last_ob, last_action, draw_word(seed, env, ctr, DOMAIN_POLICY, 0));
         uint32_t s2; int32_t ob, fl; float rw;
-        Env::step1(p, tbl, s, a, seed, env, ctr, s2, ob, rw, fl);
+        if (NOPP == 1) tag_step_1opp(p, T, s, a, draw_word(seed, env, ctr, DOMAIN_STEP, 0), s2, ob, rw, fl);   // one table word (TagTables.lut)
+        else Env::step1(p, tbl, s, a, seed, env, ctr, s2, ob, rw, fl);
         s = s2; last_ob = ob; last_action = a;
         acc.add((double)rw, gamma, fl);
     }

@@ -707,7 +707,7 @@ pomdp_tag_rollout_preferred_kernel(const __grid_constant__ TagDev p, const void*
     typedef TagEnvT<NOPP> Env;
     extern __shared__ __align__(128) unsigned char smem_table[];
     __shared__ alignas(8) uint64_t bar;
-    stage_table_sync<Env>(smem_table, g_table, TAG_TABLES_BASE_BYTES, &bar);
+    stage_table_sync<Env>(smem_table, g_table, NOPP == 1 ? (uint32_t)sizeof(TagTables) : TAG_TABLES_BASE_BYTES, &bar);   // one opponent: + the LUT
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
         uint32_t s = (uint32_t)state[i];
@@ -2594,7 +2594,7 @@ int pomdp_tag_rollout_preferred(const PomdpTagParams* q, const void* d_table, co
         return host::fail(POMDP_E_ALIGN, "%s: array pointers must be 4-byte aligned", what);
     if (n == 0) return 0;
     if (!d_table || ((uintptr_t)d_table & 15)) return host::fail(POMDP_E_BADARG, "%s: d_table must be a 16-byte aligned device pointer", what);
-    const size_t smem = TAG_TABLES_BASE_BYTES;
+    const size_t smem = d.n_opp == 1 ? sizeof(TagTables) : (size_t)TAG_TABLES_BASE_BYTES;     // one opponent: the step reads the LUT
     if (d.n_opp == 1) {
         auto k = pomdp_tag_rollout_preferred_kernel<1>;
         k<<<grid_for(k, n, POMDP_THREADS, smem), POMDP_THREADS, smem, (cudaStream_t)stream>>>(
