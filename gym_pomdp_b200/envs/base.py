@@ -241,19 +241,29 @@ class BatchedPomdpEnv(_EnvBase):
         if not hasattr(self, "_c_step_hist"):
             self.simulate(state, action, out=out, step_ctr=step_ctr)
             return next_state, obs, reward, flags, self.belief_histogram(next_state, all_reduce=all_reduce)
-        p0, p1 = self._hist_args()
-        bins = _lib.lib().pomdp_belief_hist_bins(self.kind, p0, p1)
-        hist = self._empty((bins,), torch.int64) if hist_out is None else hist_out
-        if hist.dtype != torch.int64 or hist.numel() != bins or not hist.is_contiguous() or hist.device != self.device:
-            raise ValueError("hist_out must be a contiguous int64[%d] tensor on %s" % (bins, self.device))
-        sink = _lib.HistSink()
-        sink.hist_out = _lib.ptr(hist)
-        if all_reduce == "fused":
-            st = self._fused_hist_state()
-            sink.scratch, sink.d_peer_bufs = _lib.ptr(st["scratch"]), st["hdl"].buffer_ptrs_dev
-            sink.world, sink.rank, sink.wait = st["hdl"].world_size, st["hdl"].rank, 1
+        bins = self._hist_n_bins()
+        if hist_out is None:
+            hist = self._empty((bins,), torch.int64)
         else:
-            sink.scratch = _lib.ptr(self._local_hist_scratch())
+            hist = hist_out
+            if hist.dtype != torch.int64 or hist.numel() != bins or not hist.is_contiguous() or hist.device != self.device:
+                raise ValueError("hist_out must be a contiguous int64[%d] tensor on %s" % (bins, self.device))
+        # the sink structs are built once (per stream for the local one): an eager caller of a 2^20-env step is host-bound
+        if all_reduce == "fused":
+            sink = self.__dict__.get("_sink_fused")
+            if sink is None:
+                st = self._fused_hist_state()
+                sink = self._sink_fused = _lib.HistSink()
+                sink.scratch, sink.d_peer_bufs = _lib.ptr(st["scratch"]), st["hdl"].buffer_ptrs_dev
+                sink.world, sink.rank, sink.wait = st["hdl"].world_size, st["hdl"].rank, 1
+        else:
+            stream = self._stream()
+            sinks = self.__dict__.setdefault("_sinks_local", {})
+            sink = sinks.get(stream)
+            if sink is None:
+                sink = sinks[stream] = _lib.HistSink()
+                sink.scratch = _lib.ptr(self._local_hist_scratch())
+        sink.hist_out = hist.data_ptr()
         ctr = self._next_ctr() if step_ctr is None else int(step_ctr)
         with self._guard():
             self._c_step_hist(state, action, next_state, obs, reward, flags, n, ctr, sink)
@@ -262,6 +272,13 @@ class BatchedPomdpEnv(_EnvBase):
             if dist.is_available() and dist.is_initialized():
                 dist.all_reduce(hist, op=dist.ReduceOp.SUM)
         return next_state, obs, reward, flags, hist
+
+    def _hist_n_bins(self):
+        bins = self.__dict__.get("_hist_bins_cached")
+        if bins is None:
+            p0, p1 = self._hist_args()
+            bins = self._hist_bins_cached = _lib.lib().pomdp_belief_hist_bins(self.kind, p0, p1)
+        return bins
 
     def _local_hist_scratch(self):
         """The self-cleaning scratch of the one-launch histogram calls, one per stream (calls on one stream are ordered)."""
@@ -611,9 +628,9 @@ class BatchedPomdpEnv(_EnvBase):
             return self._belief_histogram_fused(state)
         p0, p1 = self._hist_args()
         L = _lib.lib()
-        bins = L.pomdp_belief_hist_bins(self.kind, p0, p1)
-        # ONE launch (pomdp_belief_hist_once): the kernel's last CTA moves the counts from a self-cleaning scratch to the
-        # result, so no zero-fill kernel runs before it.  One scratch per stream: calls on one stream are ordered.
+        bins = self._hist_n_bins()
+        # ONE launch (pomdp_belief_hist_once): the last arrival at every bin moves its count from a self-cleaning scratch to
+        # the result, so no zero-fill kernel runs before it.  One scratch per stream: calls on one stream are ordered.
         scratch = self._local_hist_scratch()
         hist = torch.empty(bins, dtype=torch.int64, device=self.device)
         n = state.shape[0]
